@@ -1,0 +1,557 @@
+"""CPU oracle for the COMBAT alternated generator/surrogate training step.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``combat_b200/`` may import this
+module; only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
+``cpu_baseline`` / ``--impl reference`` legs use it, and only as the checker or
+the CPU baseline -- never as the product path.
+
+What it is: a functional (state-dict driven) restatement, on torch-CPU fp32, of
+the algorithm the reference runs for the hot path.  The reference is pure
+Python/PyTorch, so the arithmetic primitives (conv2d, batch_norm,
+instance_norm, fft, autograd) are the same torch CPU ops the reference itself
+dispatches; what is *restated* here is the reference's own control flow, layer
+wiring, RNG consumption order, losses and optimiser.  It contains no reference
+source and does not import ``/root/reference``.
+
+Parity pins (see tests/golden/ and tests/test_oracle_golden.py): the fixtures in
+``tests/golden/*.npz`` were produced by running the UNMODIFIED reference
+(`/root/reference`, through `oracle/ref_loader.py`) in the build container with
+`tests/golden/make_golden.py`; this oracle reproduces them (integer selections
+bit-exact, floats to <=1e-6 relative -- they are bit-equal on the same torch
+build and thread count).
+
+Every function cites the reference file:line it follows (paths relative to the
+reference root).
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+# --------------------------------------------------------------------------
+# DCT  (utils/dct.py)
+# --------------------------------------------------------------------------
+
+
+def dct(x: torch.Tensor, norm: str = "ortho") -> torch.Tensor:
+    """DCT-II along the last dim via one length-N complex FFT (utils/dct.py:13-42)."""
+    shape = x.shape
+    N = shape[-1]
+    x = x.contiguous().view(-1, N)
+    v = torch.cat([x[:, ::2], x[:, 1::2].flip([1])], dim=1)  # :26
+    Vc = torch.view_as_real(torch.fft.fft(v, dim=1))  # :6,28
+    # :30 -- note: for uint8 input the arange is uint8 and the negation wraps
+    k = -torch.arange(N, dtype=x.dtype, device=x.device)[None, :] * np.pi / (2 * N)
+    W_r, W_i = torch.cos(k), torch.sin(k)
+    V = Vc[:, :, 0] * W_r - Vc[:, :, 1] * W_i  # :34
+    if norm == "ortho":  # :36-38
+        V[:, 0] /= np.sqrt(N) * 2
+        V[:, 1:] /= np.sqrt(N / 2) * 2
+    return 2 * V.view(*shape)  # :40
+
+
+def idct(X: torch.Tensor, norm: str = "ortho") -> torch.Tensor:
+    """DCT-III (inverse of `dct`) along the last dim via irfft (utils/dct.py:45-82)."""
+    shape = X.shape
+    N = shape[-1]
+    X_v = X.contiguous().view(-1, N) / 2  # :59
+    if norm == "ortho":  # :61-63
+        X_v[:, 0] *= np.sqrt(N) * 2
+        X_v[:, 1:] *= np.sqrt(N / 2) * 2
+    k = torch.arange(N, dtype=X.dtype, device=X.device)[None, :] * np.pi / (2 * N)
+    W_r, W_i = torch.cos(k), torch.sin(k)
+    V_t_r = X_v
+    V_t_i = torch.cat([X_v[:, :1] * 0, -X_v.flip([1])[:, :-1]], dim=1)  # :70
+    V_r = V_t_r * W_r - V_t_i * W_i
+    V_i = V_t_r * W_i + V_t_i * W_r
+    V = torch.cat([V_r.unsqueeze(2), V_i.unsqueeze(2)], dim=2)
+    v = torch.fft.irfft(torch.view_as_complex(V), n=N, dim=1)  # :10,77
+    x = v.new_zeros(v.shape)
+    x[:, ::2] += v[:, : N - (N // 2)]  # :79
+    x[:, 1::2] += v.flip([1])[:, : N // 2]  # :80
+    return x.view(*shape)
+
+
+def dct_2d(x: torch.Tensor, norm: str = "ortho") -> torch.Tensor:
+    """utils/dct.py:85-96."""
+    X1 = dct(x, norm=norm)
+    X2 = dct(X1.transpose(-1, -2), norm=norm)
+    return X2.transpose(-1, -2)
+
+
+def idct_2d(X: torch.Tensor, norm: str = "ortho") -> torch.Tensor:
+    """utils/dct.py:99-111."""
+    x1 = idct(X, norm=norm)
+    x2 = idct(x1.transpose(-1, -2), norm=norm)
+    return x2.transpose(-1, -2)
+
+
+def dct_matrix(N: int) -> np.ndarray:
+    """Exact float64 orthonormal DCT-II matrix D (rows = frequencies): the closed
+    form the FFT route above evaluates; scipy.fft.dctn(norm='ortho') == D X D^T."""
+    n = np.arange(N, dtype=np.float64)
+    k = n[:, None]
+    D = np.sqrt(2.0 / N) * np.cos(np.pi * (2 * n[None, :] + 1) * k / (2 * N))
+    D[0, :] *= 1.0 / np.sqrt(2.0)
+    return D
+
+
+def dct_2d_exact(x: np.ndarray) -> np.ndarray:
+    D = dct_matrix(x.shape[-1])
+    return D @ x.astype(np.float64) @ D.T
+
+
+def idct_2d_exact(X: np.ndarray) -> np.ndarray:
+    D = dct_matrix(X.shape[-1])
+    return D.T @ X.astype(np.float64) @ D
+
+
+def low_freq(x: torch.Tensor, image_size: int, ratio: float) -> torch.Tensor:
+    """train_generator.py:47-55."""
+    k = int(image_size * ratio)
+    mask = torch.zeros_like(x)
+    mask[:, :, :k, :k] = 1
+    x_dct = dct_2d((x + 1) / 2 * 255)
+    x_dct = x_dct * mask
+    return (idct_2d(x_dct) / 255 * 2) - 1
+
+
+def low_freq_exact(x: np.ndarray, image_size: int, ratio: float) -> np.ndarray:
+    """P X P^T with P = D^T diag(1_k) D -- the closed form of `low_freq`
+    (the affine (x+1)/2*255 ... /255*2-1 cancels because the DC term is kept)."""
+    k = int(image_size * ratio)
+    D = dct_matrix(x.shape[-1])
+    P = D[:k].T @ D[:k]
+    return P @ x.astype(np.float64) @ P.T
+
+
+# --------------------------------------------------------------------------
+# poison selection / targets (train_generator.py:70-77,181-188)
+# --------------------------------------------------------------------------
+
+
+def create_targets_bd(targets: torch.Tensor, attack_mode: str, target_label: int, num_classes: int) -> torch.Tensor:
+    """train_generator.py:70-77."""
+    if attack_mode == "all2one":
+        return torch.ones_like(targets) * target_label
+    if attack_mode == "all2all":
+        return torch.tensor([(int(l) + 1) % num_classes for l in targets])
+    raise Exception("{} attack mode is not implemented".format(attack_mode))
+
+
+def select_poison(targets: torch.Tensor, bd_targets: torch.Tensor, pc: float, rng=np.random):
+    """train_generator.py:181-183.  Returns (trg_ind, ntrg_ind, num_bd).
+    Consumes exactly one ``rng.rand(n_trg)`` from the numpy global RandomState."""
+    trg_ind = (targets == bd_targets).nonzero()[:, 0]
+    ntrg_ind = (targets != bd_targets).nonzero()[:, 0]
+    num_bd = int(np.sum(rng.rand(trg_ind.shape[0]) < pc))
+    return trg_ind, ntrg_ind, num_bd
+
+
+# --------------------------------------------------------------------------
+# Gaussian blur (torchvision GaussianBlur(3,(0.1,1.0)), train_generator.py:165,194,226)
+# --------------------------------------------------------------------------
+
+
+def draw_sigma(lo: float = 0.1, hi: float = 1.0) -> float:
+    """One torch CPU-generator uniform per call (torchvision GaussianBlur.get_params)."""
+    return torch.empty(1).uniform_(lo, hi).item()
+
+
+def gaussian_kernel1d(sigma: float, ksize: int = 3) -> torch.Tensor:
+    half = (ksize - 1) * 0.5
+    x = torch.linspace(-half, half, steps=ksize, dtype=torch.float32)
+    pdf = torch.exp(-0.5 * (x / sigma).pow(2))
+    return pdf / pdf.sum()
+
+
+def gaussian_blur(img: torch.Tensor, sigma: float, ksize: int = 3) -> torch.Tensor:
+    """Separable Gaussian as a depthwise conv with reflect padding."""
+    k1 = gaussian_kernel1d(sigma, ksize).to(img.dtype)
+    k2 = torch.mm(k1[:, None], k1[None, :])
+    C = img.shape[-3]
+    w = k2.expand(C, 1, ksize, ksize)
+    pad = ksize // 2
+    x = F.pad(img, [pad, pad, pad, pad], mode="reflect")
+    return F.conv2d(x, w, groups=C)
+
+
+# --------------------------------------------------------------------------
+# networks -- functional forwards over reference state-dict names
+# --------------------------------------------------------------------------
+
+
+def unet_forward(p: dict, x: torch.Tensor, y: torch.Tensor | None = None, num_classes: int | None = None):
+    """UnetGenerator.forward (networks/models.py:318-341) and, when `y` is given,
+    CUnetGeneratorv1.forward (networks/models.py:523-555).
+
+    `self.act` is LeakyReLU(0.2, inplace=True) (:273): every `self.act(t)` mutates `t`,
+    so the skip tensors f0/f1/f2 that are added back (:331,334,337) are the ACTIVATED ones.
+    InstanceNorm2d defaults: affine=False, eps=1e-5, no running stats.  Upsample is
+    bilinear, align_corners=False (:274)."""
+
+    def act(t):
+        return F.leaky_relu(t, 0.2)
+
+    def conv(name, t, stride=1):
+        return F.conv2d(t, p[name + ".weight"], p[name + ".bias"], stride=stride, padding=1)
+
+    def inorm(t):
+        return F.instance_norm(t, eps=1e-5)
+
+    def up(t):
+        return F.interpolate(t, scale_factor=(2, 2), mode="bilinear")
+
+    f0 = conv("conv0_0", x, 2)
+    if y is not None:  # models.py:525-530
+        y_emb = F.one_hot(y, num_classes=num_classes).float()[:, :, None, None].expand(-1, -1, f0.shape[2], f0.shape[3])
+        f0 = torch.cat((f0, y_emb), 1)
+    f0 = act(inorm(conv("conv0_1", act(f0))))  # f0 after the in-place act at :322
+    f1 = act(inorm(conv("conv1_0", f0, 2)))
+    f1 = act(inorm(conv("conv1_1", f1)))  # activated by :324
+    f2 = act(inorm(conv("conv2_0", f1, 2)))
+    f2 = act(inorm(conv("conv2_1", f2)))  # activated by :326
+    f3 = act(inorm(conv("conv3_0", f2, 2)))
+    f3 = inorm(conv("conv3_1", f3))
+    u3 = act(inorm(conv("upconv3_1", act(up(f3)))))
+    u3 = inorm(conv("upconv3_0", u3)) + f2
+    u2 = act(inorm(conv("upconv2_1", act(up(u3)))))
+    u2 = inorm(conv("upconv2_0", u2)) + f1
+    u1 = act(inorm(conv("upconv1_1", act(up(u2)))))
+    u1 = inorm(conv("upconv1_0", u1)) + f0
+    u0 = act(inorm(conv("upconv0_1", act(up(u1)))))
+    return torch.tanh(conv("upconv0_0", u0))
+
+
+def _bn(p, b, name, x, training, momentum=0.1, eps=1e-5):
+    """nn.BatchNorm2d: batch stats + running update (train) or running stats (eval)."""
+    rm, rv = b[name + ".running_mean"], b[name + ".running_var"]
+    out = F.batch_norm(x, rm, rv, p[name + ".weight"], p[name + ".bias"], training, momentum, eps)
+    if training and (name + ".num_batches_tracked") in b:
+        b[name + ".num_batches_tracked"] += 1
+    return out
+
+
+def preact_resnet18_forward(p: dict, b: dict, x: torch.Tensor, training: bool):
+    """PreActResNet18 (classifier_models/preact_resnet.py:13-40,72-110).
+    `p` = parameters, `b` = buffers (running stats; updated in place when training)."""
+    out = F.conv2d(x, p["conv1.weight"], None, 1, 1)  # :77,93
+    in_planes = 64
+    for li, (planes, stride0) in enumerate([(64, 1), (128, 2), (256, 2), (512, 2)], start=1):
+        for bi, stride in enumerate([stride0, 1]):
+            pre = "layer%d.%d." % (li, bi)
+            o = F.relu(_bn(p, b, pre + "bn1", out, training))  # :32
+            if stride != 1 or in_planes != planes:  # :26-29,33
+                sc = F.conv2d(o, p[pre + "shortcut.0.weight"], None, stride, 0)
+            else:
+                sc = out
+            o = F.conv2d(o, p[pre + "conv1.weight"], None, stride, 1)  # :34
+            o = F.conv2d(F.relu(_bn(p, b, pre + "bn2", o, training)), p[pre + "conv2.weight"], None, 1, 1)  # :35
+            out = o + sc  # :39
+            in_planes = planes
+    out = F.avg_pool2d(out, 4)  # :99
+    out = out.view(out.size(0), -1)
+    return F.linear(out, p["linear.weight"], p["linear.bias"])  # :101
+
+
+def resnet18_forward(p: dict, b: dict, x: torch.Tensor, training: bool):
+    """ResNet18 (classifier_models/resnet.py:15-37,68-106), post-activation BasicBlocks."""
+    out = F.relu(_bn(p, b, "bn1", F.conv2d(x, p["conv1.weight"], None, 1, 1), training))  # :90
+    in_planes = 64
+    for li, (planes, stride0) in enumerate([(64, 1), (128, 2), (256, 2), (512, 2)], start=1):
+        for bi, stride in enumerate([stride0, 1]):
+            pre = "layer%d.%d." % (li, bi)
+            o = F.relu(_bn(p, b, pre + "bn1", F.conv2d(out, p[pre + "conv1.weight"], None, stride, 1), training))
+            o = _bn(p, b, pre + "bn2", F.conv2d(o, p[pre + "conv2.weight"], None, 1, 1), training)
+            if stride != 1 or in_planes != planes:  # :25-29
+                sc = _bn(p, b, pre + "shortcut.1", F.conv2d(out, p[pre + "shortcut.0.weight"], None, stride, 0), training)
+            else:
+                sc = out
+            out = F.relu(o + sc)  # :34-35
+            in_planes = planes
+    out = F.avg_pool2d(out, 4)  # :95
+    out = out.view(out.size(0), -1)
+    return F.linear(out, p["linear.weight"], p["linear.bias"])
+
+
+def frequency_model_forward(p: dict, b: dict, x: torch.Tensor):
+    """FrequencyModel in eval mode (defenses/frequency_based/model.py:8-52):
+    conv -> ELU -> BN (x6), maxpool after 2/4/6, dropout = identity, flatten, linear."""
+    for i in range(1, 7):
+        x = F.conv2d(x, p["conv%d.weight" % i], p["conv%d.bias" % i], 1, 1)
+        x = F.elu(x)
+        x = _bn(p, b, "bn%d" % i, x, False)
+        if i % 2 == 0:
+            x = F.max_pool2d(x, 2)
+    x = x.flatten(1)
+    return F.linear(x, p["linear6.weight"], p["linear6.bias"])
+
+
+CLASSIFIERS = {"preact_resnet18": preact_resnet18_forward, "resnet18": resnet18_forward}
+
+
+def split_state(sd: dict):
+    """Split a state_dict into (parameters, buffers) by the reference's naming."""
+    p, b = {}, {}
+    for k, v in sd.items():
+        if k.endswith("running_mean") or k.endswith("running_var") or k.endswith("num_batches_tracked"):
+            b[k] = v
+        else:
+            p[k] = v
+    return p, b
+
+
+# --------------------------------------------------------------------------
+# SGD (torch.optim.SGD(momentum=.9, weight_decay=5e-4, nesterov=True), train_generator.py:123-126)
+# --------------------------------------------------------------------------
+
+
+def sgd_nesterov_step(params: dict, grads: dict, bufs: dict, lr: float, momentum=0.9, wd=5e-4):
+    """g <- g + wd*p; buf <- g (first step) or mu*buf + g; p <- p - lr*(g + mu*buf).
+    Parameters with grad None are skipped (torch semantics)."""
+    for k, pt in params.items():
+        g = grads.get(k)
+        if g is None:
+            continue
+        g = g + wd * pt
+        if k not in bufs:
+            bufs[k] = g.clone()
+        else:
+            bufs[k].mul_(momentum).add_(g)
+        g = g + momentum * bufs[k]
+        pt.add_(g, alpha=-lr)
+
+
+# --------------------------------------------------------------------------
+# The alternated step (train_generator.py:170-255), --post_transform_option no_use
+# --------------------------------------------------------------------------
+
+
+def default_opt(**kw):
+    """The hot-path flags of config.py:4-86 with their defaults."""
+    o = SimpleNamespace(
+        input_height=32, input_width=32, input_channel=3, num_classes=10, attack_mode="all2one",
+        noise_rate=0.08, target_label=0, pc=0.5, ratio=0.65, kernel_size=3, sigma=(0.1, 1.0),
+        L2_weight=0.02, clean_model_weight=0.8, lr_C=1e-2, lr_G=1e-2, classifier="preact_resnet18",
+    )
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+def make_bd(netG_p, x, opt, sigma, y=None):
+    """noise = low_freq(netG(x)); x_bd = blur(clamp(x + noise*noise_rate, -1, 1))
+    (train_generator.py:189-194 / :223-226)."""
+    raw = unet_forward(netG_p, x, y, opt.num_classes if y is not None else None)
+    noise = low_freq(raw, opt.input_height, opt.ratio)
+    x_bd = torch.clamp(x + noise * opt.noise_rate, -1, 1)
+    return gaussian_blur(x_bd, sigma, opt.kernel_size), noise, raw
+
+
+def alternated_step(state: dict, x: torch.Tensor, y: torch.Tensor, opt, with_metrics: bool = True) -> dict:
+    """One iteration of train() (train_generator.py:170-255) with identity PostTensorTransform.
+
+    `state` holds: netC_p/netC_b, clean_p/clean_b, netG_p (dicts of tensors, updated IN PLACE),
+    netF_p/netF_b (optional), momC/momG (momentum buffer dicts, {} before the first step).
+    RNG order: numpy rand(n_trg) -> torch uniform (if num_bd>0) -> torch uniform.
+    Returns a dict of everything observable (indices, losses, logits, metric counts)."""
+    fwdC = CLASSIFIERS[opt.classifier]
+    netC_p, netC_b, netG_p = state["netC_p"], state["netC_b"], state["netG_p"]
+    clean_p, clean_b = state["clean_p"], state["clean_b"]
+    out = {}
+    bd_targets = create_targets_bd(y, opt.attack_mode, opt.target_label, opt.num_classes)
+
+    # ---------------- C-step (:176-212) ----------------
+    trg_ind, ntrg_ind, num_bd = select_poison(y, bd_targets, opt.pc)
+    out["trg_ind"], out["ntrg_ind"], out["num_bd"] = trg_ind.clone(), ntrg_ind.clone(), num_bd
+    x_sel = x[trg_ind[:num_bd]]
+    for t in netC_p.values():
+        t.requires_grad_(True)
+        t.grad = None
+    with torch.no_grad():  # G grads from this backward are discarded at :220
+        if num_bd > 0:
+            sigma_c = draw_sigma(*opt.sigma)
+            x_bd_c, _, _ = make_bd(netG_p, x_sel, opt, sigma_c)
+        else:
+            sigma_c = None
+            x_bd_c = x_sel
+    out["sigma_c"] = sigma_c
+    total_x = torch.cat([x_bd_c, x[trg_ind[num_bd:]], x[ntrg_ind]], dim=0)  # :195
+    total_y = torch.cat([bd_targets[trg_ind[:num_bd]], y[trg_ind[num_bd:]], y[ntrg_ind]], dim=0)  # :197-204
+    logits_c = fwdC(netC_p, netC_b, total_x, True)  # netC.train()
+    loss_c = F.cross_entropy(logits_c, total_y)
+    loss_c.backward()
+    out["total_x"], out["total_y"] = total_x.detach(), total_y
+    out["logits_c"], out["loss_c"] = logits_c.detach().clone(), float(loss_c)
+    gradsC = {k: v.grad for k, v in netC_p.items()}
+    out["gradsC"] = {k: g.clone() for k, g in gradsC.items()}
+    with torch.no_grad():
+        for t in netC_p.values():
+            t.requires_grad_(False)
+        sgd_nesterov_step(netC_p, gradsC, state["momC"], opt.lr_C)
+        if with_metrics:
+            out["clean_preds"] = fwdC(clean_p, clean_b, x, False)  # :214
+
+    # ---------------- G-step (:217-255) ----------------
+    for t in netG_p.values():
+        t.requires_grad_(True)
+        t.grad = None
+    sigma_g = draw_sigma(*opt.sigma)
+    out["sigma_g"] = sigma_g
+    x_bd, noise, noise_raw = make_bd(netG_p, x, opt, sigma_g)
+    with torch.no_grad():
+        if with_metrics:
+            out["pred_clean"] = fwdC(netC_p, netC_b, x, False)  # :227
+    pred_bd = fwdC(netC_p, netC_b, x_bd, False)  # :228 netC.eval(), weights AFTER the C update
+    loss_ce = F.cross_entropy(pred_bd, bd_targets)  # :231
+    loss_l2 = F.mse_loss(x_bd, x)  # :234
+    clean_model_preds = fwdC(clean_p, clean_b, x_bd, False)  # :250
+    clean_model_loss = F.cross_entropy(clean_model_preds, y)  # :251
+    loss = loss_ce + opt.L2_weight * loss_l2 + opt.clean_model_weight * clean_model_loss  # :253
+    loss.backward()
+    gradsG = {k: v.grad for k, v in netG_p.items()}
+    out["gradsG"] = {k: g.clone() for k, g in gradsG.items()}
+    with torch.no_grad():
+        for t in netG_p.values():
+            t.requires_grad_(False)
+        sgd_nesterov_step(netG_p, gradsG, state["momG"], opt.lr_G)
+        if with_metrics and state.get("netF_p") is not None:
+            inputs_F = dct_2d(((x_bd.detach() + 1) / 2 * 255).byte())  # :245 (uint8 -> float32)
+            out["inputs_F"] = inputs_F
+            out["pred_F"] = frequency_model_forward(state["netF_p"], state["netF_b"], inputs_F)  # :247
+    out.update(
+        x_bd=x_bd.detach(), noise=noise.detach(), noise_raw=noise_raw.detach(), pred_bd=pred_bd.detach(), clean_model_preds=clean_model_preds.detach(),
+        loss_ce=float(loss_ce), loss_l2=float(loss_l2), clean_model_loss=float(clean_model_loss), loss_g=float(loss),
+        bd_targets=bd_targets,
+    )
+    if with_metrics:  # :262-267
+        am = lambda t: torch.argmax(t, dim=1)
+        out["n_clean_correct"] = int((am(out["pred_clean"]) == y).sum())
+        out["n_bd_correct"] = int((am(out["pred_bd"]) == bd_targets).sum())
+        out["n_clean_model_correct"] = int((am(out["clean_preds"]) == y).sum())
+        out["n_clean_model_bd_ba"] = int((am(out["clean_model_preds"]) == y).sum())
+        out["n_clean_model_bd_asr"] = int((am(out["clean_model_preds"]) == bd_targets).sum())
+        if "pred_F" in out:
+            out["n_F_correct"] = int((am(out["pred_F"]) == 1).sum())
+    return out
+
+
+# --------------------------------------------------------------------------
+# deterministic random-init state (shapes of the reference modules), no reference import
+# --------------------------------------------------------------------------
+
+
+def _uniform(shape, bound, gen):
+    return torch.empty(shape).uniform_(-bound, bound, generator=gen)
+
+
+def _kaiming_bound(fan_in):
+    """torch.nn.init.kaiming_uniform_(w, a=sqrt(5)) bound, evaluated the way torch does so that the
+    draw is bit-identical to constructing nn.Conv2d / nn.Linear under the same seed."""
+    gain = math.sqrt(2.0 / (1 + math.sqrt(5) ** 2))
+    std = gain / math.sqrt(fan_in)
+    return math.sqrt(3.0) * std
+
+
+def _conv_init(cout, cin, k, bias, gen):
+    """nn.Conv2d default init (weight: kaiming_uniform a=sqrt(5); bias: U(+-1/sqrt(fan_in)))."""
+    fan_in = cin * k * k
+    w = _uniform((cout, cin, k, k), _kaiming_bound(fan_in), gen)
+    bb = _uniform((cout,), 1 / math.sqrt(fan_in), gen) if bias else None
+    return w, bb
+
+
+def _linear_init(cout, cin, gen):
+    w = _uniform((cout, cin), _kaiming_bound(cin), gen)
+    bb = _uniform((cout,), 1 / math.sqrt(cin), gen)
+    return w, bb
+
+
+def init_unet_state(gen, in_ch=3, nf=64, num_classes=0):
+    """Parameter shapes of UnetGenerator / CUnetGeneratorv1 (networks/models.py:268-316,472-521)."""
+    spec = [("conv0_0", in_ch, nf), ("conv0_1", nf + num_classes, nf), ("conv1_0", nf, nf * 2), ("conv1_1", nf * 2, nf * 2),
+            ("conv2_0", nf * 2, nf * 4), ("conv2_1", nf * 4, nf * 4), ("conv3_0", nf * 4, nf * 8), ("conv3_1", nf * 8, nf * 8),
+            ("upconv3_1", nf * 8, nf * 8), ("upconv3_0", nf * 8, nf * 4), ("upconv2_1", nf * 4, nf * 4),
+            ("upconv2_0", nf * 4, nf * 2), ("upconv1_1", nf * 2, nf * 2), ("upconv1_0", nf * 2, nf),
+            ("upconv0_1", nf, nf), ("upconv0_0", nf, in_ch)]
+    p = {}
+    for name, ci, co in spec:
+        w, bb = _conv_init(co, ci, 3, True, gen)
+        p[name + ".weight"], p[name + ".bias"] = w, bb
+    return p
+
+
+def _bn_state(p, b, name, c):
+    p[name + ".weight"], p[name + ".bias"] = torch.ones(c), torch.zeros(c)
+    b[name + ".running_mean"], b[name + ".running_var"] = torch.zeros(c), torch.ones(c)
+    b[name + ".num_batches_tracked"] = torch.zeros((), dtype=torch.long)
+
+
+def init_preact_resnet18_state(gen, num_classes=10, n_input=3, scaler=1):
+    p, b = {}, {}
+    p["conv1.weight"], _ = _conv_init(64, n_input, 3, False, gen)
+    in_planes = 64
+    for li, (planes, stride0) in enumerate([(64, 1), (128, 2), (256, 2), (512, 2)], start=1):
+        for bi, stride in enumerate([stride0, 1]):
+            pre = "layer%d.%d." % (li, bi)
+            _bn_state(p, b, pre + "bn1", in_planes)
+            p[pre + "conv1.weight"], _ = _conv_init(planes, in_planes, 3, False, gen)
+            _bn_state(p, b, pre + "bn2", planes)
+            p[pre + "conv2.weight"], _ = _conv_init(planes, planes, 3, False, gen)
+            if stride != 1 or in_planes != planes:
+                p[pre + "shortcut.0.weight"], _ = _conv_init(planes, in_planes, 1, False, gen)
+            in_planes = planes
+    p["linear.weight"], p["linear.bias"] = _linear_init(num_classes, 512 * scaler, gen)
+    return p, b
+
+
+def init_resnet18_state(gen, num_classes=10, n_input=3, scaler=4):
+    p, b = {}, {}
+    p["conv1.weight"], _ = _conv_init(64, n_input, 3, False, gen)
+    _bn_state(p, b, "bn1", 64)
+    in_planes = 64
+    for li, (planes, stride0) in enumerate([(64, 1), (128, 2), (256, 2), (512, 2)], start=1):
+        for bi, stride in enumerate([stride0, 1]):
+            pre = "layer%d.%d." % (li, bi)
+            p[pre + "conv1.weight"], _ = _conv_init(planes, in_planes, 3, False, gen)
+            _bn_state(p, b, pre + "bn1", planes)
+            p[pre + "conv2.weight"], _ = _conv_init(planes, planes, 3, False, gen)
+            _bn_state(p, b, pre + "bn2", planes)
+            if stride != 1 or in_planes != planes:
+                p[pre + "shortcut.0.weight"], _ = _conv_init(planes, in_planes, 1, False, gen)
+                _bn_state(p, b, pre + "shortcut.1", planes)
+            in_planes = planes
+    p["linear.weight"], p["linear.bias"] = _linear_init(num_classes, 512 * scaler, gen)
+    return p, b
+
+
+def init_frequency_model_state(gen, num_classes=2, n_input=3, scaler=1, randomize_bn_stats=False):
+    p, b = {}, {}
+    chans = [n_input, 32, 32, 64, 64, 128, 128]
+    for i in range(1, 7):
+        w, bb = _conv_init(chans[i], chans[i - 1], 3, True, gen)
+        p["conv%d.weight" % i], p["conv%d.bias" % i] = w, bb
+        _bn_state(p, b, "bn%d" % i, chans[i])
+    p["linear6.weight"], p["linear6.bias"] = _linear_init(num_classes, 2048 * scaler, gen)
+    if randomize_bn_stats:  # non-trivial eval statistics so the BN leg is actually exercised (drawn last)
+        for i in range(1, 7):
+            b["bn%d.running_mean" % i] = torch.randn(chans[i], generator=gen) * 0.1
+            b["bn%d.running_var" % i] = torch.rand(chans[i], generator=gen) + 0.5
+    return p, b
+
+
+def init_step_state(seed: int = 0, classifier: str = "preact_resnet18", num_classes: int = 10, scaler: int = 1,
+                    cond_classes: int = 0):
+    """A complete, seeded state for `alternated_step` (synthetic weights of the reference shapes)."""
+    gen = torch.Generator().manual_seed(seed)
+    initC = init_preact_resnet18_state if classifier == "preact_resnet18" else init_resnet18_state
+    netC_p, netC_b = initC(gen, num_classes=num_classes, scaler=scaler)
+    clean_p, clean_b = initC(gen, num_classes=num_classes, scaler=scaler)
+    netG_p = init_unet_state(gen, num_classes=cond_classes)
+    netF_p, netF_b = init_frequency_model_state(gen, scaler=scaler)
+    return dict(netC_p=netC_p, netC_b=netC_b, clean_p=clean_p, clean_b=clean_b, netG_p=netG_p,
+                netF_p=netF_p, netF_b=netF_b, momC={}, momG={})

@@ -1,0 +1,268 @@
+"""Generate the committed golden fixtures by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):
+    python tests/golden/make_golden.py
+Writes tests/golden/*.npz.  The reference has no tests or golden vectors of its own
+(SURVEY.md section 4), so these outputs of the reference itself are the parity pins for
+oracle/combat_oracle.py (tests/test_oracle_golden.py) and, through the oracle and
+directly, for the CUDA path (tests/test_*_gpu.py).
+
+Everything recorded here is observed from outside the reference code: forward hooks on
+the reference's own nn.Modules, recording wrappers around torch.nn.functional losses,
+and state_dicts before/after `train()`.
+"""
+import os
+import random
+import sys
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+from oracle.ref_loader import NullWriter, load_reference  # noqa: E402
+
+tg, config = load_reference()
+from classifier_models.preact_resnet import PreActResNet18  # noqa: E402
+from classifier_models.resnet import ResNet18  # noqa: E402
+from defenses.frequency_based.model import FrequencyModel  # noqa: E402
+from networks.models import CUnetGeneratorv1, UnetGenerator  # noqa: E402
+from utils.dct import dct_2d, idct_2d  # noqa: E402
+
+torch.set_num_threads(8)
+
+
+def seed_all(s):
+    torch.manual_seed(s)
+    np.random.seed(s)
+    random.seed(s)
+
+
+def get_opt(extra=()):
+    opt = config.get_arguments().parse_args(["--device", "cpu", "--post_transform_option", "no_use", *extra])
+    return opt
+
+
+def save(name, **kw):
+    path = os.path.join(HERE, name)
+    np.savez_compressed(path, **{k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in kw.items()})
+    print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024))
+
+
+# ---------------------------------------------------------------- DCT
+def gen_dct():
+    seed_all(1)
+    out = {}
+    for N in (32, 64):
+        x = torch.rand(2, 3, N, N) * 255
+        xu = (torch.rand(2, 3, N, N) * 256).clamp(0, 255).byte()
+        xn = torch.rand(2, 3, N, N) * 2 - 1
+        opt = get_opt()
+        opt.input_height = N
+        out.update({
+            "x%d" % N: x, "dct%d" % N: dct_2d(x), "idct%d" % N: idct_2d(x),
+            "xu%d" % N: xu, "dctu%d" % N: dct_2d(xu),
+            "xn%d" % N: xn, "lowfreq%d" % N: tg.low_freq(xn, opt),
+        })
+    # odd size (full-plane, non power of two) as used at ImageNet shape, kept tiny: N=28 plays the role of 224
+    x = torch.rand(1, 3, 28, 28) * 255
+    out.update(x28=x, dct28=dct_2d(x), idct28=idct_2d(x))
+    save("dct.npz", **out)
+
+
+# ---------------------------------------------------------------- modules
+def tensor_digest(t):
+    t = t.detach().flatten().double()
+    return np.array([t.sum().item(), t.abs().sum().item(), (t * t).sum().item()])
+
+
+def gen_modules():
+    out = {}
+    # UnetGenerator forward + input-grad + weight-grad digests, seed 2
+    seed_all(2)
+    opt = get_opt()
+    netG = UnetGenerator(opt)
+    x = (torch.rand(4, 3, 32, 32) * 2 - 1).requires_grad_(True)
+    y = netG(x)
+    w = torch.rand(4, 3, 32, 32)
+    (y * w).sum().backward()
+    out.update(unet_x=x, unet_y=y, unet_w=w, unet_dx=x.grad)
+    for k, p in netG.named_parameters():
+        out["unet_g_" + k] = tensor_digest(p.grad)
+        out["unet_p_" + k] = tensor_digest(p)
+    out["unet_gfull_conv0_0.weight"] = netG.conv0_0.weight.grad
+    out["unet_gfull_upconv0_0.weight"] = netG.upconv0_0.weight.grad
+    out["unet_gfull_conv3_1.bias"] = netG.conv3_1.bias.grad
+    # CUnetGeneratorv1 (CelebA: 8 classes) at 64x64, seed 3
+    seed_all(3)
+    opt.num_classes = 8
+    netG2 = CUnetGeneratorv1(opt)
+    x2 = torch.rand(2, 3, 64, 64) * 2 - 1
+    y2 = torch.randint(0, 8, (2,))
+    out.update(cunet_x=x2, cunet_lbl=y2, cunet_y=netG2(x2, y2))
+    # PreActResNet18: train-mode forward/backward + running stats, then eval-mode forward, seed 4
+    seed_all(4)
+    netC = PreActResNet18()
+    x3 = (torch.rand(8, 3, 32, 32) * 2 - 1).requires_grad_(True)
+    t3 = torch.randint(0, 10, (8,))
+    netC.train()
+    logits = netC(x3)
+    loss = F.cross_entropy(logits, t3)
+    loss.backward()
+    out.update(preact_x=x3, preact_t=t3, preact_logits_train=logits, preact_loss=loss, preact_dx=x3.grad)
+    for k, p in netC.named_parameters():
+        out["preact_g_" + k] = tensor_digest(p.grad)
+    out["preact_gfull_conv1.weight"] = netC.conv1.weight.grad
+    out["preact_gfull_linear.weight"] = netC.linear.weight.grad
+    out["preact_gfull_layer2.0.shortcut.0.weight"] = netC.layer2[0].shortcut[0].weight.grad
+    out["preact_rm_layer1.0.bn1"] = netC.layer1[0].bn1.running_mean
+    out["preact_rv_layer4.1.bn2"] = netC.layer4[1].bn2.running_var
+    netC.eval()
+    out["preact_logits_eval"] = netC(x3.detach())
+    # ResNet18 (CelebA 64x64, 8 classes), seed 5
+    seed_all(5)
+    netR = ResNet18(num_classes=8)
+    x4 = torch.rand(2, 3, 64, 64) * 2 - 1
+    netR.train()
+    out.update(resnet_x=x4, resnet_logits_train=netR(x4))
+    netR.eval()
+    out["resnet_logits_eval"] = netR(x4)
+    # FrequencyModel with the SHIPPED cifar10 detector weights: dct_2d(uint8) -> netF known answer
+    seed_all(6)
+    netF = FrequencyModel(2, 3, 32)
+    ck = torch.load(os.path.join("/root/reference/defenses/frequency_based/checkpoints/cifar10/cifar10_original_detector.pth.tar"),
+                    map_location="cpu")
+    sd = ck["netC"] if "netC" in ck else ck
+    netF.load_state_dict(sd)
+    netF.eval()
+    xu = (torch.rand(4, 3, 32, 32) * 256).clamp(0, 255).byte()
+    with torch.no_grad():
+        out.update(freq_xu=xu, freq_logits=netF(dct_2d(xu)))
+    # the shipped weights are 1.2 MB: keep them as fp16-free exact float32 in the fixture so the GPU box has them
+    for k, v in netF.state_dict().items():
+        out["freq_sd_" + k] = v
+    save("modules.npz", **out)
+
+
+# ---------------------------------------------------------------- full alternated step(s)
+class Recorder:
+    """Observes an unmodified train() call from outside."""
+
+    def __init__(self, netC, netG, clean_model, netF):
+        self.calls = {"netC": [], "netG": [], "clean": [], "netF": []}
+        self.losses = []
+        self.sigmas = []
+        for name, m in (("netC", netC), ("netG", netG), ("clean", clean_model), ("netF", netF)):
+            m.register_forward_hook(lambda mod, inp, outp, name=name: self.calls[name].append(
+                (inp[0].detach().clone(), outp.detach().clone(), mod.training)))
+        self._ce, self._mse = F.cross_entropy, F.mse_loss
+
+    def __enter__(self):
+        rec = self
+
+        def ce(*a, **k):
+            v = rec._ce(*a, **k)
+            rec.losses.append(("ce", float(v)))
+            return v
+
+        def mse(*a, **k):
+            v = rec._mse(*a, **k)
+            rec.losses.append(("mse", float(v)))
+            return v
+
+        F.cross_entropy, F.mse_loss = ce, mse
+        import torchvision.transforms as T
+        self._gp = T.GaussianBlur.get_params
+
+        def gp(lo, hi):
+            s = rec._gp(lo, hi)
+            rec.sigmas.append(s)
+            return s
+
+        T.GaussianBlur.get_params = staticmethod(gp)
+        return self
+
+    def __exit__(self, *a):
+        F.cross_entropy, F.mse_loss = self._ce, self._mse
+        import torchvision.transforms as T
+        T.GaussianBlur.get_params = staticmethod(self._gp)
+
+
+def param_summary(prefix, before, after, out, full_keys=()):
+    for k in after:
+        if not torch.is_floating_point(after[k]):
+            out[prefix + "int_" + k] = after[k]
+            continue
+        d = (after[k] - before[k]).double()
+        out[prefix + "dnorm_" + k] = np.array([d.norm().item(), d.sum().item()])
+        out[prefix + "dhead_" + k] = (after[k] - before[k]).flatten()[:8]
+        if k in full_keys:
+            out[prefix + "dfull_" + k] = after[k] - before[k]
+
+
+def gen_step(name, B, n_batches, seed):
+    """SURVEY 8c-4 recipe: seed all three RNGs, get_model (netC, clean_model, netG, netF), then data."""
+    opt = get_opt()
+    opt.input_height = opt.input_width = 32
+    opt.input_channel = 3
+    seed_all(seed)
+    netC, optC, schC, netG, optG, schG, netF, clean = tg.get_model(opt)
+    netF.eval()
+    clean.eval()
+    batches = [(torch.rand(B, 3, 32, 32) * 2 - 1, torch.randint(0, 10, (B,))) for _ in range(n_batches)]
+    sd0 = {n: {k: v.clone() for k, v in m.state_dict().items()} for n, m in (("netC", netC), ("netG", netG), ("clean", clean))}
+    rec = Recorder(netC, netG, clean, netF)
+    with rec:
+        tg.train(netC, optC, schC, netG, optG, schG, netF, clean, batches, NullWriter(), 1, opt)
+    torch.autograd.set_detect_anomaly(False)
+    out = {"seed": seed, "B": B, "n_batches": n_batches, "sigmas": np.array(rec.sigmas)}
+    out["loss_kinds"] = np.array([k for k, _ in rec.losses])
+    out["loss_values"] = np.array([v for _, v in rec.losses])
+    for i, (x, y) in enumerate(batches):
+        out["y_%d" % i] = y
+    # per iteration module calls: netG [C-step subset, G-step full]; netC [train total_x, eval x, eval x_bd];
+    # clean [x, x_bd]; netF [dct]
+    gi = ci = 0
+    for i, (x, y) in enumerate(batches):
+        g_sel_in, g_sel_out, _ = rec.calls["netG"][gi]
+        g_all_in, g_all_out, g_train = rec.calls["netG"][gi + 1]
+        gi += 2
+        # recover which rows were poisoned by matching the generator's C-step input rows against the batch
+        idx = [int((x == r).flatten(1).all(1).nonzero()[0, 0]) for r in g_sel_in]
+        out["poison_idx_%d" % i] = np.array(idx, dtype=np.int64)
+        out["num_bd_%d" % i] = len(idx)
+        c_tot_in, c_tot_out, c_tr = rec.calls["netC"][ci]
+        c_cl_in, c_cl_out, _ = rec.calls["netC"][ci + 1]
+        c_bd_in, c_bd_out, _ = rec.calls["netC"][ci + 2]
+        ci += 3
+        assert c_tr and not g_train is False
+        # batch order of total_x: recover the permutation
+        perm = [int((x == r).flatten(1).all(1).nonzero()[0, 0]) if (x == r).flatten(1).all(1).any() else -1 for r in c_tot_in]
+        out["total_perm_%d" % i] = np.array(perm, dtype=np.int64)  # -1 = poisoned (modified) rows
+        out["logits_c_%d" % i] = c_tot_out
+        out["pred_clean_%d" % i] = c_cl_out
+        out["pred_bd_%d" % i] = c_bd_out
+        out["clean_preds_%d" % i] = rec.calls["clean"][2 * i][1]
+        out["clean_model_preds_%d" % i] = rec.calls["clean"][2 * i + 1][1]
+        out["pred_F_%d" % i] = rec.calls["netF"][i][1]
+        out["inputs_F_head_%d" % i] = rec.calls["netF"][i][0][:2]
+        out["x_bd_head_%d" % i] = c_bd_in[:4]
+        out["x_bd_digest_%d" % i] = tensor_digest(c_bd_in)
+        out["noise_head_%d" % i] = g_all_out[:4]
+        out["x_bd_c_%d" % i] = c_tot_in[: len(idx)]
+    param_summary("netC_", sd0["netC"], netC.state_dict(), out, full_keys=("conv1.weight", "linear.weight", "linear.bias", "layer1.0.bn1.running_mean", "layer1.0.bn1.running_var", "layer3.1.bn2.weight"))
+    param_summary("netG_", sd0["netG"], netG.state_dict(), out, full_keys=("conv0_0.weight", "conv0_0.bias", "upconv0_0.weight", "upconv0_0.bias", "conv3_1.bias"))
+    param_summary("clean_", sd0["clean"], clean.state_dict(), out)
+    save(name, **out)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["dct", "modules", "step"]
+    if "dct" in which:
+        gen_dct()
+    if "modules" in which:
+        gen_modules()
+    if "step" in which:
+        gen_step("step_b128.npz", 128, 1, 0)      # the SURVEY 8c-4 known-answer vector
+        gen_step("step_b32x2.npz", 32, 2, 7)      # two iterations: momentum buffers + RNG interleaving
