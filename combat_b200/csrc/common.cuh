@@ -1,0 +1,92 @@
+// Shared helpers for the combat_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/combat_b200.h"
+
+typedef __nv_bfloat16 bf16;
+
+extern long long g_combat_launches;
+extern char g_combat_err[256];
+void combat_set_err(const char* what, cudaError_t e);
+
+#define COMBAT_COUNT_LAUNCH() (++g_combat_launches)
+
+// launch-and-check used by every entry point: peeks (does not clear a sticky error from elsewhere)
+#define COMBAT_RETURN_LAUNCH(name)               \
+  do {                                           \
+    COMBAT_COUNT_LAUNCH();                       \
+    cudaError_t e__ = cudaGetLastError();        \
+    if (e__ != cudaSuccess) {                    \
+      combat_set_err(name, e__);                 \
+      return -(int)e__;                          \
+    }                                            \
+    return 0;                                    \
+  } while (0)
+
+#define COMBAT_CHECK_LAUNCH(name)                \
+  do {                                           \
+    COMBAT_COUNT_LAUNCH();                       \
+    cudaError_t e__ = cudaGetLastError();        \
+    if (e__ != cudaSuccess) {                    \
+      combat_set_err(name, e__);                 \
+      return -(int)e__;                          \
+    }                                            \
+  } while (0)
+
+#define COMBAT_ARG(cond, k)                      \
+  do {                                           \
+    if (!(cond)) {                               \
+      combat_set_err("bad argument: " #cond, cudaErrorInvalidValue); \
+      return -1000 - (k);                        \
+    }                                            \
+  } while (0)
+
+template <typename T>
+__device__ __forceinline__ float to_f(T v);
+template <>
+__device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__device__ __forceinline__ T from_f(float v);
+template <>
+__device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// dtype-erased scalar load/store (generic strided SIMT paths)
+__device__ __forceinline__ float ld_any(const void* p, long long i, int dtype) {
+  return dtype == COMBAT_F32 ? ((const float*)p)[i] : __bfloat162float(((const bf16*)p)[i]);
+}
+__device__ __forceinline__ void st_any(void* p, long long i, int dtype, float v) {
+  if (dtype == COMBAT_F32)
+    ((float*)p)[i] = v;
+  else
+    ((bf16*)p)[i] = __float2bfloat16_rn(v);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+#define DISPATCH_DTYPE(dtype, ...)        \
+  if ((dtype) == COMBAT_F32) {            \
+    typedef float T;                      \
+    __VA_ARGS__                           \
+  } else {                                \
+    typedef bf16 T;                       \
+    __VA_ARGS__                           \
+  }

@@ -1,0 +1,759 @@
+// tcgen05 implicit-GEMM convolution for sm_100a: TMA-fed (tiled 4-D boxes with hardware zero fill as the
+// implicit padding), SWIZZLE_128B shared-memory operands, fp32 accumulators in TMEM, warp-specialised
+// persistent CTAs (1 TMA warp, 1 MMA warp, 4 epilogue warps), double-buffered accumulators.
+//
+//   forward / dgrad :  D[pixel, co] = sum_{tap, ci} A[pixel @ tap, ci] * W[co, tap, ci]          (K-major A and B)
+//   wgrad           :  D[(tap,ci), co] = sum_{pixel} X[pixel @ tap, ci] * dY[pixel, co]           (MN-major A and B)
+//
+// An M tile is a BW x BH x BNI box of output pixels (128 of them); the A operand of filter tap (kh,kw) is the
+// same box shifted by the tap offset, fetched by ONE TMA box load whose out-of-range rows/columns the hardware
+// fills with zeros.  Strided forward convs read one of four parity views of the input (tensor maps with doubled
+// strides); the input-gradient of a strided conv is computed per output parity class, each class being a
+// stride-1 problem over a subset of the taps.
+//
+// Replaces aten::conv2d / convolution_backward (cuDNN) for every conv with Cin % 64 == 0 and Cout % 64 == 0:
+// classifier_models/preact_resnet.py:21-28, resnet.py:18-27, networks/models.py:275-314.
+#include <cuda.h>
+
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// arrives on the mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B, version 1
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // version = 1 (Blackwell)
+  d |= (uint64_t)2 << 61;  // layout type = SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D=f32, A=B=bf16, majorness bits, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------- parameters
+#define TC_MAX_CLASSES 4
+#define TC_MAX_TAPS 9
+#define TILE_M 128
+#define KCHUNK 64  // bf16 elements per 128-byte swizzle row
+
+struct TcTaps {
+  int ntaps[TC_MAX_CLASSES];
+  signed char view[TC_MAX_CLASSES][TC_MAX_TAPS];
+  signed char dh[TC_MAX_CLASSES][TC_MAX_TAPS];
+  signed char dw[TC_MAX_CLASSES][TC_MAX_TAPS];
+  signed char wtap[TC_MAX_CLASSES][TC_MAX_TAPS];
+  int cls_p[TC_MAX_CLASSES], cls_q[TC_MAX_CLASSES];
+};
+
+struct TcParams {
+  int N, Hc, Wc;          // pixel grid of one class (== output grid when n_classes == 1)
+  int out_H, out_W, Co;   // full output tensor
+  int out_scale;          // output pixel = class pixel * out_scale + (cls_p, cls_q)
+  int BW, BH, BNI;        // pixel box, BW*BH*BNI == 128
+  int tiles_w, tiles_h, tiles_n, tiles_co, n_classes, total_tiles;
+  int kchunks;            // Ci / 64
+  bf16* out;
+  const bf16* residual;
+  const float* bias;
+  TcTaps taps;
+};
+
+struct TcMaps {
+  CUtensorMap in[4];  // parity views of the input (only [0] when unstrided)
+  CUtensorMap w;      // [Co][taps][Ci] as (Ci, taps, Co)
+};
+
+template <int BLOCK_N>
+struct TcCfg {
+  static constexpr int A_BYTES = TILE_M * KCHUNK * 2;    // 16 KB
+  static constexpr int B_BYTES = BLOCK_N * KCHUNK * 2;   // 8 / 16 KB
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = BLOCK_N == 64 ? 8 : 6;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;          // two accumulator buffers (128 or 256: powers of two)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ void decode_tile(const TcParams& p, int tile, int& cls, int& nt, int& ht, int& wt, int& cot) {
+  cot = tile % p.tiles_co;
+  int r = tile / p.tiles_co;
+  wt = r % p.tiles_w;
+  r /= p.tiles_w;
+  ht = r % p.tiles_h;
+  r /= p.tiles_h;
+  nt = r % p.tiles_n;
+  cls = r / p.tiles_n;
+}
+
+// ---------------------------------------------------------------------------------------------- fwd / dgrad kernel
+template <int BLOCK_N>
+__global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
+  using Cfg = TcCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B atoms need 1024 B alignment
+  uint64_t* bars = (uint64_t*)(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::STAGES;
+  uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;
+  uint64_t* tempty_bar = bars + 2 * Cfg::STAGES + 2;
+  uint32_t* tmem_ptr_smem = (uint32_t*)(bars + 2 * Cfg::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.w);
+    tma_prefetch_desc(&maps.in[0]);
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int cls, nt, ht, wt, cot;
+        decode_tile(p, tile, cls, nt, ht, wt, cot);
+        const int ntaps = p.taps.ntaps[cls];
+        for (int t = 0; t < ntaps; ++t) {
+          const CUtensorMap* amap = &maps.in[p.taps.view[cls][t]];
+          const int cw = wt * p.BW + p.taps.dw[cls][t];
+          const int ch = ht * p.BH + p.taps.dh[cls][t];
+          const int cn = nt * p.BNI;
+          const int wtap = p.taps.wtap[cls][t];
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+            uint8_t* sb = sa + Cfg::A_BYTES;
+            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            tma_load_4d(sa, amap, &full_bar[stage], kc * KCHUNK, cw, ch, cn);
+            tma_load_3d(sb, &maps.w, &full_bar[stage], kc * KCHUNK, wtap, cot * BLOCK_N);
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(TILE_M, BLOCK_N, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int cls, nt, ht, wt, cot;
+        decode_tile(p, tile, cls, nt, ht, wt, cot);
+        const int kiters = p.taps.ntaps[cls] * p.kchunks;
+        if (kiters == 0) continue;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int it = 0; it < kiters; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint64_t adesc = make_smem_desc(sa, 16, 1024);
+          const uint64_t bdesc = make_smem_desc(sb, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < KCHUNK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> (bias, residual) -> bf16 global =====================
+    const int quarter = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    const int row = quarter * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int cls, nt, ht, wt, cot;
+      decode_tile(p, tile, cls, nt, ht, wt, cot);
+      const bool has_acc = p.taps.ntaps[cls] > 0;
+      // pixel of this row
+      const int wi = row % p.BW;
+      const int r2 = row / p.BW;
+      const int hi = r2 % p.BH;
+      const int ni = r2 / p.BH;
+      const int n = nt * p.BNI + ni, a = ht * p.BH + hi, b = wt * p.BW + wi;
+      const bool valid = n < p.N && a < p.Hc && b < p.Wc;
+      const int oh = a * p.out_scale + p.taps.cls_p[cls], ow = b * p.out_scale + p.taps.cls_q[cls];
+      const long long obase = (((long long)n * p.out_H + oh) * p.out_W + ow) * p.Co + (long long)cot * BLOCK_N;
+      if (has_acc) {
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+      }
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+        uint32_t v[16];
+        if (has_acc) {
+          tmem_ld16(taddr + c0, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0u;
+        }
+        if (valid) {
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias) {
+            const float4* bp = (const float4*)(p.bias + cot * BLOCK_N + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float4 bb = bp[j];
+              f[4 * j] += bb.x; f[4 * j + 1] += bb.y; f[4 * j + 2] += bb.z; f[4 * j + 3] += bb.w;
+            }
+          }
+          if (p.residual) {
+            const uint4* rp = (const uint4*)(p.residual + obase + c0);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              uint4 rr = rp[j];
+              const uint32_t w4[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                float2 t2 = __bfloat1622float2(*(const __nv_bfloat162*)&w4[q]);
+                f[8 * j + 2 * q] += t2.x;
+                f[8 * j + 2 * q + 1] += t2.y;
+              }
+            }
+          }
+          uint4* op = (uint4*)(p.out + obase + c0);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            uint32_t w4[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(f[8 * j + 2 * q], f[8 * j + 2 * q + 1]);
+              w4[q] = *(uint32_t*)&h2;
+            }
+            op[j] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+          }
+        }
+      }
+      if (has_acc) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = (PFN_encodeTiled)ptr;
+  }
+  return fn;
+}
+
+// NHWC bf16 activation (possibly a parity view): dims (C, W, H, N), element strides given for w/h/n
+static int make_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, long long sw, long long sh, long long sn,
+                        int BW, int BH, int BNI) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return -1;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)sw * 2, (cuuint64_t)sh * 2, (cuuint64_t)sn * 2};
+  cuuint32_t box[4] = {KCHUNK, (cuuint32_t)BW, (cuuint32_t)BH, (cuuint32_t)BNI};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -(int)r - 2000;
+}
+
+// weights [rows][taps][K] bf16 as (K, taps, rows); box (64, 1, box_rows)
+static int make_w_map(CUtensorMap* m, const void* base, int K, int taps, int rows, int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return -1;
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)taps, (cuuint64_t)rows};
+  cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)K * taps * 2};
+  cuuint32_t box[3] = {KCHUNK, 1, (cuuint32_t)box_rows};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -(int)r - 2000;
+}
+
+static int p2ceil(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+static void pick_box(int Hc, int Wc, int pixels, int* BW, int* BH, int* BNI) {
+  int bw = p2ceil(Wc);
+  if (bw > pixels) bw = pixels;
+  int bh = p2ceil(Hc);
+  if (bh > pixels / bw) bh = pixels / bw;
+  *BW = bw;
+  *BH = bh;
+  *BNI = pixels / (bw * bh);
+}
+
+static int floordiv2(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }
+
+extern "C" int combat_conv_tc_supported(const combat_conv_tc_desc* d) {
+  if (!d) return 0;
+  if (d->Ci % 64 || d->Co % 64) return 0;
+  if (d->KH != d->KW || (d->KH != 1 && d->KH != 3)) return 0;
+  if (!((d->stride == 1 && d->up == 1) || (d->stride == 2 && d->up == 1) || (d->stride == 1 && d->up == 2))) return 0;
+  if (d->stride == 2 && ((d->Hi | d->Wi) & 1)) return 0;
+  if (d->up == 2 && ((d->Ho | d->Wo) & 1)) return 0;
+  return get_encode() != nullptr;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+extern "C" int combat_conv_tc(const combat_conv_tc_desc* d, void* stream) {
+  COMBAT_ARG(d && d->in && d->w && d->out, 0);
+  COMBAT_ARG(combat_conv_tc_supported(d), 0);
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  TcMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  const int KH = d->KH, KW = d->KW, pad = d->pad;
+  p.N = d->N;
+  p.out_H = d->Ho;
+  p.out_W = d->Wo;
+  p.Co = d->Co;
+  p.kchunks = d->Ci / KCHUNK;
+  p.out = (bf16*)d->out;
+  p.residual = (const bf16*)d->residual;
+  p.bias = d->bias;
+  const int BLOCK_N = (d->Co % 128 == 0) ? 128 : 64;
+  p.tiles_co = d->Co / BLOCK_N;
+  int rc;
+  if (d->up == 1) {
+    p.n_classes = 1;
+    p.out_scale = 1;
+    p.Hc = d->Ho;
+    p.Wc = d->Wo;
+    pick_box(p.Hc, p.Wc, TILE_M, &p.BW, &p.BH, &p.BNI);
+    const int s = d->stride;
+    int nt = 0;
+    for (int kh = 0; kh < KH; ++kh)
+      for (int kw = 0; kw < KW; ++kw) {
+        const int oh = kh - pad, ow = kw - pad;
+        int ph = 0, pw = 0, dh = oh, dw = ow;
+        if (s == 2) {
+          ph = ((oh % 2) + 2) % 2;
+          pw = ((ow % 2) + 2) % 2;
+          dh = floordiv2(oh);
+          dw = floordiv2(ow);
+        }
+        p.taps.view[0][nt] = (signed char)(ph * 2 + pw);
+        p.taps.dh[0][nt] = (signed char)dh;
+        p.taps.dw[0][nt] = (signed char)dw;
+        p.taps.wtap[0][nt] = (signed char)(kh * KW + kw);
+        ++nt;
+      }
+    p.taps.ntaps[0] = nt;
+    const long long C = d->Ci, W = d->Wi, H = d->Hi;
+    if (s == 1) {
+      rc = make_act_map(&maps.in[0], d->in, d->Ci, d->Wi, d->Hi, d->N, C, W * C, H * W * C, p.BW, p.BH, p.BNI);
+      if (rc) return rc;
+    } else {
+      for (int ph = 0; ph < 2; ++ph)
+        for (int pw = 0; pw < 2; ++pw) {
+          const bf16* base = (const bf16*)d->in + ((long long)ph * W + pw) * C;
+          rc = make_act_map(&maps.in[ph * 2 + pw], base, d->Ci, (d->Wi - pw + 1) / 2, (d->Hi - ph + 1) / 2, d->N, 2 * C,
+                            2 * W * C, H * W * C, p.BW, p.BH, p.BNI);
+          if (rc) return rc;
+        }
+    }
+  } else {
+    // input gradient of a stride-2 conv: one stride-1 problem per output parity class
+    p.n_classes = 4;
+    p.out_scale = 2;
+    p.Hc = d->Ho / 2;
+    p.Wc = d->Wo / 2;
+    pick_box(p.Hc, p.Wc, TILE_M, &p.BW, &p.BH, &p.BNI);
+    for (int cp = 0; cp < 2; ++cp)
+      for (int cq = 0; cq < 2; ++cq) {
+        const int cls = cp * 2 + cq;
+        p.taps.cls_p[cls] = cp;
+        p.taps.cls_q[cls] = cq;
+        int nt = 0;
+        for (int kh = 0; kh < KH; ++kh)
+          for (int kw = 0; kw < KW; ++kw) {
+            const int nh = cp - pad + kh, nw = cq - pad + kw;  // (2a + p - pad + kh) / 2 = a + nh / 2
+            if ((nh & 1) || (nw & 1)) continue;
+            p.taps.view[cls][nt] = 0;
+            p.taps.dh[cls][nt] = (signed char)(nh / 2);
+            p.taps.dw[cls][nt] = (signed char)(nw / 2);
+            p.taps.wtap[cls][nt] = (signed char)(kh * KW + kw);
+            ++nt;
+          }
+        p.taps.ntaps[cls] = nt;
+      }
+    const long long C = d->Ci, W = d->Wi, H = d->Hi;
+    rc = make_act_map(&maps.in[0], d->in, d->Ci, d->Wi, d->Hi, d->N, C, W * C, H * W * C, p.BW, p.BH, p.BNI);
+    if (rc) return rc;
+  }
+  rc = make_w_map(&maps.w, d->w, d->Ci, KH * KW, d->Co, BLOCK_N);
+  if (rc) return rc;
+  p.tiles_w = cdiv(p.Wc, p.BW);
+  p.tiles_h = cdiv(p.Hc, p.BH);
+  p.tiles_n = cdiv(p.N, p.BNI);
+  p.total_tiles = p.n_classes * p.tiles_n * p.tiles_h * p.tiles_w * p.tiles_co;
+  int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  cudaStream_t st = (cudaStream_t)stream;
+  if (BLOCK_N == 128) {
+    cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM_BYTES);
+    conv_tc_kernel<128><<<grid, 192, TcCfg<128>::SMEM_BYTES, st>>>(maps, p);
+  } else {
+    cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::SMEM_BYTES);
+    conv_tc_kernel<64><<<grid, 192, TcCfg<64>::SMEM_BYTES, st>>>(maps, p);
+  }
+  COMBAT_RETURN_LAUNCH("conv_tc");
+}
+
+// ---------------------------------------------------------------------------------------------- wgrad kernel
+// D[(tap,ci), co] = sum_pixels X[pixel @ tap, ci] * dY[pixel, co]; both operands MN-major (pixels are the K dim).
+// One CTA = (pair of 64-row (tap, ci-chunk) blocks) x (BLOCK_N output channels) x (one split of the pixel range);
+// partial sums are reduced with coalesced fp32 red.global.add into the channels-last (OHWI) gradient buffer.
+struct TcWgradParams {
+  int N, Ho, Wo, Co, Ci, taps;
+  int BW, BH, BNI;  // 64-pixel box
+  int tiles_w, tiles_h, tiles_n, total_boxes, boxes_per_split;
+  int kchunks, row_chunks, m_tiles, n_tiles;
+  float* dw;  // [Co][taps][Ci] fp32
+  TcTaps taps_tbl;  // class 0 only
+};
+struct TcWgradMaps {
+  CUtensorMap x[4];
+  CUtensorMap dy;
+};
+
+template <int BLOCK_N>
+struct TcWCfg {
+  static constexpr int A_BYTES = 2 * 64 * KCHUNK * 2;             // two 64-pixel x 64-channel boxes: 16 KB
+  static constexpr int B_BYTES = (BLOCK_N / 64) * 64 * KCHUNK * 2;  // 8 KB per 64 output channels
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(192, 1) conv_tc_wgrad_kernel(const __grid_constant__ TcWgradMaps maps, const TcWgradParams p) {
+  using Cfg = TcWCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::STAGES;
+  uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;
+  uint32_t* tmem_ptr_smem = (uint32_t*)(bars + 2 * Cfg::STAGES + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int m_tile = blockIdx.x % p.m_tiles, n_tile = blockIdx.x / p.m_tiles;
+  const int box0 = blockIdx.y * p.boxes_per_split;
+  int box1 = box0 + p.boxes_per_split;
+  if (box1 > p.total_boxes) box1 = p.total_boxes;
+  const int nbox = box1 - box0;  // >= 1 by construction
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.dy);
+    tma_prefetch_desc(&maps.x[0]);
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  // the two 64-row blocks of this M tile
+  int rc[2], tap[2], cic[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    rc[j] = m_tile * 2 + j;
+    const int r = rc[j] < p.row_chunks ? rc[j] : 0;
+    tap[j] = r / p.kchunks;
+    cic[j] = r % p.kchunks;
+  }
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int b = box0; b < box1; ++b) {
+        const int wt = b % p.tiles_w;
+        const int r2 = b / p.tiles_w;
+        const int ht = r2 % p.tiles_h, nt = r2 / p.tiles_h;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+        uint8_t* sb = sa + Cfg::A_BYTES;
+        mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int t = tap[j];
+          tma_load_4d(sa + j * 8192, &maps.x[p.taps_tbl.view[0][t]], &full_bar[stage], cic[j] * KCHUNK,
+                      wt * p.BW + p.taps_tbl.dw[0][t], ht * p.BH + p.taps_tbl.dh[0][t], nt * p.BNI);
+        }
+#pragma unroll
+        for (int j = 0; j < BLOCK_N / 64; ++j)
+          tma_load_4d(sb + j * 8192, &maps.dy, &full_bar[stage], n_tile * BLOCK_N + j * 64, wt * p.BW, ht * p.BH, nt * p.BNI);
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(TILE_M, BLOCK_N, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int b = 0; b < nbox; ++b) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const uint32_t sb = sa + Cfg::A_BYTES;
+        // MN-major SWIZZLE_128B: LBO = distance between 64-element MN chunks (8 KB), SBO = 8 K-rows (1 KB)
+        const uint64_t adesc = make_smem_desc(sa, 8192, 1024);
+        const uint64_t bdesc = make_smem_desc(sb, 8192, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // 16 pixels (K rows of 128 B) per MMA: +2048 B = +128 in the (addr >> 4) field
+          umma_bf16(tmem_base, adesc + 128 * k, bdesc + 128 * k, idesc, (b | k) != 0);
+        umma_commit(&empty_bar[stage]);
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tfull_bar);
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int j = row >> 6;
+    const int ci = cic[j] * KCHUNK + (row & 63);
+    const bool valid = rc[j] < p.row_chunks;
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    float* base = p.dw + (long long)tap[j] * p.Ci + ci;
+    const long long co_stride = (long long)p.taps * p.Ci;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(taddr + c0, v);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const int co = n_tile * BLOCK_N + c0 + q;
+          atomicAdd(base + co * co_stride, __uint_as_float(v[q]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+extern "C" int combat_conv_tc_wgrad(const combat_conv_tc_desc* d, const void* dy, float* dw_ohwi, void* stream) {
+  COMBAT_ARG(d && d->in && dy && dw_ohwi, 0);
+  COMBAT_ARG(combat_conv_tc_supported(d) && d->up == 1, 0);
+  TcWgradParams p;
+  memset(&p, 0, sizeof(p));
+  TcWgradMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  const int KH = d->KH, KW = d->KW, pad = d->pad, s = d->stride;
+  p.N = d->N; p.Ho = d->Ho; p.Wo = d->Wo; p.Co = d->Co; p.Ci = d->Ci; p.taps = KH * KW;
+  p.kchunks = d->Ci / KCHUNK;
+  p.row_chunks = p.taps * p.kchunks;
+  p.m_tiles = (p.row_chunks + 1) / 2;
+  const int BLOCK_N = d->Co % 256 == 0 ? 256 : (d->Co % 128 == 0 ? 128 : 64);
+  p.n_tiles = d->Co / BLOCK_N;
+  p.dw = dw_ohwi;
+  pick_box(d->Ho, d->Wo, 64, &p.BW, &p.BH, &p.BNI);
+  int nt = 0;
+  for (int kh = 0; kh < KH; ++kh)
+    for (int kw = 0; kw < KW; ++kw) {
+      const int oh = kh - pad, ow = kw - pad;
+      int ph = 0, pw = 0, dh = oh, dwv = ow;
+      if (s == 2) {
+        ph = ((oh % 2) + 2) % 2; pw = ((ow % 2) + 2) % 2;
+        dh = floordiv2(oh); dwv = floordiv2(ow);
+      }
+      p.taps_tbl.view[0][nt] = (signed char)(ph * 2 + pw);
+      p.taps_tbl.dh[0][nt] = (signed char)dh;
+      p.taps_tbl.dw[0][nt] = (signed char)dwv;
+      ++nt;
+    }
+  int rc;
+  const long long C = d->Ci, W = d->Wi, H = d->Hi;
+  if (s == 1) {
+    rc = make_act_map(&maps.x[0], d->in, d->Ci, d->Wi, d->Hi, d->N, C, W * C, H * W * C, p.BW, p.BH, p.BNI);
+    if (rc) return rc;
+  } else {
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw) {
+        const bf16* base = (const bf16*)d->in + ((long long)ph * W + pw) * C;
+        rc = make_act_map(&maps.x[ph * 2 + pw], base, d->Ci, (d->Wi - pw + 1) / 2, (d->Hi - ph + 1) / 2, d->N, 2 * C, 2 * W * C,
+                          H * W * C, p.BW, p.BH, p.BNI);
+        if (rc) return rc;
+      }
+  }
+  const long long Co = d->Co;
+  rc = make_act_map(&maps.dy, dy, d->Co, d->Wo, d->Ho, d->N, Co, (long long)d->Wo * Co, (long long)d->Ho * d->Wo * Co, p.BW, p.BH,
+                    p.BNI);
+  if (rc) return rc;
+  p.tiles_w = cdiv(d->Wo, p.BW);
+  p.tiles_h = cdiv(d->Ho, p.BH);
+  p.tiles_n = cdiv(d->N, p.BNI);
+  p.total_boxes = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int ctas_mn = p.m_tiles * p.n_tiles;
+  int splits = cdiv(2 * num_sms(), ctas_mn);
+  if (splits > p.total_boxes) splits = p.total_boxes;
+  if (splits < 1) splits = 1;
+  p.boxes_per_split = cdiv(p.total_boxes, splits);
+  splits = cdiv(p.total_boxes, p.boxes_per_split);
+  dim3 grid(ctas_mn, splits);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH_W(BN)                                                                                              \
+  {                                                                                                               \
+    cudaFuncSetAttribute(conv_tc_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcWCfg<BN>::SMEM_BYTES); \
+    conv_tc_wgrad_kernel<BN><<<grid, 192, TcWCfg<BN>::SMEM_BYTES, st>>>(maps, p);                                 \
+  }
+  if (BLOCK_N == 256) LAUNCH_W(256) else if (BLOCK_N == 128) LAUNCH_W(128) else LAUNCH_W(64)
+#undef LAUNCH_W
+  COMBAT_RETURN_LAUNCH("conv_tc_wgrad");
+}

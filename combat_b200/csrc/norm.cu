@@ -1,0 +1,820 @@
+// Normalisation / activation / resampling / pooling kernels on NHWC activations (float32 or bf16 storage,
+// float32 arithmetic and statistics).  Replaces, for the hot path of the reference:
+//   nn.BatchNorm2d + F.relu          classifier_models/preact_resnet.py:20,22,32,35 ; resnet.py:18-35,75,90
+//   nn.InstanceNorm2d + LeakyReLU    networks/models.py:273-340
+//   nn.Upsample(bilinear, x2)        networks/models.py:274
+//   AvgPool2d(4) + Linear            classifier_models/preact_resnet.py:99-101 ; resnet.py:95-97
+//   MaxPool2d(2), ELU+BN(eval)       defenses/frequency_based/model.py:13-44
+#include "common.cuh"
+
+// ---- two adjacent channels per thread
+template <typename T>
+__device__ __forceinline__ float2 ld2(const T* p);
+template <>
+__device__ __forceinline__ float2 ld2<float>(const float* p) { return *(const float2*)p; }
+template <>
+__device__ __forceinline__ float2 ld2<bf16>(const bf16* p) { return __bfloat1622float2(*(const __nv_bfloat162*)p); }
+template <typename T>
+__device__ __forceinline__ void st2(T* p, float2 v);
+template <>
+__device__ __forceinline__ void st2<float>(float* p, float2 v) { *(float2*)p = v; }
+template <>
+__device__ __forceinline__ void st2<bf16>(bf16* p, float2 v) { *(__nv_bfloat162*)p = __float22bfloat162_rn(v); }
+
+// Column-reduction geometry: blockDim = (32, 8); a thread owns channels 2*(blockIdx.y*32+tx)+{0,1};
+// row lanes ty stride over the block's row range.
+#define CR_TX 32
+#define CR_TY 8
+#define CR_CPB 64  // channels per block
+
+// reduce (a,b) float2 pairs across threadIdx.y; result valid on ty == 0
+__device__ __forceinline__ void block_reduce_y(float2& a, float2& b) {
+  __shared__ float2 sa[CR_TY][CR_TX], sb[CR_TY][CR_TX];
+  sa[threadIdx.y][threadIdx.x] = a;
+  sb[threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    for (int y = 1; y < CR_TY; ++y) {
+      float2 u = sa[y][threadIdx.x], v = sb[y][threadIdx.x];
+      a.x += u.x; a.y += u.y; b.x += v.x; b.y += v.y;
+    }
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------ BatchNorm
+template <typename T>
+__global__ void __launch_bounds__(256) bn_stats_k(const T* __restrict__ x, long long R, int C, long long rows_per_block,
+                                                  float* __restrict__ partial) {
+  const int c = 2 * (blockIdx.y * CR_TX + threadIdx.x);
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > R) r1 = R;
+  float2 s = {0.f, 0.f}, ss = {0.f, 0.f};
+  if (c < C) {
+    for (long long r = r0 + threadIdx.y; r < r1; r += CR_TY) {
+      float2 v = ld2<T>(x + r * C + c);
+      s.x += v.x; s.y += v.y;
+      ss.x = fmaf(v.x, v.x, ss.x); ss.y = fmaf(v.y, v.y, ss.y);
+    }
+  }
+  block_reduce_y(s, ss);
+  if (threadIdx.y == 0 && c < C) {
+    float* p0 = partial + ((long long)blockIdx.x * 2) * C + c;
+    p0[0] = s.x; p0[1] = s.y;
+    p0[C] = ss.x; p0[C + 1] = ss.y;
+  }
+}
+
+__global__ void bn_finalize_k(const float* __restrict__ partial, int nblk, long long R, int C,
+                              const float* __restrict__ gamma, const float* __restrict__ beta, float* running_mean,
+                              float* running_var, float momentum, float eps, float* __restrict__ scale,
+                              float* __restrict__ shift, float* save_mean, float* save_invstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mean, invstd;
+  if (nblk > 0) {
+    double s = 0.0, ss = 0.0;
+    for (int b = 0; b < nblk; ++b) {
+      s += (double)partial[((long long)b * 2) * C + c];
+      ss += (double)partial[((long long)b * 2 + 1) * C + c];
+    }
+    double m = s / (double)R;
+    double var = ss / (double)R - m * m;
+    if (var < 0.0) var = 0.0;
+    mean = (float)m;
+    invstd = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean) {
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      double unb = R > 1 ? var * (double)R / (double)(R - 1) : var;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+    }
+  } else {
+    mean = running_mean[c];
+    invstd = 1.0f / sqrtf(running_var[c] + eps);
+  }
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  const float sc = g * invstd;
+  scale[c] = sc;
+  shift[c] = b - mean * sc;
+  if (save_mean) { save_mean[c] = mean; save_invstd[c] = invstd; }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) affine_act_k(const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ y,
+                                                    long long n2, int C, const float* __restrict__ scale,
+                                                    const float* __restrict__ shift, int relu) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+    const long long e = i * 2;
+    const int c = (int)(e % C);
+    float2 v = ld2<T>(x + e);
+    v.x = fmaf(v.x, scale[c], shift[c]);
+    v.y = fmaf(v.y, scale[c + 1], shift[c + 1]);
+    if (res) {
+      float2 r = ld2<T>(res + e);
+      v.x += r.x; v.y += r.y;
+    }
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
+    st2<T>(y + e, v);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_k(const T* __restrict__ dy, const T* __restrict__ x,
+                                                       const T* __restrict__ y, long long R, int C,
+                                                       long long rows_per_block, const float* __restrict__ mean,
+                                                       const float* __restrict__ invstd, float* __restrict__ partial,
+                                                       int relu) {
+  const int c = 2 * (blockIdx.y * CR_TX + threadIdx.x);
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > R) r1 = R;
+  float2 s = {0.f, 0.f}, sx = {0.f, 0.f};
+  if (c < C) {
+    const float m0 = mean[c], m1 = mean[c + 1], i0 = invstd[c], i1 = invstd[c + 1];
+    for (long long r = r0 + threadIdx.y; r < r1; r += CR_TY) {
+      float2 g = ld2<T>(dy + r * C + c);
+      if (relu) {
+        float2 yy = ld2<T>(y + r * C + c);
+        if (!(yy.x > 0.f)) g.x = 0.f;
+        if (!(yy.y > 0.f)) g.y = 0.f;
+      }
+      float2 v = ld2<T>(x + r * C + c);
+      s.x += g.x; s.y += g.y;
+      sx.x = fmaf(g.x, (v.x - m0) * i0, sx.x);
+      sx.y = fmaf(g.y, (v.y - m1) * i1, sx.y);
+    }
+  }
+  block_reduce_y(s, sx);
+  if (threadIdx.y == 0 && c < C) {
+    float* p0 = partial + ((long long)blockIdx.x * 2) * C + c;
+    p0[0] = s.x; p0[1] = s.y;
+    p0[C] = sx.x; p0[C + 1] = sx.y;
+  }
+}
+
+__global__ void bn_bwd_finalize_k(const float* __restrict__ partial, int nblk, int C, float* __restrict__ dgamma,
+                                  float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, sx = 0.0;
+  for (int b = 0; b < nblk; ++b) {
+    s += (double)partial[((long long)b * 2) * C + c];
+    sx += (double)partial[((long long)b * 2 + 1) * C + c];
+  }
+  dbeta[c] = (float)s;
+  dgamma[c] = (float)sx;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_bwd_apply_k(const T* __restrict__ dy, const T* __restrict__ x,
+                                                      const T* __restrict__ y, const T* __restrict__ dadd,
+                                                      T* __restrict__ dx, T* __restrict__ dres, long long n2, long long R,
+                                                      int C, const float* __restrict__ gamma,
+                                                      const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                      const float* __restrict__ dgamma, const float* __restrict__ dbeta,
+                                                      const float* __restrict__ eval_scale, int relu) {
+  const float invR = 1.f / (float)R;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+    const long long e = i * 2;
+    const int c = (int)(e % C);
+    float2 g = ld2<T>(dy + e);
+    if (relu) {
+      float2 yy = ld2<T>(y + e);
+      if (!(yy.x > 0.f)) g.x = 0.f;
+      if (!(yy.y > 0.f)) g.y = 0.f;
+    }
+    if (dres) st2<T>(dres + e, g);
+    float2 o;
+    if (eval_scale) {
+      o.x = g.x * eval_scale[c];
+      o.y = g.y * eval_scale[c + 1];
+    } else {
+      float2 v = ld2<T>(x + e);
+      const float g0 = gamma ? gamma[c] : 1.f, g1 = gamma ? gamma[c + 1] : 1.f;
+      float xh0 = (v.x - mean[c]) * invstd[c], xh1 = (v.y - mean[c + 1]) * invstd[c + 1];
+      o.x = g0 * invstd[c] * (g.x - dbeta[c] * invR - xh0 * dgamma[c] * invR);
+      o.y = g1 * invstd[c + 1] * (g.y - dbeta[c + 1] * invR - xh1 * dgamma[c + 1] * invR);
+    }
+    if (dadd) {
+      float2 a = ld2<T>(dadd + e);
+      o.x += a.x; o.y += a.y;
+    }
+    st2<T>(dx + e, o);
+  }
+}
+
+static inline int ew_grid(long long n) {
+  long long g = (n + 255) / 256;
+  if (g > 148 * 32) g = 148 * 32;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+static inline int cr_plan(long long R, int max_blocks, long long* rows_per_block) {
+  int nblk = (int)((R + 255) / 256);  // >= 32 rows per row-lane
+  if (nblk > max_blocks) nblk = max_blocks;
+  if (nblk < 1) nblk = 1;
+  long long rpb = (R + nblk - 1) / nblk;
+  nblk = (int)((R + rpb - 1) / rpb);
+  *rows_per_block = rpb;
+  return nblk;
+}
+
+extern "C" int combat_bn_stats(const void* x, int dtype, long long R, int C, float* partial, int max_blocks,
+                               int* nblk_out_host, void* stream) {
+  COMBAT_ARG(x && partial && nblk_out_host, 0);
+  COMBAT_ARG(R > 0 && C > 0 && (C % 2) == 0 && max_blocks > 0, 2);
+  long long rpb;
+  int nblk = cr_plan(R, max_blocks, &rpb);
+  *nblk_out_host = nblk;
+  dim3 grid(nblk, cdiv(C, CR_CPB)), block(CR_TX, CR_TY);
+  DISPATCH_DTYPE(dtype, bn_stats_k<T><<<grid, block, 0, (cudaStream_t)stream>>>((const T*)x, R, C, rpb, partial);)
+  COMBAT_RETURN_LAUNCH("bn_stats");
+}
+
+extern "C" int combat_bn_finalize(const float* partial, int nblk, long long R, int C, const float* gamma, const float* beta,
+                                  float* running_mean, float* running_var, float momentum, float eps, float* scale,
+                                  float* shift, float* save_mean, float* save_invstd, void* stream) {
+  COMBAT_ARG(scale && shift, 10);
+  COMBAT_ARG(nblk > 0 ? partial != nullptr : (running_mean && running_var), 0);
+  bn_finalize_k<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(partial, nblk, R, C, gamma, beta, running_mean, running_var,
+                                                                momentum, eps, scale, shift, save_mean, save_invstd);
+  COMBAT_RETURN_LAUNCH("bn_finalize");
+}
+
+extern "C" int combat_affine_act(const void* x, const void* residual, void* y, int dtype, long long R, int C,
+                                 const float* scale, const float* shift, int relu, void* stream) {
+  COMBAT_ARG(x && y && scale && shift, 0);
+  COMBAT_ARG((C % 2) == 0, 5);
+  long long n2 = R * C / 2;
+  if (n2 <= 0) return 0;
+  DISPATCH_DTYPE(dtype, affine_act_k<T><<<ew_grid(n2), 256, 0, (cudaStream_t)stream>>>((const T*)x, (const T*)residual, (T*)y,
+                                                                                        n2, C, scale, shift, relu);)
+  COMBAT_RETURN_LAUNCH("affine_act");
+}
+
+extern "C" int combat_bn_bwd_reduce(const void* dy, const void* x, const void* y, int dtype, long long R, int C,
+                                    const float* mean, const float* invstd, float* partial, int max_blocks,
+                                    int* nblk_out_host, int relu, void* stream) {
+  COMBAT_ARG(dy && x && partial && mean && invstd && nblk_out_host, 0);
+  COMBAT_ARG(!relu || y, 2);
+  long long rpb;
+  int nblk = cr_plan(R, max_blocks, &rpb);
+  *nblk_out_host = nblk;
+  dim3 grid(nblk, cdiv(C, CR_CPB)), block(CR_TX, CR_TY);
+  DISPATCH_DTYPE(dtype, bn_bwd_reduce_k<T><<<grid, block, 0, (cudaStream_t)stream>>>((const T*)dy, (const T*)x, (const T*)y, R,
+                                                                                    C, rpb, mean, invstd, partial, relu);)
+  COMBAT_RETURN_LAUNCH("bn_bwd_reduce");
+}
+
+extern "C" int combat_bn_bwd_finalize(const float* partial, int nblk, int C, float* dgamma, float* dbeta, void* stream) {
+  COMBAT_ARG(partial && dgamma && dbeta && nblk > 0, 0);
+  bn_bwd_finalize_k<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(partial, nblk, C, dgamma, dbeta);
+  COMBAT_RETURN_LAUNCH("bn_bwd_finalize");
+}
+
+extern "C" int combat_bn_bwd_apply(const void* dy, const void* x, const void* y, const void* dadd, void* dx, void* dres,
+                                   int dtype, long long R, int C, const float* gamma, const float* mean,
+                                   const float* invstd, const float* dgamma, const float* dbeta, const float* eval_scale,
+                                   int relu, void* stream) {
+  COMBAT_ARG(dy && dx, 0);
+  COMBAT_ARG(eval_scale || (x && mean && invstd && dgamma && dbeta), 1);
+  COMBAT_ARG(!relu || y, 2);
+  long long n2 = R * C / 2;
+  if (n2 <= 0) return 0;
+  DISPATCH_DTYPE(dtype, bn_bwd_apply_k<T><<<ew_grid(n2), 256, 0, (cudaStream_t)stream>>>(
+                            (const T*)dy, (const T*)x, (const T*)y, (const T*)dadd, (T*)dx, (T*)dres, n2, R, C, gamma, mean,
+                            invstd, dgamma, dbeta, eval_scale, relu);)
+  COMBAT_RETURN_LAUNCH("bn_bwd_apply");
+}
+
+// ------------------------------------------------------------------ InstanceNorm + LeakyReLU (+ skip)
+// grid = (N, C/64), block (32, 8).  Three cached passes: mean, centred variance, apply.
+template <typename T>
+__global__ void __launch_bounds__(256) instnorm_fwd_k(const T* __restrict__ x, const T* __restrict__ skip, T* __restrict__ y,
+                                                      int HW, int C, float eps, float slope, int act,
+                                                      float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+  const int n = blockIdx.x;
+  const int c = 2 * (blockIdx.y * CR_TX + threadIdx.x);
+  const bool ok = c < C;
+  const long long base = (long long)n * HW * C + c;
+  float2 s = {0.f, 0.f}, dummy = {0.f, 0.f};
+  if (ok)
+    for (int r = threadIdx.y; r < HW; r += CR_TY) {
+      float2 v = ld2<T>(x + base + (long long)r * C);
+      s.x += v.x; s.y += v.y;
+    }
+  block_reduce_y(s, dummy);
+  __shared__ float2 bc[CR_TX], bi[CR_TX];
+  if (threadIdx.y == 0) bc[threadIdx.x] = make_float2(s.x / (float)HW, s.y / (float)HW);
+  __syncthreads();
+  const float2 mean = bc[threadIdx.x];
+  float2 q = {0.f, 0.f};
+  if (ok)
+    for (int r = threadIdx.y; r < HW; r += CR_TY) {
+      float2 v = ld2<T>(x + base + (long long)r * C);
+      float a = v.x - mean.x, b = v.y - mean.y;
+      q.x = fmaf(a, a, q.x); q.y = fmaf(b, b, q.y);
+    }
+  block_reduce_y(q, dummy);
+  if (threadIdx.y == 0) {
+    float2 iv = make_float2(1.0f / sqrtf(q.x / (float)HW + eps), 1.0f / sqrtf(q.y / (float)HW + eps));
+    bi[threadIdx.x] = iv;
+    if (ok) {
+      save_mean[(long long)n * C + c] = mean.x; save_mean[(long long)n * C + c + 1] = mean.y;
+      save_invstd[(long long)n * C + c] = iv.x; save_invstd[(long long)n * C + c + 1] = iv.y;
+    }
+  }
+  __syncthreads();
+  const float2 inv = bi[threadIdx.x];
+  if (ok)
+    for (int r = threadIdx.y; r < HW; r += CR_TY) {
+      const long long o = base + (long long)r * C;
+      float2 v = ld2<T>(x + o);
+      v.x = (v.x - mean.x) * inv.x;
+      v.y = (v.y - mean.y) * inv.y;
+      if (act) {
+        v.x = v.x > 0.f ? v.x : v.x * slope;
+        v.y = v.y > 0.f ? v.y : v.y * slope;
+      }
+      if (skip) {
+        float2 k = ld2<T>(skip + o);
+        v.x += k.x; v.y += k.y;
+      }
+      st2<T>(y + o, v);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) instnorm_bwd_k(const T* __restrict__ dy1, const T* __restrict__ dy2,
+                                                      const T* __restrict__ x, T* __restrict__ dx, int HW, int C,
+                                                      float slope, int act, const float* __restrict__ mean_,
+                                                      const float* __restrict__ invstd_) {
+  const int n = blockIdx.x;
+  const int c = 2 * (blockIdx.y * CR_TX + threadIdx.x);
+  const bool ok = c < C;
+  const long long base = (long long)n * HW * C + c;
+  float2 mean = {0.f, 0.f}, inv = {0.f, 0.f};
+  if (ok) {
+    mean = make_float2(mean_[(long long)n * C + c], mean_[(long long)n * C + c + 1]);
+    inv = make_float2(invstd_[(long long)n * C + c], invstd_[(long long)n * C + c + 1]);
+  }
+  float2 s = {0.f, 0.f}, sx = {0.f, 0.f};
+  if (ok)
+    for (int r = threadIdx.y; r < HW; r += CR_TY) {
+      const long long o = base + (long long)r * C;
+      float2 g = ld2<T>(dy1 + o);
+      if (dy2) { float2 g2 = ld2<T>(dy2 + o); g.x += g2.x; g.y += g2.y; }
+      float2 v = ld2<T>(x + o);
+      float xh0 = (v.x - mean.x) * inv.x, xh1 = (v.y - mean.y) * inv.y;
+      if (act) {
+        if (!(xh0 > 0.f)) g.x *= slope;
+        if (!(xh1 > 0.f)) g.y *= slope;
+      }
+      s.x += g.x; s.y += g.y;
+      sx.x = fmaf(g.x, xh0, sx.x); sx.y = fmaf(g.y, xh1, sx.y);
+    }
+  block_reduce_y(s, sx);
+  __shared__ float2 b0[CR_TX], b1[CR_TX];
+  if (threadIdx.y == 0) {
+    b0[threadIdx.x] = make_float2(s.x / (float)HW, s.y / (float)HW);
+    b1[threadIdx.x] = make_float2(sx.x / (float)HW, sx.y / (float)HW);
+  }
+  __syncthreads();
+  const float2 mg = b0[threadIdx.x], mgx = b1[threadIdx.x];
+  if (ok)
+    for (int r = threadIdx.y; r < HW; r += CR_TY) {
+      const long long o = base + (long long)r * C;
+      float2 g = ld2<T>(dy1 + o);
+      if (dy2) { float2 g2 = ld2<T>(dy2 + o); g.x += g2.x; g.y += g2.y; }
+      float2 v = ld2<T>(x + o);
+      float xh0 = (v.x - mean.x) * inv.x, xh1 = (v.y - mean.y) * inv.y;
+      if (act) {
+        if (!(xh0 > 0.f)) g.x *= slope;
+        if (!(xh1 > 0.f)) g.y *= slope;
+      }
+      float2 d;
+      d.x = inv.x * (g.x - mg.x - xh0 * mgx.x);
+      d.y = inv.y * (g.y - mg.y - xh1 * mgx.y);
+      st2<T>(dx + o, d);
+    }
+}
+
+extern "C" int combat_instnorm_fwd(const void* x, const void* skip, void* y, int dtype, int N, int HW, int C, float eps,
+                                   float slope, int act, float* save_mean, float* save_invstd, void* stream) {
+  COMBAT_ARG(x && y && save_mean && save_invstd, 0);
+  COMBAT_ARG(N > 0 && HW > 0 && C > 0 && (C % 2) == 0, 4);
+  dim3 grid(N, cdiv(C, CR_CPB)), block(CR_TX, CR_TY);
+  DISPATCH_DTYPE(dtype, instnorm_fwd_k<T><<<grid, block, 0, (cudaStream_t)stream>>>((const T*)x, (const T*)skip, (T*)y, HW, C,
+                                                                                   eps, slope, act, save_mean, save_invstd);)
+  COMBAT_RETURN_LAUNCH("instnorm_fwd");
+}
+
+extern "C" int combat_instnorm_bwd(const void* dy1, const void* dy2, const void* x, void* dx, int dtype, int N, int HW,
+                                   int C, float slope, int act, const float* mean, const float* invstd, void* stream) {
+  COMBAT_ARG(dy1 && x && dx && mean && invstd, 0);
+  COMBAT_ARG(N > 0 && HW > 0 && C > 0 && (C % 2) == 0, 5);
+  dim3 grid(N, cdiv(C, CR_CPB)), block(CR_TX, CR_TY);
+  DISPATCH_DTYPE(dtype, instnorm_bwd_k<T><<<grid, block, 0, (cudaStream_t)stream>>>((const T*)dy1, (const T*)dy2, (const T*)x,
+                                                                                   (T*)dx, HW, C, slope, act, mean, invstd);)
+  COMBAT_RETURN_LAUNCH("instnorm_bwd");
+}
+
+// ------------------------------------------------------------------ bilinear x2 upsample (+ LeakyReLU)
+__device__ __forceinline__ void up_src(int o, int n_in, int& i0, int& i1, float& l0, float& l1) {
+  // PyTorch area_pixel_compute_source_index, align_corners=False, scale 0.5
+  float r = 0.5f * ((float)o + 0.5f) - 0.5f;
+  if (r < 0.f) r = 0.f;
+  i0 = (int)r;
+  i1 = i0 + (i0 < n_in - 1 ? 1 : 0);
+  l1 = r - (float)i0;
+  l0 = 1.f - l1;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) upsample2x_act_k(const T* __restrict__ x, T* __restrict__ y, long long total2, int H,
+                                                        int W, int C, float slope) {
+  const int C2 = C / 2, Ho = 2 * H, Wo = 2 * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total2; i += (long long)gridDim.x * blockDim.x) {
+    const int c = 2 * (int)(i % C2);
+    long long p = i / C2;
+    const int ow = (int)(p % Wo);
+    p /= Wo;
+    const int oh = (int)(p % Ho);
+    const long long n = p / Ho;
+    int h0, h1, w0, w1;
+    float lh0, lh1, lw0, lw1;
+    up_src(oh, H, h0, h1, lh0, lh1);
+    up_src(ow, W, w0, w1, lw0, lw1);
+    const T* xb = x + n * H * W * C + c;
+    float2 a = ld2<T>(xb + ((long long)h0 * W + w0) * C), b = ld2<T>(xb + ((long long)h0 * W + w1) * C);
+    float2 cc = ld2<T>(xb + ((long long)h1 * W + w0) * C), d = ld2<T>(xb + ((long long)h1 * W + w1) * C);
+    float2 v;
+    v.x = lh0 * (lw0 * a.x + lw1 * b.x) + lh1 * (lw0 * cc.x + lw1 * d.x);
+    v.y = lh0 * (lw0 * a.y + lw1 * b.y) + lh1 * (lw0 * cc.y + lw1 * d.y);
+    v.x = v.x > 0.f ? v.x : v.x * slope;
+    v.y = v.y > 0.f ? v.y : v.y * slope;
+    st2<T>(y + i * 2, v);
+  }
+}
+
+// weight with which input index `i` enters output index `o` (0 if not referenced)
+__device__ __forceinline__ float up_w(int o, int i, int n_in) {
+  int i0, i1;
+  float l0, l1;
+  up_src(o, n_in, i0, i1, l0, l1);
+  float w = 0.f;
+  if (i0 == i) w += l0;
+  if (i1 == i) w += l1;
+  return w;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) upsample2x_act_bwd_k(const T* __restrict__ dy, const T* __restrict__ y,
+                                                            T* __restrict__ dx, long long total2, int H, int W, int C,
+                                                            float slope) {
+  const int C2 = C / 2, Ho = 2 * H, Wo = 2 * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total2; i += (long long)gridDim.x * blockDim.x) {
+    const int c = 2 * (int)(i % C2);
+    long long p = i / C2;
+    const int w = (int)(p % W);
+    p /= W;
+    const int h = (int)(p % H);
+    const long long n = p / H;
+    float2 acc = {0.f, 0.f};
+    for (int oh = 2 * h - 1; oh <= 2 * h + 2; ++oh) {
+      if (oh < 0 || oh >= Ho) continue;
+      const float wh = up_w(oh, h, H);
+      if (wh == 0.f) continue;
+      for (int ow = 2 * w - 1; ow <= 2 * w + 2; ++ow) {
+        if (ow < 0 || ow >= Wo) continue;
+        const float ww = up_w(ow, w, W);
+        if (ww == 0.f) continue;
+        const long long o = ((n * Ho + oh) * Wo + ow) * C + c;
+        float2 g = ld2<T>(dy + o);
+        if (slope != 1.f) {
+          float2 yy = ld2<T>(y + o);
+          if (!(yy.x > 0.f)) g.x *= slope;
+          if (!(yy.y > 0.f)) g.y *= slope;
+        }
+        acc.x = fmaf(wh * ww, g.x, acc.x);
+        acc.y = fmaf(wh * ww, g.y, acc.y);
+      }
+    }
+    st2<T>(dx + i * 2, acc);
+  }
+}
+
+extern "C" int combat_upsample2x_act(const void* x, void* y, int dtype, int N, int H, int W, int C, float slope,
+                                     void* stream) {
+  COMBAT_ARG(x && y && (C % 2) == 0, 0);
+  long long total2 = (long long)N * 4 * H * W * C / 2;
+  if (total2 <= 0) return 0;
+  DISPATCH_DTYPE(dtype, upsample2x_act_k<T><<<ew_grid(total2), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, total2, H, W,
+                                                                                              C, slope);)
+  COMBAT_RETURN_LAUNCH("upsample2x_act");
+}
+
+extern "C" int combat_upsample2x_act_bwd(const void* dy, const void* y, void* dx, int dtype, int N, int H, int W, int C,
+                                         float slope, void* stream) {
+  COMBAT_ARG(dy && dx && (C % 2) == 0, 0);
+  COMBAT_ARG(slope == 1.f || y, 1);
+  long long total2 = (long long)N * H * W * C / 2;
+  if (total2 <= 0) return 0;
+  DISPATCH_DTYPE(dtype, upsample2x_act_bwd_k<T><<<ew_grid(total2), 256, 0, (cudaStream_t)stream>>>(
+                            (const T*)dy, (const T*)y, (T*)dx, total2, H, W, C, slope);)
+  COMBAT_RETURN_LAUNCH("upsample2x_act_bwd");
+}
+
+// ------------------------------------------------------------------ elementwise
+template <typename T>
+__global__ void __launch_bounds__(256) leaky_relu_k(const T* __restrict__ x, T* __restrict__ y, long long n, float slope) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = to_f<T>(x[i]);
+    y[i] = from_f<T>(v > 0.f ? v : v * slope);
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) leaky_relu_bwd_k(const T* __restrict__ dy, const T* __restrict__ x, T* __restrict__ dx,
+                                                        long long n, float slope) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float g = to_f<T>(dy[i]);
+    dx[i] = from_f<T>(to_f<T>(x[i]) > 0.f ? g : g * slope);
+  }
+}
+__global__ void __launch_bounds__(256) tanh_bwd_k(const float* __restrict__ dy, const float* __restrict__ y,
+                                                  float* __restrict__ dz, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float t = y[i];
+    dz[i] = dy[i] * (1.f - t * t);
+  }
+}
+
+extern "C" int combat_leaky_relu(const void* x, void* y, int dtype, long long n, float slope, void* stream) {
+  COMBAT_ARG(x && y, 0);
+  if (n <= 0) return 0;
+  DISPATCH_DTYPE(dtype, leaky_relu_k<T><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, n, slope);)
+  COMBAT_RETURN_LAUNCH("leaky_relu");
+}
+extern "C" int combat_leaky_relu_bwd(const void* dy, const void* x, void* dx, int dtype, long long n, float slope,
+                                     void* stream) {
+  COMBAT_ARG(dy && x && dx, 0);
+  if (n <= 0) return 0;
+  DISPATCH_DTYPE(dtype,
+                 leaky_relu_bwd_k<T><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>((const T*)dy, (const T*)x, (T*)dx, n, slope);)
+  COMBAT_RETURN_LAUNCH("leaky_relu_bwd");
+}
+extern "C" int combat_tanh_bwd(const float* dy, const float* y, float* dz, long long n, void* stream) {
+  COMBAT_ARG(dy && y && dz, 0);
+  if (n <= 0) return 0;
+  tanh_bwd_k<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(dy, y, dz, n);
+  COMBAT_RETURN_LAUNCH("tanh_bwd");
+}
+
+// column sums (conv bias gradient): one block column per 64 channels, all rows; accumulate flag
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_k(const T* __restrict__ x, long long R, int C, long long rows_per_block,
+                                                float* __restrict__ out) {
+  const int c = 2 * (blockIdx.y * CR_TX + threadIdx.x);
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > R) r1 = R;
+  float2 s = {0.f, 0.f}, dummy = {0.f, 0.f};
+  if (c < C)
+    for (long long r = r0 + threadIdx.y; r < r1; r += CR_TY) {
+      float2 v = ld2<T>(x + r * C + c);
+      s.x += v.x; s.y += v.y;
+    }
+  block_reduce_y(s, dummy);
+  if (threadIdx.y == 0 && c < C) {
+    atomicAdd(out + c, s.x);
+    atomicAdd(out + c + 1, s.y);
+  }
+}
+extern "C" int combat_colsum(const void* x, int dtype, long long R, int C, float* out, void* stream) {
+  COMBAT_ARG(x && out && (C % 2) == 0, 0);
+  long long rpb;
+  int nblk = cr_plan(R, 128, &rpb);
+  dim3 grid(nblk, cdiv(C, CR_CPB)), block(CR_TX, CR_TY);
+  DISPATCH_DTYPE(dtype, colsum_k<T><<<grid, block, 0, (cudaStream_t)stream>>>((const T*)x, R, C, rpb, out);)
+  COMBAT_RETURN_LAUNCH("colsum");
+}
+
+// ------------------------------------------------------------------ avg_pool(P) + flatten + linear
+// one CTA per sample.  feature index f = c*(ph*pw) + hp*pw + wp (NCHW flatten order of the reference)
+template <typename T>
+__global__ void __launch_bounds__(256) pool_linear_fwd_k(const T* __restrict__ x, int Hf, int Wf, int C, int P,
+                                                         const float* __restrict__ Wt, const float* __restrict__ bias,
+                                                         int ncls, float* __restrict__ pooled, float* __restrict__ logits) {
+  extern __shared__ float feat[];  // F
+  const int b = blockIdx.x;
+  const int ph = Hf / P, pw = Wf / P, F = C * ph * pw;
+  const float inv = 1.f / (float)(P * P);
+  const T* xb = x + (long long)b * Hf * Wf * C;
+  for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    // iterate f in an order where consecutive threads take consecutive channels
+    const int c = f % C, cell = f / C;
+    const int hp = cell / pw, wp = cell % pw;
+    float s = 0.f;
+    for (int i = 0; i < P; ++i)
+      for (int j = 0; j < P; ++j) s += to_f<T>(xb[((long long)(hp * P + i) * Wf + (wp * P + j)) * C + c]);
+    const int fi = c * (ph * pw) + cell;
+    float v = s * inv;
+    feat[fi] = v;
+    pooled[(long long)b * F + fi] = v;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int k = warp; k < ncls; k += nwarp) {
+    float s = 0.f;
+    for (int f = lane; f < F; f += 32) s = fmaf(Wt[(long long)k * F + f], feat[f], s);
+    s = warp_sum(s);
+    if (lane == 0) logits[(long long)b * ncls + k] = s + bias[k];
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) pool_linear_bwd_dx_k(const float* __restrict__ dlogits, const float* __restrict__ Wt,
+                                                            int Hf, int Wf, int C, int P, int ncls, T* __restrict__ dx) {
+  extern __shared__ float dfeat[];  // F
+  __shared__ float dl[64];
+  const int b = blockIdx.x;
+  const int ph = Hf / P, pw = Wf / P, F = C * ph * pw;
+  if ((int)threadIdx.x < ncls) dl[threadIdx.x] = dlogits[(long long)b * ncls + threadIdx.x];
+  __syncthreads();
+  const float inv = 1.f / (float)(P * P);
+  for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < ncls; ++k) s = fmaf(dl[k], Wt[(long long)k * F + f], s);
+    dfeat[f] = s * inv;
+  }
+  __syncthreads();
+  T* xb = dx + (long long)b * Hf * Wf * C;
+  const int tot = Hf * Wf * C;
+  for (int e = threadIdx.x; e < tot; e += blockDim.x) {
+    const int c = e % C, pix = e / C;
+    const int h = pix / Wf, w = pix % Wf;
+    const int hp = h / P, wp = w / P;
+    float v = (hp < ph && wp < pw) ? dfeat[c * (ph * pw) + hp * pw + wp] : 0.f;
+    xb[e] = from_f<T>(v);
+  }
+}
+
+// dW[k][f] = sum_b dlogits[b][k] * pooled[b][f]; db[k] = sum_b dlogits[b][k]
+__global__ void __launch_bounds__(256) linear_wgrad_k(const float* __restrict__ dlogits, const float* __restrict__ pooled,
+                                                      int B, int F, int ncls, float* __restrict__ dW, float* __restrict__ db) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y;
+  if (f < F) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s = fmaf(dlogits[(long long)b * ncls + k], pooled[(long long)b * F + f], s);
+    dW[(long long)k * F + f] = s;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += dlogits[(long long)b * ncls + k];
+    db[k] = s;
+  }
+}
+
+extern "C" int combat_pool_linear_fwd(const void* x, int dtype, int B, int Hf, int Wf, int C, int P, const float* W,
+                                      const float* b, int ncls, float* pooled, float* logits, void* stream) {
+  COMBAT_ARG(x && W && b && pooled && logits, 0);
+  COMBAT_ARG(P > 0 && Hf >= P && Wf >= P, 6);
+  int F = C * (Hf / P) * (Wf / P);
+  size_t smem = (size_t)F * sizeof(float);
+  COMBAT_ARG(smem <= 200 * 1024, 5);
+  DISPATCH_DTYPE(dtype, {
+    cudaFuncSetAttribute(pool_linear_fwd_k<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    pool_linear_fwd_k<T><<<B, 256, smem, (cudaStream_t)stream>>>((const T*)x, Hf, Wf, C, P, W, b, ncls, pooled, logits);
+  })
+  COMBAT_RETURN_LAUNCH("pool_linear_fwd");
+}
+
+extern "C" int combat_pool_linear_bwd(const float* dlogits, const float* pooled, const float* W, int B, int Hf, int Wf,
+                                      int C, int P, int ncls, void* dx, int dtype, float* dW, float* db, void* stream) {
+  COMBAT_ARG(dlogits && W, 0);
+  COMBAT_ARG(ncls <= 64, 8);
+  int F = C * (Hf / P) * (Wf / P);
+  size_t smem = (size_t)F * sizeof(float);
+  if (dx) {
+    DISPATCH_DTYPE(dtype, {
+      cudaFuncSetAttribute(pool_linear_bwd_dx_k<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      pool_linear_bwd_dx_k<T><<<B, 256, smem, (cudaStream_t)stream>>>(dlogits, W, Hf, Wf, C, P, ncls, (T*)dx);
+    })
+    COMBAT_CHECK_LAUNCH("pool_linear_bwd_dx");
+  }
+  if (dW) {
+    COMBAT_ARG(pooled && db, 1);
+    dim3 grid(cdiv(F, 256), ncls);
+    linear_wgrad_k<<<grid, 256, 0, (cudaStream_t)stream>>>(dlogits, pooled, B, F, ncls, dW, db);
+    COMBAT_CHECK_LAUNCH("linear_wgrad");
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ maxpool 2x2, layout conversion, one-hot planes
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool2_k(const T* __restrict__ x, T* __restrict__ y, long long total, int H, int W,
+                                                  int C) {
+  const int Ho = H / 2, Wo = W / 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long p = i / C;
+    const int ow = (int)(p % Wo);
+    p /= Wo;
+    const int oh = (int)(p % Ho);
+    const long long n = p / Ho;
+    const T* xb = x + ((n * H + 2 * oh) * W + 2 * ow) * C + c;
+    float m = fmaxf(fmaxf(to_f<T>(xb[0]), to_f<T>(xb[C])), fmaxf(to_f<T>(xb[(long long)W * C]), to_f<T>(xb[(long long)W * C + C])));
+    y[i] = from_f<T>(m);
+  }
+}
+extern "C" int combat_maxpool2(const void* x, void* y, int dtype, int N, int H, int W, int C, void* stream) {
+  COMBAT_ARG(x && y, 0);
+  long long total = (long long)N * (H / 2) * (W / 2) * C;
+  if (total <= 0) return 0;
+  DISPATCH_DTYPE(dtype, maxpool2_k<T><<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, total, H, W, C);)
+  COMBAT_RETURN_LAUNCH("maxpool2");
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) nchw_to_nhwc_k(const float* __restrict__ x, T* __restrict__ y, long long total, int C,
+                                                      int HW) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long p = i / C;
+    const int hw = (int)(p % HW);
+    const long long n = p / HW;
+    y[i] = from_f<T>(x[(n * C + c) * HW + hw]);
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) nhwc_to_nchw_k(const T* __restrict__ x, float* __restrict__ y, long long total, int C,
+                                                      int HW) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int hw = (int)(i % HW);
+    long long p = i / HW;
+    const int c = (int)(p % C);
+    const long long n = p / C;
+    y[i] = to_f<T>(x[(n * HW + hw) * C + c]);
+  }
+}
+extern "C" int combat_nchw_to_nhwc(const float* x, void* y, int dtype, int N, int C, int H, int W, void* stream) {
+  COMBAT_ARG(x && y, 0);
+  long long total = (long long)N * C * H * W;
+  if (total <= 0) return 0;
+  DISPATCH_DTYPE(dtype, nchw_to_nhwc_k<T><<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(x, (T*)y, total, C, H * W);)
+  COMBAT_RETURN_LAUNCH("nchw_to_nhwc");
+}
+extern "C" int combat_nhwc_to_nchw(const void* x, int dtype, float* y, int N, int C, int H, int W, void* stream) {
+  COMBAT_ARG(x && y, 0);
+  long long total = (long long)N * C * H * W;
+  if (total <= 0) return 0;
+  DISPATCH_DTYPE(dtype, nhwc_to_nchw_k<T><<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>((const T*)x, y, total, C, H * W);)
+  COMBAT_RETURN_LAUNCH("nhwc_to_nchw");
+}
+
+// writes one-hot(label) planes into channels [c_off, c_off+ncls) of an NHWC tensor with Ctot channels
+template <typename T>
+__global__ void __launch_bounds__(256) onehot_planes_k(T* __restrict__ y, const long long* __restrict__ labels, long long total,
+                                                       int HW, int Ctot, int c_off, int ncls) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % ncls);
+    const long long pix = i / ncls;
+    const long long n = pix / HW;
+    y[pix * Ctot + c_off + k] = from_f<T>(labels[n] == k ? 1.f : 0.f);
+  }
+}
+extern "C" int combat_onehot_planes(void* y, int dtype, const long long* labels, int N, int HW, int Ctot, int c_off,
+                                    int ncls, void* stream) {
+  COMBAT_ARG(y && labels, 0);
+  long long total = (long long)N * HW * ncls;
+  if (total <= 0) return 0;
+  DISPATCH_DTYPE(dtype, onehot_planes_k<T><<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>((T*)y, labels, total, HW, Ctot,
+                                                                                            c_off, ncls);)
+  COMBAT_RETURN_LAUNCH("onehot_planes");
+}
+
+// dst[pix, c_off + c] = leaky_relu(src[pix, c]) for c < Csrc: writes an activated copy into a channel slice of a wider
+// NHWC tensor (CUnetGeneratorv1 concatenation, networks/models.py:524-531)
+template <typename T>
+__global__ void __launch_bounds__(256) lrelu_into_slice_k(const T* __restrict__ src, T* __restrict__ dst, long long total,
+                                                          int Csrc, int Cdst, int c_off, float slope) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Csrc);
+    const long long pix = i / Csrc;
+    float v = to_f<T>(src[i]);
+    dst[pix * Cdst + c_off + c] = from_f<T>(v > 0.f ? v : v * slope);
+  }
+}
+extern "C" int combat_lrelu_into_slice(const void* src, void* dst, int dtype, long long npix, int Csrc, int Cdst, int c_off,
+                                       float slope, void* stream) {
+  COMBAT_ARG(src && dst && c_off + Csrc <= Cdst, 0);
+  long long total = npix * Csrc;
+  if (total <= 0) return 0;
+  DISPATCH_DTYPE(dtype, lrelu_into_slice_k<T><<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>((const T*)src, (T*)dst, total,
+                                                                                               Csrc, Cdst, c_off, slope);)
+  COMBAT_RETURN_LAUNCH("lrelu_into_slice");
+}

@@ -1,0 +1,281 @@
+"""The alternated generator / surrogate training step (train_generator.py:170-255 of the reference) as an
+explicit schedule of sm_100a kernel launches -- CUDA-graph capturable, data-parallel ready.
+
+Schedule ("strictly needed" column; verified bit-identical to the reference on CPU):
+  * the generator runs ONCE per iteration on the full batch; the C-step's poisoned rows are gathered from that
+    result (same weights, same inputs as the reference's separate `netG(inputs_toChange)` call, and
+    InstanceNorm is per-sample);
+  * the C-step does not back-propagate into the generator (the reference zeroes those gradients at :220);
+  * the G-step back-propagates through netC and clean_model with input gradients only.
+Everything observable by the reference's train() -- losses, the six accuracy counters, parameter and
+BatchNorm-buffer updates -- is produced.
+
+RNG parity: one `np.random.rand(n_trg)` for the poison count, one torch CPU uniform for
+the C-step blur sigma (only when num_bd > 0), one for the G-step sigma -- all drawn on the host in `plan()`
+from the HOST copy of the labels, so the device never has to sync.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from . import ops
+from .nets import Classifier, FrequencyDetector, Generator
+
+
+def default_opt(**kw):
+    """Hot-path flags with the defaults of the reference's config.py:4-86."""
+    o = SimpleNamespace(
+        dataset="cifar10", input_height=32, input_width=32, input_channel=3, num_classes=10, attack_mode="all2one",
+        noise_rate=0.08, target_label=0, pc=0.5, ratio=0.65, kernel_size=3, sigma=(0.1, 1.0), L2_weight=0.02,
+        clean_model_weight=0.8, lr_C=1e-2, lr_G=1e-2, bs=128,
+    )
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+@dataclass
+class StepPlan:
+    """Host-side, per-iteration decisions (integer selection + RNG draws)."""
+    perm: np.ndarray          # int32 [B]: batch order of total_inputs = cat(trg_ind, ntrg_ind)
+    num_bd: int
+    trg_ind: np.ndarray
+    ntrg_ind: np.ndarray
+    bd_targets: np.ndarray    # int64 [B]
+    total_targets: np.ndarray  # int64 [B]
+    sigma_c: float | None
+    sigma_g: float
+    taps_c: tuple
+    taps_g: tuple
+
+
+def create_targets_bd_np(targets: np.ndarray, opt) -> np.ndarray:
+    """train_generator.py:70-77."""
+    if opt.attack_mode == "all2one":
+        return np.ones_like(targets) * opt.target_label
+    if opt.attack_mode == "all2all":
+        return (targets + 1) % opt.num_classes
+    raise Exception("{} attack mode is not implemented".format(opt.attack_mode))
+
+
+def make_plan(targets_host, opt) -> StepPlan:
+    """train_generator.py:173,181-183,193-194,226 -- consumes the numpy global RNG and the torch CPU generator in
+    the reference's order."""
+    y = np.asarray(targets_host, dtype=np.int64)
+    bd = create_targets_bd_np(y, opt).astype(np.int64)
+    trg = np.nonzero(y == bd)[0]
+    ntrg = np.nonzero(y != bd)[0]
+    num_bd = int(np.sum(np.random.rand(trg.shape[0]) < opt.pc))
+    sigma_c = None
+    taps_c = (1.0, 0.0)
+    if num_bd > 0:
+        sigma_c = torch.empty(1).uniform_(opt.sigma[0], opt.sigma[1]).item()
+        taps_c = ops.gaussian_taps(sigma_c)
+    sigma_g = torch.empty(1).uniform_(opt.sigma[0], opt.sigma[1]).item()
+    perm = np.concatenate([trg, ntrg]).astype(np.int32)
+    total_y = np.concatenate([bd[trg[:num_bd]], y[trg[num_bd:]], y[ntrg]]).astype(np.int64)
+    return StepPlan(perm, num_bd, trg, ntrg, bd, total_y, sigma_c, sigma_g, taps_c, ops.gaussian_taps(sigma_g))
+
+
+class AlternatedStep:
+    """Owns netC / clean_model / netG / netF and runs alternated iterations on one GPU.
+
+    `step(x, y, plan)` launches everything on the current stream and returns device scalars; with
+    `use_graph=True` the launches of the first call are captured and later iterations replay the graph after
+    refreshing the small per-iteration parameter block (perm, targets, num_bd, blur taps, learning rates)."""
+
+    def __init__(self, opt=None, device="cuda", dtype=torch.bfloat16, classifier="preact_resnet18", with_metrics=True,
+                 use_tc=True, cond_classes=0, grad_hook=None):
+        self.opt = opt or default_opt()
+        o = self.opt
+        self.device = torch.device(device)
+        self.dtype = dtype
+        self.with_metrics = with_metrics
+        H = o.input_height
+        mk = dict(device=self.device, dtype=dtype, use_tc=use_tc)
+        self.netC = Classifier(classifier, o.num_classes, o.input_channel, H, **mk)
+        self.clean = Classifier(classifier, o.num_classes, o.input_channel, H, **mk)
+        self.netG = Generator(o.input_channel, 64, cond_classes, **mk)
+        self.netF = FrequencyDetector(2, o.input_channel, H, device=self.device) if (with_metrics and H in (32, 64)) else None
+        self.keep = int(H * o.ratio)
+        self.lr_C = torch.full((1,), float(o.lr_C), dtype=torch.float32, device=self.device)
+        self.lr_G = torch.full((1,), float(o.lr_G), dtype=torch.float32, device=self.device)
+        self.grad_hook = grad_hook  # callable(net_name, flat_grad_tensor): data-parallel all-reduce
+        self._bufs = None
+        self._graph = None
+
+    # ------------------------------------------------------------ state
+    def load_state(self, netC=None, clean=None, netG=None, netF=None):
+        dev = self.device
+
+        def mv(sd):
+            return {k: v.to(dev) for k, v in sd.items()}
+
+        if netC is not None:
+            self.netC.load_state_dict(mv(netC))
+        if clean is not None:
+            self.clean.load_state_dict(mv(clean))
+        if netG is not None:
+            self.netG.load_state_dict(mv(netG))
+        if netF is not None and self.netF is not None:
+            self.netF.load_state_dict(mv(netF))
+
+    def set_lr(self, lr_C=None, lr_G=None):
+        if lr_C is not None:
+            self.lr_C.fill_(float(lr_C))
+        if lr_G is not None:
+            self.lr_G.fill_(float(lr_G))
+
+    # ------------------------------------------------------------ per-iteration device parameter block
+    def _ensure_bufs(self, B):
+        if self._bufs is not None and self._bufs["B"] == B:
+            return self._bufs
+        dev = self.device
+        o = self.opt
+        b = {"B": B}
+        b["x"] = torch.empty((B, o.input_channel, o.input_height, o.input_width), dtype=torch.float32, device=dev)
+        b["y"] = torch.empty(B, dtype=torch.int64, device=dev)
+        b["bd_targets"] = torch.empty(B, dtype=torch.int64, device=dev)
+        b["total_y"] = torch.empty(B, dtype=torch.int64, device=dev)
+        b["perm"] = torch.empty(B, dtype=torch.int32, device=dev)
+        b["num_bd"] = torch.zeros(1, dtype=torch.int32, device=dev)
+        b["taps_c"] = torch.zeros(2, dtype=torch.float32, device=dev)
+        b["taps_g"] = torch.zeros(2, dtype=torch.float32, device=dev)
+        b["ones"] = torch.ones(B, dtype=torch.int64, device=dev)
+        b["sq_partial"] = torch.empty(B * o.input_channel, dtype=torch.float32, device=dev)
+        b["losses"] = torch.zeros(8, dtype=torch.float32, device=dev)   # loss_c, loss_ce, loss_l2, clean_model_loss
+        b["counts"] = torch.zeros(16, dtype=torch.int32, device=dev)
+        # pinned staging for the tiny parameter block
+        b["h_i64"] = torch.empty((3, B), dtype=torch.int64).pin_memory()
+        b["h_perm"] = torch.empty(B, dtype=torch.int32).pin_memory()
+        b["h_small"] = torch.empty(8, dtype=torch.float32).pin_memory()
+        b["h_nbd"] = torch.empty(1, dtype=torch.int32).pin_memory()
+        self._bufs = b
+        self._graph = None
+        return b
+
+    def upload_plan(self, y_host, plan: StepPlan):
+        """async H2D of labels + the per-iteration parameter block (a few KB)."""
+        B = len(plan.perm)
+        b = self._ensure_bufs(B)
+        b["h_i64"][0].copy_(torch.as_tensor(np.asarray(y_host, dtype=np.int64)))
+        b["h_i64"][1].copy_(torch.from_numpy(plan.bd_targets))
+        b["h_i64"][2].copy_(torch.from_numpy(plan.total_targets))
+        b["h_perm"].copy_(torch.from_numpy(plan.perm))
+        b["h_small"][0], b["h_small"][1] = plan.taps_c
+        b["h_small"][2], b["h_small"][3] = plan.taps_g
+        b["h_nbd"][0] = plan.num_bd
+        b["y"].copy_(b["h_i64"][0], non_blocking=True)
+        b["bd_targets"].copy_(b["h_i64"][1], non_blocking=True)
+        b["total_y"].copy_(b["h_i64"][2], non_blocking=True)
+        b["perm"].copy_(b["h_perm"], non_blocking=True)
+        b["taps_c"].copy_(b["h_small"][0:2], non_blocking=True)
+        b["taps_g"].copy_(b["h_small"][2:4], non_blocking=True)
+        b["num_bd"].copy_(b["h_nbd"], non_blocking=True)
+
+    # ------------------------------------------------------------ the step
+    def _launch(self, b, keep_debug=False):
+        o = self.opt
+        x, y = b["x"], b["y"]
+        B = b["B"]
+        losses, counts = b["losses"], b["counts"]
+        dbg = {} if keep_debug else None
+        numel = x.numel()
+
+        # generator forward, once (train_generator.py:189 and :223)
+        noise_raw, ctxG = self.netG.forward(x, b.get("labels_g"), save=True)
+        noise = ops.plane_op(noise_raw, "lowfreq", keep=self.keep)                          # :190-191 / :224
+
+        # ---------------- C-step (:176-212)
+        total_x = ops.poison_blend_fwd(x, noise, b["perm"], 0, o.noise_rate, None, taps_dev=b["taps_c"],
+                                       num_bd_dev=b["num_bd"])                                # :192-195
+        logits_c, ctxC = self.netC.forward(total_x, train=True, save=True)                   # :205
+        _, dlog, _ = ops.cross_entropy(logits_c, b["total_y"], 1.0, True, loss_out=losses[0:1], counts_out=counts[0:2])
+        self.netC.zero_grad()                                                                # :179
+        self.netC.backward(ctxC, dlog, need_wgrad=True, need_dx=False)                       # :211
+        if self.grad_hook is not None:
+            self.grad_hook("netC", self.netC.store.grad)
+        self.netC.sgd_step(self.lr_C)                                                        # :212
+        del ctxC
+        if self.with_metrics:
+            clean_preds, _ = self.clean.forward(x, train=False, save=False)                  # :214
+            ops.cross_entropy(clean_preds, y, 1.0, False, loss_out=losses[4:5], counts_out=counts[2:4])
+
+        # ---------------- G-step (:217-255)
+        x_bd = ops.poison_blend_fwd(x, noise, None, B, o.noise_rate, None, sq_partial=b["sq_partial"],
+                                    taps_dev=b["taps_g"])                                     # :225-226
+        ops.sum_scale(b["sq_partial"], 1.0 / numel, out=losses[2:3])                         # :234
+        if self.with_metrics:
+            pred_clean, _ = self.netC.forward(x, train=False, save=False)                    # :227
+            ops.cross_entropy(pred_clean, y, 1.0, False, loss_out=losses[5:6], counts_out=counts[4:6])
+        pred_bd, ctxB = self.netC.forward(x_bd, train=False, save=True)                      # :228
+        _, dl1, _ = ops.cross_entropy(pred_bd, b["bd_targets"], 1.0, True, loss_out=losses[1:2], counts_out=counts[6:8])
+        g1 = self.netC.backward(ctxB, dl1, need_wgrad=False, need_dx=True)
+        del ctxB
+        cm_preds, ctxK = self.clean.forward(x_bd, train=False, save=True)                    # :250
+        _, dl2, _ = ops.cross_entropy(cm_preds, y, o.clean_model_weight, True, targets2=b["bd_targets"],
+                                      loss_out=losses[3:4], counts_out=counts[8:10])          # :251,266-267
+        g2 = self.clean.backward(ctxK, dl2, need_wgrad=False, need_dx=True)
+        del ctxK
+        dnoise = ops.poison_blend_bwd(x, noise, x_bd, g1, g2, 2.0 * o.L2_weight / numel, o.noise_rate, None,
+                                      taps_dev=b["taps_g"])
+        dnoise_raw = ops.plane_op(dnoise, "lowfreq", keep=self.keep)                          # P is symmetric
+        self.netG.zero_grad()                                                                # :220
+        self.netG.backward(ctxG, dnoise_raw)                                                 # :254
+        if self.grad_hook is not None:
+            self.grad_hook("netG", self.netG.store.grad)
+        self.netG.sgd_step(self.lr_G)                                                        # :255
+        if self.with_metrics and self.netF is not None:
+            inputs_F = ops.plane_op(x_bd, "dct", in_mode=2)                                   # :245
+            pred_F = self.netF.forward(inputs_F)                                              # :247
+            ops.cross_entropy(pred_F, b["ones"], 1.0, False, loss_out=losses[6:7], counts_out=counts[10:12])
+            if dbg is not None:
+                dbg.update(inputs_F=inputs_F, pred_F=pred_F)
+        if dbg is not None:
+            dbg.update(noise_raw=noise_raw, noise=noise, total_x=total_x, logits_c=logits_c, x_bd=x_bd, pred_bd=pred_bd,
+                       clean_model_preds=cm_preds, g1=g1, g2=g2, dnoise=dnoise)
+            if self.with_metrics:
+                dbg.update(clean_preds=clean_preds, pred_clean=pred_clean)
+        return dbg
+
+    def step(self, x_dev, y_host, plan: StepPlan | None = None, use_graph=False, keep_debug=False):
+        """One alternated iteration.  x_dev: float32 NCHW tensor already on the device (or a pinned host tensor,
+        which is copied asynchronously); y_host: host labels.  Returns {'losses': dev[8], 'counts': dev[16]}."""
+        if plan is None:
+            plan = make_plan(y_host, self.opt)
+        B = len(plan.perm)
+        b = self._ensure_bufs(B)
+        b["x"].copy_(x_dev, non_blocking=True)
+        self.upload_plan(y_host, plan)
+        dbg = None
+        if use_graph and not keep_debug:
+            if self._graph is None:
+                # warm-up launch outside capture (allocator pools, function attributes, first-step SGD), then capture
+                self._launch(b)
+                torch.cuda.current_stream().synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._launch(b)
+                self._graph = g
+            else:
+                self._graph.replay()
+        else:
+            dbg = self._launch(b, keep_debug)
+        out = {"losses": b["losses"], "counts": b["counts"], "plan": plan}
+        if dbg is not None:
+            out["debug"] = dbg
+        return out
+
+    @staticmethod
+    def unpack(out) -> dict:
+        """One D2H read of the step's scalars (call sparingly)."""
+        l = out["losses"].cpu().numpy()
+        c = out["counts"].cpu().numpy()
+        return dict(loss_c=float(l[0]), loss_ce=float(l[1]), loss_l2=float(l[2]), clean_model_loss=float(l[3]),
+                    n_total_correct=int(c[0]), n_clean_model_correct=int(c[2]), n_clean_correct=int(c[4]),
+                    n_bd_correct=int(c[6]), n_clean_model_bd_ba=int(c[8]), n_clean_model_bd_asr=int(c[9]),
+                    n_F_correct=int(c[10]))

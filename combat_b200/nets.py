@@ -1,0 +1,663 @@
+"""Explicit forward/backward graphs of the networks on the hot path, built from the C-ABI kernels.
+
+No autograd: every network is a hand-scheduled sequence of kernel launches with saved activations, so the
+alternated step can be captured in a CUDA graph and run the "strictly needed" schedule of SURVEY.md section 3.1
+(dgrad-only backward through netC / clean_model in the G-step, no generator backward in the C-step).
+
+Reference structures restated here (paths relative to the reference root):
+  PreActResNet18   classifier_models/preact_resnet.py:13-40,72-110
+  ResNet18         classifier_models/resnet.py:15-37,68-106
+  UnetGenerator    networks/models.py:268-341         CUnetGeneratorv1  networks/models.py:472-555
+  FrequencyModel   defenses/frequency_based/model.py:8-52
+Parameter names, shapes and order are the reference's state_dict keys.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import torch
+
+from . import ops
+from ._lib import check, lib
+
+
+def _align(n, a=4):
+    return (n + a - 1) // a * a
+
+
+class ParamStore:
+    """All parameters of a network in ONE flat float32 buffer (+ gradient and momentum buffers of the same
+    shape) so that SGD, gradient zeroing and the data-parallel all-reduce are single launches.
+
+    4-D (conv) weights are STORED channels-last ([Cout][KH][KW][Cin], the layout the kernels consume and the
+    weight-gradient kernels produce); `p(name)` exposes them as a permuted view with the reference's OIHW shape,
+    i.e. exactly a torch channels_last tensor, so state_dict round-trips keep the reference's names and shapes."""
+
+    def __init__(self, specs, device):
+        self.names = [n for n, _ in specs]
+        self.shapes = {n: tuple(s) for n, s in specs}
+        self.offsets = {}
+        off = 0
+        for n, s in specs:
+            self.offsets[n] = off
+            num = 1
+            for d in s:
+                num *= d
+            off += _align(num)
+        self.numel = off
+        self.flat = torch.zeros(off, dtype=torch.float32, device=device)
+        self.grad = torch.zeros(off, dtype=torch.float32, device=device)
+        self.mom = torch.zeros(off, dtype=torch.float32, device=device)
+        self.first_step = True
+
+    def _view(self, buf, n):
+        s = self.shapes[n]
+        num = 1
+        for d in s:
+            num *= d
+        o = self.offsets[n]
+        if len(s) == 4:
+            co, ci, kh, kw = s
+            return buf[o:o + num].view(co, kh, kw, ci).permute(0, 3, 1, 2)
+        return buf[o:o + num].view(s)
+
+    def raw(self, buf, n):
+        """contiguous storage-order view (channels-last for conv weights)"""
+        s = self.shapes[n]
+        num = 1
+        for d in s:
+            num *= d
+        o = self.offsets[n]
+        return buf[o:o + num]
+
+    def p(self, n):
+        return self._view(self.flat, n)
+
+    def g(self, n):
+        return self._view(self.grad, n)
+
+    def m(self, n):
+        return self._view(self.mom, n)
+
+    def gptr(self, n):
+        return self.grad.data_ptr() + 4 * self.offsets[n]
+
+    def load(self, sd: dict):
+        for n in self.names:
+            self.p(n).copy_(sd[n].to(torch.float32))
+
+    def state(self) -> dict:
+        return {n: self.p(n).contiguous().clone() for n in self.names}
+
+
+@dataclass
+class ConvSpec:
+    name: str
+    Cin: int
+    Cout: int
+    k: int
+    stride: int
+    pad: int
+    bias: bool = False
+    need_dgrad: bool = True
+    fwd_off: int = 0
+    dgrad_off: int = -1
+
+
+class NetBase:
+    """Shared machinery: parameter store, compute-layout weights, conv dispatch."""
+
+    def __init__(self, device, dtype, use_tc=True):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("combat_b200 networks run on CUDA devices only (no CPU fallback)")
+        self.dtype = dtype
+        self.dt = ops.dt_code(dtype)
+        self.use_tc = bool(use_tc) and dtype == torch.bfloat16
+        self.convs: dict[str, ConvSpec] = {}
+
+    # ---- construction helpers
+    def _finish_params(self, specs, conv_specs):
+        self.store = ParamStore(specs, self.device)
+        off = 0
+        table = []
+        for cs in conv_specs:
+            n = cs.Cout * cs.Cin * cs.k * cs.k
+            cs.fwd_off = off
+            off += _align(n, 64)
+            if cs.need_dgrad:
+                cs.dgrad_off = off
+                off += _align(n, 64)
+            self.convs[cs.name] = cs
+            table.append((self.store.offsets[cs.name + ".weight"], cs.fwd_off, cs.dgrad_off, cs.Cout, cs.Cin, cs.k, cs.k))
+        self.wbuf = torch.zeros(off, dtype=self.dtype, device=self.device)
+        self._wtable, self._wmax = ops.make_wprep_table(table, self.device)
+        self._n_wdesc = len(table)
+        self.esz = self.wbuf.element_size()
+
+    def prep_weights(self):
+        """master OIHW float32 -> compute layouts (OHWI and flipped/transposed for dgrad) in the compute dtype."""
+        ops.prep_weights(self.store.flat, self.wbuf, self._wtable, self._n_wdesc, self._wmax)
+
+    def zero_grad(self):
+        self.store.grad.zero_()
+
+    def sgd_step(self, lr_dev, momentum=0.9, wd=5e-4):
+        st = self.store
+        ops.sgd_nesterov(st.flat, st.grad, st.mom, lr_dev, momentum, wd, st.first_step)
+        st.first_step = False
+        self.prep_weights()
+
+    def _wptr(self, cs: ConvSpec, dgrad=False):
+        return self.wbuf.data_ptr() + (cs.dgrad_off if dgrad else cs.fwd_off) * self.esz
+
+    def _bias(self, cs):
+        return self.store.p(cs.name + ".bias") if cs.bias else None
+
+    # ---- conv dispatch (NHWC activations)
+    def _tc_ok(self, cs: ConvSpec):
+        return self.use_tc and cs.Cin % 64 == 0 and cs.Cout % 64 == 0
+
+    def conv_fwd(self, x, cs: ConvSpec, residual=None, x_cview=None):
+        """x: NHWC [N,H,W,Cin(+extra)] in compute dtype -> NHWC out."""
+        N, H, W, Ct = x.shape
+        Ho = (H + 2 * cs.pad - cs.k) // cs.stride + 1
+        Wo = (W + 2 * cs.pad - cs.k) // cs.stride + 1
+        out = torch.empty((N, Ho, Wo, cs.Cout), dtype=self.dtype, device=self.device)
+        if self._tc_ok(cs) and Ct == cs.Cin:
+            d = ops.conv_tc_desc(x, self._wptr(cs), out, N, H, W, cs.Cin, Ho, Wo, cs.Cout, cs.k, cs.k, cs.stride, cs.pad, 1,
+                                 bias=self._bias(cs), residual=residual)
+            if lib.combat_conv_tc_supported(C.byref(d)):
+                check(lib.combat_conv_tc(C.byref(d), ops._s()), "conv_tc")
+                return out
+        ops.conv_simt(x, (N, H, W), ops.nhwc_strides(H, W, Ct), self._wptr(cs), self.dt, out, (Ho, Wo),
+                      ops.nhwc_strides(Ho, Wo, cs.Cout), Ci=cs.Cin, Co=cs.Cout, KH=cs.k, KW=cs.k, stride=cs.stride,
+                      pad=cs.pad, bias=self._bias(cs), residual=residual)
+        return out
+
+    def conv_dgrad(self, dy, cs: ConvSpec, in_hw, residual=None, n_out_ch=None):
+        """dy: NHWC [N,Ho,Wo,Cout] -> dx NHWC [N,H,W,n_out_ch or Cin] (+ residual)."""
+        N, Ho, Wo, _ = dy.shape
+        H, W = in_hw
+        Cx = cs.Cin if n_out_ch is None else n_out_ch
+        dx = torch.empty((N, H, W, Cx), dtype=self.dtype, device=self.device)
+        padp = cs.k - 1 - cs.pad
+        if self._tc_ok(cs) and Cx == cs.Cin:
+            d = ops.conv_tc_desc(dy, self._wptr(cs, True), dx, N, Ho, Wo, cs.Cout, H, W, cs.Cin, cs.k, cs.k, 1, padp,
+                                 cs.stride, residual=residual)
+            if lib.combat_conv_tc_supported(C.byref(d)):
+                check(lib.combat_conv_tc(C.byref(d), ops._s()), "conv_tc(dgrad)")
+                return dx
+        ops.conv_simt(dy, (N, Ho, Wo), ops.nhwc_strides(Ho, Wo, cs.Cout), self._wptr(cs, True), self.dt, dx, (H, W),
+                      ops.nhwc_strides(H, W, Cx), Ci=cs.Cout, Co=Cx, KH=cs.k, KW=cs.k, stride=1, pad=padp, up=cs.stride,
+                      residual=residual)
+        return dx
+
+    def conv_wgrad(self, x, dy, cs: ConvSpec):
+        """accumulates dW (OIHW float32) and the bias gradient into the flat gradient buffer."""
+        N, H, W, Ct = x.shape
+        _, Ho, Wo, _ = dy.shape
+        dw = self.store.raw(self.store.grad, cs.name + ".weight")
+        db = self.store.g(cs.name + ".bias") if cs.bias else None
+        if self._tc_ok(cs) and Ct == cs.Cin:
+            d = ops.conv_tc_desc(x, None, None, N, H, W, cs.Cin, Ho, Wo, cs.Cout, cs.k, cs.k, cs.stride, cs.pad, 1)
+            if lib.combat_conv_tc_supported(C.byref(d)):
+                check(lib.combat_conv_tc_wgrad(C.byref(d), ops._p(dy), ops._p(dw), ops._s()), "conv_tc_wgrad")
+                if db is not None:
+                    ops.colsum(dy, cs.Cout, db)
+                return
+        ops.conv_wgrad_simt(x, (N, H, W), ops.nhwc_strides(H, W, Ct), dy, (Ho, Wo), ops.nhwc_strides(Ho, Wo, cs.Cout), dw,
+                            Ci=cs.Cin, Co=cs.Cout, KH=cs.k, KW=cs.k, stride=cs.stride, pad=cs.pad, db=db)
+
+    # ---- image-boundary convs (NCHW float32 on the 3-channel side), always CUDA-core kernels
+    def conv_first_fwd(self, x_nchw, cs: ConvSpec, out=None, out_ctot=None):
+        N, Cc, H, W = x_nchw.shape
+        Ho = (H + 2 * cs.pad - cs.k) // cs.stride + 1
+        Wo = (W + 2 * cs.pad - cs.k) // cs.stride + 1
+        Ct = cs.Cout if out_ctot is None else out_ctot
+        if out is None:
+            out = torch.empty((N, Ho, Wo, Ct), dtype=self.dtype, device=self.device)
+        ops.conv_simt(x_nchw, (N, H, W), ops.nchw_strides(Cc, H, W), self._wptr(cs), self.dt, out, (Ho, Wo),
+                      ops.nhwc_strides(Ho, Wo, Ct), Ci=cs.Cin, Co=cs.Cout, KH=cs.k, KW=cs.k, stride=cs.stride, pad=cs.pad,
+                      bias=self._bias(cs))
+        return out
+
+    def conv_first_wgrad(self, x_nchw, dy, cs: ConvSpec, dy_ctot=None):
+        N, Cc, H, W = x_nchw.shape
+        _, Ho, Wo, Ct = dy.shape
+        ops.conv_wgrad_simt(x_nchw, (N, H, W), ops.nchw_strides(Cc, H, W), dy, (Ho, Wo), ops.nhwc_strides(Ho, Wo, Ct),
+                            self.store.raw(self.store.grad, cs.name + ".weight"), Ci=cs.Cin, Co=cs.Cout, KH=cs.k, KW=cs.k, stride=cs.stride,
+                            pad=cs.pad, db=self.store.g(cs.name + ".bias") if cs.bias else None)
+
+    def conv_first_dgrad(self, dy, cs: ConvSpec, in_hw):
+        """-> dx NCHW float32 (gradient w.r.t. the input image)."""
+        N, Ho, Wo, _ = dy.shape
+        H, W = in_hw
+        dx = torch.empty((N, cs.Cin, H, W), dtype=torch.float32, device=self.device)
+        ops.conv_simt(dy, (N, Ho, Wo), ops.nhwc_strides(Ho, Wo, cs.Cout), self._wptr(cs, True), self.dt, dx, (H, W),
+                      ops.nchw_strides(cs.Cin, H, W), Ci=cs.Cout, Co=cs.Cin, KH=cs.k, KW=cs.k, stride=1,
+                      pad=cs.k - 1 - cs.pad, up=cs.stride)
+        return dx
+
+
+# ===================================================================== classifiers
+@dataclass
+class _BN:
+    name: str
+    C: int
+
+
+class Classifier(NetBase):
+    """PreActResNet18 / ResNet18 with explicit train/eval forward and (dgrad[, wgrad]) backward."""
+
+    def __init__(self, arch="preact_resnet18", num_classes=10, n_input=3, input_size=32, device="cuda",
+                 dtype=torch.bfloat16, use_tc=True, scaler=None):
+        super().__init__(device, dtype, use_tc)
+        assert arch in ("preact_resnet18", "resnet18")
+        self.arch, self.num_classes, self.n_input, self.input_size = arch, num_classes, n_input, input_size
+        if scaler is None:
+            scaler = {32: 1, 64: 4, 224: 49}[input_size]  # reference: {32:1, 64:4}; 224 -> 49 is the natural extension
+        self.scaler = scaler
+        pre = arch == "preact_resnet18"
+        specs, convs, self.bns, self.blocks = [], [], [], []
+
+        def add_conv(name, ci, co, k, s, p, need_dgrad=True):
+            specs.append((name + ".weight", (co, ci, k, k)))
+            cs = ConvSpec(name, ci, co, k, s, p, False, need_dgrad)
+            convs.append(cs)
+            return cs
+
+        def add_bn(name, c):
+            specs.append((name + ".weight", (c,)))
+            specs.append((name + ".bias", (c,)))
+            bn = _BN(name, c)
+            self.bns.append(bn)
+            return bn
+
+        self.conv1 = add_conv("conv1", n_input, 64, 3, 1, 1)
+        self.bn1 = None if pre else add_bn("bn1", 64)
+        in_planes = 64
+        for li, (planes, stride0) in enumerate([(64, 1), (128, 2), (256, 2), (512, 2)], start=1):
+            for bi, stride in enumerate([stride0, 1]):
+                pfx = "layer%d.%d." % (li, bi)
+                blk = {"stride": stride, "in": in_planes, "planes": planes}
+                if pre:
+                    blk["bn1"] = add_bn(pfx + "bn1", in_planes)
+                    blk["conv1"] = add_conv(pfx + "conv1", in_planes, planes, 3, stride, 1)
+                    blk["bn2"] = add_bn(pfx + "bn2", planes)
+                    blk["conv2"] = add_conv(pfx + "conv2", planes, planes, 3, 1, 1)
+                    if stride != 1 or in_planes != planes:
+                        blk["sc"] = add_conv(pfx + "shortcut.0", in_planes, planes, 1, stride, 0)
+                else:
+                    blk["conv1"] = add_conv(pfx + "conv1", in_planes, planes, 3, stride, 1)
+                    blk["bn1"] = add_bn(pfx + "bn1", planes)
+                    blk["conv2"] = add_conv(pfx + "conv2", planes, planes, 3, 1, 1)
+                    blk["bn2"] = add_bn(pfx + "bn2", planes)
+                    if stride != 1 or in_planes != planes:
+                        blk["sc"] = add_conv(pfx + "shortcut.0", in_planes, planes, 1, stride, 0)
+                        blk["scbn"] = add_bn(pfx + "shortcut.1", planes)
+                self.blocks.append(blk)
+                in_planes = planes
+        specs.append(("linear.weight", (num_classes, 512 * scaler)))
+        specs.append(("linear.bias", (num_classes,)))
+        self._finish_params(specs, convs)
+        # buffers: running stats of every BN in one flat buffer (mean | var per layer)
+        self.buf_off = {}
+        off = 0
+        for bn in self.bns:
+            self.buf_off[bn.name] = off
+            off += 2 * bn.C
+        self.bufs = torch.zeros(off, dtype=torch.float32, device=self.device)
+        self.num_batches_tracked = {bn.name: 0 for bn in self.bns}
+        for bn in self.bns:
+            self.store.p(bn.name + ".weight").fill_(1.0)
+            self.rv(bn).fill_(1.0)
+        self.momentum, self.eps = 0.1, 1e-5
+
+    # ---- buffers
+    def rm(self, bn):
+        o = self.buf_off[bn.name]
+        return self.bufs[o:o + bn.C]
+
+    def rv(self, bn):
+        o = self.buf_off[bn.name] + bn.C
+        return self.bufs[o:o + bn.C]
+
+    def load_state_dict(self, sd: dict):
+        self.store.load(sd)
+        for bn in self.bns:
+            self.rm(bn).copy_(sd[bn.name + ".running_mean"])
+            self.rv(bn).copy_(sd[bn.name + ".running_var"])
+            self.num_batches_tracked[bn.name] = int(sd.get(bn.name + ".num_batches_tracked", 0))
+        self.prep_weights()
+
+    def state_dict(self) -> dict:
+        sd = self.store.state()
+        for bn in self.bns:
+            sd[bn.name + ".running_mean"] = self.rm(bn).clone()
+            sd[bn.name + ".running_var"] = self.rv(bn).clone()
+            sd[bn.name + ".num_batches_tracked"] = torch.tensor(self.num_batches_tracked[bn.name])
+        return sd
+
+    # ---- BN helpers
+    def _bn_fwd(self, bn, x, train, relu, residual=None):
+        Cc = bn.C
+        R = x.numel() // Cc
+        g, b = self.store.p(bn.name + ".weight"), self.store.p(bn.name + ".bias")
+        if train:
+            scale, shift, mean, invstd = ops.bn_train_prepare(x, R, Cc, g, b, self.rm(bn), self.rv(bn), self.momentum, self.eps)
+            self.num_batches_tracked[bn.name] += 1
+            st = (scale, mean, invstd)
+        else:
+            scale, shift = ops.bn_eval_prepare(Cc, g, b, self.rm(bn), self.rv(bn), self.eps)
+            st = (scale, None, None)
+        y = ops.affine_act(x, scale, shift, relu, residual=residual)
+        return y, st
+
+    def _bn_bwd(self, bn, dy, x, y, st, train, relu, need_wgrad, dadd=None, want_dres=False):
+        scale, mean, invstd = st
+        if train:
+            if need_wgrad:
+                dg, db = self.store.g(bn.name + ".weight"), self.store.g(bn.name + ".bias")
+            else:
+                tmp = torch.empty((2, bn.C), dtype=torch.float32, device=self.device)
+                dg, db = tmp[0], tmp[1]
+            return ops.bn_bwd_train(dy, x, y, self.store.p(bn.name + ".weight"), mean, invstd, relu, dg, db, dadd, want_dres)
+        return ops.bn_bwd_eval(dy, y, scale, relu, dadd, want_dres)
+
+    # ---- forward
+    def forward(self, x_nchw, train: bool, save: bool = True):
+        """x_nchw float32 [N,C,H,W] -> (logits float32 [N,num_classes], ctx)."""
+        pre = self.arch == "preact_resnet18"
+        ctx = {"x": x_nchw, "train": train, "blocks": []} if save else None
+        h = self.conv_first_fwd(x_nchw, self.conv1)
+        if not pre:
+            c0 = h
+            h, st0 = self._bn_fwd(self.bn1, c0, train, True)
+            if save:
+                ctx["stem"] = (c0, h, st0)
+        for blk in self.blocks:
+            if pre:
+                o1, st1 = self._bn_fwd(blk["bn1"], h, train, True)
+                s = self.conv_fwd(o1, blk["sc"]) if "sc" in blk else h
+                c1 = self.conv_fwd(o1, blk["conv1"])
+                o2, st2 = self._bn_fwd(blk["bn2"], c1, train, True)
+                out = self.conv_fwd(o2, blk["conv2"], residual=s)
+                if save:
+                    ctx["blocks"].append((h, o1, c1, o2, st1, st2))
+            else:
+                c1 = self.conv_fwd(h, blk["conv1"])
+                o1, st1 = self._bn_fwd(blk["bn1"], c1, train, True)
+                c2 = self.conv_fwd(o1, blk["conv2"])
+                if "sc" in blk:
+                    cs_ = self.conv_fwd(h, blk["sc"])
+                    s, sts = self._bn_fwd(blk["scbn"], cs_, train, False)
+                else:
+                    cs_, s, sts = None, h, None
+                out, st2 = self._bn_fwd(blk["bn2"], c2, train, True, residual=s)
+                if save:
+                    ctx["blocks"].append((h, c1, o1, c2, out, cs_, st1, st2, sts))
+            h = out
+        logits, pooled = ops.pool_linear_fwd(h, 4, self.store.p("linear.weight"), self.store.p("linear.bias"))
+        if save:
+            ctx["feat_shape"], ctx["pooled"] = tuple(h.shape), pooled
+        return logits, ctx
+
+    # ---- backward
+    def backward(self, ctx, dlogits, need_wgrad: bool, need_dx: bool):
+        """Returns dx (NCHW float32) if need_dx.  Parameter gradients are accumulated into store.grad."""
+        pre = self.arch == "preact_resnet18"
+        train = ctx["train"]
+        st = self.store
+        dh = ops.pool_linear_bwd(dlogits, ctx["pooled"], st.p("linear.weight"), ctx["feat_shape"], self.dtype, 4,
+                                 dW=st.g("linear.weight") if need_wgrad else None,
+                                 db=st.g("linear.bias") if need_wgrad else None)
+        for blk, saved in zip(reversed(self.blocks), reversed(ctx["blocks"])):
+            if pre:
+                h_in, o1, c1, o2, st1, st2 = saved
+                hw_in, hw_mid = h_in.shape[1:3], c1.shape[1:3]
+                if need_wgrad:
+                    self.conv_wgrad(o2, dh, blk["conv2"])
+                d_o2 = self.conv_dgrad(dh, blk["conv2"], hw_mid)
+                d_c1, _ = self._bn_bwd(blk["bn2"], d_o2, c1, o2, st2, train, True, need_wgrad)
+                if need_wgrad:
+                    self.conv_wgrad(o1, d_c1, blk["conv1"])
+                d_o1 = self.conv_dgrad(d_c1, blk["conv1"], hw_in)
+                if "sc" in blk:
+                    if need_wgrad:
+                        self.conv_wgrad(o1, dh, blk["sc"])
+                    d_o1 = self.conv_dgrad(dh, blk["sc"], hw_in, residual=d_o1)
+                    dadd = None
+                else:
+                    dadd = dh
+                dh, _ = self._bn_bwd(blk["bn1"], d_o1, h_in, o1, st1, train, True, need_wgrad, dadd=dadd)
+            else:
+                h_in, c1, o1, c2, out, cs_, st1, st2, sts = saved
+                hw_in, hw_mid = h_in.shape[1:3], c1.shape[1:3]
+                d_c2, dres = self._bn_bwd(blk["bn2"], dh, c2, out, st2, train, True, need_wgrad, want_dres=True)
+                if need_wgrad:
+                    self.conv_wgrad(o1, d_c2, blk["conv2"])
+                d_o1 = self.conv_dgrad(d_c2, blk["conv2"], hw_mid)
+                d_c1, _ = self._bn_bwd(blk["bn1"], d_o1, c1, o1, st1, train, True, need_wgrad)
+                if need_wgrad:
+                    self.conv_wgrad(h_in, d_c1, blk["conv1"])
+                if "sc" in blk:
+                    d_cs, _ = self._bn_bwd(blk["scbn"], dres, cs_, None, sts, train, False, need_wgrad)
+                    if need_wgrad:
+                        self.conv_wgrad(h_in, d_cs, blk["sc"])
+                    d_h = self.conv_dgrad(d_cs, blk["sc"], hw_in)
+                    dh = self.conv_dgrad(d_c1, blk["conv1"], hw_in, residual=d_h)
+                else:
+                    dh = self.conv_dgrad(d_c1, blk["conv1"], hw_in, residual=dres)
+        if not pre:
+            c0, h0, st0 = ctx["stem"]
+            dh, _ = self._bn_bwd(self.bn1, dh, c0, h0, st0, train, True, need_wgrad)
+        x = ctx["x"]
+        if need_wgrad:
+            self.conv_first_wgrad(x, dh, self.conv1)
+        if need_dx:
+            return self.conv_first_dgrad(dh, self.conv1, x.shape[2:4])
+        return None
+
+
+# ===================================================================== trigger generator
+class Generator(NetBase):
+    """UnetGenerator (num_classes=0) / CUnetGeneratorv1 (num_classes>0: one-hot label planes after conv0_0)."""
+
+    LAYERS = [("conv0_0", 2), ("conv0_1", 1), ("conv1_0", 2), ("conv1_1", 1), ("conv2_0", 2), ("conv2_1", 1),
+              ("conv3_0", 2), ("conv3_1", 1), ("upconv3_1", 1), ("upconv3_0", 1), ("upconv2_1", 1), ("upconv2_0", 1),
+              ("upconv1_1", 1), ("upconv1_0", 1), ("upconv0_1", 1), ("upconv0_0", 1)]
+
+    def __init__(self, in_channels=3, nf=64, num_classes=0, out_channel=None, device="cuda", dtype=torch.bfloat16,
+                 use_tc=True):
+        super().__init__(device, dtype, use_tc)
+        if out_channel is None:
+            out_channel = in_channels
+        self.nf, self.cond, self.in_channels, self.out_channel = nf, num_classes, in_channels, out_channel
+        ch = {"conv0_0": (in_channels, nf), "conv0_1": (nf + num_classes, nf), "conv1_0": (nf, nf * 2),
+              "conv1_1": (nf * 2, nf * 2), "conv2_0": (nf * 2, nf * 4), "conv2_1": (nf * 4, nf * 4),
+              "conv3_0": (nf * 4, nf * 8), "conv3_1": (nf * 8, nf * 8), "upconv3_1": (nf * 8, nf * 8),
+              "upconv3_0": (nf * 8, nf * 4), "upconv2_1": (nf * 4, nf * 4), "upconv2_0": (nf * 4, nf * 2),
+              "upconv1_1": (nf * 2, nf * 2), "upconv1_0": (nf * 2, nf), "upconv0_1": (nf, nf),
+              "upconv0_0": (nf, out_channel)}
+        specs, convs = [], []
+        for name, stride in self.LAYERS:
+            ci, co = ch[name]
+            specs.append((name + ".weight", (co, ci, 3, 3)))
+            specs.append((name + ".bias", (co,)))
+            convs.append(ConvSpec(name, ci, co, 3, stride, 1, True, need_dgrad=(name != "conv0_0")))
+        self._finish_params(specs, convs)
+
+    def load_state_dict(self, sd):
+        self.store.load(sd)
+        self.prep_weights()
+
+    def state_dict(self):
+        return self.store.state()
+
+    def forward(self, x_nchw, labels=None, save=True):
+        """x float32 NCHW -> tanh output float32 NCHW (networks/models.py:318-341; :523-555 with labels)."""
+        cv = self.convs
+        N, _, H, W = x_nchw.shape
+        nf = self.nf
+        ctx = {"x": x_nchw} if save else None
+        c00 = self.conv_first_fwd(x_nchw, cv["conv0_0"])
+        if self.cond:  # cat(f0, one_hot planes) then the in-place LeakyReLU (identity on the 0/1 planes)
+            a00 = torch.empty((N, H // 2, W // 2, nf + self.cond), dtype=self.dtype, device=self.device)
+            ops.lrelu_into_slice(c00, a00, 0)
+            ops.onehot_planes(a00, labels, nf, self.cond)
+        else:
+            a00 = ops.leaky_relu(c00)
+        acts = {"c00": c00, "a00": a00}
+
+        def down(name, xin, act=True):
+            c = self.conv_fwd(xin, cv[name])
+            y, st = ops.instnorm_fwd(c, act)
+            acts[name] = (xin, c, st)
+            return y
+
+        f0 = down("conv0_1", a00)
+        f1 = down("conv1_1", down("conv1_0", f0))
+        f2 = down("conv2_1", down("conv2_0", f1))
+        f3 = down("conv3_1", down("conv3_0", f2), act=False)
+
+        def up_block(n1, n0, xin, skip):
+            t = ops.upsample2x_act(xin)
+            c1 = self.conv_fwd(t, cv[n1])
+            a1, st1 = ops.instnorm_fwd(c1, True)
+            acts[n1] = (t, c1, st1)
+            c0 = self.conv_fwd(a1, cv[n0])
+            u, st0 = ops.instnorm_fwd(c0, False, skip=skip)
+            acts[n0] = (a1, c0, st0)
+            return u
+
+        u3 = up_block("upconv3_1", "upconv3_0", f3, f2)
+        u2 = up_block("upconv2_1", "upconv2_0", u3, f1)
+        u1 = up_block("upconv1_1", "upconv1_0", u2, f0)
+        t0 = ops.upsample2x_act(u1)
+        c01 = self.conv_fwd(t0, cv["upconv0_1"])
+        a01, st01 = ops.instnorm_fwd(c01, True)
+        acts["upconv0_1"] = (t0, c01, st01)
+        cs = cv["upconv0_0"]
+        out = torch.empty((N, self.out_channel, H, W), dtype=torch.float32, device=self.device)
+        ops.conv_simt(a01, (N, H, W), ops.nhwc_strides(H, W, nf), self._wptr(cs), self.dt, out, (H, W),
+                      ops.nchw_strides(self.out_channel, H, W), Ci=nf, Co=self.out_channel, KH=3, KW=3, stride=1, pad=1,
+                      bias=self._bias(cs), act=1)
+        if save:
+            acts["a01"] = a01
+            ctx["acts"], ctx["out"] = acts, out
+        return out, ctx
+
+    def backward(self, ctx, dout):
+        """dout: gradient w.r.t. the tanh output (NCHW float32).  Accumulates all parameter gradients."""
+        cv, acts = self.convs, ctx["acts"]
+        x = ctx["x"]
+        N, _, H, W = x.shape
+        nf = self.nf
+        dz = ops.tanh_bwd(dout, ctx["out"])
+        cs = cv["upconv0_0"]
+        a01 = acts["a01"]
+        nchw_o = ops.nchw_strides(self.out_channel, H, W)
+        ops.conv_wgrad_simt(a01, (N, H, W), ops.nhwc_strides(H, W, nf), dz, (H, W), nchw_o,
+                            self.store.raw(self.store.grad, cs.name + ".weight"),
+                            Ci=nf, Co=self.out_channel, KH=3, KW=3, stride=1, pad=1, db=self.store.g(cs.name + ".bias"))
+        d_a01 = torch.empty((N, H, W, nf), dtype=self.dtype, device=self.device)
+        ops.conv_simt(dz, (N, H, W), nchw_o, self._wptr(cs, True), self.dt, d_a01, (H, W), ops.nhwc_strides(H, W, nf),
+                      Ci=self.out_channel, Co=nf, KH=3, KW=3, stride=1, pad=1, up=1)
+
+        def conv_in_bwd(name, dy1, dy2, act, n_out_ch=None, want_dx=True):
+            """backward through  y = [lrelu](IN(conv(xin)))  given dL/dy = dy1 (+ dy2)."""
+            xin, c, st = acts[name]
+            d_c = ops.instnorm_bwd(dy1, dy2, c, st, act)
+            self.conv_wgrad(xin, d_c, cv[name])
+            if not want_dx:
+                return None
+            return self.conv_dgrad(d_c, cv[name], xin.shape[1:3], n_out_ch=n_out_ch)
+
+        d_t0 = conv_in_bwd("upconv0_1", d_a01, None, True)
+        d_u1 = ops.upsample2x_act_bwd(d_t0, acts["upconv0_1"][0])
+
+        def up_block_bwd(n1, n0, d_u):
+            d_a1 = conv_in_bwd(n0, d_u, None, False)
+            d_t = conv_in_bwd(n1, d_a1, None, True)
+            return ops.upsample2x_act_bwd(d_t, acts[n1][0])
+
+        d_u2 = up_block_bwd("upconv1_1", "upconv1_0", d_u1)  # d_u1 is also the skip gradient of f0
+        d_u3 = up_block_bwd("upconv2_1", "upconv2_0", d_u2)  # d_u2 ... of f1
+        d_f3 = up_block_bwd("upconv3_1", "upconv3_0", d_u3)  # d_u3 ... of f2
+        d_a30 = conv_in_bwd("conv3_1", d_f3, None, False)
+        d_f2 = conv_in_bwd("conv3_0", d_a30, None, True)
+        d_a20 = conv_in_bwd("conv2_1", d_f2, d_u3, True)
+        d_f1 = conv_in_bwd("conv2_0", d_a20, None, True)
+        d_a10 = conv_in_bwd("conv1_1", d_f1, d_u2, True)
+        d_f0 = conv_in_bwd("conv1_0", d_a10, None, True)
+        d_a00 = conv_in_bwd("conv0_1", d_f0, d_u1, True, n_out_ch=nf if self.cond else None)
+        d_c00 = ops.leaky_relu_bwd(d_a00, acts["c00"])
+        self.conv_first_wgrad(x, d_c00, cv["conv0_0"])
+
+
+# ===================================================================== frequency detector (forward only)
+class FrequencyDetector(NetBase):
+    """FrequencyModel in eval mode: conv -> ELU -> BN(eval) (x6), maxpool after 2/4/6, flatten (NCHW order), linear.
+    Always float32 CUDA-core kernels: its input are DCT coefficients of magnitude up to ~8e3 (metrics leg only)."""
+
+    def __init__(self, num_classes=2, n_input=3, input_size=32, device="cuda"):
+        super().__init__(device, torch.float32, use_tc=False)
+        self.scaler = {32: 1, 64: 4}[input_size]
+        chans = [n_input, 32, 32, 64, 64, 128, 128]
+        specs, convs = [], []
+        self.chans = chans
+        for i in range(1, 7):
+            specs.append(("conv%d.weight" % i, (chans[i], chans[i - 1], 3, 3)))
+            specs.append(("conv%d.bias" % i, (chans[i],)))
+            specs.append(("bn%d.weight" % i, (chans[i],)))
+            specs.append(("bn%d.bias" % i, (chans[i],)))
+            convs.append(ConvSpec("conv%d" % i, chans[i - 1], chans[i], 3, 1, 1, True, need_dgrad=False))
+        specs.append(("linear6.weight", (num_classes, 2048 * self.scaler)))
+        specs.append(("linear6.bias", (num_classes,)))
+        self._finish_params(specs, convs)
+        self.rm = {i: torch.zeros(chans[i], device=self.device) for i in range(1, 7)}
+        self.rv = {i: torch.ones(chans[i], device=self.device) for i in range(1, 7)}
+        for i in range(1, 7):
+            self.store.p("bn%d.weight" % i).fill_(1.0)
+        self._affine = None
+
+    def load_state_dict(self, sd):
+        self.store.load(sd)
+        for i in range(1, 7):
+            self.rm[i].copy_(sd["bn%d.running_mean" % i])
+            self.rv[i].copy_(sd["bn%d.running_var" % i])
+        self.prep_weights()
+        self._affine = None
+
+    def state_dict(self):
+        sd = self.store.state()
+        for i in range(1, 7):
+            sd["bn%d.running_mean" % i] = self.rm[i].clone()
+            sd["bn%d.running_var" % i] = self.rv[i].clone()
+            sd["bn%d.num_batches_tracked" % i] = torch.tensor(0)
+        return sd
+
+    def forward(self, x_nchw):
+        """x: float32 NCHW DCT coefficients -> logits [N, num_classes]."""
+        if self._affine is None:  # frozen network: fold BN(eval) once
+            self._affine = {i: ops.bn_eval_prepare(self.chans[i], self.store.p("bn%d.weight" % i), self.store.p("bn%d.bias" % i),
+                                                   self.rm[i], self.rv[i], 1e-5) for i in range(1, 7)}
+        N, Cc, H, W = x_nchw.shape
+        h, strides, hw = x_nchw, ops.nchw_strides(Cc, H, W), (H, W)
+        for i in range(1, 7):
+            cs = self.convs["conv%d" % i]
+            out = torch.empty((N, hw[0], hw[1], cs.Cout), dtype=torch.float32, device=self.device)
+            sc, sh = self._affine[i]
+            ops.conv_simt(h, (N, hw[0], hw[1]), strides, self._wptr(cs), self.dt, out, hw, ops.nhwc_strides(hw[0], hw[1], cs.Cout),
+                          Ci=cs.Cin, Co=cs.Cout, KH=3, KW=3, stride=1, pad=1, bias=self._bias(cs), act=2, post_scale=sc,
+                          post_shift=sh)
+            h = out
+            if i % 2 == 0:
+                h = ops.maxpool2(h)
+                hw = (hw[0] // 2, hw[1] // 2)
+            strides = ops.nhwc_strides(hw[0], hw[1], cs.Cout)
+        # flatten in NCHW order + linear == pool_linear with P = 1
+        logits, _ = ops.pool_linear_fwd(h, 1, self.store.p("linear6.weight"), self.store.p("linear6.bias"))
+        return logits

@@ -1,0 +1,202 @@
+/*
+ * combat_b200 -- C-ABI of the B200-native (sm_100a) kernels behind COMBAT's alternated
+ * generator/surrogate training step and its batched 2-D DCT.
+ *
+ * The reference (VinAIResearch/COMBAT) is pure Python/PyTorch and has no FFI of its own
+ * (SURVEY.md section 8b): the boundary a maintainer binds is this header, from Python via ctypes
+ * (combat_b200/_lib.py; INTEGRATION.md shows the stub).  Conventions:
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - no allocation inside; callers provide outputs and workspaces;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant, and
+ *     may be captured into a CUDA graph;
+ *   - return value: 0 on success, a negative cudaError_t otherwise, -1000-k for argument k invalid;
+ *   - `dtype`: 0 = float32, 1 = bfloat16 (storage type of activations; statistics, losses,
+ *     master weights, gradients of parameters are always float32);
+ *   - images at the reference-facing boundary are NCHW float32 (as the reference's tensors);
+ *     activations inside the networks are NHWC.
+ * Each entry point cites the reference code it replaces (paths relative to the reference root).
+ */
+#ifndef COMBAT_B200_H
+#define COMBAT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define COMBAT_F32 0
+#define COMBAT_BF16 1
+
+/* library / device info */
+int combat_version(void);
+/* counts every kernel launched through this library since load (bench.py's gpu_launches) */
+long long combat_launch_count(void);
+const char* combat_last_error(void);
+
+/* ---------------------------------------------------------------- plane transforms (DCT family)
+ * out[p] = L * X[p] * R^T for `planes` contiguous N x N planes (row-major, NCHW image planes).
+ *   utils/dct.py:85-96   dct_2d   : L = R = D   (orthonormal DCT-II matrix)
+ *   utils/dct.py:99-111  idct_2d  : L = R = D^T
+ *   train_generator.py:47-55 low_freq : L = R = P = D^T diag(1_k) D  (also its own backward: P symmetric)
+ * in_mode: 0 = float32 input, 1 = uint8 input (train_generator.py:245, defenses/frequency_based/train.py:195-197),
+ *          2 = float32 input quantised on the fly as ((x+1)/2*255).byte() (train_generator.py:245).
+ * L, R: N*N float32 row-major on device.  workspace: planes*N*N floats, only touched when N > 64.
+ * fast != 0 and N == 32 and L == R selects the register butterfly kernels: kind 1 = DCT-II, 2 = DCT-III,
+ * 3 = low-pass projection with `keep` retained coefficients per axis (L/R unused).
+ */
+int combat_plane_transform(const void* in, float* out, const float* L, const float* R, long long planes, int N,
+                           int in_mode, float* workspace, void* stream);
+int combat_dct32_fast(const void* in, float* out, long long planes, int kind, int keep, int in_mode, void* stream);
+
+/* ---------------------------------------------------------------- poisoned-batch builder
+ * train_generator.py:188-195 (C-step) and :223-226 (G-step), torchvision GaussianBlur(3) with reflect padding.
+ *   out[r] = r < num_bd ? blur3x3(clamp(x[perm[r]] + noise[nperm[r]] * noise_rate, -1, 1)) : x[perm[r]]
+ * perm/nperm may be NULL (identity).  k0,k1: the normalised 1-D Gaussian taps (centre, side) for this call's sigma.
+ * sq_partial (optional, rows*C floats): per-plane sum((out-x[perm[r]])^2) for the MSE term (:234).
+ * taps_dev (optional, 2 floats) / num_bd_dev (optional, 1 int): device-resident overrides of k0,k1 / num_bd, so that a
+ * captured CUDA graph follows the per-iteration sigma draw and poison count.
+ */
+int combat_poison_blend_fwd(const float* x, const float* noise, const int* perm, const int* nperm, int rows, int num_bd,
+                            float noise_rate, float k0, float k1, float* out, float* sq_partial, int C, int H, int W,
+                            const float* taps_dev, const int* num_bd_dev, void* stream);
+/* backward of blur(clamp(x + noise*rate)) w.r.t. noise (G-step, train_generator.py:225-226,254):
+ *   g = g1 + g2 + mse_scale * (x_bd - x);  dnoise = rate * [|x + noise*rate| <= 1] * blur^T(g)
+ * g2 may be NULL.  mse_scale = 2 * L2_weight / numel. */
+int combat_poison_blend_bwd(const float* x, const float* noise, const float* x_bd, const float* g1, const float* g2,
+                            float mse_scale, float noise_rate, float k0, float k1, float* dnoise, int rows, int C, int H,
+                            int W, const float* taps_dev, void* stream);
+
+/* ---------------------------------------------------------------- losses
+ * torch.nn.CrossEntropyLoss (mean) forward+backward and argmax metrics, train_generator.py:207,231,251,262-267.
+ *   loss_out[0]  = mean_b( logsumexp(logits[b]) - logits[b, t[b]] )
+ *   dlogits[b,c] = grad_scale * (softmax(logits[b])[c] - [c == t[b]]) / B      (dlogits may be NULL)
+ *   counts_out[0] = #{b: argmax == t[b]},  counts_out[1] = #{b: argmax == t2[b]} (t2 may be NULL)
+ */
+int combat_cross_entropy(const float* logits, const long long* targets, const long long* targets2, int B, int C,
+                         float grad_scale, float* loss_out, float* dlogits, int* counts_out, void* stream);
+/* out[0] = scale * sum(partial[0..n)) -- finishes the MSE mean (train_generator.py:234) deterministically */
+int combat_sum_scale(const float* partial, int n, float scale, float* out, void* stream);
+
+/* ---------------------------------------------------------------- optimiser
+ * torch.optim.SGD(momentum, weight_decay, nesterov=True) over a flat parameter buffer, train_generator.py:123-126,212,255:
+ *   g += wd*p;  buf = first ? g : mu*buf + g;  p -= lr*(g + mu*buf)
+ * lr is read from device memory (lr_dev[0]) so a captured graph follows MultiStepLR. */
+int combat_sgd_nesterov(float* p, const float* g, float* buf, long long n, const float* lr_dev, float momentum, float wd,
+                        int first_step, void* stream);
+
+/* weight layout preparation: master channels-last (OHWI) float32 -> compute layouts in `dtype`.
+ * For every descriptor: fwd[co][kh][kw][ci] and (if dgrad_off >= 0) dgrad[ci][KH-1-kh][KW-1-kw][co]. */
+typedef struct {
+  long long src_off;   /* float offset into the flat parameter buffer (OHWI) */
+  long long fwd_off;   /* element offset into the compute-weight buffer, OHWI */
+  long long dgrad_off; /* element offset of the flipped/transposed copy, or -1 */
+  int Cout, Cin, KH, KW;
+} combat_wprep_desc;
+int combat_prep_weights(const float* params, void* wbuf, int dtype, const combat_wprep_desc* table_dev, int n_desc,
+                        long long max_elems, void* stream);
+
+/* ---------------------------------------------------------------- convolution (nn.Conv2d)
+ * Generic strided descriptor so both NCHW float32 images and NHWC activations can be read/written.
+ * forward  : out[n,oh,ow,co] = act( sum_{kh,kw,ci} in[n, (oh*stride-pad+kh)/up, (ow*stride-pad+kw)/up, ci] * w[co,kh,kw,ci] + bias[co] ) (+ residual)
+ *            taps whose numerator is negative, not divisible by `up`, or out of range contribute 0.
+ *            up == 1 is nn.Conv2d forward; stride == 1 with up == s and the flipped weights is its input gradient.
+ * wgrad    : dw[co,kh,kw,ci] (channels-last OHWI float32, ACCUMULATED with atomics) += sum_{n,oh,ow} dy[n,oh,ow,co] * in[n, oh*stride-pad+kh, ow*stride-pad+kw, ci]
+ */
+typedef struct {
+  const void* in;
+  const void* w;         /* OHWI, w_dtype */
+  void* out;
+  const float* bias;     /* or NULL */
+  const void* residual;  /* same layout/dtype as out, or NULL */
+  const float* post_scale; /* per-channel affine applied after act (eval BatchNorm of FrequencyModel), or NULL */
+  const float* post_shift;
+  int N, Hi, Wi, Ci, Ho, Wo, Co, KH, KW, stride, pad, up;
+  long long in_sn, in_sh, in_sw, in_sc;     /* element strides of `in` */
+  long long out_sn, out_sh, out_sw, out_sc; /* element strides of `out` (and residual) */
+  int in_dtype, w_dtype, out_dtype;
+  int act;               /* 0 none, 1 tanh, 2 ELU(alpha=1) */
+} combat_conv_desc;
+int combat_conv_simt(const combat_conv_desc* d_host, void* stream);
+/* wgrad: `in` = layer input (fwd geometry), `out`/`w` unused; dy given separately (strided like out_s*);
+ * if `bias` is non-NULL it is the float32 bias-GRADIENT accumulator: bias[co] += sum_{n,oh,ow} dy[n,oh,ow,co]. */
+int combat_conv_wgrad_simt(const combat_conv_desc* d_host, const void* dy, int dy_dtype, float* dw_ohwi, void* stream);
+
+/* tcgen05 implicit-GEMM convolution (sm_100a tensor cores, TMA-fed, TMEM accumulators), bf16 NHWC.
+ * Requires Ci % 64 == 0 and Co % 64 == 0.  See combat_b200/csrc/conv_tc.cu. */
+typedef struct {
+  const void* in;        /* NHWC bf16 [N,Hi,Wi,Ci] */
+  const void* w;         /* [taps][Co][Ci] bf16 (tap-major OHWI) */
+  void* out;             /* NHWC bf16 [N,Ho,Wo,Co] */
+  const float* bias;     /* or NULL */
+  const void* residual;  /* NHWC bf16 like out, or NULL */
+  float* stats;          /* optional [2*Co] per-channel sum / sum-of-squares of the fp32 result (BatchNorm train) */
+  int N, Hi, Wi, Ci, Ho, Wo, Co, KH, KW, stride, pad, up;
+} combat_conv_tc_desc;
+int combat_conv_tc(const combat_conv_tc_desc* d_host, void* stream);
+int combat_conv_tc_wgrad(const combat_conv_tc_desc* d_host, const void* dy, float* dw_ohwi, void* stream);
+int combat_conv_tc_supported(const combat_conv_tc_desc* d_host);
+
+/* ---------------------------------------------------------------- normalisation / activation (NHWC, dtype)
+ * BatchNorm2d (classifier_models/preact_resnet.py:20,22,32,35; resnet.py:22-35) */
+/* partial per-channel sums over rows [R,C]: partial[(2*blk+0)*C+c] = sum x, [(2*blk+1)*C+c] = sum x^2 ; returns #blocks via nblk_out_host */
+int combat_bn_stats(const void* x, int dtype, long long R, int C, float* partial, int max_blocks, int* nblk_out_host,
+                    void* stream);
+/* train: mean/var from partials -> scale=gamma*invstd, shift=beta-mean*scale, save mean/invstd, update running stats
+ *        (momentum, unbiased var); eval (nblk == 0): scale/shift from running stats. */
+int combat_bn_finalize(const float* partial, int nblk, long long R, int C, const float* gamma, const float* beta,
+                       float* running_mean, float* running_var, float momentum, float eps, float* scale, float* shift,
+                       float* save_mean, float* save_invstd, void* stream);
+/* y = [relu]( x*scale[c] + shift[c] (+ residual) ) */
+int combat_affine_act(const void* x, const void* residual, void* y, int dtype, long long R, int C, const float* scale,
+                      const float* shift, int relu, void* stream);
+/* backward of y = relu(x*scale+shift (+res)):  dyh = dy * [y > 0]
+ *   train: partial sums of dyh and dyh*xhat per channel (then combat_bn_bwd_finalize, combat_bn_bwd_apply)
+ *   eval : dx = dyh * scale directly (combat_bn_bwd_apply with dgamma/dbeta NULL)  */
+int combat_bn_bwd_reduce(const void* dy, const void* x, const void* y, int dtype, long long R, int C, const float* mean,
+                         const float* invstd, float* partial, int max_blocks, int* nblk_out_host, int relu, void* stream);
+int combat_bn_bwd_finalize(const float* partial, int nblk, int C, float* dgamma, float* dbeta, void* stream);
+/* train: dx = gamma*invstd*(dyh - dbeta/R - xhat*dgamma/R); eval (eval_scale != NULL): dx = dyh*eval_scale.
+ * dadd (optional) is added to dx (gradient arriving over an identity shortcut); dres (optional) receives dyh. */
+int combat_bn_bwd_apply(const void* dy, const void* x, const void* y, const void* dadd, void* dx, void* dres, int dtype,
+                        long long R, int C, const float* gamma, const float* mean, const float* invstd,
+                        const float* dgamma, const float* dbeta, const float* eval_scale, int relu, void* stream);
+
+/* InstanceNorm2d(affine=False, eps) + LeakyReLU(slope) (+ skip), networks/models.py:273-340.
+ *   y = IN(x); if (act) y = leaky_relu(y); if (skip) y += skip     ; saves mean/invstd [N,C] */
+int combat_instnorm_fwd(const void* x, const void* skip, void* y, int dtype, int N, int HW, int C, float eps, float slope,
+                        int act, float* save_mean, float* save_invstd, void* stream);
+/* dy = dy1 (+ dy2); dyh = act ? dy*lrelu'(xhat) : dy; dx = invstd*(dyh - mean(dyh) - xhat*mean(dyh*xhat)) */
+int combat_instnorm_bwd(const void* dy1, const void* dy2, const void* x, void* dx, int dtype, int N, int HW, int C,
+                        float slope, int act, const float* mean, const float* invstd, void* stream);
+/* t = leaky_relu(bilinear_up2x(x)) (align_corners=False), networks/models.py:274; slope==1 -> no activation */
+int combat_upsample2x_act(const void* x, void* y, int dtype, int N, int H, int W, int C, float slope, void* stream);
+int combat_upsample2x_act_bwd(const void* dy, const void* y, void* dx, int dtype, int N, int H, int W, int C, float slope,
+                              void* stream);
+/* y = leaky_relu(x) elementwise and its backward (used for conv0_0 output, networks/models.py:321) */
+int combat_leaky_relu(const void* x, void* y, int dtype, long long n, float slope, void* stream);
+int combat_leaky_relu_bwd(const void* dy, const void* x, void* dx, int dtype, long long n, float slope, void* stream);
+/* dz = dy*(1-y^2) for y = tanh(z), NCHW float32 (networks/models.py:340) */
+int combat_tanh_bwd(const float* dy, const float* y, float* dz, long long n, void* stream);
+/* column sums over rows of a [R,C] matrix: out[c] (+)= sum_r x[r,c]  (conv bias gradient) */
+int combat_colsum(const void* x, int dtype, long long R, int C, float* out, void* stream);
+/* avg_pool2d(P) + flatten(NCHW order) + Linear (preact_resnet.py:99-101, resnet.py:95-97) */
+int combat_pool_linear_fwd(const void* x, int dtype, int B, int Hf, int Wf, int C, int P, const float* W, const float* b,
+                           int ncls, float* pooled, float* logits, void* stream);
+int combat_pool_linear_bwd(const float* dlogits, const float* pooled, const float* W, int B, int Hf, int Wf, int C, int P,
+                           int ncls, void* dx, int dtype, float* dW, float* db, void* stream);
+/* max_pool2d(2) NHWC (defenses/frequency_based/model.py:21,32,43) */
+int combat_maxpool2(const void* x, void* y, int dtype, int N, int H, int W, int C, void* stream);
+/* layout/dtype helpers */
+int combat_nchw_to_nhwc(const float* x, void* y, int dtype, int N, int C, int H, int W, void* stream);
+int combat_nhwc_to_nchw(const void* x, int dtype, float* y, int N, int C, int H, int W, void* stream);
+int combat_onehot_planes(void* y, int dtype, const long long* labels, int N, int HW, int Ctot, int c_off, int ncls,
+                         void* stream);
+/* dst[pix, c_off + c] = leaky_relu(src[pix, c]): activated copy into a channel slice (networks/models.py:524-531) */
+int combat_lrelu_into_slice(const void* src, void* dst, int dtype, long long npix, int Csrc, int Cdst, int c_off,
+                            float slope, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
