@@ -34,7 +34,7 @@ class ConvDesc(C.Structure):
 class ConvTcDesc(C.Structure):
     _fields_ = [("in_", vp), ("w", vp), ("out", vp), ("bias", vp), ("residual", vp), ("stats", vp),
                 ("N", i32), ("Hi", i32), ("Wi", i32), ("Ci", i32), ("Ho", i32), ("Wo", i32), ("Co", i32),
-                ("KH", i32), ("KW", i32), ("stride", i32), ("pad", i32), ("up", i32)]
+                ("KH", i32), ("KW", i32), ("stride", i32), ("pad", i32), ("up", i32), ("out_f32", i32), ("res_f32", i32)]
 
 
 P = C.POINTER
@@ -57,12 +57,12 @@ _SIGS = {
     "combat_conv_tc_supported": ([P(ConvTcDesc)], i32),
     "combat_bn_stats": ([vp, i32, i64, i32, vp, i32, P(i32), vp], i32),
     "combat_bn_finalize": ([vp, i32, i64, i32, vp, vp, vp, vp, f32, f32, vp, vp, vp, vp, vp], i32),
-    "combat_affine_act": ([vp, vp, vp, i32, i64, i32, vp, vp, i32, vp], i32),
-    "combat_bn_bwd_reduce": ([vp, vp, vp, i32, i64, i32, vp, vp, vp, i32, P(i32), i32, vp], i32),
+    "combat_affine_act": ([vp, i32, vp, vp, i32, i64, i32, vp, vp, i32, vp], i32),
+    "combat_bn_bwd_reduce": ([vp, vp, i32, vp, i32, i64, i32, vp, vp, vp, i32, P(i32), i32, vp], i32),
     "combat_bn_bwd_finalize": ([vp, i32, i32, vp, vp, vp], i32),
-    "combat_bn_bwd_apply": ([vp, vp, vp, vp, vp, vp, i32, i64, i32, vp, vp, vp, vp, vp, vp, i32, vp], i32),
-    "combat_instnorm_fwd": ([vp, vp, vp, i32, i32, i32, i32, f32, f32, i32, vp, vp, vp], i32),
-    "combat_instnorm_bwd": ([vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, vp, vp, vp], i32),
+    "combat_bn_bwd_apply": ([vp, vp, i32, vp, vp, vp, vp, i32, i64, i32, vp, vp, vp, vp, vp, vp, i32, vp], i32),
+    "combat_instnorm_fwd": ([vp, i32, vp, vp, i32, i32, i32, i32, f32, f32, i32, vp, vp, vp], i32),
+    "combat_instnorm_bwd": ([vp, vp, vp, i32, vp, i32, i32, i32, i32, f32, i32, vp, vp, vp], i32),
     "combat_upsample2x_act": ([vp, vp, i32, i32, i32, i32, i32, f32, vp], i32),
     "combat_upsample2x_act_bwd": ([vp, vp, vp, i32, i32, i32, i32, i32, f32, vp], i32),
     "combat_leaky_relu": ([vp, vp, i32, i64, f32, vp], i32),

@@ -134,9 +134,10 @@ struct TcParams {
   int BW, BH, BNI;        // pixel box, BW*BH*BNI == 128
   int tiles_w, tiles_h, tiles_n, tiles_co, n_classes, total_tiles;
   int kchunks;            // Ci / 64
-  bf16* out;
-  const bf16* residual;
+  void* out;             // bf16 or float32 (out_f32)
+  const void* residual;  // bf16 or float32 (res_f32)
   const float* bias;
+  int out_f32, res_f32;
   TcTaps taps;
 };
 
@@ -309,29 +310,44 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
             }
           }
           if (p.residual) {
-            const uint4* rp = (const uint4*)(p.residual + obase + c0);
+            if (p.res_f32) {
+              const float4* rp = (const float4*)((const float*)p.residual + obase + c0);
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              uint4 rr = rp[j];
-              const uint32_t w4[4] = {rr.x, rr.y, rr.z, rr.w};
+              for (int j = 0; j < 4; ++j) {
+                float4 rr = rp[j];
+                f[4 * j] += rr.x; f[4 * j + 1] += rr.y; f[4 * j + 2] += rr.z; f[4 * j + 3] += rr.w;
+              }
+            } else {
+              const uint4* rp = (const uint4*)((const bf16*)p.residual + obase + c0);
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                float2 t2 = __bfloat1622float2(*(const __nv_bfloat162*)&w4[q]);
-                f[8 * j + 2 * q] += t2.x;
-                f[8 * j + 2 * q + 1] += t2.y;
+              for (int j = 0; j < 2; ++j) {
+                uint4 rr = rp[j];
+                const uint32_t w4[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  float2 t2 = __bfloat1622float2(*(const __nv_bfloat162*)&w4[q]);
+                  f[8 * j + 2 * q] += t2.x;
+                  f[8 * j + 2 * q + 1] += t2.y;
+                }
               }
             }
           }
-          uint4* op = (uint4*)(p.out + obase + c0);
+          if (p.out_f32) {
+            float4* op = (float4*)((float*)p.out + obase + c0);
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            uint32_t w4[4];
+            for (int j = 0; j < 4; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          } else {
+            uint4* op = (uint4*)((bf16*)p.out + obase + c0);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(f[8 * j + 2 * q], f[8 * j + 2 * q + 1]);
-              w4[q] = *(uint32_t*)&h2;
+            for (int j = 0; j < 2; ++j) {
+              uint32_t w4[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[8 * j + 2 * q], f[8 * j + 2 * q + 1]);
+                w4[q] = *(uint32_t*)&h2;
+              }
+              op[j] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
             }
-            op[j] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
           }
         }
       }
@@ -448,9 +464,11 @@ extern "C" int combat_conv_tc(const combat_conv_tc_desc* d, void* stream) {
   p.out_W = d->Wo;
   p.Co = d->Co;
   p.kchunks = d->Ci / KCHUNK;
-  p.out = (bf16*)d->out;
-  p.residual = (const bf16*)d->residual;
+  p.out = d->out;
+  p.residual = d->residual;
   p.bias = d->bias;
+  p.out_f32 = d->out_f32;
+  p.res_f32 = d->res_f32;
   const int BLOCK_N = (d->Co % 128 == 0) ? 128 : 64;
   p.tiles_co = d->Co / BLOCK_N;
   int rc;

@@ -100,14 +100,14 @@ __global__ void bn_finalize_k(const float* __restrict__ partial, int nblk, long 
   if (save_mean) { save_mean[c] = mean; save_invstd[c] = invstd; }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) affine_act_k(const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ y,
+template <typename TX, typename T>
+__global__ void __launch_bounds__(256) affine_act_k(const TX* __restrict__ x, const T* __restrict__ res, T* __restrict__ y,
                                                     long long n2, int C, const float* __restrict__ scale,
                                                     const float* __restrict__ shift, int relu) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
     const long long e = i * 2;
     const int c = (int)(e % C);
-    float2 v = ld2<T>(x + e);
+    float2 v = ld2<TX>(x + e);
     v.x = fmaf(v.x, scale[c], shift[c]);
     v.y = fmaf(v.y, scale[c + 1], shift[c + 1]);
     if (res) {
@@ -119,8 +119,8 @@ __global__ void __launch_bounds__(256) affine_act_k(const T* __restrict__ x, con
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) bn_bwd_reduce_k(const T* __restrict__ dy, const T* __restrict__ x,
+template <typename TX, typename T>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_k(const T* __restrict__ dy, const TX* __restrict__ x,
                                                        const T* __restrict__ y, long long R, int C,
                                                        long long rows_per_block, const float* __restrict__ mean,
                                                        const float* __restrict__ invstd, float* __restrict__ partial,
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_k(const T* __restrict__ dy,
         if (!(yy.x > 0.f)) g.x = 0.f;
         if (!(yy.y > 0.f)) g.y = 0.f;
       }
-      float2 v = ld2<T>(x + r * C + c);
+      float2 v = ld2<TX>(x + r * C + c);
       s.x += g.x; s.y += g.y;
       sx.x = fmaf(g.x, (v.x - m0) * i0, sx.x);
       sx.y = fmaf(g.y, (v.y - m1) * i1, sx.y);
@@ -166,8 +166,8 @@ __global__ void bn_bwd_finalize_k(const float* __restrict__ partial, int nblk, i
   dgamma[c] = (float)sx;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) bn_bwd_apply_k(const T* __restrict__ dy, const T* __restrict__ x,
+template <typename TX, typename T>
+__global__ void __launch_bounds__(256) bn_bwd_apply_k(const T* __restrict__ dy, const TX* __restrict__ x,
                                                       const T* __restrict__ y, const T* __restrict__ dadd,
                                                       T* __restrict__ dx, T* __restrict__ dres, long long n2, long long R,
                                                       int C, const float* __restrict__ gamma,
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_k(const T* __restrict__ dy, 
       o.x = g.x * eval_scale[c];
       o.y = g.y * eval_scale[c + 1];
     } else {
-      float2 v = ld2<T>(x + e);
+      float2 v = ld2<TX>(x + e);
       const float g0 = gamma ? gamma[c] : 1.f, g1 = gamma ? gamma[c + 1] : 1.f;
       float xh0 = (v.x - mean[c]) * invstd[c], xh1 = (v.y - mean[c + 1]) * invstd[c + 1];
       o.x = g0 * invstd[c] * (g.x - dbeta[c] * invR - xh0 * dgamma[c] * invR);
@@ -203,6 +203,13 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_k(const T* __restrict__ dy, 
     st2<T>(dx + e, o);
   }
 }
+
+// TX = dtype of the pre-normalisation tensor (conv output), T = dtype of activations / gradients
+#define DISPATCH_2(xdt, dt, ...)                 \
+  if ((xdt) == COMBAT_F32 && (dt) == COMBAT_F32) { typedef float TX; typedef float T; __VA_ARGS__ } \
+  else if ((xdt) == COMBAT_F32) { typedef float TX; typedef bf16 T; __VA_ARGS__ }                   \
+  else if ((dt) == COMBAT_F32) { typedef bf16 TX; typedef float T; __VA_ARGS__ }                    \
+  else { typedef bf16 TX; typedef bf16 T; __VA_ARGS__ }
 
 static inline int ew_grid(long long n) {
   long long g = (n + 255) / 256;
@@ -243,18 +250,18 @@ extern "C" int combat_bn_finalize(const float* partial, int nblk, long long R, i
   COMBAT_RETURN_LAUNCH("bn_finalize");
 }
 
-extern "C" int combat_affine_act(const void* x, const void* residual, void* y, int dtype, long long R, int C,
+extern "C" int combat_affine_act(const void* x, int x_dtype, const void* residual, void* y, int dtype, long long R, int C,
                                  const float* scale, const float* shift, int relu, void* stream) {
   COMBAT_ARG(x && y && scale && shift, 0);
   COMBAT_ARG((C % 2) == 0, 5);
   long long n2 = R * C / 2;
   if (n2 <= 0) return 0;
-  DISPATCH_DTYPE(dtype, affine_act_k<T><<<ew_grid(n2), 256, 0, (cudaStream_t)stream>>>((const T*)x, (const T*)residual, (T*)y,
-                                                                                        n2, C, scale, shift, relu);)
+  DISPATCH_2(x_dtype, dtype, affine_act_k<TX, T><<<ew_grid(n2), 256, 0, (cudaStream_t)stream>>>(
+                                 (const TX*)x, (const T*)residual, (T*)y, n2, C, scale, shift, relu);)
   COMBAT_RETURN_LAUNCH("affine_act");
 }
 
-extern "C" int combat_bn_bwd_reduce(const void* dy, const void* x, const void* y, int dtype, long long R, int C,
+extern "C" int combat_bn_bwd_reduce(const void* dy, const void* x, int x_dtype, const void* y, int dtype, long long R, int C,
                                     const float* mean, const float* invstd, float* partial, int max_blocks,
                                     int* nblk_out_host, int relu, void* stream) {
   COMBAT_ARG(dy && x && partial && mean && invstd && nblk_out_host, 0);
@@ -263,8 +270,8 @@ extern "C" int combat_bn_bwd_reduce(const void* dy, const void* x, const void* y
   int nblk = cr_plan(R, max_blocks, &rpb);
   *nblk_out_host = nblk;
   dim3 grid(nblk, cdiv(C, CR_CPB)), block(CR_TX, CR_TY);
-  DISPATCH_DTYPE(dtype, bn_bwd_reduce_k<T><<<grid, block, 0, (cudaStream_t)stream>>>((const T*)dy, (const T*)x, (const T*)y, R,
-                                                                                    C, rpb, mean, invstd, partial, relu);)
+  DISPATCH_2(x_dtype, dtype, bn_bwd_reduce_k<TX, T><<<grid, block, 0, (cudaStream_t)stream>>>(
+                                 (const T*)dy, (const TX*)x, (const T*)y, R, C, rpb, mean, invstd, partial, relu);)
   COMBAT_RETURN_LAUNCH("bn_bwd_reduce");
 }
 
@@ -274,8 +281,8 @@ extern "C" int combat_bn_bwd_finalize(const float* partial, int nblk, int C, flo
   COMBAT_RETURN_LAUNCH("bn_bwd_finalize");
 }
 
-extern "C" int combat_bn_bwd_apply(const void* dy, const void* x, const void* y, const void* dadd, void* dx, void* dres,
-                                   int dtype, long long R, int C, const float* gamma, const float* mean,
+extern "C" int combat_bn_bwd_apply(const void* dy, const void* x, int x_dtype, const void* y, const void* dadd, void* dx,
+                                   void* dres, int dtype, long long R, int C, const float* gamma, const float* mean,
                                    const float* invstd, const float* dgamma, const float* dbeta, const float* eval_scale,
                                    int relu, void* stream) {
   COMBAT_ARG(dy && dx, 0);
@@ -283,16 +290,16 @@ extern "C" int combat_bn_bwd_apply(const void* dy, const void* x, const void* y,
   COMBAT_ARG(!relu || y, 2);
   long long n2 = R * C / 2;
   if (n2 <= 0) return 0;
-  DISPATCH_DTYPE(dtype, bn_bwd_apply_k<T><<<ew_grid(n2), 256, 0, (cudaStream_t)stream>>>(
-                            (const T*)dy, (const T*)x, (const T*)y, (const T*)dadd, (T*)dx, (T*)dres, n2, R, C, gamma, mean,
-                            invstd, dgamma, dbeta, eval_scale, relu);)
+  DISPATCH_2(x_dtype, dtype, bn_bwd_apply_k<TX, T><<<ew_grid(n2), 256, 0, (cudaStream_t)stream>>>(
+                                 (const T*)dy, (const TX*)x, (const T*)y, (const T*)dadd, (T*)dx, (T*)dres, n2, R, C, gamma,
+                                 mean, invstd, dgamma, dbeta, eval_scale, relu);)
   COMBAT_RETURN_LAUNCH("bn_bwd_apply");
 }
 
 // ------------------------------------------------------------------ InstanceNorm + LeakyReLU (+ skip)
 // grid = (N, C/64), block (32, 8).  Three cached passes: mean, centred variance, apply.
-template <typename T>
-__global__ void __launch_bounds__(256) instnorm_fwd_k(const T* __restrict__ x, const T* __restrict__ skip, T* __restrict__ y,
+template <typename TX, typename T>
+__global__ void __launch_bounds__(256) instnorm_fwd_k(const TX* __restrict__ x, const T* __restrict__ skip, T* __restrict__ y,
                                                       int HW, int C, float eps, float slope, int act,
                                                       float* __restrict__ save_mean, float* __restrict__ save_invstd) {
   const int n = blockIdx.x;
@@ -302,7 +309,7 @@ __global__ void __launch_bounds__(256) instnorm_fwd_k(const T* __restrict__ x, c
   float2 s = {0.f, 0.f}, dummy = {0.f, 0.f};
   if (ok)
     for (int r = threadIdx.y; r < HW; r += CR_TY) {
-      float2 v = ld2<T>(x + base + (long long)r * C);
+      float2 v = ld2<TX>(x + base + (long long)r * C);
       s.x += v.x; s.y += v.y;
     }
   block_reduce_y(s, dummy);
@@ -313,7 +320,7 @@ __global__ void __launch_bounds__(256) instnorm_fwd_k(const T* __restrict__ x, c
   float2 q = {0.f, 0.f};
   if (ok)
     for (int r = threadIdx.y; r < HW; r += CR_TY) {
-      float2 v = ld2<T>(x + base + (long long)r * C);
+      float2 v = ld2<TX>(x + base + (long long)r * C);
       float a = v.x - mean.x, b = v.y - mean.y;
       q.x = fmaf(a, a, q.x); q.y = fmaf(b, b, q.y);
     }
@@ -331,7 +338,7 @@ __global__ void __launch_bounds__(256) instnorm_fwd_k(const T* __restrict__ x, c
   if (ok)
     for (int r = threadIdx.y; r < HW; r += CR_TY) {
       const long long o = base + (long long)r * C;
-      float2 v = ld2<T>(x + o);
+      float2 v = ld2<TX>(x + o);
       v.x = (v.x - mean.x) * inv.x;
       v.y = (v.y - mean.y) * inv.y;
       if (act) {
@@ -346,9 +353,9 @@ __global__ void __launch_bounds__(256) instnorm_fwd_k(const T* __restrict__ x, c
     }
 }
 
-template <typename T>
+template <typename TX, typename T>
 __global__ void __launch_bounds__(256) instnorm_bwd_k(const T* __restrict__ dy1, const T* __restrict__ dy2,
-                                                      const T* __restrict__ x, T* __restrict__ dx, int HW, int C,
+                                                      const TX* __restrict__ x, T* __restrict__ dx, int HW, int C,
                                                       float slope, int act, const float* __restrict__ mean_,
                                                       const float* __restrict__ invstd_) {
   const int n = blockIdx.x;
@@ -366,7 +373,7 @@ __global__ void __launch_bounds__(256) instnorm_bwd_k(const T* __restrict__ dy1,
       const long long o = base + (long long)r * C;
       float2 g = ld2<T>(dy1 + o);
       if (dy2) { float2 g2 = ld2<T>(dy2 + o); g.x += g2.x; g.y += g2.y; }
-      float2 v = ld2<T>(x + o);
+      float2 v = ld2<TX>(x + o);
       float xh0 = (v.x - mean.x) * inv.x, xh1 = (v.y - mean.y) * inv.y;
       if (act) {
         if (!(xh0 > 0.f)) g.x *= slope;
@@ -388,7 +395,7 @@ __global__ void __launch_bounds__(256) instnorm_bwd_k(const T* __restrict__ dy1,
       const long long o = base + (long long)r * C;
       float2 g = ld2<T>(dy1 + o);
       if (dy2) { float2 g2 = ld2<T>(dy2 + o); g.x += g2.x; g.y += g2.y; }
-      float2 v = ld2<T>(x + o);
+      float2 v = ld2<TX>(x + o);
       float xh0 = (v.x - mean.x) * inv.x, xh1 = (v.y - mean.y) * inv.y;
       if (act) {
         if (!(xh0 > 0.f)) g.x *= slope;
@@ -401,23 +408,23 @@ __global__ void __launch_bounds__(256) instnorm_bwd_k(const T* __restrict__ dy1,
     }
 }
 
-extern "C" int combat_instnorm_fwd(const void* x, const void* skip, void* y, int dtype, int N, int HW, int C, float eps,
+extern "C" int combat_instnorm_fwd(const void* x, int x_dtype, const void* skip, void* y, int dtype, int N, int HW, int C, float eps,
                                    float slope, int act, float* save_mean, float* save_invstd, void* stream) {
   COMBAT_ARG(x && y && save_mean && save_invstd, 0);
   COMBAT_ARG(N > 0 && HW > 0 && C > 0 && (C % 2) == 0, 4);
   dim3 grid(N, cdiv(C, CR_CPB)), block(CR_TX, CR_TY);
-  DISPATCH_DTYPE(dtype, instnorm_fwd_k<T><<<grid, block, 0, (cudaStream_t)stream>>>((const T*)x, (const T*)skip, (T*)y, HW, C,
-                                                                                   eps, slope, act, save_mean, save_invstd);)
+  DISPATCH_2(x_dtype, dtype, instnorm_fwd_k<TX, T><<<grid, block, 0, (cudaStream_t)stream>>>(
+                                 (const TX*)x, (const T*)skip, (T*)y, HW, C, eps, slope, act, save_mean, save_invstd);)
   COMBAT_RETURN_LAUNCH("instnorm_fwd");
 }
 
-extern "C" int combat_instnorm_bwd(const void* dy1, const void* dy2, const void* x, void* dx, int dtype, int N, int HW,
+extern "C" int combat_instnorm_bwd(const void* dy1, const void* dy2, const void* x, int x_dtype, void* dx, int dtype, int N, int HW,
                                    int C, float slope, int act, const float* mean, const float* invstd, void* stream) {
   COMBAT_ARG(dy1 && x && dx && mean && invstd, 0);
   COMBAT_ARG(N > 0 && HW > 0 && C > 0 && (C % 2) == 0, 5);
   dim3 grid(N, cdiv(C, CR_CPB)), block(CR_TX, CR_TY);
-  DISPATCH_DTYPE(dtype, instnorm_bwd_k<T><<<grid, block, 0, (cudaStream_t)stream>>>((const T*)dy1, (const T*)dy2, (const T*)x,
-                                                                                   (T*)dx, HW, C, slope, act, mean, invstd);)
+  DISPATCH_2(x_dtype, dtype, instnorm_bwd_k<TX, T><<<grid, block, 0, (cudaStream_t)stream>>>(
+                                 (const T*)dy1, (const T*)dy2, (const TX*)x, (T*)dx, HW, C, slope, act, mean, invstd);)
   COMBAT_RETURN_LAUNCH("instnorm_bwd");
 }
 

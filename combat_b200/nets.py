@@ -115,6 +115,9 @@ class NetBase:
         self.dtype = dtype
         self.dt = ops.dt_code(dtype)
         self.use_tc = bool(use_tc) and dtype == torch.bfloat16
+        # conv outputs that feed a normalisation (and the residual stream) stay float32: statistics and the
+        # normalisation itself then see the unrounded fp32 accumulator; activations/gradients use `dtype`
+        self.pre_dtype = torch.float32
         self.convs: dict[str, ConvSpec] = {}
 
     # ---- construction helpers
@@ -159,12 +162,12 @@ class NetBase:
     def _tc_ok(self, cs: ConvSpec):
         return self.use_tc and cs.Cin % 64 == 0 and cs.Cout % 64 == 0
 
-    def conv_fwd(self, x, cs: ConvSpec, residual=None, x_cview=None):
-        """x: NHWC [N,H,W,Cin(+extra)] in compute dtype -> NHWC out."""
+    def conv_fwd(self, x, cs: ConvSpec, residual=None, pre=True):
+        """x: NHWC [N,H,W,Cin] in the activation dtype -> NHWC out (float32 when `pre`, i.e. feeding a norm)."""
         N, H, W, Ct = x.shape
         Ho = (H + 2 * cs.pad - cs.k) // cs.stride + 1
         Wo = (W + 2 * cs.pad - cs.k) // cs.stride + 1
-        out = torch.empty((N, Ho, Wo, cs.Cout), dtype=self.dtype, device=self.device)
+        out = torch.empty((N, Ho, Wo, cs.Cout), dtype=self.pre_dtype if pre else self.dtype, device=self.device)
         if self._tc_ok(cs) and Ct == cs.Cin:
             d = ops.conv_tc_desc(x, self._wptr(cs), out, N, H, W, cs.Cin, Ho, Wo, cs.Cout, cs.k, cs.k, cs.stride, cs.pad, 1,
                                  bias=self._bias(cs), residual=residual)
@@ -211,13 +214,13 @@ class NetBase:
                             Ci=cs.Cin, Co=cs.Cout, KH=cs.k, KW=cs.k, stride=cs.stride, pad=cs.pad, db=db)
 
     # ---- image-boundary convs (NCHW float32 on the 3-channel side), always CUDA-core kernels
-    def conv_first_fwd(self, x_nchw, cs: ConvSpec, out=None, out_ctot=None):
+    def conv_first_fwd(self, x_nchw, cs: ConvSpec, out=None, out_ctot=None, pre=True):
         N, Cc, H, W = x_nchw.shape
         Ho = (H + 2 * cs.pad - cs.k) // cs.stride + 1
         Wo = (W + 2 * cs.pad - cs.k) // cs.stride + 1
         Ct = cs.Cout if out_ctot is None else out_ctot
         if out is None:
-            out = torch.empty((N, Ho, Wo, Ct), dtype=self.dtype, device=self.device)
+            out = torch.empty((N, Ho, Wo, Ct), dtype=self.pre_dtype if pre else self.dtype, device=self.device)
         ops.conv_simt(x_nchw, (N, H, W), ops.nchw_strides(Cc, H, W), self._wptr(cs), self.dt, out, (Ho, Wo),
                       ops.nhwc_strides(Ho, Wo, Ct), Ci=cs.Cin, Co=cs.Cout, KH=cs.k, KW=cs.k, stride=cs.stride, pad=cs.pad,
                       bias=self._bias(cs))
@@ -352,7 +355,7 @@ class Classifier(NetBase):
         else:
             scale, shift = ops.bn_eval_prepare(Cc, g, b, self.rm(bn), self.rv(bn), self.eps)
             st = (scale, None, None)
-        y = ops.affine_act(x, scale, shift, relu, residual=residual)
+        y = ops.affine_act(x, scale, shift, relu, residual=residual, out_dtype=self.dtype)
         return y, st
 
     def _bn_bwd(self, bn, dy, x, y, st, train, relu, need_wgrad, dadd=None, want_dres=False):
@@ -502,7 +505,7 @@ class Generator(NetBase):
         N, _, H, W = x_nchw.shape
         nf = self.nf
         ctx = {"x": x_nchw} if save else None
-        c00 = self.conv_first_fwd(x_nchw, cv["conv0_0"])
+        c00 = self.conv_first_fwd(x_nchw, cv["conv0_0"], pre=False)
         if self.cond:  # cat(f0, one_hot planes) then the in-place LeakyReLU (identity on the 0/1 planes)
             a00 = torch.empty((N, H // 2, W // 2, nf + self.cond), dtype=self.dtype, device=self.device)
             ops.lrelu_into_slice(c00, a00, 0)
@@ -513,7 +516,7 @@ class Generator(NetBase):
 
         def down(name, xin, act=True):
             c = self.conv_fwd(xin, cv[name])
-            y, st = ops.instnorm_fwd(c, act)
+            y, st = ops.instnorm_fwd(c, act, out_dtype=self.dtype)
             acts[name] = (xin, c, st)
             return y
 
@@ -525,10 +528,10 @@ class Generator(NetBase):
         def up_block(n1, n0, xin, skip):
             t = ops.upsample2x_act(xin)
             c1 = self.conv_fwd(t, cv[n1])
-            a1, st1 = ops.instnorm_fwd(c1, True)
+            a1, st1 = ops.instnorm_fwd(c1, True, out_dtype=self.dtype)
             acts[n1] = (t, c1, st1)
             c0 = self.conv_fwd(a1, cv[n0])
-            u, st0 = ops.instnorm_fwd(c0, False, skip=skip)
+            u, st0 = ops.instnorm_fwd(c0, False, skip=skip, out_dtype=self.dtype)
             acts[n0] = (a1, c0, st0)
             return u
 
@@ -537,7 +540,7 @@ class Generator(NetBase):
         u1 = up_block("upconv1_1", "upconv1_0", u2, f0)
         t0 = ops.upsample2x_act(u1)
         c01 = self.conv_fwd(t0, cv["upconv0_1"])
-        a01, st01 = ops.instnorm_fwd(c01, True)
+        a01, st01 = ops.instnorm_fwd(c01, True, out_dtype=self.dtype)
         acts["upconv0_1"] = (t0, c01, st01)
         cs = cv["upconv0_0"]
         out = torch.empty((N, self.out_channel, H, W), dtype=torch.float32, device=self.device)

@@ -29,6 +29,8 @@ def dt_code(t: torch.Tensor | torch.dtype) -> int:
 def _p(t):
     if t is None:
         return None
+    if isinstance(t, int):  # raw device address (a slice of a larger device buffer)
+        return t
     if not t.is_cuda:
         raise RuntimeError("combat_b200 kernels need CUDA tensors (no CPU fallback)")
     return t.data_ptr()
@@ -221,6 +223,8 @@ def conv_wgrad_simt(x, x_geom, x_strides, dy, dy_geom, dy_strides, dw, *, Ci, Co
 def conv_tc_desc(x, w_ptr, out, N, Hi, Wi, Ci, Ho, Wo, Co, KH, KW, stride, pad, up, bias=None, residual=None, stats=None):
     d = ConvTcDesc()
     d.in_, d.w, d.out, d.bias, d.residual, d.stats = _p(x), w_ptr, _p(out), _p(bias), _p(residual), _p(stats)
+    d.out_f32 = int(out is not None and out.dtype == torch.float32)
+    d.res_f32 = int(residual is not None and residual.dtype == torch.float32)
     d.N, d.Hi, d.Wi, d.Ci, d.Ho, d.Wo, d.Co = N, Hi, Wi, Ci, Ho, Wo, Co
     d.KH, d.KW, d.stride, d.pad, d.up = KH, KW, stride, pad, up
     return d
@@ -262,13 +266,14 @@ def bn_eval_prepare(Cc, gamma, beta, rm, rv, eps):
     return st[0], st[1]
 
 
-def affine_act(x, scale, shift, relu, residual=None, out=None):
+def affine_act(x, scale, shift, relu, residual=None, out=None, out_dtype=None):
+    """x may be float32 (pre-normalisation tensor) while residual / output use the activation dtype."""
     Cc = x.shape[-1]
     R = x.numel() // Cc
     if out is None:
-        out = torch.empty_like(x)
-    check(lib.combat_affine_act(_p(x), _p(residual), _p(out), dt_code(x), R, Cc, _p(scale), _p(shift), int(relu), _s()),
-          "affine_act")
+        out = torch.empty(x.shape, dtype=out_dtype or x.dtype, device=x.device)
+    check(lib.combat_affine_act(_p(x), dt_code(x), _p(residual), _p(out), dt_code(out), R, Cc, _p(scale), _p(shift),
+                                int(relu), _s()), "affine_act")
     return out
 
 
@@ -278,13 +283,13 @@ def bn_bwd_train(dy, x, y, gamma, mean, invstd, relu, dgamma_out, dbeta_out, dad
     R = x.numel() // Cc
     partial = Scratch.get(x.device)
     nblk = C.c_int(0)
-    check(lib.combat_bn_bwd_reduce(_p(dy), _p(x), _p(y), dt_code(x), R, Cc, _p(mean), _p(invstd), _p(partial),
+    check(lib.combat_bn_bwd_reduce(_p(dy), _p(x), dt_code(x), _p(y), dt_code(dy), R, Cc, _p(mean), _p(invstd), _p(partial),
                                    _PARTIAL_BLOCKS, C.byref(nblk), int(relu), _s()), "bn_bwd_reduce")
     check(lib.combat_bn_bwd_finalize(_p(partial), nblk.value, Cc, _p(dgamma_out), _p(dbeta_out), _s()), "bn_bwd_finalize")
-    dx = torch.empty_like(x)
-    dres = torch.empty_like(x) if want_dres else None
-    check(lib.combat_bn_bwd_apply(_p(dy), _p(x), _p(y), _p(dadd), _p(dx), _p(dres), dt_code(x), R, Cc, _p(gamma), _p(mean),
-                                  _p(invstd), _p(dgamma_out), _p(dbeta_out), None, int(relu), _s()), "bn_bwd_apply")
+    dx = torch.empty_like(dy)
+    dres = torch.empty_like(dy) if want_dres else None
+    check(lib.combat_bn_bwd_apply(_p(dy), _p(x), dt_code(x), _p(y), _p(dadd), _p(dx), _p(dres), dt_code(dy), R, Cc, _p(gamma),
+                                  _p(mean), _p(invstd), _p(dgamma_out), _p(dbeta_out), None, int(relu), _s()), "bn_bwd_apply")
     return dx, dres
 
 
@@ -293,25 +298,25 @@ def bn_bwd_eval(dy, y, eval_scale, relu, dadd=None, want_dres=False):
     R = dy.numel() // Cc
     dx = torch.empty_like(dy)
     dres = torch.empty_like(dy) if want_dres else None
-    check(lib.combat_bn_bwd_apply(_p(dy), None, _p(y), _p(dadd), _p(dx), _p(dres), dt_code(dy), R, Cc, None, None, None,
-                                  None, None, _p(eval_scale), int(relu), _s()), "bn_bwd_apply(eval)")
+    check(lib.combat_bn_bwd_apply(_p(dy), None, dt_code(dy), _p(y), _p(dadd), _p(dx), _p(dres), dt_code(dy), R, Cc, None, None,
+                                  None, None, None, _p(eval_scale), int(relu), _s()), "bn_bwd_apply(eval)")
     return dx, dres
 
 
-def instnorm_fwd(x, act, skip=None, eps=1e-5, slope=0.2):
+def instnorm_fwd(x, act, skip=None, eps=1e-5, slope=0.2, out_dtype=None):
     N, H, W, Cc = x.shape
-    y = torch.empty_like(x)
+    y = torch.empty(x.shape, dtype=out_dtype or x.dtype, device=x.device)
     st = torch.empty((2, N, Cc), dtype=torch.float32, device=x.device)
-    check(lib.combat_instnorm_fwd(_p(x), _p(skip), _p(y), dt_code(x), N, H * W, Cc, eps, slope, int(act), _p(st[0]),
-                                  _p(st[1]), _s()), "instnorm_fwd")
+    check(lib.combat_instnorm_fwd(_p(x), dt_code(x), _p(skip), _p(y), dt_code(y), N, H * W, Cc, eps, slope, int(act),
+                                  _p(st[0]), _p(st[1]), _s()), "instnorm_fwd")
     return y, st
 
 
 def instnorm_bwd(dy1, dy2, x, st, act, slope=0.2):
     N, H, W, Cc = x.shape
-    dx = torch.empty_like(x)
-    check(lib.combat_instnorm_bwd(_p(dy1), _p(dy2), _p(x), _p(dx), dt_code(x), N, H * W, Cc, slope, int(act), _p(st[0]),
-                                  _p(st[1]), _s()), "instnorm_bwd")
+    dx = torch.empty_like(dy1)
+    check(lib.combat_instnorm_bwd(_p(dy1), _p(dy2), _p(x), dt_code(x), _p(dx), dt_code(dy1), N, H * W, Cc, slope, int(act),
+                                  _p(st[0]), _p(st[1]), _s()), "instnorm_bwd")
     return dx
 
 

@@ -127,11 +127,13 @@ int combat_conv_wgrad_simt(const combat_conv_desc* d_host, const void* dy, int d
 typedef struct {
   const void* in;        /* NHWC bf16 [N,Hi,Wi,Ci] */
   const void* w;         /* [taps][Co][Ci] bf16 (tap-major OHWI) */
-  void* out;             /* NHWC bf16 [N,Ho,Wo,Co] */
+  void* out;             /* NHWC [N,Ho,Wo,Co], bf16 or float32 (out_f32) */
   const float* bias;     /* or NULL */
-  const void* residual;  /* NHWC bf16 like out, or NULL */
-  float* stats;          /* optional [2*Co] per-channel sum / sum-of-squares of the fp32 result (BatchNorm train) */
+  const void* residual;  /* NHWC like out, bf16 or float32 (res_f32), or NULL */
+  float* stats;          /* reserved (fused BatchNorm statistics) */
   int N, Hi, Wi, Ci, Ho, Wo, Co, KH, KW, stride, pad, up;
+  int out_f32;           /* 1: `out` is float32 (pre-normalisation tensors keep the unrounded accumulator) */
+  int res_f32;           /* 1: `residual` is float32 */
 } combat_conv_tc_desc;
 int combat_conv_tc(const combat_conv_tc_desc* d_host, void* stream);
 int combat_conv_tc_wgrad(const combat_conv_tc_desc* d_host, const void* dy, float* dw_ohwi, void* stream);
@@ -147,27 +149,29 @@ int combat_bn_stats(const void* x, int dtype, long long R, int C, float* partial
 int combat_bn_finalize(const float* partial, int nblk, long long R, int C, const float* gamma, const float* beta,
                        float* running_mean, float* running_var, float momentum, float eps, float* scale, float* shift,
                        float* save_mean, float* save_invstd, void* stream);
-/* y = [relu]( x*scale[c] + shift[c] (+ residual) ) */
-int combat_affine_act(const void* x, const void* residual, void* y, int dtype, long long R, int C, const float* scale,
-                      const float* shift, int relu, void* stream);
+/* y = [relu]( x*scale[c] + shift[c] (+ residual) ).  x_dtype: storage type of the pre-normalisation tensor x (the
+ * conv output -- kept float32 next to bf16 activations so that statistics and normalisation see unrounded values);
+ * dtype: storage type of residual / y (and of every gradient tensor below). */
+int combat_affine_act(const void* x, int x_dtype, const void* residual, void* y, int dtype, long long R, int C,
+                      const float* scale, const float* shift, int relu, void* stream);
 /* backward of y = relu(x*scale+shift (+res)):  dyh = dy * [y > 0]
  *   train: partial sums of dyh and dyh*xhat per channel (then combat_bn_bwd_finalize, combat_bn_bwd_apply)
  *   eval : dx = dyh * scale directly (combat_bn_bwd_apply with dgamma/dbeta NULL)  */
-int combat_bn_bwd_reduce(const void* dy, const void* x, const void* y, int dtype, long long R, int C, const float* mean,
+int combat_bn_bwd_reduce(const void* dy, const void* x, int x_dtype, const void* y, int dtype, long long R, int C, const float* mean,
                          const float* invstd, float* partial, int max_blocks, int* nblk_out_host, int relu, void* stream);
 int combat_bn_bwd_finalize(const float* partial, int nblk, int C, float* dgamma, float* dbeta, void* stream);
 /* train: dx = gamma*invstd*(dyh - dbeta/R - xhat*dgamma/R); eval (eval_scale != NULL): dx = dyh*eval_scale.
  * dadd (optional) is added to dx (gradient arriving over an identity shortcut); dres (optional) receives dyh. */
-int combat_bn_bwd_apply(const void* dy, const void* x, const void* y, const void* dadd, void* dx, void* dres, int dtype,
-                        long long R, int C, const float* gamma, const float* mean, const float* invstd,
+int combat_bn_bwd_apply(const void* dy, const void* x, int x_dtype, const void* y, const void* dadd, void* dx, void* dres,
+                        int dtype, long long R, int C, const float* gamma, const float* mean, const float* invstd,
                         const float* dgamma, const float* dbeta, const float* eval_scale, int relu, void* stream);
 
 /* InstanceNorm2d(affine=False, eps) + LeakyReLU(slope) (+ skip), networks/models.py:273-340.
  *   y = IN(x); if (act) y = leaky_relu(y); if (skip) y += skip     ; saves mean/invstd [N,C] */
-int combat_instnorm_fwd(const void* x, const void* skip, void* y, int dtype, int N, int HW, int C, float eps, float slope,
+int combat_instnorm_fwd(const void* x, int x_dtype, const void* skip, void* y, int dtype, int N, int HW, int C, float eps, float slope,
                         int act, float* save_mean, float* save_invstd, void* stream);
 /* dy = dy1 (+ dy2); dyh = act ? dy*lrelu'(xhat) : dy; dx = invstd*(dyh - mean(dyh) - xhat*mean(dyh*xhat)) */
-int combat_instnorm_bwd(const void* dy1, const void* dy2, const void* x, void* dx, int dtype, int N, int HW, int C,
+int combat_instnorm_bwd(const void* dy1, const void* dy2, const void* x, int x_dtype, void* dx, int dtype, int N, int HW, int C,
                         float slope, int act, const float* mean, const float* invstd, void* stream);
 /* t = leaky_relu(bilinear_up2x(x)) (align_corners=False), networks/models.py:274; slope==1 -> no activation */
 int combat_upsample2x_act(const void* x, void* y, int dtype, int N, int H, int W, int C, float slope, void* stream);
