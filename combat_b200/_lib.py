@@ -34,7 +34,8 @@ class ConvDesc(C.Structure):
 class ConvTcDesc(C.Structure):
     _fields_ = [("in_", vp), ("w", vp), ("out", vp), ("bias", vp), ("residual", vp), ("stats", vp),
                 ("N", i32), ("Hi", i32), ("Wi", i32), ("Ci", i32), ("Ho", i32), ("Wo", i32), ("Co", i32),
-                ("KH", i32), ("KW", i32), ("stride", i32), ("pad", i32), ("up", i32), ("out_f32", i32), ("res_f32", i32)]
+                ("KH", i32), ("KW", i32), ("stride", i32), ("pad", i32), ("up", i32), ("out_f32", i32), ("res_f32", i32),
+                ("act", i32), ("post_scale", vp), ("post_shift", vp)]
 
 
 P = C.POINTER
@@ -52,6 +53,10 @@ _SIGS = {
     "combat_prep_weights": ([vp, vp, i32, vp, i32, i64, vp], i32),
     "combat_conv_simt": ([P(ConvDesc), vp], i32),
     "combat_conv_wgrad_simt": ([P(ConvDesc), vp, i32, vp, vp], i32),
+    "combat_conv_cin3": ([vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp], i32),
+    "combat_conv_cout3": ([vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, vp], i32),
+    "combat_wgrad_cin3": ([vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, vp], i32),
+    "combat_wgrad_cout3": ([vp, i32, vp, vp, vp, i32, i32, i32, i32, vp], i32),
     "combat_conv_tc": ([P(ConvTcDesc), vp], i32),
     "combat_conv_tc_wgrad": ([P(ConvTcDesc), vp, vp, vp], i32),
     "combat_conv_tc_supported": ([P(ConvTcDesc)], i32),

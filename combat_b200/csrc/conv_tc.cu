@@ -138,6 +138,9 @@ struct TcParams {
   const void* residual;  // bf16 or float32 (res_f32)
   const float* bias;
   int out_f32, res_f32;
+  int act;
+  const float* post_scale;
+  const float* post_shift;
   TcTaps taps;
 };
 
@@ -309,6 +312,20 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
               f[4 * j] += bb.x; f[4 * j + 1] += bb.y; f[4 * j + 2] += bb.z; f[4 * j + 3] += bb.w;
             }
           }
+          if (p.act == 2) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = f[j] > 0.f ? f[j] : expm1f(f[j]);
+          }
+          if (p.post_scale) {
+            const float4* sp = (const float4*)(p.post_scale + cot * BLOCK_N + c0);
+            const float4* hp = (const float4*)(p.post_shift + cot * BLOCK_N + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float4 ss = sp[j], hh = hp[j];
+              f[4 * j] = fmaf(f[4 * j], ss.x, hh.x); f[4 * j + 1] = fmaf(f[4 * j + 1], ss.y, hh.y);
+              f[4 * j + 2] = fmaf(f[4 * j + 2], ss.z, hh.z); f[4 * j + 3] = fmaf(f[4 * j + 3], ss.w, hh.w);
+            }
+          }
           if (p.residual) {
             if (p.res_f32) {
               const float4* rp = (const float4*)((const float*)p.residual + obase + c0);
@@ -469,6 +486,9 @@ extern "C" int combat_conv_tc(const combat_conv_tc_desc* d, void* stream) {
   p.bias = d->bias;
   p.out_f32 = d->out_f32;
   p.res_f32 = d->res_f32;
+  p.act = d->act;
+  p.post_scale = d->post_scale;
+  p.post_shift = d->post_shift;
   const int BLOCK_N = (d->Co % 128 == 0) ? 128 : 64;
   p.tiles_co = d->Co / BLOCK_N;
   int rc;

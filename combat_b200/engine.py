@@ -89,7 +89,7 @@ class AlternatedStep:
     refreshing the small per-iteration parameter block (perm, targets, num_bd, blur taps, learning rates)."""
 
     def __init__(self, opt=None, device="cuda", dtype=torch.bfloat16, classifier="preact_resnet18", with_metrics=True,
-                 use_tc=True, cond_classes=0, grad_hook=None):
+                 use_tc=True, cond_classes=0, grad_hook=None, buf_hook=None):
         self.opt = opt or default_opt()
         o = self.opt
         self.device = torch.device(device)
@@ -100,11 +100,13 @@ class AlternatedStep:
         self.netC = Classifier(classifier, o.num_classes, o.input_channel, H, **mk)
         self.clean = Classifier(classifier, o.num_classes, o.input_channel, H, **mk)
         self.netG = Generator(o.input_channel, 64, cond_classes, **mk)
-        self.netF = FrequencyDetector(2, o.input_channel, H, device=self.device) if (with_metrics and H in (32, 64)) else None
+        self.netF = FrequencyDetector(2, o.input_channel, H, device=self.device, dtype=dtype) if (with_metrics and H in (32, 64)) else None
         self.keep = int(H * o.ratio)
         self.lr_C = torch.full((1,), float(o.lr_C), dtype=torch.float32, device=self.device)
         self.lr_G = torch.full((1,), float(o.lr_G), dtype=torch.float32, device=self.device)
         self.grad_hook = grad_hook  # callable(net_name, flat_grad_tensor): data-parallel all-reduce
+        self.buf_hook = buf_hook    # callable(flat_running_stats): keeps BatchNorm buffers identical across ranks
+        self.launches_per_step = 0  # kernels of this library launched by one iteration (counted on the last eager/capture pass)
         self._bufs = None
         self._graph = None
 
@@ -179,6 +181,14 @@ class AlternatedStep:
 
     # ------------------------------------------------------------ the step
     def _launch(self, b, keep_debug=False):
+        from ._lib import launch_count
+        n0 = launch_count()
+        try:
+            return self._launch_impl(b, keep_debug)
+        finally:
+            self.launches_per_step = launch_count() - n0
+
+    def _launch_impl(self, b, keep_debug=False):
         o = self.opt
         x, y = b["x"], b["y"]
         B = b["B"]
@@ -200,6 +210,8 @@ class AlternatedStep:
         if self.grad_hook is not None:
             self.grad_hook("netC", self.netC.store.grad)
         self.netC.sgd_step(self.lr_C)                                                        # :212
+        if self.buf_hook is not None:
+            self.buf_hook(self.netC.bufs)
         del ctxC
         if self.with_metrics:
             clean_preds, _ = self.clean.forward(x, train=False, save=False)                  # :214

@@ -22,6 +22,22 @@ from . import ops
 from ._lib import check, lib
 
 
+# Optional per-launch timing of the tensor-core convolutions (bench.py's roofline leg): when TC_PROFILE is a list,
+# every tcgen05 launch is bracketed by CUDA events on the launching stream and (name, flops, start, end) is appended.
+TC_PROFILE = None
+
+
+def _tc_launch(fn, name, flops):
+    if TC_PROFILE is None:
+        check(fn(), name)
+        return
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    check(fn(), name)
+    e.record()
+    TC_PROFILE.append((name, flops, s, e))
+
+
 def _align(n, a=4):
     return (n + a - 1) // a * a
 
@@ -118,6 +134,7 @@ class NetBase:
         # conv outputs that feed a normalisation (and the residual stream) stay float32: statistics and the
         # normalisation itself then see the unrounded fp32 accumulator; activations/gradients use `dtype`
         self.pre_dtype = torch.float32
+        self.fast_small = True  # direct kernels for the 3-channel boundary layers (csrc/conv_small.cu)
         self.convs: dict[str, ConvSpec] = {}
 
     # ---- construction helpers
@@ -172,7 +189,7 @@ class NetBase:
             d = ops.conv_tc_desc(x, self._wptr(cs), out, N, H, W, cs.Cin, Ho, Wo, cs.Cout, cs.k, cs.k, cs.stride, cs.pad, 1,
                                  bias=self._bias(cs), residual=residual)
             if lib.combat_conv_tc_supported(C.byref(d)):
-                check(lib.combat_conv_tc(C.byref(d), ops._s()), "conv_tc")
+                _tc_launch(lambda: lib.combat_conv_tc(C.byref(d), ops._s()), "conv_tc", 2.0 * N * Ho * Wo * cs.Cout * cs.Cin * cs.k * cs.k)
                 return out
         ops.conv_simt(x, (N, H, W), ops.nhwc_strides(H, W, Ct), self._wptr(cs), self.dt, out, (Ho, Wo),
                       ops.nhwc_strides(Ho, Wo, cs.Cout), Ci=cs.Cin, Co=cs.Cout, KH=cs.k, KW=cs.k, stride=cs.stride,
@@ -190,7 +207,7 @@ class NetBase:
             d = ops.conv_tc_desc(dy, self._wptr(cs, True), dx, N, Ho, Wo, cs.Cout, H, W, cs.Cin, cs.k, cs.k, 1, padp,
                                  cs.stride, residual=residual)
             if lib.combat_conv_tc_supported(C.byref(d)):
-                check(lib.combat_conv_tc(C.byref(d), ops._s()), "conv_tc(dgrad)")
+                _tc_launch(lambda: lib.combat_conv_tc(C.byref(d), ops._s()), "conv_tc(dgrad)", 2.0 * N * Ho * Wo * cs.Cout * cs.Cin * cs.k * cs.k)
                 return dx
         ops.conv_simt(dy, (N, Ho, Wo), ops.nhwc_strides(Ho, Wo, cs.Cout), self._wptr(cs, True), self.dt, dx, (H, W),
                       ops.nhwc_strides(H, W, Cx), Ci=cs.Cout, Co=Cx, KH=cs.k, KW=cs.k, stride=1, pad=padp, up=cs.stride,
@@ -206,7 +223,7 @@ class NetBase:
         if self._tc_ok(cs) and Ct == cs.Cin:
             d = ops.conv_tc_desc(x, None, None, N, H, W, cs.Cin, Ho, Wo, cs.Cout, cs.k, cs.k, cs.stride, cs.pad, 1)
             if lib.combat_conv_tc_supported(C.byref(d)):
-                check(lib.combat_conv_tc_wgrad(C.byref(d), ops._p(dy), ops._p(dw), ops._s()), "conv_tc_wgrad")
+                _tc_launch(lambda: lib.combat_conv_tc_wgrad(C.byref(d), ops._p(dy), ops._p(dw), ops._s()), "conv_tc_wgrad", 2.0 * N * Ho * Wo * cs.Cout * cs.Cin * cs.k * cs.k)
                 if db is not None:
                     ops.colsum(dy, cs.Cout, db)
                 return
@@ -221,6 +238,8 @@ class NetBase:
         Ct = cs.Cout if out_ctot is None else out_ctot
         if out is None:
             out = torch.empty((N, Ho, Wo, Ct), dtype=self.pre_dtype if pre else self.dtype, device=self.device)
+        if self.fast_small and Cc == 3 and cs.k == 3 and cs.pad == 1 and Ct == cs.Cout and cs.Cout % 32 == 0 and 256 % cs.Cout == 0:
+            return ops.conv_cin3(x_nchw, self._wptr(cs), self.dt, out, cs.Cout, cs.stride, bias=self._bias(cs))
         ops.conv_simt(x_nchw, (N, H, W), ops.nchw_strides(Cc, H, W), self._wptr(cs), self.dt, out, (Ho, Wo),
                       ops.nhwc_strides(Ho, Wo, Ct), Ci=cs.Cin, Co=cs.Cout, KH=cs.k, KW=cs.k, stride=cs.stride, pad=cs.pad,
                       bias=self._bias(cs))
@@ -229,6 +248,9 @@ class NetBase:
     def conv_first_wgrad(self, x_nchw, dy, cs: ConvSpec, dy_ctot=None):
         N, Cc, H, W = x_nchw.shape
         _, Ho, Wo, Ct = dy.shape
+        if self.fast_small and Cc == 3 and cs.k == 3 and cs.pad == 1 and Ct == cs.Cout and cs.Cout % 32 == 0 and 256 % cs.Cout == 0:
+            return ops.wgrad_cin3(x_nchw, dy, self.store.raw(self.store.grad, cs.name + ".weight"),
+                                  self.store.g(cs.name + ".bias") if cs.bias else None, cs.Cout, cs.stride)
         ops.conv_wgrad_simt(x_nchw, (N, H, W), ops.nchw_strides(Cc, H, W), dy, (Ho, Wo), ops.nhwc_strides(Ho, Wo, Ct),
                             self.store.raw(self.store.grad, cs.name + ".weight"), Ci=cs.Cin, Co=cs.Cout, KH=cs.k, KW=cs.k, stride=cs.stride,
                             pad=cs.pad, db=self.store.g(cs.name + ".bias") if cs.bias else None)
@@ -238,6 +260,8 @@ class NetBase:
         N, Ho, Wo, _ = dy.shape
         H, W = in_hw
         dx = torch.empty((N, cs.Cin, H, W), dtype=torch.float32, device=self.device)
+        if self.fast_small and cs.Cin == 3 and cs.Cout == 64 and cs.k == 3 and cs.pad == 1 and cs.stride == 1:
+            return ops.conv_cout3(dy, self._wptr(cs, True), self.dt, dx)
         ops.conv_simt(dy, (N, Ho, Wo), ops.nhwc_strides(Ho, Wo, cs.Cout), self._wptr(cs, True), self.dt, dx, (H, W),
                       ops.nchw_strides(cs.Cin, H, W), Ci=cs.Cout, Co=cs.Cin, KH=cs.k, KW=cs.k, stride=1,
                       pad=cs.k - 1 - cs.pad, up=cs.stride)
@@ -544,9 +568,13 @@ class Generator(NetBase):
         acts["upconv0_1"] = (t0, c01, st01)
         cs = cv["upconv0_0"]
         out = torch.empty((N, self.out_channel, H, W), dtype=torch.float32, device=self.device)
-        ops.conv_simt(a01, (N, H, W), ops.nhwc_strides(H, W, nf), self._wptr(cs), self.dt, out, (H, W),
-                      ops.nchw_strides(self.out_channel, H, W), Ci=nf, Co=self.out_channel, KH=3, KW=3, stride=1, pad=1,
-                      bias=self._bias(cs), act=1)
+        small = self.fast_small and nf == 64 and self.out_channel == 3
+        if small:
+            ops.conv_cout3(a01, self._wptr(cs), self.dt, out, bias=self._bias(cs), act=1)
+        else:
+            ops.conv_simt(a01, (N, H, W), ops.nhwc_strides(H, W, nf), self._wptr(cs), self.dt, out, (H, W),
+                          ops.nchw_strides(self.out_channel, H, W), Ci=nf, Co=self.out_channel, KH=3, KW=3, stride=1, pad=1,
+                          bias=self._bias(cs), act=1)
         if save:
             acts["a01"] = a01
             ctx["acts"], ctx["out"] = acts, out
@@ -562,12 +590,16 @@ class Generator(NetBase):
         cs = cv["upconv0_0"]
         a01 = acts["a01"]
         nchw_o = ops.nchw_strides(self.out_channel, H, W)
-        ops.conv_wgrad_simt(a01, (N, H, W), ops.nhwc_strides(H, W, nf), dz, (H, W), nchw_o,
-                            self.store.raw(self.store.grad, cs.name + ".weight"),
-                            Ci=nf, Co=self.out_channel, KH=3, KW=3, stride=1, pad=1, db=self.store.g(cs.name + ".bias"))
         d_a01 = torch.empty((N, H, W, nf), dtype=self.dtype, device=self.device)
-        ops.conv_simt(dz, (N, H, W), nchw_o, self._wptr(cs, True), self.dt, d_a01, (H, W), ops.nhwc_strides(H, W, nf),
-                      Ci=self.out_channel, Co=nf, KH=3, KW=3, stride=1, pad=1, up=1)
+        if self.fast_small and nf == 64 and self.out_channel == 3:
+            ops.wgrad_cout3(a01, dz, self.store.raw(self.store.grad, cs.name + ".weight"), self.store.g(cs.name + ".bias"))
+            ops.conv_cin3(dz, self._wptr(cs, True), self.dt, d_a01, nf, 1)
+        else:
+            ops.conv_wgrad_simt(a01, (N, H, W), ops.nhwc_strides(H, W, nf), dz, (H, W), nchw_o,
+                                self.store.raw(self.store.grad, cs.name + ".weight"),
+                                Ci=nf, Co=self.out_channel, KH=3, KW=3, stride=1, pad=1, db=self.store.g(cs.name + ".bias"))
+            ops.conv_simt(dz, (N, H, W), nchw_o, self._wptr(cs, True), self.dt, d_a01, (H, W), ops.nhwc_strides(H, W, nf),
+                          Ci=self.out_channel, Co=nf, KH=3, KW=3, stride=1, pad=1, up=1)
 
         def conv_in_bwd(name, dy1, dy2, act, n_out_ch=None, want_dx=True):
             """backward through  y = [lrelu](IN(conv(xin)))  given dL/dy = dy1 (+ dy2)."""
@@ -602,11 +634,18 @@ class Generator(NetBase):
 
 # ===================================================================== frequency detector (forward only)
 class FrequencyDetector(NetBase):
-    """FrequencyModel in eval mode: conv -> ELU -> BN(eval) (x6), maxpool after 2/4/6, flatten (NCHW order), linear.
-    Always float32 CUDA-core kernels: its input are DCT coefficients of magnitude up to ~8e3 (metrics leg only)."""
+    """FrequencyModel in eval mode: conv -> ELU -> BN(eval) (x6), maxpool after 2/4/6, flatten (NCHW order), linear
+    (defenses/frequency_based/model.py:8-52).  Metrics leg only (train_generator.py:245-247).
 
-    def __init__(self, num_classes=2, n_input=3, input_size=32, device="cuda"):
+    dtype float32: CUDA-core kernels throughout.  dtype bfloat16: conv1 (3 input channels; its input are raw DCT
+    coefficients of magnitude up to ~8e3) stays float32 arithmetic with float32 weights, conv2..conv6 run on the
+    tcgen05 kernel with ELU + folded BatchNorm in its epilogue; channel counts below 64 are zero-padded to 64 once,
+    when the (frozen) weights are loaded."""
+
+    def __init__(self, num_classes=2, n_input=3, input_size=32, device="cuda", dtype=torch.float32):
         super().__init__(device, torch.float32, use_tc=False)
+        self.act_dtype = dtype
+        self.tc = dtype == torch.bfloat16
         self.scaler = {32: 1, 64: 4}[input_size]
         chans = [n_input, 32, 32, 64, 64, 128, 128]
         specs, convs = [], []
@@ -625,6 +664,7 @@ class FrequencyDetector(NetBase):
         for i in range(1, 7):
             self.store.p("bn%d.weight" % i).fill_(1.0)
         self._affine = None
+        self._padded = None
 
     def load_state_dict(self, sd):
         self.store.load(sd)
@@ -633,6 +673,7 @@ class FrequencyDetector(NetBase):
             self.rv[i].copy_(sd["bn%d.running_var" % i])
         self.prep_weights()
         self._affine = None
+        self._padded = None
 
     def state_dict(self):
         sd = self.store.state()
@@ -642,25 +683,67 @@ class FrequencyDetector(NetBase):
             sd["bn%d.num_batches_tracked" % i] = torch.tensor(0)
         return sd
 
-    def forward(self, x_nchw):
-        """x: float32 NCHW DCT coefficients -> logits [N, num_classes]."""
-        if self._affine is None:  # frozen network: fold BN(eval) once
+    def _prepare(self):
+        """frozen network: fold BN(eval) into per-channel (scale, shift) once; build the padded bf16 weights."""
+        if self._affine is None:
             self._affine = {i: ops.bn_eval_prepare(self.chans[i], self.store.p("bn%d.weight" % i), self.store.p("bn%d.bias" % i),
                                                    self.rm[i], self.rv[i], 1e-5) for i in range(1, 7)}
+        if self.tc and self._padded is None:
+            pad = lambda c: max(64, c)
+            P = {}
+            for i in range(1, 7):
+                ci, co = self.chans[i - 1], self.chans[i]
+                cip, cop = (ci if i == 1 else pad(ci)), pad(co)
+                w = self.store.raw(self.store.flat, "conv%d.weight" % i).view(co, 9, ci)  # channels-last master
+                wp = torch.zeros((cop, 9, cip), dtype=torch.float32 if i == 1 else torch.bfloat16, device=self.device)
+                wp[:co, :, :ci] = w.to(wp.dtype)
+                vec = torch.zeros((3, cop), dtype=torch.float32, device=self.device)  # bias, scale, shift (0 on the padding)
+                vec[0, :co] = self.store.p("conv%d.bias" % i)
+                vec[1, :co], vec[2, :co] = self._affine[i]
+                P[i] = (wp, vec, cip, cop)
+            self._padded = P
+
+    def forward(self, x_nchw):
+        """x: float32 NCHW DCT coefficients -> logits [N, num_classes]."""
+        self._prepare()
         N, Cc, H, W = x_nchw.shape
+        if self.tc and Cc == 3:
+            return self._forward_tc(x_nchw)
         h, strides, hw = x_nchw, ops.nchw_strides(Cc, H, W), (H, W)
         for i in range(1, 7):
             cs = self.convs["conv%d" % i]
             out = torch.empty((N, hw[0], hw[1], cs.Cout), dtype=torch.float32, device=self.device)
             sc, sh = self._affine[i]
-            ops.conv_simt(h, (N, hw[0], hw[1]), strides, self._wptr(cs), self.dt, out, hw, ops.nhwc_strides(hw[0], hw[1], cs.Cout),
-                          Ci=cs.Cin, Co=cs.Cout, KH=3, KW=3, stride=1, pad=1, bias=self._bias(cs), act=2, post_scale=sc,
-                          post_shift=sh)
+            if i == 1 and Cc == 3 and self.fast_small:
+                ops.conv_cin3(h, self._wptr(cs), self.dt, out, cs.Cout, 1, bias=self._bias(cs), act=2, post_scale=sc, post_shift=sh)
+            else:
+                ops.conv_simt(h, (N, hw[0], hw[1]), strides, self._wptr(cs), self.dt, out, hw,
+                              ops.nhwc_strides(hw[0], hw[1], cs.Cout), Ci=cs.Cin, Co=cs.Cout, KH=3, KW=3, stride=1, pad=1,
+                              bias=self._bias(cs), act=2, post_scale=sc, post_shift=sh)
             h = out
             if i % 2 == 0:
                 h = ops.maxpool2(h)
                 hw = (hw[0] // 2, hw[1] // 2)
             strides = ops.nhwc_strides(hw[0], hw[1], cs.Cout)
         # flatten in NCHW order + linear == pool_linear with P = 1
+        logits, _ = ops.pool_linear_fwd(h, 1, self.store.p("linear6.weight"), self.store.p("linear6.bias"))
+        return logits
+
+    def _forward_tc(self, x_nchw):
+        N, _, H, W = x_nchw.shape
+        hw = (H, W)
+        wp, vec, _, cop = self._padded[1]
+        h = torch.empty((N, H, W, cop), dtype=torch.bfloat16, device=self.device)
+        ops.conv_cin3(x_nchw, wp.data_ptr(), ops.F32, h, cop, 1, bias=vec[0], act=2, post_scale=vec[1], post_shift=vec[2])
+        for i in range(2, 7):
+            wp, vec, cip, cop = self._padded[i]
+            out = torch.empty((N, hw[0], hw[1], cop), dtype=torch.bfloat16, device=self.device)
+            d = ops.conv_tc_desc(h, wp.data_ptr(), out, N, hw[0], hw[1], cip, hw[0], hw[1], cop, 3, 3, 1, 1, 1, bias=vec[0],
+                                 act=2, post_scale=vec[1], post_shift=vec[2])
+            _tc_launch(lambda: lib.combat_conv_tc(C.byref(d), ops._s()), "conv_tc", 2.0 * N * hw[0] * hw[1] * cop * cip * 9)
+            h = out
+            if i % 2 == 0:
+                h = ops.maxpool2(h)
+                hw = (hw[0] // 2, hw[1] // 2)
         logits, _ = ops.pool_linear_fwd(h, 1, self.store.p("linear6.weight"), self.store.p("linear6.bias"))
         return logits

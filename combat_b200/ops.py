@@ -220,8 +220,34 @@ def conv_wgrad_simt(x, x_geom, x_strides, dy, dy_geom, dy_strides, dw, *, Ci, Co
     check(lib.combat_conv_wgrad_simt(C.byref(d), _p(dy), dt_code(dy), _p(dw), _s()), "conv_wgrad_simt")
 
 
-def conv_tc_desc(x, w_ptr, out, N, Hi, Wi, Ci, Ho, Wo, Co, KH, KW, stride, pad, up, bias=None, residual=None, stats=None):
+def conv_cin3(x_nchw, w_ptr, w_dt, out, Co, stride, bias=None, act=0, post_scale=None, post_shift=None):
+    N, _, H, W = x_nchw.shape
+    check(lib.combat_conv_cin3(_p(x_nchw), w_ptr, w_dt, _p(bias), _p(out), dt_code(out), N, H, W, Co, stride, act,
+                               _p(post_scale), _p(post_shift), _s()), "conv_cin3")
+    return out
+
+
+def conv_cout3(x_nhwc, w_ptr, w_dt, out_nchw, bias=None, act=0):
+    N, H, W, Ci = x_nhwc.shape
+    check(lib.combat_conv_cout3(_p(x_nhwc), dt_code(x_nhwc), w_ptr, w_dt, _p(bias), _p(out_nchw), N, H, W, Ci, act, _s()),
+          "conv_cout3")
+    return out_nchw
+
+
+def wgrad_cin3(x_nchw, dy, dw, db, Co, stride):
+    N, _, H, W = x_nchw.shape
+    check(lib.combat_wgrad_cin3(_p(x_nchw), _p(dy), dt_code(dy), _p(dw), _p(db), N, H, W, Co, stride, _s()), "wgrad_cin3")
+
+
+def wgrad_cout3(a_nhwc, dz_nchw, dw, db):
+    N, H, W, Ci = a_nhwc.shape
+    check(lib.combat_wgrad_cout3(_p(a_nhwc), dt_code(a_nhwc), _p(dz_nchw), _p(dw), _p(db), N, H, W, Ci, _s()), "wgrad_cout3")
+
+
+def conv_tc_desc(x, w_ptr, out, N, Hi, Wi, Ci, Ho, Wo, Co, KH, KW, stride, pad, up, bias=None, residual=None, stats=None,
+                 act=0, post_scale=None, post_shift=None):
     d = ConvTcDesc()
+    d.act, d.post_scale, d.post_shift = act, _p(post_scale), _p(post_shift)
     d.in_, d.w, d.out, d.bias, d.residual, d.stats = _p(x), w_ptr, _p(out), _p(bias), _p(residual), _p(stats)
     d.out_f32 = int(out is not None and out.dtype == torch.float32)
     d.res_f32 = int(residual is not None and residual.dtype == torch.float32)

@@ -122,6 +122,20 @@ int combat_conv_simt(const combat_conv_desc* d_host, void* stream);
  * if `bias` is non-NULL it is the float32 bias-GRADIENT accumulator: bias[co] += sum_{n,oh,ow} dy[n,oh,ow,co]. */
 int combat_conv_wgrad_simt(const combat_conv_desc* d_host, const void* dy, int dy_dtype, float* dw_ohwi, void* stream);
 
+/* Direct kernels for the image-boundary layers (3 input or 3 output channels, 3x3, pad 1; csrc/conv_small.cu).
+ *   conv_cin3  : x NCHW float32 [N,3,H,W], w [Co][9][3] -> out NHWC [N,Ho,Wo,Co]; act 0 none / 2 ELU, optional affine
+ *   conv_cout3 : in NHWC [N,H,W,64], w [3][9][64] -> out NCHW float32 [N,3,H,W] (stride 1); act 0 none / 1 tanh
+ *   wgrad_cin3 : dw[Co][9][3] += sum dy[pix][co] * x[pix@tap][ci], db[co] += sum dy      (x NCHW float32, dy NHWC)
+ *   wgrad_cout3: dw[3][9][64] += sum dz[n,co,h,w] * a[pix@tap][ci], db[co] += sum dz     (a NHWC, dz NCHW float32) */
+int combat_conv_cin3(const float* x, const void* w, int w_dtype, const float* bias, void* out, int out_dtype, int N, int H,
+                     int W, int Co, int stride, int act, const float* post_scale, const float* post_shift, void* stream);
+int combat_conv_cout3(const void* in, int in_dtype, const void* w, int w_dtype, const float* bias, float* out, int N, int H,
+                      int W, int Ci, int act, void* stream);
+int combat_wgrad_cin3(const float* x, const void* dy, int dy_dtype, float* dw, float* db, int N, int H, int W, int Co,
+                      int stride, void* stream);
+int combat_wgrad_cout3(const void* a, int a_dtype, const float* dz, float* dw, float* db, int N, int H, int W, int Ci,
+                       void* stream);
+
 /* tcgen05 implicit-GEMM convolution (sm_100a tensor cores, TMA-fed, TMEM accumulators), bf16 NHWC.
  * Requires Ci % 64 == 0 and Co % 64 == 0.  See combat_b200/csrc/conv_tc.cu. */
 typedef struct {
@@ -134,6 +148,9 @@ typedef struct {
   int N, Hi, Wi, Ci, Ho, Wo, Co, KH, KW, stride, pad, up;
   int out_f32;           /* 1: `out` is float32 (pre-normalisation tensors keep the unrounded accumulator) */
   int res_f32;           /* 1: `residual` is float32 */
+  int act;               /* 0 none, 2 ELU(alpha=1) applied after bias */
+  const float* post_scale; /* optional per-channel affine after act (eval BatchNorm of FrequencyModel) */
+  const float* post_shift;
 } combat_conv_tc_desc;
 int combat_conv_tc(const combat_conv_tc_desc* d_host, void* stream);
 int combat_conv_tc_wgrad(const combat_conv_tc_desc* d_host, const void* dy, float* dw_ohwi, void* stream);

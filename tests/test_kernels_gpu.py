@@ -397,3 +397,93 @@ def test_small_ops(ops):
     ops.onehot_planes(t, dev(lab), 64, 8)
     exp = F.one_hot(lab, 8).float()[:, None, None, :].expand(-1, 4, 4, -1)
     assert torch.equal(t[..., 64:].cpu(), exp)
+
+
+# ------------------------------------------------------------------ direct kernels for the 3-channel boundary layers
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("stride,Co", [(1, 64), (2, 64), (1, 32)])
+def test_conv_small_cin3(ops, dtype, tol, stride, Co):
+    g = torch.Generator().manual_seed(20 + stride + Co)
+    N, H = 5, 16
+    x = torch.randn(N, 3, H, H, generator=g, requires_grad=True)
+    w = (torch.randn(Co, 3, 3, 3, generator=g) * 0.2).requires_grad_(True)
+    bias = torch.randn(Co, generator=g)
+    wq = w.detach().to(dtype).float()
+    y = F.conv2d(x, wq, bias, stride, 1)
+    Ho = y.shape[2]
+    w_cl = dev(w.detach().permute(0, 2, 3, 1).to(dtype))
+    out = torch.empty(N, Ho, Ho, Co, device="cuda", dtype=dtype)
+    ops.conv_cin3(dev(x.detach()), w_cl.data_ptr(), ops.dt_code(dtype), out, Co, stride, bias=dev(bias))
+    assert rel(out.float().permute(0, 3, 1, 2), y) < tol
+    # ELU + affine epilogue (FrequencyModel conv1)
+    sc, sh = torch.rand(Co, generator=g) + 0.5, torch.randn(Co, generator=g)
+    out2 = torch.empty(N, Ho, Ho, Co, device="cuda", dtype=torch.float32)
+    ops.conv_cin3(dev(x.detach()), w_cl.data_ptr(), ops.dt_code(dtype), out2, Co, stride, bias=dev(bias), act=2,
+                  post_scale=dev(sc), post_shift=dev(sh))
+    assert rel(out2.permute(0, 3, 1, 2), F.elu(y) * sc[None, :, None, None] + sh[None, :, None, None]) < 1e-5
+    # weight / bias gradient
+    dy = torch.randn(y.shape, generator=g).to(dtype).float()
+    F.conv2d(x, w, bias, stride, 1).backward(dy)
+    dw = torch.zeros(Co, 3, 3, 3, device="cuda")  # [co][kh][kw][ci]
+    db = torch.zeros(Co, device="cuda")
+    ops.wgrad_cin3(dev(x.detach()), dev(_nhwc(dy).to(dtype)), dw, db, Co, stride)
+    assert rel(dw.permute(0, 3, 1, 2), w.grad) < 2e-5
+    assert rel(db, dy.sum((0, 2, 3))) < 2e-5
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
+def test_conv_small_cout3(ops, dtype, tol):
+    g = torch.Generator().manual_seed(31)
+    N, H = 3, 16
+    x = torch.randn(N, 64, H, H, generator=g).to(dtype).float().requires_grad_(True)
+    w = (torch.randn(3, 64, 3, 3, generator=g) * 0.05).to(dtype).float().requires_grad_(True)
+    bias = torch.randn(3, generator=g)
+    y = torch.tanh(F.conv2d(x, w, bias, 1, 1))
+    out = torch.empty(N, 3, H, H, device="cuda")
+    w_cl = dev(w.detach().permute(0, 2, 3, 1).to(dtype))
+    xd = dev(_nhwc(x.detach()).to(dtype))
+    ops.conv_cout3(xd, w_cl.data_ptr(), ops.dt_code(dtype), out, bias=dev(bias), act=1)
+    assert rel(out, y) < 1e-5
+    dz = torch.randn(N, 3, H, H, generator=g)
+    z = F.conv2d(x, w, bias, 1, 1)
+    z.backward(dz)
+    dw = torch.zeros(3, 3, 3, 64, device="cuda")
+    db = torch.zeros(3, device="cuda")
+    ops.wgrad_cout3(xd, dev(dz), dw, db)
+    assert rel(dw.permute(0, 3, 1, 2), w.grad) < 2e-5
+    assert rel(db, dz.sum((0, 2, 3))) < 2e-5
+    # input gradient of a 3 -> 64 conv == 64 -> 3 conv with the flipped, transposed weights (classifier conv1 dgrad)
+    w2 = (torch.randn(64, 3, 3, 3, generator=g) * 0.2).to(dtype).float()
+    xin = torch.randn(N, 3, H, H, generator=g, requires_grad=True)
+    dy2 = torch.randn(N, 64, H, H, generator=g).to(dtype).float()
+    F.conv2d(xin, w2, None, 1, 1).backward(dy2)
+    w_d = dev(w2.flip(2, 3).permute(1, 2, 3, 0).to(dtype))  # [ci][kh'][kw'][co]
+    dx = torch.empty(N, 3, H, H, device="cuda")
+    ops.conv_cout3(dev(_nhwc(dy2).to(dtype)), w_d.data_ptr(), ops.dt_code(dtype), dx)
+    assert rel(dx, xin.grad) < 1e-5
+
+
+def test_conv_tc_elu_affine_epilogue(ops):
+    import ctypes as C
+
+    from combat_b200._lib import check, lib
+    g = torch.Generator().manual_seed(41)
+    N, Ci, Co, H = 4, 64, 128, 8
+    x = torch.randn(N, Ci, H, H, generator=g).bfloat16().float()
+    w = (torch.randn(Co, Ci, 3, 3, generator=g) * 0.05).bfloat16().float()
+    bias, sc, sh = torch.randn(Co, generator=g), torch.rand(Co, generator=g) + 0.5, torch.randn(Co, generator=g)
+    y = F.elu(F.conv2d(x, w, bias, 1, 1)) * sc[None, :, None, None] + sh[None, :, None, None]
+    out = torch.empty(N, H, H, Co, device="cuda", dtype=torch.bfloat16)
+    w_f = dev(w.permute(0, 2, 3, 1).bfloat16())
+    d = ops.conv_tc_desc(dev(_nhwc(x).bfloat16()), w_f.data_ptr(), out, N, H, H, Ci, H, H, Co, 3, 3, 1, 1, 1, bias=dev(bias),
+                         act=2, post_scale=dev(sc), post_shift=dev(sh))
+    check(lib.combat_conv_tc(C.byref(d), ops._s()), "conv_tc")
+    torch.cuda.synchronize()
+    assert rel(out.float().permute(0, 3, 1, 2), y) < 6e-3
+    # float32 output + float32 residual (pre-normalisation tensors)
+    res = torch.randn(N, Co, H, H, generator=g)
+    out32 = torch.empty(N, H, H, Co, device="cuda", dtype=torch.float32)
+    d2 = ops.conv_tc_desc(dev(_nhwc(x).bfloat16()), w_f.data_ptr(), out32, N, H, H, Ci, H, H, Co, 3, 3, 1, 1, 1, residual=dev(_nhwc(res)))
+    check(lib.combat_conv_tc(C.byref(d2), ops._s()), "conv_tc")
+    torch.cuda.synchronize()
+    assert rel(out32.permute(0, 3, 1, 2), F.conv2d(x, w, None, 1, 1) + res) < 2e-5

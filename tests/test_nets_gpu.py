@@ -211,3 +211,19 @@ def test_frequency_detector_shipped_weights(golden):
     xu = torch.from_numpy(g["freq_xu"]).cuda()
     logits = net.forward(ops.plane_op(xu, "dct", in_mode=1))
     assert rel(logits, torch.from_numpy(g["freq_logits"])) < 5e-5
+
+
+def test_frequency_detector_bf16_tensor_core_path(golden):
+    """same known answer through the bf16 tcgen05 path (metrics leg of the bf16 step): logits within 2e-2, same argmax"""
+    need_gpu()
+    from combat_b200 import ops
+    from combat_b200.nets import FrequencyDetector
+    g = golden("modules.npz")
+    sd = {k[len("freq_sd_"):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("freq_sd_")}
+    net = FrequencyDetector(2, 3, 32, device="cuda", dtype=torch.bfloat16)
+    net.load_state_dict({k: v.cuda() for k, v in sd.items()})
+    xu = torch.from_numpy(g["freq_xu"]).cuda()
+    logits = net.forward(ops.plane_op(xu, "dct", in_mode=1))
+    ref = torch.from_numpy(g["freq_logits"])
+    assert rel2(logits, ref) < 2e-2, rel2(logits, ref)
+    assert torch.equal(logits.argmax(1).cpu(), ref.argmax(1))
