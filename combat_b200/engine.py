@@ -89,7 +89,7 @@ class AlternatedStep:
     refreshing the small per-iteration parameter block (perm, targets, num_bd, blur taps, learning rates)."""
 
     def __init__(self, opt=None, device="cuda", dtype=torch.bfloat16, classifier="preact_resnet18", with_metrics=True,
-                 use_tc=True, cond_classes=0, grad_hook=None, buf_hook=None):
+                 use_tc=True, cond_classes=0, grad_hook=None, buf_hook=None, nets=None):
         self.opt = opt or default_opt()
         o = self.opt
         self.device = torch.device(device)
@@ -97,10 +97,14 @@ class AlternatedStep:
         self.with_metrics = with_metrics
         H = o.input_height
         mk = dict(device=self.device, dtype=dtype, use_tc=use_tc)
-        self.netC = Classifier(classifier, o.num_classes, o.input_channel, H, **mk)
-        self.clean = Classifier(classifier, o.num_classes, o.input_channel, H, **mk)
-        self.netG = Generator(o.input_channel, 64, cond_classes, **mk)
-        self.netF = FrequencyDetector(2, o.input_channel, H, device=self.device, dtype=dtype) if (with_metrics and H in (32, 64)) else None
+        if nets is not None:  # adopt networks owned by the reference-facing nn.Module wrappers
+            self.netC, self.clean, self.netG, self.netF = nets
+            self.dtype = self.netC.dtype
+        else:
+            self.netC = Classifier(classifier, o.num_classes, o.input_channel, H, **mk)
+            self.clean = Classifier(classifier, o.num_classes, o.input_channel, H, **mk)
+            self.netG = Generator(o.input_channel, 64, cond_classes, **mk)
+            self.netF = FrequencyDetector(2, o.input_channel, H, device=self.device, dtype=dtype) if (with_metrics and H in (32, 64)) else None
         self.keep = int(H * o.ratio)
         self.lr_C = torch.full((1,), float(o.lr_C), dtype=torch.float32, device=self.device)
         self.lr_G = torch.full((1,), float(o.lr_G), dtype=torch.float32, device=self.device)

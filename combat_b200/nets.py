@@ -126,7 +126,9 @@ class NetBase:
 
     def __init__(self, device, dtype, use_tc=True):
         self.device = torch.device(device)
-        if self.device.type != "cuda":
+        if self.device.type == "cuda" and self.device.index is None and torch.cuda.is_available():
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        if self.device.type not in ("cuda", "meta"):  # "meta": shape-only introspection (names / shapes), nothing can run
             raise RuntimeError("combat_b200 networks run on CUDA devices only (no CPU fallback)")
         self.dtype = dtype
         self.dt = ops.dt_code(dtype)
@@ -152,6 +154,9 @@ class NetBase:
             self.convs[cs.name] = cs
             table.append((self.store.offsets[cs.name + ".weight"], cs.fwd_off, cs.dgrad_off, cs.Cout, cs.Cin, cs.k, cs.k))
         self.wbuf = torch.zeros(off, dtype=self.dtype, device=self.device)
+        if self.device.type == "meta":
+            self._wtable, self._wmax, self._n_wdesc, self.esz = None, 0, len(table), 2
+            return
         self._wtable, self._wmax = ops.make_wprep_table(table, self.device)
         self._n_wdesc = len(table)
         self.esz = self.wbuf.element_size()

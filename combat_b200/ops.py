@@ -71,6 +71,8 @@ def transform_matrix(kind: str, N: int, device, keep: int = 0) -> torch.Tensor:
             M = D.T
         elif kind == "lowfreq":
             M = D[:keep].T @ D[:keep]
+        elif kind == "eye":
+            M = np.eye(N)
         else:
             raise ValueError(kind)
         m = torch.from_numpy(np.ascontiguousarray(M).astype(np.float32)).to(device)
@@ -98,6 +100,27 @@ def plane_transform(x: torch.Tensor, M: torch.Tensor, in_mode: int = 0, out: tor
             n = min(chunk, planes - p0)
             check(lib.combat_plane_transform(x.data_ptr() + p0 * N * N * esz, out.data_ptr() + p0 * N * N * 4, _p(M), _p(M),
                                              n, N, in_mode, _p(ws), _s()), "plane_transform")
+    return out
+
+
+def plane_transform_lr(x, L, R, in_mode=0):
+    """out[p] = L x[p] R^T with distinct left / right matrices (1-D transforms: L = I)."""
+    x = _contig(x)
+    N = x.shape[-1]
+    planes = x.numel() // (N * N)
+    out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    if planes == 0:
+        return out
+    if N <= 64 and N % 4 == 0:
+        check(lib.combat_plane_transform(_p(x), _p(out), _p(L), _p(R), planes, N, in_mode, None, _s()), "plane_transform")
+        return out
+    esz = x.element_size()
+    chunk = 4096
+    ws = torch.empty(min(planes, chunk) * N * N, dtype=torch.float32, device=x.device)
+    for p0 in range(0, planes, chunk):
+        n = min(chunk, planes - p0)
+        check(lib.combat_plane_transform(x.data_ptr() + p0 * N * N * esz, out.data_ptr() + p0 * N * N * 4, _p(L), _p(R), n, N,
+                                         in_mode, _p(ws), _s()), "plane_transform")
     return out
 
 

@@ -266,3 +266,32 @@ if __name__ == "__main__":
     if "step" in which:
         gen_step("step_b128.npz", 128, 1, 0)      # the SURVEY 8c-4 known-answer vector
         gen_step("step_b32x2.npz", 32, 2, 7)      # two iterations: momentum buffers + RNG interleaving
+
+
+def gen_api():
+    """API surface pins: parser flags/defaults and state_dict key -> shape maps of the reference modules."""
+    import json
+    p = config.get_arguments()
+    flags = {}
+    for a in p._actions:
+        if a.dest == "help":
+            continue
+        d = a.default
+        flags[a.dest] = {"default": list(d) if isinstance(d, (list, tuple)) else d,
+                         "type": getattr(a.type, "__name__", None) if a.type else ("bool" if a.nargs == 0 else None)}
+    opt = get_opt()
+    opt8 = get_opt()
+    opt8.num_classes = 8
+    mods = {
+        "PreActResNet18": PreActResNet18(), "ResNet18_c8_64": ResNet18(num_classes=8),
+        "UnetGenerator": UnetGenerator(opt), "CUnetGeneratorv1_c8": CUnetGeneratorv1(opt8), "FrequencyModel": FrequencyModel(2, 3, 32),
+    }
+    sds = {k: {n: list(v.shape) for n, v in m.state_dict().items()} for k, m in mods.items()}
+    nparams = {k: sum(p.numel() for p in m.parameters()) for k, m in mods.items()}
+    with open(os.path.join(HERE, "api.json"), "w") as f:
+        json.dump({"flags": flags, "state_dicts": sds, "n_params": nparams}, f, indent=0, sort_keys=True)
+    print("wrote api.json")
+
+
+if __name__ == "__main__" and "api" in (sys.argv[1:] or ["api"]):
+    gen_api()

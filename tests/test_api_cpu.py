@@ -1,0 +1,107 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads and exports every symbol the header declares, the CLI
+parser matches the reference's flags/defaults, and the modules expose the reference's state_dict keys and shapes
+(tests/golden/api.json was recorded from the unmodified reference by tests/golden/make_golden.py)."""
+import json
+import os
+
+import pytest
+import torch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_library_loads_and_exports_every_header_symbol():
+    from combat_b200 import _lib
+    declared = _lib.header_symbols()
+    assert len(declared) >= 40
+    for name in declared:
+        assert hasattr(_lib.lib, name), "symbol %s declared in include/combat_b200.h is not exported" % name
+        assert name in _lib._SIGS, "symbol %s has no ctypes signature" % name
+    assert sorted(_lib._SIGS) == declared
+    assert _lib.lib.combat_version() >= 100
+
+
+def test_no_cpu_fallback():
+    from combat_b200 import ops
+    from combat_b200.nets import Classifier
+    with pytest.raises(RuntimeError):
+        ops.plane_op(torch.zeros(1, 3, 32, 32), "dct")
+    with pytest.raises(RuntimeError):
+        Classifier("preact_resnet18", device="cpu")
+
+
+def test_product_code_never_imports_the_oracle():
+    root = os.path.join(os.path.dirname(GOLDEN), "..", "combat_b200")
+    for dp, _, fs in os.walk(root):
+        for f in fs:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert "oracle" not in src.replace("# oracle", ""), os.path.join(dp, f)
+
+
+def test_cli_flags_match_reference():
+    from combat_b200 import config
+    g = json.load(open(os.path.join(GOLDEN, "api.json")))["flags"]
+    p = config.get_arguments()
+    mine = {a.dest: a for a in p._actions if a.dest != "help"}
+    for dest, spec in g.items():
+        assert dest in mine, dest
+        d = mine[dest].default
+        d = list(d) if isinstance(d, (list, tuple)) else d
+        assert d == spec["default"], (dest, d, spec["default"])
+    extra = set(mine) - set(g)
+    assert extra == {"dtype", "no_graph", "log_every"}, extra
+    opt = p.parse_args(["--pc", "0.3", "--noise_rate", "0.1", "--post_transform_option", "no_use"])
+    assert opt.pc == 0.3 and opt.noise_rate == 0.1
+
+
+@pytest.mark.parametrize("key,ctor", [
+    ("PreActResNet18", lambda N: N.Classifier("preact_resnet18", 10, 3, 32, device="meta", dtype=torch.float32)),
+    ("ResNet18_c8_64", lambda N: N.Classifier("resnet18", 8, 3, 64, device="meta", dtype=torch.float32)),
+    ("UnetGenerator", lambda N: N.Generator(3, 64, 0, device="meta", dtype=torch.float32)),
+    ("CUnetGeneratorv1_c8", lambda N: N.Generator(3, 64, 8, device="meta", dtype=torch.float32)),
+])
+def test_parameter_names_and_shapes_match_reference(key, ctor):
+    from combat_b200 import nets
+    g = json.load(open(os.path.join(GOLDEN, "api.json")))
+    net = ctor(nets)
+    ref = g["state_dicts"][key]
+    ref_params = {k: v for k, v in ref.items() if not k.endswith(("running_mean", "running_var", "num_batches_tracked"))}
+    assert list(net.store.names) == list(k for k in ref if k in ref_params) or set(net.store.names) == set(ref_params)
+    for n in net.store.names:
+        assert list(net.store.shapes[n]) == ref_params[n], n
+    n_params = sum(int(torch.tensor(net.store.shapes[n]).prod()) for n in net.store.names)
+    assert n_params == g["n_params"][key]
+    if hasattr(net, "bns"):
+        bufs = {b.name + s for b in net.bns for s in (".running_mean", ".running_var", ".num_batches_tracked")}
+        assert bufs == set(ref) - set(ref_params)
+
+
+def test_plan_matches_oracle_selection():
+    """host-side poison selection / RNG order (engine.make_plan) == oracle.select_poison on the same seeds"""
+    import numpy as np
+
+    from combat_b200.engine import default_opt, make_plan
+    from oracle import combat_oracle as O
+    for seed in range(5):
+        y = torch.randint(0, 10, (257,), generator=torch.Generator().manual_seed(seed))
+        np.random.seed(seed)
+        torch.manual_seed(seed)
+        bd = O.create_targets_bd(y, "all2one", 0, 10)
+        trg, ntrg, nbd = O.select_poison(y, bd, 0.5)
+        s_c = O.draw_sigma() if nbd > 0 else None
+        s_g = O.draw_sigma()
+        np.random.seed(seed)
+        torch.manual_seed(seed)
+        plan = make_plan(y.numpy(), default_opt())
+        assert plan.num_bd == nbd and np.array_equal(plan.trg_ind, trg.numpy()) and np.array_equal(plan.ntrg_ind, ntrg.numpy())
+        assert plan.sigma_c == s_c and plan.sigma_g == s_g
+        assert np.array_equal(plan.perm, torch.cat([trg, ntrg]).numpy())
+    # empty and degenerate batches
+    np.random.seed(0)
+    plan = make_plan(np.array([3, 4, 5]), default_opt())  # no target-class row: nothing poisoned, no C-step sigma draw
+    assert plan.num_bd == 0 and plan.sigma_c is None and list(plan.perm) == [0, 1, 2]
+    plan = make_plan(np.array([1, 2, 3]), default_opt(attack_mode="all2all"))
+    assert plan.num_bd == 0 and list(plan.bd_targets) == [2, 3, 4]
+    with pytest.raises(Exception):
+        make_plan(np.array([1]), default_opt(attack_mode="nope"))
