@@ -127,30 +127,25 @@ def run_reference(args):
 def run_ours(args):
     import torch.distributed as dist
 
-    from combat_b200 import nets
-    from combat_b200.engine import AlternatedStep, make_plan
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from combat_b200 import config, nets, parallel
+    from combat_b200 import train_generator as tg
+    from combat_b200.engine import AlternatedStep
+    rank, world, local = parallel.env_rank()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    parallel.init(device=dev)
     B = args.batch
-    np.random.seed(1234 + rank)
-    torch.manual_seed(1234 + rank)
-
-    def grad_hook(name, flat):
-        dist.all_reduce(flat, op=dist.ReduceOp.AVG)
-
-    def buf_hook(flat):
-        dist.all_reduce(flat, op=dist.ReduceOp.AVG)
-
-    eng = AlternatedStep(device=dev, dtype=torch.bfloat16, with_metrics=True,
-                         grad_hook=grad_hook if world > 1 else None, buf_hook=buf_hook if world > 1 else None)
-    st = synthetic_state(0)  # identical replicas on every rank
-    eng.load_state(netC={**st["netC_p"], **st["netC_b"]}, clean={**st["clean_p"], **st["clean_b"]}, netG=st["netG_p"],
-                   netF={**st["netF_p"], **st["netF_b"]})
+    # the reference's own construction path (get_model, train_generator.py:80-128): random init in the reference's
+    # order from seed 0 on every rank -> identical replicas; no checkpoint, no dataset (synthetic)
+    opt = config.get_arguments().parse_args(["--device", str(dev), "--post_transform_option", "no_use"])
+    opt.input_height = opt.input_width = 32
+    opt.input_channel = 3
+    torch.manual_seed(0)
+    netC, _, _, netG, _, _, netF, clean_model = tg.get_model(opt)
+    sync = parallel.GradSync()
+    eng = AlternatedStep(opt, device=dev, with_metrics=True, nets=(netC.net, clean_model.net, netG.net, netF.net),
+                         grad_hook=sync.grad_hook if world > 1 else None, buf_hook=sync.buf_hook if world > 1 else None)
+    parallel.seed_rank(1234, rank)
     g = torch.Generator().manual_seed(99 + rank)
     n_host = 4
     xs_host = [(torch.rand(B, 3, 32, 32, generator=g) * 2 - 1).pin_memory() for _ in range(n_host)]
@@ -213,15 +208,21 @@ def run_ours(args):
         eng.step(xs_dev[0], ys_host[0], use_graph=False)
         torch.cuda.synchronize()
         prof, nets.TC_PROFILE = nets.TC_PROFILE, None
-        tot_ms = sum(s.elapsed_time(e) for _, _, s, e in prof)
-        tot_fl = sum(f for _, f, _, _ in prof)
+        tot_ms = sum(s.elapsed_time(e) for _, _, s, e, _ in prof)
+        tot_fl = sum(f for _, f, _, _, _ in prof)
         peak_tf, peak_bw, which = peaks()
         by = {}
-        for name, f, s, e in prof:
-            a = by.setdefault(name, [0.0, 0.0, 0])
-            a[0] += f
-            a[1] += s.elapsed_time(e)
-            a[2] += 1
+        layers = {}
+        for name, f, s, e, tag in prof:
+            for d, k in ((by, name), (layers, name + " | " + tag)):
+                a = d.setdefault(k, [0.0, 0.0, 0])
+                a[0] += f
+                a[1] += s.elapsed_time(e)
+                a[2] += 1
+        if args.dump_layers:
+            with open(args.dump_layers, "w") as fh:
+                for k, v in sorted(layers.items(), key=lambda kv: -kv[1][1]):
+                    fh.write("%-60s launches %3d  ms %8.3f  TFLOP/s %7.1f\n" % (k, v[2], v[1], v[0] / (v[1] * 1e-3) / 1e12))
         ach = tot_fl / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
         roof = {"bound": "tensor", "kernel": "conv_tc_kernel / conv_tc_wgrad_kernel (tcgen05 implicit GEMM)", "achieved": ach,
                 "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None, "peak_source": which + " (sustained bf16)",
@@ -263,6 +264,7 @@ def main():
     ap.add_argument("--batch", type=int, default=512, help="batch per GPU")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-layers", default=None, help="write the per-layer tcgen05 conv timing table to this file")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

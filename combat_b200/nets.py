@@ -27,7 +27,7 @@ from ._lib import check, lib
 TC_PROFILE = None
 
 
-def _tc_launch(fn, name, flops):
+def _tc_launch(fn, name, flops, tag=""):
     if TC_PROFILE is None:
         check(fn(), name)
         return
@@ -35,7 +35,11 @@ def _tc_launch(fn, name, flops):
     s.record()
     check(fn(), name)
     e.record()
-    TC_PROFILE.append((name, flops, s, e))
+    TC_PROFILE.append((name, flops, s, e, tag))
+
+
+def _tag(N, H, W, cs):
+    return "N%d %dx%d %d->%d k%d s%d" % (N, H, W, cs.Cin, cs.Cout, cs.k, cs.stride)
 
 
 def _align(n, a=4):
@@ -194,7 +198,8 @@ class NetBase:
             d = ops.conv_tc_desc(x, self._wptr(cs), out, N, H, W, cs.Cin, Ho, Wo, cs.Cout, cs.k, cs.k, cs.stride, cs.pad, 1,
                                  bias=self._bias(cs), residual=residual)
             if lib.combat_conv_tc_supported(C.byref(d)):
-                _tc_launch(lambda: lib.combat_conv_tc(C.byref(d), ops._s()), "conv_tc", 2.0 * N * Ho * Wo * cs.Cout * cs.Cin * cs.k * cs.k)
+                _tc_launch(lambda: lib.combat_conv_tc(C.byref(d), ops._s()), "conv_tc", 2.0 * N * Ho * Wo * cs.Cout * cs.Cin * cs.k * cs.k,
+                           _tag(N, H, W, cs))
                 return out
         ops.conv_simt(x, (N, H, W), ops.nhwc_strides(H, W, Ct), self._wptr(cs), self.dt, out, (Ho, Wo),
                       ops.nhwc_strides(Ho, Wo, cs.Cout), Ci=cs.Cin, Co=cs.Cout, KH=cs.k, KW=cs.k, stride=cs.stride,
@@ -212,7 +217,8 @@ class NetBase:
             d = ops.conv_tc_desc(dy, self._wptr(cs, True), dx, N, Ho, Wo, cs.Cout, H, W, cs.Cin, cs.k, cs.k, 1, padp,
                                  cs.stride, residual=residual)
             if lib.combat_conv_tc_supported(C.byref(d)):
-                _tc_launch(lambda: lib.combat_conv_tc(C.byref(d), ops._s()), "conv_tc(dgrad)", 2.0 * N * Ho * Wo * cs.Cout * cs.Cin * cs.k * cs.k)
+                _tc_launch(lambda: lib.combat_conv_tc(C.byref(d), ops._s()), "conv_tc(dgrad)", 2.0 * N * Ho * Wo * cs.Cout * cs.Cin * cs.k * cs.k,
+                           _tag(N, H, W, cs))
                 return dx
         ops.conv_simt(dy, (N, Ho, Wo), ops.nhwc_strides(Ho, Wo, cs.Cout), self._wptr(cs, True), self.dt, dx, (H, W),
                       ops.nhwc_strides(H, W, Cx), Ci=cs.Cout, Co=Cx, KH=cs.k, KW=cs.k, stride=1, pad=padp, up=cs.stride,
@@ -228,7 +234,7 @@ class NetBase:
         if self._tc_ok(cs) and Ct == cs.Cin:
             d = ops.conv_tc_desc(x, None, None, N, H, W, cs.Cin, Ho, Wo, cs.Cout, cs.k, cs.k, cs.stride, cs.pad, 1)
             if lib.combat_conv_tc_supported(C.byref(d)):
-                _tc_launch(lambda: lib.combat_conv_tc_wgrad(C.byref(d), ops._p(dy), ops._p(dw), ops._s()), "conv_tc_wgrad", 2.0 * N * Ho * Wo * cs.Cout * cs.Cin * cs.k * cs.k)
+                _tc_launch(lambda: lib.combat_conv_tc_wgrad(C.byref(d), ops._p(dy), ops._p(dw), ops._s()), "conv_tc_wgrad", 2.0 * N * Ho * Wo * cs.Cout * cs.Cin * cs.k * cs.k, _tag(N, H, W, cs))
                 if db is not None:
                     ops.colsum(dy, cs.Cout, db)
                 return
@@ -745,7 +751,8 @@ class FrequencyDetector(NetBase):
             out = torch.empty((N, hw[0], hw[1], cop), dtype=torch.bfloat16, device=self.device)
             d = ops.conv_tc_desc(h, wp.data_ptr(), out, N, hw[0], hw[1], cip, hw[0], hw[1], cop, 3, 3, 1, 1, 1, bias=vec[0],
                                  act=2, post_scale=vec[1], post_shift=vec[2])
-            _tc_launch(lambda: lib.combat_conv_tc(C.byref(d), ops._s()), "conv_tc", 2.0 * N * hw[0] * hw[1] * cop * cip * 9)
+            _tc_launch(lambda: lib.combat_conv_tc(C.byref(d), ops._s()), "conv_tc", 2.0 * N * hw[0] * hw[1] * cop * cip * 9,
+                       "N%d %dx%d %d->%d k3 s1 (netF)" % (N, hw[0], hw[1], cip, cop))
             h = out
             if i % 2 == 0:
                 h = ops.maxpool2(h)

@@ -352,12 +352,15 @@ def make_bd(netG_p, x, opt, sigma, y=None):
     return gaussian_blur(x_bd, sigma, opt.kernel_size), noise, raw
 
 
-def alternated_step(state: dict, x: torch.Tensor, y: torch.Tensor, opt, with_metrics: bool = True) -> dict:
+def alternated_step(state: dict, x: torch.Tensor, y: torch.Tensor, opt, with_metrics: bool = True, grad_hook=None,
+                    buf_hook=None) -> dict:
     """One iteration of train() (train_generator.py:170-255) with identity PostTensorTransform.
 
     `state` holds: netC_p/netC_b, clean_p/clean_b, netG_p (dicts of tensors, updated IN PLACE),
     netF_p/netF_b (optional), momC/momG (momentum buffer dicts, {} before the first step).
     RNG order: numpy rand(n_trg) -> torch uniform (if num_bd>0) -> torch uniform.
+    grad_hook(name, grads_dict) / buf_hook(buffers_dict): data-parallel exchange points (local-BN policy) --
+    called after each backward, before the optimiser step / after the C-step update; None for the single-process step.
     Returns a dict of everything observable (indices, losses, logits, metric counts)."""
     fwdC = CLASSIFIERS[opt.classifier]
     netC_p, netC_b, netG_p = state["netC_p"], state["netC_b"], state["netG_p"]
@@ -389,10 +392,14 @@ def alternated_step(state: dict, x: torch.Tensor, y: torch.Tensor, opt, with_met
     out["logits_c"], out["loss_c"] = logits_c.detach().clone(), float(loss_c)
     gradsC = {k: v.grad for k, v in netC_p.items()}
     out["gradsC"] = {k: g.clone() for k, g in gradsC.items()}
+    if grad_hook is not None:
+        grad_hook("netC", gradsC)
     with torch.no_grad():
         for t in netC_p.values():
             t.requires_grad_(False)
         sgd_nesterov_step(netC_p, gradsC, state["momC"], opt.lr_C)
+        if buf_hook is not None:
+            buf_hook(netC_b)
         if with_metrics:
             out["clean_preds"] = fwdC(clean_p, clean_b, x, False)  # :214
 
@@ -415,6 +422,8 @@ def alternated_step(state: dict, x: torch.Tensor, y: torch.Tensor, opt, with_met
     loss.backward()
     gradsG = {k: v.grad for k, v in netG_p.items()}
     out["gradsG"] = {k: g.clone() for k, g in gradsG.items()}
+    if grad_hook is not None:
+        grad_hook("netG", gradsG)
     with torch.no_grad():
         for t in netG_p.values():
             t.requires_grad_(False)
