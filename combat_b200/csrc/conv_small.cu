@@ -24,7 +24,7 @@ __device__ __forceinline__ void store8<bf16>(bf16* p, const float* v) {
 // x: NCHW float32 [N,3,H,W]; w: [Co][9][3] (TW); out: NHWC [N,Ho,Wo,Co] (TO).  8 channels per thread, Co/8 threads per
 // pixel, weights staged in shared memory as [27][Co] float32.
 template <typename TW, typename TO>
-__global__ void __launch_bounds__(256) conv_cin3_k(const float* __restrict__ x, const TW* __restrict__ w,
+__global__ void __launch_bounds__(256) conv_cin3_generic_k(const float* __restrict__ x, const TW* __restrict__ w,
                                                    const float* __restrict__ bias, TO* __restrict__ out, int N, int H, int W,
                                                    int Ho, int Wo, int Co, int stride, int act,
                                                    const float* __restrict__ post_scale, const float* __restrict__ post_shift) {
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(256) conv_cin3_k(const float* __restrict__ x, 
 // in: NHWC [N,H,W,64] (TI); w: [3][9][64] (TW); out: NCHW float32 [N,3,H,W] (+bias, optional tanh).
 // One warp per pixel, 2 channels per lane, weights in registers, 3 warp reductions per pixel.
 template <typename TI, typename TW>
-__global__ void __launch_bounds__(256) conv_cout3_k(const TI* __restrict__ in, const TW* __restrict__ w,
+__global__ void __launch_bounds__(256) conv_cout3_generic_k(const TI* __restrict__ in, const TW* __restrict__ w,
                                                     const float* __restrict__ bias, float* __restrict__ out, int N, int H, int W,
                                                     int act) {
   const int lane = threadIdx.x & 31;
@@ -132,110 +132,275 @@ __global__ void __launch_bounds__(256) conv_cout3_k(const TI* __restrict__ in, c
   }
 }
 
-// ---------------------------------------------------------------------------------- wgrad, 3 input channels
-// dw[co][9][3] (+)= sum_pix dy[pix][co] * x[pix @ tap][ci];  db[co] += sum_pix dy[pix][co].
-// x NCHW float32, dy NHWC [N,Ho,Wo,Co] (T).  blockDim = (Co, 256/Co): a thread owns one co and strides over pixels.
-template <typename T>
-__global__ void __launch_bounds__(256) wgrad_cin3_k(const float* __restrict__ x, const T* __restrict__ dy,
-                                                    float* __restrict__ dw, float* __restrict__ db, int N, int H, int W, int Ho,
-                                                    int Wo, int Co, int stride) {
-  const int co = threadIdx.x;
-  float acc[28];
+// =====================================================================================================================
+// Register-tiled kernels (the paths the step uses).  All three are fp32-FMA bound at ~0.9 GFMA per 512-image batch
+// (K = 27 or N = 3 cannot feed a 128-wide tensor tile); the tiling keeps shared-memory and global load instructions
+// at <= 1 per 4..8 FMAs so the FMA pipe, not the load/store unit, is the limiter.
+// =====================================================================================================================
+
+// ---------------------------------------------------------------------------------- 3 -> Co, 4 pixels x 8 channels per thread
+// x: NCHW float32 [N,3,H,W]; w: [Co][9][3] (TW); out: NHWC [N,Ho,Wo,Co] (TO); Wo % 4 == 0.
+template <typename TW, typename TO, int S>
+__global__ void __launch_bounds__(256) conv_cin3_k(const float* __restrict__ x, const TW* __restrict__ w,
+                                                   const float* __restrict__ bias, TO* __restrict__ out, int N, int H, int W,
+                                                   int Ho, int Wo, int Co, int act, const float* __restrict__ post_scale,
+                                                   const float* __restrict__ post_shift) {
+  extern __shared__ float ws[];  // [27][Co]
+  for (int e = threadIdx.x; e < 27 * Co; e += blockDim.x) {
+    const int co = e / 27, k = e % 27;
+    ws[k * Co + co] = to_f<TW>(w[e]);
+  }
+  __syncthreads();
+  constexpr int NV = 3 * S + 3;            // input columns touched by 4 adjacent output pixels
+  const int tpq = Co >> 3;                 // threads per pixel quad
+  const int qpb = blockDim.x / tpq;        // quads per block iteration
+  const int cg = (threadIdx.x % tpq) * 8;
+  const int ql = threadIdx.x / tpq;
+  const int Wq = Wo >> 2;
+  const long long Q = (long long)N * Ho * Wq;
+  const long long HW = (long long)H * W;
+  for (long long q = (long long)blockIdx.x * qpb + ql; q < Q; q += (long long)gridDim.x * qpb) {
+    const int ow0 = (int)(q % Wq) * 4;
+    const long long r = q / Wq;
+    const int oh = (int)(r % Ho);
+    const long long n = r / Ho;
+    float acc[4][8];
 #pragma unroll
-  for (int j = 0; j < 28; ++j) acc[j] = 0.f;
-  const long long M = (long long)N * Ho * Wo, HW = (long long)H * W;
-  for (long long m = (long long)blockIdx.x * blockDim.y + threadIdx.y; m < M; m += (long long)gridDim.x * blockDim.y) {
-    const int ow = (int)(m % Wo);
-    const long long q = m / Wo;
-    const int oh = (int)(q % Ho);
-    const long long n = q / Ho;
-    const float g = to_f<T>(dy[m * Co + co]);
-    acc[27] += g;
+    for (int c = 0; c < 8; ++c) {
+      const float b = bias ? bias[cg + c] : 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j][c] = b;
+    }
     const float* xb = x + n * 3 * HW;
+    const int iw0 = ow0 * S - 1;
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
-      const int ih = oh * stride - 1 + kh;
+      const int ih = oh * S - 1 + kh;
       if (ih < 0 || ih >= H) continue;
 #pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const int iw = ow * stride - 1 + kw;
-        if (iw < 0 || iw >= W) continue;
+      for (int ci = 0; ci < 3; ++ci) {
+        const float* xr = xb + ci * HW + (long long)ih * W;
+        float v[NV];
 #pragma unroll
-        for (int ci = 0; ci < 3; ++ci) acc[(kh * 3 + kw) * 3 + ci] = fmaf(g, xb[ci * HW + (long long)ih * W + iw], acc[(kh * 3 + kw) * 3 + ci]);
+        for (int i = 0; i < NV; ++i) {
+          const int iw = iw0 + i;
+          v[i] = (iw >= 0 && iw < W) ? __ldg(xr + iw) : 0.f;
+        }
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const float* wp = ws + ((kh * 3 + kw) * 3 + ci) * Co + cg;
+          const float4 w0 = *(const float4*)wp, w1 = *(const float4*)(wp + 4);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float a = v[j * S + kw];
+            acc[j][0] = fmaf(a, w0.x, acc[j][0]); acc[j][1] = fmaf(a, w0.y, acc[j][1]);
+            acc[j][2] = fmaf(a, w0.z, acc[j][2]); acc[j][3] = fmaf(a, w0.w, acc[j][3]);
+            acc[j][4] = fmaf(a, w1.x, acc[j][4]); acc[j][5] = fmaf(a, w1.y, acc[j][5]);
+            acc[j][6] = fmaf(a, w1.z, acc[j][6]); acc[j][7] = fmaf(a, w1.w, acc[j][7]);
+          }
+        }
       }
     }
-  }
-  // reduce over threadIdx.y through shared memory, then one atomic per (co, k) per block
-  extern __shared__ float red[];  // [blockDim.y][Co][28]
-  float* mine = red + ((size_t)threadIdx.y * Co + co) * 28;
+    float sc[8], sh[8];
+    if (post_scale) {
 #pragma unroll
-  for (int j = 0; j < 28; ++j) mine[j] = acc[j];
-  __syncthreads();
-  if (threadIdx.y == 0) {
-    for (int y = 1; y < (int)blockDim.y; ++y) {
-      const float* o = red + ((size_t)y * Co + co) * 28;
-#pragma unroll
-      for (int j = 0; j < 28; ++j) acc[j] += o[j];
+      for (int c = 0; c < 8; ++c) { sc[c] = post_scale[cg + c]; sh[c] = post_shift[cg + c]; }
     }
+    const long long m0 = (r * Wo + ow0);
 #pragma unroll
-    for (int j = 0; j < 27; ++j) atomicAdd(dw + (long long)co * 27 + j, acc[j]);
-    if (db) atomicAdd(db + co, acc[27]);
+    for (int j = 0; j < 4; ++j) {
+      if (act == 2) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[j][c] = acc[j][c] > 0.f ? acc[j][c] : expm1f(acc[j][c]);
+      }
+      if (post_scale) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[j][c] = fmaf(acc[j][c], sc[c], sh[c]);
+      }
+      store8<TO>(out + (m0 + j) * Co + cg, acc[j]);
+    }
   }
 }
 
-// ---------------------------------------------------------------------------------- wgrad, 3 output channels
-// dw[co<3][9][64] += sum_pix dz[n,co,oh,ow] * a[pix @ tap][ci];  db[co] += sum dz.   a NHWC [N,H,W,64] (T), dz NCHW float32.
 template <typename T>
-__global__ void __launch_bounds__(256) wgrad_cout3_k(const T* __restrict__ a, const float* __restrict__ dz,
-                                                     float* __restrict__ dw, float* __restrict__ db, int N, int H, int W) {
-  const int ci = threadIdx.x;  // 64
-  float acc[27];
+__device__ __forceinline__ void load8(const T* p, float* v);
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float* v) {
+  const float4 a = ((const float4*)p)[0], b = ((const float4*)p)[1];
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void load8<bf16>(const bf16* p, float* v) {
+  const uint4 u = *(const uint4*)p;
+  const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-  for (int j = 0; j < 27; ++j) acc[j] = 0.f;
-  float bsum = 0.f;
-  const long long M = (long long)N * H * W, HW = (long long)H * W;
-  for (long long m = (long long)blockIdx.x * blockDim.y + threadIdx.y; m < M; m += (long long)gridDim.x * blockDim.y) {
-    const int ow = (int)(m % W);
-    const long long q = m / W;
-    const int oh = (int)(q % H);
-    const long long n = q / H;
-    const float* zp = dz + n * 3 * HW + (long long)oh * W + ow;
-    const float g0 = zp[0], g1 = zp[HW], g2 = zp[2 * HW];
-    if (ci < 3) bsum += ci == 0 ? g0 : (ci == 1 ? g1 : g2);
-#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(*(const __nv_bfloat162*)&w4[i]);
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+
+// ---------------------------------------------------------------------------------- 64 -> 3, 2 pixels per thread
+// in: NHWC [N,H,W,64] (TI); w: [3][9][64] (TW); out: NCHW float32 [N,3,H,W]; W % 2 == 0.
+// Weights sit in shared memory as [9][64] float4 (co0, co1, co2, 0): every weight read is a warp-wide broadcast and
+// feeds 6 FMAs (3 outputs x 2 pixels).
+template <typename TI, typename TW>
+__global__ void __launch_bounds__(128) conv_cout3_k(const TI* __restrict__ in, const TW* __restrict__ w,
+                                                    const float* __restrict__ bias, float* __restrict__ out, int N, int H, int W,
+                                                    int act) {
+  __shared__ float4 wsm[9 * 64];
+  for (int e = threadIdx.x; e < 9 * 64; e += blockDim.x)
+    wsm[e] = make_float4(to_f<TW>(w[e]), to_f<TW>(w[576 + e]), to_f<TW>(w[1152 + e]), 0.f);
+  __syncthreads();
+  const int Wp = W >> 1;
+  const long long P = (long long)N * H * Wp, HW = (long long)H * W;
+  const float b0 = bias ? bias[0] : 0.f, b1 = bias ? bias[1] : 0.f, b2 = bias ? bias[2] : 0.f;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+    const int ow0 = (int)(p % Wp) * 2;
+    const long long r = p / Wp;
+    const int oh = (int)(r % H);
+    const long long n = r / H;
+    float a[2][3] = {{b0, b1, b2}, {b0, b1, b2}};
+#pragma unroll 1
     for (int kh = 0; kh < 3; ++kh) {
       const int ih = oh - 1 + kh;
       if (ih < 0 || ih >= H) continue;
+      const TI* rowp = in + ((n * H + ih) * W) * 64;
+#pragma unroll 2
+      for (int ch = 0; ch < 8; ++ch) {
+        float v[4][8];
 #pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const int iw = ow - 1 + kw;
-        if (iw < 0 || iw >= W) continue;
-        const float v = to_f<T>(a[((n * H + ih) * W + iw) * 64 + ci]);
-        const int t = kh * 3 + kw;
-        acc[t] = fmaf(g0, v, acc[t]);
-        acc[9 + t] = fmaf(g1, v, acc[9 + t]);
-        acc[18 + t] = fmaf(g2, v, acc[18 + t]);
+        for (int c = 0; c < 4; ++c) {
+          const int iw = ow0 - 1 + c;
+          if (iw >= 0 && iw < W) {
+            load8<TI>(rowp + (long long)iw * 64 + ch * 8, v[c]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[c][i] = 0.f;
+          }
+        }
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const float4* wp = wsm + (kh * 3 + kw) * 64 + ch * 8;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 ww = wp[i];
+            a[0][0] = fmaf(v[kw][i], ww.x, a[0][0]); a[0][1] = fmaf(v[kw][i], ww.y, a[0][1]); a[0][2] = fmaf(v[kw][i], ww.z, a[0][2]);
+            a[1][0] = fmaf(v[kw + 1][i], ww.x, a[1][0]); a[1][1] = fmaf(v[kw + 1][i], ww.y, a[1][1]);
+            a[1][2] = fmaf(v[kw + 1][i], ww.z, a[1][2]);
+          }
+        }
       }
     }
-  }
-  extern __shared__ float red[];  // [blockDim.y][64][28]
-  float* mine = red + ((size_t)threadIdx.y * 64 + ci) * 28;
+    float* op = out + n * 3 * HW + (long long)oh * W + ow0;
 #pragma unroll
-  for (int j = 0; j < 27; ++j) mine[j] = acc[j];
-  mine[27] = bsum;
-  __syncthreads();
-  if (threadIdx.y == 0) {
-    for (int y = 1; y < (int)blockDim.y; ++y) {
-      const float* o = red + ((size_t)y * 64 + ci) * 28;
-#pragma unroll
-      for (int j = 0; j < 27; ++j) acc[j] += o[j];
-      bsum += o[27];
+    for (int co = 0; co < 3; ++co) {
+      float y0 = a[0][co], y1 = a[1][co];
+      if (act == 1) { y0 = tanhf(y0); y1 = tanhf(y1); }
+      *(float2*)(op + co * HW) = make_float2(y0, y1);
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------- weight gradient of both boundary convs
+// G[c][t][j] = sum_m wide[m][c] * narrow[n, j, oh*S - 1 + kh, ow*S - 1 + kw]      (t = kh*3 + kw, j < 3, c < C)
+//   MODE 0 (3 -> C conv, wgrad_cin3): wide = dy NHWC, narrow = x NCHW;  dw[(c*9 + t)*3 + j] += G;  db[c] += sum_m wide[m][c]
+//   MODE 1 (C -> 3 conv, wgrad_cout3, C = 64, S = 1): wide = layer input a NHWC, narrow = dz NCHW;
+//                                                     dw[(j*9 + 8 - t)*C + c] += G;  db[j] += sum dz[j]
+// Per tile of 64 wide pixels the block builds the [64][28] im2col patch of the narrow tensor in shared memory; a thread
+// owns 2 wide channels x 27 patch columns (54 accumulators) and reads the patch with broadcast LDS.128.
+#define WG_TP 64
+template <typename T>
+__device__ __forceinline__ float2 load2(const T* p);
+template <>
+__device__ __forceinline__ float2 load2<float>(const float* p) { return *(const float2*)p; }
+template <>
+__device__ __forceinline__ float2 load2<bf16>(const bf16* p) { return __bfloat1622float2(*(const __nv_bfloat162*)p); }
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) wgrad3_k(const float* __restrict__ narrow, const T* __restrict__ wide,
+                                                float* __restrict__ dw, float* __restrict__ db, int N, int Hn, int Wn, int Hw,
+                                                int Ww, int C, int S) {
+  __shared__ __align__(16) float patch[WG_TP * 28];
+  __shared__ __align__(16) float red[128 * 56];  // [blockDim.y / 2 pixel groups][blockDim.x threads][2][28] = 128 threads x 56
+  const int cx = threadIdx.x, py = threadIdx.y, GY = blockDim.y, TX = blockDim.x;
+  const int tid = py * TX + cx;
+  float acc[2][28];
 #pragma unroll
-    for (int co = 0; co < 3; ++co)
+  for (int k = 0; k < 28; ++k) acc[0][k] = acc[1][k] = 0.f;
+  float nsum = 0.f;  // MODE 1: bias gradient = sum of the centre column of the patch (threads cx < 3)
+  const long long M = (long long)N * Hw * Ww, HWn = (long long)Hn * Wn;
+  const long long tiles = (M + WG_TP - 1) / WG_TP;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const long long m0 = tile * WG_TP;
+    __syncthreads();  // previous tile's readers are done
+    for (int e = tid; e < WG_TP * 28; e += 256) {
+      const int p = e / 28, k = e - p * 28;
+      const long long m = m0 + p;
+      float v = 0.f;
+      if (k < 27 && m < M) {
+        const int ow = (int)(m % Ww);
+        const long long r = m / Ww;
+        const int oh = (int)(r % Hw);
+        const long long n = r / Hw;
+        const int t = k / 3, j = k - t * 3;
+        const int ih = oh * S - 1 + t / 3, iw = ow * S - 1 + t % 3;
+        if (ih >= 0 && ih < Hn && iw >= 0 && iw < Wn) v = __ldg(narrow + (n * 3 + j) * HWn + (long long)ih * Wn + iw);
+      }
+      patch[e] = v;
+    }
+    __syncthreads();
+    for (int p = py; p < WG_TP; p += GY) {
+      const long long m = m0 + p;
+      if (m >= M) break;
+      const float2 g = load2<T>(wide + m * C + 2 * cx);
+      const float4* pp = (const float4*)(patch + p * 28);
+      float v[28];
 #pragma unroll
-      for (int t = 0; t < 9; ++t) atomicAdd(dw + ((long long)co * 9 + t) * 64 + ci, acc[co * 9 + t]);
-    if (db && ci < 3) atomicAdd(db + ci, bsum);
+      for (int i = 0; i < 7; ++i) {
+        const float4 q = pp[i];
+        v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+      }
+#pragma unroll
+      for (int k = 0; k < 27; ++k) {
+        acc[0][k] = fmaf(g.x, v[k], acc[0][k]);
+        acc[1][k] = fmaf(g.y, v[k], acc[1][k]);
+      }
+      if (MODE == 0) { acc[0][27] += g.x; acc[1][27] += g.y; }
+      if (MODE == 1 && cx < 3) nsum += cx == 0 ? v[12] : (cx == 1 ? v[13] : v[14]);
+    }
+  }
+  // tree reduction over the pixel groups (threadIdx.y), then one atomic per accumulator per block
+  for (int half = GY >> 1; half >= 1; half >>= 1) {
+    __syncthreads();
+    if (py >= half && py < 2 * half) {
+      float* o = red + ((size_t)(py - half) * TX + cx) * 56;
+#pragma unroll
+      for (int k = 0; k < 28; ++k) { o[k] = acc[0][k]; o[28 + k] = acc[1][k]; }
+      if (MODE == 1) o[27] = nsum;
+    }
+    __syncthreads();
+    if (py < half) {
+      const float* o = red + ((size_t)py * TX + cx) * 56;
+      if (MODE == 1) nsum += o[27];
+#pragma unroll
+      for (int k = 0; k < 27; ++k) { acc[0][k] += o[k]; acc[1][k] += o[28 + k]; }
+      if (MODE == 0) { acc[0][27] += o[27]; acc[1][27] += o[55]; }
+    }
+  }
+  if (py == 0) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = 2 * cx + h;
+#pragma unroll
+      for (int k = 0; k < 27; ++k) {
+        const int t = k / 3, j = k - t * 3;
+        if (MODE == 0) atomicAdd(dw + (long long)c * 27 + k, acc[h][k]);
+        else atomicAdd(dw + ((long long)j * 9 + (8 - t)) * C + c, acc[h][k]);
+      }
+      if (MODE == 0 && db) atomicAdd(db + c, acc[h][27]);
+    }
+    if (MODE == 1 && db && cx < 3) atomicAdd(db + cx, nsum);
   }
 }
 
@@ -253,11 +418,26 @@ extern "C" int combat_conv_cin3(const float* x, const void* w, int w_dtype, cons
   const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
   const long long M = (long long)N * Ho * Wo;
   if (M <= 0) return 0;
-  const int ppb = 256 / (Co / 8);
-  const int grid = grid_for(M, ppb * 4);
   const size_t smem = (size_t)27 * Co * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
-#define LCI(TW, TO) conv_cin3_k<TW, TO><<<grid, 256, smem, st>>>(x, (const TW*)w, bias, (TO*)out, N, H, W, Ho, Wo, Co, stride, act, post_scale, post_shift)
+  if (Wo % 4 == 0) {
+    const int qpb = 256 / (Co / 8);
+    const int grid = grid_for(M / 4, qpb * 2);
+#define LCI(TW, TO)                                                                                                         \
+  {                                                                                                                         \
+    if (stride == 1)                                                                                                        \
+      conv_cin3_k<TW, TO, 1><<<grid, 256, smem, st>>>(x, (const TW*)w, bias, (TO*)out, N, H, W, Ho, Wo, Co, act, post_scale, post_shift); \
+    else                                                                                                                    \
+      conv_cin3_k<TW, TO, 2><<<grid, 256, smem, st>>>(x, (const TW*)w, bias, (TO*)out, N, H, W, Ho, Wo, Co, act, post_scale, post_shift); \
+  }
+    if (w_dtype == COMBAT_F32) { if (out_dtype == COMBAT_F32) LCI(float, float) else LCI(float, bf16) }
+    else { if (out_dtype == COMBAT_F32) LCI(bf16, float) else LCI(bf16, bf16) }
+#undef LCI
+    COMBAT_RETURN_LAUNCH("conv_cin3");
+  }
+  const int ppb = 256 / (Co / 8);
+  const int grid = grid_for(M, ppb * 4);
+#define LCI(TW, TO) conv_cin3_generic_k<TW, TO><<<grid, 256, smem, st>>>(x, (const TW*)w, bias, (TO*)out, N, H, W, Ho, Wo, Co, stride, act, post_scale, post_shift)
   if (w_dtype == COMBAT_F32) { if (out_dtype == COMBAT_F32) LCI(float, float); else LCI(float, bf16); }
   else { if (out_dtype == COMBAT_F32) LCI(bf16, float); else LCI(bf16, bf16); }
 #undef LCI
@@ -270,30 +450,43 @@ extern "C" int combat_conv_cout3(const void* in, int in_dtype, const void* w, in
   COMBAT_ARG(Ci == 64, 9);
   const long long M = (long long)N * H * W;
   if (M <= 0) return 0;
-  const int grid = grid_for(M, 8 * 16);
   cudaStream_t st = (cudaStream_t)stream;
-#define LCO(TI, TW) conv_cout3_k<TI, TW><<<grid, 256, 0, st>>>((const TI*)in, (const TW*)w, bias, out, N, H, W, act)
+  if (W % 2 == 0) {
+    const int grid = grid_for(M / 2, 128);
+#define LCO(TI, TW) conv_cout3_k<TI, TW><<<grid, 128, 0, st>>>((const TI*)in, (const TW*)w, bias, out, N, H, W, act)
+    if (in_dtype == COMBAT_F32) { if (w_dtype == COMBAT_F32) LCO(float, float); else LCO(float, bf16); }
+    else { if (w_dtype == COMBAT_F32) LCO(bf16, float); else LCO(bf16, bf16); }
+#undef LCO
+    COMBAT_RETURN_LAUNCH("conv_cout3");
+  }
+  const int grid = grid_for(M, 8 * 16);
+#define LCO(TI, TW) conv_cout3_generic_k<TI, TW><<<grid, 256, 0, st>>>((const TI*)in, (const TW*)w, bias, out, N, H, W, act)
   if (in_dtype == COMBAT_F32) { if (w_dtype == COMBAT_F32) LCO(float, float); else LCO(float, bf16); }
   else { if (w_dtype == COMBAT_F32) LCO(bf16, float); else LCO(bf16, bf16); }
 #undef LCO
   COMBAT_RETURN_LAUNCH("conv_cout3");
 }
 
+static int wgrad_grid(long long M) {
+  const long long tiles = (M + WG_TP - 1) / WG_TP;
+  const long long cap = 148 * 2;
+  return (int)(tiles < cap ? (tiles < 1 ? 1 : tiles) : cap);
+}
+
 extern "C" int combat_wgrad_cin3(const float* x, const void* dy, int dy_dtype, float* dw, float* db, int N, int H, int W, int Co,
                                  int stride, void* stream) {
   COMBAT_ARG(x && dy && dw, 0);
-  COMBAT_ARG(Co >= 32 && Co <= 256 && 256 % Co == 0 && (stride == 1 || stride == 2), 8);
+  COMBAT_ARG((Co == 32 || Co == 64 || Co == 128) && (stride == 1 || stride == 2), 8);
   const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
   const long long M = (long long)N * Ho * Wo;
   if (M <= 0) return 0;
-  dim3 block(Co, 256 / Co);
-  const int grid = grid_for(M, block.y * 64);
-  const size_t smem = (size_t)256 * 28 * sizeof(float);
+  dim3 block(Co / 2, 256 / (Co / 2));
+  const int grid = wgrad_grid(M);
   cudaStream_t st = (cudaStream_t)stream;
   if (dy_dtype == COMBAT_F32)
-    wgrad_cin3_k<float><<<grid, block, smem, st>>>(x, (const float*)dy, dw, db, N, H, W, Ho, Wo, Co, stride);
+    wgrad3_k<float, 0><<<grid, block, 0, st>>>(x, (const float*)dy, dw, db, N, H, W, Ho, Wo, Co, stride);
   else
-    wgrad_cin3_k<bf16><<<grid, block, smem, st>>>(x, (const bf16*)dy, dw, db, N, H, W, Ho, Wo, Co, stride);
+    wgrad3_k<bf16, 0><<<grid, block, 0, st>>>(x, (const bf16*)dy, dw, db, N, H, W, Ho, Wo, Co, stride);
   COMBAT_RETURN_LAUNCH("wgrad_cin3");
 }
 
@@ -303,13 +496,12 @@ extern "C" int combat_wgrad_cout3(const void* a, int a_dtype, const float* dz, f
   COMBAT_ARG(Ci == 64, 9);
   const long long M = (long long)N * H * W;
   if (M <= 0) return 0;
-  dim3 block(64, 4);
-  const int grid = grid_for(M, 4 * 64);
-  const size_t smem = (size_t)256 * 28 * sizeof(float);
+  dim3 block(32, 8);
+  const int grid = wgrad_grid(M);
   cudaStream_t st = (cudaStream_t)stream;
   if (a_dtype == COMBAT_F32)
-    wgrad_cout3_k<float><<<grid, block, smem, st>>>((const float*)a, dz, dw, db, N, H, W);
+    wgrad3_k<float, 1><<<grid, block, 0, st>>>(dz, (const float*)a, dw, db, N, H, W, H, W, 64, 1);
   else
-    wgrad_cout3_k<bf16><<<grid, block, smem, st>>>((const bf16*)a, dz, dw, db, N, H, W);
+    wgrad3_k<bf16, 1><<<grid, block, 0, st>>>(dz, (const bf16*)a, dw, db, N, H, W, H, W, 64, 1);
   COMBAT_RETURN_LAUNCH("wgrad_cout3");
 }
