@@ -35,7 +35,8 @@ class ConvTcDesc(C.Structure):
     _fields_ = [("in_", vp), ("w", vp), ("out", vp), ("bias", vp), ("residual", vp), ("stats", vp),
                 ("N", i32), ("Hi", i32), ("Wi", i32), ("Ci", i32), ("Ho", i32), ("Wo", i32), ("Co", i32),
                 ("KH", i32), ("KW", i32), ("stride", i32), ("pad", i32), ("up", i32), ("out_f32", i32), ("res_f32", i32),
-                ("act", i32), ("post_scale", vp), ("post_shift", vp)]
+                ("act", i32), ("post_scale", vp), ("post_shift", vp),
+                ("out2", vp), ("scale2", vp), ("shift2", vp), ("mask", vp), ("mask_scale", vp), ("post_add", vp)]
 
 
 P = C.POINTER
@@ -53,7 +54,7 @@ _SIGS = {
     "combat_prep_weights": ([vp, vp, i32, vp, i32, i64, vp], i32),
     "combat_conv_simt": ([P(ConvDesc), vp], i32),
     "combat_conv_wgrad_simt": ([P(ConvDesc), vp, i32, vp, vp], i32),
-    "combat_conv_cin3": ([vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp], i32),
+    "combat_conv_cin3": ([vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp], i32),
     "combat_conv_cout3": ([vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, vp], i32),
     "combat_wgrad_cin3": ([vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, vp], i32),
     "combat_wgrad_cout3": ([vp, i32, vp, vp, vp, i32, i32, i32, i32, vp], i32),
@@ -62,6 +63,7 @@ _SIGS = {
     "combat_conv_tc_supported": ([P(ConvTcDesc)], i32),
     "combat_bn_stats": ([vp, i32, i64, i32, vp, i32, P(i32), vp], i32),
     "combat_bn_finalize": ([vp, i32, i64, i32, vp, vp, vp, vp, f32, f32, vp, vp, vp, vp, vp], i32),
+    "combat_bn_eval_affine": ([vp, vp, vp, i32, f32, vp, vp, vp], i32),
     "combat_affine_act": ([vp, i32, vp, vp, i32, i64, i32, vp, vp, i32, vp], i32),
     "combat_bn_bwd_reduce": ([vp, vp, i32, vp, i32, i64, i32, vp, vp, vp, i32, P(i32), i32, vp], i32),
     "combat_bn_bwd_finalize": ([vp, i32, i32, vp, vp, vp], i32),

@@ -144,7 +144,8 @@ template <typename TW, typename TO, int S>
 __global__ void __launch_bounds__(256) conv_cin3_k(const float* __restrict__ x, const TW* __restrict__ w,
                                                    const float* __restrict__ bias, TO* __restrict__ out, int N, int H, int W,
                                                    int Ho, int Wo, int Co, int act, const float* __restrict__ post_scale,
-                                                   const float* __restrict__ post_shift) {
+                                                   const float* __restrict__ post_shift, bf16* __restrict__ out2,
+                                                   const float* __restrict__ scale2, const float* __restrict__ shift2) {
   extern __shared__ float ws[];  // [27][Co]
   for (int e = threadIdx.x; e < 27 * Co; e += blockDim.x) {
     const int co = e / 27, k = e % 27;
@@ -218,6 +219,12 @@ __global__ void __launch_bounds__(256) conv_cin3_k(const float* __restrict__ x, 
         for (int c = 0; c < 8; ++c) acc[j][c] = fmaf(acc[j][c], sc[c], sh[c]);
       }
       store8<TO>(out + (m0 + j) * Co + cg, acc[j]);
+      if (out2) {  // eval-mode BatchNorm + ReLU of the first PreAct block, fused (preact_resnet.py:29-31)
+        float u[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) u[c] = fmaxf(fmaf(acc[j][c], scale2[cg + c], shift2[cg + c]), 0.f);
+        store8<bf16>(out2 + (m0 + j) * Co + cg, u);
+      }
     }
   }
 }
@@ -412,8 +419,9 @@ static int grid_for(long long work_items, int per_block) {
 
 extern "C" int combat_conv_cin3(const float* x, const void* w, int w_dtype, const float* bias, void* out, int out_dtype, int N,
                                 int H, int W, int Co, int stride, int act, const float* post_scale, const float* post_shift,
-                                void* stream) {
+                                void* out2, const float* scale2, const float* shift2, void* stream) {
   COMBAT_ARG(x && w && out, 0);
+  COMBAT_ARG(!out2 || (scale2 && shift2), 15);
   COMBAT_ARG(Co % 8 == 0 && Co <= 256 && 256 % (Co / 8) == 0 && (stride == 1 || stride == 2), 9);
   const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
   const long long M = (long long)N * Ho * Wo;
@@ -426,15 +434,16 @@ extern "C" int combat_conv_cin3(const float* x, const void* w, int w_dtype, cons
 #define LCI(TW, TO)                                                                                                         \
   {                                                                                                                         \
     if (stride == 1)                                                                                                        \
-      conv_cin3_k<TW, TO, 1><<<grid, 256, smem, st>>>(x, (const TW*)w, bias, (TO*)out, N, H, W, Ho, Wo, Co, act, post_scale, post_shift); \
+      conv_cin3_k<TW, TO, 1><<<grid, 256, smem, st>>>(x, (const TW*)w, bias, (TO*)out, N, H, W, Ho, Wo, Co, act, post_scale, post_shift, (bf16*)out2, scale2, shift2); \
     else                                                                                                                    \
-      conv_cin3_k<TW, TO, 2><<<grid, 256, smem, st>>>(x, (const TW*)w, bias, (TO*)out, N, H, W, Ho, Wo, Co, act, post_scale, post_shift); \
+      conv_cin3_k<TW, TO, 2><<<grid, 256, smem, st>>>(x, (const TW*)w, bias, (TO*)out, N, H, W, Ho, Wo, Co, act, post_scale, post_shift, (bf16*)out2, scale2, shift2); \
   }
     if (w_dtype == COMBAT_F32) { if (out_dtype == COMBAT_F32) LCI(float, float) else LCI(float, bf16) }
     else { if (out_dtype == COMBAT_F32) LCI(bf16, float) else LCI(bf16, bf16) }
 #undef LCI
     COMBAT_RETURN_LAUNCH("conv_cin3");
   }
+  COMBAT_ARG(!out2, 15);  // the fused second output needs Wo % 4 == 0
   const int ppb = 256 / (Co / 8);
   const int grid = grid_for(M, ppb * 4);
 #define LCI(TW, TO) conv_cin3_generic_k<TW, TO><<<grid, 256, smem, st>>>(x, (const TW*)w, bias, (TO*)out, N, H, W, Ho, Wo, Co, stride, act, post_scale, post_shift)

@@ -117,6 +117,10 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
 #define TC_MAX_TAPS 9
 #define TILE_M 128
 #define KCHUNK 64  // bf16 elements per 128-byte swizzle row
+#define TC_EPI_WARPS 8
+#define TC_THREADS (64 + 32 * TC_EPI_WARPS)
+#define EPI_CH 32                    // accumulator columns per epilogue chunk
+#define EPI_ROWB (EPI_CH * 4 + 16)   // padded row pitch of the per-warp transpose tile (conflict-free 16-byte accesses)
 
 struct TcTaps {
   int ntaps[TC_MAX_CLASSES];
@@ -131,7 +135,8 @@ struct TcParams {
   int N, Hc, Wc;          // pixel grid of one class (== output grid when n_classes == 1)
   int out_H, out_W, Co;   // full output tensor
   int out_scale;          // output pixel = class pixel * out_scale + (cls_p, cls_q)
-  int BW, BH, BNI;        // pixel box, BW*BH*BNI == 128
+  int BW, BH, BNI;        // pixel box, BW*BH*BNI == 128 (all powers of two)
+  int lbw, lbh;           // log2(BW), log2(BH)
   int tiles_w, tiles_h, tiles_n, tiles_co, n_classes, total_tiles;
   int kchunks;            // Ci / 64
   void* out;             // bf16 or float32 (out_f32)
@@ -141,6 +146,13 @@ struct TcParams {
   int act;
   const float* post_scale;
   const float* post_shift;
+  // fused consumers of the accumulator (all optional)
+  void* out2;               // bf16 NHWC: relu(v * scale2[c] + shift2[c]) -- the eval-mode BatchNorm+ReLU the next conv reads
+  const float* scale2;
+  const float* shift2;
+  const bf16* mask;         // bf16 NHWC like out: v = mask > 0 ? v * mask_scale[c] : 0 -- backward of relu(bn_eval(.))
+  const float* mask_scale;
+  const bf16* post_add;     // bf16 NHWC like out, added after the mask (gradient arriving over an identity shortcut)
   TcTaps taps;
 };
 
@@ -154,9 +166,9 @@ struct TcCfg {
   static constexpr int A_BYTES = TILE_M * KCHUNK * 2;    // 16 KB
   static constexpr int B_BYTES = BLOCK_N * KCHUNK * 2;   // 8 / 16 KB
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BLOCK_N == 64 ? 8 : 6;
+  static constexpr int STAGES = BLOCK_N == 64 ? 7 : 5;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;          // two accumulator buffers (128 or 256: powers of two)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + TC_EPI_WARPS * 32 * EPI_ROWB /*epilogue*/;
 };
 
 __device__ __forceinline__ void decode_tile(const TcParams& p, int tile, int& cls, int& nt, int& ht, int& wt, int& cot) {
@@ -171,8 +183,10 @@ __device__ __forceinline__ void decode_tile(const TcParams& p, int tile, int& cl
 }
 
 // ---------------------------------------------------------------------------------------------- fwd / dgrad kernel
-template <int BLOCK_N>
-__global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
+// MODE 0: out = act(acc + bias)*post_scale+post_shift + residual; out2 = bf16 relu(out*scale2+shift2)
+// MODE 1: out = bf16( mask > 0 ? (acc + residual) * mask_scale : 0 ) + post_add     (residual XOR post_add, both bf16)
+template <int BLOCK_N, int MODE>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   using Cfg = TcCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B atoms need 1024 B alignment
@@ -194,7 +208,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[a], TC_EPI_WARPS);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -267,105 +281,169 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
       }
     }
   } else {
-    // ===================== epilogue: TMEM -> registers -> (bias, residual) -> bf16 global =====================
-    const int quarter = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
-    const int row = quarter * 32 + lane;
+    // ===================== epilogue: TMEM -> registers -> shared (transpose) -> coalesced global =====================
+    // 8 warps: warp w owns TMEM lanes [32*(w%4), +32) (hardware rule) and the column half (w-2)/4 of the tile.
+    // tcgen05.ld hands a thread one accumulator ROW (pixel); writing rows straight to NHWC memory makes every store
+    // instruction touch 32 different lines.  Each warp therefore transposes its 32 x 32 chunk through a padded
+    // shared-memory tile and continues in a layout where a warp instruction covers 4 rows x 128 contiguous bytes:
+    // residual / mask / shortcut-gradient loads and all stores are full-line accesses.  Those loads are ISSUED BEFORE
+    // the wait on the accumulator, so their latency hides under the tile's MMAs.
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int NCH = BLOCK_N / 64;  // 32-column chunks per warp
+    uint8_t* stg = smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256 + (warp - 2) * (32 * EPI_ROWB);
+    const int sub = lane >> 3;     // row within a group of 4
+    const int cseg = lane & 7;     // 16-byte column segment: columns cseg*4 .. cseg*4+3 of the chunk
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       int cls, nt, ht, wt, cot;
       decode_tile(p, tile, cls, nt, ht, wt, cot);
       const bool has_acc = p.taps.ntaps[cls] > 0;
-      // pixel of this row
-      const int wi = row % p.BW;
-      const int r2 = row / p.BW;
-      const int hi = r2 % p.BH;
-      const int ni = r2 / p.BH;
-      const int n = nt * p.BNI + ni, a = ht * p.BH + hi, b = wt * p.BW + wi;
-      const bool valid = n < p.N && a < p.Hc && b < p.Wc;
-      const int oh = a * p.out_scale + p.taps.cls_p[cls], ow = b * p.out_scale + p.taps.cls_q[cls];
-      const long long obase = (((long long)n * p.out_H + oh) * p.out_W + ow) * p.Co + (long long)cot * BLOCK_N;
+      const int col0 = cot * BLOCK_N + half * (BLOCK_N / 2) + cseg * 4;  // this lane's first channel of chunk 0
+      // the 8 rows this lane owns in the coalesced phase: row = quarter*32 + 4*i + sub
+      long long ob[8];
+      uint32_t okmask = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = quarter * 32 + 4 * i + sub;
+        const int wi = row & (p.BW - 1);
+        const int r2 = row >> p.lbw;
+        const int hi = r2 & (p.BH - 1);
+        const int ni = r2 >> p.lbh;
+        const int n = nt * p.BNI + ni, a = ht * p.BH + hi, b = wt * p.BW + wi;
+        const bool valid = n < p.N && a < p.Hc && b < p.Wc;
+        const int oh = a * p.out_scale + p.taps.cls_p[cls], ow = b * p.out_scale + p.taps.cls_q[cls];
+        ob[i] = (((long long)n * p.out_H + oh) * p.out_W + ow) * p.Co + col0;
+        okmask |= (valid ? 1u : 0u) << i;
+      }
+      // ---- prefetch the epilogue inputs of this tile
+      float4 pr[NCH][8];  // MODE 0: float32 residual | bf16 residual in .x,.y;  MODE 1: mask in .x,.y, addend in .z,.w
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          pr[ch][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (okmask >> i & 1) {
+            const long long o = ob[i] + ch * EPI_CH;
+            if (MODE == 0) {
+              if (p.residual) {
+                if (p.res_f32) {
+                  pr[ch][i] = *(const float4*)((const float*)p.residual + o);
+                } else {
+                  const uint2 rr = *(const uint2*)((const bf16*)p.residual + o);
+                  pr[ch][i].x = __uint_as_float(rr.x); pr[ch][i].y = __uint_as_float(rr.y);
+                }
+              }
+            } else {
+              const uint2 mm = *(const uint2*)(p.mask + o);
+              pr[ch][i].x = __uint_as_float(mm.x); pr[ch][i].y = __uint_as_float(mm.y);
+              const bf16* addp = p.residual ? (const bf16*)p.residual : p.post_add;
+              if (addp) {
+                const uint2 aa = *(const uint2*)(addp + o);
+                pr[ch][i].z = __uint_as_float(aa.x); pr[ch][i].w = __uint_as_float(aa.y);
+              }
+            }
+          }
+        }
       if (has_acc) {
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
       }
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
-        uint32_t v[16];
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + half * (BLOCK_N / 2);
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        const int c0 = ch * EPI_CH;
+        const int colg = col0 + c0;
+        float4 f[8];
         if (has_acc) {
-          tmem_ld16(taddr + c0, v);
+          uint32_t v[32];
+          tmem_ld16(taddr + c0, *(uint32_t(*)[16])&v[0]);
+          tmem_ld16(taddr + c0 + 16, *(uint32_t(*)[16])&v[16]);
           tmem_ld_wait();
+          uint8_t* wr = stg + lane * EPI_ROWB;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) *(uint4*)(wr + j * 16) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = *(const float4*)(stg + (4 * i + sub) * EPI_ROWB + cseg * 16);
+          __syncwarp();
         } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = 0u;
+          for (int i = 0; i < 8; ++i) f[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        if (valid) {
-          float f[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+        if (MODE == 0) {
           if (p.bias) {
-            const float4* bp = (const float4*)(p.bias + cot * BLOCK_N + c0);
+            const float4 bb = *(const float4*)(p.bias + colg);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float4 bb = bp[j];
-              f[4 * j] += bb.x; f[4 * j + 1] += bb.y; f[4 * j + 2] += bb.z; f[4 * j + 3] += bb.w;
-            }
+            for (int i = 0; i < 8; ++i) { f[i].x += bb.x; f[i].y += bb.y; f[i].z += bb.z; f[i].w += bb.w; }
           }
           if (p.act == 2) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = f[j] > 0.f ? f[j] : expm1f(f[j]);
+            for (int i = 0; i < 8; ++i) {
+              f[i].x = f[i].x > 0.f ? f[i].x : expm1f(f[i].x); f[i].y = f[i].y > 0.f ? f[i].y : expm1f(f[i].y);
+              f[i].z = f[i].z > 0.f ? f[i].z : expm1f(f[i].z); f[i].w = f[i].w > 0.f ? f[i].w : expm1f(f[i].w);
+            }
           }
           if (p.post_scale) {
-            const float4* sp = (const float4*)(p.post_scale + cot * BLOCK_N + c0);
-            const float4* hp = (const float4*)(p.post_shift + cot * BLOCK_N + c0);
+            const float4 ss = *(const float4*)(p.post_scale + colg), hh = *(const float4*)(p.post_shift + colg);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float4 ss = sp[j], hh = hp[j];
-              f[4 * j] = fmaf(f[4 * j], ss.x, hh.x); f[4 * j + 1] = fmaf(f[4 * j + 1], ss.y, hh.y);
-              f[4 * j + 2] = fmaf(f[4 * j + 2], ss.z, hh.z); f[4 * j + 3] = fmaf(f[4 * j + 3], ss.w, hh.w);
+            for (int i = 0; i < 8; ++i) {
+              f[i].x = fmaf(f[i].x, ss.x, hh.x); f[i].y = fmaf(f[i].y, ss.y, hh.y);
+              f[i].z = fmaf(f[i].z, ss.z, hh.z); f[i].w = fmaf(f[i].w, ss.w, hh.w);
             }
           }
           if (p.residual) {
             if (p.res_f32) {
-              const float4* rp = (const float4*)((const float*)p.residual + obase + c0);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float4 rr = rp[j];
-                f[4 * j] += rr.x; f[4 * j + 1] += rr.y; f[4 * j + 2] += rr.z; f[4 * j + 3] += rr.w;
-              }
+              for (int i = 0; i < 8; ++i) { f[i].x += pr[ch][i].x; f[i].y += pr[ch][i].y; f[i].z += pr[ch][i].z; f[i].w += pr[ch][i].w; }
             } else {
-              const uint4* rp = (const uint4*)((const bf16*)p.residual + obase + c0);
 #pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                uint4 rr = rp[j];
-                const uint32_t w4[4] = {rr.x, rr.y, rr.z, rr.w};
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  float2 t2 = __bfloat1622float2(*(const __nv_bfloat162*)&w4[q]);
-                  f[8 * j + 2 * q] += t2.x;
-                  f[8 * j + 2 * q + 1] += t2.y;
-                }
+              for (int i = 0; i < 8; ++i) {
+                const uint32_t u0 = __float_as_uint(pr[ch][i].x), u1 = __float_as_uint(pr[ch][i].y);
+                const float2 r0 = __bfloat1622float2(*(const __nv_bfloat162*)&u0), r1 = __bfloat1622float2(*(const __nv_bfloat162*)&u1);
+                f[i].x += r0.x; f[i].y += r0.y; f[i].z += r1.x; f[i].w += r1.y;
               }
             }
           }
+        } else {
+          const float4 ms = *(const float4*)(p.mask_scale + colg);
+          const bool pre_add = p.residual != nullptr;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t m0u = __float_as_uint(pr[ch][i].x), m1u = __float_as_uint(pr[ch][i].y);
+            const uint32_t a0u = __float_as_uint(pr[ch][i].z), a1u = __float_as_uint(pr[ch][i].w);
+            const float2 m0 = __bfloat1622float2(*(const __nv_bfloat162*)&m0u), m1 = __bfloat1622float2(*(const __nv_bfloat162*)&m1u);
+            const float2 a0 = __bfloat1622float2(*(const __nv_bfloat162*)&a0u), a1 = __bfloat1622float2(*(const __nv_bfloat162*)&a1u);
+            if (pre_add) { f[i].x += a0.x; f[i].y += a0.y; f[i].z += a1.x; f[i].w += a1.y; }
+            f[i].x = m0.x > 0.f ? f[i].x * ms.x : 0.f; f[i].y = m0.y > 0.f ? f[i].y * ms.y : 0.f;
+            f[i].z = m1.x > 0.f ? f[i].z * ms.z : 0.f; f[i].w = m1.y > 0.f ? f[i].w * ms.w : 0.f;
+            if (!pre_add) { f[i].x += a0.x; f[i].y += a0.y; f[i].z += a1.x; f[i].w += a1.y; }
+          }
+        }
+        if (p.out) {
           if (p.out_f32) {
-            float4* op = (float4*)((float*)p.out + obase + c0);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            for (int i = 0; i < 8; ++i)
+              if (okmask >> i & 1) *(float4*)((float*)p.out + ob[i] + c0) = f[i];
           } else {
-            uint4* op = (uint4*)((bf16*)p.out + obase + c0);
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              uint32_t w4[4];
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[8 * j + 2 * q], f[8 * j + 2 * q + 1]);
-                w4[q] = *(uint32_t*)&h2;
+            for (int i = 0; i < 8; ++i)
+              if (okmask >> i & 1) {
+                const __nv_bfloat162 h0 = __floats2bfloat162_rn(f[i].x, f[i].y), h1 = __floats2bfloat162_rn(f[i].z, f[i].w);
+                *(uint2*)((bf16*)p.out + ob[i] + c0) = make_uint2(*(const uint32_t*)&h0, *(const uint32_t*)&h1);
               }
-              op[j] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-            }
           }
+        }
+        if (MODE == 0 && p.out2) {
+          const float4 ss = *(const float4*)(p.scale2 + colg), hh = *(const float4*)(p.shift2 + colg);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (okmask >> i & 1) {
+              const __nv_bfloat162 h0 = __floats2bfloat162_rn(fmaxf(fmaf(f[i].x, ss.x, hh.x), 0.f), fmaxf(fmaf(f[i].y, ss.y, hh.y), 0.f));
+              const __nv_bfloat162 h1 = __floats2bfloat162_rn(fmaxf(fmaf(f[i].z, ss.z, hh.z), 0.f), fmaxf(fmaf(f[i].w, ss.w, hh.w), 0.f));
+              *(uint2*)((bf16*)p.out2 + ob[i] + c0) = make_uint2(*(const uint32_t*)&h0, *(const uint32_t*)&h1);
+            }
         }
       }
       if (has_acc) {
@@ -469,8 +547,14 @@ static int num_sms() {
 }
 
 extern "C" int combat_conv_tc(const combat_conv_tc_desc* d, void* stream) {
-  COMBAT_ARG(d && d->in && d->w && d->out, 0);
+  COMBAT_ARG(d && d->in && d->w && (d->out || d->out2), 0);
   COMBAT_ARG(combat_conv_tc_supported(d), 0);
+  COMBAT_ARG(!d->out2 || (d->scale2 && d->shift2), 0);
+  COMBAT_ARG(!d->mask || d->mask_scale, 0);
+  // masked (backward) epilogue: bf16 in/out, at most one addend, no forward-only features
+  COMBAT_ARG(!d->mask || (d->out && !d->out_f32 && !d->res_f32 && !(d->residual && d->post_add) && !d->out2 && !d->bias &&
+                          !d->act && !d->post_scale), 0);
+  COMBAT_ARG(d->mask || !d->post_add, 0);
   TcParams p;
   memset(&p, 0, sizeof(p));
   TcMaps maps;
@@ -489,6 +573,12 @@ extern "C" int combat_conv_tc(const combat_conv_tc_desc* d, void* stream) {
   p.act = d->act;
   p.post_scale = d->post_scale;
   p.post_shift = d->post_shift;
+  p.out2 = d->out2;
+  p.scale2 = d->scale2;
+  p.shift2 = d->shift2;
+  p.mask = (const bf16*)d->mask;
+  p.mask_scale = d->mask_scale;
+  p.post_add = (const bf16*)d->post_add;
   const int BLOCK_N = (d->Co % 128 == 0) ? 128 : 64;
   p.tiles_co = d->Co / BLOCK_N;
   int rc;
@@ -561,19 +651,25 @@ extern "C" int combat_conv_tc(const combat_conv_tc_desc* d, void* stream) {
   }
   rc = make_w_map(&maps.w, d->w, d->Ci, KH * KW, d->Co, BLOCK_N);
   if (rc) return rc;
+  p.lbw = 0;
+  while ((1 << p.lbw) < p.BW) ++p.lbw;
+  p.lbh = 0;
+  while ((1 << p.lbh) < p.BH) ++p.lbh;
   p.tiles_w = cdiv(p.Wc, p.BW);
   p.tiles_h = cdiv(p.Hc, p.BH);
   p.tiles_n = cdiv(p.N, p.BNI);
   p.total_tiles = p.n_classes * p.tiles_n * p.tiles_h * p.tiles_w * p.tiles_co;
   int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   cudaStream_t st = (cudaStream_t)stream;
-  if (BLOCK_N == 128) {
-    cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM_BYTES);
-    conv_tc_kernel<128><<<grid, 192, TcCfg<128>::SMEM_BYTES, st>>>(maps, p);
-  } else {
-    cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::SMEM_BYTES);
-    conv_tc_kernel<64><<<grid, 192, TcCfg<64>::SMEM_BYTES, st>>>(maps, p);
+#define LAUNCH_C(BN, MD)                                                                                                  \
+  {                                                                                                                       \
+    cudaFuncSetAttribute(conv_tc_kernel<BN, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES);     \
+    conv_tc_kernel<BN, MD><<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st>>>(maps, p);                                     \
   }
+  const int mode = d->mask ? 1 : 0;
+  if (BLOCK_N == 128) { if (mode) LAUNCH_C(128, 1) else LAUNCH_C(128, 0) }
+  else { if (mode) LAUNCH_C(64, 1) else LAUNCH_C(64, 0) }
+#undef LAUNCH_C
   COMBAT_RETURN_LAUNCH("conv_tc");
 }
 

@@ -250,6 +250,27 @@ extern "C" int combat_bn_finalize(const float* partial, int nblk, long long R, i
   COMBAT_RETURN_LAUNCH("bn_finalize");
 }
 
+// eval-mode scale/shift of EVERY BatchNorm of a network in one launch: table4[i] = (gamma, beta, mean, var) indices of
+// flattened channel i into the flat parameter / running-stat buffers
+__global__ void bn_eval_affine_k(const float* __restrict__ params, const float* __restrict__ bufs, const int4* __restrict__ table,
+                                 int n, float eps, float* __restrict__ scale, float* __restrict__ shift) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int4 t = table[i];
+  const float invstd = 1.0f / sqrtf(bufs[t.w] + eps);
+  const float sc = params[t.x] * invstd;
+  scale[i] = sc;
+  shift[i] = params[t.y] - bufs[t.z] * sc;
+}
+
+extern "C" int combat_bn_eval_affine(const float* params, const float* bufs, const int* table4, int n, float eps, float* scale,
+                                     float* shift, void* stream) {
+  COMBAT_ARG(params && bufs && table4 && scale && shift, 0);
+  if (n <= 0) return 0;
+  bn_eval_affine_k<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(params, bufs, (const int4*)table4, n, eps, scale, shift);
+  COMBAT_RETURN_LAUNCH("bn_eval_affine");
+}
+
 extern "C" int combat_affine_act(const void* x, int x_dtype, const void* residual, void* y, int dtype, long long R, int C,
                                  const float* scale, const float* shift, int relu, void* stream) {
   COMBAT_ARG(x && y && scale && shift, 0);

@@ -29,7 +29,10 @@ class _NetFn(torch.autograd.Function):
         elif isinstance(net, nets.FrequencyDetector):
             y, c = net.forward(x.contiguous().float()), None
         else:
-            y, c = net.forward(x.contiguous().float(), train=mod.training, save=need_grad)
+            # an eval-mode forward whose weight gradients are wanted (the reference computes and discards them) keeps the
+            # unfused path; inference and input-gradient-only uses take the fused one
+            y, c = net.forward(x.contiguous().float(), train=mod.training, save=need_grad,
+                               fuse=not any(p.requires_grad for p in params))
         ctx.mod, ctx.c = mod, c
         ctx.wgrad = any(p.requires_grad for p in params)
         ctx.xgrad = x.requires_grad

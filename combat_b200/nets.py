@@ -188,11 +188,24 @@ class NetBase:
     def _tc_ok(self, cs: ConvSpec):
         return self.use_tc and cs.Cin % 64 == 0 and cs.Cout % 64 == 0
 
-    def conv_fwd(self, x, cs: ConvSpec, residual=None, pre=True):
-        """x: NHWC [N,H,W,Cin] in the activation dtype -> NHWC out (float32 when `pre`, i.e. feeding a norm)."""
+    def conv_fwd(self, x, cs: ConvSpec, residual=None, pre=True, bn_relu=None, want_out=True):
+        """x: NHWC [N,H,W,Cin] in the activation dtype -> NHWC out (float32 when `pre`, i.e. feeding a norm).
+        bn_relu=(scale, shift): the tcgen05 epilogue ALSO writes out2 = bf16 relu(out*scale+shift) (eval BatchNorm+ReLU of
+        the consumer); returns (out or None, out2) then."""
         N, H, W, Ct = x.shape
         Ho = (H + 2 * cs.pad - cs.k) // cs.stride + 1
         Wo = (W + 2 * cs.pad - cs.k) // cs.stride + 1
+        if bn_relu is not None:
+            out = torch.empty((N, Ho, Wo, cs.Cout), dtype=self.pre_dtype, device=self.device) if want_out else None
+            out2 = torch.empty((N, Ho, Wo, cs.Cout), dtype=self.dtype, device=self.device)
+            d = ops.conv_tc_desc(x, self._wptr(cs), out, N, H, W, cs.Cin, Ho, Wo, cs.Cout, cs.k, cs.k, cs.stride, cs.pad, 1,
+                                 bias=self._bias(cs), residual=residual, out2=out2, scale2=bn_relu[0], shift2=bn_relu[1])
+            d.res_f32 = int(residual is not None and residual.dtype == torch.float32)
+            if not (self._tc_ok(cs) and Ct == cs.Cin and lib.combat_conv_tc_supported(C.byref(d))):
+                raise RuntimeError("fused BatchNorm epilogue needs the tcgen05 path")
+            _tc_launch(lambda: lib.combat_conv_tc(C.byref(d), ops._s()), "conv_tc", 2.0 * N * Ho * Wo * cs.Cout * cs.Cin * cs.k * cs.k,
+                       _tag(N, H, W, cs) + " +bn")
+            return out, out2
         out = torch.empty((N, Ho, Wo, cs.Cout), dtype=self.pre_dtype if pre else self.dtype, device=self.device)
         if self._tc_ok(cs) and Ct == cs.Cin:
             d = ops.conv_tc_desc(x, self._wptr(cs), out, N, H, W, cs.Cin, Ho, Wo, cs.Cout, cs.k, cs.k, cs.stride, cs.pad, 1,
@@ -206,8 +219,10 @@ class NetBase:
                       pad=cs.pad, bias=self._bias(cs), residual=residual)
         return out
 
-    def conv_dgrad(self, dy, cs: ConvSpec, in_hw, residual=None, n_out_ch=None):
-        """dy: NHWC [N,Ho,Wo,Cout] -> dx NHWC [N,H,W,n_out_ch or Cin] (+ residual)."""
+    def conv_dgrad(self, dy, cs: ConvSpec, in_hw, residual=None, n_out_ch=None, mask=None, mask_scale=None, post_add=None):
+        """dy: NHWC [N,Ho,Wo,Cout] -> dx NHWC [N,H,W,n_out_ch or Cin] (+ residual).
+        mask/mask_scale/post_add: fused backward of the eval-mode relu(bn(.)) in front of this conv (tcgen05 path only):
+        dx = (mask > 0 ? (dgrad + residual) * mask_scale[c] : 0) + post_add."""
         N, Ho, Wo, _ = dy.shape
         H, W = in_hw
         Cx = cs.Cin if n_out_ch is None else n_out_ch
@@ -215,11 +230,13 @@ class NetBase:
         padp = cs.k - 1 - cs.pad
         if self._tc_ok(cs) and Cx == cs.Cin:
             d = ops.conv_tc_desc(dy, self._wptr(cs, True), dx, N, Ho, Wo, cs.Cout, H, W, cs.Cin, cs.k, cs.k, 1, padp,
-                                 cs.stride, residual=residual)
+                                 cs.stride, residual=residual, mask=mask, mask_scale=mask_scale, post_add=post_add)
             if lib.combat_conv_tc_supported(C.byref(d)):
                 _tc_launch(lambda: lib.combat_conv_tc(C.byref(d), ops._s()), "conv_tc(dgrad)", 2.0 * N * Ho * Wo * cs.Cout * cs.Cin * cs.k * cs.k,
                            _tag(N, H, W, cs))
                 return dx
+        if mask is not None or post_add is not None:
+            raise RuntimeError("fused BatchNorm backward epilogue needs the tcgen05 path")
         ops.conv_simt(dy, (N, Ho, Wo), ops.nhwc_strides(Ho, Wo, cs.Cout), self._wptr(cs, True), self.dt, dx, (H, W),
                       ops.nhwc_strides(H, W, Cx), Ci=cs.Cout, Co=Cx, KH=cs.k, KW=cs.k, stride=1, pad=padp, up=cs.stride,
                       residual=residual)
@@ -242,7 +259,7 @@ class NetBase:
                             Ci=cs.Cin, Co=cs.Cout, KH=cs.k, KW=cs.k, stride=cs.stride, pad=cs.pad, db=db)
 
     # ---- image-boundary convs (NCHW float32 on the 3-channel side), always CUDA-core kernels
-    def conv_first_fwd(self, x_nchw, cs: ConvSpec, out=None, out_ctot=None, pre=True):
+    def conv_first_fwd(self, x_nchw, cs: ConvSpec, out=None, out_ctot=None, pre=True, bn_relu=None):
         N, Cc, H, W = x_nchw.shape
         Ho = (H + 2 * cs.pad - cs.k) // cs.stride + 1
         Wo = (W + 2 * cs.pad - cs.k) // cs.stride + 1
@@ -250,7 +267,14 @@ class NetBase:
         if out is None:
             out = torch.empty((N, Ho, Wo, Ct), dtype=self.pre_dtype if pre else self.dtype, device=self.device)
         if self.fast_small and Cc == 3 and cs.k == 3 and cs.pad == 1 and Ct == cs.Cout and cs.Cout % 32 == 0 and 256 % cs.Cout == 0:
+            if bn_relu is not None:
+                out2 = torch.empty((N, Ho, Wo, Ct), dtype=self.dtype, device=self.device)
+                ops.conv_cin3(x_nchw, self._wptr(cs), self.dt, out, cs.Cout, cs.stride, bias=self._bias(cs), out2=out2,
+                              scale2=bn_relu[0], shift2=bn_relu[1])
+                return out, out2
             return ops.conv_cin3(x_nchw, self._wptr(cs), self.dt, out, cs.Cout, cs.stride, bias=self._bias(cs))
+        if bn_relu is not None:
+            raise RuntimeError("fused BatchNorm epilogue needs the direct 3-channel kernel")
         ops.conv_simt(x_nchw, (N, H, W), ops.nchw_strides(Cc, H, W), self._wptr(cs), self.dt, out, (Ho, Wo),
                       ops.nhwc_strides(Ho, Wo, Ct), Ci=cs.Cin, Co=cs.Cout, KH=cs.k, KW=cs.k, stride=cs.stride, pad=cs.pad,
                       bias=self._bias(cs))
@@ -352,6 +376,21 @@ class Classifier(NetBase):
             self.store.p(bn.name + ".weight").fill_(1.0)
             self.rv(bn).fill_(1.0)
         self.momentum, self.eps = 0.1, 1e-5
+        # eval-mode (scale, shift) of every BatchNorm in one launch: per-channel index table into store.flat / bufs
+        self.aff_off, tab, n = {}, [], 0
+        for bn in self.bns:
+            self.aff_off[bn.name] = n
+            go, bo, ro = self.store.offsets[bn.name + ".weight"], self.store.offsets[bn.name + ".bias"], self.buf_off[bn.name]
+            tab += [[go + c, bo + c, ro + c, ro + bn.C + c] for c in range(bn.C)]
+            n += bn.C
+        self.n_bn_ch = n
+        self._aff_table = torch.tensor(tab, dtype=torch.int32).to(self.device) if self.device.type == "cuda" else None
+        # the fused eval path (BatchNorm+ReLU in the tcgen05 epilogues) exists for the PreAct ordering on the bf16 path
+        self.fuse_eval = pre and self.use_tc
+
+    def eval_affine(self):
+        out = torch.empty((2, self.n_bn_ch), dtype=torch.float32, device=self.device)
+        return ops.bn_eval_affine(self.store.flat, self.bufs, self._aff_table, self.n_bn_ch, self.eps, out)
 
     # ---- buffers
     def rm(self, bn):
@@ -405,9 +444,12 @@ class Classifier(NetBase):
         return ops.bn_bwd_eval(dy, y, scale, relu, dadd, want_dres)
 
     # ---- forward
-    def forward(self, x_nchw, train: bool, save: bool = True):
-        """x_nchw float32 [N,C,H,W] -> (logits float32 [N,num_classes], ctx)."""
+    def forward(self, x_nchw, train: bool, save: bool = True, fuse: bool = True):
+        """x_nchw float32 [N,C,H,W] -> (logits float32 [N,num_classes], ctx).  fuse=False keeps the pre-normalisation
+        tensors of an eval-mode forward (needed only if weight gradients are wanted from it)."""
         pre = self.arch == "preact_resnet18"
+        if fuse and self.fuse_eval and not train and self.fast_small and x_nchw.shape[1] == 3 and x_nchw.shape[3] % 4 == 0:
+            return self._forward_eval_fused(x_nchw, save)
         ctx = {"x": x_nchw, "train": train, "blocks": []} if save else None
         h = self.conv_first_fwd(x_nchw, self.conv1)
         if not pre:
@@ -442,9 +484,60 @@ class Classifier(NetBase):
             ctx["feat_shape"], ctx["pooled"] = tuple(h.shape), pooled
         return logits, ctx
 
+    # ---- eval-mode PreAct forward/backward with BatchNorm+ReLU folded into the conv epilogues
+    def _forward_eval_fused(self, x_nchw, save):
+        """netC.eval() / clean_model forward (train_generator.py:214,227,228,250): per block the chain
+        bn1-relu-[shortcut]-conv1-bn2-relu-conv2-add is three tcgen05 launches and no elementwise pass -- each conv's
+        epilogue writes the bf16 relu(bn(.)) tensor its consumer reads (and the float32 residual stream when needed)."""
+        aff = self.eval_affine()
+
+        def sl(bn):
+            o = self.aff_off[bn.name]
+            return aff[0, o:o + bn.C], aff[1, o:o + bn.C]
+
+        ctx = {"x": x_nchw, "train": False, "fused": True, "blocks": []} if save else None
+        blocks = self.blocks
+        sc1 = sl(blocks[0]["bn1"])
+        h, o1 = self.conv_first_fwd(x_nchw, self.conv1, bn_relu=sc1)
+        for i, blk in enumerate(blocks):
+            s = self.conv_fwd(o1, blk["sc"]) if "sc" in blk else h
+            sc2 = sl(blk["bn2"])
+            _, o2 = self.conv_fwd(o1, blk["conv1"], bn_relu=sc2, want_out=False)
+            if save:
+                ctx["blocks"].append((o1, o2, sc1[0], sc2[0]))
+            if i + 1 < len(blocks):
+                sc1 = sl(blocks[i + 1]["bn1"])
+                # the float32 residual stream is only read by an identity shortcut
+                h, o1 = self.conv_fwd(o2, blk["conv2"], residual=s, bn_relu=sc1, want_out="sc" not in blocks[i + 1])
+            else:
+                h = self.conv_fwd(o2, blk["conv2"], residual=s)
+        logits, pooled = ops.pool_linear_fwd(h, 4, self.store.p("linear.weight"), self.store.p("linear.bias"))
+        if save:
+            ctx["feat_shape"], ctx["pooled"] = tuple(h.shape), pooled
+        return logits, ctx
+
+    def _backward_eval_fused(self, ctx, dlogits, need_dx):
+        st = self.store
+        dh = ops.pool_linear_bwd(dlogits, ctx["pooled"], st.p("linear.weight"), ctx["feat_shape"], self.dtype, 4, dW=None, db=None)
+        for blk, (o1, o2, scale1, scale2) in zip(reversed(self.blocks), reversed(ctx["blocks"])):
+            hw_in, hw_mid = o1.shape[1:3], o2.shape[1:3]
+            d_c1 = self.conv_dgrad(dh, blk["conv2"], hw_mid, mask=o2, mask_scale=scale2)
+            if "sc" in blk:
+                t = self.conv_dgrad(dh, blk["sc"], hw_in)
+                dh = self.conv_dgrad(d_c1, blk["conv1"], hw_in, residual=t, mask=o1, mask_scale=scale1)
+            else:
+                dh = self.conv_dgrad(d_c1, blk["conv1"], hw_in, mask=o1, mask_scale=scale1, post_add=dh)
+        if need_dx:
+            return self.conv_first_dgrad(dh, self.conv1, ctx["x"].shape[2:4])
+        return None
+
     # ---- backward
     def backward(self, ctx, dlogits, need_wgrad: bool, need_dx: bool):
         """Returns dx (NCHW float32) if need_dx.  Parameter gradients are accumulated into store.grad."""
+        if ctx.get("fused"):
+            if need_wgrad:
+                raise RuntimeError("the fused eval-mode path saves no pre-normalisation tensors: weight gradients need train mode")
+            return self._backward_eval_fused(ctx, dlogits, need_dx)
         pre = self.arch == "preact_resnet18"
         train = ctx["train"]
         st = self.store

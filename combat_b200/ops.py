@@ -243,10 +243,11 @@ def conv_wgrad_simt(x, x_geom, x_strides, dy, dy_geom, dy_strides, dw, *, Ci, Co
     check(lib.combat_conv_wgrad_simt(C.byref(d), _p(dy), dt_code(dy), _p(dw), _s()), "conv_wgrad_simt")
 
 
-def conv_cin3(x_nchw, w_ptr, w_dt, out, Co, stride, bias=None, act=0, post_scale=None, post_shift=None):
+def conv_cin3(x_nchw, w_ptr, w_dt, out, Co, stride, bias=None, act=0, post_scale=None, post_shift=None, out2=None,
+              scale2=None, shift2=None):
     N, _, H, W = x_nchw.shape
     check(lib.combat_conv_cin3(_p(x_nchw), w_ptr, w_dt, _p(bias), _p(out), dt_code(out), N, H, W, Co, stride, act,
-                               _p(post_scale), _p(post_shift), _s()), "conv_cin3")
+                               _p(post_scale), _p(post_shift), _p(out2), _p(scale2), _p(shift2), _s()), "conv_cin3")
     return out
 
 
@@ -268,9 +269,12 @@ def wgrad_cout3(a_nhwc, dz_nchw, dw, db):
 
 
 def conv_tc_desc(x, w_ptr, out, N, Hi, Wi, Ci, Ho, Wo, Co, KH, KW, stride, pad, up, bias=None, residual=None, stats=None,
-                 act=0, post_scale=None, post_shift=None):
+                 act=0, post_scale=None, post_shift=None, out2=None, scale2=None, shift2=None, mask=None, mask_scale=None,
+                 post_add=None):
     d = ConvTcDesc()
     d.act, d.post_scale, d.post_shift = act, _p(post_scale), _p(post_shift)
+    d.out2, d.scale2, d.shift2 = _p(out2), _p(scale2), _p(shift2)
+    d.mask, d.mask_scale, d.post_add = _p(mask), _p(mask_scale), _p(post_add)
     d.in_, d.w, d.out, d.bias, d.residual, d.stats = _p(x), w_ptr, _p(out), _p(bias), _p(residual), _p(stats)
     d.out_f32 = int(out is not None and out.dtype == torch.float32)
     d.res_f32 = int(residual is not None and residual.dtype == torch.float32)
@@ -313,6 +317,12 @@ def bn_eval_prepare(Cc, gamma, beta, rm, rv, eps):
     check(lib.combat_bn_finalize(None, 0, 1, Cc, _p(gamma), _p(beta), _p(rm), _p(rv), 0.0, eps, _p(st[0]), _p(st[1]),
                                  None, None, _s()), "bn_finalize(eval)")
     return st[0], st[1]
+
+
+def bn_eval_affine(params, bufs, table4, n, eps, out):
+    """out: float32 [2, n] (scale | shift) for every BatchNorm channel of a network, one launch."""
+    check(lib.combat_bn_eval_affine(_p(params), _p(bufs), _p(table4), n, eps, _p(out[0]), _p(out[1]), _s()), "bn_eval_affine")
+    return out
 
 
 def affine_act(x, scale, shift, relu, residual=None, out=None, out_dtype=None):

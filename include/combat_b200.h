@@ -123,12 +123,14 @@ int combat_conv_simt(const combat_conv_desc* d_host, void* stream);
 int combat_conv_wgrad_simt(const combat_conv_desc* d_host, const void* dy, int dy_dtype, float* dw_ohwi, void* stream);
 
 /* Direct kernels for the image-boundary layers (3 input or 3 output channels, 3x3, pad 1; csrc/conv_small.cu).
- *   conv_cin3  : x NCHW float32 [N,3,H,W], w [Co][9][3] -> out NHWC [N,Ho,Wo,Co]; act 0 none / 2 ELU, optional affine
+ *   conv_cin3  : x NCHW float32 [N,3,H,W], w [Co][9][3] -> out NHWC [N,Ho,Wo,Co]; act 0 none / 2 ELU, optional affine;
+ *                optional second output out2 = bf16 relu(out * scale2[c] + shift2[c]) (eval BatchNorm+ReLU of the next block)
  *   conv_cout3 : in NHWC [N,H,W,64], w [3][9][64] -> out NCHW float32 [N,3,H,W] (stride 1); act 0 none / 1 tanh
  *   wgrad_cin3 : dw[Co][9][3] += sum dy[pix][co] * x[pix@tap][ci], db[co] += sum dy      (x NCHW float32, dy NHWC)
  *   wgrad_cout3: dw[3][9][64] += sum dz[n,co,h,w] * a[pix@tap][ci], db[co] += sum dz     (a NHWC, dz NCHW float32) */
 int combat_conv_cin3(const float* x, const void* w, int w_dtype, const float* bias, void* out, int out_dtype, int N, int H,
-                     int W, int Co, int stride, int act, const float* post_scale, const float* post_shift, void* stream);
+                     int W, int Co, int stride, int act, const float* post_scale, const float* post_shift, void* out2,
+                     const float* scale2, const float* shift2, void* stream);
 int combat_conv_cout3(const void* in, int in_dtype, const void* w, int w_dtype, const float* bias, float* out, int N, int H,
                       int W, int Ci, int act, void* stream);
 int combat_wgrad_cin3(const float* x, const void* dy, int dy_dtype, float* dw, float* db, int N, int H, int W, int Co,
@@ -151,6 +153,18 @@ typedef struct {
   int act;               /* 0 none, 2 ELU(alpha=1) applied after bias */
   const float* post_scale; /* optional per-channel affine after act (eval BatchNorm of FrequencyModel) */
   const float* post_shift;
+  /* fused consumers of v = acc + bias (+ act, affine) + residual; all optional, `out` may be NULL when out2 is given:
+   *   mask/mask_scale : v = mask > 0 ? v * mask_scale[c] : 0   (backward of relu(bn_eval(x)): preact_resnet.py:20,22 in
+   *                     eval mode; mask = the saved bf16 activation, NHWC like out)
+   *   post_add        : v += post_add (bf16 NHWC like out; gradient arriving over an identity shortcut, added after the mask)
+   *   out             <- v
+   *   out2            <- bf16 relu(v * scale2[c] + shift2[c])  (the eval-mode BatchNorm+ReLU the NEXT conv reads) */
+  void* out2;
+  const float* scale2;
+  const float* shift2;
+  const void* mask;
+  const float* mask_scale;
+  const void* post_add;
 } combat_conv_tc_desc;
 int combat_conv_tc(const combat_conv_tc_desc* d_host, void* stream);
 int combat_conv_tc_wgrad(const combat_conv_tc_desc* d_host, const void* dy, float* dw_ohwi, void* stream);
@@ -166,6 +180,11 @@ int combat_bn_stats(const void* x, int dtype, long long R, int C, float* partial
 int combat_bn_finalize(const float* partial, int nblk, long long R, int C, const float* gamma, const float* beta,
                        float* running_mean, float* running_var, float momentum, float eps, float* scale, float* shift,
                        float* save_mean, float* save_invstd, void* stream);
+/* eval-mode (scale, shift) of every BatchNorm of a network in one launch: table4[4*i..4*i+3] = indices of (gamma, beta)
+ * in `params` and (running_mean, running_var) in `bufs` for flattened channel i:
+ *   scale[i] = gamma / sqrt(var + eps), shift[i] = beta - mean * scale[i]   (preact_resnet.py:20,22 under netC.eval()) */
+int combat_bn_eval_affine(const float* params, const float* bufs, const int* table4, int n, float eps, float* scale,
+                          float* shift, void* stream);
 /* y = [relu]( x*scale[c] + shift[c] (+ residual) ).  x_dtype: storage type of the pre-normalisation tensor x (the
  * conv output -- kept float32 next to bf16 activations so that statistics and normalisation see unrounded values);
  * dtype: storage type of residual / y (and of every gradient tensor below). */

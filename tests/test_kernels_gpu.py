@@ -487,3 +487,61 @@ def test_conv_tc_elu_affine_epilogue(ops):
     check(lib.combat_conv_tc(C.byref(d2), ops._s()), "conv_tc")
     torch.cuda.synchronize()
     assert rel(out32.permute(0, 3, 1, 2), F.conv2d(x, w, None, 1, 1) + res) < 2e-5
+
+
+@pytest.mark.parametrize("stride_up", [(1, 1), (1, 2)])
+def test_conv_tc_fused_batchnorm_epilogues(ops, stride_up):
+    """out2 = relu(v*scale2+shift2) next to out (eval BatchNorm+ReLU of the consumer); mask/mask_scale/post_add (its
+    backward) -- the epilogues behind nets.Classifier._forward_eval_fused / _backward_eval_fused."""
+    import ctypes as C
+
+    from combat_b200._lib import check, lib
+    _, up = stride_up
+    g = torch.Generator().manual_seed(77 + up)
+    N, Ci, Co, H = 3, 64, 128, 8
+    x = torch.randn(N, Ci, H, H, generator=g).bfloat16().float()
+    w = (torch.randn(Co, Ci, 3, 3, generator=g) * 0.05).bfloat16().float()
+    sc, sh = torch.rand(Co, generator=g) + 0.5, torch.randn(Co, generator=g) * 0.3
+    xd = dev(_nhwc(x).bfloat16())
+    w_f = dev(w.permute(0, 2, 3, 1).bfloat16())
+    if up == 1:
+        res = torch.randn(N, Co, H, H, generator=g)
+        y = F.conv2d(x, w, None, 1, 1) + res
+        y2 = F.relu(y * sc[None, :, None, None] + sh[None, :, None, None])
+        out = torch.empty(N, H, H, Co, device="cuda", dtype=torch.float32)
+        out2 = torch.empty(N, H, H, Co, device="cuda", dtype=torch.bfloat16)
+        d = ops.conv_tc_desc(xd, w_f.data_ptr(), out, N, H, H, Ci, H, H, Co, 3, 3, 1, 1, 1, residual=dev(_nhwc(res)), out2=out2,
+                             scale2=dev(sc), shift2=dev(sh))
+        check(lib.combat_conv_tc(C.byref(d), ops._s()), "conv_tc")
+        torch.cuda.synchronize()
+        assert rel(out.permute(0, 3, 1, 2), y) < 2e-5
+        assert rel(out2.float().permute(0, 3, 1, 2), y2) < 6e-3
+        # out2 only
+        out2b = torch.zeros_like(out2)
+        d = ops.conv_tc_desc(xd, w_f.data_ptr(), None, N, H, H, Ci, H, H, Co, 3, 3, 1, 1, 1, residual=dev(_nhwc(res)), out2=out2b,
+                             scale2=dev(sc), shift2=dev(sh))
+        d.res_f32 = 1
+        check(lib.combat_conv_tc(C.byref(d), ops._s()), "conv_tc")
+        torch.cuda.synchronize()
+        assert torch.equal(out2b, out2)
+    # masked backward epilogue on a (possibly stride-2) input-gradient problem
+    s = up
+    Ho = H // s
+    dy = torch.randn(N, Co, Ho, Ho, generator=g).bfloat16().float()
+    xin = x.clone().requires_grad_(True)
+    F.conv2d(xin, w, None, s, 1).backward(dy)
+    mask = (torch.randn(N, Ci, H, H, generator=g) > 0).float() * torch.rand(N, Ci, H, H, generator=g)
+    msc = torch.rand(Ci, generator=g) + 0.5
+    pre = torch.randn(N, Ci, H, H, generator=g).bfloat16().float()
+    post = torch.randn(N, Ci, H, H, generator=g).bfloat16().float()
+    w_d = dev(w.flip(2, 3).permute(1, 2, 3, 0).bfloat16())
+    for use_pre in (True, False):  # the shortcut gradient arrives either before the mask (conv shortcut) or after it (identity)
+        exp = (xin.grad + pre) * (mask > 0).float() * msc[None, :, None, None] if use_pre else \
+            xin.grad * (mask > 0).float() * msc[None, :, None, None] + post
+        dx = torch.empty(N, H, H, Ci, device="cuda", dtype=torch.bfloat16)
+        d2 = ops.conv_tc_desc(dev(_nhwc(dy).bfloat16()), w_d.data_ptr(), dx, N, Ho, Ho, Co, H, H, Ci, 3, 3, 1, 1, s,
+                              residual=dev(_nhwc(pre).bfloat16()) if use_pre else None, mask=dev(_nhwc(mask).bfloat16()),
+                              mask_scale=dev(msc), post_add=None if use_pre else dev(_nhwc(post).bfloat16()))
+        check(lib.combat_conv_tc(C.byref(d2), ops._s()), "conv_tc dgrad")
+        torch.cuda.synchronize()
+        assert rel(dx.float().permute(0, 3, 1, 2), exp) < 6e-3

@@ -227,3 +227,43 @@ def test_frequency_detector_bf16_tensor_core_path(golden):
     ref = torch.from_numpy(g["freq_logits"])
     assert rel2(logits, ref) < 2e-2, rel2(logits, ref)
     assert torch.equal(logits.argmax(1).cpu(), ref.argmax(1))
+
+
+def test_fused_eval_path_equals_unfused():
+    """The eval-mode PreAct path with BatchNorm+ReLU folded into the tcgen05 epilogues computes the same function as
+    the unfused kernels: forward bit-identical (same fp32 accumulators, same rounding points), input gradient equal up
+    to one bf16 rounding that the fused path no longer performs."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from combat_b200 import ops
+    from combat_b200.nets import Classifier
+    from oracle import combat_oracle as O
+    gen = torch.Generator().manual_seed(5)
+    p, b = O.init_preact_resnet18_state(gen)
+    for k in b:
+        if k.endswith("running_mean"):
+            b[k] = torch.randn(b[k].shape, generator=gen) * 0.1
+        elif k.endswith("running_var"):
+            b[k] = torch.rand(b[k].shape, generator=gen) + 0.5
+    net = Classifier("preact_resnet18", 10, 3, 32, device="cuda", dtype=torch.bfloat16)
+    net.load_state_dict({**p, **b})
+    x = (torch.rand(8, 3, 32, 32, generator=gen) * 2 - 1).cuda()
+    t = torch.randint(0, 10, (8,), generator=gen).cuda()
+    outs = []
+    for fuse in (True, False):
+        logits, ctx = net.forward(x, train=False, save=True, fuse=fuse)
+        assert bool(ctx.get("fused")) == fuse
+        _, dl, _ = ops.cross_entropy(logits, t, 1.0, True)
+        dx = net.backward(ctx, dl, need_wgrad=False, need_dx=True)
+        outs.append((logits.clone(), dx.clone()))
+    assert torch.equal(outs[0][0], outs[1][0])
+    e = float((outs[0][1] - outs[1][1]).norm() / outs[1][1].norm())
+    assert e < 2e-2, e
+    # and against the float64 oracle
+    pr = {k: v.double() for k, v in p.items()}
+    br = {k: (v.double() if v.is_floating_point() else v) for k, v in b.items()}
+    xr = x.cpu().double().requires_grad_(True)
+    lo = O.preact_resnet18_forward(pr, br, xr, False)
+    torch.nn.functional.cross_entropy(lo, t.cpu()).backward()
+    assert float((outs[0][0].cpu().double() - lo).norm() / lo.norm()) < 3e-2
+    assert float((outs[0][1].cpu().double() - xr.grad).norm() / xr.grad.norm()) < 1e-1
