@@ -204,23 +204,31 @@ def run_ours(args):
     # ---- roofline leg: per-launch CUDA-event timing of the tcgen05 convolutions in one eager iteration
     roof = None
     if rank == 0:
-        nets.TC_PROFILE = []
         # park the GPU behind a ~150 ms spin so that the host (eager launches through ctypes) runs ahead of it: each
-        # event pair then brackets device time only, not the host-side launch latency of the kernel between them
-        torch.cuda._sleep(int(0.15 * 1.9e9))
-        eng.step(xs_dev[0], ys_host[0], use_graph=False)
-        torch.cuda.synchronize()
-        prof, nets.TC_PROFILE = nets.TC_PROFILE, None
-        tot_ms = sum(s.elapsed_time(e) for _, _, s, e, _ in prof)
-        tot_fl = sum(f for _, f, _, _, _ in prof)
+        # event pair then brackets device time only, not the host-side launch latency of the kernel between them.
+        # Two passes, per-launch minimum: a host hiccup (allocator growth, page fault) in one pass does not pollute it.
+        passes = []
+        for _ in range(2):
+            nets.TC_PROFILE = []
+            torch.cuda._sleep(int(0.15 * 1.9e9))
+            eng.step(xs_dev[0], ys_host[0], use_graph=False)
+            torch.cuda.synchronize()
+            passes.append([(n, f, s.elapsed_time(e), t) for n, f, s, e, t in nets.TC_PROFILE])
+        nets.TC_PROFILE = None
+        if len(passes[0]) == len(passes[1]):
+            prof = [(a[0], a[1], min(a[2], b[2]), a[3]) for a, b in zip(*passes)]
+        else:
+            prof = passes[-1]
+        tot_ms = sum(ms_ for _, _, ms_, _ in prof)
+        tot_fl = sum(f for _, f, _, _ in prof)
         peak_tf, peak_bw, which = peaks()
         by = {}
         layers = {}
-        for name, f, s, e, tag in prof:
+        for name, f, ms_, tag in prof:
             for d, k in ((by, name), (layers, name + " | " + tag)):
                 a = d.setdefault(k, [0.0, 0.0, 0])
                 a[0] += f
-                a[1] += s.elapsed_time(e)
+                a[1] += ms_
                 a[2] += 1
         if args.dump_layers:
             with open(args.dump_layers, "w") as fh:

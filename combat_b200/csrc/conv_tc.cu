@@ -14,11 +14,21 @@
 // Replaces aten::conv2d / convolution_backward (cuDNN) for every conv with Cin % 64 == 0 and Cout % 64 == 0:
 // classifier_models/preact_resnet.py:21-28, resnet.py:18-27, networks/models.py:275-314.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -182,9 +192,203 @@ __device__ __forceinline__ void decode_tile(const TcParams& p, int tile, int& cl
   cls = r / p.tiles_n;
 }
 
-// ---------------------------------------------------------------------------------------------- fwd / dgrad kernel
+// ---------------------------------------------------------------------------------------------- epilogue (shared by all mainloops)
 // MODE 0: out = act(acc + bias)*post_scale+post_shift + residual; out2 = bf16 relu(out*scale2+shift2)
 // MODE 1: out = bf16( mask > 0 ? (acc + residual) * mask_scale : 0 ) + post_add     (residual XOR post_add, both bf16)
+template <int BLOCK_N, int MODE>
+__device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* stg_base, uint32_t tmem_base, uint64_t* tfull_bar,
+                                            uint64_t* tempty_bar, int warp, int lane) {
+  // ===================== epilogue: TMEM -> registers -> shared (transpose) -> coalesced global =====================
+  // 8 warps: warp w owns TMEM lanes [32*(w%4), +32) (hardware rule) and the column half (w-2)/4 of the tile.
+  // tcgen05.ld hands a thread one accumulator ROW (pixel); writing rows straight to NHWC memory makes every store
+  // instruction touch 32 different lines.  Each warp therefore transposes its 32 x 32 chunk through a padded
+  // shared-memory tile and continues in a layout where a warp instruction covers 4 rows x 128 contiguous bytes:
+  // residual / mask / shortcut-gradient loads and all stores are full-line accesses.  Those loads are ISSUED BEFORE
+  // the wait on the accumulator, so their latency hides under the tile's MMAs.
+  const int quarter = warp & 3;
+  const int half = (warp - 2) >> 2;
+  constexpr int NCH = BLOCK_N / 64;  // 32-column chunks per warp
+  const uint32_t stg = smem_u32(stg_base) + (warp - 2) * (32 * EPI_ROWB);  // explicit shared-space address
+  const int sub = lane >> 3;     // row within a group of 4
+  const int cseg = lane & 7;     // 16-byte column segment: columns cseg*4 .. cseg*4+3 of the chunk
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  // per-tile addressing + prefetch of the epilogue inputs, software-pipelined ONE TILE AHEAD: the loads of tile t+1 are
+  // in flight while tile t is transposed, combined and stored
+  struct TileCtx {
+    uint32_t ob[8];           // element offset of (row i, this lane's first channel) in the NHWC output (< 2^32 elements)
+    uint32_t okmask;          // rows inside the tensor
+    int col0;
+    bool has_acc;
+    float4 pr[NCH][8];        // MODE 0: float32 residual | bf16 residual in .x,.y;  MODE 1: mask in .x,.y, addend in .z,.w
+  };
+  auto prepare = [&](int tile, TileCtx& t) {
+    int cls, nt, ht, wt, cot;
+    decode_tile(p, tile, cls, nt, ht, wt, cot);
+    t.has_acc = p.taps.ntaps[cls] > 0;
+    t.col0 = cot * BLOCK_N + half * (BLOCK_N / 2) + cseg * 4;  // this lane's first channel of chunk 0
+    t.okmask = 0;
+    // the 8 rows this lane owns in the coalesced phase: row = quarter*32 + 4*i + sub
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = quarter * 32 + 4 * i + sub;
+      const int wi = row & (p.BW - 1);
+      const int r2 = row >> p.lbw;
+      const int hi = r2 & (p.BH - 1);
+      const int ni = r2 >> p.lbh;
+      const int n = nt * p.BNI + ni, a = ht * p.BH + hi, b = wt * p.BW + wi;
+      const bool valid = n < p.N && a < p.Hc && b < p.Wc;
+      const int oh = a * p.out_scale + p.taps.cls_p[cls], ow = b * p.out_scale + p.taps.cls_q[cls];
+      t.ob[i] = (uint32_t)((((long long)n * p.out_H + oh) * p.out_W + ow) * p.Co + t.col0);
+      t.okmask |= (valid ? 1u : 0u) << i;
+    }
+    // Unconditional loads (rows outside the tensor read element 0 and are discarded at the store): a predicated load
+    // into a zero-initialised register becomes "load to a temporary, wait, move" and serialises the whole batch.
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t o = (t.okmask >> i & 1) ? t.ob[i] + ch * EPI_CH : 0u;
+        if (MODE == 0) {
+          if (p.residual) {
+            if (p.res_f32) t.pr[ch][i] = __ldg((const float4*)((const float*)p.residual + o));
+            else *(uint2*)&t.pr[ch][i].x = __ldg((const uint2*)((const bf16*)p.residual + o));
+          }
+        } else {
+          *(uint2*)&t.pr[ch][i].x = __ldg((const uint2*)(p.mask + o));
+          const bf16* addp = p.residual ? (const bf16*)p.residual : p.post_add;
+          if (addp) *(uint2*)&t.pr[ch][i].z = __ldg((const uint2*)(addp + o));
+        }
+      }
+  };
+  // one tile ahead only where the register file allows it (64-wide tiles: 32 prefetch registers per tile)
+  constexpr bool AHEAD = NCH == 1;
+  TileCtx cur, nxt;
+  if (AHEAD && (int)blockIdx.x < p.total_tiles) prepare(blockIdx.x, cur);
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    const bool more = AHEAD && tile + (int)gridDim.x < p.total_tiles;
+    if (AHEAD) {
+      if (more) prepare(tile + gridDim.x, nxt);
+    } else {
+      prepare(tile, cur);
+    }
+    const bool has_acc = cur.has_acc;
+    const int col0 = cur.col0;
+    const uint32_t okmask = cur.okmask;
+    uint32_t (&ob)[8] = cur.ob;
+    float4 (&pr)[NCH][8] = cur.pr;
+    if (has_acc) {
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+    }
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + half * (BLOCK_N / 2);
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      const int c0 = ch * EPI_CH;
+      const int colg = col0 + c0;
+      float4 f[8];
+      if (has_acc) {
+        uint32_t v[32];
+        tmem_ld16(taddr + c0, *(uint32_t(*)[16])&v[0]);
+        tmem_ld16(taddr + c0 + 16, *(uint32_t(*)[16])&v[16]);
+        tmem_ld_wait();
+        const uint32_t wr = stg + lane * EPI_ROWB;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sts128(wr + j * 16, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = lds128(stg + (4 * i + sub) * EPI_ROWB + cseg * 16);
+        __syncwarp();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (MODE == 0) {
+        if (p.bias) {
+          const float4 bb = *(const float4*)(p.bias + colg);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { f[i].x += bb.x; f[i].y += bb.y; f[i].z += bb.z; f[i].w += bb.w; }
+        }
+        if (p.act == 2) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            f[i].x = f[i].x > 0.f ? f[i].x : expm1f(f[i].x); f[i].y = f[i].y > 0.f ? f[i].y : expm1f(f[i].y);
+            f[i].z = f[i].z > 0.f ? f[i].z : expm1f(f[i].z); f[i].w = f[i].w > 0.f ? f[i].w : expm1f(f[i].w);
+          }
+        }
+        if (p.post_scale) {
+          const float4 ss = *(const float4*)(p.post_scale + colg), hh = *(const float4*)(p.post_shift + colg);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            f[i].x = fmaf(f[i].x, ss.x, hh.x); f[i].y = fmaf(f[i].y, ss.y, hh.y);
+            f[i].z = fmaf(f[i].z, ss.z, hh.z); f[i].w = fmaf(f[i].w, ss.w, hh.w);
+          }
+        }
+        if (p.residual) {
+          if (p.res_f32) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { f[i].x += pr[ch][i].x; f[i].y += pr[ch][i].y; f[i].z += pr[ch][i].z; f[i].w += pr[ch][i].w; }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint32_t u0 = __float_as_uint(pr[ch][i].x), u1 = __float_as_uint(pr[ch][i].y);
+              const float2 r0 = __bfloat1622float2(*(const __nv_bfloat162*)&u0), r1 = __bfloat1622float2(*(const __nv_bfloat162*)&u1);
+              f[i].x += r0.x; f[i].y += r0.y; f[i].z += r1.x; f[i].w += r1.y;
+            }
+          }
+        }
+      } else {
+        const float4 ms = *(const float4*)(p.mask_scale + colg);
+        const bool pre_add = p.residual != nullptr;
+        const bool any_add = pre_add || p.post_add != nullptr;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t m0u = __float_as_uint(pr[ch][i].x), m1u = __float_as_uint(pr[ch][i].y);
+          const uint32_t a0u = any_add ? __float_as_uint(pr[ch][i].z) : 0u, a1u = any_add ? __float_as_uint(pr[ch][i].w) : 0u;
+          const float2 m0 = __bfloat1622float2(*(const __nv_bfloat162*)&m0u), m1 = __bfloat1622float2(*(const __nv_bfloat162*)&m1u);
+          const float2 a0 = __bfloat1622float2(*(const __nv_bfloat162*)&a0u), a1 = __bfloat1622float2(*(const __nv_bfloat162*)&a1u);
+          if (pre_add) { f[i].x += a0.x; f[i].y += a0.y; f[i].z += a1.x; f[i].w += a1.y; }
+          f[i].x = m0.x > 0.f ? f[i].x * ms.x : 0.f; f[i].y = m0.y > 0.f ? f[i].y * ms.y : 0.f;
+          f[i].z = m1.x > 0.f ? f[i].z * ms.z : 0.f; f[i].w = m1.y > 0.f ? f[i].w * ms.w : 0.f;
+          if (!pre_add) { f[i].x += a0.x; f[i].y += a0.y; f[i].z += a1.x; f[i].w += a1.y; }
+        }
+      }
+      if (p.out) {
+        if (p.out_f32) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (okmask >> i & 1) *(float4*)((float*)p.out + ob[i] + c0) = f[i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (okmask >> i & 1) {
+              const __nv_bfloat162 h0 = __floats2bfloat162_rn(f[i].x, f[i].y), h1 = __floats2bfloat162_rn(f[i].z, f[i].w);
+              *(uint2*)((bf16*)p.out + ob[i] + c0) = make_uint2(*(const uint32_t*)&h0, *(const uint32_t*)&h1);
+            }
+        }
+      }
+      if (MODE == 0 && p.out2) {
+        const float4 ss = *(const float4*)(p.scale2 + colg), hh = *(const float4*)(p.shift2 + colg);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (okmask >> i & 1) {
+            const __nv_bfloat162 h0 = __floats2bfloat162_rn(fmaxf(fmaf(f[i].x, ss.x, hh.x), 0.f), fmaxf(fmaf(f[i].y, ss.y, hh.y), 0.f));
+            const __nv_bfloat162 h1 = __floats2bfloat162_rn(fmaxf(fmaf(f[i].z, ss.z, hh.z), 0.f), fmaxf(fmaf(f[i].w, ss.w, hh.w), 0.f));
+            *(uint2*)((bf16*)p.out2 + ob[i] + c0) = make_uint2(*(const uint32_t*)&h0, *(const uint32_t*)&h1);
+          }
+      }
+    }
+    if (has_acc) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (more) cur = nxt;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- fwd / dgrad kernel
 template <int BLOCK_N, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   using Cfg = TcCfg<BLOCK_N>;
@@ -281,184 +485,125 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       }
     }
   } else {
-    // ===================== epilogue: TMEM -> registers -> shared (transpose) -> coalesced global =====================
-    // 8 warps: warp w owns TMEM lanes [32*(w%4), +32) (hardware rule) and the column half (w-2)/4 of the tile.
-    // tcgen05.ld hands a thread one accumulator ROW (pixel); writing rows straight to NHWC memory makes every store
-    // instruction touch 32 different lines.  Each warp therefore transposes its 32 x 32 chunk through a padded
-    // shared-memory tile and continues in a layout where a warp instruction covers 4 rows x 128 contiguous bytes:
-    // residual / mask / shortcut-gradient loads and all stores are full-line accesses.  Those loads are ISSUED BEFORE
-    // the wait on the accumulator, so their latency hides under the tile's MMAs.
-    const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
-    constexpr int NCH = BLOCK_N / 64;  // 32-column chunks per warp
-    uint8_t* stg = smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256 + (warp - 2) * (32 * EPI_ROWB);
-    const int sub = lane >> 3;     // row within a group of 4
-    const int cseg = lane & 7;     // 16-byte column segment: columns cseg*4 .. cseg*4+3 of the chunk
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      int cls, nt, ht, wt, cot;
-      decode_tile(p, tile, cls, nt, ht, wt, cot);
-      const bool has_acc = p.taps.ntaps[cls] > 0;
-      const int col0 = cot * BLOCK_N + half * (BLOCK_N / 2) + cseg * 4;  // this lane's first channel of chunk 0
-      // the 8 rows this lane owns in the coalesced phase: row = quarter*32 + 4*i + sub
-      long long ob[8];
-      uint32_t okmask = 0;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = quarter * 32 + 4 * i + sub;
-        const int wi = row & (p.BW - 1);
-        const int r2 = row >> p.lbw;
-        const int hi = r2 & (p.BH - 1);
-        const int ni = r2 >> p.lbh;
-        const int n = nt * p.BNI + ni, a = ht * p.BH + hi, b = wt * p.BW + wi;
-        const bool valid = n < p.N && a < p.Hc && b < p.Wc;
-        const int oh = a * p.out_scale + p.taps.cls_p[cls], ow = b * p.out_scale + p.taps.cls_q[cls];
-        ob[i] = (((long long)n * p.out_H + oh) * p.out_W + ow) * p.Co + col0;
-        okmask |= (valid ? 1u : 0u) << i;
-      }
-      // ---- prefetch the epilogue inputs of this tile
-      float4 pr[NCH][8];  // MODE 0: float32 residual | bf16 residual in .x,.y;  MODE 1: mask in .x,.y, addend in .z,.w
-#pragma unroll
-      for (int ch = 0; ch < NCH; ++ch)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          pr[ch][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (okmask >> i & 1) {
-            const long long o = ob[i] + ch * EPI_CH;
-            if (MODE == 0) {
-              if (p.residual) {
-                if (p.res_f32) {
-                  pr[ch][i] = *(const float4*)((const float*)p.residual + o);
-                } else {
-                  const uint2 rr = *(const uint2*)((const bf16*)p.residual + o);
-                  pr[ch][i].x = __uint_as_float(rr.x); pr[ch][i].y = __uint_as_float(rr.y);
-                }
-              }
-            } else {
-              const uint2 mm = *(const uint2*)(p.mask + o);
-              pr[ch][i].x = __uint_as_float(mm.x); pr[ch][i].y = __uint_as_float(mm.y);
-              const bf16* addp = p.residual ? (const bf16*)p.residual : p.post_add;
-              if (addp) {
-                const uint2 aa = *(const uint2*)(addp + o);
-                pr[ch][i].z = __uint_as_float(aa.x); pr[ch][i].w = __uint_as_float(aa.y);
-              }
-            }
-          }
-        }
-      if (has_acc) {
-        mbar_wait(&tfull_bar[acc], acc_phase);
-        tc_fence_after();
-      }
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + half * (BLOCK_N / 2);
-#pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) {
-        const int c0 = ch * EPI_CH;
-        const int colg = col0 + c0;
-        float4 f[8];
-        if (has_acc) {
-          uint32_t v[32];
-          tmem_ld16(taddr + c0, *(uint32_t(*)[16])&v[0]);
-          tmem_ld16(taddr + c0 + 16, *(uint32_t(*)[16])&v[16]);
-          tmem_ld_wait();
-          uint8_t* wr = stg + lane * EPI_ROWB;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) *(uint4*)(wr + j * 16) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] = *(const float4*)(stg + (4 * i + sub) * EPI_ROWB + cseg * 16);
-          __syncwarp();
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        if (MODE == 0) {
-          if (p.bias) {
-            const float4 bb = *(const float4*)(p.bias + colg);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { f[i].x += bb.x; f[i].y += bb.y; f[i].z += bb.z; f[i].w += bb.w; }
-          }
-          if (p.act == 2) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              f[i].x = f[i].x > 0.f ? f[i].x : expm1f(f[i].x); f[i].y = f[i].y > 0.f ? f[i].y : expm1f(f[i].y);
-              f[i].z = f[i].z > 0.f ? f[i].z : expm1f(f[i].z); f[i].w = f[i].w > 0.f ? f[i].w : expm1f(f[i].w);
-            }
-          }
-          if (p.post_scale) {
-            const float4 ss = *(const float4*)(p.post_scale + colg), hh = *(const float4*)(p.post_shift + colg);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              f[i].x = fmaf(f[i].x, ss.x, hh.x); f[i].y = fmaf(f[i].y, ss.y, hh.y);
-              f[i].z = fmaf(f[i].z, ss.z, hh.z); f[i].w = fmaf(f[i].w, ss.w, hh.w);
-            }
-          }
-          if (p.residual) {
-            if (p.res_f32) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) { f[i].x += pr[ch][i].x; f[i].y += pr[ch][i].y; f[i].z += pr[ch][i].z; f[i].w += pr[ch][i].w; }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const uint32_t u0 = __float_as_uint(pr[ch][i].x), u1 = __float_as_uint(pr[ch][i].y);
-                const float2 r0 = __bfloat1622float2(*(const __nv_bfloat162*)&u0), r1 = __bfloat1622float2(*(const __nv_bfloat162*)&u1);
-                f[i].x += r0.x; f[i].y += r0.y; f[i].z += r1.x; f[i].w += r1.y;
-              }
-            }
-          }
-        } else {
-          const float4 ms = *(const float4*)(p.mask_scale + colg);
-          const bool pre_add = p.residual != nullptr;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const uint32_t m0u = __float_as_uint(pr[ch][i].x), m1u = __float_as_uint(pr[ch][i].y);
-            const uint32_t a0u = __float_as_uint(pr[ch][i].z), a1u = __float_as_uint(pr[ch][i].w);
-            const float2 m0 = __bfloat1622float2(*(const __nv_bfloat162*)&m0u), m1 = __bfloat1622float2(*(const __nv_bfloat162*)&m1u);
-            const float2 a0 = __bfloat1622float2(*(const __nv_bfloat162*)&a0u), a1 = __bfloat1622float2(*(const __nv_bfloat162*)&a1u);
-            if (pre_add) { f[i].x += a0.x; f[i].y += a0.y; f[i].z += a1.x; f[i].w += a1.y; }
-            f[i].x = m0.x > 0.f ? f[i].x * ms.x : 0.f; f[i].y = m0.y > 0.f ? f[i].y * ms.y : 0.f;
-            f[i].z = m1.x > 0.f ? f[i].z * ms.z : 0.f; f[i].w = m1.y > 0.f ? f[i].w * ms.w : 0.f;
-            if (!pre_add) { f[i].x += a0.x; f[i].y += a0.y; f[i].z += a1.x; f[i].w += a1.y; }
-          }
-        }
-        if (p.out) {
-          if (p.out_f32) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (okmask >> i & 1) *(float4*)((float*)p.out + ob[i] + c0) = f[i];
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (okmask >> i & 1) {
-                const __nv_bfloat162 h0 = __floats2bfloat162_rn(f[i].x, f[i].y), h1 = __floats2bfloat162_rn(f[i].z, f[i].w);
-                *(uint2*)((bf16*)p.out + ob[i] + c0) = make_uint2(*(const uint32_t*)&h0, *(const uint32_t*)&h1);
-              }
-          }
-        }
-        if (MODE == 0 && p.out2) {
-          const float4 ss = *(const float4*)(p.scale2 + colg), hh = *(const float4*)(p.shift2 + colg);
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (okmask >> i & 1) {
-              const __nv_bfloat162 h0 = __floats2bfloat162_rn(fmaxf(fmaf(f[i].x, ss.x, hh.x), 0.f), fmaxf(fmaf(f[i].y, ss.y, hh.y), 0.f));
-              const __nv_bfloat162 h1 = __floats2bfloat162_rn(fmaxf(fmaf(f[i].z, ss.z, hh.z), 0.f), fmaxf(fmaf(f[i].w, ss.w, hh.w), 0.f));
-              *(uint2*)((bf16*)p.out2 + ob[i] + c0) = make_uint2(*(const uint32_t*)&h0, *(const uint32_t*)&h1);
-            }
-        }
-      }
-      if (has_acc) {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      }
-    }
+    tc_epilogue<BLOCK_N, MODE>(p, smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256, tmem_base, tfull_bar, tempty_bar, warp, lane);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- 64 -> 64 channels, 3x3, stride 1
+// The widest feature maps (32x32x64: PreAct layer1, the generator's outer convs) are bound by the L2 -> shared-memory
+// operand stream of the generic kernel above, which reloads every input pixel once per filter tap and the whole filter
+// once per tile (216 KB per 128-pixel tile).  Here
+//   * all 9 taps of the 64x64 filter (72 KB) stay resident in shared memory for the lifetime of the CTA;
+//   * a tile is BH full-width image rows; for each horizontal tap offset dw one TMA box of BH+2 rows is loaded, and the
+//     three vertical taps read it at row offsets 0, W, 2W (whole 1024-byte swizzle atoms, so the shared-memory
+//     descriptors stay aligned): 3 loads of (BH+2)*W pixels instead of 9 loads of BH*W -- 72 KB per tile.
+struct Tc64Cfg {
+  static constexpr int W_BYTES = 9 * 64 * KCHUNK * 2;  // 72 KB resident filter
+  static constexpr int STAGES = 4;  // upper bound; the launch picks how many fit (n_stages)
+  static constexpr int SMEM_BYTES_FIXED = W_BYTES + 1024 /*align*/ + 256 /*barriers*/ + TC_EPI_WARPS * 32 * EPI_ROWB;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc64_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
+                                                                  const int stage_bytes, const int n_stages) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* wsm = smem;                               // [9 taps][64 co][64 ci] bf16, SWIZZLE_128B
+  uint8_t* stages = smem + Tc64Cfg::W_BYTES;         // STAGES x stage_bytes ((BH+2)*BW pixels x 128 B, 1024-aligned)
+  uint8_t* tail = stages + n_stages * stage_bytes;
+  uint64_t* bars = (uint64_t*)tail;
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Tc64Cfg::STAGES;
+  uint64_t* tfull_bar = bars + 2 * Tc64Cfg::STAGES;
+  uint64_t* tempty_bar = bars + 2 * Tc64Cfg::STAGES + 2;
+  uint64_t* w_bar = bars + 2 * Tc64Cfg::STAGES + 4;
+  uint32_t* tmem_ptr_smem = (uint32_t*)(bars + 2 * Tc64Cfg::STAGES + 5);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.w);
+    tma_prefetch_desc(&maps.in[0]);
+    for (int s = 0; s < Tc64Cfg::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], TC_EPI_WARPS);
+    }
+    mbar_init(w_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_smem, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(w_bar, Tc64Cfg::W_BYTES);
+      for (int t = 0; t < 9; ++t) tma_load_3d(wsm + t * 8192, &maps.w, w_bar, 0, t, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int cls, nt, ht, wt, cot;
+        decode_tile(p, tile, cls, nt, ht, wt, cot);
+        for (int dw = -1; dw <= 1; ++dw) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], stage_bytes);
+          tma_load_4d(stages + stage * stage_bytes, &maps.in[0], &full_bar[stage], 0, dw, ht * p.BH - 1, nt);
+          if (++stage == n_stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(TILE_M, 64, 0, 0);
+      mbar_wait(w_bar, 0);
+      tc_fence_after();
+      const uint32_t wbase = smem_u32(wsm);
+      const uint32_t row_step = (uint32_t)p.BW * 128;  // one image row of the staged box
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 64;
+        for (int dwi = 0; dwi < 3; ++dwi) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stages + stage * stage_bytes);
+#pragma unroll
+          for (int dhi = 0; dhi < 3; ++dhi) {
+            const uint64_t adesc = make_smem_desc(sa + dhi * row_step, 16, 1024);
+            const uint64_t bdesc = make_smem_desc(wbase + (dhi * 3 + dwi) * 8192, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < KCHUNK / 16; ++k) umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (dwi | dhi | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == n_stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    tc_epilogue<64, MODE>(p, tail + 256, tmem_base, tfull_bar, tempty_bar, warp, lane);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 128);
   }
 }
 
@@ -482,7 +627,7 @@ static PFN_encodeTiled get_encode() {
 
 // NHWC bf16 activation (possibly a parity view): dims (C, W, H, N), element strides given for w/h/n
 static int make_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, long long sw, long long sh, long long sn,
-                        int BW, int BH, int BNI) {
+                        int BW, int BH, int BNI) {  // BH: rows of the box (BH+2 for the row-reuse kernel)
   PFN_encodeTiled enc = get_encode();
   if (!enc) return -1;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
@@ -549,6 +694,7 @@ static int num_sms() {
 extern "C" int combat_conv_tc(const combat_conv_tc_desc* d, void* stream) {
   COMBAT_ARG(d && d->in && d->w && (d->out || d->out2), 0);
   COMBAT_ARG(combat_conv_tc_supported(d), 0);
+  COMBAT_ARG((long long)d->N * d->Ho * d->Wo * d->Co < (1LL << 32), 0);  // 32-bit element offsets in the epilogue
   COMBAT_ARG(!d->out2 || (d->scale2 && d->shift2), 0);
   COMBAT_ARG(!d->mask || d->mask_scale, 0);
   // masked (backward) epilogue: bf16 in/out, at most one addend, no forward-only features
@@ -651,6 +797,17 @@ extern "C" int combat_conv_tc(const combat_conv_tc_desc* d, void* stream) {
   }
   rc = make_w_map(&maps.w, d->w, d->Ci, KH * KW, d->Co, BLOCK_N);
   if (rc) return rc;
+  // 64 -> 64, 3x3, stride 1, tiles of whole image rows (8 | W so that a row is a whole number of swizzle atoms)
+  const int stage_bytes64 = (p.BH + 2) * p.BW * 128;
+  int n_stages64 = (232448 - Tc64Cfg::SMEM_BYTES_FIXED) / stage_bytes64;
+  if (n_stages64 > Tc64Cfg::STAGES) n_stages64 = Tc64Cfg::STAGES;
+  const bool use64 = d->Ci == 64 && d->Co == 64 && KH == 3 && pad == 1 && d->stride == 1 && d->up == 1 && p.BW == d->Wo &&
+                     p.BNI == 1 && (p.BW % 8) == 0 && n_stages64 >= 2 && !getenv("COMBAT_NO_TC64");
+  if (use64) {
+    const long long C = d->Ci, W = d->Wi, H = d->Hi;
+    rc = make_act_map(&maps.in[0], d->in, d->Ci, d->Wi, d->Hi, d->N, C, W * C, H * W * C, p.BW, p.BH + 2, 1);
+    if (rc) return rc;
+  }
   p.lbw = 0;
   while ((1 << p.lbw) < p.BW) ++p.lbw;
   p.lbh = 0;
@@ -667,6 +824,17 @@ extern "C" int combat_conv_tc(const combat_conv_tc_desc* d, void* stream) {
     conv_tc_kernel<BN, MD><<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st>>>(maps, p);                                     \
   }
   const int mode = d->mask ? 1 : 0;
+  if (use64) {
+    const int smem_bytes = Tc64Cfg::SMEM_BYTES_FIXED + n_stages64 * stage_bytes64;
+    if (mode) {
+      cudaFuncSetAttribute(conv_tc64_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+      conv_tc64_kernel<1><<<grid, TC_THREADS, smem_bytes, st>>>(maps, p, stage_bytes64, n_stages64);
+    } else {
+      cudaFuncSetAttribute(conv_tc64_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+      conv_tc64_kernel<0><<<grid, TC_THREADS, smem_bytes, st>>>(maps, p, stage_bytes64, n_stages64);
+    }
+    COMBAT_RETURN_LAUNCH("conv_tc64");
+  }
   if (BLOCK_N == 128) { if (mode) LAUNCH_C(128, 1) else LAUNCH_C(128, 0) }
   else { if (mode) LAUNCH_C(64, 1) else LAUNCH_C(64, 0) }
 #undef LAUNCH_C

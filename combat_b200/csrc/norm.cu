@@ -66,25 +66,35 @@ __global__ void __launch_bounds__(256) bn_stats_k(const T* __restrict__ x, long 
   }
 }
 
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// one WARP per channel: lanes stride over the partial blocks (double accumulation), shuffle reduction
 __global__ void bn_finalize_k(const float* __restrict__ partial, int nblk, long long R, int C,
                               const float* __restrict__ gamma, const float* __restrict__ beta, float* running_mean,
                               float* running_var, float momentum, float eps, float* __restrict__ scale,
                               float* __restrict__ shift, float* save_mean, float* save_invstd) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (c >= C) return;
   float mean, invstd;
   if (nblk > 0) {
     double s = 0.0, ss = 0.0;
-    for (int b = 0; b < nblk; ++b) {
+    for (int b = lane; b < nblk; b += 32) {
       s += (double)partial[((long long)b * 2) * C + c];
       ss += (double)partial[((long long)b * 2 + 1) * C + c];
     }
+    s = warp_sum_d(s);
+    ss = warp_sum_d(ss);
     double m = s / (double)R;
     double var = ss / (double)R - m * m;
     if (var < 0.0) var = 0.0;
     mean = (float)m;
     invstd = (float)(1.0 / sqrt(var + (double)eps));
-    if (running_mean) {
+    if (running_mean && lane == 0) {
       running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
       double unb = R > 1 ? var * (double)R / (double)(R - 1) : var;
       running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
@@ -93,6 +103,7 @@ __global__ void bn_finalize_k(const float* __restrict__ partial, int nblk, long 
     mean = running_mean[c];
     invstd = 1.0f / sqrtf(running_var[c] + eps);
   }
+  if (lane != 0) return;
   const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
   const float sc = g * invstd;
   scale[c] = sc;
@@ -155,15 +166,20 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_k(const T* __restrict__ dy,
 
 __global__ void bn_bwd_finalize_k(const float* __restrict__ partial, int nblk, int C, float* __restrict__ dgamma,
                                   float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per channel
+  const int lane = threadIdx.x & 31;
   if (c >= C) return;
   double s = 0.0, sx = 0.0;
-  for (int b = 0; b < nblk; ++b) {
+  for (int b = lane; b < nblk; b += 32) {
     s += (double)partial[((long long)b * 2) * C + c];
     sx += (double)partial[((long long)b * 2 + 1) * C + c];
   }
-  dbeta[c] = (float)s;
-  dgamma[c] = (float)sx;
+  s = warp_sum_d(s);
+  sx = warp_sum_d(sx);
+  if (lane == 0) {
+    dbeta[c] = (float)s;
+    dgamma[c] = (float)sx;
+  }
 }
 
 template <typename TX, typename T>
@@ -245,7 +261,7 @@ extern "C" int combat_bn_finalize(const float* partial, int nblk, long long R, i
                                   float* shift, float* save_mean, float* save_invstd, void* stream) {
   COMBAT_ARG(scale && shift, 10);
   COMBAT_ARG(nblk > 0 ? partial != nullptr : (running_mean && running_var), 0);
-  bn_finalize_k<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(partial, nblk, R, C, gamma, beta, running_mean, running_var,
+  bn_finalize_k<<<cdiv(C, 8), 256, 0, (cudaStream_t)stream>>>(partial, nblk, R, C, gamma, beta, running_mean, running_var,
                                                                 momentum, eps, scale, shift, save_mean, save_invstd);
   COMBAT_RETURN_LAUNCH("bn_finalize");
 }
@@ -298,7 +314,7 @@ extern "C" int combat_bn_bwd_reduce(const void* dy, const void* x, int x_dtype, 
 
 extern "C" int combat_bn_bwd_finalize(const float* partial, int nblk, int C, float* dgamma, float* dbeta, void* stream) {
   COMBAT_ARG(partial && dgamma && dbeta && nblk > 0, 0);
-  bn_bwd_finalize_k<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(partial, nblk, C, dgamma, dbeta);
+  bn_bwd_finalize_k<<<cdiv(C, 8), 256, 0, (cudaStream_t)stream>>>(partial, nblk, C, dgamma, dbeta);
   COMBAT_RETURN_LAUNCH("bn_bwd_finalize");
 }
 

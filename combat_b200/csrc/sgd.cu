@@ -46,26 +46,45 @@ extern "C" int combat_sgd_nesterov(float* p, const float* g, float* buf, long lo
   COMBAT_RETURN_LAUNCH("sgd_nesterov");
 }
 
-// grid.y = descriptor, grid.x strides over the layer's elements (dst-major so that writes coalesce)
+// grid.y = descriptor, grid.x strides over 32x32 (co, ci) tiles of every filter tap.  The forward copy is a cast of the
+// channels-last master; the input-gradient copy is its (co <-> ci) transpose with the taps reversed, staged through a
+// padded shared-memory tile so that both the reads (along ci) and the writes (along co) are coalesced.
 template <typename T>
 __global__ void __launch_bounds__(256) prep_weights_k(const float* __restrict__ params, T* __restrict__ wbuf,
                                                       const combat_wprep_desc* __restrict__ table) {
+  __shared__ float tile[32][33];
   const combat_wprep_desc d = table[blockIdx.y];
   const int KK = d.KH * d.KW;
-  const long long total = (long long)d.Cout * d.Cin * KK;
+  const int tco = (d.Cout + 31) / 32, tci = (d.Cin + 31) / 32;
+  const int ntiles = KK * tco * tci;
   const float* src = params + d.src_off;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    // master and fwd layout are both channels-last [co][kk][ci]: the forward copy is a pure cast
-    int ci = (int)(e % d.Cin);
-    long long r = e / d.Cin;
-    int kk = (int)(r % KK);
-    int co = (int)(r / KK);
-    float v = src[e];
-    wbuf[d.fwd_off + e] = from_f<T>(v);
-    if (d.dgrad_off >= 0) {
-      // dgrad layout [ci][KK-1-kk][co]
-      wbuf[d.dgrad_off + ((long long)ci * KK + (KK - 1 - kk)) * d.Cout + co] = from_f<T>(v);
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int ci0 = (t % tci) * 32;
+    const int r = t / tci;
+    const int co0 = (r % tco) * 32;
+    const int kk = r / tco;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = co0 + ty + 8 * j, ci = ci0 + tx;
+      float v = 0.f;
+      if (co < d.Cout && ci < d.Cin) {
+        const long long e = ((long long)co * KK + kk) * d.Cin + ci;
+        v = src[e];
+        wbuf[d.fwd_off + e] = from_f<T>(v);
+      }
+      tile[ty + 8 * j][tx] = v;
     }
+    __syncthreads();
+    if (d.dgrad_off >= 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int ci = ci0 + ty + 8 * j, co = co0 + tx;
+        if (co < d.Cout && ci < d.Cin)  // dgrad layout [ci][KK-1-kk][co]
+          wbuf[d.dgrad_off + ((long long)ci * KK + (KK - 1 - kk)) * d.Cout + co] = from_f<T>(tile[tx][ty + 8 * j]);
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -73,8 +92,8 @@ extern "C" int combat_prep_weights(const float* params, void* wbuf, int dtype, c
                                    int n_desc, long long max_elems, void* stream) {
   COMBAT_ARG(params && wbuf && table_dev, 0);
   if (n_desc <= 0) return 0;
-  int gx = (int)((max_elems + 255) / 256);
-  if (gx > 64) gx = 64;
+  int gx = (int)((max_elems + 1023) / 1024);  // one 32x32 tile per block iteration
+  if (gx > 96) gx = 96;
   if (gx < 1) gx = 1;
   dim3 grid(gx, n_desc);
   DISPATCH_DTYPE(dtype, prep_weights_k<T><<<grid, 256, 0, (cudaStream_t)stream>>>(params, (T*)wbuf, table_dev);)

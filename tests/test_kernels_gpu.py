@@ -224,6 +224,9 @@ TC_CASES = [
     (40, 512, 512, 2, 3, 1, 1),   # UNet bottleneck 2x2: tile spans 32 images, ragged last tile
     (3, 128, 64, 16, 3, 1, 1),    # ragged batch (3 images of 256 pixels -> 6 tiles)
     (2, 64, 64, 28, 3, 1, 1),     # non power-of-two plane (masked tile columns)
+    (5, 64, 64, 16, 3, 1, 1),     # resident-filter / row-reuse kernel, tile = 8 rows of 16
+    (300, 64, 64, 32, 3, 1, 1),   # same kernel, more tiles than SMs (persistent loop, pipeline wrap-around)
+    (2, 64, 64, 24, 3, 1, 1),     # 8 | W but H not a multiple of the tile height
 ]
 
 
