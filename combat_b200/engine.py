@@ -184,50 +184,44 @@ class AlternatedStep:
         b["num_bd"].copy_(b["h_nbd"], non_blocking=True)
 
     # ------------------------------------------------------------ the step
-    def _launch(self, b, keep_debug=False):
-        from ._lib import launch_count
-        n0 = launch_count()
-        try:
-            return self._launch_impl(b, keep_debug)
-        finally:
-            self.launches_per_step = launch_count() - n0
-
-    def _launch_impl(self, b, keep_debug=False):
+    # The iteration is three launch phases separated by the data-parallel exchange points (combat_b200.parallel):
+    #   A: generator forward, C-step forward + backward            -> mean of netC gradients and BatchNorm buffers
+    #   B: netC SGD, metric forwards, G-step forward + backward     -> mean of netG gradients
+    #   C: netG SGD, frequency-detector metric leg
+    # Single GPU: one CUDA graph over A+B+C.  Data parallel: one graph per phase, the NCCL all-reduces are issued between
+    # the replays on the same stream (no collective inside a captured graph).
+    def _phase_a(self, b, st):
         o = self.opt
-        x, y = b["x"], b["y"]
-        B = b["B"]
+        x = b["x"]
         losses, counts = b["losses"], b["counts"]
-        dbg = {} if keep_debug else None
-        numel = x.numel()
-
-        # generator forward, once (train_generator.py:189 and :223)
-        noise_raw, ctxG = self.netG.forward(x, b.get("labels_g"), save=True)
+        noise_raw, ctxG = self.netG.forward(x, b.get("labels_g"), save=True)                 # :189 and :223, once
         noise = ops.plane_op(noise_raw, "lowfreq", keep=self.keep)                          # :190-191 / :224
-
-        # ---------------- C-step (:176-212)
         total_x = ops.poison_blend_fwd(x, noise, b["perm"], 0, o.noise_rate, None, taps_dev=b["taps_c"],
                                        num_bd_dev=b["num_bd"])                                # :192-195
         logits_c, ctxC = self.netC.forward(total_x, train=True, save=True)                   # :205
         _, dlog, _ = ops.cross_entropy(logits_c, b["total_y"], 1.0, True, loss_out=losses[0:1], counts_out=counts[0:2])
         self.netC.zero_grad()                                                                # :179
         self.netC.backward(ctxC, dlog, need_wgrad=True, need_dx=False)                       # :211
-        if self.grad_hook is not None:
-            self.grad_hook("netC", self.netC.store.grad)
+        st.update(noise_raw=noise_raw, ctxG=ctxG, noise=noise, total_x=total_x, logits_c=logits_c)
+
+    def _phase_b(self, b, st):
+        o = self.opt
+        x, y, B = b["x"], b["y"], b["B"]
+        losses, counts = b["losses"], b["counts"]
+        noise = st["noise"]
+        numel = x.numel()
         self.netC.sgd_step(self.lr_C)                                                        # :212
-        if self.buf_hook is not None:
-            self.buf_hook(self.netC.bufs)
-        del ctxC
         if self.with_metrics:
             clean_preds, _ = self.clean.forward(x, train=False, save=False)                  # :214
             ops.cross_entropy(clean_preds, y, 1.0, False, loss_out=losses[4:5], counts_out=counts[2:4])
-
-        # ---------------- G-step (:217-255)
+            st["clean_preds"] = clean_preds
         x_bd = ops.poison_blend_fwd(x, noise, None, B, o.noise_rate, None, sq_partial=b["sq_partial"],
                                     taps_dev=b["taps_g"])                                     # :225-226
         ops.sum_scale(b["sq_partial"], 1.0 / numel, out=losses[2:3])                         # :234
         if self.with_metrics:
             pred_clean, _ = self.netC.forward(x, train=False, save=False)                    # :227
             ops.cross_entropy(pred_clean, y, 1.0, False, loss_out=losses[5:6], counts_out=counts[4:6])
+            st["pred_clean"] = pred_clean
         pred_bd, ctxB = self.netC.forward(x_bd, train=False, save=True)                      # :228
         _, dl1, _ = ops.cross_entropy(pred_bd, b["bd_targets"], 1.0, True, loss_out=losses[1:2], counts_out=counts[6:8])
         g1 = self.netC.backward(ctxB, dl1, need_wgrad=False, need_dx=True)
@@ -241,22 +235,45 @@ class AlternatedStep:
                                       taps_dev=b["taps_g"])
         dnoise_raw = ops.plane_op(dnoise, "lowfreq", keep=self.keep)                          # P is symmetric
         self.netG.zero_grad()                                                                # :220
-        self.netG.backward(ctxG, dnoise_raw)                                                 # :254
-        if self.grad_hook is not None:
-            self.grad_hook("netG", self.netG.store.grad)
+        self.netG.backward(st.pop("ctxG"), dnoise_raw)                                       # :254
+        st.update(x_bd=x_bd, pred_bd=pred_bd, clean_model_preds=cm_preds, g1=g1, g2=g2, dnoise=dnoise)
+
+    def _phase_c(self, b, st):
+        losses, counts = b["losses"], b["counts"]
         self.netG.sgd_step(self.lr_G)                                                        # :255
         if self.with_metrics and self.netF is not None:
-            inputs_F = ops.plane_op(x_bd, "dct", in_mode=2)                                   # :245
+            inputs_F = ops.plane_op(st["x_bd"], "dct", in_mode=2)                             # :245
             pred_F = self.netF.forward(inputs_F)                                              # :247
             ops.cross_entropy(pred_F, b["ones"], 1.0, False, loss_out=losses[6:7], counts_out=counts[10:12])
-            if dbg is not None:
-                dbg.update(inputs_F=inputs_F, pred_F=pred_F)
-        if dbg is not None:
-            dbg.update(noise_raw=noise_raw, noise=noise, total_x=total_x, logits_c=logits_c, x_bd=x_bd, pred_bd=pred_bd,
-                       clean_model_preds=cm_preds, g1=g1, g2=g2, dnoise=dnoise)
-            if self.with_metrics:
-                dbg.update(clean_preds=clean_preds, pred_clean=pred_clean)
-        return dbg
+            st.update(inputs_F=inputs_F, pred_F=pred_F)
+
+    def _exchange_c(self):
+        if self.grad_hook is not None:
+            self.grad_hook("netC", self.netC.store.grad)
+        if self.buf_hook is not None:
+            self.buf_hook(self.netC.bufs)
+
+    def _exchange_g(self):
+        if self.grad_hook is not None:
+            self.grad_hook("netG", self.netG.store.grad)
+
+    @property
+    def _parallel(self):
+        return self.grad_hook is not None or self.buf_hook is not None
+
+    def _launch(self, b, keep_debug=False):
+        from ._lib import launch_count
+        n0 = launch_count()
+        st = {}
+        try:
+            self._phase_a(b, st)
+            self._exchange_c()
+            self._phase_b(b, st)
+            self._exchange_g()
+            self._phase_c(b, st)
+        finally:
+            self.launches_per_step = launch_count() - n0
+        return st if keep_debug else None
 
     def step(self, x_dev, y_host, plan: StepPlan | None = None, use_graph=False, keep_debug=False):
         """One alternated iteration.  x_dev: float32 NCHW tensor already on the device (or a pinned host tensor,
@@ -273,12 +290,32 @@ class AlternatedStep:
                 # warm-up launch outside capture (allocator pools, function attributes, first-step SGD), then capture
                 self._launch(b)
                 torch.cuda.current_stream().synchronize()
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self._launch(b)
-                self._graph = g
+                pool = torch.cuda.graph_pool_handle()
+                self._gstate = {}  # tensors handed from one captured phase to the next stay referenced here
+                phases = [self._phase_a, self._phase_b, self._phase_c]
+                if self._parallel:
+                    graphs = []
+                    for ph in phases:
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g, pool=pool):
+                            ph(b, self._gstate)
+                        graphs.append(g)
+                else:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, pool=pool):
+                        for ph in phases:
+                            ph(b, self._gstate)
+                    graphs = [g]
+                self._graph = graphs
             else:
-                self._graph.replay()
+                if len(self._graph) == 1:
+                    self._graph[0].replay()
+                else:
+                    self._graph[0].replay()
+                    self._exchange_c()
+                    self._graph[1].replay()
+                    self._exchange_g()
+                    self._graph[2].replay()
         else:
             dbg = self._launch(b, keep_debug)
         out = {"losses": b["losses"], "counts": b["counts"], "plan": plan}
