@@ -208,6 +208,7 @@ def run_ours(args):
         # event pair then brackets device time only, not the host-side launch latency of the kernel between them.
         # Two passes, per-launch minimum: a host hiccup (allocator growth, page fault) in one pass does not pollute it.
         passes = []
+        eng.grad_hook = eng.buf_hook = None  # rank-0-only eager passes: no collective may be issued here (measurement is over)
         for _ in range(2):
             nets.TC_PROFILE = []
             torch.cuda._sleep(int(0.15 * 1.9e9))
