@@ -46,6 +46,7 @@ _SIGS = {
     "combat_last_error": ([], C.c_char_p),
     "combat_plane_transform": ([vp, vp, vp, vp, i64, i32, i32, vp, vp], i32),
     "combat_dct32_fast": ([vp, vp, i64, i32, i32, i32, vp], i32),
+    "combat_dct64_fast": ([vp, vp, i64, i32, i32, i32, vp], i32),
     "combat_poison_blend_fwd": ([vp, vp, vp, vp, i32, i32, f32, f32, f32, vp, vp, i32, i32, i32, vp, vp, vp], i32),
     "combat_poison_blend_bwd": ([vp, vp, vp, vp, vp, f32, f32, f32, f32, vp, i32, i32, i32, i32, vp, vp], i32),
     "combat_cross_entropy": ([vp, vp, vp, i32, i32, f32, vp, vp, vp, vp], i32),

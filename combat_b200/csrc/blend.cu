@@ -86,6 +86,170 @@ __global__ void __launch_bounds__(256) poison_blend_fwd_k(const float* __restric
   }
 }
 
+// Vectorised forward for W % 4 == 0 and W <= 128 (every shape on the path): a thread owns 4 horizontally adjacent pixels;
+// the rows above / below are re-read from global memory (L1 hits: they are other threads' centre rows), the left / right
+// neighbours come from the adjacent lanes by warp shuffle (a row is W/4 <= 32 consecutive lanes) -- no shared-memory
+// tile, no barrier before the stencil.  Same arithmetic (and accumulation order) per pixel as the scalar kernel.
+__device__ __forceinline__ float4 blend_clamp4(const float4 a, const float4 b, float rate) {
+  return make_float4(clamp1(a.x + b.x * rate), clamp1(a.y + b.y * rate), clamp1(a.z + b.z * rate), clamp1(a.w + b.w * rate));
+}
+
+__global__ void __launch_bounds__(256) poison_blend_fwd_v4_k(const float* __restrict__ x, const float* __restrict__ noise,
+                                                             const int* __restrict__ perm, const int* __restrict__ nperm,
+                                                             int num_bd, float rate, float k0, float k1,
+                                                             float* __restrict__ out, float* __restrict__ sq_partial, int C,
+                                                             int H, int W, const float* __restrict__ taps_dev,
+                                                             const int* __restrict__ num_bd_dev) {
+  if (taps_dev) { k0 = taps_dev[0]; k1 = taps_dev[1]; }
+  if (num_bd_dev) num_bd = num_bd_dev[0];
+  const int plane = blockIdx.x;
+  const int r = plane / C, c = plane % C;
+  const int src = perm ? perm[r] : r;
+  const int HW4 = (H * W) >> 2, W4 = W >> 2;
+  const float4* xp = (const float4*)(x + ((long long)src * C + c) * H * W);
+  float4* op = (float4*)(out + ((long long)r * C + c) * H * W);
+  float sq = 0.f;
+  if (r >= num_bd) {  // pass-through row of the concatenation
+    for (int i = threadIdx.x; i < HW4; i += blockDim.x) op[i] = xp[i];
+  } else {
+    const int nsrc = nperm ? nperm[r] : src;
+    const float4* np_ = (const float4*)(noise + ((long long)nsrc * C + c) * H * W);
+    const float kk[3] = {k1, k0, k1};
+    const int lane = threadIdx.x & 31;
+    // every lane of a warp takes part in the shuffles: iterate whole warps (HW4 is a multiple of W4, W4 divides 32)
+    for (int i0 = threadIdx.x - lane; i0 < HW4; i0 += blockDim.x) {
+      const int i = i0 + lane;
+      const bool act = i < HW4;
+      const int ii = act ? i : HW4 - 1;
+      const int h = ii / W4, q = ii - h * W4;
+      const int hh[3] = {reflect1(h - 1, H), h, reflect1(h + 1, H)};
+      const float4 xc = xp[ii];
+      float v[3][6];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const int j = hh[a] * W4 + q;
+        const float4 m = a == 1 ? blend_clamp4(xc, np_[j], rate) : blend_clamp4(xp[j], np_[j], rate);
+        const float lft = __shfl_up_sync(0xffffffffu, m.w, 1), rgt = __shfl_down_sync(0xffffffffu, m.x, 1);
+        v[a][0] = q == 0 ? m.y : lft;          // reflect: column -1 -> column 1
+        v[a][1] = m.x; v[a][2] = m.y; v[a][3] = m.z; v[a][4] = m.w;
+        v[a][5] = q == W4 - 1 ? m.z : rgt;     // reflect: column W -> column W-2
+      }
+      if (!act) continue;
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        // depthwise conv with kernel2d = k1d (x) k1d, accumulated in the row-major tap order of the reference conv
+        float acc = 0.f;
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int b = 0; b < 3; ++b) acc = fmaf(kk[a] * kk[b], v[a][j + b], acc);
+        o[j] = acc;
+      }
+      op[i] = make_float4(o[0], o[1], o[2], o[3]);
+      float d = o[0] - xc.x; sq = fmaf(d, d, sq);
+      d = o[1] - xc.y; sq = fmaf(d, d, sq);
+      d = o[2] - xc.z; sq = fmaf(d, d, sq);
+      d = o[3] - xc.w; sq = fmaf(d, d, sq);
+    }
+  }
+  if (sq_partial) {
+    __shared__ float red[8];
+    sq = warp_sum(sq);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+      sq_partial[plane] = s;
+    }
+  }
+}
+
+// 4 x 4 pixel block per thread (H % 4 == 0, W % 4 == 0, W/4 * H/4 threads per plane, a multiple of 32 dividing 256): six
+// staged rows feed four output rows, i.e. 12 independent 16-byte loads in flight per thread and a 1.5x (L1-served) re-read
+// instead of 3x; 256 / (W/4 * H/4) planes per CTA.
+__global__ void __launch_bounds__(256) poison_blend_fwd_b16_k(const float* __restrict__ x, const float* __restrict__ noise,
+                                                              const int* __restrict__ perm, const int* __restrict__ nperm,
+                                                              int num_bd, float rate, float k0, float k1,
+                                                              float* __restrict__ out, float* __restrict__ sq_partial, int C,
+                                                              int H, int W, int planes, const float* __restrict__ taps_dev,
+                                                              const int* __restrict__ num_bd_dev) {
+  if (taps_dev) { k0 = taps_dev[0]; k1 = taps_dev[1]; }
+  if (num_bd_dev) num_bd = num_bd_dev[0];
+  const int W4 = W >> 2, H4 = H >> 2, TPP = W4 * H4;  // threads per plane
+  const int ppc = blockDim.x / TPP;                   // planes per CTA
+  const int pl = threadIdx.x / TPP, t = threadIdx.x - pl * TPP;
+  const int plane = blockIdx.x * ppc + pl;
+  const bool pvalid = plane < planes;
+  const int pc = pvalid ? plane : planes - 1;
+  const int r = pc / C, c = pc % C;
+  const int src = perm ? perm[r] : r;
+  const float4* xp = (const float4*)(x + ((long long)src * C + c) * H * W);
+  float4* op = (float4*)(out + ((long long)r * C + c) * H * W);
+  const int hb = (t / W4) * 4, q = t % W4;
+  float sq = 0.f;
+  if (r >= num_bd) {  // pass-through row of the concatenation (whole warps share a plane: no divergence around shuffles)
+    if (pvalid) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) op[(hb + j) * W4 + q] = xp[(hb + j) * W4 + q];
+    }
+  } else {
+    const int nsrc = nperm ? nperm[r] : src;
+    const float4* np_ = (const float4*)(noise + ((long long)nsrc * C + c) * H * W);
+    float4 xv[6], nv[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      const int j = reflect1(hb - 1 + a, H) * W4 + q;
+      xv[a] = xp[j];
+      nv[a] = np_[j];
+    }
+    float v[6][6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      const float4 m = blend_clamp4(xv[a], nv[a], rate);
+      const float lft = __shfl_up_sync(0xffffffffu, m.w, 1), rgt = __shfl_down_sync(0xffffffffu, m.x, 1);
+      v[a][0] = q == 0 ? m.y : lft;
+      v[a][1] = m.x; v[a][2] = m.y; v[a][3] = m.z; v[a][4] = m.w;
+      v[a][5] = q == W4 - 1 ? m.z : rgt;
+    }
+    const float kk[3] = {k1, k0, k1};
+    if (pvalid) {
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float acc = 0.f;  // row-major tap order of the reference's depthwise conv
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) acc = fmaf(kk[a] * kk[b], v[rr + a][j + b], acc);
+          o[j] = acc;
+        }
+        op[(hb + rr) * W4 + q] = make_float4(o[0], o[1], o[2], o[3]);
+        const float4 xc = xv[rr + 1];
+        float d = o[0] - xc.x; sq = fmaf(d, d, sq);
+        d = o[1] - xc.y; sq = fmaf(d, d, sq);
+        d = o[2] - xc.z; sq = fmaf(d, d, sq);
+        d = o[3] - xc.w; sq = fmaf(d, d, sq);
+      }
+    }
+  }
+  if (sq_partial) {
+    __shared__ float red[8];
+    sq = warp_sum(sq);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    if (t == 0 && pvalid) {
+      const int w0 = threadIdx.x >> 5, nw = TPP >> 5;
+      float s = 0.f;
+      for (int i = 0; i < nw; ++i) s += red[w0 + i];
+      sq_partial[plane] = s;
+    }
+  }
+}
+
 // adjoint coefficient of the 1-D reflect-padded 3-tap filter: d out[p] / d v[q]
 __device__ __forceinline__ float adj_coef(int p, int q, int n, float k0, float k1) {
   if (p == q) return k0;
@@ -129,6 +293,66 @@ __global__ void __launch_bounds__(256) poison_blend_bwd_k(const float* __restric
   }
 }
 
+// Vectorised backward for W % 4 == 0: same per-pixel arithmetic, 4 pixels per thread.
+__global__ void __launch_bounds__(256) poison_blend_bwd_v4_k(const float* __restrict__ x, const float* __restrict__ noise,
+                                                             const float* __restrict__ x_bd, const float* __restrict__ g1,
+                                                             const float* __restrict__ g2, float mse_scale, float rate,
+                                                             float k0, float k1, float* __restrict__ dnoise, int H, int W,
+                                                             const float* __restrict__ taps_dev) {
+  extern __shared__ float gt[];  // total upstream gradient of the plane
+  if (taps_dev) { k0 = taps_dev[0]; k1 = taps_dev[1]; }
+  const int HW4 = (H * W) >> 2, W4 = W >> 2;
+  const long long base4 = (long long)blockIdx.x * HW4;
+  const float4* x4 = (const float4*)x + base4;
+  const float4* n4 = (const float4*)noise + base4;
+  const float4* b4 = (const float4*)x_bd + base4;
+  const float4* g14 = (const float4*)g1 + base4;
+  const float4* g24 = g2 ? (const float4*)g2 + base4 : nullptr;
+  float4* d4 = (float4*)dnoise + base4;
+  float4 xkeep = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = threadIdx.x; i < HW4; i += blockDim.x) {
+    float4 g = g14[i];
+    if (g24) { const float4 t = g24[i]; g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w; }
+    const float4 xb = b4[i], xx = x4[i];
+    xkeep = xx;
+    g.x = fmaf(mse_scale, xb.x - xx.x, g.x); g.y = fmaf(mse_scale, xb.y - xx.y, g.y);
+    g.z = fmaf(mse_scale, xb.z - xx.z, g.z); g.w = fmaf(mse_scale, xb.w - xx.w, g.w);
+    ((float4*)gt)[i] = g;
+  }
+  __syncthreads();
+  const bool one_pass = HW4 <= (int)blockDim.x;
+  for (int i = threadIdx.x; i < HW4; i += blockDim.x) {
+    const int h = i / W4, w0 = (i - h * W4) * 4;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int dh = -1; dh <= 1; ++dh) {
+      const int ph = h + dh;
+      if (ph < 0 || ph >= H) continue;
+      const float ch = adj_coef(ph, h, H, k0, k1);
+      const float* row = gt + ph * W;
+      const float4 m = *(const float4*)(row + w0);
+      const float gv[6] = {w0 > 0 ? row[w0 - 1] : 0.f, m.x, m.y, m.z, m.w, w0 + 4 < W ? row[w0 + 4] : 0.f};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int w = w0 + j;
+#pragma unroll
+        for (int dw = -1; dw <= 1; ++dw) {
+          const int pw = w + dw;
+          if (pw < 0 || pw >= W) continue;
+          acc[j] = fmaf(ch * adj_coef(pw, w, W, k0, k1), gv[j + 1 + dw], acc[j]);
+        }
+      }
+    }
+    const float4 xx = one_pass ? xkeep : x4[i], nn = n4[i];
+    float4 o;
+    float pre = xx.x + nn.x * rate; o.x = (pre >= -1.f && pre <= 1.f) ? acc[0] * rate : 0.f;
+    pre = xx.y + nn.y * rate; o.y = (pre >= -1.f && pre <= 1.f) ? acc[1] * rate : 0.f;
+    pre = xx.z + nn.z * rate; o.z = (pre >= -1.f && pre <= 1.f) ? acc[2] * rate : 0.f;
+    pre = xx.w + nn.w * rate; o.w = (pre >= -1.f && pre <= 1.f) ? acc[3] * rate : 0.f;
+    d4[i] = o;
+  }
+}
+
 extern "C" int combat_poison_blend_fwd(const float* x, const float* noise, const int* perm, const int* nperm, int rows,
                                        int num_bd, float noise_rate, float k0, float k1, float* out, float* sq_partial,
                                        int C, int H, int W, const float* taps_dev, const int* num_bd_dev,
@@ -139,6 +363,20 @@ extern "C" int combat_poison_blend_fwd(const float* x, const float* noise, const
   if (rows <= 0) return 0;
   size_t smem = (size_t)H * W * sizeof(float);
   int use_smem = smem <= 64 * 1024;
+  {
+    const int tpp = (W / 4) * (H / 4);
+    if ((W & 3) == 0 && (H & 3) == 0 && tpp % 32 == 0 && tpp <= 256 && 256 % tpp == 0 && 32 % (W / 4) == 0) {
+      const int planes = rows * C, ppc = 256 / tpp;
+      poison_blend_fwd_b16_k<<<(planes + ppc - 1) / ppc, 256, 0, (cudaStream_t)stream>>>(
+          x, noise, perm, nperm, num_bd, noise_rate, k0, k1, out, sq_partial, C, H, W, planes, taps_dev, num_bd_dev);
+      COMBAT_RETURN_LAUNCH("poison_blend_fwd");
+    }
+  }
+  if ((W & 3) == 0 && W <= 128 && 32 % (W / 4) == 0) {  // a row = W/4 consecutive lanes of one warp
+    poison_blend_fwd_v4_k<<<rows * C, 256, 0, (cudaStream_t)stream>>>(x, noise, perm, nperm, num_bd, noise_rate, k0, k1, out,
+                                                                         sq_partial, C, H, W, taps_dev, num_bd_dev);
+    COMBAT_RETURN_LAUNCH("poison_blend_fwd");
+  }
   if (use_smem) cudaFuncSetAttribute(poison_blend_fwd_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   poison_blend_fwd_k<<<rows * C, 256, use_smem ? smem : 0, (cudaStream_t)stream>>>(x, noise, perm, nperm, num_bd, noise_rate,
                                                                                   k0, k1, out, sq_partial, C, H, W, use_smem,
@@ -155,6 +393,12 @@ extern "C" int combat_poison_blend_bwd(const float* x, const float* noise, const
   if (rows <= 0) return 0;
   size_t smem = (size_t)H * W * sizeof(float);
   COMBAT_ARG(smem <= 200 * 1024, 13);
+  if ((W & 3) == 0) {
+    cudaFuncSetAttribute(poison_blend_bwd_v4_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    poison_blend_bwd_v4_k<<<rows * C, 256, smem, (cudaStream_t)stream>>>(x, noise, x_bd, g1, g2, mse_scale, noise_rate, k0, k1,
+                                                                         dnoise, H, W, taps_dev);
+    COMBAT_RETURN_LAUNCH("poison_blend_bwd");
+  }
   cudaFuncSetAttribute(poison_blend_bwd_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   poison_blend_bwd_k<<<rows * C, 256, smem, (cudaStream_t)stream>>>(x, noise, x_bd, g1, g2, mse_scale, noise_rate, k0, k1,
                                                                     dnoise, H * W, H, W, taps_dev);

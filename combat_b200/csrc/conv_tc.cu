@@ -163,6 +163,7 @@ struct TcParams {
   const bf16* mask;         // bf16 NHWC like out: v = mask > 0 ? v * mask_scale[c] : 0 -- backward of relu(bn_eval(.))
   const float* mask_scale;
   const bf16* post_add;     // bf16 NHWC like out, added after the mask (gradient arriving over an identity shortcut)
+  long long* dbg;           // optional [gridDim.x][8] cycle counters (pipeline diagnostics, scripts/bench_conv.py --dbg)
   TcTaps taps;
 };
 
@@ -263,6 +264,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* stg_base
   };
   // one tile ahead only where the register file allows it (64-wide tiles: 32 prefetch registers per tile)
   constexpr bool AHEAD = NCH == 1;
+  long long e_wait = 0, e_body = 0;
   TileCtx cur, nxt;
   if (AHEAD && (int)blockIdx.x < p.total_tiles) prepare(blockIdx.x, cur);
   for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -277,10 +279,13 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* stg_base
     const uint32_t okmask = cur.okmask;
     uint32_t (&ob)[8] = cur.ob;
     float4 (&pr)[NCH][8] = cur.pr;
+    const bool dbg_w = p.dbg && warp == 2 && lane == 0;
+    const long long te0 = dbg_w ? clock64() : 0;
     if (has_acc) {
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
     }
+    const long long te1 = dbg_w ? clock64() : 0;
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + half * (BLOCK_N / 2);
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) {
@@ -384,7 +389,15 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* stg_base
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (dbg_w) {
+      e_wait += te1 - te0;          // epilogue warp waiting for the accumulator
+      e_body += clock64() - te1;    // epilogue body
+    }
     if (more) cur = nxt;
+  }
+  if (p.dbg && warp == 2 && lane == 0) {
+    p.dbg[blockIdx.x * 8 + 4] += e_wait;
+    p.dbg[blockIdx.x * 8 + 5] += e_body;
   }
 }
 
@@ -552,20 +565,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc64_kernel(const __grid_c
       for (int t = 0; t < 9; ++t) tma_load_3d(wsm + t * 8192, &maps.w, w_bar, 0, t, 0);
       int stage = 0;
       uint32_t phase = 0;
+      long long w_empty = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int cls, nt, ht, wt, cot;
         decode_tile(p, tile, cls, nt, ht, wt, cot);
         for (int dw = -1; dw <= 1; ++dw) {
+          const long long t0 = p.dbg ? clock64() : 0;
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (p.dbg) w_empty += clock64() - t0;
           mbar_expect_tx(&full_bar[stage], stage_bytes);
           tma_load_4d(stages + stage * stage_bytes, &maps.in[0], &full_bar[stage], 0, dw, ht * p.BH - 1, nt);
           if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
       }
+      if (p.dbg) p.dbg[blockIdx.x * 8 + 0] += w_empty;
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(TILE_M, 64, 0, 0);
+      long long w_tempty = 0, w_full = 0;
       mbar_wait(w_bar, 0);
       tc_fence_after();
       const uint32_t wbase = smem_u32(wsm);
@@ -574,12 +592,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc64_kernel(const __grid_c
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      const long long tstart = p.dbg ? clock64() : 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        long long t0 = p.dbg ? clock64() : 0;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        if (p.dbg) w_tempty += clock64() - t0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 64;
         for (int dwi = 0; dwi < 3; ++dwi) {
+          t0 = p.dbg ? clock64() : 0;
           mbar_wait(&full_bar[stage], phase);
+          if (p.dbg) w_full += clock64() - t0;
           tc_fence_after();
           const uint32_t sa = smem_u32(stages + stage * stage_bytes);
 #pragma unroll
@@ -594,6 +617,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc64_kernel(const __grid_c
         }
         umma_commit(&tfull_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      if (p.dbg) {
+        p.dbg[blockIdx.x * 8 + 1] += w_tempty;
+        p.dbg[blockIdx.x * 8 + 2] += w_full;
+        p.dbg[blockIdx.x * 8 + 3] += clock64() - tstart;
       }
     }
   } else {
@@ -725,6 +753,7 @@ extern "C" int combat_conv_tc(const combat_conv_tc_desc* d, void* stream) {
   p.mask = (const bf16*)d->mask;
   p.mask_scale = d->mask_scale;
   p.post_add = (const bf16*)d->post_add;
+  p.dbg = getenv("COMBAT_TC_DBG") ? (long long*)d->stats : nullptr;
   const int BLOCK_N = (d->Co % 128 == 0) ? 128 : 64;
   p.tiles_co = d->Co / BLOCK_N;
   int rc;

@@ -129,7 +129,7 @@ _KIND = {"dct": 1, "idct": 2, "lowfreq": 3}
 
 def plane_op(x: torch.Tensor, kind: str, keep: int = 0, in_mode: int = 0, out: torch.Tensor | None = None, fast=True):
     """dct_2d / idct_2d / low-pass projection over the last two (square) dims of `x`.
-    N == 32 runs the register-butterfly kernel (csrc/dct32.cu); other sizes the generic M X M^T kernels."""
+    N == 32 / 64 run the register-butterfly kernels (csrc/dct32.cu); other sizes the generic M X M^T kernels."""
     x = _contig(x)
     N = x.shape[-1]
     assert x.shape[-2] == N
@@ -137,12 +137,13 @@ def plane_op(x: torch.Tensor, kind: str, keep: int = 0, in_mode: int = 0, out: t
         raise TypeError("in_mode 1 needs a uint8 tensor")
     if in_mode != 1 and x.dtype != torch.float32:
         raise TypeError("float32 input expected")
-    if N == 32 and fast:
+    if N in (32, 64) and fast:
         if out is None:
             out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
-        planes = x.numel() // 1024
+        planes = x.numel() // (N * N)
         if planes:
-            check(lib.combat_dct32_fast(_p(x), _p(out), planes, _KIND[kind], keep, in_mode, _s()), "dct32_fast")
+            fn = lib.combat_dct32_fast if N == 32 else lib.combat_dct64_fast
+            check(fn(_p(x), _p(out), planes, _KIND[kind], keep, in_mode, _s()), "dct%d_fast" % N)
         return out
     return plane_transform(x, transform_matrix(kind, N, x.device, keep), in_mode, out)
 

@@ -48,6 +48,8 @@ const char* combat_last_error(void);
 int combat_plane_transform(const void* in, float* out, const float* L, const float* R, long long planes, int N,
                            int in_mode, float* workspace, void* stream);
 int combat_dct32_fast(const void* in, float* out, long long planes, int kind, int keep, int in_mode, void* stream);
+/* same for 64 x 64 planes (CelebA shape), one 64-thread CTA per plane */
+int combat_dct64_fast(const void* in, float* out, long long planes, int kind, int keep, int in_mode, void* stream);
 
 /* ---------------------------------------------------------------- poisoned-batch builder
  * train_generator.py:188-195 (C-step) and :223-226 (G-step), torchvision GaussianBlur(3) with reflect padding.

@@ -56,6 +56,11 @@ for name, Ci, Co, H in SHAPES:
         if args.variant and args.variant != vn:
             continue
         descs = [mk(i) for i in range(NBUF)]
+        dbg = None
+        if os.environ.get("COMBAT_TC_DBG"):
+            dbg = torch.zeros(148 * 8, dtype=torch.int64, device=dev)
+            for d in descs:
+                d.stats = dbg.data_ptr()
         for d in descs:
             check(lib.combat_conv_tc(C.byref(d), ops._s()), "conv_tc")
         torch.cuda.synchronize()
@@ -67,6 +72,12 @@ for name, Ci, Co, H in SHAPES:
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / args.iters
         print("%-8s %-16s %8.1f us  %7.1f TFLOP/s" % (name, vn, us, flops / us / 1e6))
+        if dbg is not None:
+            torch.cuda.synchronize()
+            m = dbg.view(148, 8).double().mean(0) / (args.iters + NBUF)
+            tiles = N * H * H / 128 / 148
+            print("   per tile (cycles): producer wait-empty %.0f | mma wait-tempty %.0f wait-full %.0f total %.0f | epi wait-acc %.0f body %.0f"
+                  % tuple(float(v) / tiles for v in m[:6]))
     if args.variant:
         continue
     # wgrad

@@ -17,6 +17,8 @@ def main(path, title=""):
         name = re.sub(r"^void ", "", name)
         m = re.match(r"([A-Za-z0-9_:]+(?:<[0-9, ]+>)?)", name)
         short = m.group(1) if m else name[:40]
+        if "spin_kernel" in name or short.startswith("cuda::"):
+            continue  # torch.cuda._sleep (bench.py parks the GPU before its per-launch timing pass)
         ns = float(r["Metric Value"].replace(",", ""))
         if r.get("Metric Unit") in ("us", "usecond"):
             ns *= 1e3

@@ -31,7 +31,7 @@ def dev(t):
 
 
 # ------------------------------------------------------------------ DCT family
-@pytest.mark.parametrize("N,fast", [(32, True), (32, False), (64, False), (28, False), (8, False)])
+@pytest.mark.parametrize("N,fast", [(32, True), (32, False), (64, True), (64, False), (28, False), (8, False)])
 def test_dct_idct_lowfreq(ops, N, fast):
     g = torch.Generator().manual_seed(N)
     x = torch.rand(5, 3, N, N, generator=g) * 255
@@ -49,9 +49,15 @@ def test_dct_idct_lowfreq(ops, N, fast):
     assert float((lf.cpu() - O.low_freq(xn, N, 0.65)).abs().max()) < 2e-5
     # idempotence of the projection
     assert float((ops.plane_op(lf, "lowfreq", keep=keep, fast=fast) - lf).abs().max()) < 2e-6
+    # other retained block sizes (the pruned instantiation is chosen by `keep`): below, at and above the default
+    for k2 in (1, keep - 3, keep + 1, N):
+        ratio = (k2 + 0.5) / N
+        lf2 = ops.plane_op(dev(xn), "lowfreq", keep=k2, fast=fast)
+        assert int(N * ratio) == k2
+        assert float((lf2.cpu().double() - torch.from_numpy(O.low_freq_exact(xn.numpy(), N, ratio))).abs().max()) < 2e-6, k2
 
 
-@pytest.mark.parametrize("N,fast", [(32, True), (32, False), (64, False)])
+@pytest.mark.parametrize("N,fast", [(32, True), (32, False), (64, True), (64, False)])
 def test_dct_uint8_paths(ops, N, fast):
     g = torch.Generator().manual_seed(100 + N)
     xu = (torch.rand(4, 3, N, N, generator=g) * 256).clamp(0, 255).byte()
