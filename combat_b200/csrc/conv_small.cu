@@ -3,6 +3,9 @@
 // gradient of upconv0_0) and 3 output channels (generator upconv0_0 and the input gradient of the classifiers'
 // conv1).  They are memory-bound: the 3-channel side is NCHW float32 (the reference's image tensors), the wide
 // side is NHWC in the activation dtype.  Replaces the corresponding aten::conv2d / convolution_backward calls.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 template <typename T>
@@ -138,9 +141,11 @@ __global__ void __launch_bounds__(256) conv_cout3_generic_k(const TI* __restrict
 // at <= 1 per 4..8 FMAs so the FMA pipe, not the load/store unit, is the limiter.
 // =====================================================================================================================
 
-// ---------------------------------------------------------------------------------- 3 -> Co, 4 pixels x 8 channels per thread
-// x: NCHW float32 [N,3,H,W]; w: [Co][9][3] (TW); out: NHWC [N,Ho,Wo,Co] (TO); Wo % 4 == 0.
-template <typename TW, typename TO, int S>
+// ---------------------------------------------------------------------------------- 3 -> Co, PX pixels x 8 channels per thread
+// x: NCHW float32 [N,3,H,W]; w: [Co][9][3] (TW); out: NHWC [N,Ho,Wo,Co] (TO); Wo % PX == 0.
+// A weight float read from shared memory costs one LSU cycle per warp however it is vectorised or broadcast, an FMA
+// warp-instruction a quarter of an SM cycle: PX = 8 pixels per weight keeps the FMA pipe, not the LSU, the limiter.
+template <typename TW, typename TO, int S, int PX>
 __global__ void __launch_bounds__(256) conv_cin3_k(const float* __restrict__ x, const TW* __restrict__ w,
                                                    const float* __restrict__ bias, TO* __restrict__ out, int N, int H, int W,
                                                    int Ho, int Wo, int Co, int act, const float* __restrict__ post_scale,
@@ -152,25 +157,25 @@ __global__ void __launch_bounds__(256) conv_cin3_k(const float* __restrict__ x, 
     ws[k * Co + co] = to_f<TW>(w[e]);
   }
   __syncthreads();
-  constexpr int NV = 3 * S + 3;            // input columns touched by 4 adjacent output pixels
-  const int tpq = Co >> 3;                 // threads per pixel quad
-  const int qpb = blockDim.x / tpq;        // quads per block iteration
+  constexpr int NV = (PX - 1) * S + 3;     // input columns touched by PX adjacent output pixels
+  const int tpq = Co >> 3;                 // threads per pixel group
+  const int qpb = blockDim.x / tpq;        // groups per block iteration
   const int cg = (threadIdx.x % tpq) * 8;
   const int ql = threadIdx.x / tpq;
-  const int Wq = Wo >> 2;
+  const int Wq = Wo / PX;
   const long long Q = (long long)N * Ho * Wq;
   const long long HW = (long long)H * W;
   for (long long q = (long long)blockIdx.x * qpb + ql; q < Q; q += (long long)gridDim.x * qpb) {
-    const int ow0 = (int)(q % Wq) * 4;
+    const int ow0 = (int)(q % Wq) * PX;
     const long long r = q / Wq;
     const int oh = (int)(r % Ho);
     const long long n = r / Ho;
-    float acc[4][8];
+    float acc[PX][8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       const float b = bias ? bias[cg + c] : 0.f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[j][c] = b;
+      for (int j = 0; j < PX; ++j) acc[j][c] = b;
     }
     const float* xb = x + n * 3 * HW;
     const int iw0 = ow0 * S - 1;
@@ -192,7 +197,7 @@ __global__ void __launch_bounds__(256) conv_cin3_k(const float* __restrict__ x, 
           const float* wp = ws + ((kh * 3 + kw) * 3 + ci) * Co + cg;
           const float4 w0 = *(const float4*)wp, w1 = *(const float4*)(wp + 4);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < PX; ++j) {
             const float a = v[j * S + kw];
             acc[j][0] = fmaf(a, w0.x, acc[j][0]); acc[j][1] = fmaf(a, w0.y, acc[j][1]);
             acc[j][2] = fmaf(a, w0.z, acc[j][2]); acc[j][3] = fmaf(a, w0.w, acc[j][3]);
@@ -202,21 +207,16 @@ __global__ void __launch_bounds__(256) conv_cin3_k(const float* __restrict__ x, 
         }
       }
     }
-    float sc[8], sh[8];
-    if (post_scale) {
-#pragma unroll
-      for (int c = 0; c < 8; ++c) { sc[c] = post_scale[cg + c]; sh[c] = post_shift[cg + c]; }
-    }
     const long long m0 = (r * Wo + ow0);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < PX; ++j) {
       if (act == 2) {
 #pragma unroll
         for (int c = 0; c < 8; ++c) acc[j][c] = acc[j][c] > 0.f ? acc[j][c] : expm1f(acc[j][c]);
       }
       if (post_scale) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[j][c] = fmaf(acc[j][c], sc[c], sh[c]);
+        for (int c = 0; c < 8; ++c) acc[j][c] = fmaf(acc[j][c], post_scale[cg + c], post_shift[cg + c]);
       }
       store8<TO>(out + (m0 + j) * Co + cg, acc[j]);
       if (out2) {  // eval-mode BatchNorm + ReLU of the first PreAct block, fused (preact_resnet.py:29-31)
@@ -247,11 +247,11 @@ __device__ __forceinline__ void load8<bf16>(const bf16* p, float* v) {
   }
 }
 
-// ---------------------------------------------------------------------------------- 64 -> 3, 2 pixels per thread
-// in: NHWC [N,H,W,64] (TI); w: [3][9][64] (TW); out: NCHW float32 [N,3,H,W]; W % 2 == 0.
+// ---------------------------------------------------------------------------------- 64 -> 3, PX pixels per thread
+// in: NHWC [N,H,W,64] (TI); w: [3][9][64] (TW); out: NCHW float32 [N,3,H,W]; W % PX == 0.
 // Weights sit in shared memory as [9][64] float4 (co0, co1, co2, 0): every weight read is a warp-wide broadcast and
-// feeds 6 FMAs (3 outputs x 2 pixels).
-template <typename TI, typename TW>
+// feeds 3 * PX FMAs.  PX = 8 keeps the kernel FMA-bound (see conv_cin3_k); PX = 2 serves narrow / small problems.
+template <typename TI, typename TW, int PX>
 __global__ void __launch_bounds__(128) conv_cout3_k(const TI* __restrict__ in, const TW* __restrict__ w,
                                                     const float* __restrict__ bias, float* __restrict__ out, int N, int H, int W,
                                                     int act) {
@@ -259,25 +259,27 @@ __global__ void __launch_bounds__(128) conv_cout3_k(const TI* __restrict__ in, c
   for (int e = threadIdx.x; e < 9 * 64; e += blockDim.x)
     wsm[e] = make_float4(to_f<TW>(w[e]), to_f<TW>(w[576 + e]), to_f<TW>(w[1152 + e]), 0.f);
   __syncthreads();
-  const int Wp = W >> 1;
+  const int Wp = W / PX;
   const long long P = (long long)N * H * Wp, HW = (long long)H * W;
   const float b0 = bias ? bias[0] : 0.f, b1 = bias ? bias[1] : 0.f, b2 = bias ? bias[2] : 0.f;
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
-    const int ow0 = (int)(p % Wp) * 2;
+    const int ow0 = (int)(p % Wp) * PX;
     const long long r = p / Wp;
     const int oh = (int)(r % H);
     const long long n = r / H;
-    float a[2][3] = {{b0, b1, b2}, {b0, b1, b2}};
+    float a[PX][3];
+#pragma unroll
+    for (int j = 0; j < PX; ++j) { a[j][0] = b0; a[j][1] = b1; a[j][2] = b2; }
 #pragma unroll 1
     for (int kh = 0; kh < 3; ++kh) {
       const int ih = oh - 1 + kh;
       if (ih < 0 || ih >= H) continue;
       const TI* rowp = in + ((n * H + ih) * W) * 64;
-#pragma unroll 2
+#pragma unroll 1
       for (int ch = 0; ch < 8; ++ch) {
-        float v[4][8];
+        float v[PX + 2][8];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < PX + 2; ++c) {
           const int iw = ow0 - 1 + c;
           if (iw >= 0 && iw < W) {
             load8<TI>(rowp + (long long)iw * 64 + ch * 8, v[c]);
@@ -292,9 +294,12 @@ __global__ void __launch_bounds__(128) conv_cout3_k(const TI* __restrict__ in, c
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 ww = wp[i];
-            a[0][0] = fmaf(v[kw][i], ww.x, a[0][0]); a[0][1] = fmaf(v[kw][i], ww.y, a[0][1]); a[0][2] = fmaf(v[kw][i], ww.z, a[0][2]);
-            a[1][0] = fmaf(v[kw + 1][i], ww.x, a[1][0]); a[1][1] = fmaf(v[kw + 1][i], ww.y, a[1][1]);
-            a[1][2] = fmaf(v[kw + 1][i], ww.z, a[1][2]);
+#pragma unroll
+            for (int j = 0; j < PX; ++j) {
+              a[j][0] = fmaf(v[j + kw][i], ww.x, a[j][0]);
+              a[j][1] = fmaf(v[j + kw][i], ww.y, a[j][1]);
+              a[j][2] = fmaf(v[j + kw][i], ww.z, a[j][2]);
+            }
           }
         }
       }
@@ -302,112 +307,142 @@ __global__ void __launch_bounds__(128) conv_cout3_k(const TI* __restrict__ in, c
     float* op = out + n * 3 * HW + (long long)oh * W + ow0;
 #pragma unroll
     for (int co = 0; co < 3; ++co) {
-      float y0 = a[0][co], y1 = a[1][co];
-      if (act == 1) { y0 = tanhf(y0); y1 = tanhf(y1); }
-      *(float2*)(op + co * HW) = make_float2(y0, y1);
+      float y[PX];
+#pragma unroll
+      for (int j = 0; j < PX; ++j) y[j] = act == 1 ? tanhf(a[j][co]) : a[j][co];
+#pragma unroll
+      for (int j = 0; j < PX; j += 2) *(float2*)(op + co * HW + j) = make_float2(y[j], y[j + 1]);
     }
   }
 }
 
 // ---------------------------------------------------------------------------------- weight gradient of both boundary convs
-// G[c][t][j] = sum_m wide[m][c] * narrow[n, j, oh*S - 1 + kh, ow*S - 1 + kw]      (t = kh*3 + kw, j < 3, c < C)
-//   MODE 0 (3 -> C conv, wgrad_cin3): wide = dy NHWC, narrow = x NCHW;  dw[(c*9 + t)*3 + j] += G;  db[c] += sum_m wide[m][c]
-//   MODE 1 (C -> 3 conv, wgrad_cout3, C = 64, S = 1): wide = layer input a NHWC, narrow = dz NCHW;
-//                                                     dw[(j*9 + 8 - t)*C + c] += G;  db[j] += sum dz[j]
-// Per tile of 64 wide pixels the block builds the [64][28] im2col patch of the narrow tensor in shared memory; a thread
-// owns 2 wide channels x 27 patch columns (54 accumulators) and reads the patch with broadcast LDS.128.
+// G[c][t][j] = sum_m wide[m][c] * narrow[n, j, oh*S - 1 + kh, ow*S - 1 + kw]      (t = kh*3 + kw, j < 3, c < 64)
+//   MODE 0 (3 -> 64 conv, wgrad_cin3): wide = dy NHWC, narrow = x NCHW;  dw[(c*9 + t)*3 + j] += G;  db[c] += sum_m wide[m][c]
+//   MODE 1 (64 -> 3 conv, wgrad_cout3, S = 1): wide = layer input a NHWC, narrow = dz NCHW;
+//                                              dw[(j*9 + 8 - t)*64 + c] += G;  db[j] += sum dz[j]
+// Per tile of 64 wide pixels the block builds the im2col patch of the narrow tensor in shared memory as
+// [64 pixels][4 slices][8] (7 patch columns + 1 pad per slice, 27 = 4*7 - 1 used).  A warp streams over pixels; lane
+// (cg, ks) owns an 8-channel x 7-column register tile: per pixel one 16-byte global load of 8 wide channels, two
+// broadcast 16-byte shared loads of the slice, 56 FMAs -- FMA-bound (a shared-memory float costs an LSU cycle per warp).
 #define WG_TP 64
 template <typename T>
-__device__ __forceinline__ float2 load2(const T* p);
+__device__ __forceinline__ void load8w(const T* p, float* v);
 template <>
-__device__ __forceinline__ float2 load2<float>(const float* p) { return *(const float2*)p; }
+__device__ __forceinline__ void load8w<float>(const float* p, float* v) { load8<float>(p, v); }
 template <>
-__device__ __forceinline__ float2 load2<bf16>(const bf16* p) { return __bfloat1622float2(*(const __nv_bfloat162*)p); }
+__device__ __forceinline__ void load8w<bf16>(const bf16* p, float* v) { load8<bf16>(p, v); }
 
 template <typename T, int MODE>
 __global__ void __launch_bounds__(256) wgrad3_k(const float* __restrict__ narrow, const T* __restrict__ wide,
                                                 float* __restrict__ dw, float* __restrict__ db, int N, int Hn, int Wn, int Hw,
-                                                int Ww, int C, int S) {
-  __shared__ __align__(16) float patch[WG_TP * 28];
-  __shared__ __align__(16) float red[128 * 56];  // [blockDim.y / 2 pixel groups][blockDim.x threads][2][28] = 128 threads x 56
-  const int cx = threadIdx.x, py = threadIdx.y, GY = blockDim.y, TX = blockDim.x;
-  const int tid = py * TX + cx;
-  float acc[2][28];
+                                                int Ww, int S) {
+  __shared__ __align__(16) float patch[WG_TP * 32];
+  __shared__ __align__(16) float red[4 * 32 * 64];  // tree reduction over the 8 warps: 4 x (32 lanes x 64 values)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cg = lane & 7, ks = lane >> 3;  // channels 8*cg .. 8*cg+7, patch columns 7*ks .. 7*ks+6
+  float acc[8][7];
 #pragma unroll
-  for (int k = 0; k < 28; ++k) acc[0][k] = acc[1][k] = 0.f;
-  float nsum = 0.f;  // MODE 1: bias gradient = sum of the centre column of the patch (threads cx < 3)
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int k = 0; k < 7; ++k) acc[c][k] = 0.f;
+  float wsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // MODE 0 bias gradient (lanes with ks == 0)
+  float nsum[3] = {0.f, 0.f, 0.f};                           // MODE 1 bias gradient: centre patch column j, summed at build time
   const long long M = (long long)N * Hw * Ww, HWn = (long long)Hn * Wn;
   const long long tiles = (M + WG_TP - 1) / WG_TP;
+  // patch builder: thread -> (pixel p = tid / 4, slice q = tid % 4): 7 columns k = 7q .. 7q+6, one pixel decode per tile
+  const int bp = tid >> 2, bq = tid & 3;
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const long long m0 = tile * WG_TP;
     __syncthreads();  // previous tile's readers are done
-    for (int e = tid; e < WG_TP * 28; e += 256) {
-      const int p = e / 28, k = e - p * 28;
-      const long long m = m0 + p;
-      float v = 0.f;
-      if (k < 27 && m < M) {
+    {
+      const long long m = m0 + bp;
+      float pv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) pv[i] = 0.f;
+      if (m < M) {
         const int ow = (int)(m % Ww);
         const long long r = m / Ww;
         const int oh = (int)(r % Hw);
         const long long n = r / Hw;
-        const int t = k / 3, j = k - t * 3;
-        const int ih = oh * S - 1 + t / 3, iw = ow * S - 1 + t % 3;
-        if (ih >= 0 && ih < Hn && iw >= 0 && iw < Wn) v = __ldg(narrow + (n * 3 + j) * HWn + (long long)ih * Wn + iw);
+        const float* nb = narrow + n * 3 * HWn;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+          const int k = bq * 7 + i;  // < 28; k == 27 is the unused tail
+          const int t = k / 3, j = k - t * 3;
+          const int ih = oh * S - 1 + t / 3, iw = ow * S - 1 + t % 3;
+          if (k < 27 && ih >= 0 && ih < Hn && iw >= 0 && iw < Wn) pv[i] = __ldg(nb + j * HWn + (long long)ih * Wn + iw);
+          if (MODE == 1 && t == 4) nsum[j] += pv[i];  // centre tap: every narrow pixel exactly once over all tiles
+        }
       }
-      patch[e] = v;
+      float4* dst = (float4*)(patch + bp * 32 + bq * 8);
+      dst[0] = make_float4(pv[0], pv[1], pv[2], pv[3]);
+      dst[1] = make_float4(pv[4], pv[5], pv[6], 0.f);
     }
     __syncthreads();
-    for (int p = py; p < WG_TP; p += GY) {
+    for (int p = warp; p < WG_TP; p += 8) {
       const long long m = m0 + p;
       if (m >= M) break;
-      const float2 g = load2<T>(wide + m * C + 2 * cx);
-      const float4* pp = (const float4*)(patch + p * 28);
-      float v[28];
+      float g[8];
+      load8w<T>(wide + m * 64 + cg * 8, g);
+      const float4* pp = (const float4*)(patch + p * 32 + ks * 8);
+      const float4 q0 = pp[0], q1 = pp[1];
+      const float v[7] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z};
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+#pragma unroll
+        for (int k = 0; k < 7; ++k) acc[c][k] = fmaf(g[c], v[k], acc[c][k]);
+      if (MODE == 0 && ks == 0) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) wsum[c] += g[c];
+      }
+    }
+  }
+  // tree reduction over the 8 warps (each holds a full partial [64 channels][28 columns]), then atomics by warp 0
+  for (int half = 4; half >= 1; half >>= 1) {
+    __syncthreads();
+    if (warp >= half && warp < 2 * half) {
+      float* o = red + ((warp - half) * 32 + lane) * 64;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) o[c * 8 + k] = acc[c][k];
+        o[c * 8 + 7] = wsum[c];
+      }
+    }
+    __syncthreads();
+    if (warp < half) {
+      const float* o = red + (warp * 32 + lane) * 64;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) acc[c][k] += o[c * 8 + k];
+        wsum[c] += o[c * 8 + 7];
+      }
+    }
+  }
+  if (warp == 0) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int ch = cg * 8 + c;
 #pragma unroll
       for (int i = 0; i < 7; ++i) {
-        const float4 q = pp[i];
-        v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+        const int k = ks * 7 + i;
+        if (k < 27) {
+          const int t = k / 3, j = k - t * 3;
+          if (MODE == 0) atomicAdd(dw + (long long)ch * 27 + k, acc[c][i]);
+          else atomicAdd(dw + ((long long)j * 9 + (8 - t)) * 64 + ch, acc[c][i]);
+        }
       }
-#pragma unroll
-      for (int k = 0; k < 27; ++k) {
-        acc[0][k] = fmaf(g.x, v[k], acc[0][k]);
-        acc[1][k] = fmaf(g.y, v[k], acc[1][k]);
-      }
-      if (MODE == 0) { acc[0][27] += g.x; acc[1][27] += g.y; }
-      if (MODE == 1 && cx < 3) nsum += cx == 0 ? v[12] : (cx == 1 ? v[13] : v[14]);
+      if (MODE == 0 && db && ks == 0) atomicAdd(db + ch, wsum[c]);
     }
   }
-  // tree reduction over the pixel groups (threadIdx.y), then one atomic per accumulator per block
-  for (int half = GY >> 1; half >= 1; half >>= 1) {
-    __syncthreads();
-    if (py >= half && py < 2 * half) {
-      float* o = red + ((size_t)(py - half) * TX + cx) * 56;
+  if (MODE == 1 && db) {
 #pragma unroll
-      for (int k = 0; k < 28; ++k) { o[k] = acc[0][k]; o[28 + k] = acc[1][k]; }
-      if (MODE == 1) o[27] = nsum;
+    for (int j = 0; j < 3; ++j) {
+      const float v = warp_sum(nsum[j]);
+      if (lane == 0) atomicAdd(db + j, v);
     }
-    __syncthreads();
-    if (py < half) {
-      const float* o = red + ((size_t)py * TX + cx) * 56;
-      if (MODE == 1) nsum += o[27];
-#pragma unroll
-      for (int k = 0; k < 27; ++k) { acc[0][k] += o[k]; acc[1][k] += o[28 + k]; }
-      if (MODE == 0) { acc[0][27] += o[27]; acc[1][27] += o[55]; }
-    }
-  }
-  if (py == 0) {
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int c = 2 * cx + h;
-#pragma unroll
-      for (int k = 0; k < 27; ++k) {
-        const int t = k / 3, j = k - t * 3;
-        if (MODE == 0) atomicAdd(dw + (long long)c * 27 + k, acc[h][k]);
-        else atomicAdd(dw + ((long long)j * 9 + (8 - t)) * C + c, acc[h][k]);
-      }
-      if (MODE == 0 && db) atomicAdd(db + c, acc[h][27]);
-    }
-    if (MODE == 1 && db && cx < 3) atomicAdd(db + cx, nsum);
   }
 }
 
@@ -430,17 +465,22 @@ extern "C" int combat_conv_cin3(const float* x, const void* w, int w_dtype, cons
   cudaStream_t st = (cudaStream_t)stream;
   if (Wo % 4 == 0) {
     const int qpb = 256 / (Co / 8);
-    const int grid = grid_for(M / 4, qpb * 2);
-#define LCI(TW, TO)                                                                                                         \
-  {                                                                                                                         \
-    if (stride == 1)                                                                                                        \
-      conv_cin3_k<TW, TO, 1><<<grid, 256, smem, st>>>(x, (const TW*)w, bias, (TO*)out, N, H, W, Ho, Wo, Co, act, post_scale, post_shift, (bf16*)out2, scale2, shift2); \
-    else                                                                                                                    \
-      conv_cin3_k<TW, TO, 2><<<grid, 256, smem, st>>>(x, (const TW*)w, bias, (TO*)out, N, H, W, Ho, Wo, Co, act, post_scale, post_shift, (bf16*)out2, scale2, shift2); \
+    // measured on B200 (scripts/bench_small.py): 8 pixels per thread halves the shared-memory weight reads per FMA but
+    // its 190 registers leave one CTA per SM and the kernel latency-bound -- no gain over 4, which stays the default
+    const int px = (Wo % 8 == 0 && getenv("COMBAT_CIN3_PX8")) ? 8 : 4;
+    const int grid = grid_for(M / px, qpb);
+#define LCI2(TW, TO, SS, PP)                                                                                      \
+  conv_cin3_k<TW, TO, SS, PP><<<grid, 256, smem, st>>>(x, (const TW*)w, bias, (TO*)out, N, H, W, Ho, Wo, Co, act, \
+                                                       post_scale, post_shift, (bf16*)out2, scale2, shift2)
+#define LCI(TW, TO)                                          \
+  {                                                          \
+    if (stride == 1) { if (px == 8) LCI2(TW, TO, 1, 8); else LCI2(TW, TO, 1, 4); } \
+    else { if (px == 8) LCI2(TW, TO, 2, 8); else LCI2(TW, TO, 2, 4); }             \
   }
     if (w_dtype == COMBAT_F32) { if (out_dtype == COMBAT_F32) LCI(float, float) else LCI(float, bf16) }
     else { if (out_dtype == COMBAT_F32) LCI(bf16, float) else LCI(bf16, bf16) }
 #undef LCI
+#undef LCI2
     COMBAT_RETURN_LAUNCH("conv_cin3");
   }
   COMBAT_ARG(!out2, 15);  // the fused second output needs Wo % 4 == 0
@@ -461,10 +501,15 @@ extern "C" int combat_conv_cout3(const void* in, int in_dtype, const void* w, in
   if (M <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   if (W % 2 == 0) {
-    const int grid = grid_for(M / 2, 128);
-#define LCO(TI, TW) conv_cout3_k<TI, TW><<<grid, 128, 0, st>>>((const TI*)in, (const TW*)w, bias, out, N, H, W, act)
-    if (in_dtype == COMBAT_F32) { if (w_dtype == COMBAT_F32) LCO(float, float); else LCO(float, bf16); }
-    else { if (w_dtype == COMBAT_F32) LCO(bf16, float); else LCO(bf16, bf16); }
+    const int px = (W % 8 == 0 && M / 8 >= 148 * 128) ? 8 : 2;  // 8 pixels per thread once that still fills the GPU
+    const int grid = grid_for(M / px, 128);
+#define LCO(TI, TW)                                                                                                     \
+  {                                                                                                                     \
+    if (px == 8) conv_cout3_k<TI, TW, 8><<<grid, 128, 0, st>>>((const TI*)in, (const TW*)w, bias, out, N, H, W, act);   \
+    else conv_cout3_k<TI, TW, 2><<<grid, 128, 0, st>>>((const TI*)in, (const TW*)w, bias, out, N, H, W, act);           \
+  }
+    if (in_dtype == COMBAT_F32) { if (w_dtype == COMBAT_F32) LCO(float, float) else LCO(float, bf16) }
+    else { if (w_dtype == COMBAT_F32) LCO(bf16, float) else LCO(bf16, bf16) }
 #undef LCO
     COMBAT_RETURN_LAUNCH("conv_cout3");
   }
@@ -485,17 +530,27 @@ static int wgrad_grid(long long M) {
 extern "C" int combat_wgrad_cin3(const float* x, const void* dy, int dy_dtype, float* dw, float* db, int N, int H, int W, int Co,
                                  int stride, void* stream) {
   COMBAT_ARG(x && dy && dw, 0);
-  COMBAT_ARG((Co == 32 || Co == 64 || Co == 128) && (stride == 1 || stride == 2), 8);
+  COMBAT_ARG(stride == 1 || stride == 2, 9);
+  if (Co != 64) {  // other widths: generic strided kernel (not on the measured path)
+    combat_conv_desc d;
+    memset(&d, 0, sizeof(d));
+    const int Ho_ = (H + 2 - 3) / stride + 1, Wo_ = (W + 2 - 3) / stride + 1;
+    d.in = x; d.bias = db;
+    d.N = N; d.Hi = H; d.Wi = W; d.Ci = 3; d.Ho = Ho_; d.Wo = Wo_; d.Co = Co; d.KH = d.KW = 3; d.stride = stride; d.pad = 1; d.up = 1;
+    d.in_sn = 3LL * H * W; d.in_sc = (long long)H * W; d.in_sh = W; d.in_sw = 1;
+    d.out_sn = (long long)Ho_ * Wo_ * Co; d.out_sh = (long long)Wo_ * Co; d.out_sw = Co; d.out_sc = 1;
+    d.in_dtype = COMBAT_F32; d.w_dtype = COMBAT_F32; d.out_dtype = dy_dtype;
+    return combat_conv_wgrad_simt(&d, dy, dy_dtype, dw, stream);
+  }
   const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
   const long long M = (long long)N * Ho * Wo;
   if (M <= 0) return 0;
-  dim3 block(Co / 2, 256 / (Co / 2));
   const int grid = wgrad_grid(M);
   cudaStream_t st = (cudaStream_t)stream;
   if (dy_dtype == COMBAT_F32)
-    wgrad3_k<float, 0><<<grid, block, 0, st>>>(x, (const float*)dy, dw, db, N, H, W, Ho, Wo, Co, stride);
+    wgrad3_k<float, 0><<<grid, 256, 0, st>>>(x, (const float*)dy, dw, db, N, H, W, Ho, Wo, stride);
   else
-    wgrad3_k<bf16, 0><<<grid, block, 0, st>>>(x, (const bf16*)dy, dw, db, N, H, W, Ho, Wo, Co, stride);
+    wgrad3_k<bf16, 0><<<grid, 256, 0, st>>>(x, (const bf16*)dy, dw, db, N, H, W, Ho, Wo, stride);
   COMBAT_RETURN_LAUNCH("wgrad_cin3");
 }
 
@@ -505,12 +560,11 @@ extern "C" int combat_wgrad_cout3(const void* a, int a_dtype, const float* dz, f
   COMBAT_ARG(Ci == 64, 9);
   const long long M = (long long)N * H * W;
   if (M <= 0) return 0;
-  dim3 block(32, 8);
   const int grid = wgrad_grid(M);
   cudaStream_t st = (cudaStream_t)stream;
   if (a_dtype == COMBAT_F32)
-    wgrad3_k<float, 1><<<grid, block, 0, st>>>(dz, (const float*)a, dw, db, N, H, W, H, W, 64, 1);
+    wgrad3_k<float, 1><<<grid, 256, 0, st>>>(dz, (const float*)a, dw, db, N, H, W, H, W, 1);
   else
-    wgrad3_k<bf16, 1><<<grid, block, 0, st>>>(dz, (const bf16*)a, dw, db, N, H, W, H, W, 64, 1);
+    wgrad3_k<bf16, 1><<<grid, 256, 0, st>>>(dz, (const bf16*)a, dw, db, N, H, W, H, W, 1);
   COMBAT_RETURN_LAUNCH("wgrad_cout3");
 }
