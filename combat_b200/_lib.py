@@ -47,8 +47,8 @@ _SIGS = {
     "combat_plane_transform": ([vp, vp, vp, vp, i64, i32, i32, vp, vp], i32),
     "combat_dct32_fast": ([vp, vp, i64, i32, i32, i32, vp], i32),
     "combat_dct64_fast": ([vp, vp, i64, i32, i32, i32, vp], i32),
-    "combat_poison_blend_fwd": ([vp, vp, vp, vp, i32, i32, f32, f32, f32, vp, vp, i32, i32, i32, vp, vp, vp], i32),
-    "combat_poison_blend_bwd": ([vp, vp, vp, vp, vp, f32, f32, f32, f32, vp, i32, i32, i32, i32, vp, vp], i32),
+    "combat_poison_blend_fwd": ([vp, vp, vp, vp, i32, i32, f32, f32, f32, vp, vp, i32, i32, i32, vp, vp, vp, vp], i32),
+    "combat_poison_blend_bwd": ([vp, vp, vp, vp, vp, f32, f32, f32, f32, vp, i32, i32, i32, i32, vp, vp, vp], i32),
     "combat_cross_entropy": ([vp, vp, vp, i32, i32, f32, vp, vp, vp, vp], i32),
     "combat_sum_scale": ([vp, i32, f32, vp, vp], i32),
     "combat_sgd_nesterov": ([vp, vp, vp, i64, vp, f32, f32, i32, vp], i32),

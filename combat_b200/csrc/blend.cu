@@ -12,12 +12,14 @@ __global__ void __launch_bounds__(256) poison_blend_fwd_k(const float* __restric
                                                           int num_bd, float rate, float k0, float k1,
                                                           float* __restrict__ out, float* __restrict__ sq_partial, int C,
                                                           int H, int W, int use_smem, const float* __restrict__ taps_dev,
-                                                          const int* __restrict__ num_bd_dev) {
+                                                          const int* __restrict__ num_bd_dev,
+                                                          const float* __restrict__ taps_rows) {
   extern __shared__ float tile[];  // H*W clamped values (use_smem)
   if (taps_dev) { k0 = taps_dev[0]; k1 = taps_dev[1]; }
   if (num_bd_dev) num_bd = num_bd_dev[0];
   const int plane = blockIdx.x;
   const int r = plane / C, c = plane % C;
+  if (taps_rows) { k0 = taps_rows[2 * r]; k1 = taps_rows[2 * r + 1]; }
   const int src = perm ? perm[r] : r;
   const int HW = H * W;
   const float* xp = x + ((long long)src * C + c) * HW;
@@ -99,11 +101,13 @@ __global__ void __launch_bounds__(256) poison_blend_fwd_v4_k(const float* __rest
                                                              int num_bd, float rate, float k0, float k1,
                                                              float* __restrict__ out, float* __restrict__ sq_partial, int C,
                                                              int H, int W, const float* __restrict__ taps_dev,
-                                                             const int* __restrict__ num_bd_dev) {
+                                                             const int* __restrict__ num_bd_dev,
+                                                             const float* __restrict__ taps_rows) {
   if (taps_dev) { k0 = taps_dev[0]; k1 = taps_dev[1]; }
   if (num_bd_dev) num_bd = num_bd_dev[0];
   const int plane = blockIdx.x;
   const int r = plane / C, c = plane % C;
+  if (taps_rows) { k0 = taps_rows[2 * r]; k1 = taps_rows[2 * r + 1]; }
   const int src = perm ? perm[r] : r;
   const int HW4 = (H * W) >> 2, W4 = W >> 2;
   const float4* xp = (const float4*)(x + ((long long)src * C + c) * H * W);
@@ -174,7 +178,8 @@ __global__ void __launch_bounds__(256) poison_blend_fwd_b16_k(const float* __res
                                                               int num_bd, float rate, float k0, float k1,
                                                               float* __restrict__ out, float* __restrict__ sq_partial, int C,
                                                               int H, int W, int planes, const float* __restrict__ taps_dev,
-                                                              const int* __restrict__ num_bd_dev) {
+                                                              const int* __restrict__ num_bd_dev,
+                                                              const float* __restrict__ taps_rows) {
   if (taps_dev) { k0 = taps_dev[0]; k1 = taps_dev[1]; }
   if (num_bd_dev) num_bd = num_bd_dev[0];
   const int W4 = W >> 2, H4 = H >> 2, TPP = W4 * H4;  // threads per plane
@@ -184,6 +189,7 @@ __global__ void __launch_bounds__(256) poison_blend_fwd_b16_k(const float* __res
   const bool pvalid = plane < planes;
   const int pc = pvalid ? plane : planes - 1;
   const int r = pc / C, c = pc % C;
+  if (taps_rows) { k0 = taps_rows[2 * r]; k1 = taps_rows[2 * r + 1]; }
   const int src = perm ? perm[r] : r;
   const float4* xp = (const float4*)(x + ((long long)src * C + c) * H * W);
   float4* op = (float4*)(out + ((long long)r * C + c) * H * W);
@@ -262,9 +268,11 @@ __global__ void __launch_bounds__(256) poison_blend_bwd_k(const float* __restric
                                                           const float* __restrict__ x_bd, const float* __restrict__ g1,
                                                           const float* __restrict__ g2, float mse_scale, float rate,
                                                           float k0, float k1, float* __restrict__ dnoise, int HW, int H,
-                                                          int W, const float* __restrict__ taps_dev) {
+                                                          int W, const float* __restrict__ taps_dev, int C,
+                                                          const float* __restrict__ taps_rows) {
   extern __shared__ float gt[];  // total upstream gradient of the plane
   if (taps_dev) { k0 = taps_dev[0]; k1 = taps_dev[1]; }
+  if (taps_rows) { k0 = taps_rows[2 * (blockIdx.x / C)]; k1 = taps_rows[2 * (blockIdx.x / C) + 1]; }
   const long long base = (long long)blockIdx.x * HW;
   for (int i = threadIdx.x; i < HW; i += blockDim.x) {
     float g = g1[base + i];
@@ -298,9 +306,11 @@ __global__ void __launch_bounds__(256) poison_blend_bwd_v4_k(const float* __rest
                                                              const float* __restrict__ x_bd, const float* __restrict__ g1,
                                                              const float* __restrict__ g2, float mse_scale, float rate,
                                                              float k0, float k1, float* __restrict__ dnoise, int H, int W,
-                                                             const float* __restrict__ taps_dev) {
+                                                             const float* __restrict__ taps_dev, int C,
+                                                             const float* __restrict__ taps_rows) {
   extern __shared__ float gt[];  // total upstream gradient of the plane
   if (taps_dev) { k0 = taps_dev[0]; k1 = taps_dev[1]; }
+  if (taps_rows) { k0 = taps_rows[2 * (blockIdx.x / C)]; k1 = taps_rows[2 * (blockIdx.x / C) + 1]; }
   const int HW4 = (H * W) >> 2, W4 = W >> 2;
   const long long base4 = (long long)blockIdx.x * HW4;
   const float4* x4 = (const float4*)x + base4;
@@ -356,7 +366,7 @@ __global__ void __launch_bounds__(256) poison_blend_bwd_v4_k(const float* __rest
 extern "C" int combat_poison_blend_fwd(const float* x, const float* noise, const int* perm, const int* nperm, int rows,
                                        int num_bd, float noise_rate, float k0, float k1, float* out, float* sq_partial,
                                        int C, int H, int W, const float* taps_dev, const int* num_bd_dev,
-                                       void* stream) {
+                                       const float* taps_rows, void* stream) {
   COMBAT_ARG(x && out, 0);
   COMBAT_ARG((num_bd == 0 && !num_bd_dev) || noise, 1);
   COMBAT_ARG(H >= 2 && W >= 2 && C > 0 && num_bd >= 0 && num_bd <= rows, 5);
@@ -368,26 +378,26 @@ extern "C" int combat_poison_blend_fwd(const float* x, const float* noise, const
     if ((W & 3) == 0 && (H & 3) == 0 && tpp % 32 == 0 && tpp <= 256 && 256 % tpp == 0 && 32 % (W / 4) == 0) {
       const int planes = rows * C, ppc = 256 / tpp;
       poison_blend_fwd_b16_k<<<(planes + ppc - 1) / ppc, 256, 0, (cudaStream_t)stream>>>(
-          x, noise, perm, nperm, num_bd, noise_rate, k0, k1, out, sq_partial, C, H, W, planes, taps_dev, num_bd_dev);
+          x, noise, perm, nperm, num_bd, noise_rate, k0, k1, out, sq_partial, C, H, W, planes, taps_dev, num_bd_dev, taps_rows);
       COMBAT_RETURN_LAUNCH("poison_blend_fwd");
     }
   }
   if ((W & 3) == 0 && W <= 128 && 32 % (W / 4) == 0) {  // a row = W/4 consecutive lanes of one warp
     poison_blend_fwd_v4_k<<<rows * C, 256, 0, (cudaStream_t)stream>>>(x, noise, perm, nperm, num_bd, noise_rate, k0, k1, out,
-                                                                         sq_partial, C, H, W, taps_dev, num_bd_dev);
+                                                                         sq_partial, C, H, W, taps_dev, num_bd_dev, taps_rows);
     COMBAT_RETURN_LAUNCH("poison_blend_fwd");
   }
   if (use_smem) cudaFuncSetAttribute(poison_blend_fwd_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   poison_blend_fwd_k<<<rows * C, 256, use_smem ? smem : 0, (cudaStream_t)stream>>>(x, noise, perm, nperm, num_bd, noise_rate,
                                                                                   k0, k1, out, sq_partial, C, H, W, use_smem,
-                                                                                  taps_dev, num_bd_dev);
+                                                                                  taps_dev, num_bd_dev, taps_rows);
   COMBAT_RETURN_LAUNCH("poison_blend_fwd");
 }
 
 extern "C" int combat_poison_blend_bwd(const float* x, const float* noise, const float* x_bd, const float* g1,
                                        const float* g2, float mse_scale, float noise_rate, float k0, float k1,
                                        float* dnoise, int rows, int C, int H, int W, const float* taps_dev,
-                                       void* stream) {
+                                       const float* taps_rows, void* stream) {
   COMBAT_ARG(x && noise && x_bd && g1 && dnoise, 0);
   COMBAT_ARG(H >= 3 && W >= 3, 12);
   if (rows <= 0) return 0;
@@ -396,11 +406,11 @@ extern "C" int combat_poison_blend_bwd(const float* x, const float* noise, const
   if ((W & 3) == 0) {
     cudaFuncSetAttribute(poison_blend_bwd_v4_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     poison_blend_bwd_v4_k<<<rows * C, 256, smem, (cudaStream_t)stream>>>(x, noise, x_bd, g1, g2, mse_scale, noise_rate, k0, k1,
-                                                                         dnoise, H, W, taps_dev);
+                                                                         dnoise, H, W, taps_dev, C, taps_rows);
     COMBAT_RETURN_LAUNCH("poison_blend_bwd");
   }
   cudaFuncSetAttribute(poison_blend_bwd_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   poison_blend_bwd_k<<<rows * C, 256, smem, (cudaStream_t)stream>>>(x, noise, x_bd, g1, g2, mse_scale, noise_rate, k0, k1,
-                                                                    dnoise, H * W, H, W, taps_dev);
+                                                                    dnoise, H * W, H, W, taps_dev, C, taps_rows);
   COMBAT_RETURN_LAUNCH("poison_blend_bwd");
 }

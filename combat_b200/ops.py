@@ -159,8 +159,9 @@ def gaussian_taps(sigma: float) -> tuple[float, float]:
 
 
 def poison_blend_fwd(x, noise, perm, num_bd, noise_rate, taps, out=None, sq_partial=None, nperm=None, taps_dev=None,
-                     num_bd_dev=None):
-    """taps = (k0, k1) host floats, or pass taps_dev / num_bd_dev (device tensors) for graph-captured steps."""
+                     num_bd_dev=None, taps_rows=None):
+    """taps = (k0, k1) host floats, or pass taps_dev / num_bd_dev (device tensors) for graph-captured steps;
+    taps_rows: device float32 [rows, 2] per-row taps (multilabel step: one sigma per class chunk)."""
     x = _contig(x)
     B, Cc, H, W = x.shape
     rows = B if perm is None else perm.numel()
@@ -168,17 +169,18 @@ def poison_blend_fwd(x, noise, perm, num_bd, noise_rate, taps, out=None, sq_part
         out = torch.empty((rows, Cc, H, W), dtype=torch.float32, device=x.device)
     k0, k1 = taps if taps is not None else (1.0, 0.0)
     check(lib.combat_poison_blend_fwd(_p(x), _p(noise), _p(perm), _p(nperm), rows, num_bd, noise_rate, k0, k1,
-                                      _p(out), _p(sq_partial), Cc, H, W, _p(taps_dev), _p(num_bd_dev), _s()), "poison_blend_fwd")
+                                      _p(out), _p(sq_partial), Cc, H, W, _p(taps_dev), _p(num_bd_dev), _p(taps_rows), _s()),
+          "poison_blend_fwd")
     return out
 
 
-def poison_blend_bwd(x, noise, x_bd, g1, g2, mse_scale, noise_rate, taps, out=None, taps_dev=None):
+def poison_blend_bwd(x, noise, x_bd, g1, g2, mse_scale, noise_rate, taps, out=None, taps_dev=None, taps_rows=None):
     B, Cc, H, W = x.shape
     if out is None:
         out = torch.empty_like(x)
     k0, k1 = taps if taps is not None else (1.0, 0.0)
     check(lib.combat_poison_blend_bwd(_p(x), _p(noise), _p(x_bd), _p(g1), _p(g2), mse_scale, noise_rate, k0, k1,
-                                      _p(out), B, Cc, H, W, _p(taps_dev), _s()), "poison_blend_bwd")
+                                      _p(out), B, Cc, H, W, _p(taps_dev), _p(taps_rows), _s()), "poison_blend_bwd")
     return out
 
 

@@ -58,16 +58,18 @@ int combat_dct64_fast(const void* in, float* out, long long planes, int kind, in
  * sq_partial (optional, rows*C floats): per-plane sum((out-x[perm[r]])^2) for the MSE term (:234).
  * taps_dev (optional, 2 floats) / num_bd_dev (optional, 1 int): device-resident overrides of k0,k1 / num_bd, so that a
  * captured CUDA graph follows the per-iteration sigma draw and poison count.
+ * taps_rows (optional, rows*2 floats on device): per-ROW taps -- train_generator_multilabel.py:67-75,203-220 blurs every
+ * class chunk of the batch with its own sigma draw.
  */
 int combat_poison_blend_fwd(const float* x, const float* noise, const int* perm, const int* nperm, int rows, int num_bd,
                             float noise_rate, float k0, float k1, float* out, float* sq_partial, int C, int H, int W,
-                            const float* taps_dev, const int* num_bd_dev, void* stream);
+                            const float* taps_dev, const int* num_bd_dev, const float* taps_rows, void* stream);
 /* backward of blur(clamp(x + noise*rate)) w.r.t. noise (G-step, train_generator.py:225-226,254):
  *   g = g1 + g2 + mse_scale * (x_bd - x);  dnoise = rate * [|x + noise*rate| <= 1] * blur^T(g)
  * g2 may be NULL.  mse_scale = 2 * L2_weight / numel. */
 int combat_poison_blend_bwd(const float* x, const float* noise, const float* x_bd, const float* g1, const float* g2,
                             float mse_scale, float noise_rate, float k0, float k1, float* dnoise, int rows, int C, int H,
-                            int W, const float* taps_dev, void* stream);
+                            int W, const float* taps_dev, const float* taps_rows, void* stream);
 
 /* ---------------------------------------------------------------- losses
  * torch.nn.CrossEntropyLoss (mean) forward+backward and argmax metrics, train_generator.py:207,231,251,262-267.

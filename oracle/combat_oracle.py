@@ -450,6 +450,114 @@ def alternated_step(state: dict, x: torch.Tensor, y: torch.Tensor, opt, with_met
 
 
 # --------------------------------------------------------------------------
+# multilabel variant (train_generator_multilabel.py:160-242): conditional generator, class-chunked G-step
+# --------------------------------------------------------------------------
+
+
+def make_bd_cond(netG_p, x, labels, opt, sigma):
+    """create_inputs_bd (train_generator_multilabel.py:66-75) with the sigma drawn by the caller."""
+    noise_raw = unet_forward(netG_p, x, labels, opt.num_classes)
+    noise = low_freq(noise_raw, opt.input_height, opt.ratio)
+    x_bd = torch.clamp(x + noise * opt.noise_rate, -1, 1)
+    return gaussian_blur(x_bd, sigma), noise, noise_raw
+
+
+def multilabel_chunks(bs: int, num_classes: int):
+    """:203-211 -- contiguous chunks of ps rows, chunk ci is pushed towards class ci."""
+    ps = int((bs - 1) / num_classes) + 1
+    out = []
+    for ci in range(num_classes):
+        si, ei = ci * ps, min(ci * ps + ps, bs)
+        if si >= ei:
+            break
+        out.append((ci, si, ei))
+    return out
+
+
+def alternated_step_multilabel(state: dict, x: torch.Tensor, y: torch.Tensor, opt, with_metrics: bool = True) -> dict:
+    """One iteration of train_generator_multilabel.train() (:160-242), identity PostTensorTransform.
+    RNG order: numpy rand(bs) (:171) -> torch uniform for the C-step blur (only if num_bd > 0, :74) -> one torch uniform
+    per class chunk of the G-step (:219 via create_inputs_bd)."""
+    fwdC = CLASSIFIERS[opt.classifier]
+    netC_p, netC_b, netG_p = state["netC_p"], state["netC_b"], state["netG_p"]
+    clean_p, clean_b = state["clean_p"], state["clean_b"]
+    bs = x.shape[0]
+    out = {}
+    # ---------------- C-step (:163-191)
+    num_bd = int(np.sum(np.random.rand(bs) < opt.pc))  # :171
+    out["num_bd"] = num_bd
+    for t in netC_p.values():
+        t.requires_grad_(True)
+        t.grad = None
+    with torch.no_grad():
+        if num_bd > 0:
+            sigma_c = draw_sigma(*opt.sigma)
+            x_bd_c, _, _ = make_bd_cond(netG_p, x[:num_bd], y[:num_bd], opt, sigma_c)  # conditioned on the TRUE labels
+        else:
+            sigma_c, x_bd_c = None, x[:0]
+    out["sigma_c"] = sigma_c
+    total_x = torch.cat([x_bd_c, x[num_bd:]], dim=0)  # :178
+    logits_c = fwdC(netC_p, netC_b, total_x, True)
+    loss_c = F.cross_entropy(logits_c, y)  # :180-183, labels unchanged
+    loss_c.backward()
+    out["total_x"], out["logits_c"], out["loss_c"] = total_x.detach(), logits_c.detach().clone(), float(loss_c.detach())
+    gradsC = {k: v.grad for k, v in netC_p.items()}
+    with torch.no_grad():
+        for t in netC_p.values():
+            t.requires_grad_(False)
+        sgd_nesterov_step(netC_p, gradsC, state["momC"], opt.lr_C)
+        if with_metrics:
+            out["clean_preds"] = fwdC(clean_p, clean_b, x, False)  # :191
+    # ---------------- G-step (:193-232)
+    for t in netG_p.values():
+        t.requires_grad_(True)
+        t.grad = None
+    with torch.no_grad():
+        if with_metrics:
+            out["pred_clean"] = fwdC(netC_p, netC_b, x, False)  # :199
+    parts, bd_t, sigmas = [], [], []
+    for ci, si, ei in multilabel_chunks(bs, opt.num_classes):
+        tmp = y[si:ei] * 0 + ci
+        sg = draw_sigma(*opt.sigma)
+        sigmas.append(sg)
+        xb, _, _ = make_bd_cond(netG_p, x[si:ei], tmp, opt, sg)
+        parts.append(xb)
+        bd_t.append(tmp)
+    x_bd = torch.cat(parts, 0)
+    bd_targets = torch.cat(bd_t, 0)
+    out["sigmas_g"] = sigmas
+    pred_bd = fwdC(netC_p, netC_b, x_bd, False)  # :224
+    loss_ce = F.cross_entropy(pred_bd, bd_targets)
+    loss_l2 = F.mse_loss(x_bd, x)
+    clean_model_preds = fwdC(clean_p, clean_b, x_bd, False)  # :235
+    clean_model_loss = F.cross_entropy(clean_model_preds, y)
+    loss = loss_ce + opt.L2_weight * loss_l2 + opt.clean_model_weight * clean_model_loss  # :239
+    loss.backward()
+    gradsG = {k: v.grad for k, v in netG_p.items()}
+    with torch.no_grad():
+        for t in netG_p.values():
+            t.requires_grad_(False)
+        sgd_nesterov_step(netG_p, gradsG, state["momG"], opt.lr_G)
+        if with_metrics and state.get("netF_p") is not None:
+            inputs_F = dct_2d(((x_bd.detach() + 1) / 2 * 255).byte())  # :230
+            out["inputs_F"] = inputs_F
+            out["pred_F"] = frequency_model_forward(state["netF_p"], state["netF_b"], inputs_F)
+    out.update(x_bd=x_bd.detach(), pred_bd=pred_bd.detach(), clean_model_preds=clean_model_preds.detach(),
+               loss_ce=float(loss_ce.detach()), loss_l2=float(loss_l2.detach()), clean_model_loss=float(clean_model_loss.detach()),
+               loss_g=float(loss.detach()), bd_targets=bd_targets)
+    if with_metrics:  # :247-252
+        am = lambda t: torch.argmax(t, dim=1)
+        out["n_clean_correct"] = int((am(out["pred_clean"]) == y).sum())
+        out["n_bd_correct"] = int((am(out["pred_bd"]) == bd_targets).sum())
+        out["n_clean_model_correct"] = int((am(out["clean_preds"]) == y).sum())
+        out["n_clean_model_bd_ba"] = int((am(out["clean_model_preds"]) == y).sum())
+        out["n_clean_model_bd_asr"] = int((am(out["clean_model_preds"]) == bd_targets).sum())
+        if "pred_F" in out:
+            out["n_F_correct"] = int((am(out["pred_F"]) == 1).sum())
+    return out
+
+
+# --------------------------------------------------------------------------
 # deterministic random-init state (shapes of the reference modules), no reference import
 # --------------------------------------------------------------------------
 

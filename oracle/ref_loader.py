@@ -52,6 +52,14 @@ def load_reference(ref: str = REF):
     return train_generator, config
 
 
+def load_reference_multilabel(ref: str = REF):
+    """train_generator_multilabel.py of the reference (same stand-ins)."""
+    load_reference(ref)
+    import train_generator_multilabel
+
+    return train_generator_multilabel
+
+
 class NullWriter:
     """tf_writer stand-in for train()."""
 

@@ -257,8 +257,74 @@ def gen_step(name, B, n_batches, seed):
     save(name, **out)
 
 
+def gen_mstep(name, dataset, B, n_batches, seed):
+    """One or more iterations of the UNMODIFIED train_generator_multilabel.train() (reference :142-318).
+    cifar10: models from the reference's own get_model; celeba: get_model passes an unknown keyword to CUnetGeneratorv1
+    (TypeError as shipped), so the same classes are constructed here in get_model's order."""
+    from oracle.ref_loader import load_reference_multilabel
+    tm = load_reference_multilabel()
+    opt = get_opt()
+    opt.dataset = dataset
+    if dataset == "cifar10":
+        opt.input_height = opt.input_width = 32
+        opt.input_channel, opt.num_classes = 3, 10
+    else:
+        opt.input_height = opt.input_width = 64
+        opt.input_channel, opt.num_classes = 3, 8
+    seed_all(seed)
+    if dataset == "cifar10":
+        netC, optC, schC, netG, optG, schG, netF, clean = tm.get_model(opt)
+    else:
+        netC, clean = ResNet18(num_classes=8), ResNet18(num_classes=8)
+        netG = CUnetGeneratorv1(opt)
+        netF = FrequencyModel(num_classes=2, n_input=3, input_size=64)
+        optC = torch.optim.SGD(netC.parameters(), opt.lr_C, momentum=0.9, weight_decay=5e-4, nesterov=True)
+        schC = torch.optim.lr_scheduler.MultiStepLR(optC, opt.schedulerC_milestones, opt.schedulerC_lambda)
+        optG = torch.optim.SGD(netG.parameters(), opt.lr_C * 0.1, momentum=0.9, weight_decay=5e-4, nesterov=True)
+        schG = torch.optim.lr_scheduler.MultiStepLR(optG, opt.schedulerC_milestones, opt.schedulerC_lambda)
+    netF.eval()
+    clean.eval()
+    H = opt.input_height
+    batches = [(torch.rand(B, 3, H, H) * 2 - 1, torch.randint(0, opt.num_classes, (B,))) for _ in range(n_batches)]
+    sd0 = {n: {k: v.clone() for k, v in m.state_dict().items()} for n, m in (("netC", netC), ("netG", netG), ("clean", clean), ("netF", netF))}
+    rec = Recorder(netC, netG, clean, netF)
+    with rec:
+        tm.train(netC, optC, schC, netG, optG, schG, netF, clean, batches, None, None, NullWriter(), 1, opt)
+    torch.autograd.set_detect_anomaly(False)
+    out = {"seed": seed, "B": B, "n_batches": n_batches, "sigmas": np.array(rec.sigmas), "num_classes": opt.num_classes}
+    out["loss_kinds"] = np.array([k for k, _ in rec.losses])
+    out["loss_values"] = np.array([v for _, v in rec.losses])
+    # module calls per iteration: netG [C-step rows (skipped by the hook? no: called even when empty)] + one per class chunk;
+    # netC [train total_x, eval x, eval x_bd]; clean [x, x_bd]; netF [dct]
+    gi = 0
+    for i, (x, y) in enumerate(batches):
+        out["y_%d" % i] = y
+        g_c_in = rec.calls["netG"][gi][0]
+        out["num_bd_%d" % i] = g_c_in.shape[0]
+        n_chunks = len([1 for ci in range(opt.num_classes) if ci * (int((B - 1) / opt.num_classes) + 1) < B])
+        gi += 1 + n_chunks
+        out["logits_c_%d" % i] = rec.calls["netC"][3 * i][1]
+        out["total_x_head_%d" % i] = rec.calls["netC"][3 * i][0][:4]
+        out["pred_clean_%d" % i] = rec.calls["netC"][3 * i + 1][1]
+        out["pred_bd_%d" % i] = rec.calls["netC"][3 * i + 2][1]
+        out["x_bd_%d" % i] = rec.calls["netC"][3 * i + 2][0]
+        out["clean_preds_%d" % i] = rec.calls["clean"][2 * i][1]
+        out["clean_model_preds_%d" % i] = rec.calls["clean"][2 * i + 1][1]
+        out["pred_F_%d" % i] = rec.calls["netF"][i][1]
+    # the initial weights are NOT stored (3 x 11 M floats): the oracle's init_* functions reproduce them from the same seed
+    # and construction order; these digests pin that
+    for n in ("netC", "netG", "clean", "netF"):
+        out["init_digest_" + n] = tensor_digest(torch.cat([v.flatten().double() for k, v in sd0[n].items() if torch.is_floating_point(v)]))
+    param_summary("netC_", sd0["netC"], netC.state_dict(), out, full_keys=("conv1.weight", "linear.weight", "linear.bias"))
+    param_summary("netG_", sd0["netG"], netG.state_dict(), out, full_keys=("conv0_0.weight", "conv0_1.weight", "upconv0_0.bias"))
+    save(name, **out)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["dct", "modules", "step"]
+    if "mstep" in which:
+        gen_mstep("mstep_cifar_b24x2.npz", "cifar10", 24, 2, 3)   # 10 classes, chunks of 3 (last chunk short: 24 = 7*3+3)
+        gen_mstep("mstep_celeba_b12.npz", "celeba", 12, 1, 4)     # CelebA shape 64x64, 8 classes, ResNet18 + CUnetGeneratorv1
     if "dct" in which:
         gen_dct()
     if "modules" in which:
