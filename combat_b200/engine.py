@@ -51,6 +51,8 @@ class StepPlan:
     sigma_g: float
     taps_c: tuple
     taps_g: tuple
+    taps_rows: np.ndarray | None = None   # multilabel: float32 [B, 2] per-row blur taps (one sigma per class chunk)
+    sigmas_g: list | None = None          # multilabel: the per-chunk sigma draws
 
 
 def create_targets_bd_np(targets: np.ndarray, opt) -> np.ndarray:
@@ -81,6 +83,41 @@ def make_plan(targets_host, opt) -> StepPlan:
     return StepPlan(perm, num_bd, trg, ntrg, bd, total_y, sigma_c, sigma_g, taps_c, ops.gaussian_taps(sigma_g))
 
 
+def multilabel_chunks(bs: int, num_classes: int):
+    """train_generator_multilabel.py:203-211 -- contiguous chunks of ps rows, chunk ci is pushed towards class ci."""
+    ps = int((bs - 1) / num_classes) + 1
+    out = []
+    for ci in range(num_classes):
+        si, ei = ci * ps, min(ci * ps + ps, bs)
+        if si >= ei:
+            break
+        out.append((ci, si, ei))
+    return out
+
+
+def make_plan_multilabel(targets_host, opt) -> StepPlan:
+    """train_generator_multilabel.py:171,74,203-220 -- numpy rand(bs) for the poison count (the FIRST num_bd rows are
+    poisoned, labels unchanged), one torch CPU uniform for the C-step blur (only when num_bd > 0), then one per class
+    chunk of the G-step, in chunk order."""
+    y = np.asarray(targets_host, dtype=np.int64)
+    bs = y.shape[0]
+    num_bd = int(np.sum(np.random.rand(bs) < opt.pc))
+    sigma_c, taps_c = None, (1.0, 0.0)
+    if num_bd > 0:
+        sigma_c = torch.empty(1).uniform_(opt.sigma[0], opt.sigma[1]).item()
+        taps_c = ops.gaussian_taps(sigma_c)
+    bd = np.zeros(bs, dtype=np.int64)
+    taps_rows = np.zeros((bs, 2), dtype=np.float32)
+    sigmas = []
+    for ci, si, ei in multilabel_chunks(bs, opt.num_classes):
+        sg = torch.empty(1).uniform_(opt.sigma[0], opt.sigma[1]).item()
+        sigmas.append(sg)
+        bd[si:ei] = ci
+        taps_rows[si:ei] = ops.gaussian_taps(sg)
+    return StepPlan(np.arange(bs, dtype=np.int32), num_bd, np.arange(bs), np.arange(0), bd, y.copy(), sigma_c,
+                    sigmas[0], taps_c, (float(taps_rows[0, 0]), float(taps_rows[0, 1])), taps_rows, sigmas)
+
+
 class AlternatedStep:
     """Owns netC / clean_model / netG / netF and runs alternated iterations on one GPU.
 
@@ -89,7 +126,7 @@ class AlternatedStep:
     refreshing the small per-iteration parameter block (perm, targets, num_bd, blur taps, learning rates)."""
 
     def __init__(self, opt=None, device="cuda", dtype=torch.bfloat16, classifier="preact_resnet18", with_metrics=True,
-                 use_tc=True, cond_classes=0, grad_hook=None, buf_hook=None, nets=None):
+                 use_tc=True, cond_classes=0, grad_hook=None, buf_hook=None, nets=None, multilabel=False):
         self.opt = opt or default_opt()
         o = self.opt
         self.device = torch.device(device)
@@ -105,6 +142,10 @@ class AlternatedStep:
             self.clean = Classifier(classifier, o.num_classes, o.input_channel, H, **mk)
             self.netG = Generator(o.input_channel, 64, cond_classes, **mk)
             self.netF = FrequencyDetector(2, o.input_channel, H, device=self.device, dtype=dtype) if (with_metrics and H in (32, 64)) else None
+        # multilabel=True: the step of train_generator_multilabel.py (conditional generator, class-chunked G-step)
+        self.multilabel = bool(multilabel)
+        if self.multilabel and not self.netG.cond:
+            raise ValueError("the multilabel step needs the conditional generator (cond_classes = num_classes)")
         self.keep = int(H * o.ratio)
         self.lr_C = torch.full((1,), float(o.lr_C), dtype=torch.float32, device=self.device)
         self.lr_G = torch.full((1,), float(o.lr_G), dtype=torch.float32, device=self.device)
@@ -151,6 +192,8 @@ class AlternatedStep:
         b["num_bd"] = torch.zeros(1, dtype=torch.int32, device=dev)
         b["taps_c"] = torch.zeros(2, dtype=torch.float32, device=dev)
         b["taps_g"] = torch.zeros(2, dtype=torch.float32, device=dev)
+        b["taps_rows"] = torch.zeros((B, 2), dtype=torch.float32, device=dev) if self.multilabel else None
+        b["h_taps_rows"] = torch.zeros((B, 2), dtype=torch.float32).pin_memory() if self.multilabel else None
         b["ones"] = torch.ones(B, dtype=torch.int64, device=dev)
         b["sq_partial"] = torch.empty(B * o.input_channel, dtype=torch.float32, device=dev)
         b["losses"] = torch.zeros(8, dtype=torch.float32, device=dev)   # loss_c, loss_ce, loss_l2, clean_model_loss
@@ -182,6 +225,9 @@ class AlternatedStep:
         b["taps_c"].copy_(b["h_small"][0:2], non_blocking=True)
         b["taps_g"].copy_(b["h_small"][2:4], non_blocking=True)
         b["num_bd"].copy_(b["h_nbd"], non_blocking=True)
+        if self.multilabel:
+            b["h_taps_rows"].copy_(torch.from_numpy(plan.taps_rows))
+            b["taps_rows"].copy_(b["h_taps_rows"], non_blocking=True)
 
     # ------------------------------------------------------------ the step
     # The iteration is three launch phases separated by the data-parallel exchange points (combat_b200.parallel):
@@ -194,10 +240,19 @@ class AlternatedStep:
         o = self.opt
         x = b["x"]
         losses, counts = b["losses"], b["counts"]
-        noise_raw, ctxG = self.netG.forward(x, b.get("labels_g"), save=True)                 # :189 and :223, once
-        noise = ops.plane_op(noise_raw, "lowfreq", keep=self.keep)                          # :190-191 / :224
-        total_x = ops.poison_blend_fwd(x, noise, b["perm"], 0, o.noise_rate, None, taps_dev=b["taps_c"],
-                                       num_bd_dev=b["num_bd"])                                # :192-195
+        if self.multilabel:
+            # C-step trigger: conditioned on the TRUE labels (train_generator_multilabel.py:172-176); the G-step runs its own
+            # forward conditioned on the chunk classes, so nothing is saved here
+            noise_c_raw, _ = self.netG.forward(x, b["y"], save=False)
+            noise_c = ops.plane_op(noise_c_raw, "lowfreq", keep=self.keep)
+            total_x = ops.poison_blend_fwd(x, noise_c, None, 0, o.noise_rate, None, taps_dev=b["taps_c"],
+                                           num_bd_dev=b["num_bd"])                            # first num_bd rows, :178
+            noise_raw = ctxG = noise = None
+        else:
+            noise_raw, ctxG = self.netG.forward(x, None, save=True)                          # :189 and :223, once
+            noise = ops.plane_op(noise_raw, "lowfreq", keep=self.keep)                      # :190-191 / :224
+            total_x = ops.poison_blend_fwd(x, noise, b["perm"], 0, o.noise_rate, None, taps_dev=b["taps_c"],
+                                           num_bd_dev=b["num_bd"])                            # :192-195
         logits_c, ctxC = self.netC.forward(total_x, train=True, save=True)                   # :205
         _, dlog, _ = ops.cross_entropy(logits_c, b["total_y"], 1.0, True, loss_out=losses[0:1], counts_out=counts[0:2])
         self.netC.zero_grad()                                                                # :179
@@ -215,8 +270,12 @@ class AlternatedStep:
             clean_preds, _ = self.clean.forward(x, train=False, save=False)                  # :214
             ops.cross_entropy(clean_preds, y, 1.0, False, loss_out=losses[4:5], counts_out=counts[2:4])
             st["clean_preds"] = clean_preds
+        if self.multilabel:                                                                  # multilabel :203-221
+            noise_raw, ctxG = self.netG.forward(x, b["bd_targets"], save=True)
+            noise = ops.plane_op(noise_raw, "lowfreq", keep=self.keep)
+            st.update(noise_raw=noise_raw, noise=noise, ctxG=ctxG)
         x_bd = ops.poison_blend_fwd(x, noise, None, B, o.noise_rate, None, sq_partial=b["sq_partial"],
-                                    taps_dev=b["taps_g"])                                     # :225-226
+                                    taps_dev=b["taps_g"], taps_rows=b["taps_rows"])          # :225-226
         ops.sum_scale(b["sq_partial"], 1.0 / numel, out=losses[2:3])                         # :234
         if self.with_metrics:
             pred_clean, _ = self.netC.forward(x, train=False, save=False)                    # :227
@@ -232,7 +291,7 @@ class AlternatedStep:
         g2 = self.clean.backward(ctxK, dl2, need_wgrad=False, need_dx=True)
         del ctxK
         dnoise = ops.poison_blend_bwd(x, noise, x_bd, g1, g2, 2.0 * o.L2_weight / numel, o.noise_rate, None,
-                                      taps_dev=b["taps_g"])
+                                      taps_dev=b["taps_g"], taps_rows=b["taps_rows"])
         dnoise_raw = ops.plane_op(dnoise, "lowfreq", keep=self.keep)                          # P is symmetric
         self.netG.zero_grad()                                                                # :220
         self.netG.backward(st.pop("ctxG"), dnoise_raw)                                       # :254
@@ -279,7 +338,7 @@ class AlternatedStep:
         """One alternated iteration.  x_dev: float32 NCHW tensor already on the device (or a pinned host tensor,
         which is copied asynchronously); y_host: host labels.  Returns {'losses': dev[8], 'counts': dev[16]}."""
         if plan is None:
-            plan = make_plan(y_host, self.opt)
+            plan = make_plan_multilabel(y_host, self.opt) if self.multilabel else make_plan(y_host, self.opt)
         B = len(plan.perm)
         b = self._ensure_bufs(B)
         b["x"].copy_(x_dev, non_blocking=True)

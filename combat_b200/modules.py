@@ -20,10 +20,10 @@ def default_dtype():
 
 class _NetFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, mod, x, labels, *params):
+    def forward(ctx, mod, x, labels, need_grad, *params):
+        # need_grad is decided by the caller: grad mode is always OFF inside autograd.Function.forward
         net = mod.net
         net.prep_weights()  # parameters may have been updated in place by an external optimiser
-        need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
         if isinstance(net, nets.Generator):
             y, c = net.forward(x.contiguous().float(), labels, save=need_grad)
         elif isinstance(net, nets.FrequencyDetector):
@@ -51,7 +51,13 @@ class _NetFn(torch.autograd.Function):
         else:
             dx = net.backward(ctx.c, dy, need_wgrad=ctx.wgrad, need_dx=ctx.xgrad)
         grads = [net.store.g(n).clone() if (p.requires_grad and ctx.wgrad) else None for n, p in mod._plist]
-        return (None, dx, None, *grads)
+        return (None, dx, None, None, *grads)
+
+
+def _run(mod, x, labels):
+    params = [p for _, p in mod._plist]
+    need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+    return _NetFn.apply(mod, x, labels, need_grad, *params)
 
 
 class _KernelModule(nn.Module):
@@ -136,7 +142,7 @@ class ClassifierModule(_KernelModule):
         self.net.prep_weights()
 
     def forward(self, x):
-        y = _NetFn.apply(self, x, None, *[p for _, p in self._plist])
+        y = _run(self, x, None)
         if self.training:
             for n, b in self.named_buffers():
                 if n.endswith("num_batches_tracked"):
@@ -187,7 +193,7 @@ class UnetGenerator(_GeneratorModule):
     def forward(self, x):
         if x.shape[0] == 0:
             return x.new_empty(x.shape)
-        return _NetFn.apply(self, x, None, *[p for _, p in self._plist])
+        return _run(self, x, None)
 
 
 class CUnetGeneratorv1(_GeneratorModule):
@@ -198,7 +204,7 @@ class CUnetGeneratorv1(_GeneratorModule):
         super().__init__(opt, in_channels, nf, use_bias, out_channel, opt.num_classes, **kw)
 
     def forward(self, x, y):
-        return _NetFn.apply(self, x, y.contiguous(), *[p for _, p in self._plist])
+        return _run(self, x, y.contiguous())
 
 
 class FrequencyModel(_KernelModule):

@@ -1,0 +1,119 @@
+"""GPU tests of the reference-facing surface (the names a COMBAT user imports): get_model / train / modules / dct."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+class _Writer:
+    def __init__(self):
+        self.scalars = []
+
+    def add_scalars(self, tag, d, epoch):
+        self.scalars.append((tag, dict(d), epoch))
+
+    def add_image(self, *a, **k):
+        pass
+
+
+def _opt(extra=()):
+    from combat_b200 import config
+    opt = config.get_arguments().parse_args(["--device", "cuda", "--post_transform_option", "no_use", *extra])
+    opt.input_height = opt.input_width = 32
+    opt.input_channel = 3
+    return opt
+
+
+def test_train_reproduces_the_reference_known_answer_vector(golden):
+    """SURVEY 8c-4 through the public API: seed the three RNGs, get_model(opt) (construction order fixes the init stream),
+    draw the batch, one train() call -- poison selection, losses and one-step updates of the unmodified reference."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from combat_b200 import train_generator as tg
+    g = golden("step_b128.npz")
+    opt = _opt(["--dtype", "fp32", "--no_graph", "--log_every", "1"])
+    torch.manual_seed(0)
+    np.random.seed(0)
+    random.seed(0)
+    netC, optC, schC, netG, optG, schG, netF, clean = tg.get_model(opt)
+    x = torch.rand(128, 3, 32, 32) * 2 - 1
+    y = torch.randint(0, 10, (128,))
+    assert np.array_equal(y.numpy(), g["y_0"])          # same RNG stream consumed by the constructors as the reference's
+    sd0 = {n: {k: v.detach().clone().cpu() for k, v in m.state_dict().items()} for n, m in (("netC_", netC), ("netG_", netG))}
+    w = _Writer()
+    tg.train(netC, optC, schC, netG, optG, schG, netF, clean, [(x, y)], w, 1, opt)
+    torch.cuda.synchronize()
+    assert len(w.scalars) == 1 and "L2 Loss" in w.scalars[0][1]
+    # losses: train() reports sums over iterations / total_sample, exactly like the reference's avg_loss_l2
+    vals = g["loss_values"]
+    assert abs(w.scalars[0][1]["L2 Loss"] * 128 - vals[2]) < 2e-6
+    for pre, mod in (("netC_", netC), ("netG_", netG)):
+        sd = mod.state_dict()
+        for n, v0 in sd0[pre].items():
+            if not torch.is_floating_point(v0) or (pre + "dnorm_" + n) not in g.files:
+                continue
+            dead = pre == "netG_" and n.endswith("bias") and n not in ("conv0_0.bias", "upconv0_0.bias")
+            if dead:
+                continue
+            d = float((sd[n].detach().cpu() - v0).double().norm())
+            ref = g[pre + "dnorm_" + n][0]
+            assert abs(d - ref) <= 2e-2 * ref + 1e-12, (pre, n, d, ref)
+    # schedulers stepped once, momentum buffers exposed through the torch optimisers, BN counters advanced
+    assert schC.last_epoch == 1 and schG.last_epoch == 1
+    p0 = next(iter(netC.parameters()))
+    assert "momentum_buffer" in optC.state[p0] and float(optC.state[p0]["momentum_buffer"].abs().sum()) > 0
+    assert int(netC.state_dict()["layer1.0.bn1.num_batches_tracked"]) == 1
+
+
+def test_modules_autograd_and_state_dict_roundtrip():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from combat_b200.classifier_models import PreActResNet18
+    from combat_b200.networks.models import UnetGenerator
+    from combat_b200.utils.dct import dct_2d, idct_2d
+    torch.manual_seed(3)
+    opt = _opt()
+    netC = PreActResNet18(dtype=torch.float32)
+    netG = UnetGenerator(opt, dtype=torch.float32)
+    x = (torch.rand(4, 3, 32, 32) * 2 - 1).cuda().requires_grad_(True)
+    netC.train()
+    loss = torch.nn.functional.cross_entropy(netC(netG(x) * 0.08 + x), torch.tensor([0, 1, 2, 3]).cuda())
+    loss.backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in netC.parameters())
+    assert all(p.grad is not None for p in netG.parameters())
+    # same function as torch's own modules fed with the same weights (the reference's definition), float32 path
+    sd = {k: v.detach().clone() for k, v in netC.state_dict().items()}
+    netC2 = PreActResNet18(dtype=torch.float32)
+    netC2.load_state_dict(sd)
+    netC.eval(); netC2.eval()
+    with torch.no_grad():
+        a, b = netC(x.detach()), netC2(x.detach())
+    assert torch.equal(a, b)
+    # reference checkpoints are plain OIHW tensors: shapes match and conv weights load from contiguous tensors
+    netC2.load_state_dict({k: v.contiguous() for k, v in sd.items()})
+    with torch.no_grad():
+        assert torch.equal(netC2(x.detach()), a)
+    z = torch.rand(6, 3, 32, 32, device="cuda") * 255
+    assert float((idct_2d(dct_2d(z)) - z).abs().max()) < 1e-3
+    with pytest.raises(RuntimeError):
+        dct_2d(z.cpu())
+
+
+def test_multilabel_train_api_runs_with_graph_replay():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from combat_b200 import train_generator_multilabel as tm
+    opt = _opt(["--log_every", "2"])
+    torch.manual_seed(1)
+    np.random.seed(1)
+    netC, optC, schC, netG, optG, schG, netF, clean = tm.get_model(opt)
+    assert optG.param_groups[0]["lr"] == pytest.approx(opt.lr_C * 0.1)
+    g = torch.Generator().manual_seed(0)
+    data = [(torch.rand(32, 3, 32, 32, generator=g) * 2 - 1, torch.randint(0, 10, (32,), generator=g)) for _ in range(4)]
+    w = _Writer()
+    tm.train(netC, optC, schC, netG, optG, schG, netF, clean, data, None, None, w, 1, opt)
+    torch.cuda.synchronize()
+    assert len(w.scalars) == 1 and all(np.isfinite(v) for v in w.scalars[0][1].values())
