@@ -194,3 +194,44 @@ def test_cuda_graph_replay_matches_eager():
         assert abs(a[0][k] - b[0][k]) < 2e-2 * max(1.0, abs(a[0][k])), k
     # atomics make the weight-gradient sums order dependent: compare, do not demand bit equality
     assert rel2(b[1], a[1]) < 1e-2 and rel2(b[2], a[2]) < 1e-2
+
+
+@pytest.mark.parametrize("name,dtype", [("fp32", torch.float32), ("bf16", torch.bfloat16)])
+def test_imagenet_shape_step_vs_oracle(name, dtype):
+    """BASELINE configs[3] shape: 3x224x224, ResNet18 (scaler-49 extension: the reference's factory raises KeyError for 224,
+    SURVEY 0) + UnetGenerator, no frequency detector (no reference for that input size).  One iteration, small batch."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from combat_b200.engine import AlternatedStep, default_opt, make_plan
+    B, S = 6, 224
+    torch.manual_seed(3)
+    gen = torch.Generator().manual_seed(31)
+    netC_p, netC_b = O.init_resnet18_state(gen, num_classes=10, scaler=49)
+    clean_p, clean_b = O.init_resnet18_state(gen, num_classes=10, scaler=49)
+    netG_p = O.init_unet_state(gen)
+    state = dict(netC_p=netC_p, netC_b=netC_b, clean_p=clean_p, clean_b=clean_b, netG_p=netG_p, netF_p=None, netF_b=None,
+                 momC={}, momG={})
+    eopt = default_opt(input_height=S, input_width=S, dataset="imagenet10")
+    eng = AlternatedStep(eopt, device="cuda", dtype=dtype, classifier="resnet18")
+    assert eng.netF is None
+    j = lambda p, b: {**p, **b}
+    eng.load_state(netC=j(netC_p, netC_b), clean=j(clean_p, clean_b), netG=netG_p)
+    x = torch.rand(B, 3, S, S, generator=gen) * 2 - 1
+    y = torch.tensor([0, 3, 0, 5, 0, 7])
+    oopt = O.default_opt(input_height=S, input_width=S, classifier="resnet18")
+    np.random.seed(2)
+    torch.manual_seed(2)
+    r = O.alternated_step(state, x, y, oopt)
+    np.random.seed(2)
+    torch.manual_seed(2)
+    plan = make_plan(y.numpy(), eng.opt)
+    assert plan.num_bd == r["num_bd"] and plan.sigma_g == r["sigma_g"] and plan.sigma_c == r["sigma_c"]
+    out = eng.step(x.cuda(), y.numpy(), plan, keep_debug=True)
+    s = AlternatedStep.unpack(out)
+    d = out["debug"]
+    fp32 = dtype == torch.float32
+    for k in ("noise", "x_bd", "total_x", "logits_c", "pred_bd", "clean_model_preds"):
+        e = rel(d[k], r[k]) if fp32 else rel2(d[k], r[k])
+        assert e < (2e-4 if fp32 else 6e-2), (k, e)
+    for k in ("loss_c", "loss_ce", "loss_l2", "clean_model_loss"):
+        assert abs(s[k] - r[k]) < (5e-5 if fp32 else 2e-2) * max(1.0, abs(r[k])), (k, s[k], r[k])
