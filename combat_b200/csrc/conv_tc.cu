@@ -317,8 +317,10 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* stg_base
         if (p.act == 2) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            f[i].x = f[i].x > 0.f ? f[i].x : expm1f(f[i].x); f[i].y = f[i].y > 0.f ? f[i].y : expm1f(f[i].y);
-            f[i].z = f[i].z > 0.f ? f[i].z : expm1f(f[i].z); f[i].w = f[i].w > 0.f ? f[i].w : expm1f(f[i].w);
+            // ELU on the SFU: exp(x) - 1 has an ABSOLUTE error of ~1e-7 for x <= 0, far below the bf16 / float32-accumulator
+            // noise of the tensor-core path (the float32 CUDA-core path keeps expm1f)
+            f[i].x = f[i].x > 0.f ? f[i].x : __expf(f[i].x) - 1.f; f[i].y = f[i].y > 0.f ? f[i].y : __expf(f[i].y) - 1.f;
+            f[i].z = f[i].z > 0.f ? f[i].z : __expf(f[i].z) - 1.f; f[i].w = f[i].w > 0.f ? f[i].w : __expf(f[i].w) - 1.f;
           }
         }
         if (p.post_scale) {
@@ -1019,6 +1021,129 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_kernel(const __grid_cons
   }
 }
 
+// ---------------------------------------------------------------------------------------------- wgrad, 64 -> 64 channels, 3x3, stride 1
+// The generic weight-gradient kernel above gives every pair of filter taps its own CTAs, so the layer input is streamed
+// from L2 ten times and dY five times (986 MB for a 512 x 32 x 32 x 64 layer: L2-bandwidth bound at ~350 TFLOP/s).
+// Here one CTA owns ALL nine taps for its share of the pixels: per 128-pixel tile it loads the three horizontally shifted
+// (BH+2)-row boxes of X (as conv_tc64_kernel) and one box of dY, and accumulates the whole 576 x 64 gradient in five
+// 128 x 64 TMEM accumulators (tap pairs; the vertical taps are row offsets into the same box).  The accumulators live
+// for the whole kernel; one pass of coalesced float32 red.global.add at the end.
+struct TcW64Params {
+  int N, H, W;            // output == input plane (stride 1)
+  int BW, BH;             // tile = BH full rows
+  int tiles_h, total_tiles;
+  int copy_bytes;         // (BH+2) * BW * 128
+  float* dw;              // [64 co][9 taps][64 ci] float32
+};
+struct TcW64Maps {
+  CUtensorMap x;   // box (64, BW, BH+2, 1)
+  CUtensorMap dy;  // box (64, BW, BH, 1)
+};
+
+__global__ void __launch_bounds__(192, 1) conv_tc_wgrad64_kernel(const __grid_constant__ TcW64Maps maps, const TcW64Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int stage_bytes = 3 * p.copy_bytes + 128 * 128;  // three X copies + the 128-pixel dY box
+  uint64_t* bars = (uint64_t*)(smem + 2 * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + 2;
+  uint64_t* tfull_bar = bars + 4;
+  uint32_t* tmem_ptr_smem = (uint32_t*)(bars + 5);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.x);
+    tma_prefetch_desc(&maps.dy);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_smem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int ht = tile % p.tiles_h, n = tile / p.tiles_h;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * stage_bytes;
+        mbar_expect_tx(&full_bar[stage], stage_bytes);
+        for (int dwi = 0; dwi < 3; ++dwi) tma_load_4d(sa + dwi * p.copy_bytes, &maps.x, &full_bar[stage], 0, dwi - 1, ht * p.BH - 1, n);
+        tma_load_4d(sa + 3 * p.copy_bytes, &maps.dy, &full_bar[stage], 0, 0, ht * p.BH, n);
+        if (++stage == 2) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(TILE_M, 64, 1, 1);
+      const uint32_t row_step = (uint32_t)p.BW * 128;
+      int stage = 0;
+      uint32_t phase = 0;
+      bool first = true;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+        const uint32_t sb = sa + 3 * p.copy_bytes;
+        // taps in address order: index i = dwi*3 + dhi at sa + dwi*copy + dhi*row_step; accumulator a pairs (2a, 2a+1),
+        // the last one pairs (7, 8) again and only its upper 64 rows (tap index 8) are used
+#pragma unroll
+        for (int a = 0; a < 5; ++a) {
+          const int i0 = a < 4 ? 2 * a : 7, i1 = i0 + 1;
+          const uint32_t addr0 = sa + (i0 / 3) * p.copy_bytes + (i0 % 3) * row_step;
+          const uint32_t addr1 = sa + (i1 / 3) * p.copy_bytes + (i1 % 3) * row_step;
+          const uint64_t adesc = make_smem_desc(addr0, addr1 - addr0, 1024);
+          const uint64_t bdesc = make_smem_desc(sb, 8192, 1024);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)  // 16 pixels (K rows of 128 B) per MMA: +2048 B = +128 in the (addr >> 4) field
+            umma_bf16(tmem_base + a * 64, adesc + 128 * k, bdesc + 128 * k, idesc, !(first && k == 0));
+        }
+        first = false;
+        umma_commit(&empty_bar[stage]);
+        if (++stage == 2) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tfull_bar);
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    const long long co_stride = 9LL * 64;
+#pragma unroll 1
+    for (int a = 0; a < 5; ++a) {
+      const int i = (a < 4 ? 2 * a : 7) + (row >> 6);   // address-order tap index of this row's chunk
+      const bool used = a < 4 || row >= 64;
+      const int dwi = i / 3, dhi = i % 3;
+      float* base = p.dw + (long long)(dhi * 3 + dwi) * 64 + (row & 63);  // tap (kh = dhi, kw = dwi), ci = row & 63
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * 64;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c0, v);
+        tmem_ld_wait();
+        if (used) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) atomicAdd(base + (c0 + q) * co_stride, __uint_as_float(v[q]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 extern "C" int combat_conv_tc_wgrad(const combat_conv_tc_desc* d, const void* dy, float* dw_ohwi, void* stream) {
   COMBAT_ARG(d && d->in && dy && dw_ohwi, 0);
   COMBAT_ARG(combat_conv_tc_supported(d) && d->up == 1, 0);
@@ -1027,6 +1152,32 @@ extern "C" int combat_conv_tc_wgrad(const combat_conv_tc_desc* d, const void* dy
   TcWgradMaps maps;
   memset(&maps, 0, sizeof(maps));
   const int KH = d->KH, KW = d->KW, pad = d->pad, s = d->stride;
+  if (d->Ci == 64 && d->Co == 64 && KH == 3 && pad == 1 && s == 1 && !getenv("COMBAT_NO_TC64")) {
+    // all nine taps in one CTA (conv_tc_wgrad64_kernel): tiles of BH full-width rows of one image
+    TcW64Params q;
+    memset(&q, 0, sizeof(q));
+    int bni;
+    pick_box(d->Ho, d->Wo, TILE_M, &q.BW, &q.BH, &bni);
+    q.copy_bytes = (q.BH + 2) * q.BW * 128;
+    const int smem_bytes = 2 * (3 * q.copy_bytes + 128 * 128) + 1024 + 256;
+    if (q.BW == d->Wo && bni == 1 && (q.BW % 8) == 0 && smem_bytes <= 232448) {
+      TcW64Maps wm;
+      memset(&wm, 0, sizeof(wm));
+      const long long C = 64, W = d->Wi, H = d->Hi;
+      int rc = make_act_map(&wm.x, d->in, 64, d->Wi, d->Hi, d->N, C, W * C, H * W * C, q.BW, q.BH + 2, 1);
+      if (rc) return rc;
+      rc = make_act_map(&wm.dy, dy, 64, d->Wo, d->Ho, d->N, C, W * C, H * W * C, q.BW, q.BH, 1);
+      if (rc) return rc;
+      q.N = d->N; q.H = d->Ho; q.W = d->Wo;
+      q.tiles_h = cdiv(d->Ho, q.BH);
+      q.total_tiles = q.tiles_h * d->N;
+      q.dw = dw_ohwi;
+      const int grid = q.total_tiles < num_sms() ? q.total_tiles : num_sms();
+      cudaFuncSetAttribute(conv_tc_wgrad64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+      conv_tc_wgrad64_kernel<<<grid, 192, smem_bytes, (cudaStream_t)stream>>>(wm, q);
+      COMBAT_RETURN_LAUNCH("conv_tc_wgrad64");
+    }
+  }
   p.N = d->N; p.Ho = d->Ho; p.Wo = d->Wo; p.Co = d->Co; p.Ci = d->Ci; p.taps = KH * KW;
   p.kchunks = d->Ci / KCHUNK;
   p.row_chunks = p.taps * p.kchunks;
