@@ -163,6 +163,7 @@ struct TcParams {
   const bf16* mask;         // bf16 NHWC like out: v = mask > 0 ? v * mask_scale[c] : 0 -- backward of relu(bn_eval(.))
   const float* mask_scale;
   const bf16* post_add;     // bf16 NHWC like out, added after the mask (gradient arriving over an identity shortcut)
+  float* stats;             // optional [gridDim.x][2][Co] per-CTA partial sums / sums of squares of `out` (train-mode BatchNorm)
   long long* dbg;           // optional [gridDim.x][8] cycle counters (pipeline diagnostics, scripts/bench_conv.py --dbg)
   TcTaps taps;
 };
@@ -195,6 +196,7 @@ __device__ __forceinline__ void decode_tile(const TcParams& p, int tile, int& cl
 
 // ---------------------------------------------------------------------------------------------- epilogue (shared by all mainloops)
 // MODE 0: out = act(acc + bias)*post_scale+post_shift + residual; out2 = bf16 relu(out*scale2+shift2)
+// MODE 2: MODE 0 + per-(CTA, row quarter) partial sums / sums of squares of `out` (train-mode BatchNorm statistics)
 // MODE 1: out = bf16( mask > 0 ? (acc + residual) * mask_scale : 0 ) + post_add     (residual XOR post_add, both bf16)
 template <int BLOCK_N, int MODE>
 __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* stg_base, uint32_t tmem_base, uint64_t* tfull_bar,
@@ -210,6 +212,13 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* stg_base
   const int half = (warp - 2) >> 2;
   constexpr int NCH = BLOCK_N / 64;  // 32-column chunks per warp
   const uint32_t stg = smem_u32(stg_base) + (warp - 2) * (32 * EPI_ROWB);  // explicit shared-space address
+  constexpr bool FWD = MODE != 1;    // MODE 2 = MODE 0 + train-mode BatchNorm statistics of `out`
+  constexpr bool STATS = MODE == 2;
+  // running per-column sum / sum of squares of this warp's rows over ALL its tiles (the launcher guarantees that the
+  // output-channel tile of a CTA never changes: gridDim.x % tiles_co == 0); written once at the end
+  float4 ssum[NCH], ssq[NCH];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) ssum[ch] = ssq[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
   const int sub = lane >> 3;     // row within a group of 4
   const int cseg = lane & 7;     // 16-byte column segment: columns cseg*4 .. cseg*4+3 of the chunk
   int acc = 0;
@@ -250,7 +259,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* stg_base
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const uint32_t o = (t.okmask >> i & 1) ? t.ob[i] + ch * EPI_CH : 0u;
-        if (MODE == 0) {
+        if (FWD) {
           if (p.residual) {
             if (p.res_f32) t.pr[ch][i] = __ldg((const float4*)((const float*)p.residual + o));
             else *(uint2*)&t.pr[ch][i].x = __ldg((const uint2*)((const bf16*)p.residual + o));
@@ -308,7 +317,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* stg_base
 #pragma unroll
         for (int i = 0; i < 8; ++i) f[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      if (MODE == 0) {
+      if (FWD) {
         if (p.bias) {
           const float4 bb = *(const float4*)(p.bias + colg);
 #pragma unroll
@@ -360,6 +369,15 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* stg_base
           if (!pre_add) { f[i].x += a0.x; f[i].y += a0.y; f[i].z += a1.x; f[i].w += a1.y; }
         }
       }
+      if (STATS) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (okmask >> i & 1) {
+            ssum[ch].x += f[i].x; ssum[ch].y += f[i].y; ssum[ch].z += f[i].z; ssum[ch].w += f[i].w;
+            ssq[ch].x = fmaf(f[i].x, f[i].x, ssq[ch].x); ssq[ch].y = fmaf(f[i].y, f[i].y, ssq[ch].y);
+            ssq[ch].z = fmaf(f[i].z, f[i].z, ssq[ch].z); ssq[ch].w = fmaf(f[i].w, f[i].w, ssq[ch].w);
+          }
+      }
       if (p.out) {
         if (p.out_f32) {
 #pragma unroll
@@ -374,7 +392,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* stg_base
             }
         }
       }
-      if (MODE == 0 && p.out2) {
+      if (FWD && p.out2) {
         const float4 ss = *(const float4*)(p.scale2 + colg), hh = *(const float4*)(p.shift2 + colg);
 #pragma unroll
         for (int i = 0; i < 8; ++i)
@@ -400,6 +418,26 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* stg_base
   if (p.dbg && warp == 2 && lane == 0) {
     p.dbg[blockIdx.x * 8 + 4] += e_wait;
     p.dbg[blockIdx.x * 8 + 5] += e_body;
+  }
+  if (STATS) {
+    // partial block = (CTA, quarter): [2][Co]; lanes with sub == 0 hold the sums of the warp's 32 rows after the reduction
+    const int cot = (int)blockIdx.x % p.tiles_co;
+    float* dst = p.stats + ((long long)blockIdx.x * 4 + quarter) * 2 * p.Co + cot * BLOCK_N + half * (BLOCK_N / 2) + cseg * 4;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      float4 sm = ssum[ch], sq = ssq[ch];
+#pragma unroll
+      for (int o = 8; o <= 16; o <<= 1) {
+        sm.x += __shfl_xor_sync(0xffffffffu, sm.x, o); sm.y += __shfl_xor_sync(0xffffffffu, sm.y, o);
+        sm.z += __shfl_xor_sync(0xffffffffu, sm.z, o); sm.w += __shfl_xor_sync(0xffffffffu, sm.w, o);
+        sq.x += __shfl_xor_sync(0xffffffffu, sq.x, o); sq.y += __shfl_xor_sync(0xffffffffu, sq.y, o);
+        sq.z += __shfl_xor_sync(0xffffffffu, sq.z, o); sq.w += __shfl_xor_sync(0xffffffffu, sq.w, o);
+      }
+      if (sub == 0) {
+        *(float4*)(dst + ch * EPI_CH) = sm;
+        *(float4*)(dst + p.Co + ch * EPI_CH) = sq;
+      }
+    }
   }
 }
 
@@ -721,6 +759,9 @@ static int num_sms() {
   return n;
 }
 
+static int g_last_grid = 0;
+extern "C" int combat_conv_tc_last_grid(void) { return g_last_grid; }
+
 extern "C" int combat_conv_tc(const combat_conv_tc_desc* d, void* stream) {
   COMBAT_ARG(d && d->in && d->w && (d->out || d->out2), 0);
   COMBAT_ARG(combat_conv_tc_supported(d), 0);
@@ -756,6 +797,7 @@ extern "C" int combat_conv_tc(const combat_conv_tc_desc* d, void* stream) {
   p.mask_scale = d->mask_scale;
   p.post_add = (const bf16*)d->post_add;
   p.dbg = getenv("COMBAT_TC_DBG") ? (long long*)d->stats : nullptr;
+  p.stats = p.dbg ? nullptr : d->stats;
   const int BLOCK_N = (d->Co % 128 == 0) ? 128 : 64;
   p.tiles_co = d->Co / BLOCK_N;
   int rc;
@@ -848,26 +890,36 @@ extern "C" int combat_conv_tc(const combat_conv_tc_desc* d, void* stream) {
   p.tiles_n = cdiv(p.N, p.BNI);
   p.total_tiles = p.n_classes * p.tiles_n * p.tiles_h * p.tiles_w * p.tiles_co;
   int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  g_last_grid = grid;
+  COMBAT_ARG(!d->stats || (d->Co <= 512 && !d->mask), 0);
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH_C(BN, MD)                                                                                                  \
   {                                                                                                                       \
     cudaFuncSetAttribute(conv_tc_kernel<BN, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES);     \
     conv_tc_kernel<BN, MD><<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st>>>(maps, p);                                     \
   }
-  const int mode = d->mask ? 1 : 0;
+  const int mode = d->mask ? 1 : (p.stats ? 2 : 0);
+  if (p.stats) {  // partial blocks of (CTA, quarter): zero-filled, every warp writes only its own column range
+    COMBAT_ARG(grid % p.tiles_co == 0, 0);
+    cudaMemsetAsync(p.stats, 0, (size_t)grid * 4 * 2 * d->Co * sizeof(float), st);
+    g_last_grid = grid * 4;
+  }
   if (use64) {
     const int smem_bytes = Tc64Cfg::SMEM_BYTES_FIXED + n_stages64 * stage_bytes64;
-    if (mode) {
+    if (mode == 1) {
       cudaFuncSetAttribute(conv_tc64_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
       conv_tc64_kernel<1><<<grid, TC_THREADS, smem_bytes, st>>>(maps, p, stage_bytes64, n_stages64);
+    } else if (mode == 2) {
+      cudaFuncSetAttribute(conv_tc64_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+      conv_tc64_kernel<2><<<grid, TC_THREADS, smem_bytes, st>>>(maps, p, stage_bytes64, n_stages64);
     } else {
       cudaFuncSetAttribute(conv_tc64_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
       conv_tc64_kernel<0><<<grid, TC_THREADS, smem_bytes, st>>>(maps, p, stage_bytes64, n_stages64);
     }
     COMBAT_RETURN_LAUNCH("conv_tc64");
   }
-  if (BLOCK_N == 128) { if (mode) LAUNCH_C(128, 1) else LAUNCH_C(128, 0) }
-  else { if (mode) LAUNCH_C(64, 1) else LAUNCH_C(64, 0) }
+  if (BLOCK_N == 128) { if (mode == 1) LAUNCH_C(128, 1) else if (mode == 2) LAUNCH_C(128, 2) else LAUNCH_C(128, 0) }
+  else { if (mode == 1) LAUNCH_C(64, 1) else if (mode == 2) LAUNCH_C(64, 2) else LAUNCH_C(64, 0) }
 #undef LAUNCH_C
   COMBAT_RETURN_LAUNCH("conv_tc");
 }

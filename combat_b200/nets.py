@@ -141,6 +141,7 @@ class NetBase:
         # normalisation itself then see the unrounded fp32 accumulator; activations/gradients use `dtype`
         self.pre_dtype = torch.float32
         self.fast_small = True  # direct kernels for the 3-channel boundary layers (csrc/conv_small.cu)
+        self.last_stats_nblk = 0
         self.convs: dict[str, ConvSpec] = {}
 
     # ---- construction helpers
@@ -188,7 +189,7 @@ class NetBase:
     def _tc_ok(self, cs: ConvSpec):
         return self.use_tc and cs.Cin % 64 == 0 and cs.Cout % 64 == 0
 
-    def conv_fwd(self, x, cs: ConvSpec, residual=None, pre=True, bn_relu=None, want_out=True):
+    def conv_fwd(self, x, cs: ConvSpec, residual=None, pre=True, bn_relu=None, want_out=True, stats=False):
         """x: NHWC [N,H,W,Cin] in the activation dtype -> NHWC out (float32 when `pre`, i.e. feeding a norm).
         bn_relu=(scale, shift): the tcgen05 epilogue ALSO writes out2 = bf16 relu(out*scale+shift) (eval BatchNorm+ReLU of
         the consumer); returns (out or None, out2) then."""
@@ -207,12 +208,16 @@ class NetBase:
                        _tag(N, H, W, cs) + " +bn")
             return out, out2
         out = torch.empty((N, Ho, Wo, cs.Cout), dtype=self.pre_dtype if pre else self.dtype, device=self.device)
+        self.last_stats_nblk = 0  # > 0: the launch left train-mode BatchNorm partial sums of `out` in ops.Scratch
         if self._tc_ok(cs) and Ct == cs.Cin:
+            want_stats = stats and pre and cs.Cout <= 512
             d = ops.conv_tc_desc(x, self._wptr(cs), out, N, H, W, cs.Cin, Ho, Wo, cs.Cout, cs.k, cs.k, cs.stride, cs.pad, 1,
-                                 bias=self._bias(cs), residual=residual)
+                                 bias=self._bias(cs), residual=residual, stats=ops.Scratch.get(self.device) if want_stats else None)
             if lib.combat_conv_tc_supported(C.byref(d)):
                 _tc_launch(lambda: lib.combat_conv_tc(C.byref(d), ops._s()), "conv_tc", 2.0 * N * Ho * Wo * cs.Cout * cs.Cin * cs.k * cs.k,
-                           _tag(N, H, W, cs))
+                           _tag(N, H, W, cs) + (" +stats" if want_stats else ""))
+                if want_stats:
+                    self.last_stats_nblk = lib.combat_conv_tc_last_grid()
                 return out
         ops.conv_simt(x, (N, H, W), ops.nhwc_strides(H, W, Ct), self._wptr(cs), self.dt, out, (Ho, Wo),
                       ops.nhwc_strides(Ho, Wo, cs.Cout), Ci=cs.Cin, Co=cs.Cout, KH=cs.k, KW=cs.k, stride=cs.stride,
@@ -418,12 +423,18 @@ class Classifier(NetBase):
         return sd
 
     # ---- BN helpers
-    def _bn_fwd(self, bn, x, train, relu, residual=None):
+    def _bn_fwd(self, bn, x, train, relu, residual=None, stats_nblk=0):
+        """stats_nblk > 0: the conv that produced x already reduced its per-CTA sums (fused epilogue statistics)."""
         Cc = bn.C
         R = x.numel() // Cc
         g, b = self.store.p(bn.name + ".weight"), self.store.p(bn.name + ".bias")
         if train:
-            scale, shift, mean, invstd = ops.bn_train_prepare(x, R, Cc, g, b, self.rm(bn), self.rv(bn), self.momentum, self.eps)
+            if stats_nblk > 0:
+                scale, shift, mean, invstd = ops.bn_train_finalize(stats_nblk, R, Cc, g, b, self.rm(bn), self.rv(bn),
+                                                                   self.momentum, self.eps)
+            else:
+                scale, shift, mean, invstd = ops.bn_train_prepare(x, R, Cc, g, b, self.rm(bn), self.rv(bn), self.momentum,
+                                                                  self.eps)
             self.num_batches_tracked[bn.name] += 1
             st = (scale, mean, invstd)
         else:
@@ -457,13 +468,15 @@ class Classifier(NetBase):
             h, st0 = self._bn_fwd(self.bn1, c0, train, True)
             if save:
                 ctx["stem"] = (c0, h, st0)
+        h_nblk = 0  # partial-sum blocks of h left by its producer conv (train mode, tcgen05 path)
         for blk in self.blocks:
             if pre:
-                o1, st1 = self._bn_fwd(blk["bn1"], h, train, True)
+                o1, st1 = self._bn_fwd(blk["bn1"], h, train, True, stats_nblk=h_nblk)
                 s = self.conv_fwd(o1, blk["sc"]) if "sc" in blk else h
-                c1 = self.conv_fwd(o1, blk["conv1"])
-                o2, st2 = self._bn_fwd(blk["bn2"], c1, train, True)
-                out = self.conv_fwd(o2, blk["conv2"], residual=s)
+                c1 = self.conv_fwd(o1, blk["conv1"], stats=train)
+                o2, st2 = self._bn_fwd(blk["bn2"], c1, train, True, stats_nblk=self.last_stats_nblk if train else 0)
+                out = self.conv_fwd(o2, blk["conv2"], residual=s, stats=train)  # statistics of the next block's bn1 input
+                h_nblk = self.last_stats_nblk if train else 0
                 if save:
                     ctx["blocks"].append((h, o1, c1, o2, st1, st2))
             else:

@@ -315,6 +315,17 @@ def bn_train_prepare(x2d, R, Cc, gamma, beta, rm, rv, momentum, eps):
     return st[0], st[1], st[2], st[3]
 
 
+def bn_train_finalize(nblk, R, Cc, gamma, beta, rm, rv, momentum, eps):
+    """Same as bn_train_prepare when the producer conv already left its per-CTA partial sums in the scratch buffer
+    (conv_tc_desc(stats=Scratch.get(dev)); nblk = lib.combat_conv_tc_last_grid())."""
+    dev = rm.device
+    partial = Scratch.get(dev)
+    st = torch.empty((4, Cc), dtype=torch.float32, device=dev)
+    check(lib.combat_bn_finalize(_p(partial), nblk, R, Cc, _p(gamma), _p(beta), _p(rm), _p(rv), momentum, eps,
+                                 _p(st[0]), _p(st[1]), _p(st[2]), _p(st[3]), _s()), "bn_finalize")
+    return st[0], st[1], st[2], st[3]
+
+
 def bn_eval_prepare(Cc, gamma, beta, rm, rv, eps):
     st = torch.empty((2, Cc), dtype=torch.float32, device=rm.device)
     check(lib.combat_bn_finalize(None, 0, 1, Cc, _p(gamma), _p(beta), _p(rm), _p(rv), 0.0, eps, _p(st[0]), _p(st[1]),

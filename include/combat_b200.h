@@ -150,7 +150,9 @@ typedef struct {
   void* out;             /* NHWC [N,Ho,Wo,Co], bf16 or float32 (out_f32) */
   const float* bias;     /* or NULL */
   const void* residual;  /* NHWC like out, bf16 or float32 (res_f32), or NULL */
-  float* stats;          /* reserved (fused BatchNorm statistics) */
+  float* stats;          /* optional: per-CTA partial sums [grid][2][Co] (sum, sum of squares over pixels) of the float32
+                          * value written to `out` -- train-mode BatchNorm statistics fused into the producer conv;
+                          * grid = combat_conv_tc_last_grid() CTAs, reduced by combat_bn_finalize(partial, nblk = grid) */
   int N, Hi, Wi, Ci, Ho, Wo, Co, KH, KW, stride, pad, up;
   int out_f32;           /* 1: `out` is float32 (pre-normalisation tensors keep the unrounded accumulator) */
   int res_f32;           /* 1: `residual` is float32 */
@@ -173,6 +175,8 @@ typedef struct {
 int combat_conv_tc(const combat_conv_tc_desc* d_host, void* stream);
 int combat_conv_tc_wgrad(const combat_conv_tc_desc* d_host, const void* dy, float* dw_ohwi, void* stream);
 int combat_conv_tc_supported(const combat_conv_tc_desc* d_host);
+/* number of CTAs (= partial-sum blocks written to desc.stats) of the most recent combat_conv_tc launch of this thread */
+int combat_conv_tc_last_grid(void);
 
 /* ---------------------------------------------------------------- normalisation / activation (NHWC, dtype)
  * BatchNorm2d (classifier_models/preact_resnet.py:20,22,32,35; resnet.py:22-35) */

@@ -525,6 +525,14 @@ def test_conv_tc_fused_batchnorm_epilogues(ops, stride_up):
         torch.cuda.synchronize()
         assert rel(out.permute(0, 3, 1, 2), y) < 2e-5
         assert rel(out2.float().permute(0, 3, 1, 2), y2) < 6e-3
+        # fused train-mode BatchNorm statistics of `out`: per-CTA partial sums / sums of squares
+        part = torch.full((256 * 2 * Co,), 7.0, device="cuda")
+        d = ops.conv_tc_desc(xd, w_f.data_ptr(), out, N, H, H, Ci, H, H, Co, 3, 3, 1, 1, 1, residual=dev(_nhwc(res)), stats=part)
+        check(lib.combat_conv_tc(C.byref(d), ops._s()), "conv_tc")
+        nblk = lib.combat_conv_tc_last_grid()
+        torch.cuda.synchronize()
+        ps = part[: nblk * 2 * Co].view(nblk, 2, Co).double().sum(0).cpu()
+        assert rel(ps[0], y.double().sum((0, 2, 3))) < 1e-5 and rel(ps[1], (y.double() ** 2).sum((0, 2, 3))) < 1e-5
         # out2 only
         out2b = torch.zeros_like(out2)
         d = ops.conv_tc_desc(xd, w_f.data_ptr(), None, N, H, H, Ci, H, H, Co, 3, 3, 1, 1, 1, residual=dev(_nhwc(res)), out2=out2b,
