@@ -21,6 +21,40 @@ __device__ __forceinline__ void st2<float>(float* p, float2 v) { *(float2*)p = v
 template <>
 __device__ __forceinline__ void st2<bf16>(bf16* p, float2 v) { *(__nv_bfloat162*)p = __float22bfloat162_rn(v); }
 
+// 8 consecutive channels per thread (16 bytes of bf16, 32 of float32): the elementwise kernels below are HBM-bound and
+// spend their issue slots on index arithmetic when they move 4 bytes per thread
+template <typename T>
+__device__ __forceinline__ void ld8(const T* p, float* v);
+template <>
+__device__ __forceinline__ void ld8<float>(const float* p, float* v) {
+  const float4 a = ((const float4*)p)[0], b = ((const float4*)p)[1];
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void ld8<bf16>(const bf16* p, float* v) {
+  const uint4 u = *(const uint4*)p;
+  const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(*(const __nv_bfloat162*)&w4[i]);
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+template <typename T>
+__device__ __forceinline__ void st8(T* p, const float* v);
+template <>
+__device__ __forceinline__ void st8<float>(float* p, const float* v) {
+  ((float4*)p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  ((float4*)p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <>
+__device__ __forceinline__ void st8<bf16>(bf16* p, const float* v) {
+  __nv_bfloat162 h[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  *(uint4*)p = *(uint4*)h;
+}
+
 // Column-reduction geometry: blockDim = (32, 8); a thread owns channels 2*(blockIdx.y*32+tx)+{0,1};
 // row lanes ty stride over the block's row range.
 #define CR_TX 32
@@ -131,6 +165,33 @@ __global__ void __launch_bounds__(256) affine_act_k(const TX* __restrict__ x, co
 }
 
 template <typename TX, typename T>
+__global__ void __launch_bounds__(256) affine_act_v8_k(const TX* __restrict__ x, const T* __restrict__ res, T* __restrict__ y,
+                                                       long long n8, int C, const float* __restrict__ scale,
+                                                       const float* __restrict__ shift, int relu) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const long long e = i * 8;
+    const int c = (int)(e % C);
+    float v[8], sc[8], sh[8];
+    ld8<TX>(x + e, v);
+    ld8<float>(scale + c, sc);
+    ld8<float>(shift + c, sh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+    if (res) {
+      float r[8];
+      ld8<T>(res + e, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += r[j];
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    st8<T>(y + e, v);
+  }
+}
+
+template <typename TX, typename T>
 __global__ void __launch_bounds__(256) bn_bwd_reduce_k(const T* __restrict__ dy, const TX* __restrict__ x,
                                                        const T* __restrict__ y, long long R, int C,
                                                        long long rows_per_block, const float* __restrict__ mean,
@@ -220,6 +281,62 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_k(const T* __restrict__ dy, 
   }
 }
 
+template <typename TX, typename T>
+__global__ void __launch_bounds__(256) bn_bwd_apply_v8_k(const T* __restrict__ dy, const TX* __restrict__ x,
+                                                         const T* __restrict__ y, const T* __restrict__ dadd,
+                                                         T* __restrict__ dx, T* __restrict__ dres, long long n8, long long R,
+                                                         int C, const float* __restrict__ gamma,
+                                                         const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                         const float* __restrict__ dgamma, const float* __restrict__ dbeta,
+                                                         const float* __restrict__ eval_scale, int relu) {
+  const float invR = 1.f / (float)R;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const long long e = i * 8;
+    const int c = (int)(e % C);
+    float g[8], o[8];
+    ld8<T>(dy + e, g);
+    if (relu) {
+      float yy[8];
+      ld8<T>(y + e, yy);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (!(yy[j] > 0.f)) g[j] = 0.f;
+    }
+    if (dres) st8<T>(dres + e, g);
+    if (eval_scale) {
+      float es[8];
+      ld8<float>(eval_scale + c, es);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = g[j] * es[j];
+    } else {
+      float v[8], mu[8], is[8], dg[8], db[8], gm[8];
+      ld8<TX>(x + e, v);
+      ld8<float>(mean + c, mu);
+      ld8<float>(invstd + c, is);
+      ld8<float>(dgamma + c, dg);
+      ld8<float>(dbeta + c, db);
+      if (gamma) {
+        ld8<float>(gamma + c, gm);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gm[j] = 1.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (v[j] - mu[j]) * is[j];
+        o[j] = gm[j] * is[j] * (g[j] - db[j] * invR - xh * dg[j] * invR);
+      }
+    }
+    if (dadd) {
+      float a[8];
+      ld8<T>(dadd + e, a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += a[j];
+    }
+    st8<T>(dx + e, o);
+  }
+}
+
 // TX = dtype of the pre-normalisation tensor (conv output), T = dtype of activations / gradients
 #define DISPATCH_2(xdt, dt, ...)                 \
   if ((xdt) == COMBAT_F32 && (dt) == COMBAT_F32) { typedef float TX; typedef float T; __VA_ARGS__ } \
@@ -293,6 +410,12 @@ extern "C" int combat_affine_act(const void* x, int x_dtype, const void* residua
   COMBAT_ARG((C % 2) == 0, 5);
   long long n2 = R * C / 2;
   if (n2 <= 0) return 0;
+  if ((C % 8) == 0) {
+    const long long n8 = R * C / 8;
+    DISPATCH_2(x_dtype, dtype, affine_act_v8_k<TX, T><<<ew_grid(n8), 256, 0, (cudaStream_t)stream>>>(
+                                   (const TX*)x, (const T*)residual, (T*)y, n8, C, scale, shift, relu);)
+    COMBAT_RETURN_LAUNCH("affine_act");
+  }
   DISPATCH_2(x_dtype, dtype, affine_act_k<TX, T><<<ew_grid(n2), 256, 0, (cudaStream_t)stream>>>(
                                  (const TX*)x, (const T*)residual, (T*)y, n2, C, scale, shift, relu);)
   COMBAT_RETURN_LAUNCH("affine_act");
@@ -327,6 +450,13 @@ extern "C" int combat_bn_bwd_apply(const void* dy, const void* x, int x_dtype, c
   COMBAT_ARG(!relu || y, 2);
   long long n2 = R * C / 2;
   if (n2 <= 0) return 0;
+  if ((C % 8) == 0) {
+    const long long n8 = R * C / 8;
+    DISPATCH_2(x_dtype, dtype, bn_bwd_apply_v8_k<TX, T><<<ew_grid(n8), 256, 0, (cudaStream_t)stream>>>(
+                                   (const T*)dy, (const TX*)x, (const T*)y, (const T*)dadd, (T*)dx, (T*)dres, n8, R, C, gamma,
+                                   mean, invstd, dgamma, dbeta, eval_scale, relu);)
+    COMBAT_RETURN_LAUNCH("bn_bwd_apply");
+  }
   DISPATCH_2(x_dtype, dtype, bn_bwd_apply_k<TX, T><<<ew_grid(n2), 256, 0, (cudaStream_t)stream>>>(
                                  (const T*)dy, (const TX*)x, (const T*)y, (const T*)dadd, (T*)dx, (T*)dres, n2, R, C, gamma,
                                  mean, invstd, dgamma, dbeta, eval_scale, relu);)
@@ -503,6 +633,36 @@ __global__ void __launch_bounds__(256) upsample2x_act_k(const T* __restrict__ x,
   }
 }
 
+template <typename T>
+__global__ void __launch_bounds__(256) upsample2x_act_v8_k(const T* __restrict__ x, T* __restrict__ y, long long total8, int H,
+                                                           int W, int C, float slope) {
+  const int C8 = C / 8, Ho = 2 * H, Wo = 2 * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
+    const int c = 8 * (int)(i % C8);
+    long long p = i / C8;
+    const int ow = (int)(p % Wo);
+    p /= Wo;
+    const int oh = (int)(p % Ho);
+    const long long n = p / Ho;
+    int h0, h1, w0, w1;
+    float lh0, lh1, lw0, lw1;
+    up_src(oh, H, h0, h1, lh0, lh1);
+    up_src(ow, W, w0, w1, lw0, lw1);
+    const T* xb = x + n * H * W * C + c;
+    float a[8], b[8], cc[8], d[8], v[8];
+    ld8<T>(xb + ((long long)h0 * W + w0) * C, a);
+    ld8<T>(xb + ((long long)h0 * W + w1) * C, b);
+    ld8<T>(xb + ((long long)h1 * W + w0) * C, cc);
+    ld8<T>(xb + ((long long)h1 * W + w1) * C, d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float t = lh0 * (lw0 * a[j] + lw1 * b[j]) + lh1 * (lw0 * cc[j] + lw1 * d[j]);
+      v[j] = t > 0.f ? t : t * slope;
+    }
+    st8<T>(y + i * 8, v);
+  }
+}
+
 // weight with which input index `i` enters output index `o` (0 if not referenced)
 __device__ __forceinline__ float up_w(int o, int i, int n_in) {
   int i0, i1;
@@ -550,11 +710,56 @@ __global__ void __launch_bounds__(256) upsample2x_act_bwd_k(const T* __restrict_
   }
 }
 
+template <typename T>
+__global__ void __launch_bounds__(256) upsample2x_act_bwd_v8_k(const T* __restrict__ dy, const T* __restrict__ y,
+                                                               T* __restrict__ dx, long long total8, int H, int W, int C,
+                                                               float slope) {
+  const int C8 = C / 8, Ho = 2 * H, Wo = 2 * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
+    const int c = 8 * (int)(i % C8);
+    long long p = i / C8;
+    const int w = (int)(p % W);
+    p /= W;
+    const int h = (int)(p % H);
+    const long long n = p / H;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int oh = 2 * h - 1; oh <= 2 * h + 2; ++oh) {
+      if (oh < 0 || oh >= Ho) continue;
+      const float wh = up_w(oh, h, H);
+      if (wh == 0.f) continue;
+      for (int ow = 2 * w - 1; ow <= 2 * w + 2; ++ow) {
+        if (ow < 0 || ow >= Wo) continue;
+        const float ww = up_w(ow, w, W);
+        if (ww == 0.f) continue;
+        const long long o = ((n * Ho + oh) * Wo + ow) * C + c;
+        float g[8];
+        ld8<T>(dy + o, g);
+        if (slope != 1.f) {
+          float yy[8];
+          ld8<T>(y + o, yy);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (!(yy[j] > 0.f)) g[j] *= slope;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(wh * ww, g[j], acc[j]);
+      }
+    }
+    st8<T>(dx + i * 8, acc);
+  }
+}
+
 extern "C" int combat_upsample2x_act(const void* x, void* y, int dtype, int N, int H, int W, int C, float slope,
                                      void* stream) {
   COMBAT_ARG(x && y && (C % 2) == 0, 0);
   long long total2 = (long long)N * 4 * H * W * C / 2;
   if (total2 <= 0) return 0;
+  if ((C % 8) == 0) {
+    const long long total8 = total2 / 4;
+    DISPATCH_DTYPE(dtype, upsample2x_act_v8_k<T><<<ew_grid(total8), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, total8, H,
+                                                                                                   W, C, slope);)
+    COMBAT_RETURN_LAUNCH("upsample2x_act");
+  }
   DISPATCH_DTYPE(dtype, upsample2x_act_k<T><<<ew_grid(total2), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, total2, H, W,
                                                                                               C, slope);)
   COMBAT_RETURN_LAUNCH("upsample2x_act");
@@ -566,6 +771,12 @@ extern "C" int combat_upsample2x_act_bwd(const void* dy, const void* y, void* dx
   COMBAT_ARG(slope == 1.f || y, 1);
   long long total2 = (long long)N * H * W * C / 2;
   if (total2 <= 0) return 0;
+  if ((C % 8) == 0) {
+    const long long total8 = total2 / 4;
+    DISPATCH_DTYPE(dtype, upsample2x_act_bwd_v8_k<T><<<ew_grid(total8), 256, 0, (cudaStream_t)stream>>>(
+                              (const T*)dy, (const T*)y, (T*)dx, total8, H, W, C, slope);)
+    COMBAT_RETURN_LAUNCH("upsample2x_act_bwd");
+  }
   DISPATCH_DTYPE(dtype, upsample2x_act_bwd_k<T><<<ew_grid(total2), 256, 0, (cudaStream_t)stream>>>(
                             (const T*)dy, (const T*)y, (T*)dx, total2, H, W, C, slope);)
   COMBAT_RETURN_LAUNCH("upsample2x_act_bwd");
