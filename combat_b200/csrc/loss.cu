@@ -13,6 +13,46 @@ __global__ void __launch_bounds__(1024) cross_entropy_k(const float* __restrict_
   float loss_acc = 0.f;
   int c1 = 0, c2 = 0;
   const float invB = 1.f / (float)B;
+  if (C <= 16) {
+    // few classes (10 / 8 on this path): one THREAD per row, all loads independent -- the warp-per-row form below spends
+    // three dependent global round trips per row on ten values
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+      const float* row = logits + (long long)b * C;
+      float v[16];
+      float m = -INFINITY;
+      int am = 0;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        v[c] = c < C ? row[c] : -INFINITY;
+        if (v[c] > m) { m = v[c]; am = c; }  // first index wins ties
+      }
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        if (c < C) s += expf(v[c] - m);
+      const float lse = m + logf(s);
+      const int t = (int)tgt[b];
+      if (dlogits) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+          if (c < C) dlogits[(long long)b * C + c] = gscale * invB * (expf(v[c] - lse) - (c == t ? 1.f : 0.f));
+      }
+      float vt = 0.f;
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        if (c == t) vt = v[c];
+      loss_acc += lse - vt;
+      c1 += (am == t);
+      if (tgt2) c2 += (am == (int)tgt2[b]);
+    }
+    // fixed-order reduction: lanes -> warps -> thread 0
+    loss_acc = warp_sum(loss_acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+      c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+    }
+  } else
   for (int b = warp; b < B; b += nwarp) {
     const float* row = logits + (long long)b * C;
     float m = -INFINITY;

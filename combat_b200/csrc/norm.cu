@@ -917,19 +917,32 @@ __global__ void __launch_bounds__(256) pool_linear_bwd_dx_k(const float* __restr
 }
 
 // dW[k][f] = sum_b dlogits[b][k] * pooled[b][f]; db[k] = sum_b dlogits[b][k]
+// grid (F / 32, ncls), block (32 features, 8 batch slices): fixed-order shared-memory reduction over the slices
 __global__ void __launch_bounds__(256) linear_wgrad_k(const float* __restrict__ dlogits, const float* __restrict__ pooled,
                                                       int B, int F, int ncls, float* __restrict__ dW, float* __restrict__ db) {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float red[8][33];
+  const int f = blockIdx.x * 32 + threadIdx.x;
   const int k = blockIdx.y;
-  if (f < F) {
-    float s = 0.f;
-    for (int b = 0; b < B; ++b) s = fmaf(dlogits[(long long)b * ncls + k], pooled[(long long)b * F + f], s);
-    dW[(long long)k * F + f] = s;
+  float s = 0.f, sb = 0.f;
+  for (int b = threadIdx.y; b < B; b += 8) {
+    const float g = dlogits[(long long)b * ncls + k];
+    if (f < F) s = fmaf(g, pooled[(long long)b * F + f], s);
+    sb += g;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    float s = 0.f;
-    for (int b = 0; b < B; ++b) s += dlogits[(long long)b * ncls + k];
-    db[k] = s;
+  red[threadIdx.y][threadIdx.x] = s;
+  if (threadIdx.x == 0) red[threadIdx.y][32] = sb;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x];
+    if (f < F) dW[(long long)k * F + f] = t;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      float tb = 0.f;
+#pragma unroll
+      for (int y = 0; y < 8; ++y) tb += red[y][32];
+      db[k] = tb;
+    }
   }
 }
 
@@ -962,8 +975,8 @@ extern "C" int combat_pool_linear_bwd(const float* dlogits, const float* pooled,
   }
   if (dW) {
     COMBAT_ARG(pooled && db, 1);
-    dim3 grid(cdiv(F, 256), ncls);
-    linear_wgrad_k<<<grid, 256, 0, (cudaStream_t)stream>>>(dlogits, pooled, B, F, ncls, dW, db);
+    dim3 grid(cdiv(F, 32), ncls), block(32, 8);
+    linear_wgrad_k<<<grid, block, 0, (cudaStream_t)stream>>>(dlogits, pooled, B, F, ncls, dW, db);
     COMBAT_CHECK_LAUNCH("linear_wgrad");
   }
   return 0;
