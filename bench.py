@@ -98,6 +98,17 @@ def cpu_reference_rate(batch, steps, warmup, seed=0):
     return batch * len(times) / sum(times), sum(times) / len(times)
 
 
+WORKLOAD = ("CIFAR-10 shape alternated step (train_generator.py:170-255), PreActResNet18 + UnetGenerator, pc=0.5 noise_rate=0.08, "
+            "bf16 tcgen05 convs, all metric forwards included (BASELINE configs[1])")
+
+
+def workload_config(B, world, use_graph):
+    return {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
+            "cuda_graph": use_graph,
+            "l2_policy": "working set per step (several GB of activations) is far larger than the 126 MB L2",
+            "flops_per_image": FLOPS_PER_IMG_FULL}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -112,10 +123,11 @@ def run_reference(args):
     cores = torch.get_num_threads()
     line = {
         "impl": "reference", "metric": "alternated-step images/sec at CIFAR-10 shape", "value": rate, "unit": "images/s",
-        "n_gpus": 0, "steps": args.steps, "warmup": args.warmup, "ms_per_step": tstep * 1e3, "higher_is_better": True,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": tstep * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "CIFAR-10 shape alternated step (train_generator.py:170-255), PreActResNet18 + UnetGenerator, "
-                               "pc=0.5 noise_rate=0.08, reference CPU path", "batch_per_step": batch},
+        # same workload as the CUDA arm; every timed step is a bounded SAMPLE of it (one alternated step over `batch` images of
+        # the same synthetic distribution, fp32, all host threads) -- images/s is batch-size independent on the CPU
+        "config": dict(workload_config(args.batch, max(1, args.gpus), not args.no_graph), reference_sample_batch=batch),
         "cpu_baseline": {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
                          "sample": "%d alternated steps of batch %d on the host cores (oracle/combat_oracle.py)" % (args.steps, batch)},
         "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -236,8 +248,16 @@ def run_ours(args):
                 for k, v in sorted(layers.items(), key=lambda kv: -kv[1][1]):
                     fh.write("%-60s launches %3d  ms %8.3f  TFLOP/s %7.1f\n" % (k, v[2], v[1], v[0] / (v[1] * 1e-3) / 1e12))
         ach = tot_fl / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
-        roof = {"bound": "tensor", "kernel": "conv_tc_kernel / conv_tc_wgrad_kernel (tcgen05 implicit GEMM)", "achieved": ach,
-                "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None, "peak_source": which + " (sustained bf16)",
+        # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (profiles/r01_ncu_traffic.json):
+        # per launch of the most frequent shape of conv_tc_kernel<128,0>, next to its algorithmic bytes
+        traffic, traffic_of = None, None
+        tp = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+        if os.path.exists(tp):
+            kname, kd = next(iter(json.load(open(tp))["kernels"].items()))
+            traffic, traffic_of = kd["dram_bytes_read"] + kd["dram_bytes_write"], {"kernel": kname, "algorithmic_bytes": kd["algorithmic_bytes"]}
+        roof = {"bound": "tensor", "kernel": "conv_tc_kernel / conv_tc64_kernel / conv_tc_wgrad*_kernel (tcgen05 implicit GEMM)", "achieved": ach,
+                "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic, "traffic_of": traffic_of,
+                "peak_source": which + " (sustained bf16)",
                 "launches": len(prof), "conv_ms_per_step": tot_ms,
                 "by_kind": {k: {"tflops": v[0] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else 0.0, "ms": v[1], "launches": v[2]} for k, v in by.items()},
                 "step_frac_of_tensor_peak": (value / world) * FLOPS_PER_IMG_FULL / 1e12 / peak_tf}
@@ -253,11 +273,7 @@ def run_ours(args):
             "metric": "alternated-step images/sec at CIFAR-10 shape", "value": value, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "CIFAR-10 shape alternated step (train_generator.py:170-255), PreActResNet18 + UnetGenerator, "
-                                   "pc=0.5 noise_rate=0.08, bf16 tcgen05 convs, all metric forwards included (BASELINE configs[1])",
-                       "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world, "cuda_graph": use_graph,
-                       "l2_policy": "working set per step (several GB of activations) is far larger than the 126 MB L2",
-                       "flops_per_image": FLOPS_PER_IMG_FULL},
+            "config": workload_config(B, world, use_graph),
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
