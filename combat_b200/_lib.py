@@ -55,6 +55,7 @@ _SIGS = {
     "combat_prep_weights": ([vp, vp, i32, vp, i32, i64, vp], i32),
     "combat_conv_simt": ([P(ConvDesc), vp], i32),
     "combat_conv_wgrad_simt": ([P(ConvDesc), vp, i32, vp, vp], i32),
+    "combat_im2col3": ([vp, vp, i32, i32, i32, i32, vp], i32),
     "combat_conv_cin3": ([vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp], i32),
     "combat_conv_cout3": ([vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, vp], i32),
     "combat_wgrad_cin3": ([vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, vp], i32),

@@ -452,6 +452,53 @@ static int grid_for(long long work_items, int per_block) {
   return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
 }
 
+// ---------------------------------------------------------------------------------- im2col of a 3-channel image for tcgen05
+// A[pix][64] (bf16, NHWC with 64 "channels") = [ hi(patch[0..26]), 0 x5, lo(patch[0..26]), 0 x5 ] with patch[(kh*3+kw)*3+ci] =
+// x[n, ci, oh*S-1+kh, ow*S-1+kw] (zero outside), hi = bf16(v), lo = bf16(v - hi).  A 3x3 conv over 3 input channels then
+// is a 1x1 tensor-core conv over A with the filter duplicated into both halves: K = 27 would waste a 64-deep MMA chunk
+// anyway, so the second half carries the rounding residual and the image enters with ~16 mantissa bits at no extra cost.
+__global__ void __launch_bounds__(256) im2col3_k(const float* __restrict__ x, bf16* __restrict__ A, int N, int H, int W, int Ho,
+                                                 int Wo, int S) {
+  const long long total = (long long)N * Ho * Wo * 8;  // one 16-byte chunk (8 columns) per thread
+  const long long HW = (long long)H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i & 7);
+    const long long m = i >> 3;
+    const int ow = (int)(m % Wo);
+    const long long r = m / Wo;
+    const int oh = (int)(r % Ho);
+    const long long n = r / Ho;
+    const bool lo = j >= 4;
+    const int kk0 = (j & 3) * 8;
+    const float* xb = x + n * 3 * HW;
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int kk = kk0 + q;
+      float t = 0.f;
+      if (kk < 27) {
+        const int tap = kk / 3, ci = kk - tap * 3;
+        const int ih = oh * S - 1 + tap / 3, iw = ow * S - 1 + tap % 3;
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W) t = __ldg(xb + ci * HW + (long long)ih * W + iw);
+        if (lo) t = t - __bfloat162float(__float2bfloat16_rn(t));
+      }
+      v[q] = t;
+    }
+    store8<bf16>(A + m * 64 + j * 8, v);
+  }
+}
+
+extern "C" int combat_im2col3(const float* x, void* A, int N, int H, int W, int stride, void* stream) {
+  COMBAT_ARG(x && A, 0);
+  COMBAT_ARG(stride == 1 || stride == 2, 5);
+  const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+  const long long total = (long long)N * Ho * Wo * 8;
+  if (total <= 0) return 0;
+  im2col3_k<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (bf16*)A, N, H, W, Ho, Wo, stride);
+  COMBAT_RETURN_LAUNCH("im2col3");
+}
+
+
 extern "C" int combat_conv_cin3(const float* x, const void* w, int w_dtype, const float* bias, void* out, int out_dtype, int N,
                                 int H, int W, int Co, int stride, int act, const float* post_scale, const float* post_shift,
                                 void* out2, const float* scale2, const float* shift2, void* stream) {

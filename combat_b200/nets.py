@@ -14,6 +14,7 @@ Parameter names, shapes and order are the reference's state_dict keys.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 
 import torch
@@ -141,6 +142,11 @@ class NetBase:
         # normalisation itself then see the unrounded fp32 accumulator; activations/gradients use `dtype`
         self.pre_dtype = torch.float32
         self.fast_small = True  # direct kernels for the 3-channel boundary layers (csrc/conv_small.cu)
+        # 3-input-channel convs as im2col3 + 1x1 tcgen05 conv instead of the direct kernel: measured on B200 at B=512 (A/B, 20
+        # steps, twice): 12.97 ms/step with it, 12.80 without -- the 1x1 conv is bound by its 201 MB of output writes either
+        # way (pure-write streams run at ~3.3 TB/s here) and the im2col pass costs more than the FMA work it removes.  Opt-in.
+        self.tc_first = bool(os.environ.get("COMBAT_TC_FIRST"))
+        self._w64 = {}
         self.last_stats_nblk = 0
         self.convs: dict[str, ConvSpec] = {}
 
@@ -169,6 +175,38 @@ class NetBase:
     def prep_weights(self):
         """master OIHW float32 -> compute layouts (OHWI and flipped/transposed for dgrad) in the compute dtype."""
         ops.prep_weights(self.store.flat, self.wbuf, self._wtable, self._n_wdesc, self._wmax)
+        for (name, dgrad), w64 in self._w64.items():  # [rows][27] -> [rows][27 | 0 | 27 | 0] (hi and lo halves of im2col3)
+            cs = self.convs[name]
+            rows = cs.Cin if dgrad else cs.Cout
+            off = cs.dgrad_off if dgrad else cs.fwd_off
+            src = self.wbuf[off:off + rows * 27].view(rows, 27)
+            w64[:, 0:27].copy_(src)
+            w64[:, 32:59].copy_(src)
+
+    def _use_im2col(self, cs: "ConvSpec", rows, n_in):
+        """3 input channels, 3x3, pad 1, `rows` (a multiple of 64) output channels on the bf16 tensor-core path."""
+        return self.use_tc and self.tc_first and n_in == 3 and cs.k == 3 and cs.pad == 1 and rows % 64 == 0
+
+    def _w64_for(self, cs: "ConvSpec", dgrad=False):
+        key = (cs.name, dgrad)
+        if key not in self._w64:
+            rows = cs.Cin if dgrad else cs.Cout
+            self._w64[key] = torch.zeros((rows, 64), dtype=self.dtype, device=self.device)
+            self.prep_weights()
+        return self._w64[key]
+
+    def cin3_tc(self, x_nchw, w64, rows, stride, out, bias=None, out2=None, bn_relu=None, stats=False, tag=""):
+        """3 -> rows conv of an NCHW float32 image on the tensor cores: im2col3 + 1x1 tcgen05 conv (same epilogues)."""
+        A = ops.im2col3(x_nchw, stride)
+        N, Ho, Wo, _ = A.shape
+        want_stats = stats and out is not None and out.dtype == torch.float32
+        d = ops.conv_tc_desc(A, w64.data_ptr(), out, N, Ho, Wo, 64, Ho, Wo, rows, 1, 1, 1, 0, 1, bias=bias, out2=out2,
+                             scale2=bn_relu[0] if bn_relu is not None else None, shift2=bn_relu[1] if bn_relu is not None else None,
+                             stats=ops.Scratch.get(self.device) if want_stats else None)
+        _tc_launch(lambda: lib.combat_conv_tc(C.byref(d), ops._s()), "conv_tc", 2.0 * N * Ho * Wo * rows * 27,
+                   "N%d %dx%d 3->%d k3 s%d im2col%s" % (N, Ho * stride, Wo * stride, rows, stride, tag))
+        self.last_stats_nblk = lib.combat_conv_tc_last_grid() if want_stats else 0
+        return out
 
     def zero_grad(self):
         self.store.grad.zero_()
@@ -264,13 +302,19 @@ class NetBase:
                             Ci=cs.Cin, Co=cs.Cout, KH=cs.k, KW=cs.k, stride=cs.stride, pad=cs.pad, db=db)
 
     # ---- image-boundary convs (NCHW float32 on the 3-channel side), always CUDA-core kernels
-    def conv_first_fwd(self, x_nchw, cs: ConvSpec, out=None, out_ctot=None, pre=True, bn_relu=None):
+    def conv_first_fwd(self, x_nchw, cs: ConvSpec, out=None, out_ctot=None, pre=True, bn_relu=None, stats=False):
         N, Cc, H, W = x_nchw.shape
         Ho = (H + 2 * cs.pad - cs.k) // cs.stride + 1
         Wo = (W + 2 * cs.pad - cs.k) // cs.stride + 1
         Ct = cs.Cout if out_ctot is None else out_ctot
         if out is None:
             out = torch.empty((N, Ho, Wo, Ct), dtype=self.pre_dtype if pre else self.dtype, device=self.device)
+        self.last_stats_nblk = 0
+        if Ct == cs.Cout and self._use_im2col(cs, cs.Cout, Cc):
+            out2 = torch.empty((N, Ho, Wo, Ct), dtype=self.dtype, device=self.device) if bn_relu is not None else None
+            self.cin3_tc(x_nchw, self._w64_for(cs), cs.Cout, cs.stride, out, bias=self._bias(cs), out2=out2, bn_relu=bn_relu,
+                         stats=stats)
+            return (out, out2) if bn_relu is not None else out
         if self.fast_small and Cc == 3 and cs.k == 3 and cs.pad == 1 and Ct == cs.Cout and cs.Cout % 32 == 0 and 256 % cs.Cout == 0:
             if bn_relu is not None:
                 out2 = torch.empty((N, Ho, Wo, Ct), dtype=self.dtype, device=self.device)
@@ -288,6 +332,20 @@ class NetBase:
     def conv_first_wgrad(self, x_nchw, dy, cs: ConvSpec, dy_ctot=None):
         N, Cc, H, W = x_nchw.shape
         _, Ho, Wo, Ct = dy.shape
+        if Ct == cs.Cout and dy.dtype == torch.bfloat16 and self._use_im2col(cs, cs.Cout, Cc):
+            # dW'[co][64] over the im2col operand (recomputed: 20 us, cheaper than keeping 64 MB alive), then the hi and
+            # lo halves fold into dW[co][27]
+            A = ops.im2col3(x_nchw, cs.stride)
+            dw64 = torch.zeros((cs.Cout, 64), dtype=torch.float32, device=self.device)
+            d = ops.conv_tc_desc(A, None, None, N, Ho, Wo, 64, Ho, Wo, cs.Cout, 1, 1, 1, 0, 1)
+            _tc_launch(lambda: lib.combat_conv_tc_wgrad(C.byref(d), ops._p(dy), ops._p(dw64), ops._s()), "conv_tc_wgrad",
+                       2.0 * N * Ho * Wo * cs.Cout * 27, "N%d %dx%d 3->%d k3 s%d im2col" % (N, H, W, cs.Cout, cs.stride))
+            g = self.store.raw(self.store.grad, cs.name + ".weight").view(cs.Cout, 27)
+            g.add_(dw64[:, 0:27])
+            g.add_(dw64[:, 32:59])
+            if cs.bias:
+                ops.colsum(dy, cs.Cout, self.store.g(cs.name + ".bias"))
+            return
         if self.fast_small and Cc == 3 and cs.k == 3 and cs.pad == 1 and Ct == cs.Cout and cs.Cout % 32 == 0 and 256 % cs.Cout == 0:
             return ops.wgrad_cin3(x_nchw, dy, self.store.raw(self.store.grad, cs.name + ".weight"),
                                   self.store.g(cs.name + ".bias") if cs.bias else None, cs.Cout, cs.stride)
@@ -462,13 +520,14 @@ class Classifier(NetBase):
         if fuse and self.fuse_eval and not train and self.fast_small and x_nchw.shape[1] == 3 and x_nchw.shape[3] % 4 == 0:
             return self._forward_eval_fused(x_nchw, save)
         ctx = {"x": x_nchw, "train": train, "blocks": []} if save else None
-        h = self.conv_first_fwd(x_nchw, self.conv1)
+        h = self.conv_first_fwd(x_nchw, self.conv1, stats=train and pre)
+        h0_nblk = self.last_stats_nblk
         if not pre:
             c0 = h
             h, st0 = self._bn_fwd(self.bn1, c0, train, True)
             if save:
                 ctx["stem"] = (c0, h, st0)
-        h_nblk = 0  # partial-sum blocks of h left by its producer conv (train mode, tcgen05 path)
+        h_nblk = h0_nblk if (train and pre) else 0  # partial-sum blocks of h left by its producer conv (train mode, tcgen05 path)
         for blk in self.blocks:
             if pre:
                 o1, st1 = self._bn_fwd(blk["bn1"], h, train, True, stats_nblk=h_nblk)
@@ -710,7 +769,10 @@ class Generator(NetBase):
         d_a01 = torch.empty((N, H, W, nf), dtype=self.dtype, device=self.device)
         if self.fast_small and nf == 64 and self.out_channel == 3:
             ops.wgrad_cout3(a01, dz, self.store.raw(self.store.grad, cs.name + ".weight"), self.store.g(cs.name + ".bias"))
-            ops.conv_cin3(dz, self._wptr(cs, True), self.dt, d_a01, nf, 1)
+            if self._use_im2col(cs, nf, 3):  # input gradient of the 64 -> 3 conv == 3 -> 64 conv with the flipped filter
+                self.cin3_tc(dz, self._w64_for(cs, dgrad=True), nf, 1, d_a01, tag=" (dgrad)")
+            else:
+                ops.conv_cin3(dz, self._wptr(cs, True), self.dt, d_a01, nf, 1)
         else:
             ops.conv_wgrad_simt(a01, (N, H, W), ops.nhwc_strides(H, W, nf), dz, (H, W), nchw_o,
                                 self.store.raw(self.store.grad, cs.name + ".weight"),

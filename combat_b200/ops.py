@@ -246,6 +246,15 @@ def conv_wgrad_simt(x, x_geom, x_strides, dy, dy_geom, dy_strides, dw, *, Ci, Co
     check(lib.combat_conv_wgrad_simt(C.byref(d), _p(dy), dt_code(dy), _p(dw), _s()), "conv_wgrad_simt")
 
 
+def im2col3(x_nchw, stride):
+    """3-channel NCHW float32 image -> bf16 [N, Ho, Wo, 64] im2col operand ([hi | lo] halves) of the tensor-core path."""
+    N, _, H, W = x_nchw.shape
+    Ho, Wo = (H + 2 - 3) // stride + 1, (W + 2 - 3) // stride + 1
+    A = torch.empty((N, Ho, Wo, 64), dtype=torch.bfloat16, device=x_nchw.device)
+    check(lib.combat_im2col3(_p(x_nchw), _p(A), N, H, W, stride, _s()), "im2col3")
+    return A
+
+
 def conv_cin3(x_nchw, w_ptr, w_dt, out, Co, stride, bias=None, act=0, post_scale=None, post_shift=None, out2=None,
               scale2=None, shift2=None):
     N, _, H, W = x_nchw.shape

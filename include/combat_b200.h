@@ -132,6 +132,9 @@ int combat_conv_wgrad_simt(const combat_conv_desc* d_host, const void* dy, int d
  *   conv_cout3 : in NHWC [N,H,W,64], w [3][9][64] -> out NCHW float32 [N,3,H,W] (stride 1); act 0 none / 1 tanh
  *   wgrad_cin3 : dw[Co][9][3] += sum dy[pix][co] * x[pix@tap][ci], db[co] += sum dy      (x NCHW float32, dy NHWC)
  *   wgrad_cout3: dw[3][9][64] += sum dz[n,co,h,w] * a[pix@tap][ci], db[co] += sum dz     (a NHWC, dz NCHW float32) */
+/* im2col of a 3-channel NCHW float32 image for the tensor-core path: A[N,Ho,Wo,64] bf16 = [hi(27) | 0 | lo(27) | 0]
+ * (3x3, pad 1, stride 1|2); a 3 -> Co conv is then combat_conv_tc over A as a 1x1 conv with the filter stored twice. */
+int combat_im2col3(const float* x, void* A_bf16, int N, int H, int W, int stride, void* stream);
 int combat_conv_cin3(const float* x, const void* w, int w_dtype, const float* bias, void* out, int out_dtype, int N, int H,
                      int W, int Co, int stride, int act, const float* post_scale, const float* post_shift, void* out2,
                      const float* scale2, const float* shift2, void* stream);

@@ -562,3 +562,35 @@ def test_conv_tc_fused_batchnorm_epilogues(ops, stride_up):
         check(lib.combat_conv_tc(C.byref(d2), ops._s()), "conv_tc dgrad")
         torch.cuda.synchronize()
         assert rel(dx.float().permute(0, 3, 1, 2), exp) < 6e-3
+
+
+@pytest.mark.parametrize("stride,N,H", [(1, 5, 16), (2, 6, 32), (1, 3, 24)])
+def test_im2col3_tensor_core_conv(ops, stride, N, H):
+    """3 -> 64 conv as im2col3 ([hi | lo] bf16 halves of the float32 image) + 1x1 tcgen05 conv with the filter stored twice:
+    the image enters with ~16 mantissa bits, so only the bf16 rounding of the FILTER separates it from float32."""
+    import ctypes as C
+
+    from combat_b200._lib import check, lib
+    g = torch.Generator().manual_seed(50 + stride)
+    Co = 64
+    x = torch.randn(N, 3, H, H, generator=g) * 3.0
+    w = (torch.randn(Co, 3, 3, 3, generator=g) * 0.2).bfloat16().float()
+    bias = torch.randn(Co, generator=g)
+    y = F.conv2d(x, w, bias, stride, 1)
+    Ho = y.shape[2]
+    A = ops.im2col3(dev(x), stride)
+    assert A.shape == (N, Ho, Ho, 64) and A.dtype == torch.bfloat16
+    # the operand itself: hi + lo reproduces the patch to 2^-16 relative, padding columns are zero
+    patches = F.unfold(x, 3, padding=1, stride=stride).view(N, 3, 9, Ho, Ho).permute(0, 3, 4, 2, 1).reshape(N, Ho, Ho, 27)
+    Af = A.float().cpu()
+    assert float((Af[..., :27] + Af[..., 32:59] - patches).abs().max()) <= 2e-5 * float(patches.abs().max())
+    assert float(Af[..., 27:32].abs().max()) == 0 and float(Af[..., 59:].abs().max()) == 0
+    w64 = torch.zeros(Co, 64, dtype=torch.bfloat16)
+    w64[:, :27] = w.permute(0, 2, 3, 1).reshape(Co, 27).bfloat16()
+    w64[:, 32:59] = w64[:, :27]
+    w64 = dev(w64)
+    out = torch.empty(N, Ho, Ho, Co, device="cuda")
+    d = ops.conv_tc_desc(A, w64.data_ptr(), out, N, Ho, Ho, 64, Ho, Ho, Co, 1, 1, 1, 0, 1, bias=dev(bias))
+    check(lib.combat_conv_tc(C.byref(d), ops._s()), "conv_tc")
+    torch.cuda.synchronize()
+    assert rel(out.permute(0, 3, 1, 2), y) < 2e-5
