@@ -31,13 +31,13 @@ __global__ void __launch_bounds__(1024) cross_entropy_k(const float* __restrict_
       for (int c = 0; c < 16; ++c)
         if (c < C) s += expf(v[c] - m);
       const float lse = m + logf(s);
-      const int t = (int)tgt[b];
+      const int t = (int)tgt[b];  // t < 0: row ignored (no loss, no gradient, never counted) -- eval() masks rows this way
       if (dlogits) {
 #pragma unroll
         for (int c = 0; c < 16; ++c)
-          if (c < C) dlogits[(long long)b * C + c] = gscale * invB * (expf(v[c] - lse) - (c == t ? 1.f : 0.f));
+          if (c < C) dlogits[(long long)b * C + c] = t < 0 ? 0.f : gscale * invB * (expf(v[c] - lse) - (c == t ? 1.f : 0.f));
       }
-      float vt = 0.f;
+      float vt = lse;
 #pragma unroll
       for (int c = 0; c < 16; ++c)
         if (c == t) vt = v[c];
@@ -72,15 +72,15 @@ __global__ void __launch_bounds__(1024) cross_entropy_k(const float* __restrict_
     for (int c = lane; c < C; c += 32) s += expf(row[c] - m);
     s = warp_sum(s);
     const float lse = m + logf(s);
-    const int t = (int)tgt[b];
+    const int t = (int)tgt[b];  // t < 0: row ignored
     if (dlogits) {
       for (int c = lane; c < C; c += 32) {
         float p = expf(row[c] - lse);
-        dlogits[(long long)b * C + c] = gscale * invB * (p - (c == t ? 1.f : 0.f));
+        dlogits[(long long)b * C + c] = t < 0 ? 0.f : gscale * invB * (p - (c == t ? 1.f : 0.f));
       }
     }
     if (lane == 0) {
-      loss_acc += lse - row[t];
+      if (t >= 0) loss_acc += lse - row[t];
       c1 += (am == t);
       if (tgt2) c2 += (am == (int)tgt2[b]);
     }

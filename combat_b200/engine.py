@@ -382,6 +382,72 @@ class AlternatedStep:
             out["debug"] = dbg
         return out
 
+    # ------------------------------------------------------------ evaluation (train_generator.py:355-391)
+    def eval_step(self, x_dev, y_host, sigma=None, use_graph=False):
+        """One batch of eval(): clean accuracy of netC, attack success on the NON-TARGET samples, detector and clean-model
+        legs.  The trigger is built for every row of the fixed-shape batch (eval-mode networks and the blur are per-sample
+        independent, so the non-target rows are bit-identical to the reference's gathered sub-batch) and the target rows are
+        masked out of the counters with a negative label; one blur sigma per batch, drawn like torchvision's GaussianBlur.
+        Returns device int32 counts [clean, -, bd, -, F, -, clean_model, -, bd_ba, bd_asr] and the host-side n_bd."""
+        o = self.opt
+        y = np.asarray(y_host, dtype=np.int64)
+        if sigma is None:
+            sigma = torch.empty(1).uniform_(o.sigma[0], o.sigma[1]).item()
+        bd = create_targets_bd_np(y, o)
+        ntrg = y != o.target_label
+        B = len(y)
+        b = self._ensure_bufs(B)
+        eb = b.setdefault("eval", {})
+        if not eb:
+            dev = self.device
+            eb["h"] = torch.empty((4, B), dtype=torch.int64).pin_memory()
+            eb["t"] = torch.empty((4, B), dtype=torch.int64, device=dev)   # y | bd masked | ones masked | y masked
+            eb["counts"] = torch.zeros(16, dtype=torch.int32, device=dev)
+            eb["graph"] = None
+        h = eb["h"]
+        h[0].copy_(torch.from_numpy(y))
+        h[1].copy_(torch.from_numpy(np.where(ntrg, bd, -1)))
+        h[2].copy_(torch.from_numpy(np.where(ntrg, 1, -1).astype(np.int64)))
+        h[3].copy_(torch.from_numpy(np.where(ntrg, y, -1)))
+        eb["t"].copy_(h, non_blocking=True)
+        b["x"].copy_(x_dev, non_blocking=True)
+        k0, k1 = ops.gaussian_taps(sigma)
+        b["h_small"][2], b["h_small"][3] = k0, k1
+        b["taps_g"].copy_(b["h_small"][2:4], non_blocking=True)
+
+        def launch():
+            x, t, counts = b["x"], eb["t"], eb["counts"]
+            preds_clean, _ = self.netC.forward(x, train=False, save=False)                          # :360
+            ops.cross_entropy(preds_clean, t[0], 1.0, False, counts_out=counts[0:2])
+            noise_raw, _ = self.netG.forward(x, None, save=False)                                    # :369
+            noise = ops.plane_op(noise_raw, "lowfreq", keep=self.keep)                               # :370
+            x_bd = ops.poison_blend_fwd(x, noise, None, B, o.noise_rate, None, taps_dev=b["taps_g"])  # :372-373
+            preds_bd, _ = self.netC.forward(x_bd, train=False, save=False)                          # :375
+            ops.cross_entropy(preds_bd, t[1], 1.0, False, counts_out=counts[2:4])
+            if self.netF is not None:
+                preds_F = self.netF.forward(ops.plane_op(x_bd, "dct", in_mode=2))                    # :381-383
+                ops.cross_entropy(preds_F, t[2], 1.0, False, counts_out=counts[4:6])
+            cm_clean, _ = self.clean.forward(x, train=False, save=False)                             # :387
+            ops.cross_entropy(cm_clean, t[0], 1.0, False, counts_out=counts[6:8])
+            cm_bd, _ = self.clean.forward(x_bd, train=False, save=False)                             # :389
+            ops.cross_entropy(cm_bd, t[3], 1.0, False, targets2=t[1], counts_out=counts[8:10])
+            return dict(preds_clean=preds_clean, preds_bd=preds_bd, x_bd=x_bd, cm_clean=cm_clean, cm_bd=cm_bd)
+
+        dbg = None
+        if use_graph:
+            if eb["graph"] is None:
+                launch()
+                torch.cuda.current_stream().synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    eb["keep"] = launch()
+                eb["graph"] = g
+            else:
+                eb["graph"].replay()
+        else:
+            dbg = launch()
+        return {"counts": eb["counts"], "n_bd": int(ntrg.sum()), "n": B, "sigma": sigma, "debug": dbg}
+
     @staticmethod
     def unpack(out) -> dict:
         """One D2H read of the step's scalars (call sparingly)."""

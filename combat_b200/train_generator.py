@@ -155,6 +155,54 @@ def train(netC, optimizerC, schedulerC, netG, optimizerG, schedulerG, netF, clea
     schedulerG.step()
 
 
+def eval(netC, optimizerC, schedulerC, netG, optimizerG, schedulerG, netF, clean_model, test_dl, best_clean_acc, best_bd_acc,
+         best_F_acc, best_clean_model_acc, best_clean_model_bd_ba, best_clean_model_bd_asr, tf_writer, epoch, opt):
+    """train_generator.py:321-465: clean accuracy, attack success on every non-target sample, detector and clean-model
+    legs; saves the reference's checkpoint dict to opt.ckpt_path when the clean accuracy improves.  Returns the six bests."""
+    print(" Eval:")
+    netC.eval()
+    eng = _engine_for(netC, clean_model, netG, netF, opt)
+    use_graph = not getattr(opt, "no_graph", False)
+    dev = netC.net.device
+    tot = torch.zeros(16, dtype=torch.int64, device=dev)
+    n_clean = n_bd = 0
+    for inputs, targets in test_dl:
+        y_host = targets.cpu().numpy() if torch.is_tensor(targets) else np.asarray(targets)
+        if not inputs.is_cuda:
+            inputs = inputs.pin_memory()
+        out = eng.eval_step(inputs, y_host, use_graph=use_graph)
+        tot += out["counts"].long()
+        n_clean += out["n"]
+        n_bd += out["n_bd"]
+    c = tot.cpu().numpy()
+    n_bd_ = max(n_bd, 1)
+    acc_clean, acc_bd, acc_F = c[0] * 100.0 / n_clean, c[2] * 100.0 / n_bd_, c[4] * 100.0 / n_bd_
+    acc_clean_model, bd_ba_clean_model, bd_asr_clean_model = c[6] * 100.0 / n_clean, c[8] * 100.0 / n_bd_, c[9] * 100.0 / n_bd_
+    print("Clean Acc: {:.4f} - Best: {:.4f} | Bd Acc: {:.4f} - Best: {:.4f} | F Acc: {:.4f} - Best: {:.4f} | Clean Model Acc: {:.4f} - "
+          "Best: {:.4f} | Clean Model Bd BA: {:.4f} - Best: {:.4f} | Clean Model Bd ASR: {:.4f} - Best: {:.4f}".format(
+              acc_clean, best_clean_acc, acc_bd, best_bd_acc, acc_F, best_F_acc, acc_clean_model, best_clean_model_acc,
+              bd_ba_clean_model, best_clean_model_bd_ba, bd_asr_clean_model, best_clean_model_bd_asr))
+    if not epoch % 1:
+        tf_writer.add_scalars("Test Accuracy", {"Clean": acc_clean, "Bd": acc_bd, "F": acc_F, "Clean Model Acc": acc_clean_model,
+                                                "Clean Model Bd BA": bd_ba_clean_model, "Clean Model Bd ASR": bd_asr_clean_model}, epoch)
+    if acc_clean > best_clean_acc or (acc_clean == best_clean_acc and acc_bd > best_bd_acc):  # :433
+        print(" Saving...")
+        best_clean_acc, best_bd_acc, best_F_acc = acc_clean, acc_bd, acc_F
+        best_clean_model_acc, best_clean_model_bd_ba, best_clean_model_bd_asr = acc_clean_model, bd_ba_clean_model, bd_asr_clean_model
+        state_dict = {
+            "netC": netC.state_dict(), "schedulerC": schedulerC.state_dict(), "optimizerC": optimizerC.state_dict(),
+            "netG": netG.state_dict(), "schedulerG": schedulerG.state_dict(), "optimizerG": optimizerG.state_dict(),
+            "clean_model": clean_model.state_dict(), "best_clean_acc": acc_clean, "best_bd_acc": acc_bd, "best_F_acc": acc_F,
+            "best_clean_model_acc": best_clean_model_acc, "best_clean_model_bd_ba": best_clean_model_bd_ba,
+            "best_clean_model_bd_asr": best_clean_model_bd_asr, "epoch_current": epoch,
+        }
+        ckpt_dir = os.path.dirname(opt.ckpt_path)
+        if ckpt_dir:
+            os.makedirs(ckpt_dir, exist_ok=True)
+        torch.save(state_dict, opt.ckpt_path)
+    return (best_clean_acc, best_bd_acc, best_F_acc, best_clean_model_acc, best_clean_model_bd_ba, best_clean_model_bd_asr)
+
+
 class _NullWriter:
     def add_scalars(self, *a, **k):
         pass

@@ -76,6 +76,8 @@ int combat_poison_blend_bwd(const float* x, const float* noise, const float* x_b
  *   loss_out[0]  = mean_b( logsumexp(logits[b]) - logits[b, t[b]] )
  *   dlogits[b,c] = grad_scale * (softmax(logits[b])[c] - [c == t[b]]) / B      (dlogits may be NULL)
  *   counts_out[0] = #{b: argmax == t[b]},  counts_out[1] = #{b: argmax == t2[b]} (t2 may be NULL)
+ * A negative target marks an ignored row: no loss, zero gradient, never counted (the mean still divides by B) -- used by
+ * the evaluation loop (train_generator.py:366-391) to count only the non-target samples of a fixed-shape batch.
  */
 int combat_cross_entropy(const float* logits, const long long* targets, const long long* targets2, int B, int C,
                          float grad_scale, float* loss_out, float* dlogits, int* counts_out, void* stream);

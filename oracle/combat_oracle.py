@@ -450,6 +450,39 @@ def alternated_step(state: dict, x: torch.Tensor, y: torch.Tensor, opt, with_met
 
 
 # --------------------------------------------------------------------------
+# evaluation loop (train_generator.py:321-465), one batch
+# --------------------------------------------------------------------------
+
+
+def eval_batch(state: dict, x: torch.Tensor, y: torch.Tensor, opt) -> dict:
+    """One iteration of eval() (:355-391): clean accuracy of netC, attack success on ALL non-target samples, detector
+    and clean-model legs.  RNG: one torch uniform per batch (GaussianBlur.get_params, :372)."""
+    fwdC = CLASSIFIERS[opt.classifier]
+    netC_p, netC_b, netG_p = state["netC_p"], state["netC_b"], state["netG_p"]
+    clean_p, clean_b = state["clean_p"], state["clean_b"]
+    am = lambda t: torch.argmax(t, dim=1)
+    out = {}
+    with torch.no_grad():
+        preds_clean = fwdC(netC_p, netC_b, x, False)  # :360
+        ntrg = (y != opt.target_label).nonzero()[:, 0]  # :366
+        x_sel, y_sel = x[ntrg], y[ntrg]
+        sigma = draw_sigma(*opt.sigma)
+        x_bd, _, _ = make_bd(netG_p, x_sel, opt, sigma)  # :369-373
+        bd_t = create_targets_bd(y_sel, opt.attack_mode, opt.target_label, opt.num_classes)
+        preds_bd = fwdC(netC_p, netC_b, x_bd, False)
+        inputs_F = dct_2d(((x_bd + 1) / 2 * 255).byte())  # :381
+        preds_F = frequency_model_forward(state["netF_p"], state["netF_b"], inputs_F)
+        cm_clean = fwdC(clean_p, clean_b, x, False)
+        cm_bd = fwdC(clean_p, clean_b, x_bd, False)
+    out.update(sigma=sigma, ntrg=ntrg, x_bd=x_bd, preds_clean=preds_clean, preds_bd=preds_bd, preds_F=preds_F, cm_clean=cm_clean,
+               cm_bd=cm_bd, n_clean=len(x), n_bd=len(ntrg),
+               clean_correct=int((am(preds_clean) == y).sum()), bd_correct=int((am(preds_bd) == bd_t).sum()),
+               F_correct=int((am(preds_F) == 1).sum()), cm_correct=int((am(cm_clean) == y).sum()),
+               cm_bd_ba=int((am(cm_bd) == y_sel).sum()), cm_bd_asr=int((am(cm_bd) == bd_t).sum()))
+    return out
+
+
+# --------------------------------------------------------------------------
 # multilabel variant (train_generator_multilabel.py:160-242): conditional generator, class-chunked G-step
 # --------------------------------------------------------------------------
 

@@ -320,8 +320,40 @@ def gen_mstep(name, dataset, B, n_batches, seed):
     save(name, **out)
 
 
+def gen_eval(name, B, n_batches, seed):
+    """The UNMODIFIED eval() of the reference (train_generator.py:321-465) over synthetic batches."""
+    import tempfile
+    opt = get_opt()
+    opt.input_height = opt.input_width = 32
+    opt.input_channel = 3
+    opt.ckpt_path = os.path.join(tempfile.mkdtemp(), "ckpt.pth.tar")
+    seed_all(seed)
+    netC, optC, schC, netG, optG, schG, netF, clean = tg.get_model(opt)
+    netF.eval()
+    clean.eval()
+    netG.eval()
+    batches = [(torch.rand(B, 3, 32, 32) * 2 - 1, torch.randint(0, 10, (B,))) for _ in range(n_batches)]
+    rec = Recorder(netC, netG, clean, netF)
+    with rec:
+        best = tg.eval(netC, optC, schC, netG, optG, schG, netF, clean, batches, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, NullWriter(), 1, opt)
+    ck = torch.load(opt.ckpt_path, weights_only=False)
+    out = {"seed": seed, "B": B, "n_batches": n_batches, "sigmas": np.array(rec.sigmas), "best": np.array([float(b) for b in best]),
+           "ckpt_keys": np.array(sorted(ck.keys())), "ckpt_netC_keys": np.array(list(ck["netC"].keys()))}
+    for i, (x, y) in enumerate(batches):
+        out["y_%d" % i] = y
+        out["preds_clean_%d" % i] = rec.calls["netC"][2 * i][1]
+        out["preds_bd_%d" % i] = rec.calls["netC"][2 * i + 1][1]
+        out["x_bd_%d" % i] = rec.calls["netC"][2 * i + 1][0]
+        out["preds_F_%d" % i] = rec.calls["netF"][i][1]
+        out["cm_clean_%d" % i] = rec.calls["clean"][2 * i][1]
+        out["cm_bd_%d" % i] = rec.calls["clean"][2 * i + 1][1]
+    save(name, **out)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["dct", "modules", "step"]
+    if "eval" in which:
+        gen_eval("eval_b64x2.npz", 64, 2, 5)
     if "mstep" in which:
         gen_mstep("mstep_cifar_b24x2.npz", "cifar10", 24, 2, 3)   # 10 classes, chunks of 3 (last chunk short: 24 = 7*3+3)
         gen_mstep("mstep_celeba_b12.npz", "celeba", 12, 1, 4)     # CelebA shape 64x64, 8 classes, ResNet18 + CUnetGeneratorv1
