@@ -146,6 +146,7 @@ class NetBase:
         # steps, twice): 12.97 ms/step with it, 12.80 without -- the 1x1 conv is bound by its 201 MB of output writes either
         # way (pure-write streams run at ~3.3 TB/s here) and the im2col pass costs more than the FMA work it removes.  Opt-in.
         self.tc_first = bool(os.environ.get("COMBAT_TC_FIRST"))
+        self.tc_first_wgrad = not os.environ.get("COMBAT_NO_TC_FIRST_WGRAD")  # the weight gradient of those convs through im2col3
         self._w64 = {}
         self.last_stats_nblk = 0
         self.convs: dict[str, ConvSpec] = {}
@@ -183,9 +184,10 @@ class NetBase:
             w64[:, 0:27].copy_(src)
             w64[:, 32:59].copy_(src)
 
-    def _use_im2col(self, cs: "ConvSpec", rows, n_in):
+    def _use_im2col(self, cs: "ConvSpec", rows, n_in, wgrad=False):
         """3 input channels, 3x3, pad 1, `rows` (a multiple of 64) output channels on the bf16 tensor-core path."""
-        return self.use_tc and self.tc_first and n_in == 3 and cs.k == 3 and cs.pad == 1 and rows % 64 == 0
+        on = self.tc_first_wgrad if wgrad else self.tc_first
+        return self.use_tc and on and n_in == 3 and cs.k == 3 and cs.pad == 1 and rows % 64 == 0
 
     def _w64_for(self, cs: "ConvSpec", dgrad=False):
         key = (cs.name, dgrad)
@@ -336,7 +338,7 @@ class NetBase:
     def conv_first_wgrad(self, x_nchw, dy, cs: ConvSpec, dy_ctot=None):
         N, Cc, H, W = x_nchw.shape
         _, Ho, Wo, Ct = dy.shape
-        if Ct == cs.Cout and dy.dtype == torch.bfloat16 and self._use_im2col(cs, cs.Cout, Cc):
+        if Ct == cs.Cout and dy.dtype == torch.bfloat16 and self._use_im2col(cs, cs.Cout, Cc, wgrad=True):
             # dW'[co][64] over the im2col operand (recomputed: 20 us, cheaper than keeping 64 MB alive), then the hi and
             # lo halves fold into dW[co][27]
             A = ops.im2col3(x_nchw, cs.stride)
