@@ -201,14 +201,23 @@ def run_ours(args):
 
     # ---- end-to-end leg: host batch in, host scalars out, every step
     sink = []
+    pend = [None]
 
     def step_e2e(i):
+        # the public loop (combat_b200.train_generator.train): this batch's pinned host tensor in, the NEXT batch's copy
+        # started on the side stream while the graph runs, every step's scalars copied to the host (stream-ordered after
+        # the step) and consumed one iteration later so that the host never drains the GPU queue
         out = eng.step(xs_host[i % n_host], ys_host[i % n_host], use_graph=use_graph)
-        sink.append(AlternatedStep.unpack(out)["loss_c"])
+        eng.prefetch(xs_host[(i + 1) % n_host])
+        p, pend[0] = pend[0], eng.read_async(out)
+        if p is not None:
+            sink.append(p.get()["loss_c"])
 
     for i in range(2):
         step_e2e(i)
     ms_e2e = timed(step_e2e, args.steps)
+    sink.append(pend[0].get()["loss_c"])  # the last step's scalars (their copy was enqueued inside the timed region)
+    assert all(np.isfinite(v) for v in sink)
     e2e = world * B * args.steps / (ms_e2e / 1e3)
     h2d = xs_host[0].numel() * 4 + B * 8 * 3 + B * 4 + 20
     d2h = 8 * 4 + 16 * 4

@@ -334,6 +334,40 @@ class AlternatedStep:
             self.launches_per_step = launch_count() - n0
         return st if keep_debug else None
 
+    def prefetch(self, x_host):
+        """Start the host->device copy of the NEXT batch on a side stream while the current iteration runs; a following
+        `step(x_host, ...)` with the same tensor waits for it and takes a device-to-device copy instead of a PCIe one."""
+        if x_host.is_cuda:
+            return
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._stage = {}
+        buf = self._stage.get(tuple(x_host.shape))
+        if buf is None:
+            buf = self._stage[tuple(x_host.shape)] = torch.empty(x_host.shape, dtype=torch.float32, device=self.device)
+        # only the previous consumer of the staging buffer (last step's device-to-device copy) must have finished -- NOT the
+        # iteration that was just launched, which is what this copy overlaps with
+        free = getattr(self, "_stage_free", None)
+        if free is not None:
+            self._copy_stream.wait_event(free)
+        with torch.cuda.stream(self._copy_stream):
+            buf.copy_(x_host, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        self._prefetched = (x_host, buf, ev)
+
+    def _take_input(self, x, dst):
+        pf = getattr(self, "_prefetched", None)
+        if pf is not None and pf[0] is x:
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_event(pf[2])
+            dst.copy_(pf[1], non_blocking=True)
+            self._stage_free = torch.cuda.Event()
+            self._stage_free.record(cur)
+            self._prefetched = None
+        else:
+            dst.copy_(x, non_blocking=True)
+
     def step(self, x_dev, y_host, plan: StepPlan | None = None, use_graph=False, keep_debug=False):
         """One alternated iteration.  x_dev: float32 NCHW tensor already on the device (or a pinned host tensor,
         which is copied asynchronously); y_host: host labels.  Returns {'losses': dev[8], 'counts': dev[16]}."""
@@ -341,7 +375,7 @@ class AlternatedStep:
             plan = make_plan_multilabel(y_host, self.opt) if self.multilabel else make_plan(y_host, self.opt)
         B = len(plan.perm)
         b = self._ensure_bufs(B)
-        b["x"].copy_(x_dev, non_blocking=True)
+        self._take_input(x_dev, b["x"])
         self.upload_plan(y_host, plan)
         dbg = None
         if use_graph and not keep_debug:
@@ -448,12 +482,39 @@ class AlternatedStep:
             dbg = launch()
         return {"counts": eb["counts"], "n_bd": int(ntrg.sum()), "n": B, "sigma": sigma, "debug": dbg}
 
+    class _Pending:
+        """Handle of an asynchronous device->host read of a step's scalars (stream-ordered right after that step)."""
+
+        def __init__(self, l, c, ev):
+            self._l, self._c, self._ev = l, c, ev
+
+        def get(self) -> dict:
+            self._ev.synchronize()
+            return AlternatedStep._to_dict(self._l.numpy().copy(), self._c.numpy().copy())
+
+    def read_async(self, out):
+        """Enqueue the device->host copy of this step's losses / counters into pinned memory and return a handle; calling
+        `.get()` one iteration later keeps the host from draining the GPU queue after every step."""
+        slot = getattr(self, "_rd_slot", 0)
+        self._rd_slot = slot ^ 1
+        if getattr(self, "_rd_bufs", None) is None:
+            self._rd_bufs = [(torch.empty(8, dtype=torch.float32).pin_memory(), torch.empty(16, dtype=torch.int32).pin_memory())
+                             for _ in range(2)]
+        l, c = self._rd_bufs[slot]
+        l.copy_(out["losses"], non_blocking=True)
+        c.copy_(out["counts"], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        return AlternatedStep._Pending(l, c, ev)
+
     @staticmethod
-    def unpack(out) -> dict:
-        """One D2H read of the step's scalars (call sparingly)."""
-        l = out["losses"].cpu().numpy()
-        c = out["counts"].cpu().numpy()
+    def _to_dict(l, c) -> dict:
         return dict(loss_c=float(l[0]), loss_ce=float(l[1]), loss_l2=float(l[2]), clean_model_loss=float(l[3]),
                     n_total_correct=int(c[0]), n_clean_model_correct=int(c[2]), n_clean_correct=int(c[4]),
                     n_bd_correct=int(c[6]), n_clean_model_bd_ba=int(c[8]), n_clean_model_bd_asr=int(c[9]),
                     n_F_correct=int(c[10]))
+
+    @staticmethod
+    def unpack(out) -> dict:
+        """One D2H read of the step's scalars (call sparingly)."""
+        return AlternatedStep._to_dict(out["losses"].cpu().numpy(), out["counts"].cpu().numpy())

@@ -120,12 +120,22 @@ def train(netC, optimizerC, schedulerC, netG, optimizerG, schedulerG, netF, clea
     n_batches = len(train_dl)
     acc = {}
     inputs = None
-    for batch_idx, (inputs, targets) in enumerate(train_dl):
+    it = iter(train_dl)
+    nxt = next(it, None)
+    if nxt is not None and not nxt[0].is_cuda:
+        nxt = (nxt[0].pin_memory(), nxt[1])
+    batch_idx = -1
+    while nxt is not None:
+        batch_idx += 1
+        inputs, targets = nxt
         y_host = targets.cpu().numpy() if torch.is_tensor(targets) else np.asarray(targets)
         plan = make_plan(y_host, opt)
-        if not inputs.is_cuda:
-            inputs = inputs.pin_memory()
+        nxt = next(it, None)  # overlap the next batch's host->device copy with this iteration
+        if nxt is not None and not nxt[0].is_cuda:
+            nxt = (nxt[0].pin_memory(), nxt[1])
         out = eng.step(inputs, y_host, plan, use_graph=use_graph)
+        if nxt is not None:
+            eng.prefetch(nxt[0])
         tot += out["counts"].long()
         lsum += out["losses"].double()
         total_sample += len(y_host)
