@@ -185,6 +185,7 @@ class AlternatedStep:
         o = self.opt
         b = {"B": B}
         b["x"] = torch.empty((B, o.input_channel, o.input_height, o.input_width), dtype=torch.float32, device=dev)
+        b["x2"] = torch.empty((2 * B, o.input_channel, o.input_height, o.input_width), dtype=torch.float32, device=dev)  # [x ; x_bd]
         b["y"] = torch.empty(B, dtype=torch.int64, device=dev)
         b["bd_targets"] = torch.empty(B, dtype=torch.int64, device=dev)
         b["total_y"] = torch.empty(B, dtype=torch.int64, device=dev)
@@ -266,30 +267,56 @@ class AlternatedStep:
         noise = st["noise"]
         numel = x.numel()
         self.netC.sgd_step(self.lr_C)                                                        # :212
-        if self.with_metrics:
-            clean_preds, _ = self.clean.forward(x, train=False, save=False)                  # :214
-            ops.cross_entropy(clean_preds, y, 1.0, False, loss_out=losses[4:5], counts_out=counts[2:4])
-            st["clean_preds"] = clean_preds
         if self.multilabel:                                                                  # multilabel :203-221
             noise_raw, ctxG = self.netG.forward(x, b["bd_targets"], save=True)
             noise = ops.plane_op(noise_raw, "lowfreq", keep=self.keep)
             st.update(noise_raw=noise_raw, noise=noise, ctxG=ctxG)
-        x_bd = ops.poison_blend_fwd(x, noise, None, B, o.noise_rate, None, sq_partial=b["sq_partial"],
-                                    taps_dev=b["taps_g"], taps_rows=b["taps_rows"])          # :225-226
-        ops.sum_scale(b["sq_partial"], 1.0 / numel, out=losses[2:3])                         # :234
-        if self.with_metrics:
-            pred_clean, _ = self.netC.forward(x, train=False, save=False)                    # :227
+        batched = self.with_metrics and self.netC.fuse_eval and self.clean.fuse_eval
+        if batched:
+            # the metric forward on x (:214 / :227) and the forward on x_bd (:228 / :250) of each frozen-in-this-phase
+            # classifier run as ONE eval-mode forward over [x ; x_bd]: per-sample independent, so every output is
+            # bit-identical to two separate calls; half the launches, fuller waves on the deep layers.  Only the x_bd
+            # half of the saved state is back-propagated.
+            x2 = b["x2"]
+            x2[:B].copy_(x)
+            x_bd = ops.poison_blend_fwd(x, noise, None, B, o.noise_rate, None, out=x2[B:], sq_partial=b["sq_partial"],
+                                        taps_dev=b["taps_g"], taps_rows=b["taps_rows"])      # :225-226
+            ops.sum_scale(b["sq_partial"], 1.0 / numel, out=losses[2:3])                     # :234
+            lg, ctx2 = self.netC.forward(x2, train=False, save=True)
+            pred_clean, pred_bd = lg[:B], lg[B:]
             ops.cross_entropy(pred_clean, y, 1.0, False, loss_out=losses[5:6], counts_out=counts[4:6])
-            st["pred_clean"] = pred_clean
-        pred_bd, ctxB = self.netC.forward(x_bd, train=False, save=True)                      # :228
-        _, dl1, _ = ops.cross_entropy(pred_bd, b["bd_targets"], 1.0, True, loss_out=losses[1:2], counts_out=counts[6:8])
-        g1 = self.netC.backward(ctxB, dl1, need_wgrad=False, need_dx=True)
-        del ctxB
-        cm_preds, ctxK = self.clean.forward(x_bd, train=False, save=True)                    # :250
-        _, dl2, _ = ops.cross_entropy(cm_preds, y, o.clean_model_weight, True, targets2=b["bd_targets"],
-                                      loss_out=losses[3:4], counts_out=counts[8:10])          # :251,266-267
-        g2 = self.clean.backward(ctxK, dl2, need_wgrad=False, need_dx=True)
-        del ctxK
+            _, dl1, _ = ops.cross_entropy(pred_bd, b["bd_targets"], 1.0, True, loss_out=losses[1:2], counts_out=counts[6:8])
+            g1 = self.netC.backward(self.netC.slice_ctx(ctx2, B, 2 * B), dl1, need_wgrad=False, need_dx=True)
+            del ctx2
+            lgc, ctx2 = self.clean.forward(x2, train=False, save=True)
+            clean_preds, cm_preds = lgc[:B], lgc[B:]
+            ops.cross_entropy(clean_preds, y, 1.0, False, loss_out=losses[4:5], counts_out=counts[2:4])
+            _, dl2, _ = ops.cross_entropy(cm_preds, y, o.clean_model_weight, True, targets2=b["bd_targets"],
+                                          loss_out=losses[3:4], counts_out=counts[8:10])      # :251,266-267
+            g2 = self.clean.backward(self.clean.slice_ctx(ctx2, B, 2 * B), dl2, need_wgrad=False, need_dx=True)
+            del ctx2
+            st.update(clean_preds=clean_preds, pred_clean=pred_clean)
+        else:
+            if self.with_metrics:
+                clean_preds, _ = self.clean.forward(x, train=False, save=False)              # :214
+                ops.cross_entropy(clean_preds, y, 1.0, False, loss_out=losses[4:5], counts_out=counts[2:4])
+                st["clean_preds"] = clean_preds
+            x_bd = ops.poison_blend_fwd(x, noise, None, B, o.noise_rate, None, sq_partial=b["sq_partial"],
+                                        taps_dev=b["taps_g"], taps_rows=b["taps_rows"])      # :225-226
+            ops.sum_scale(b["sq_partial"], 1.0 / numel, out=losses[2:3])                     # :234
+            if self.with_metrics:
+                pred_clean, _ = self.netC.forward(x, train=False, save=False)                # :227
+                ops.cross_entropy(pred_clean, y, 1.0, False, loss_out=losses[5:6], counts_out=counts[4:6])
+                st["pred_clean"] = pred_clean
+            pred_bd, ctxB = self.netC.forward(x_bd, train=False, save=True)                  # :228
+            _, dl1, _ = ops.cross_entropy(pred_bd, b["bd_targets"], 1.0, True, loss_out=losses[1:2], counts_out=counts[6:8])
+            g1 = self.netC.backward(ctxB, dl1, need_wgrad=False, need_dx=True)
+            del ctxB
+            cm_preds, ctxK = self.clean.forward(x_bd, train=False, save=True)                # :250
+            _, dl2, _ = ops.cross_entropy(cm_preds, y, o.clean_model_weight, True, targets2=b["bd_targets"],
+                                          loss_out=losses[3:4], counts_out=counts[8:10])      # :251,266-267
+            g2 = self.clean.backward(ctxK, dl2, need_wgrad=False, need_dx=True)
+            del ctxK
         dnoise = ops.poison_blend_bwd(x, noise, x_bd, g1, g2, 2.0 * o.L2_weight / numel, o.noise_rate, None,
                                       taps_dev=b["taps_g"], taps_rows=b["taps_rows"])
         dnoise_raw = ops.plane_op(dnoise, "lowfreq", keep=self.keep)                          # P is symmetric

@@ -596,6 +596,19 @@ class Classifier(NetBase):
             ctx["feat_shape"], ctx["pooled"] = tuple(h.shape), pooled
         return logits, ctx
 
+    @staticmethod
+    def slice_ctx(ctx, lo, hi):
+        """The saved state of rows [lo, hi) of a fused eval-mode forward (batch-major tensors: slices are contiguous views) --
+        lets one forward over [x ; x_bd] serve a metric-only half and a half that is back-propagated."""
+        if not ctx.get("fused"):
+            raise RuntimeError("slice_ctx needs a fused eval-mode context")
+        out = dict(ctx)
+        out["x"] = ctx["x"][lo:hi]
+        out["blocks"] = [(o1[lo:hi], o2[lo:hi], s1, s2) for (o1, o2, s1, s2) in ctx["blocks"]]
+        out["pooled"] = ctx["pooled"][lo:hi]
+        out["feat_shape"] = (hi - lo,) + tuple(ctx["feat_shape"][1:])
+        return out
+
     def _backward_eval_fused(self, ctx, dlogits, need_dx):
         st = self.store
         dh = ops.pool_linear_bwd(dlogits, ctx["pooled"], st.p("linear.weight"), ctx["feat_shape"], self.dtype, 4, dW=None, db=None)
