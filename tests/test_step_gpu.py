@@ -235,3 +235,46 @@ def test_imagenet_shape_step_vs_oracle(name, dtype):
         assert e < (2e-4 if fp32 else 6e-2), (k, e)
     for k in ("loss_c", "loss_ce", "loss_l2", "clean_model_loss"):
         assert abs(s[k] - r[k]) < (5e-5 if fp32 else 2e-2) * max(1.0, abs(r[k])), (k, s[k], r[k])
+
+
+@pytest.mark.parametrize("case", ["no_target_rows", "all_target_rows", "ragged_batch"])
+def test_step_edge_cases_vs_oracle(case):
+    """Edge cases of the poison selection (train_generator.py:181-194): a batch without target-class samples (num_bd = 0:
+    the C-step blur sigma is NOT drawn and total_x is the untouched batch), a batch of only target-class samples, and a
+    batch size that is a multiple of nothing (37 rows: ragged tiles in every kernel).  float32 path, one iteration."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from combat_b200.engine import AlternatedStep, make_plan
+    B = 37 if case == "ragged_batch" else 24
+    state = seeded_state(41)
+    eng = make_engine(state, torch.float32)
+    g = torch.Generator().manual_seed(4)
+    x = torch.rand(B, 3, 32, 32, generator=g) * 2 - 1
+    if case == "no_target_rows":
+        y = torch.randint(1, 10, (B,), generator=g)
+    elif case == "all_target_rows":
+        y = torch.zeros(B, dtype=torch.long)
+    else:
+        y = torch.randint(0, 10, (B,), generator=g)
+        y[:5] = 0
+    np.random.seed(13)
+    torch.manual_seed(13)
+    r = O.alternated_step(state, x, y, O.default_opt())
+    after_ref = torch.rand(1).item()          # the torch CPU generator must have been consumed identically
+    np.random.seed(13)
+    torch.manual_seed(13)
+    plan = make_plan(y.numpy(), eng.opt)
+    assert torch.rand(1).item() == after_ref
+    assert plan.num_bd == r["num_bd"] and plan.sigma_c == r["sigma_c"] and plan.sigma_g == r["sigma_g"]
+    if case == "no_target_rows":
+        assert plan.num_bd == 0 and plan.sigma_c is None
+    out = eng.step(x.cuda(), y.numpy(), plan, keep_debug=True)
+    s = AlternatedStep.unpack(out)
+    d = out["debug"]
+    assert torch.equal(d["total_x"][plan.num_bd:].cpu(), r["total_x"][plan.num_bd:])
+    for k in ("total_x", "x_bd", "logits_c", "pred_bd", "clean_model_preds", "pred_clean"):
+        assert rel(d[k], r[k]) < 2e-4, (k, rel(d[k], r[k]))
+    for k in ("loss_c", "loss_ce", "loss_l2", "clean_model_loss"):
+        assert abs(s[k] - r[k]) < 5e-5 * max(1.0, abs(r[k])), (k, s[k], r[k])
+    for k in ("n_clean_correct", "n_bd_correct", "n_clean_model_correct", "n_clean_model_bd_ba", "n_clean_model_bd_asr"):
+        assert s[k] == r[k], k
