@@ -176,10 +176,10 @@ struct TcMaps {
 template <int BLOCK_N>
 struct TcCfg {
   static constexpr int A_BYTES = TILE_M * KCHUNK * 2;    // 16 KB
-  static constexpr int B_BYTES = BLOCK_N * KCHUNK * 2;   // 8 / 16 KB
+  static constexpr int B_BYTES = BLOCK_N * KCHUNK * 2;   // 8 / 16 / 32 KB
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BLOCK_N == 64 ? 7 : 5;
-  static constexpr int TMEM_COLS = 2 * BLOCK_N;          // two accumulator buffers (128 or 256: powers of two)
+  static constexpr int STAGES = BLOCK_N == 64 ? 7 : (BLOCK_N == 128 ? 5 : 3);
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;          // two accumulator buffers (128, 256 or 512: powers of two)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + TC_EPI_WARPS * 32 * EPI_ROWB /*epilogue*/;
 };
 
@@ -211,6 +211,10 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* stg_base
   const int quarter = warp & 3;
   const int half = (warp - 2) >> 2;
   constexpr int NCH = BLOCK_N / 64;  // 32-column chunks per warp
+  // 64- / 128-wide tiles prefetch the epilogue inputs of the whole tile (64-wide: one tile ahead); 256-wide tiles have K >=
+  // 2304 of MMA work per tile to hide the epilogue behind and load per chunk instead (the prefetch would need 128 registers)
+  constexpr bool PREFETCH = NCH <= 2;
+  constexpr int NPF = PREFETCH ? NCH : 1;
   const uint32_t stg = smem_u32(stg_base) + (warp - 2) * (32 * EPI_ROWB);  // explicit shared-space address
   constexpr bool FWD = MODE != 1;    // MODE 2 = MODE 0 + train-mode BatchNorm statistics of `out`
   constexpr bool STATS = MODE == 2;
@@ -230,7 +234,24 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* stg_base
     uint32_t okmask;          // rows inside the tensor
     int col0;
     bool has_acc;
-    float4 pr[NCH][8];        // MODE 0: float32 residual | bf16 residual in .x,.y;  MODE 1: mask in .x,.y, addend in .z,.w
+    float4 pr[NPF][8];        // MODE 0: float32 residual | bf16 residual in .x,.y;  MODE 1: mask in .x,.y, addend in .z,.w
+  };
+  // epilogue inputs of one 32-column chunk (coalesced, unconditional: rows outside the tensor read element 0)
+  auto load_inputs = [&](const TileCtx& t, int ch, float4 (&dst)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t o = (t.okmask >> i & 1) ? t.ob[i] + ch * EPI_CH : 0u;
+      if (MODE != 1) {
+        if (p.residual) {
+          if (p.res_f32) dst[i] = __ldg((const float4*)((const float*)p.residual + o));
+          else *(uint2*)&dst[i].x = __ldg((const uint2*)((const bf16*)p.residual + o));
+        }
+      } else {
+        *(uint2*)&dst[i].x = __ldg((const uint2*)(p.mask + o));
+        const bf16* addp = p.residual ? (const bf16*)p.residual : p.post_add;
+        if (addp) *(uint2*)&dst[i].z = __ldg((const uint2*)(addp + o));
+      }
+    }
   };
   auto prepare = [&](int tile, TileCtx& t) {
     int cls, nt, ht, wt, cot;
@@ -254,22 +275,10 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* stg_base
     }
     // Unconditional loads (rows outside the tensor read element 0 and are discarded at the store): a predicated load
     // into a zero-initialised register becomes "load to a temporary, wait, move" and serialises the whole batch.
+    if (PREFETCH) {
 #pragma unroll
-    for (int ch = 0; ch < NCH; ++ch)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint32_t o = (t.okmask >> i & 1) ? t.ob[i] + ch * EPI_CH : 0u;
-        if (FWD) {
-          if (p.residual) {
-            if (p.res_f32) t.pr[ch][i] = __ldg((const float4*)((const float*)p.residual + o));
-            else *(uint2*)&t.pr[ch][i].x = __ldg((const uint2*)((const bf16*)p.residual + o));
-          }
-        } else {
-          *(uint2*)&t.pr[ch][i].x = __ldg((const uint2*)(p.mask + o));
-          const bf16* addp = p.residual ? (const bf16*)p.residual : p.post_add;
-          if (addp) *(uint2*)&t.pr[ch][i].z = __ldg((const uint2*)(addp + o));
-        }
-      }
+      for (int ch = 0; ch < NPF; ++ch) load_inputs(t, ch, t.pr[ch]);
+    }
   };
   // one tile ahead only where the register file allows it (64-wide tiles: 32 prefetch registers per tile)
   constexpr bool AHEAD = NCH == 1;
@@ -287,7 +296,8 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* stg_base
     const int col0 = cur.col0;
     const uint32_t okmask = cur.okmask;
     uint32_t (&ob)[8] = cur.ob;
-    float4 (&pr)[NCH][8] = cur.pr;
+    float4 (&pr_tile)[NPF][8] = cur.pr;
+    float4 pr_pipe[2][8];
     const bool dbg_w = p.dbg && warp == 2 && lane == 0;
     const long long te0 = dbg_w ? clock64() : 0;
     if (has_acc) {
@@ -300,6 +310,12 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* stg_base
     for (int ch = 0; ch < NCH; ++ch) {
       const int c0 = ch * EPI_CH;
       const int colg = col0 + c0;
+      // 256-wide tiles: inputs of chunk ch+1 are requested before chunk ch is processed (two register buffers)
+      if (!PREFETCH) {
+        if (ch == 0) load_inputs(cur, 0, pr_pipe[0]);
+        if (ch + 1 < NCH) load_inputs(cur, ch + 1, pr_pipe[(ch + 1) & 1]);
+      }
+      float4 (&prc)[8] = PREFETCH ? pr_tile[PREFETCH ? ch : 0] : pr_pipe[ch & 1];
       float4 f[8];
       if (has_acc) {
         uint32_t v[32];
@@ -343,11 +359,11 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* stg_base
         if (p.residual) {
           if (p.res_f32) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { f[i].x += pr[ch][i].x; f[i].y += pr[ch][i].y; f[i].z += pr[ch][i].z; f[i].w += pr[ch][i].w; }
+            for (int i = 0; i < 8; ++i) { f[i].x += prc[i].x; f[i].y += prc[i].y; f[i].z += prc[i].z; f[i].w += prc[i].w; }
           } else {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const uint32_t u0 = __float_as_uint(pr[ch][i].x), u1 = __float_as_uint(pr[ch][i].y);
+              const uint32_t u0 = __float_as_uint(prc[i].x), u1 = __float_as_uint(prc[i].y);
               const float2 r0 = __bfloat1622float2(*(const __nv_bfloat162*)&u0), r1 = __bfloat1622float2(*(const __nv_bfloat162*)&u1);
               f[i].x += r0.x; f[i].y += r0.y; f[i].z += r1.x; f[i].w += r1.y;
             }
@@ -359,8 +375,8 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* stg_base
         const bool any_add = pre_add || p.post_add != nullptr;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const uint32_t m0u = __float_as_uint(pr[ch][i].x), m1u = __float_as_uint(pr[ch][i].y);
-          const uint32_t a0u = any_add ? __float_as_uint(pr[ch][i].z) : 0u, a1u = any_add ? __float_as_uint(pr[ch][i].w) : 0u;
+          const uint32_t m0u = __float_as_uint(prc[i].x), m1u = __float_as_uint(prc[i].y);
+          const uint32_t a0u = any_add ? __float_as_uint(prc[i].z) : 0u, a1u = any_add ? __float_as_uint(prc[i].w) : 0u;
           const float2 m0 = __bfloat1622float2(*(const __nv_bfloat162*)&m0u), m1 = __bfloat1622float2(*(const __nv_bfloat162*)&m1u);
           const float2 a0 = __bfloat1622float2(*(const __nv_bfloat162*)&a0u), a1 = __bfloat1622float2(*(const __nv_bfloat162*)&a1u);
           if (pre_add) { f[i].x += a0.x; f[i].y += a0.y; f[i].z += a1.x; f[i].w += a1.y; }
@@ -798,7 +814,10 @@ extern "C" int combat_conv_tc(const combat_conv_tc_desc* d, void* stream) {
   p.post_add = (const bf16*)d->post_add;
   p.dbg = getenv("COMBAT_TC_DBG") ? (long long*)d->stats : nullptr;
   p.stats = p.dbg ? nullptr : d->stats;
-  const int BLOCK_N = (d->Co % 128 == 0) ? 128 : 64;
+  // 256-wide tiles for the deep layers: per MMA the 128-row A operand is read once for 256 instead of 128 output channels
+  // (the shared-memory operand path is what bounds the 128-wide kernel); they need K large enough to hide the epilogue
+  const bool wide = d->Co % 256 == 0 && d->Ci * d->KH * d->KW >= 1152 && !getenv("COMBAT_NO_BN256");
+  const int BLOCK_N = wide ? 256 : ((d->Co % 128 == 0) ? 128 : 64);
   p.tiles_co = d->Co / BLOCK_N;
   int rc;
   if (d->up == 1) {
@@ -918,7 +937,8 @@ extern "C" int combat_conv_tc(const combat_conv_tc_desc* d, void* stream) {
     }
     COMBAT_RETURN_LAUNCH("conv_tc64");
   }
-  if (BLOCK_N == 128) { if (mode == 1) LAUNCH_C(128, 1) else if (mode == 2) LAUNCH_C(128, 2) else LAUNCH_C(128, 0) }
+  if (BLOCK_N == 256) { if (mode == 1) LAUNCH_C(256, 1) else if (mode == 2) LAUNCH_C(256, 2) else LAUNCH_C(256, 0) }
+  else if (BLOCK_N == 128) { if (mode == 1) LAUNCH_C(128, 1) else if (mode == 2) LAUNCH_C(128, 2) else LAUNCH_C(128, 0) }
   else { if (mode == 1) LAUNCH_C(64, 1) else if (mode == 2) LAUNCH_C(64, 2) else LAUNCH_C(64, 0) }
 #undef LAUNCH_C
   COMBAT_RETURN_LAUNCH("conv_tc");
