@@ -107,3 +107,32 @@ def test_plan_matches_oracle_selection():
     assert plan.num_bd == 0 and list(plan.bd_targets) == [2, 3, 4]
     with pytest.raises(Exception):
         make_plan(np.array([1]), default_opt(attack_mode="nope"))
+
+
+def test_multilabel_plan_matches_oracle_chunks_and_draws():
+    """engine.make_plan_multilabel == the oracle's restatement of train_generator_multilabel.py:171,203-221 on the same seeds:
+    poison count from rand(bs), one sigma for the C-step (only if num_bd > 0), one per class chunk, chunk ids as targets."""
+    import numpy as np
+
+    from combat_b200 import ops
+    from combat_b200.engine import default_opt, make_plan_multilabel, multilabel_chunks
+    from oracle import combat_oracle as O
+    for seed, (bs, ncls) in enumerate([(24, 10), (12, 8), (7, 10), (64, 8)]):
+        y = torch.randint(0, ncls, (bs,), generator=torch.Generator().manual_seed(seed)).numpy()
+        opt = default_opt(num_classes=ncls)
+        np.random.seed(seed)
+        torch.manual_seed(seed)
+        nbd = int(np.sum(np.random.rand(bs) < opt.pc))
+        s_c = O.draw_sigma() if nbd > 0 else None
+        chunks = O.multilabel_chunks(bs, ncls)
+        sig = [O.draw_sigma() for _ in chunks]
+        np.random.seed(seed)
+        torch.manual_seed(seed)
+        plan = make_plan_multilabel(y, opt)
+        assert multilabel_chunks(bs, ncls) == chunks
+        assert plan.num_bd == nbd and plan.sigma_c == s_c and plan.sigmas_g == sig
+        assert list(plan.perm) == list(range(bs)) and np.array_equal(plan.total_targets, y)   # rows keep their order and labels
+        for (ci, si, ei), sg in zip(chunks, sig):
+            assert (plan.bd_targets[si:ei] == ci).all()
+            np.testing.assert_allclose(plan.taps_rows[si:ei], np.tile(ops.gaussian_taps(sg), (ei - si, 1)).astype(np.float32))
+        assert sum(ei - si for _, si, ei in chunks) == bs
