@@ -297,6 +297,13 @@ def conv_tc_desc(x, w_ptr, out, N, Hi, Wi, Ci, Ho, Wo, Co, KH, KW, stride, pad, 
 
 # ------------------------------------------------------------------ norm / activation
 _PARTIAL_BLOCKS = 256
+_PARTIAL_FLOATS = _PARTIAL_BLOCKS * 2 * 2048
+
+
+def _max_partial_blocks(Cc):
+    """Row blocks of a column reduction: enough CTAs to fill the GPU (8 per SM) as far as the scratch buffer allows --
+    256 blocks left a 64-channel reduction at 1.7 CTAs per SM."""
+    return max(1, min(148 * 8, _PARTIAL_FLOATS // (2 * Cc)))
 
 
 class Scratch:
@@ -308,7 +315,7 @@ class Scratch:
     def get(cls, device):
         k = str(device)
         if k not in cls._inst:
-            cls._inst[k] = torch.empty(_PARTIAL_BLOCKS * 2 * 2048, dtype=torch.float32, device=device)
+            cls._inst[k] = torch.empty(_PARTIAL_FLOATS, dtype=torch.float32, device=device)
         return cls._inst[k]
 
 
@@ -317,7 +324,7 @@ def bn_train_prepare(x2d, R, Cc, gamma, beta, rm, rv, momentum, eps):
     dev = x2d.device
     partial = Scratch.get(dev)
     nblk = C.c_int(0)
-    check(lib.combat_bn_stats(_p(x2d), dt_code(x2d), R, Cc, _p(partial), _PARTIAL_BLOCKS, C.byref(nblk), _s()), "bn_stats")
+    check(lib.combat_bn_stats(_p(x2d), dt_code(x2d), R, Cc, _p(partial), _max_partial_blocks(Cc), C.byref(nblk), _s()), "bn_stats")
     st = torch.empty((4, Cc), dtype=torch.float32, device=dev)
     check(lib.combat_bn_finalize(_p(partial), nblk.value, R, Cc, _p(gamma), _p(beta), _p(rm), _p(rv), momentum, eps,
                                  _p(st[0]), _p(st[1]), _p(st[2]), _p(st[3]), _s()), "bn_finalize")
@@ -366,7 +373,7 @@ def bn_bwd_train(dy, x, y, gamma, mean, invstd, relu, dgamma_out, dbeta_out, dad
     partial = Scratch.get(x.device)
     nblk = C.c_int(0)
     check(lib.combat_bn_bwd_reduce(_p(dy), _p(x), dt_code(x), _p(y), dt_code(dy), R, Cc, _p(mean), _p(invstd), _p(partial),
-                                   _PARTIAL_BLOCKS, C.byref(nblk), int(relu), _s()), "bn_bwd_reduce")
+                                   _max_partial_blocks(Cc), C.byref(nblk), int(relu), _s()), "bn_bwd_reduce")
     check(lib.combat_bn_bwd_finalize(_p(partial), nblk.value, Cc, _p(dgamma_out), _p(dbeta_out), _s()), "bn_bwd_finalize")
     dx = torch.empty_like(dy)
     dres = torch.empty_like(dy) if want_dres else None
