@@ -106,23 +106,38 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   return v;
 }
 
-// one WARP per channel: lanes stride over the partial blocks (double accumulation), shuffle reduction
+// block-level sum of two doubles over FIN_THREADS threads (4 warps); result valid on thread 0
+#define FIN_THREADS 128
+__device__ __forceinline__ void fin_block_sum(double& a, double& b) {
+  __shared__ double sa[FIN_THREADS / 32], sb[FIN_THREADS / 32];
+  a = warp_sum_d(a);
+  b = warp_sum_d(b);
+  if ((threadIdx.x & 31) == 0) { sa[threadIdx.x >> 5] = a; sb[threadIdx.x >> 5] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    a = sa[0]; b = sb[0];
+#pragma unroll
+    for (int w = 1; w < FIN_THREADS / 32; ++w) { a += sa[w]; b += sb[w]; }
+  }
+}
+
+// one BLOCK of 4 warps per channel: threads stride over the partial blocks (double accumulation; up to ~1200 blocks when the
+// producer conv or an 8-CTA-per-SM reduction wrote them)
 __global__ void bn_finalize_k(const float* __restrict__ partial, int nblk, long long R, int C,
                               const float* __restrict__ gamma, const float* __restrict__ beta, float* running_mean,
                               float* running_var, float momentum, float eps, float* __restrict__ scale,
                               float* __restrict__ shift, float* save_mean, float* save_invstd) {
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (c >= C) return;
-  float mean, invstd;
+  const int c = blockIdx.x;
+  const int lane = threadIdx.x;  // thread 0 finishes the channel
+  float mean = 0.f, invstd = 0.f;
   if (nblk > 0) {
     double s = 0.0, ss = 0.0;
-    for (int b = lane; b < nblk; b += 32) {
+    for (int b = threadIdx.x; b < nblk; b += FIN_THREADS) {
       s += (double)partial[((long long)b * 2) * C + c];
       ss += (double)partial[((long long)b * 2 + 1) * C + c];
     }
-    s = warp_sum_d(s);
-    ss = warp_sum_d(ss);
+    fin_block_sum(s, ss);
+    if (lane != 0) return;
     double m = s / (double)R;
     double var = ss / (double)R - m * m;
     if (var < 0.0) var = 0.0;
@@ -134,10 +149,10 @@ __global__ void bn_finalize_k(const float* __restrict__ partial, int nblk, long 
       running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
     }
   } else {
+    if (lane != 0) return;
     mean = running_mean[c];
     invstd = 1.0f / sqrtf(running_var[c] + eps);
   }
-  if (lane != 0) return;
   const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
   const float sc = g * invstd;
   scale[c] = sc;
@@ -227,17 +242,14 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_k(const T* __restrict__ dy,
 
 __global__ void bn_bwd_finalize_k(const float* __restrict__ partial, int nblk, int C, float* __restrict__ dgamma,
                                   float* __restrict__ dbeta) {
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per channel
-  const int lane = threadIdx.x & 31;
-  if (c >= C) return;
+  const int c = blockIdx.x;  // one block of 4 warps per channel
   double s = 0.0, sx = 0.0;
-  for (int b = lane; b < nblk; b += 32) {
+  for (int b = threadIdx.x; b < nblk; b += FIN_THREADS) {
     s += (double)partial[((long long)b * 2) * C + c];
     sx += (double)partial[((long long)b * 2 + 1) * C + c];
   }
-  s = warp_sum_d(s);
-  sx = warp_sum_d(sx);
-  if (lane == 0) {
+  fin_block_sum(s, sx);
+  if (threadIdx.x == 0) {
     dbeta[c] = (float)s;
     dgamma[c] = (float)sx;
   }
@@ -378,7 +390,7 @@ extern "C" int combat_bn_finalize(const float* partial, int nblk, long long R, i
                                   float* shift, float* save_mean, float* save_invstd, void* stream) {
   COMBAT_ARG(scale && shift, 10);
   COMBAT_ARG(nblk > 0 ? partial != nullptr : (running_mean && running_var), 0);
-  bn_finalize_k<<<cdiv(C, 8), 256, 0, (cudaStream_t)stream>>>(partial, nblk, R, C, gamma, beta, running_mean, running_var,
+  bn_finalize_k<<<C, FIN_THREADS, 0, (cudaStream_t)stream>>>(partial, nblk, R, C, gamma, beta, running_mean, running_var,
                                                                 momentum, eps, scale, shift, save_mean, save_invstd);
   COMBAT_RETURN_LAUNCH("bn_finalize");
 }
@@ -437,7 +449,7 @@ extern "C" int combat_bn_bwd_reduce(const void* dy, const void* x, int x_dtype, 
 
 extern "C" int combat_bn_bwd_finalize(const float* partial, int nblk, int C, float* dgamma, float* dbeta, void* stream) {
   COMBAT_ARG(partial && dgamma && dbeta && nblk > 0, 0);
-  bn_bwd_finalize_k<<<cdiv(C, 8), 256, 0, (cudaStream_t)stream>>>(partial, nblk, C, dgamma, dbeta);
+  bn_bwd_finalize_k<<<C, FIN_THREADS, 0, (cudaStream_t)stream>>>(partial, nblk, C, dgamma, dbeta);
   COMBAT_RETURN_LAUNCH("bn_bwd_finalize");
 }
 
