@@ -93,7 +93,7 @@ extern "C" int combat_prep_weights(const float* params, void* wbuf, int dtype, c
   COMBAT_ARG(params && wbuf && table_dev, 0);
   if (n_desc <= 0) return 0;
   int gx = (int)((max_elems + 1023) / 1024);  // one 32x32 tile per block iteration
-  if (gx > 96) gx = 96;
+  if (gx > 592) gx = 592;  // the big layers need ~2300 tiles: latency-bound below ~4 blocks per SM per descriptor
   if (gx < 1) gx = 1;
   dim3 grid(gx, n_desc);
   DISPATCH_DTYPE(dtype, prep_weights_k<T><<<grid, 256, 0, (cudaStream_t)stream>>>(params, (T*)wbuf, table_dev);)
