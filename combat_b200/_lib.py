@@ -56,6 +56,7 @@ _SIGS = {
     "combat_conv_simt": ([P(ConvDesc), vp], i32),
     "combat_conv_wgrad_simt": ([P(ConvDesc), vp, i32, vp, vp], i32),
     "combat_im2col3": ([vp, vp, i32, i32, i32, i32, vp], i32),
+    "combat_fold_w64": ([vp, vp, i32, i32, vp, vp, vp], i32),
     "combat_conv_cin3": ([vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp], i32),
     "combat_conv_cout3": ([vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, vp], i32),
     "combat_wgrad_cin3": ([vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, vp], i32),

@@ -488,6 +488,33 @@ __global__ void __launch_bounds__(256) im2col3_k(const float* __restrict__ x, bf
   }
 }
 
+// Folds the weight gradient computed over the im2col3 operand, dW'[row][64] = [hi-part k<27 | 0 | lo-part | 0], into the
+// filter gradient (ACCUMULATES):
+//   mode 0 (3 -> rows conv)   : dw[row][k]                  += dW'[row][k] + dW'[row][32+k]
+//   mode 1 (rows=64 -> 3 conv): dw[(j*9 + 8 - t)*64 + row]  += dW'[row][k] + dW'[row][32+k],  k = t*3 + j   (wgrad3_k MODE 1)
+//                               db[j] += colsum[12+j] + colsum[44+j]  (centre tap of the operand == the 3-channel tensor)
+__global__ void fold_w64_k(const float* __restrict__ dw64, float* __restrict__ dw, int rows, int mode,
+                           const float* __restrict__ colsum, float* __restrict__ db) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows * 27) {
+    const int row = i / 27, k = i - row * 27;
+    const float v = dw64[row * 64 + k] + dw64[row * 64 + 32 + k];
+    if (mode == 0) {
+      dw[i] += v;
+    } else {
+      const int t = k / 3, j = k - t * 3;
+      dw[(j * 9 + 8 - t) * rows + row] += v;
+    }
+  }
+  if (mode == 1 && db && colsum && i < 3) db[i] += colsum[12 + i] + colsum[44 + i];
+}
+
+extern "C" int combat_fold_w64(const float* dw64, float* dw, int rows, int mode, const float* colsum, float* db, void* stream) {
+  COMBAT_ARG(dw64 && dw && rows > 0 && (mode == 0 || mode == 1), 0);
+  fold_w64_k<<<cdiv(rows * 27, 256), 256, 0, (cudaStream_t)stream>>>(dw64, dw, rows, mode, colsum, db);
+  COMBAT_RETURN_LAUNCH("fold_w64");
+}
+
 extern "C" int combat_im2col3(const float* x, void* A, int N, int H, int W, int stride, void* stream) {
   COMBAT_ARG(x && A, 0);
   COMBAT_ARG(stride == 1 || stride == 2, 5);

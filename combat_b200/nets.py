@@ -346,9 +346,7 @@ class NetBase:
             d = ops.conv_tc_desc(A, None, None, N, Ho, Wo, 64, Ho, Wo, cs.Cout, 1, 1, 1, 0, 1)
             _tc_launch(lambda: lib.combat_conv_tc_wgrad(C.byref(d), ops._p(dy), ops._p(dw64), ops._s()), "conv_tc_wgrad",
                        2.0 * N * Ho * Wo * cs.Cout * 27, "N%d %dx%d 3->%d k3 s%d im2col" % (N, H, W, cs.Cout, cs.stride))
-            g = self.store.raw(self.store.grad, cs.name + ".weight").view(cs.Cout, 27)
-            g.add_(dw64[:, 0:27])
-            g.add_(dw64[:, 32:59])
+            ops.fold_w64(dw64, self.store.raw(self.store.grad, cs.name + ".weight"), cs.Cout, 0)
             if cs.bias:
                 ops.colsum(dy, cs.Cout, self.store.g(cs.name + ".bias"))
             return
@@ -789,7 +787,19 @@ class Generator(NetBase):
         nchw_o = ops.nchw_strides(self.out_channel, H, W)
         d_a01 = torch.empty((N, H, W, nf), dtype=self.dtype, device=self.device)
         if self.fast_small and nf == 64 and self.out_channel == 3:
-            ops.wgrad_cout3(a01, dz, self.store.raw(self.store.grad, cs.name + ".weight"), self.store.g(cs.name + ".bias"))
+            if a01.dtype == torch.bfloat16 and self._use_im2col(cs, nf, 3, wgrad=True):
+                # weight gradient of the 64 -> 3 conv on the tensor cores: dW'[ci][k] = sum_pix a[pix][ci] * im2col3(dz)[pix][k]
+                A = ops.im2col3(dz, 1)
+                dw64 = torch.zeros((nf, 64), dtype=torch.float32, device=self.device)
+                d = ops.conv_tc_desc(A, None, None, N, H, W, 64, H, W, nf, 1, 1, 1, 0, 1)
+                _tc_launch(lambda: lib.combat_conv_tc_wgrad(C.byref(d), ops._p(a01), ops._p(dw64), ops._s()), "conv_tc_wgrad",
+                           2.0 * N * H * W * nf * 27, "N%d %dx%d %d->3 k3 s1 im2col" % (N, H, W, nf))
+                csum = torch.zeros(64, dtype=torch.float32, device=self.device)
+                ops.colsum(A.view(-1, 64), 64, csum)
+                ops.fold_w64(dw64, self.store.raw(self.store.grad, cs.name + ".weight"), nf, 1, colsum=csum,
+                             db=self.store.g(cs.name + ".bias"))
+            else:
+                ops.wgrad_cout3(a01, dz, self.store.raw(self.store.grad, cs.name + ".weight"), self.store.g(cs.name + ".bias"))
             if self._use_im2col(cs, nf, 3):  # input gradient of the 64 -> 3 conv == 3 -> 64 conv with the flipped filter
                 self.cin3_tc(dz, self._w64_for(cs, dgrad=True), nf, 1, d_a01, tag=" (dgrad)")
             else:

@@ -255,6 +255,10 @@ def im2col3(x_nchw, stride):
     return A
 
 
+def fold_w64(dw64, dw, rows, mode, colsum=None, db=None):
+    check(lib.combat_fold_w64(_p(dw64), _p(dw), rows, mode, _p(colsum), _p(db), _s()), "fold_w64")
+
+
 def conv_cin3(x_nchw, w_ptr, w_dt, out, Co, stride, bias=None, act=0, post_scale=None, post_shift=None, out2=None,
               scale2=None, shift2=None):
     N, _, H, W = x_nchw.shape

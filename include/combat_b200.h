@@ -137,6 +137,10 @@ int combat_conv_wgrad_simt(const combat_conv_desc* d_host, const void* dy, int d
 /* im2col of a 3-channel NCHW float32 image for the tensor-core path: A[N,Ho,Wo,64] bf16 = [hi(27) | 0 | lo(27) | 0]
  * (3x3, pad 1, stride 1|2); a 3 -> Co conv is then combat_conv_tc over A as a 1x1 conv with the filter stored twice. */
 int combat_im2col3(const float* x, void* A_bf16, int N, int H, int W, int stride, void* stream);
+/* folds a weight gradient taken over the im2col3 operand (dW'[rows][64]: hi columns 0..26, lo columns 32..58) into the
+ * filter gradient, accumulating: mode 0 -> dw[rows][27] (3 -> rows conv); mode 1 -> dw[3][9][rows] with the taps reversed and
+ * db[j] += colsum[12+j] + colsum[44+j] (rows -> 3 conv; colsum = column sums of the operand, optional) */
+int combat_fold_w64(const float* dw64, float* dw, int rows, int mode, const float* colsum, float* db, void* stream);
 int combat_conv_cin3(const float* x, const void* w, int w_dtype, const float* bias, void* out, int out_dtype, int N, int H,
                      int W, int Co, int stride, int act, const float* post_scale, const float* post_shift, void* out2,
                      const float* scale2, const float* shift2, void* stream);
