@@ -154,6 +154,13 @@ class AlternatedStep:
         self.launches_per_step = 0  # kernels of this library launched by one iteration (counted on the last eager/capture pass)
         self._bufs = None
         self._graph = None
+        self._gstate = {}          # tensors handed from one captured phase to the next
+        self._copy_stream = None   # side stream + staging buffers of prefetch()
+        self._stage = {}
+        self._stage_free = None
+        self._prefetched = None
+        self._rd_bufs = None       # pinned double buffer of read_async()
+        self._rd_slot = 0
 
     # ------------------------------------------------------------ state
     def load_state(self, netC=None, clean=None, netG=None, netF=None):
@@ -366,17 +373,15 @@ class AlternatedStep:
         `step(x_host, ...)` with the same tensor waits for it and takes a device-to-device copy instead of a PCIe one."""
         if x_host.is_cuda:
             return
-        if getattr(self, "_copy_stream", None) is None:
+        if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
-            self._stage = {}
         buf = self._stage.get(tuple(x_host.shape))
         if buf is None:
             buf = self._stage[tuple(x_host.shape)] = torch.empty(x_host.shape, dtype=torch.float32, device=self.device)
         # only the previous consumer of the staging buffer (last step's device-to-device copy) must have finished -- NOT the
         # iteration that was just launched, which is what this copy overlaps with
-        free = getattr(self, "_stage_free", None)
-        if free is not None:
-            self._copy_stream.wait_event(free)
+        if self._stage_free is not None:
+            self._copy_stream.wait_event(self._stage_free)
         with torch.cuda.stream(self._copy_stream):
             buf.copy_(x_host, non_blocking=True)
             ev = torch.cuda.Event()
@@ -384,7 +389,7 @@ class AlternatedStep:
         self._prefetched = (x_host, buf, ev)
 
     def _take_input(self, x, dst):
-        pf = getattr(self, "_prefetched", None)
+        pf = self._prefetched
         if pf is not None and pf[0] is x:
             cur = torch.cuda.current_stream(self.device)
             cur.wait_event(pf[2])
@@ -522,9 +527,9 @@ class AlternatedStep:
     def read_async(self, out):
         """Enqueue the device->host copy of this step's losses / counters into pinned memory and return a handle; calling
         `.get()` one iteration later keeps the host from draining the GPU queue after every step."""
-        slot = getattr(self, "_rd_slot", 0)
+        slot = self._rd_slot
         self._rd_slot = slot ^ 1
-        if getattr(self, "_rd_bufs", None) is None:
+        if self._rd_bufs is None:
             self._rd_bufs = [(torch.empty(8, dtype=torch.float32).pin_memory(), torch.empty(16, dtype=torch.int32).pin_memory())
                              for _ in range(2)]
         l, c = self._rd_bufs[slot]
