@@ -919,6 +919,19 @@ __global__ void __launch_bounds__(256) pool_linear_bwd_dx_k(const float* __restr
   __syncthreads();
   T* xb = dx + (long long)b * Hf * Wf * C;
   const int tot = Hf * Wf * C;
+  if ((C & 7) == 0) {  // 8 channels (one 16-byte bf16 store) per thread
+    const int C8 = C >> 3, pp = ph * pw;
+    for (int e8 = threadIdx.x; e8 < tot / 8; e8 += blockDim.x) {
+      const int c = (e8 % C8) * 8, pix = e8 / C8;
+      const int h = pix / Wf, w = pix % Wf;
+      const int hp = h / P, wp = w / P;
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (hp < ph && wp < pw) ? dfeat[(c + j) * pp + hp * pw + wp] : 0.f;
+      st8<T>(xb + (long long)e8 * 8, v);
+    }
+    return;
+  }
   for (int e = threadIdx.x; e < tot; e += blockDim.x) {
     const int c = e % C, pix = e / C;
     const int h = pix / Wf, w = pix % Wf;
@@ -1011,10 +1024,36 @@ __global__ void __launch_bounds__(256) maxpool2_k(const T* __restrict__ x, T* __
     y[i] = from_f<T>(m);
   }
 }
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool2_v8_k(const T* __restrict__ x, T* __restrict__ y, long long total8, int H, int W,
+                                                     int C) {
+  const int Ho = H / 2, Wo = W / 2, C8 = C / 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
+    const int c = 8 * (int)(i % C8);
+    long long p = i / C8;
+    const int ow = (int)(p % Wo);
+    p /= Wo;
+    const int oh = (int)(p % Ho);
+    const long long n = p / Ho;
+    const T* xb = x + ((n * H + 2 * oh) * W + 2 * ow) * C + c;
+    float a[8], b[8], cc[8], d[8], m[8];
+    ld8<T>(xb, a);
+    ld8<T>(xb + C, b);
+    ld8<T>(xb + (long long)W * C, cc);
+    ld8<T>(xb + (long long)W * C + C, d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = fmaxf(fmaxf(a[j], b[j]), fmaxf(cc[j], d[j]));
+    st8<T>(y + i * 8, m);
+  }
+}
 extern "C" int combat_maxpool2(const void* x, void* y, int dtype, int N, int H, int W, int C, void* stream) {
   COMBAT_ARG(x && y, 0);
   long long total = (long long)N * (H / 2) * (W / 2) * C;
   if (total <= 0) return 0;
+  if ((C % 8) == 0) {
+    DISPATCH_DTYPE(dtype, maxpool2_v8_k<T><<<ew_grid(total / 8), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, total / 8, H, W, C);)
+    COMBAT_RETURN_LAUNCH("maxpool2");
+  }
   DISPATCH_DTYPE(dtype, maxpool2_k<T><<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, total, H, W, C);)
   COMBAT_RETURN_LAUNCH("maxpool2");
 }
