@@ -82,6 +82,17 @@ __device__ __forceinline__ float warp_max(float v) {
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Grid of a grid-stride kernel: every CTA resident at once (SM count x CTAs per SM at this kernel's register / shared
+// memory footprint), so that there is no partial last wave.  0 if the query fails (the caller falls back to a cap).
+template <typename Kernel>
+static inline int resident_ctas(Kernel kernel, int threads, size_t dyn_smem = 0) {
+  int dev = 0, sms = 0, per_sm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, dyn_smem) != cudaSuccess) return 0;
+  return sms * per_sm;
+}
+
 #define DISPATCH_DTYPE(dtype, ...)        \
   if ((dtype) == COMBAT_F32) {            \
     typedef float T;                      \

@@ -1,75 +1,19 @@
 // HBM-bound 32x32 and 64x64 DCT-II / DCT-III / low-pass projection: one image row (then column) per thread held in
-// registers, 1-D transforms as a recursive even/odd butterfly network (341 multiply-adds per 32-point transform
-// instead of 1024; 1365 instead of 4096 for 64 points), transposes through a padded shared-memory tile, fully
-// coalesced 16-byte global loads and stores.  Algorithmic traffic: one read + one write of the plane.
+// registers, 1-D transforms as a straight-line even/odd butterfly network with FFT-based odd parts (dct_butterfly.cuh:
+// 267 multiply-adds per 32-point transform instead of 1024, 627 instead of 4096 for 64 points), ONE transpose through
+// a padded shared-memory tile, coalesced global loads (16 bytes per thread) and stores (128 bytes per warp).
+// Algorithmic traffic: one read + one write of the plane.
 //   32x32 (CIFAR-10): one WARP per plane (8 planes per CTA, warp-level synchronisation only)
 //   64x64 (CelebA)  : one 64-thread CTA per plane
 //
 //   kind 1  dct_2d   (utils/dct.py:85-96)           kind 2  idct_2d  (utils/dct.py:99-111)
-//   kind 3  low_freq (train_generator.py:47-55): idct_2d(mask_k * dct_2d(x)) == P x P^T, P = D^T diag(1_k) D
+//   kind 3  low_freq (train_generator.py:47-55): idct_2d(mask_k * dct_2d(x)) == P x P^T, P = D^T diag(1_k) D, applied
+//           as P along the rows, then P along the columns
 //           (the (x+1)/2*255 ... /255*2-1 affine of the reference cancels exactly because the DC term is kept).
 //           The retained block size of the reference's default ratio 0.65 (keep = 20 of 32, 41 of 64) is a template
-//           constant, so the compiler prunes every butterfly output / input that the mask zeroes (~35 % of the work).
+//           constant, so the compiler prunes every butterfly output / input that the mask zeroes.
 #include "common.cuh"
-#include "dct32_tables.h"
-
-template <int F, int N>
-struct OddTable;
-#define ODD_TABLE(F, N) \
-  template <>           \
-  struct OddTable<F, N> { static __device__ __forceinline__ float at(int i) { return DCT##F##_T##N[i]; } };
-ODD_TABLE(32, 32) ODD_TABLE(32, 16) ODD_TABLE(32, 8) ODD_TABLE(32, 4) ODD_TABLE(32, 2)
-ODD_TABLE(64, 64) ODD_TABLE(64, 32) ODD_TABLE(64, 16) ODD_TABLE(64, 8) ODD_TABLE(64, 4) ODD_TABLE(64, 2)
-#undef ODD_TABLE
-template <int F>
-__device__ __forceinline__ float dc_scale() { return F == 32 ? DCT32_S0 : DCT64_S0; }
-
-// forward: X = D_N x   (scaled so that the top-level N = F result is orthonormal)
-template <int F, int N>
-struct Dct {
-  static __device__ __forceinline__ void fwd(const float (&x)[N], float (&X)[N]) {
-    constexpr int H = N / 2;
-    float u[H], v[H], E[H];
-#pragma unroll
-    for (int n = 0; n < H; ++n) {
-      u[n] = x[n] + x[N - 1 - n];
-      v[n] = x[n] - x[N - 1 - n];
-    }
-    Dct<F, H>::fwd(u, E);
-#pragma unroll
-    for (int k = 0; k < H; ++k) {
-      float o = 0.f;
-#pragma unroll
-      for (int n = 0; n < H; ++n) o = fmaf(OddTable<F, N>::at(k * H + n), v[n], o);
-      X[2 * k] = E[k];
-      X[2 * k + 1] = o;
-    }
-  }
-  // inverse (transpose of the forward flow graph): x = D_N^T X
-  static __device__ __forceinline__ void inv(const float (&X)[N], float (&x)[N]) {
-    constexpr int H = N / 2;
-    float Ein[H], Oin[H], a[H];
-#pragma unroll
-    for (int k = 0; k < H; ++k) {
-      Ein[k] = X[2 * k];
-      Oin[k] = X[2 * k + 1];
-    }
-    Dct<F, H>::inv(Ein, a);
-#pragma unroll
-    for (int n = 0; n < H; ++n) {
-      float b = 0.f;
-#pragma unroll
-      for (int k = 0; k < H; ++k) b = fmaf(OddTable<F, N>::at(k * H + n), Oin[k], b);
-      x[n] = a[n] + b;
-      x[N - 1 - n] = a[n] - b;
-    }
-  }
-};
-template <int F>
-struct Dct<F, 1> {
-  static __device__ __forceinline__ void fwd(const float (&x)[1], float (&X)[1]) { X[0] = x[0] * dc_scale<F>(); }
-  static __device__ __forceinline__ void inv(const float (&X)[1], float (&x)[1]) { x[0] = X[0] * dc_scale<F>(); }
-};
+#include "dct_butterfly.cuh"
 
 template <int IN_MODE>
 __device__ __forceinline__ void convert4(const void* in, long long idx4, float (&t)[4]) {
@@ -89,95 +33,137 @@ __device__ __forceinline__ void convert4(const void* in, long long idx4, float (
   }
 }
 
-// The transform of one plane by NP threads (thread `tid` owns row / column `tid`).  SYNC: __syncwarp or __syncthreads.
-// KEEP: compile-time upper bound of `keep` (KIND 3); keep <= KEEP.
-template <int NP, int KIND, int IN_MODE, int KEEP, typename Sync>
-__device__ __forceinline__ void transform_plane(const void* in, float* out, long long plane, float* tile, int tid, int keep,
-                                                Sync sync) {
-  constexpr int TS = NP + 1;  // padded tile stride: conflict-free for both row and column access
-  // ---- load: NP*NP/4 16-byte pieces, NP threads
+// Shared-memory tile of one plane: row stride NP + 4 floats.  Row access by 16-byte vectors (thread t, row t) is
+// conflict-free per quarter-warp ((4t + 4j) mod 32 distinct), column access by scalars (thread t, column t) always is.
+template <int NP>
+struct Tile {
+  static constexpr int TS = NP + 4;
+  static constexpr int FLOATS = NP * TS;
+  // piece q (16 bytes) of the row-major plane -> its place in the padded tile
+  static __device__ __forceinline__ float4* piece(float* tile, int q) { return (float4*)(tile + (q * 4 / NP) * TS + (q * 4 % NP)); }
+};
+
+// global -> tile through registers (any input mode): NP*NP/4 16-byte pieces, NP threads
+template <int NP, int IN_MODE>
+__device__ __forceinline__ void load_plane(const void* in, long long plane, float* tile, int tid) {
 #pragma unroll
   for (int j = 0; j < NP / 4; ++j) {
-    const int q = j * NP + tid;  // float4 index inside the plane: NP*16 contiguous bytes per instruction
+    const int q = j * NP + tid;  // NP*16 contiguous bytes per instruction
     float t4[4];
     convert4<IN_MODE>(in, plane * (NP * NP / 4) + q, t4);
-    const int e = q * 4, r = e / NP, c = e % NP;
-    float* t = tile + r * TS + c;
-    t[0] = t4[0]; t[1] = t4[1]; t[2] = t4[2]; t[3] = t4[3];
+    *Tile<NP>::piece(tile, q) = make_float4(t4[0], t4[1], t4[2], t4[3]);
   }
-  sync();
-  float a[NP], b[NP];
-  // ---- pass 1: rows (thread = row `tid`); output index = column frequency
-#pragma unroll
-  for (int k = 0; k < NP; ++k) a[k] = tile[tid * TS + k];
-  if (KIND == 2) Dct<NP, NP>::inv(a, b); else Dct<NP, NP>::fwd(a, b);
-  sync();
-#pragma unroll
-  for (int k = 0; k < NP; ++k)
-    if (KIND != 3 || k < KEEP) tile[tid * TS + k] = b[k];  // column frequencies >= KEEP are masked later: never computed
-  sync();
-  // ---- pass 2: columns (thread = column / column-frequency `tid`)
-  if (KIND != 3) {
-#pragma unroll
-    for (int k = 0; k < NP; ++k) a[k] = tile[k * TS + tid];
-    if (KIND == 2) Dct<NP, NP>::inv(a, b); else Dct<NP, NP>::fwd(a, b);
-    sync();
-#pragma unroll
-    for (int k = 0; k < NP; ++k) tile[k * TS + tid] = b[k];
-  } else {
-    const bool live = tid < keep;  // threads of masked column frequencies only write zeros
-#pragma unroll
-    for (int k = 0; k < NP; ++k) a[k] = live ? tile[k * TS + tid] : 0.f;
-    Dct<NP, NP>::fwd(a, b);
-    // b[m] = coefficient (row-frequency m, column-frequency tid): keep the top-left keep x keep block
-#pragma unroll
-    for (int m = 0; m < NP; ++m)
-      if (m >= KEEP || m >= keep) b[m] = 0.f;
-    Dct<NP, NP>::inv(b, a);  // back along the columns
-    sync();
-#pragma unroll
-    for (int k = 0; k < NP; ++k) tile[k * TS + tid] = a[k];
-    sync();
-    // rows again: inverse along the row direction (inputs at column frequencies >= KEEP are zero by construction)
-#pragma unroll
-    for (int k = 0; k < NP; ++k) a[k] = k < KEEP ? tile[tid * TS + k] : 0.f;
-    Dct<NP, NP>::inv(a, b);
-    sync();
-#pragma unroll
-    for (int k = 0; k < NP; ++k) tile[tid * TS + k] = b[k];
-  }
-  sync();
-  // ---- store
-  float4* dst = (float4*)(out + plane * (NP * NP));
+}
+
+template <int NP, int LIM>
+__device__ __forceinline__ void row_store(float* row, const float (&b)[NP]) {  // row[k] = b[k] for k < LIM
 #pragma unroll
   for (int j = 0; j < NP / 4; ++j) {
-    const int q = j * NP + tid;
-    const int e = q * 4, r = e / NP, c = e % NP;
-    const float* t = tile + r * TS + c;
-    dst[q] = make_float4(t[0], t[1], t[2], t[3]);
+    if (4 * j + 3 < LIM) {
+      *(float4*)(row + 4 * j) = make_float4(b[4 * j], b[4 * j + 1], b[4 * j + 2], b[4 * j + 3]);
+    } else {
+#pragma unroll
+      for (int k = 4 * j; k < 4 * j + 4; ++k)
+        if (k < LIM) row[k] = b[k];
+    }
   }
+}
+
+// The 1-D operator of one pass: DCT-II, DCT-III, or the low-pass projection P = D^T diag(1_keep) D.
+// KEEP: compile-time upper bound of `keep` (KIND 3): outputs of the forward half at frequencies >= KEEP are never
+// computed and the inverse half sees literal zeros there, so the compiler prunes both networks.
+template <int NP, int KIND, int KEEP>
+__device__ __forceinline__ void apply_1d(const float (&a)[NP], float (&b)[NP], int keep) {
+  if (KIND == 1) {
+    Dct<NP, NP>::fwd(a, b);
+  } else if (KIND == 2) {
+    Dct<NP, NP>::inv(a, b);
+  } else {
+    float c[NP];
+    Dct<NP, NP>::fwd(a, c);
+#pragma unroll
+    for (int m = 0; m < NP; ++m)
+      if (m >= KEEP || m >= keep) c[m] = 0.f;
+    Dct<NP, NP>::inv(c, b);
+  }
+}
+
+// The transform of the plane held in `tile` by NP threads, then its store.  Both dct_2d / idct_2d and the projection
+// P X P^T are separable: pass 1 applies the 1-D operator to the rows (thread = row `tid`, 16-byte tile accesses),
+// pass 2 to the columns (thread = column `tid`); the result leaves the registers as NP coalesced 4-byte stores
+// (a warp writes 128 contiguous bytes of one output row per instruction) - no trip back through shared memory.
+// Tile traffic per plane: fill, row read, row write, column read.
+// SYNC: __syncwarp or __syncthreads; the caller synchronises between filling the tile and this call.
+template <int NP, int KIND, int KEEP, typename Sync>
+__device__ __forceinline__ void transform_plane(float* out, long long plane, float* tile, int tid, int keep, Sync sync) {
+  constexpr int TS = Tile<NP>::TS;
+  float a[NP], b[NP];
+  float* row = tile + tid * TS;
+  // ---- pass 1: rows.  A thread only rewrites the row it has just read: no synchronisation in between.
+#pragma unroll
+  for (int j = 0; j < NP / 4; ++j) {
+    const float4 v = *(const float4*)(row + 4 * j);
+    a[4 * j] = v.x; a[4 * j + 1] = v.y; a[4 * j + 2] = v.z; a[4 * j + 3] = v.w;
+  }
+  apply_1d<NP, KIND, KEEP>(a, b, keep);
+  row_store<NP, NP>(row, b);
   sync();
+  // ---- pass 2: columns
+#pragma unroll
+  for (int k = 0; k < NP; ++k) a[k] = tile[k * TS + tid];
+  sync();  // the tile may be refilled (next plane) from here on
+  apply_1d<NP, KIND, KEEP>(a, b, keep);
+  float* dst = out + plane * (NP * NP) + tid;
+#pragma unroll
+  for (int k = 0; k < NP; ++k) dst[k * NP] = b[k];
 }
 
 struct WarpSync { __device__ __forceinline__ void operator()() const { __syncwarp(); } };
 struct BlockSync { __device__ __forceinline__ void operator()() const { __syncthreads(); } };
 
-// KIND: 1 dct, 2 idct, 3 low-pass (keep x keep)
-template <int KIND, int IN_MODE, int KEEP>
-__global__ void __launch_bounds__(256, 2) dct32_k(const void* __restrict__ in, float* __restrict__ out, long long planes,
-                                                  int keep) {
-  __shared__ float tiles[8][32 * 33];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long wstride = (long long)gridDim.x * 8;
-  for (long long p = (long long)blockIdx.x * 8 + warp; p < planes; p += wstride)
-    transform_plane<32, KIND, IN_MODE, KEEP>(in, out, p, tiles[warp], lane, keep, WarpSync());
+// One plane per NP-thread group (a warp for 32x32, a 64-thread CTA for 64x64), GROUPS groups per CTA, each with its
+// own tile; groups stride over the planes.  KIND: 1 dct, 2 idct, 3 low-pass (keep x keep).
+template <int NP, int GROUPS, int KIND, int IN_MODE, int KEEP, typename Sync>
+__device__ __forceinline__ void planes_loop(const void* in, float* out, long long planes, int keep, float* smem, Sync sync) {
+  const int group = threadIdx.x / NP, tid = threadIdx.x % NP;
+  float* tile = smem + group * Tile<NP>::FLOATS;
+  const long long stride = (long long)gridDim.x * GROUPS;
+  for (long long p = (long long)blockIdx.x * GROUPS + group; p < planes; p += stride) {
+    load_plane<NP, IN_MODE>(in, p, tile, tid);
+    sync();
+    transform_plane<NP, KIND, KEEP>(out, p, tile, tid, keep, sync);
+  }
 }
 
 template <int KIND, int IN_MODE, int KEEP>
-__global__ void __launch_bounds__(64) dct64_k(const void* __restrict__ in, float* __restrict__ out, long long planes, int keep) {
-  __shared__ float tile[64 * 65];
-  for (long long p = blockIdx.x; p < planes; p += gridDim.x)
-    transform_plane<64, KIND, IN_MODE, KEEP>(in, out, p, tile, threadIdx.x, keep, BlockSync());
+__global__ void __launch_bounds__(256, 3) dct32_k(const void* __restrict__ in, float* __restrict__ out, long long planes,
+                                                  int keep) {
+  __shared__ __align__(16) float smem[8 * Tile<32>::FLOATS];
+  planes_loop<32, 8, KIND, IN_MODE, KEEP>(in, out, planes, keep, smem, WarpSync());
+}
+
+template <int KIND, int IN_MODE, int KEEP>
+__global__ void __launch_bounds__(64, 10) dct64_k(const void* __restrict__ in, float* __restrict__ out, long long planes,
+                                                  int keep) {
+  __shared__ __align__(16) float smem[Tile<64>::FLOATS];
+  planes_loop<64, 1, KIND, IN_MODE, KEEP>(in, out, planes, keep, smem, BlockSync());
+}
+
+typedef void (*plane_kernel_t)(const void*, float*, long long, int);
+
+// One launch.  Grid = 6 x the CTAs resident at once (or fewer if there are fewer planes), each CTA striding over the
+// planes: measured on B200 at 65,536 images (profiles/r01_dct_launch_sweep.jsonl) 1x resident (a persistent grid, every
+// warp in the same load / transform / store phase) reaches 84 % of the measured copy bandwidth for dct_2d at 32x32,
+// 2x 91 %, 4x 98 %, 6x 98 %; a cp.async double-buffered tile at half the occupancy was never better.
+template <plane_kernel_t KERNEL, int THREADS>
+static void launch_planes(long long ctas_needed, const void* in, float* out, long long planes, int keep, cudaStream_t st) {
+  static int cap = -1;  // per kernel instantiation (one device per process: one rank per GPU)
+  if (cap < 0) {
+    cap = 6 * resident_ctas(KERNEL, THREADS);
+    if (cap <= 0) cap = 148 * 16;
+  }
+  const int grid = (int)(ctas_needed < cap ? ctas_needed : cap);
+  KERNEL<<<grid, THREADS, 0, st>>>(in, out, planes, keep);
 }
 
 extern "C" int combat_dct32_fast(const void* in, float* out, long long planes, int kind, int keep, int in_mode,
@@ -187,11 +173,8 @@ extern "C" int combat_dct32_fast(const void* in, float* out, long long planes, i
   COMBAT_ARG(in_mode >= 0 && in_mode <= 2, 5);
   COMBAT_ARG(kind != 3 || (keep >= 1 && keep <= 32), 4);
   if (planes <= 0) return 0;
-  long long blocks = (planes + 7) / 8;
-  const long long cap = 148 * 16;
-  int grid = (int)(blocks < cap ? blocks : cap);
   cudaStream_t st = (cudaStream_t)stream;
-#define L(K, M, KP) dct32_k<K, M, KP><<<grid, 256, 0, st>>>(in, out, planes, keep)
+#define L(K, M, KP) launch_planes<dct32_k<K, M, KP>, 256>((planes + 7) / 8, in, out, planes, keep, st)
 #define LM(K, KP) { if (in_mode == 0) L(K, 0, KP); else if (in_mode == 1) L(K, 1, KP); else L(K, 2, KP); }
   if (kind == 1) LM(1, 32)
   else if (kind == 2) LM(2, 32)
@@ -209,10 +192,8 @@ extern "C" int combat_dct64_fast(const void* in, float* out, long long planes, i
   COMBAT_ARG(in_mode >= 0 && in_mode <= 2, 5);
   COMBAT_ARG(kind != 3 || (keep >= 1 && keep <= 64), 4);
   if (planes <= 0) return 0;
-  const long long cap = 148 * 16;
-  int grid = (int)(planes < cap ? planes : cap);
   cudaStream_t st = (cudaStream_t)stream;
-#define L(K, M, KP) dct64_k<K, M, KP><<<grid, 64, 0, st>>>(in, out, planes, keep)
+#define L(K, M, KP) launch_planes<dct64_k<K, M, KP>, 64>(planes, in, out, planes, keep, st)
 #define LM(K, KP) { if (in_mode == 0) L(K, 0, KP); else if (in_mode == 1) L(K, 1, KP); else L(K, 2, KP); }
   if (kind == 1) LM(1, 64)
   else if (kind == 2) LM(2, 64)
