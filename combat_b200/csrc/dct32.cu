@@ -99,23 +99,34 @@ __device__ __forceinline__ void transform_plane(float* out, long long plane, flo
   constexpr int TS = Tile<NP>::TS;
   float a[NP], b[NP];
   float* row = tile + tid * TS;
-  // ---- pass 1: rows.  A thread only rewrites the row it has just read: no synchronisation in between.
-#pragma unroll
-  for (int j = 0; j < NP / 4; ++j) {
-    const float4 v = *(const float4*)(row + 4 * j);
-    a[4 * j] = v.x; a[4 * j + 1] = v.y; a[4 * j + 2] = v.z; a[4 * j + 3] = v.w;
-  }
-  apply_1d<NP, KIND, KEEP>(a, b, keep);
-  row_store<NP, NP>(row, b);
-  sync();
-  // ---- pass 2: columns
-#pragma unroll
-  for (int k = 0; k < NP; ++k) a[k] = tile[k * TS + tid];
-  sync();  // the tile may be refilled (next plane) from here on
-  apply_1d<NP, KIND, KEEP>(a, b, keep);
   float* dst = out + plane * (NP * NP) + tid;
+  // KIND 3: both passes run the SAME copy of the 1-D network (loop not unrolled).  The 64-point low-pass operator is
+  // 22 KB of straight-line code and two inlined copies (43 KB) overflow the 32 KB instruction cache: ncu showed 1.8
+  // warps per issue slot stalled on instruction fetch for dct64_k<3, 0, 41>; 334 -> 304 us at 16,384 images.  The plain
+  // transforms fit twice and measured faster unrolled (uint8-input dct_2d: 178 vs 193 us at 32x32, 200 vs 227 at 64x64).
+#pragma unroll(KIND == 3 ? 1 : 2)
+  for (int pass = 0; pass < 2; ++pass) {
+    if (pass == 0) {  // rows
 #pragma unroll
-  for (int k = 0; k < NP; ++k) dst[k * NP] = b[k];
+      for (int j = 0; j < NP / 4; ++j) {
+        const float4 v = *(const float4*)(row + 4 * j);
+        a[4 * j] = v.x; a[4 * j + 1] = v.y; a[4 * j + 2] = v.z; a[4 * j + 3] = v.w;
+      }
+    } else {  // columns
+#pragma unroll
+      for (int k = 0; k < NP; ++k) a[k] = tile[k * TS + tid];
+      sync();  // the tile may be refilled (next plane) from here on
+    }
+    apply_1d<NP, KIND, KEEP>(a, b, keep);
+    if (pass == 0) {
+      // a thread only rewrites the row it has just read: no synchronisation between its loads and these stores
+      row_store<NP, NP>(row, b);
+      sync();
+    } else {
+#pragma unroll
+      for (int k = 0; k < NP; ++k) dst[k * NP] = b[k];
+    }
+  }
 }
 
 struct WarpSync { __device__ __forceinline__ void operator()() const { __syncwarp(); } };
