@@ -325,7 +325,7 @@ def test_batchnorm_relu_train_eval(ops, dtype, tol):
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 1.5e-2)])
-@pytest.mark.parametrize("H", [2, 16])
+@pytest.mark.parametrize("H", [2, 4, 8, 12, 16])
 def test_instancenorm_lrelu(ops, dtype, tol, H):
     g = torch.Generator().manual_seed(6 + H)
     N, Cc = 5, 128
@@ -348,7 +348,7 @@ def test_instancenorm_lrelu(ops, dtype, tol, H):
         assert rel(yd.float().permute(0, 3, 1, 2), y) < tol
         dx = ops.instnorm_bwd(dev(_nhwc(dy).to(dtype)), dev(_nhwc(dy2).to(dtype)), xd, st, act)
         # IN backward over 4 elements is ill-conditioned in bf16 storage: compare against the gradient scale
-        assert float((dx.float().permute(0, 3, 1, 2).cpu() - xr.grad).abs().max() / xr.grad.abs().max()) < tol * (4 if H == 2 else 1)
+        assert float((dx.float().permute(0, 3, 1, 2).cpu() - xr.grad).abs().max() / xr.grad.abs().max()) < tol * (4 if H == 2 else 2 if H == 4 else 1)
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-6), (torch.bfloat16, 1e-2)])
