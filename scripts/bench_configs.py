@@ -2,7 +2,8 @@
   configs[0]  CIFAR-10 shape, batch 128 (the reference's CPU-runnable case), on the GPU path
   configs[3]  ImageNet-10 shape 3x224x224, ResNet18 (scaler-49 extension) + UnetGenerator, batch 64 and 256 per GPU
   configs[4]  CelebA 3x64x64 multilabel step (train_generator_multilabel.py:160-242), ResNet18(8) + CUnetGeneratorv1
-Device-resident inputs, CUDA-graph replay, CUDA events, bf16 tcgen05 path, one GPU.  One JSON line per case; a failing
+Device-resident inputs, CUDA-graph replay, CUDA events, bf16 tcgen05 path, one GPU.  `--eager` runs one un-graphed iteration
+per selected case instead (what `scripts/gpu_launchlist_configs.sh` puts under ncu).  One JSON line per case; a failing
 case prints its exception instead of a number.  FLOPs per image from SURVEY.md section 8(d)."""
 import json
 import os
@@ -35,8 +36,10 @@ CASES = [
     ("configs[3] ImageNet-10 shape 224x224, batch 64", "imagenet10", 224, 10, 64, False, 458e9, 1e-4),
     ("configs[3] ImageNet-10 shape 224x224, batch 256", "imagenet10", 224, 10, 256, False, 458e9, 1e-4),
 ]
-if len(sys.argv) > 1:
-    CASES = [c for c in CASES if any(a in c[0] for a in sys.argv[1:])]
+ARGS = [a for a in sys.argv[1:] if not a.startswith("--")]
+EAGER = "--eager" in sys.argv       # one eager (no CUDA graph) iteration after one warm-up: for `ncu` launch lists
+if ARGS:
+    CASES = [c for c in CASES if any(a in c[0] for a in ARGS)]
 
 
 def run(name, dataset, S, ncls, B, multilabel, flops, lr, steps=5, warmup=3):
@@ -54,20 +57,22 @@ def run(name, dataset, S, ncls, B, multilabel, flops, lr, steps=5, warmup=3):
     g = torch.Generator().manual_seed(7)
     xs = [(torch.rand(B, 3, S, S, generator=g) * 2 - 1).to(dev) for _ in range(2)]
     ys = [torch.randint(0, ncls, (B,), generator=g).numpy() for _ in range(2)]
+    if EAGER:
+        steps, warmup = 1, 1
     for i in range(warmup):
-        out = eng.step(xs[i % 2], ys[i % 2], use_graph=True)
+        out = eng.step(xs[i % 2], ys[i % 2], use_graph=not EAGER)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(steps):
-        out = eng.step(xs[i % 2], ys[i % 2], use_graph=True)
+        out = eng.step(xs[i % 2], ys[i % 2], use_graph=not EAGER)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     losses = [float(v) for v in out["losses"].cpu()]
     assert all(np.isfinite(losses)), losses
     rate = B / (ms * 1e-3)
-    return {"case": name, "images_per_s": rate, "ms_per_step": ms, "batch": B, "steps": steps, "warmup": warmup, "dtype": "bf16",
+    return {"case": name, "images_per_s": rate, "ms_per_step": ms, "batch": B, "cuda_graph": not EAGER, "steps": steps, "warmup": warmup, "dtype": "bf16",
             "lr": lr, "update_flops_per_image": flops, "step_frac_of_tensor_peak": rate * flops / 1e12 / peak_tf, "peak_TFLOP/s": peak_tf,
             "max_memory_GB": torch.cuda.max_memory_allocated() / 1e9, "losses": losses[:4]}
 
