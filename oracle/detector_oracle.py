@@ -86,7 +86,7 @@ def randshadow(img: np.ndarray, input_size=32, random_shadow=StandInRandomShadow
 
 def patching_train(sample: torch.Tensor, train_data: torch.Tensor, n_input=3, input_size=32) -> np.ndarray:
     """train.py:106-143: one synthetic-trigger image (HWC).  numpy global RNG, in the reference's order:
-    attack, pat_size_x, pat_size_y, [block noise | augmentation draws | randind], margin, rand_loc."""
+    attack, patch height, patch width, [block noise | augmentation draws | blend partner], margin, corner."""
     clean = _hwc(sample)
     attack = np.random.randint(0, 5)
     px = np.random.randint(2, 8)
@@ -106,16 +106,10 @@ def patching_train(sample: torch.Tensor, train_data: torch.Tensor, n_input=3, in
         mid[mid > 1] = 1
         return mid
     margin = np.random.randint(0, 6)
-    rand_loc = np.random.randint(0, 4)
-    s = input_size
-    if rand_loc == 0:
-        output[margin:margin + px, margin:margin + py, :] = block
-    elif rand_loc == 1:
-        output[margin:margin + px, s - margin - py:s - margin, :] = block
-    elif rand_loc == 2:
-        output[s - margin - px:s - margin, margin:margin + py, :] = block
-    else:
-        output[s - margin - px:s - margin, s - margin - py:s - margin, :] = block
+    corner = np.random.randint(0, 4)  # 0 upper left, 1 upper right, 2 lower left, 3 lower right (train.py:131-139)
+    r0 = margin if corner in (0, 1) else input_size - margin - px
+    c0 = margin if corner in (0, 2) else input_size - margin - py
+    output[r0:r0 + px, c0:c0 + py, :] = block
     output[output > 1] = 1
     return output
 
