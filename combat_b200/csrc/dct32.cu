@@ -55,18 +55,10 @@ __device__ __forceinline__ void load_plane(const void* in, long long plane, floa
   }
 }
 
-template <int NP, int LIM>
-__device__ __forceinline__ void row_store(float* row, const float (&b)[NP]) {  // row[k] = b[k] for k < LIM
+template <int NP>
+__device__ __forceinline__ void row_store(float* row, const float (&b)[NP]) {
 #pragma unroll
-  for (int j = 0; j < NP / 4; ++j) {
-    if (4 * j + 3 < LIM) {
-      *(float4*)(row + 4 * j) = make_float4(b[4 * j], b[4 * j + 1], b[4 * j + 2], b[4 * j + 3]);
-    } else {
-#pragma unroll
-      for (int k = 4 * j; k < 4 * j + 4; ++k)
-        if (k < LIM) row[k] = b[k];
-    }
-  }
+  for (int j = 0; j < NP / 4; ++j) *(float4*)(row + 4 * j) = make_float4(b[4 * j], b[4 * j + 1], b[4 * j + 2], b[4 * j + 3]);
 }
 
 // The 1-D operator of one pass: DCT-II, DCT-III, or the low-pass projection P = D^T diag(1_keep) D.
@@ -120,7 +112,7 @@ __device__ __forceinline__ void transform_plane(float* out, long long plane, flo
     apply_1d<NP, KIND, KEEP>(a, b, keep);
     if (pass == 0) {
       // a thread only rewrites the row it has just read: no synchronisation between its loads and these stores
-      row_store<NP, NP>(row, b);
+      row_store<NP>(row, b);
       sync();
     } else {
 #pragma unroll
