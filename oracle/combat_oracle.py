@@ -171,7 +171,7 @@ def gaussian_kernel1d(sigma: float, ksize: int = 3) -> torch.Tensor:
 
 def gaussian_blur(img: torch.Tensor, sigma: float, ksize: int = 3) -> torch.Tensor:
     """Separable Gaussian as a depthwise conv with reflect padding."""
-    k1 = gaussian_kernel1d(sigma, ksize).to(img.dtype)
+    k1 = gaussian_kernel1d(sigma, ksize).to(img)  # dtype and device of the image (the taps are evaluated in float32 on the host)
     k2 = torch.mm(k1[:, None], k1[None, :])
     C = img.shape[-3]
     w = k2.expand(C, 1, ksize, ksize)
