@@ -55,42 +55,49 @@ class ParamStore:
     weight-gradient kernels produce); `p(name)` exposes them as a permuted view with the reference's OIHW shape,
     i.e. exactly a torch channels_last tensor, so state_dict round-trips keep the reference's names and shapes."""
 
-    def __init__(self, specs, device):
+    def __init__(self, specs, device, store_ci=None):
+        """store_ci: {weight name: stored input channels >= the logical ones}.  The extra input channels of such a conv
+        weight exist only in storage (zero, and they stay zero: their inputs are zero planes, so their gradient is exactly
+        zero and weight decay keeps 0 at 0); `p/g/m` expose the logical OIHW shape as a slice of the stored tensor."""
         self.names = [n for n, _ in specs]
         self.shapes = {n: tuple(s) for n, s in specs}
+        self.store_ci = dict(store_ci or {})
         self.offsets = {}
         off = 0
         for n, s in specs:
             self.offsets[n] = off
-            num = 1
-            for d in s:
-                num *= d
-            off += _align(num)
+            off += _align(self._stored_numel(n))
         self.numel = off
         self.flat = torch.zeros(off, dtype=torch.float32, device=device)
         self.grad = torch.zeros(off, dtype=torch.float32, device=device)
         self.mom = torch.zeros(off, dtype=torch.float32, device=device)
         self.first_step = True
 
+    def _stored_numel(self, n):
+        s = self.shapes[n]
+        num = 1
+        for d in s:
+            num *= d
+        if n in self.store_ci:
+            num = num // s[1] * self.store_ci[n]
+        return num
+
     def _view(self, buf, n):
         s = self.shapes[n]
-        num = 1
-        for d in s:
-            num *= d
         o = self.offsets[n]
+        flat = buf[o:o + self._stored_numel(n)]
         if len(s) == 4:
             co, ci, kh, kw = s
-            return buf[o:o + num].view(co, kh, kw, ci).permute(0, 3, 1, 2)
-        return buf[o:o + num].view(s)
+            v = flat.view(co, kh, kw, self.store_ci.get(n, ci))
+            if n in self.store_ci:
+                v = v[..., :ci]
+            return v.permute(0, 3, 1, 2)
+        return flat.view(s)
 
     def raw(self, buf, n):
-        """contiguous storage-order view (channels-last for conv weights)"""
-        s = self.shapes[n]
-        num = 1
-        for d in s:
-            num *= d
+        """contiguous storage-order view (channels-last for conv weights, stored input channels included)"""
         o = self.offsets[n]
-        return buf[o:o + num]
+        return buf[o:o + self._stored_numel(n)]
 
     def p(self, n):
         return self._view(self.flat, n)
@@ -152,8 +159,8 @@ class NetBase:
         self.convs: dict[str, ConvSpec] = {}
 
     # ---- construction helpers
-    def _finish_params(self, specs, conv_specs):
-        self.store = ParamStore(specs, self.device)
+    def _finish_params(self, specs, conv_specs, store_ci=None):
+        self.store = ParamStore(specs, self.device, store_ci)
         off = 0
         table = []
         for cs in conv_specs:
@@ -273,11 +280,13 @@ class NetBase:
         Cx = cs.Cin if n_out_ch is None else n_out_ch
         dx = torch.empty((N, H, W, Cx), dtype=self.dtype, device=self.device)
         padp = cs.k - 1 - cs.pad
-        if self._tc_ok(cs) and Cx == cs.Cin:
-            d = ops.conv_tc_desc(dy, self._wptr(cs, True), dx, N, Ho, Wo, cs.Cout, H, W, cs.Cin, cs.k, cs.k, 1, padp,
+        # the dgrad filter is stored [Cin][taps][Cout]: its first Cx rows ARE the filter of the first Cx input channels, so a
+        # leading multiple-of-64 subset runs on the tensor cores as a conv with Cx output channels (stride-1 convs only)
+        if self._tc_ok(cs) and (Cx == cs.Cin or (Cx % 64 == 0 and Cx < cs.Cin and cs.stride == 1)):
+            d = ops.conv_tc_desc(dy, self._wptr(cs, True), dx, N, Ho, Wo, cs.Cout, H, W, Cx, cs.k, cs.k, 1, padp,
                                  cs.stride, residual=residual, mask=mask, mask_scale=mask_scale, post_add=post_add)
             if lib.combat_conv_tc_supported(C.byref(d)):
-                _tc_launch(lambda: lib.combat_conv_tc(C.byref(d), ops._s()), "conv_tc(dgrad)", 2.0 * N * Ho * Wo * cs.Cout * cs.Cin * cs.k * cs.k,
+                _tc_launch(lambda: lib.combat_conv_tc(C.byref(d), ops._s()), "conv_tc(dgrad)", 2.0 * N * Ho * Wo * cs.Cout * Cx * cs.k * cs.k,
                            _tag(N, H, W, cs))
                 return dx
         if mask is not None or post_add is not None:
@@ -703,13 +712,21 @@ class Generator(NetBase):
               "upconv3_0": (nf * 8, nf * 4), "upconv2_1": (nf * 4, nf * 4), "upconv2_0": (nf * 4, nf * 2),
               "upconv1_1": (nf * 2, nf * 2), "upconv1_0": (nf * 2, nf), "upconv0_1": (nf, nf),
               "upconv0_0": (nf, out_channel)}
-        specs, convs = [], []
+        # CUnetGeneratorv1.conv0_1 reads nf + num_classes channels (72 for CelebA): not a multiple of the 64-channel K chunk of
+        # the tcgen05 kernels, so it ran on the generic CUDA-core kernel (1.2 ms per launch, 8.5 ms of the 34.7 ms CelebA step,
+        # profiles/r01_launches_celeba_multilabel_partial.md).  COMBAT_PAD_COND=1 stores that weight with its input channels
+        # padded to the next multiple of 64 (zeros, see ParamStore) and gives the concatenated activation the same width.
+        # Opt-in until it has been through the GPU parity tests (written after round 1's GPU budget was spent).
+        self.cond_pad = bool(os.environ.get("COMBAT_PAD_COND")) and self.use_tc and num_classes > 0 and (nf + num_classes) % 64 != 0
+        specs, convs, store_ci = [], [], {}
         for name, stride in self.LAYERS:
             ci, co = ch[name]
             specs.append((name + ".weight", (co, ci, 3, 3)))
             specs.append((name + ".bias", (co,)))
-            convs.append(ConvSpec(name, ci, co, 3, stride, 1, True, need_dgrad=(name != "conv0_0")))
-        self._finish_params(specs, convs)
+            if name == "conv0_1" and self.cond_pad:
+                store_ci[name + ".weight"] = _align(ci, 64)
+            convs.append(ConvSpec(name, store_ci.get(name + ".weight", ci), co, 3, stride, 1, True, need_dgrad=(name != "conv0_0")))
+        self._finish_params(specs, convs, store_ci)
 
     def load_state_dict(self, sd):
         self.store.load(sd)
@@ -726,7 +743,10 @@ class Generator(NetBase):
         ctx = {"x": x_nchw} if save else None
         c00 = self.conv_first_fwd(x_nchw, cv["conv0_0"], pre=False)
         if self.cond:  # cat(f0, one_hot planes) then the in-place LeakyReLU (identity on the 0/1 planes)
-            a00 = torch.empty((N, H // 2, W // 2, nf + self.cond), dtype=self.dtype, device=self.device)
+            if self.cond_pad:  # stored width of conv0_1's input; the padding planes stay zero
+                a00 = torch.zeros((N, H // 2, W // 2, cv["conv0_1"].Cin), dtype=self.dtype, device=self.device)
+            else:
+                a00 = torch.empty((N, H // 2, W // 2, nf + self.cond), dtype=self.dtype, device=self.device)
             ops.lrelu_into_slice(c00, a00, 0)
             ops.onehot_planes(a00, labels, nf, self.cond)
         else:

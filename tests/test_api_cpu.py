@@ -136,3 +136,41 @@ def test_multilabel_plan_matches_oracle_chunks_and_draws():
             assert (plan.bd_targets[si:ei] == ci).all()
             np.testing.assert_allclose(plan.taps_rows[si:ei], np.tile(ops.gaussian_taps(sg), (ei - si, 1)).astype(np.float32))
         assert sum(ei - si for _, si, ei in chunks) == bs
+
+
+def test_param_store_padded_input_channels_round_trip():
+    """ParamStore(store_ci=...): a conv weight stored with extra (zero) input channels keeps the reference's logical OIHW
+    shape in p()/g()/state(), loads a reference tensor into the leading channels only, and lays the storage out
+    channels-last with the stored width -- what the opt-in padded CUnetGeneratorv1.conv0_1 (COMBAT_PAD_COND) relies on."""
+    import torch
+
+    from combat_b200.nets import ParamStore
+    specs = [("a.weight", (4, 5, 3, 3)), ("a.bias", (4,)), ("b.weight", (2, 3, 1, 1))]
+    st = ParamStore(specs, "cpu", {"a.weight": 8})
+    plain = ParamStore(specs, "cpu")
+    assert st.shapes == plain.shapes and tuple(st.p("a.weight").shape) == (4, 5, 3, 3)
+    assert st.raw(st.flat, "a.weight").numel() == 4 * 9 * 8 and plain.raw(plain.flat, "a.weight").numel() == 4 * 9 * 5
+    assert st.offsets["a.bias"] == 4 * 9 * 8 and plain.offsets["a.bias"] == 4 * 9 * 5
+    w = torch.randn(4, 5, 3, 3)
+    sd = {"a.weight": w, "a.bias": torch.arange(4.0), "b.weight": torch.ones(2, 3, 1, 1)}
+    st.load(sd)
+    plain.load(sd)
+    for k in sd:
+        assert torch.equal(st.state()[k], sd[k]) and torch.equal(plain.state()[k], sd[k])
+    stored = st.raw(st.flat, "a.weight").view(4, 3, 3, 8)
+    assert torch.equal(stored[..., :5].permute(0, 3, 1, 2), w) and float(stored[..., 5:].abs().sum()) == 0.0
+    st.g("a.weight").fill_(1.0)           # a gradient written through the logical view leaves the padding at zero
+    assert float(st.raw(st.grad, "a.weight").sum()) == 4 * 5 * 9
+
+
+def test_padded_conditional_generator_keeps_the_reference_shapes(monkeypatch):
+    from combat_b200 import nets
+    monkeypatch.setenv("COMBAT_PAD_COND", "1")
+    g = nets.Generator(num_classes=8, device="meta")
+    monkeypatch.delenv("COMBAT_PAD_COND")
+    ref = nets.Generator(num_classes=8, device="meta")
+    assert g.cond_pad and not ref.cond_pad
+    assert g.convs["conv0_1"].Cin == 128 and ref.convs["conv0_1"].Cin == 72
+    assert g.store.shapes == ref.store.shapes
+    assert tuple(g.store.p("conv0_1.weight").shape) == (64, 72, 3, 3)
+    assert g.store.numel - ref.store.numel == 64 * 9 * (128 - 72)
