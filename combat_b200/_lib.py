@@ -83,6 +83,10 @@ _SIGS = {
     "combat_pool_linear_fwd": ([vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp, vp, vp], i32),
     "combat_pool_linear_bwd": ([vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, i32, vp, vp, vp], i32),
     "combat_maxpool2": ([vp, vp, i32, i32, i32, i32, i32, vp], i32),
+    "combat_elu_bwd": ([vp, vp, vp, i32, i64, vp], i32),
+    "combat_maxpool2_bwd": ([vp, vp, vp, i32, i32, i32, i32, i32, vp], i32),
+    "combat_mask_scale": ([vp, vp, vp, i32, i64, f32, vp], i32),
+    "combat_adadelta": ([vp, vp, vp, vp, i64, vp, f32, f32, f32, vp], i32),
     "combat_nchw_to_nhwc": ([vp, vp, i32, i32, i32, i32, i32, vp], i32),
     "combat_nhwc_to_nchw": ([vp, i32, vp, i32, i32, i32, i32, vp], i32),
     "combat_onehot_planes": ([vp, i32, vp, i32, i32, i32, i32, i32, vp], i32),

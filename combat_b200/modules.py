@@ -208,12 +208,14 @@ class CUnetGeneratorv1(_GeneratorModule):
 
 
 class FrequencyModel(_KernelModule):
-    """defenses/frequency_based/model.py:8-52 (inference only on this path)."""
+    """defenses/frequency_based/model.py:8-52.  `forward` is the inference path; training goes through
+    combat_b200.defenses.frequency_based.train (trainable=True builds the float32 training configuration)."""
 
-    def __init__(self, num_classes=2, n_input=3, input_size=32, device=None, dtype=None):
+    def __init__(self, num_classes=2, n_input=3, input_size=32, device=None, dtype=None, trainable=False):
         super().__init__()
         device = torch.device(device or "cuda")
-        net = nets.FrequencyDetector(num_classes, n_input, input_size, device=device, dtype=dtype or default_dtype())
+        net = nets.FrequencyDetector(num_classes, n_input, input_size, device=device, dtype=dtype or default_dtype(),
+                                     trainable=trainable)
         bufs = []
         for i in range(1, 7):
             bufs += [("bn%d.running_mean" % i, net.rm[i]), ("bn%d.running_var" % i, net.rv[i]),
@@ -236,7 +238,8 @@ class FrequencyModel(_KernelModule):
 
     def forward(self, x):
         if self.training:
-            raise NotImplementedError("FrequencyModel training is outside the hot path (SURVEY.md section 8f)")
+            raise NotImplementedError("FrequencyModel.forward is the inference path; train through "
+                                      "combat_b200.defenses.frequency_based.train.train (SURVEY.md section 8f row 3)")
         self.net._affine, self.net._padded = None, None  # weights may have been (re)loaded
         with torch.no_grad():
             return self.net.forward(x.contiguous().float())

@@ -872,8 +872,9 @@ class FrequencyDetector(NetBase):
     tcgen05 kernel with ELU + folded BatchNorm in its epilogue; channel counts below 64 are zero-padded to 64 once,
     when the (frozen) weights are loaded."""
 
-    def __init__(self, num_classes=2, n_input=3, input_size=32, device="cuda", dtype=torch.float32):
+    def __init__(self, num_classes=2, n_input=3, input_size=32, device="cuda", dtype=torch.float32, trainable=False):
         super().__init__(device, torch.float32, use_tc=False)
+        self.trainable = bool(trainable)  # train_forward / train_backward / adadelta_step (float32 CUDA-core path)
         self.act_dtype = dtype
         self.tc = dtype == torch.bfloat16
         self.scaler = {32: 1, 64: 4}[input_size]
@@ -885,7 +886,7 @@ class FrequencyDetector(NetBase):
             specs.append(("conv%d.bias" % i, (chans[i],)))
             specs.append(("bn%d.weight" % i, (chans[i],)))
             specs.append(("bn%d.bias" % i, (chans[i],)))
-            convs.append(ConvSpec("conv%d" % i, chans[i - 1], chans[i], 3, 1, 1, True, need_dgrad=False))
+            convs.append(ConvSpec("conv%d" % i, chans[i - 1], chans[i], 3, 1, 1, True, need_dgrad=self.trainable and i > 1))
         specs.append(("linear6.weight", (num_classes, 2048 * self.scaler)))
         specs.append(("linear6.bias", (num_classes,)))
         self._finish_params(specs, convs)
@@ -978,3 +979,82 @@ class FrequencyDetector(NetBase):
                 hw = (hw[0] // 2, hw[1] // 2)
         logits, _ = ops.pool_linear_fwd(h, 1, self.store.p("linear6.weight"), self.store.p("linear6.bias"))
         return logits
+
+    # ------------------------------------------------------------------ training
+    # defenses/frequency_based/train.py:178-221 on the float32 CUDA-core kernels: a first CORRECT path (generic strided
+    # convolutions), to be held to oracle/detector_oracle.py before any of it moves to the tensor cores.  Written at the close
+    # of round 1, not yet run on a GPU; nothing in the alternated step calls it.
+    DROPOUT_P = 0.2
+
+    def draw_dropout_masks(self, N, H, W):
+        """The three Dropout(0.2) keep masks of one training forward (after max-pools 1..3), drawn on the HOST from the
+        torch CPU generator with the shapes and order torch's own dropout would use on the NCHW activations
+        (model.py:22,33,44), returned as uint8 NHWC device tensors."""
+        masks, hw = [], (H, W)
+        for i in (2, 4, 6):
+            hw = (hw[0] // 2, hw[1] // 2)
+            keep = torch.nn.functional.dropout(torch.ones(N, self.chans[i], hw[0], hw[1]), self.DROPOUT_P, True) != 0
+            masks.append(keep.permute(0, 2, 3, 1).contiguous().to(torch.uint8).to(self.device, non_blocking=True))
+        return masks
+
+    def train_forward(self, x_nchw, masks, momentum=0.1, eps=1e-5):
+        """x: float32 NCHW DCT coefficients; masks: draw_dropout_masks(...).  conv -> ELU -> BatchNorm(batch statistics, running
+        statistics updated) x6, MaxPool2d(2) + Dropout after layers 2 / 4 / 6, flatten (NCHW order), linear.
+        Returns (logits [N, num_classes], ctx for train_backward)."""
+        if not self.trainable or self.tc:
+            raise RuntimeError("FrequencyDetector(trainable=True, dtype=torch.float32) is the training configuration")
+        N, Cc, H, W = x_nchw.shape
+        h, strides, hw = x_nchw, ops.nchw_strides(Cc, H, W), (H, W)
+        layers = []
+        for i in range(1, 7):
+            cs = self.convs["conv%d" % i]
+            a = torch.empty((N, hw[0], hw[1], cs.Cout), dtype=torch.float32, device=self.device)
+            ops.conv_simt(h, (N, hw[0], hw[1]), strides, self._wptr(cs), self.dt, a, hw, ops.nhwc_strides(hw[0], hw[1], cs.Cout),
+                          Ci=cs.Cin, Co=cs.Cout, KH=3, KW=3, stride=1, pad=1, bias=self._bias(cs), act=2)   # a = elu(conv + bias)
+            sc, sh, mean, invstd = ops.bn_train_prepare(a, N * hw[0] * hw[1], cs.Cout, self.store.p("bn%d.weight" % i),
+                                                        self.store.p("bn%d.bias" % i), self.rm[i], self.rv[i], momentum, eps)
+            y = ops.affine_act(a, sc, sh, False)
+            rec = {"x": h, "x_strides": strides, "hw": hw, "a": a, "mean": mean, "invstd": invstd}
+            h = y
+            if i % 2 == 0:
+                pooled = ops.maxpool2(y)
+                rec["y"] = y
+                hw = (hw[0] // 2, hw[1] // 2)
+                h = ops.mask_scale(pooled, masks[i // 2 - 1], 1.0 / (1.0 - self.DROPOUT_P))
+            layers.append(rec)
+            strides = ops.nhwc_strides(hw[0], hw[1], cs.Cout)
+        logits, feat = ops.pool_linear_fwd(h, 1, self.store.p("linear6.weight"), self.store.p("linear6.bias"))
+        self._affine = None  # running statistics changed: the cached eval-mode affine is stale
+        return logits, {"layers": layers, "masks": masks, "feat": feat, "h_shape": tuple(h.shape), "N": N}
+
+    def train_backward(self, ctx, dlogits):
+        """Accumulates every parameter gradient into the flat gradient buffer (call zero_grad() first)."""
+        st = self.store
+        d = ops.pool_linear_bwd(dlogits, ctx["feat"], st.p("linear6.weight"), ctx["h_shape"], torch.float32, 1,
+                                dW=st.g("linear6.weight"), db=st.g("linear6.bias"))
+        N = ctx["N"]
+        for i in range(6, 0, -1):
+            cs, rec = self.convs["conv%d" % i], ctx["layers"][i - 1]
+            if i % 2 == 0:
+                d = ops.mask_scale(d, ctx["masks"][i // 2 - 1], 1.0 / (1.0 - self.DROPOUT_P))
+                d = ops.maxpool2_bwd(d, rec["y"])
+            da, _ = ops.bn_bwd_train(d, rec["a"], None, st.p("bn%d.weight" % i), rec["mean"], rec["invstd"], False,
+                                     st.g("bn%d.weight" % i), st.g("bn%d.bias" % i))
+            dz = ops.elu_bwd(da, rec["a"])
+            H, W = rec["hw"]
+            ops.conv_wgrad_simt(rec["x"], (N, H, W), rec["x_strides"], dz, (H, W), ops.nhwc_strides(H, W, cs.Cout),
+                                st.raw(st.grad, cs.name + ".weight"), Ci=cs.Cin, Co=cs.Cout, KH=3, KW=3, stride=1, pad=1,
+                                db=st.g(cs.name + ".bias"))
+            if i > 1:
+                d = self.conv_dgrad(dz, cs, (H, W))
+
+    def adadelta_step(self, lr_dev, rho=0.9, eps=1e-6, wd=1e-4):
+        """torch.optim.Adadelta(lr=0.05, weight_decay=1e-4) of train.py:152 over the flat buffer (square_avg lives in the
+        store's momentum buffer, acc_delta in a buffer allocated on first use), then the compute-layout weights."""
+        st = self.store
+        if not hasattr(st, "acc_delta"):
+            st.acc_delta = torch.zeros_like(st.flat)
+        ops.adadelta(st.flat, st.grad, st.mom, st.acc_delta, lr_dev, rho, eps, wd)
+        self.prep_weights()
+        self._padded = None
+

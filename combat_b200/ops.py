@@ -479,6 +479,34 @@ def maxpool2(x):
     return y
 
 
+def maxpool2_bwd(dy, x):
+    """dy: NHWC gradient of maxpool2(x); x: the pooled tensor's input."""
+    N, H, W, Cc = x.shape
+    dx = torch.empty_like(x)
+    check(lib.combat_maxpool2_bwd(_p(dy), _p(x), _p(dx), dt_code(x), N, H, W, Cc, _s()), "maxpool2_bwd")
+    return dx
+
+
+def elu_bwd(da, a):
+    """da: gradient w.r.t. a = elu(z) (the kept output) -> gradient w.r.t. z."""
+    dz = torch.empty_like(da)
+    check(lib.combat_elu_bwd(_p(da), _p(a), _p(dz), dt_code(da), da.numel(), _s()), "elu_bwd")
+    return dz
+
+
+def mask_scale(x, keep, scale):
+    """dropout with a given uint8 keep mask (same element order as x): keep ? x * scale : 0."""
+    if keep.dtype != torch.uint8 or keep.numel() != x.numel():
+        raise ValueError("keep mask: uint8, one byte per element of x")
+    y = torch.empty_like(x)
+    check(lib.combat_mask_scale(_p(x), _p(keep), _p(y), dt_code(x), x.numel(), float(scale), _s()), "mask_scale")
+    return y
+
+
+def adadelta(p, g, square_avg, acc_delta, lr_dev, rho=0.9, eps=1e-6, wd=1e-4):
+    check(lib.combat_adadelta(_p(p), _p(g), _p(square_avg), _p(acc_delta), p.numel(), _p(lr_dev), rho, eps, wd, _s()), "adadelta")
+
+
 def nchw_to_nhwc(x, dtype):
     N, Cc, H, W = x.shape
     y = torch.empty((N, H, W, Cc), dtype=dtype, device=x.device)

@@ -244,6 +244,21 @@ int combat_pool_linear_bwd(const float* dlogits, const float* pooled, const floa
                            int ncls, void* dx, int dtype, float* dW, float* db, void* stream);
 /* max_pool2d(2) NHWC (defenses/frequency_based/model.py:21,32,43) */
 int combat_maxpool2(const void* x, void* y, int dtype, int N, int H, int W, int C, void* stream);
+
+/* ---------------------------------------------------------------- frequency-detector TRAINING (csrc/detector.cu)
+ * defenses/frequency_based/train.py:178-221 with model.py:8-52 in train mode.  Next row of the scope table:
+ * declared and built, not yet part of a GPU-validated path.
+ *   combat_elu_bwd       nn.ELU backward from the kept OUTPUT a: dz = da * (a > 0 ? 1 : a + 1)           (model.py:14..39)
+ *   combat_maxpool2_bwd  nn.MaxPool2d((2,2)) backward, NHWC; gradient to the first maximum of each window (model.py:21,32,43)
+ *   combat_mask_scale    nn.Dropout(0.2) with a caller-provided keep mask (1 byte / element): y = keep ? x * scale : 0;
+ *                        forward and backward are the same map                                        (model.py:22,33,44)
+ *   combat_adadelta      torch.optim.Adadelta(lr = 0.05, weight_decay = 1e-4) over flat float32 buffers      (train.py:152)
+ */
+int combat_elu_bwd(const void* da, const void* a, void* dz, int dtype, long long n, void* stream);
+int combat_maxpool2_bwd(const void* dy, const void* x, void* dx, int dtype, int N, int H, int W, int C, void* stream);
+int combat_mask_scale(const void* x, const unsigned char* keep, void* y, int dtype, long long n, float scale, void* stream);
+int combat_adadelta(float* p, const float* g, float* square_avg, float* acc_delta, long long n, const float* lr_dev, float rho,
+                    float eps, float wd, void* stream);
 /* layout/dtype helpers */
 int combat_nchw_to_nhwc(const float* x, void* y, int dtype, int N, int C, int H, int W, void* stream);
 int combat_nhwc_to_nchw(const void* x, int dtype, float* y, int N, int C, int H, int W, void* stream);
