@@ -1004,7 +1004,7 @@ class FrequencyDetector(NetBase):
         if not self.trainable or self.tc:
             raise RuntimeError("FrequencyDetector(trainable=True, dtype=torch.float32) is the training configuration")
         N, Cc, H, W = x_nchw.shape
-        h, strides, hw = x_nchw, ops.nchw_strides(Cc, H, W), (H, W)
+        h, strides, hw = ops._contig(x_nchw), ops.nchw_strides(Cc, H, W), (H, W)   # raw-pointer kernels: dense NCHW only
         layers = []
         for i in range(1, 7):
             cs = self.convs["conv%d" % i]
