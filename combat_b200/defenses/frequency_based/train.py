@@ -8,7 +8,7 @@ backward, Adadelta) runs on the CUDA kernels of nets.FrequencyDetector.  Checker
 unmodified reference (tests/golden/detector_b8x2.npz).
 
 STATUS: written at the close of round 1 after the GPU budget was spent -- the DCT launch is GPU-validated
-(tests/test_detector_gpu.py), the training iteration has NOT yet run on a GPU (tests/test_detector_train_gpu.py is gated
+(tests/test_z_detector_dct_gpu.py), the training iteration has NOT yet run on a GPU (tests/test_detector_train_gpu.py is gated
 behind COMBAT_DETECTOR_TRAIN=1 until it has).
 """
 from __future__ import annotations
