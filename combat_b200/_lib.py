@@ -87,6 +87,9 @@ _SIGS = {
     "combat_maxpool2_bwd": ([vp, vp, vp, i32, i32, i32, i32, i32, vp], i32),
     "combat_mask_scale": ([vp, vp, vp, i32, i64, f32, vp], i32),
     "combat_adadelta": ([vp, vp, vp, vp, i64, vp, f32, f32, f32, vp], i32),
+    "combat_grad_l2": ([vp, vp, vp, vp, i32, i32, i32, i32, vp], i32),
+    "combat_post_transform_fwd": ([vp, vp, vp, i32, i32, i32, i32, vp], i32),
+    "combat_post_transform_bwd": ([vp, vp, vp, i32, i32, i32, i32, i32, vp], i32),
     "combat_nchw_to_nhwc": ([vp, vp, i32, i32, i32, i32, i32, vp], i32),
     "combat_nhwc_to_nchw": ([vp, i32, vp, i32, i32, i32, i32, vp], i32),
     "combat_onehot_planes": ([vp, i32, vp, i32, i32, i32, i32, i32, vp], i32),

@@ -1,6 +1,6 @@
 """The reference's CLI surface (config.py:4-86 of the reference): `get_arguments()` returns an argparse parser accepting the
 same flags with the same types and defaults -- pinned flag by flag against the reference by tests/golden/api.json
-(tests/test_api_cpu.py) -- plus three build-only flags that rename nothing: --dtype, --no_graph, --log_every.
+(tests/test_api_cpu.py) -- plus four build-only flags that rename nothing: --dtype, --no_graph, --log_every, --synthetic_data.
 
 The flags are declared as typed tables (name -> default) rather than one call per flag; flags this package does not act on
 (the other attack variants' knobs) are still accepted so that existing command lines keep parsing."""
@@ -53,5 +53,7 @@ def get_arguments():
     # build-only
     p.add_argument("--dtype", type=str, default="bf16", choices=["bf16", "fp32"], help="activation storage / conv operand type")
     p.add_argument("--no_graph", action="store_true", default=False, help="do not capture the step in a CUDA graph")
+    p.add_argument("--synthetic_data", action="store_true", default=False,
+                   help="uniform-noise images / random labels instead of the dataset (no network for torchvision's download)")
     p.add_argument("--log_every", type=int, default=50, help="read the device-side metric counters back every N iterations")
     return p

@@ -414,3 +414,64 @@ extern "C" int combat_poison_blend_bwd(const float* x, const float* noise, const
                                                                     dnoise, H * W, H, W, taps_dev, C, taps_rows);
   COMBAT_RETURN_LAUNCH("poison_blend_bwd");
 }
+
+// ---------------------------------------------------------------------------------------------- "Grad L2 Loss" (logged only)
+// train_generator.py:235-243: with e = inputs - inputs_bd zero-padded by F.pad(., (1, 1, 2, 1)),
+//   loss_grad_l2 = mean((e_ext[:, :, 1:] - e_ext[:, :, :-1])^2) + mean((e_ext[..., 1:] - e_ext[..., :-1])^2)
+// (MSE is taken between the difference images of inputs and inputs_bd; differences are linear, so it is the squared
+// difference image of e).  One CTA per plane writes the two partial sums; combat_grad_l2 then reduces them with the two
+// element counts B*C*(H+2)*(W+2) and B*C*(H+3)*(W+1).  The zero rows / columns of the padding only contribute through the
+// border terms e[0,c]^2, e[H-1,c]^2, e[r,0]^2, e[r,W-1]^2.
+__global__ void __launch_bounds__(256) grad_l2_partial_k(const float* __restrict__ x, const float* __restrict__ x_bd,
+                                                         float* __restrict__ partial, int H, int W) {
+  const long long base = (long long)blockIdx.x * H * W;
+  float sv = 0.f, sh = 0.f;
+  for (int i = threadIdx.x; i < H * W; i += blockDim.x) {
+    const int r = i / W, c = i - r * W;
+    const float e = x[base + i] - x_bd[base + i];
+    if (r == 0) sv = fmaf(e, e, sv);
+    if (r == H - 1) sv = fmaf(e, e, sv);
+    else { const float d = (x[base + i + W] - x_bd[base + i + W]) - e; sv = fmaf(d, d, sv); }
+    if (c == 0) sh = fmaf(e, e, sh);
+    if (c == W - 1) sh = fmaf(e, e, sh);
+    else { const float d = (x[base + i + 1] - x_bd[base + i + 1]) - e; sh = fmaf(d, d, sh); }
+  }
+  __shared__ float red[2][8];
+  sv = warp_sum(sv);
+  sh = warp_sum(sh);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = sv; red[1][threadIdx.x >> 5] = sh; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < 8; ++w) { a += red[0][w]; b += red[1][w]; }
+    partial[2 * blockIdx.x] = a;
+    partial[2 * blockIdx.x + 1] = b;
+  }
+}
+
+__global__ void __launch_bounds__(256) grad_l2_final_k(const float* __restrict__ partial, int planes, double inv_v, double inv_h,
+                                                       float* __restrict__ out) {
+  double av = 0.0, ah = 0.0;
+  for (int i = threadIdx.x; i < planes; i += blockDim.x) { av += (double)partial[2 * i]; ah += (double)partial[2 * i + 1]; }
+  __shared__ double red[2][256];
+  red[0][threadIdx.x] = av;
+  red[1][threadIdx.x] = ah;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) { red[0][threadIdx.x] += red[0][threadIdx.x + s]; red[1][threadIdx.x] += red[1][threadIdx.x + s]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = (float)(red[0][0] * inv_v + red[1][0] * inv_h);
+}
+
+extern "C" int combat_grad_l2(const float* x, const float* x_bd, float* partial, float* out, int rows, int C, int H, int W,
+                              void* stream) {
+  COMBAT_ARG(x && x_bd && partial && out, 0);
+  COMBAT_ARG(rows > 0 && C > 0 && H >= 2 && W >= 2, 4);
+  const int planes = rows * C;
+  grad_l2_partial_k<<<planes, 256, 0, (cudaStream_t)stream>>>(x, x_bd, partial, H, W);
+  COMBAT_CHECK_LAUNCH("grad_l2_partial");
+  const double inv_v = 1.0 / ((double)planes * (H + 2) * (W + 2)), inv_h = 1.0 / ((double)planes * (H + 3) * (W + 1));
+  grad_l2_final_k<<<1, 256, 0, (cudaStream_t)stream>>>(partial, planes, inv_v, inv_h, out);
+  COMBAT_RETURN_LAUNCH("grad_l2");
+}

@@ -24,6 +24,7 @@ import torch
 
 from . import ops
 from .nets import Classifier, FrequencyDetector, Generator
+from .utils.dataloader import PARAM_WIDTH as TF_W, draw_params as draw_tf_params
 
 
 def default_opt(**kw):
@@ -32,6 +33,7 @@ def default_opt(**kw):
         dataset="cifar10", input_height=32, input_width=32, input_channel=3, num_classes=10, attack_mode="all2one",
         noise_rate=0.08, target_label=0, pc=0.5, ratio=0.65, kernel_size=3, sigma=(0.1, 1.0), L2_weight=0.02,
         clean_model_weight=0.8, lr_C=1e-2, lr_G=1e-2, bs=128,
+        post_transform_option="no_use", random_crop=5, random_rotation=10,   # the CLI default is "use" (config.py:75)
     )
     for k, v in kw.items():
         setattr(o, k, v)
@@ -53,6 +55,17 @@ class StepPlan:
     taps_g: tuple
     taps_rows: np.ndarray | None = None   # multilabel: float32 [B, 2] per-row blur taps (one sigma per class chunk)
     sigmas_g: list | None = None          # multilabel: the per-chunk sigma draws
+    # PostTensorTransform parameters of the five calls of one iteration (utils/dataloader.py), float32 [5, B, 8] in STORAGE
+    # order T1 (:196) | T3 (:227) | T4 (:228) | T2 (:214) | T5 (:250): [1:3] is the parameter block of netC's batched
+    # [x ; x_bd] forward, [3:5] that of clean_model's.  None: --post_transform_option no_use.
+    tf: np.ndarray | None = None
+
+
+TF_SLOT = {"T1": 0, "T3": 1, "T4": 2, "T2": 3, "T5": 4}
+
+
+def _tf_on(opt) -> bool:
+    return getattr(opt, "post_transform_option", "no_use") != "no_use"
 
 
 def create_targets_bd_np(targets: np.ndarray, opt) -> np.ndarray:
@@ -64,10 +77,12 @@ def create_targets_bd_np(targets: np.ndarray, opt) -> np.ndarray:
     raise Exception("{} attack mode is not implemented".format(opt.attack_mode))
 
 
-def make_plan(targets_host, opt) -> StepPlan:
-    """train_generator.py:173,181-183,193-194,226 -- consumes the numpy global RNG and the torch CPU generator in
-    the reference's order."""
+def make_plan(targets_host, opt, with_metrics=True) -> StepPlan:
+    """train_generator.py:173,181-183,193-194,196,214,226-228,250 -- consumes the numpy global RNG, Python's `random` and the
+    torch CPU generator in the reference's order: poison count, C-step sigma, T1, [T2], G-step sigma, [T3], T4, T5 (the
+    transforms draw nothing under --post_transform_option no_use; T2 / T3 belong to the metric forwards)."""
     y = np.asarray(targets_host, dtype=np.int64)
+    B = y.shape[0]
     bd = create_targets_bd_np(y, opt).astype(np.int64)
     trg = np.nonzero(y == bd)[0]
     ntrg = np.nonzero(y != bd)[0]
@@ -77,10 +92,22 @@ def make_plan(targets_host, opt) -> StepPlan:
     if num_bd > 0:
         sigma_c = torch.empty(1).uniform_(opt.sigma[0], opt.sigma[1]).item()
         taps_c = ops.gaussian_taps(sigma_c)
-    sigma_g = torch.empty(1).uniform_(opt.sigma[0], opt.sigma[1]).item()
+    tf = None
+    if _tf_on(opt):
+        tf = np.zeros((5, B, TF_W), dtype=np.float32)
+        tf[:, :, 2] = 1.0
+        tf[TF_SLOT["T1"]] = draw_tf_params(B, opt)                                    # :196
+        if with_metrics:
+            tf[TF_SLOT["T2"]] = draw_tf_params(B, opt)                                # :214
+    sigma_g = torch.empty(1).uniform_(opt.sigma[0], opt.sigma[1]).item()              # :226
+    if tf is not None:
+        if with_metrics:
+            tf[TF_SLOT["T3"]] = draw_tf_params(B, opt)                                # :227
+        tf[TF_SLOT["T4"]] = draw_tf_params(B, opt)                                    # :228
+        tf[TF_SLOT["T5"]] = draw_tf_params(B, opt)                                    # :250
     perm = np.concatenate([trg, ntrg]).astype(np.int32)
     total_y = np.concatenate([bd[trg[:num_bd]], y[trg[num_bd:]], y[ntrg]]).astype(np.int64)
-    return StepPlan(perm, num_bd, trg, ntrg, bd, total_y, sigma_c, sigma_g, taps_c, ops.gaussian_taps(sigma_g))
+    return StepPlan(perm, num_bd, trg, ntrg, bd, total_y, sigma_c, sigma_g, taps_c, ops.gaussian_taps(sigma_g), tf=tf)
 
 
 def multilabel_chunks(bs: int, num_classes: int):
@@ -95,10 +122,10 @@ def multilabel_chunks(bs: int, num_classes: int):
     return out
 
 
-def make_plan_multilabel(targets_host, opt) -> StepPlan:
-    """train_generator_multilabel.py:171,74,203-220 -- numpy rand(bs) for the poison count (the FIRST num_bd rows are
-    poisoned, labels unchanged), one torch CPU uniform for the C-step blur (only when num_bd > 0), then one per class
-    chunk of the G-step, in chunk order."""
+def make_plan_multilabel(targets_host, opt, with_metrics=True) -> StepPlan:
+    """train_generator_multilabel.py:171,74,179,190,199,203-220,225,236 -- numpy rand(bs) for the poison count (the FIRST
+    num_bd rows are poisoned, labels unchanged), one torch CPU uniform for the C-step blur (only when num_bd > 0), the
+    transforms T1, [T2], [T3], then one uniform per class chunk of the G-step, in chunk order, then T4, T5."""
     y = np.asarray(targets_host, dtype=np.int64)
     bs = y.shape[0]
     num_bd = int(np.sum(np.random.rand(bs) < opt.pc))
@@ -106,6 +133,14 @@ def make_plan_multilabel(targets_host, opt) -> StepPlan:
     if num_bd > 0:
         sigma_c = torch.empty(1).uniform_(opt.sigma[0], opt.sigma[1]).item()
         taps_c = ops.gaussian_taps(sigma_c)
+    tf = None
+    if _tf_on(opt):
+        tf = np.zeros((5, bs, TF_W), dtype=np.float32)
+        tf[:, :, 2] = 1.0
+        tf[TF_SLOT["T1"]] = draw_tf_params(bs, opt)                                   # :179
+        if with_metrics:
+            tf[TF_SLOT["T2"]] = draw_tf_params(bs, opt)                               # :190
+            tf[TF_SLOT["T3"]] = draw_tf_params(bs, opt)                               # :199
     bd = np.zeros(bs, dtype=np.int64)
     taps_rows = np.zeros((bs, 2), dtype=np.float32)
     sigmas = []
@@ -114,8 +149,11 @@ def make_plan_multilabel(targets_host, opt) -> StepPlan:
         sigmas.append(sg)
         bd[si:ei] = ci
         taps_rows[si:ei] = ops.gaussian_taps(sg)
+    if tf is not None:
+        tf[TF_SLOT["T4"]] = draw_tf_params(bs, opt)                                   # :225
+        tf[TF_SLOT["T5"]] = draw_tf_params(bs, opt)                                   # :236
     return StepPlan(np.arange(bs, dtype=np.int32), num_bd, np.arange(bs), np.arange(0), bd, y.copy(), sigma_c,
-                    sigmas[0], taps_c, (float(taps_rows[0, 0]), float(taps_rows[0, 1])), taps_rows, sigmas)
+                    sigmas[0], taps_c, (float(taps_rows[0, 0]), float(taps_rows[0, 1])), taps_rows, sigmas, tf=tf)
 
 
 class AlternatedStep:
@@ -147,14 +185,14 @@ class AlternatedStep:
         if self.multilabel and not self.netG.cond:
             raise ValueError("the multilabel step needs the conditional generator (cond_classes = num_classes)")
         self.keep = int(H * o.ratio)
+        self.tf_on = _tf_on(o)      # PostTensorTransform active (five fused gather launches + two adjoints per iteration)
         self.lr_C = torch.full((1,), float(o.lr_C), dtype=torch.float32, device=self.device)
         self.lr_G = torch.full((1,), float(o.lr_G), dtype=torch.float32, device=self.device)
         self.grad_hook = grad_hook  # callable(net_name, flat_grad_tensor): data-parallel all-reduce
         self.buf_hook = buf_hook    # callable(flat_running_stats): keeps BatchNorm buffers identical across ranks
         self.launches_per_step = 0  # kernels of this library launched by one iteration (counted on the last eager/capture pass)
-        self._bufs = None
-        self._graph = None
-        self._gstate = {}          # tensors handed from one captured phase to the next
+        self._bufs = None           # buffers of the batch size used last
+        self._bufs_by_B = {}        # batch size -> buffers + captured graphs (train and eval) + ring of plan slots
         self._copy_stream = None   # side stream + staging buffers of prefetch()
         self._stage = {}
         self._stage_free = None
@@ -185,57 +223,102 @@ class AlternatedStep:
             self.lr_G.fill_(float(lr_G))
 
     # ------------------------------------------------------------ per-iteration device parameter block
+    # Layout of the parameter block (one contiguous device buffer, one pinned host image of it per ring slot, ONE
+    # cudaMemcpyAsync per iteration): y | bd_targets | total_y (int64 [B] each) | perm (int32 [B]) | small (float32 [8]:
+    # taps_c, taps_g) | num_bd (int32 [4]) | taps_rows (float32 [B, 2], multilabel only).  Every section starts 16-byte
+    # aligned.  The kernels read the DEVICE copy; the host image of slot s is only rewritten after the copy that last read
+    # it has executed (event per slot) -- the host may run many iterations ahead of the GPU (train() syncs every
+    # --log_every iterations), and a pinned buffer that is rewritten while an earlier cudaMemcpyAsync is still queued
+    # would hand that earlier iteration the labels / permutation / num_bd / blur taps of a later one.
+    PLAN_SLOTS = 4
+
+    @staticmethod
+    def _plan_layout(B, multilabel, tf_on=False):
+        a16 = lambda n: (n + 15) // 16 * 16
+        off, lay = 0, {}
+        for name, nbytes in (("y", 8 * B), ("bd_targets", 8 * B), ("total_y", 8 * B), ("perm", 4 * B), ("small", 32),
+                             ("num_bd", 16), ("taps_rows", 8 * B if multilabel else 0),
+                             ("tf", 5 * B * TF_W * 4 if tf_on else 0)):
+            lay[name] = (off, nbytes)
+            off += a16(nbytes)
+        return lay, max(off, 16)
+
+    @staticmethod
+    def _plan_views(block, lay, B):
+        def v(name, dtype, shape=None):
+            o, n = lay[name]
+            t = block[o:o + n].view(dtype)
+            return t.view(shape) if shape is not None else t
+        return {"y": v("y", torch.int64), "bd_targets": v("bd_targets", torch.int64), "total_y": v("total_y", torch.int64),
+                "perm": v("perm", torch.int32), "small": v("small", torch.float32), "num_bd": v("num_bd", torch.int32),
+                "taps_rows": v("taps_rows", torch.float32, (B, 2)) if lay["taps_rows"][1] else None,
+                "tf": v("tf", torch.float32, (5, B, TF_W)) if lay["tf"][1] else None}
+
     def _ensure_bufs(self, B):
-        if self._bufs is not None and self._bufs["B"] == B:
-            return self._bufs
+        """Buffers (and the captured graphs that reference them) are cached PER BATCH SIZE: the shorter last batch of an
+        epoch, or an eval batch size different from the training one, does not throw the other size's graphs away."""
+        b = self._bufs_by_B.get(B)
+        if b is not None:
+            self._bufs = b
+            return b
         dev = self.device
         o = self.opt
-        b = {"B": B}
+        b = {"B": B, "graph": None, "gstate": {}}
         b["x"] = torch.empty((B, o.input_channel, o.input_height, o.input_width), dtype=torch.float32, device=dev)
         b["x2"] = torch.empty((2 * B, o.input_channel, o.input_height, o.input_width), dtype=torch.float32, device=dev)  # [x ; x_bd]
-        b["y"] = torch.empty(B, dtype=torch.int64, device=dev)
-        b["bd_targets"] = torch.empty(B, dtype=torch.int64, device=dev)
-        b["total_y"] = torch.empty(B, dtype=torch.int64, device=dev)
-        b["perm"] = torch.empty(B, dtype=torch.int32, device=dev)
-        b["num_bd"] = torch.zeros(1, dtype=torch.int32, device=dev)
-        b["taps_c"] = torch.zeros(2, dtype=torch.float32, device=dev)
-        b["taps_g"] = torch.zeros(2, dtype=torch.float32, device=dev)
-        b["taps_rows"] = torch.zeros((B, 2), dtype=torch.float32, device=dev) if self.multilabel else None
-        b["h_taps_rows"] = torch.zeros((B, 2), dtype=torch.float32).pin_memory() if self.multilabel else None
+        lay, nbytes = self._plan_layout(B, self.multilabel, self.tf_on)
+        b["plan_dev"] = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        dv = self._plan_views(b["plan_dev"], lay, B)
+        b["y"], b["bd_targets"], b["total_y"], b["perm"] = dv["y"], dv["bd_targets"], dv["total_y"], dv["perm"]
+        b["taps_c"], b["taps_g"] = dv["small"][0:2], dv["small"][2:4]
+        b["num_bd"] = dv["num_bd"][0:1]
+        b["taps_rows"] = dv["taps_rows"]
+        b["tf"] = dv["tf"]
         b["ones"] = torch.ones(B, dtype=torch.int64, device=dev)
         b["sq_partial"] = torch.empty(B * o.input_channel, dtype=torch.float32, device=dev)
-        b["losses"] = torch.zeros(8, dtype=torch.float32, device=dev)   # loss_c, loss_ce, loss_l2, clean_model_loss
+        b["gl2_partial"] = torch.empty(2 * B * o.input_channel, dtype=torch.float32, device=dev)
+        b["losses"] = torch.zeros(8, dtype=torch.float32, device=dev)   # loss_c, loss_ce, loss_l2, clean_model_loss, CE of the
+        #                                                                 metric forwards [4:7], loss_grad_l2 [7]
         b["counts"] = torch.zeros(16, dtype=torch.int32, device=dev)
-        # pinned staging for the tiny parameter block
-        b["h_i64"] = torch.empty((3, B), dtype=torch.int64).pin_memory()
-        b["h_perm"] = torch.empty(B, dtype=torch.int32).pin_memory()
-        b["h_small"] = torch.empty(8, dtype=torch.float32).pin_memory()
-        b["h_nbd"] = torch.empty(1, dtype=torch.int32).pin_memory()
+        # ring of pinned host images of the parameter block, each guarded by the event of the copy that last read it
+        b["slots"] = []
+        for _ in range(self.PLAN_SLOTS):
+            h = torch.zeros(nbytes, dtype=torch.uint8).pin_memory()
+            b["slots"].append({"h": h, "v": self._plan_views(h, lay, B), "ev": None})
+        b["slot"] = 0
+        self._bufs_by_B[B] = b
         self._bufs = b
-        self._graph = None
         return b
 
+    def _next_slot(self, b):
+        s = b["slots"][b["slot"]]
+        b["slot"] = (b["slot"] + 1) % len(b["slots"])
+        if s["ev"] is not None:
+            s["ev"].synchronize()   # the H2D copy that last read this host image has executed
+        return s
+
     def upload_plan(self, y_host, plan: StepPlan):
-        """async H2D of labels + the per-iteration parameter block (a few KB)."""
+        """one async H2D copy of labels + the per-iteration parameter block (a few KB) from an event-guarded ring slot."""
         B = len(plan.perm)
         b = self._ensure_bufs(B)
-        b["h_i64"][0].copy_(torch.as_tensor(np.asarray(y_host, dtype=np.int64)))
-        b["h_i64"][1].copy_(torch.from_numpy(plan.bd_targets))
-        b["h_i64"][2].copy_(torch.from_numpy(plan.total_targets))
-        b["h_perm"].copy_(torch.from_numpy(plan.perm))
-        b["h_small"][0], b["h_small"][1] = plan.taps_c
-        b["h_small"][2], b["h_small"][3] = plan.taps_g
-        b["h_nbd"][0] = plan.num_bd
-        b["y"].copy_(b["h_i64"][0], non_blocking=True)
-        b["bd_targets"].copy_(b["h_i64"][1], non_blocking=True)
-        b["total_y"].copy_(b["h_i64"][2], non_blocking=True)
-        b["perm"].copy_(b["h_perm"], non_blocking=True)
-        b["taps_c"].copy_(b["h_small"][0:2], non_blocking=True)
-        b["taps_g"].copy_(b["h_small"][2:4], non_blocking=True)
-        b["num_bd"].copy_(b["h_nbd"], non_blocking=True)
+        s = self._next_slot(b)
+        v = s["v"]
+        v["y"].copy_(torch.as_tensor(np.asarray(y_host, dtype=np.int64)))
+        v["bd_targets"].copy_(torch.from_numpy(plan.bd_targets))
+        v["total_y"].copy_(torch.from_numpy(plan.total_targets))
+        v["perm"].copy_(torch.from_numpy(plan.perm))
+        v["small"][0], v["small"][1] = plan.taps_c
+        v["small"][2], v["small"][3] = plan.taps_g
+        v["num_bd"][0] = plan.num_bd
         if self.multilabel:
-            b["h_taps_rows"].copy_(torch.from_numpy(plan.taps_rows))
-            b["taps_rows"].copy_(b["h_taps_rows"], non_blocking=True)
+            v["taps_rows"].copy_(torch.from_numpy(plan.taps_rows))
+        if self.tf_on:
+            if plan.tf is None:
+                raise ValueError("the engine was built with PostTensorTransform on: the plan must carry its parameters")
+            v["tf"].copy_(torch.from_numpy(plan.tf))
+        b["plan_dev"].copy_(s["h"], non_blocking=True)
+        s["ev"] = torch.cuda.Event()
+        s["ev"].record(torch.cuda.current_stream(self.device))
 
     # ------------------------------------------------------------ the step
     # The iteration is three launch phases separated by the data-parallel exchange points (combat_b200.parallel):
@@ -261,11 +344,12 @@ class AlternatedStep:
             noise = ops.plane_op(noise_raw, "lowfreq", keep=self.keep)                      # :190-191 / :224
             total_x = ops.poison_blend_fwd(x, noise, b["perm"], 0, o.noise_rate, None, taps_dev=b["taps_c"],
                                            num_bd_dev=b["num_bd"])                            # :192-195
-        logits_c, ctxC = self.netC.forward(total_x, train=True, save=True)                   # :205
+        total_in = ops.post_transform_fwd(total_x, b["tf"][TF_SLOT["T1"]]) if self.tf_on else total_x   # :196
+        logits_c, ctxC = self.netC.forward(total_in, train=True, save=True)                  # :205
         _, dlog, _ = ops.cross_entropy(logits_c, b["total_y"], 1.0, True, loss_out=losses[0:1], counts_out=counts[0:2])
         self.netC.zero_grad()                                                                # :179
         self.netC.backward(ctxC, dlog, need_wgrad=True, need_dx=False)                       # :211
-        st.update(noise_raw=noise_raw, ctxG=ctxG, noise=noise, total_x=total_x, logits_c=logits_c)
+        st.update(noise_raw=noise_raw, ctxG=ctxG, noise=noise, total_x=total_x, total_in=total_in, logits_c=logits_c)
 
     def _phase_b(self, b, st):
         o = self.opt
@@ -289,13 +373,19 @@ class AlternatedStep:
             x_bd = ops.poison_blend_fwd(x, noise, None, B, o.noise_rate, None, out=x2[B:], sq_partial=b["sq_partial"],
                                         taps_dev=b["taps_g"], taps_rows=b["taps_rows"])      # :225-226
             ops.sum_scale(b["sq_partial"], 1.0 / numel, out=losses[2:3])                     # :234
-            lg, ctx2 = self.netC.forward(x2, train=False, save=True)
+            # PostTensorTransform: netC sees [T3(x) ; T4(x_bd)] (:227-228), clean_model [T2(x) ; T5(x_bd)] (:214,:250) -- one
+            # gather launch per network over the 2B rows with per-row parameters
+            tfC = b["tf"][TF_SLOT["T3"]:TF_SLOT["T4"] + 1].view(2 * B, TF_W) if self.tf_on else None
+            tfK = b["tf"][TF_SLOT["T2"]:TF_SLOT["T5"] + 1].view(2 * B, TF_W) if self.tf_on else None
+            x2c = ops.post_transform_fwd(x2, tfC) if self.tf_on else x2
+            lg, ctx2 = self.netC.forward(x2c, train=False, save=True)
             pred_clean, pred_bd = lg[:B], lg[B:]
             ops.cross_entropy(pred_clean, y, 1.0, False, loss_out=losses[5:6], counts_out=counts[4:6])
             _, dl1, _ = ops.cross_entropy(pred_bd, b["bd_targets"], 1.0, True, loss_out=losses[1:2], counts_out=counts[6:8])
             g1 = self.netC.backward(self.netC.slice_ctx(ctx2, B, 2 * B), dl1, need_wgrad=False, need_dx=True)
             del ctx2
-            lgc, ctx2 = self.clean.forward(x2, train=False, save=True)
+            x2k = ops.post_transform_fwd(x2, tfK) if self.tf_on else x2
+            lgc, ctx2 = self.clean.forward(x2k, train=False, save=True)
             clean_preds, cm_preds = lgc[:B], lgc[B:]
             ops.cross_entropy(clean_preds, y, 1.0, False, loss_out=losses[4:5], counts_out=counts[2:4])
             _, dl2, _ = ops.cross_entropy(cm_preds, y, o.clean_model_weight, True, targets2=b["bd_targets"],
@@ -304,26 +394,33 @@ class AlternatedStep:
             del ctx2
             st.update(clean_preds=clean_preds, pred_clean=pred_clean)
         else:
+            tfp = (lambda name, t: ops.post_transform_fwd(t, b["tf"][TF_SLOT[name]])) if self.tf_on else (lambda name, t: t)
             if self.with_metrics:
-                clean_preds, _ = self.clean.forward(x, train=False, save=False)              # :214
+                clean_preds, _ = self.clean.forward(tfp("T2", x), train=False, save=False)   # :214
                 ops.cross_entropy(clean_preds, y, 1.0, False, loss_out=losses[4:5], counts_out=counts[2:4])
                 st["clean_preds"] = clean_preds
             x_bd = ops.poison_blend_fwd(x, noise, None, B, o.noise_rate, None, sq_partial=b["sq_partial"],
                                         taps_dev=b["taps_g"], taps_rows=b["taps_rows"])      # :225-226
             ops.sum_scale(b["sq_partial"], 1.0 / numel, out=losses[2:3])                     # :234
             if self.with_metrics:
-                pred_clean, _ = self.netC.forward(x, train=False, save=False)                # :227
+                pred_clean, _ = self.netC.forward(tfp("T3", x), train=False, save=False)     # :227
                 ops.cross_entropy(pred_clean, y, 1.0, False, loss_out=losses[5:6], counts_out=counts[4:6])
                 st["pred_clean"] = pred_clean
-            pred_bd, ctxB = self.netC.forward(x_bd, train=False, save=True)                  # :228
+            pred_bd, ctxB = self.netC.forward(tfp("T4", x_bd), train=False, save=True)       # :228
             _, dl1, _ = ops.cross_entropy(pred_bd, b["bd_targets"], 1.0, True, loss_out=losses[1:2], counts_out=counts[6:8])
             g1 = self.netC.backward(ctxB, dl1, need_wgrad=False, need_dx=True)
             del ctxB
-            cm_preds, ctxK = self.clean.forward(x_bd, train=False, save=True)                # :250
+            cm_preds, ctxK = self.clean.forward(tfp("T5", x_bd), train=False, save=True)     # :250
             _, dl2, _ = ops.cross_entropy(cm_preds, y, o.clean_model_weight, True, targets2=b["bd_targets"],
                                           loss_out=losses[3:4], counts_out=counts[8:10])      # :251,266-267
             g2 = self.clean.backward(ctxK, dl2, need_wgrad=False, need_dx=True)
             del ctxK
+        if self.with_metrics and not self.multilabel:
+            ops.grad_l2(x, x_bd, losses[7:8], b["gl2_partial"])                              # :235-243 (logged only)
+        if self.tf_on:  # back through T4 / T5 to x_bd: both adjoints accumulate into one buffer
+            gsum = ops.post_transform_bwd(g1, b["tf"][TF_SLOT["T4"]])
+            ops.post_transform_bwd(g2, b["tf"][TF_SLOT["T5"]], out=gsum, accumulate=True)
+            g1, g2 = gsum, None
         dnoise = ops.poison_blend_bwd(x, noise, x_bd, g1, g2, 2.0 * o.L2_weight / numel, o.noise_rate, None,
                                       taps_dev=b["taps_g"], taps_rows=b["taps_rows"])
         dnoise_raw = ops.plane_op(dnoise, "lowfreq", keep=self.keep)                          # P is symmetric
@@ -404,43 +501,46 @@ class AlternatedStep:
         """One alternated iteration.  x_dev: float32 NCHW tensor already on the device (or a pinned host tensor,
         which is copied asynchronously); y_host: host labels.  Returns {'losses': dev[8], 'counts': dev[16]}."""
         if plan is None:
-            plan = make_plan_multilabel(y_host, self.opt) if self.multilabel else make_plan(y_host, self.opt)
+            mk = make_plan_multilabel if self.multilabel else make_plan
+            plan = mk(y_host, self.opt, self.with_metrics)
         B = len(plan.perm)
         b = self._ensure_bufs(B)
         self._take_input(x_dev, b["x"])
         self.upload_plan(y_host, plan)
         dbg = None
         if use_graph and not keep_debug:
-            if self._graph is None:
+            if b["graph"] is None:
                 # warm-up launch outside capture (allocator pools, function attributes, first-step SGD), then capture
                 self._launch(b)
                 torch.cuda.current_stream().synchronize()
                 pool = torch.cuda.graph_pool_handle()
-                self._gstate = {}  # tensors handed from one captured phase to the next stay referenced here
+                b["gstate"] = {}  # tensors handed from one captured phase to the next stay referenced here
                 phases = [self._phase_a, self._phase_b, self._phase_c]
                 if self._parallel:
                     graphs = []
                     for ph in phases:
                         g = torch.cuda.CUDAGraph()
                         with torch.cuda.graph(g, pool=pool):
-                            ph(b, self._gstate)
+                            ph(b, b["gstate"])
                         graphs.append(g)
                 else:
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g, pool=pool):
                         for ph in phases:
-                            ph(b, self._gstate)
+                            ph(b, b["gstate"])
                     graphs = [g]
-                self._graph = graphs
+                b["graph"] = graphs
             else:
-                if len(self._graph) == 1:
-                    self._graph[0].replay()
+                graphs = b["graph"]
+                if len(graphs) == 1:
+                    graphs[0].replay()
                 else:
-                    self._graph[0].replay()
+                    graphs[0].replay()
                     self._exchange_c()
-                    self._graph[1].replay()
+                    graphs[1].replay()
                     self._exchange_g()
-                    self._graph[2].replay()
+                    graphs[2].replay()
+                self.netC.bump_batches_tracked()   # the replayed C-step forward is one train-mode pass of every BatchNorm
         else:
             dbg = self._launch(b, keep_debug)
         out = {"losses": b["losses"], "counts": b["counts"], "plan": plan}
@@ -466,20 +566,29 @@ class AlternatedStep:
         eb = b.setdefault("eval", {})
         if not eb:
             dev = self.device
-            eb["h"] = torch.empty((4, B), dtype=torch.int64).pin_memory()
-            eb["t"] = torch.empty((4, B), dtype=torch.int64, device=dev)   # y | bd masked | ones masked | y masked
+            nbytes = 4 * B * 8 + 16
+            eb["dev"] = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+            eb["t"] = eb["dev"][:4 * B * 8].view(torch.int64).view(4, B)   # y | bd masked | ones masked | y masked
+            eb["taps"] = eb["dev"][4 * B * 8:].view(torch.float32)[0:2]
             eb["counts"] = torch.zeros(16, dtype=torch.int32, device=dev)
             eb["graph"] = None
-        h = eb["h"]
+            eb["slots"] = []   # event-guarded ring of pinned host images, as for the training plan (see _ensure_bufs)
+            for _ in range(self.PLAN_SLOTS):
+                hb = torch.zeros(nbytes, dtype=torch.uint8).pin_memory()
+                eb["slots"].append({"h": hb, "t": hb[:4 * B * 8].view(torch.int64).view(4, B),
+                                    "taps": hb[4 * B * 8:].view(torch.float32), "ev": None})
+            eb["slot"] = 0
+        s = self._next_slot(eb)
+        h = s["t"]
         h[0].copy_(torch.from_numpy(y))
         h[1].copy_(torch.from_numpy(np.where(ntrg, bd, -1)))
         h[2].copy_(torch.from_numpy(np.where(ntrg, 1, -1).astype(np.int64)))
         h[3].copy_(torch.from_numpy(np.where(ntrg, y, -1)))
-        eb["t"].copy_(h, non_blocking=True)
+        s["taps"][0], s["taps"][1] = ops.gaussian_taps(sigma)
+        eb["dev"].copy_(s["h"], non_blocking=True)
+        s["ev"] = torch.cuda.Event()
+        s["ev"].record(torch.cuda.current_stream(self.device))
         b["x"].copy_(x_dev, non_blocking=True)
-        k0, k1 = ops.gaussian_taps(sigma)
-        b["h_small"][2], b["h_small"][3] = k0, k1
-        b["taps_g"].copy_(b["h_small"][2:4], non_blocking=True)
 
         def launch():
             x, t, counts = b["x"], eb["t"], eb["counts"]
@@ -487,7 +596,7 @@ class AlternatedStep:
             ops.cross_entropy(preds_clean, t[0], 1.0, False, counts_out=counts[0:2])
             noise_raw, _ = self.netG.forward(x, None, save=False)                                    # :369
             noise = ops.plane_op(noise_raw, "lowfreq", keep=self.keep)                               # :370
-            x_bd = ops.poison_blend_fwd(x, noise, None, B, o.noise_rate, None, taps_dev=b["taps_g"])  # :372-373
+            x_bd = ops.poison_blend_fwd(x, noise, None, B, o.noise_rate, None, taps_dev=eb["taps"])  # :372-373
             preds_bd, _ = self.netC.forward(x_bd, train=False, save=False)                          # :375
             ops.cross_entropy(preds_bd, t[1], 1.0, False, counts_out=counts[2:4])
             if self.netF is not None:
@@ -542,6 +651,7 @@ class AlternatedStep:
     @staticmethod
     def _to_dict(l, c) -> dict:
         return dict(loss_c=float(l[0]), loss_ce=float(l[1]), loss_l2=float(l[2]), clean_model_loss=float(l[3]),
+                    loss_grad_l2=float(l[7]),
                     n_total_correct=int(c[0]), n_clean_model_correct=int(c[2]), n_clean_correct=int(c[4]),
                     n_bd_correct=int(c[6]), n_clean_model_bd_ba=int(c[8]), n_clean_model_bd_asr=int(c[9]),
                     n_F_correct=int(c[10]))

@@ -495,6 +495,12 @@ class Classifier(NetBase):
             sd[bn.name + ".num_batches_tracked"] = torch.tensor(self.num_batches_tracked[bn.name])
         return sd
 
+    def bump_batches_tracked(self, n=1):
+        """One train-mode forward of every BatchNorm was executed by a CUDA-graph replay (the Python of _bn_fwd did not
+        run): keep the reference's num_batches_tracked buffers in step with the iterations actually executed."""
+        for k in self.num_batches_tracked:
+            self.num_batches_tracked[k] += n
+
     # ---- BN helpers
     def _bn_fwd(self, bn, x, train, relu, residual=None, stats_nblk=0):
         """stats_nblk > 0: the conv that produced x already reduced its per-CTA sums (fused epilogue statistics)."""
@@ -508,7 +514,8 @@ class Classifier(NetBase):
             else:
                 scale, shift, mean, invstd = ops.bn_train_prepare(x, R, Cc, g, b, self.rm(bn), self.rv(bn), self.momentum,
                                                                   self.eps)
-            self.num_batches_tracked[bn.name] += 1
+            if not torch.cuda.is_current_stream_capturing():  # a capture pass executes nothing; replays are counted by
+                self.num_batches_tracked[bn.name] += 1        # bump_batches_tracked() (one call per replayed train forward)
             st = (scale, mean, invstd)
         else:
             scale, shift = ops.bn_eval_prepare(Cc, g, b, self.rm(bn), self.rv(bn), self.eps)

@@ -205,6 +205,15 @@ def sum_scale(partial, scale, out=None):
     return out
 
 
+def grad_l2(x, x_bd, out, partial=None):
+    """the logged 'Grad L2 Loss' of train_generator.py:235-243 -> out[0]"""
+    B, Cc, H, W = x.shape
+    if partial is None:
+        partial = torch.empty(2 * B * Cc, dtype=torch.float32, device=x.device)
+    check(lib.combat_grad_l2(_p(x), _p(x_bd), _p(partial), _p(out), B, Cc, H, W, _s()), "grad_l2")
+    return out
+
+
 def sgd_nesterov(p, g, buf, lr_dev, momentum, wd, first):
     check(lib.combat_sgd_nesterov(_p(p), _p(g), _p(buf), p.numel(), _p(lr_dev), momentum, wd, int(first), _s()), "sgd_nesterov")
 
@@ -505,6 +514,32 @@ def mask_scale(x, keep, scale):
 
 def adadelta(p, g, square_avg, acc_delta, lr_dev, rho=0.9, eps=1e-6, wd=1e-4):
     check(lib.combat_adadelta(_p(p), _p(g), _p(square_avg), _p(acc_delta), p.numel(), _p(lr_dev), rho, eps, wd, _s()), "adadelta")
+
+
+def post_transform_fwd(x, params, out=None):
+    """PostTensorTransform of an NCHW float32 batch with per-row parameters (device float32 [rows, 8], see csrc/augment.cu)."""
+    x = _contig(x)
+    rows, Cc, H, W = x.shape
+    if params.dtype != torch.float32 or params.numel() != rows * 8 or not params.is_contiguous():
+        raise ValueError("post_transform: params must be a contiguous float32 [rows, 8] tensor")
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib.combat_post_transform_fwd(_p(x), _p(out), _p(params), rows, Cc, H, W, _s()), "post_transform_fwd")
+    return out
+
+
+def post_transform_bwd(dout, params, out=None, accumulate=False):
+    """adjoint of post_transform_fwd: gradient w.r.t. the untransformed batch (accumulate=True adds into `out`)."""
+    dout = _contig(dout)
+    rows, Cc, H, W = dout.shape
+    if params.dtype != torch.float32 or params.numel() != rows * 8 or not params.is_contiguous():
+        raise ValueError("post_transform: params must be a contiguous float32 [rows, 8] tensor")
+    if out is None:
+        if accumulate:
+            raise ValueError("accumulate=True needs an output buffer")
+        out = torch.empty_like(dout)
+    check(lib.combat_post_transform_bwd(_p(dout), _p(out), _p(params), rows, Cc, H, W, int(accumulate), _s()), "post_transform_bwd")
+    return out
 
 
 def nchw_to_nhwc(x, dtype):

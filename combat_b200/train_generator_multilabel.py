@@ -13,7 +13,7 @@ import torch
 
 from .engine import AlternatedStep, make_plan_multilabel
 from .modules import CUnetGeneratorv1, FrequencyModel, PreActResNet18, ResNet18
-from .train_generator import _bind_momentum, _dtype, create_targets_bd, low_freq  # noqa: F401
+from .train_generator import _adopt_momentum, _bind_momentum, _dtype, _engine_for, create_targets_bd, low_freq  # noqa: F401
 from .utils.dataloader import PostTensorTransform
 
 
@@ -42,21 +42,14 @@ def get_model(opt):
     return netC, optimizerC, schedulerC, netG, optimizerG, schedulerG, netF, clean_model
 
 
-_ENGINES: dict = {}
-
-
 def train(netC, optimizerC, schedulerC, netG, optimizerG, schedulerG, netF, clean_model, train_dl, mask, pattern, tf_writer,
           epoch, opt):
     """reference :142-318 (one epoch of alternated multilabel C/G steps), every iteration one captured-graph replay."""
     print(" Train:")
     netC.train()
-    PostTensorTransform(opt)  # raises for the options that are not built
-    key = (id(netC), id(clean_model), id(netG), id(netF))
-    eng = _ENGINES.get(key)
-    if eng is None:
-        eng = AlternatedStep(opt, device=netC.net.device, with_metrics=True, multilabel=True,
-                             nets=(netC.net, clean_model.net, netG.net, netF.net if netF is not None else None))
-        _ENGINES[key] = eng
+    eng = _engine_for(netC, clean_model, netG, netF, opt, multilabel=True)
+    _adopt_momentum(optimizerC, netC)
+    _adopt_momentum(optimizerG, netG)
     eng.set_lr(optimizerC.param_groups[0]["lr"], optimizerG.param_groups[0]["lr"])
     use_graph = not getattr(opt, "no_graph", False)
     log_every = max(1, int(getattr(opt, "log_every", 50)))
@@ -66,7 +59,7 @@ def train(netC, optimizerC, schedulerC, netG, optimizerG, schedulerG, netF, clea
     total_sample, n_batches, acc = 0, len(train_dl), {}
     for batch_idx, (inputs, targets) in enumerate(train_dl):
         y_host = targets.cpu().numpy() if torch.is_tensor(targets) else np.asarray(targets)
-        plan = make_plan_multilabel(y_host, opt)
+        plan = make_plan_multilabel(y_host, opt, eng.with_metrics)
         if not inputs.is_cuda:
             inputs = inputs.pin_memory()
         out = eng.step(inputs, y_host, plan, use_graph=use_graph)

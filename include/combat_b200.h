@@ -259,6 +259,24 @@ int combat_maxpool2_bwd(const void* dy, const void* x, void* dx, int dtype, int 
 int combat_mask_scale(const void* x, const unsigned char* keep, void* y, int dtype, long long n, float scale, void* stream);
 int combat_adadelta(float* p, const float* g, float* square_avg, float* acc_delta, long long n, const float* lr_dev, float rho,
                     float eps, float wd, void* stream);
+/* "Grad L2 Loss" of train_generator.py:235-243 (a logged scalar, not part of the optimised loss): the sum of the two MSEs
+ * between the vertical / horizontal difference images of F.pad(inputs, (1,1,2,1)) and F.pad(inputs_bd, (1,1,2,1)).
+ * partial: rows*C*2 floats of scratch; out: 1 float. */
+int combat_grad_l2(const float* x, const float* x_bd, float* partial, float* out, int rows, int C, int H, int W, void* stream);
+
+/* ---------------------------------------------------------------- PostTensorTransform (csrc/augment.cu)
+ * utils/dataloader.py:45-60: kornia RandomCrop(padding) -> RandomRotation -> RandomHorizontalFlip, as one gather over NCHW
+ * float32 images and its adjoint (the G-step differentiates through transforms(inputs_bd), train_generator.py:228,250).
+ * params: rows x 8 floats per image, drawn on the host (combat_b200/utils/dataloader.py):
+ *   [0] xs - pad, [1] ys - pad (integer-valued crop shifts; 0 when the whole-batch crop gate :17 is off),
+ *   [2] cos(angle), [3] sin(angle), [4] rotation on (0/1), [5] horizontal flip (0/1), [6..7] unused.
+ * out(n,c,y,x) = bilinear sample (zeros outside, align_corners=True pixel mapping) of the cropped image at the inverse
+ * rotation of (flip ? W-1-x : x, y) about ((W-1)/2, (H-1)/2).  _bwd: din (+)= adjoint(dout); din is zero-filled first
+ * unless accumulate != 0.
+ */
+int combat_post_transform_fwd(const float* in, float* out, const float* params, int rows, int C, int H, int W, void* stream);
+int combat_post_transform_bwd(const float* dout, float* din, const float* params, int rows, int C, int H, int W,
+                              int accumulate, void* stream);
 /* layout/dtype helpers */
 int combat_nchw_to_nhwc(const float* x, void* y, int dtype, int N, int C, int H, int W, void* stream);
 int combat_nhwc_to_nchw(const void* x, int dtype, float* y, int N, int C, int H, int W, void* stream);

@@ -327,7 +327,93 @@ def sgd_nesterov_step(params: dict, grads: dict, bufs: dict, lr: float, momentum
 
 
 # --------------------------------------------------------------------------
-# The alternated step (train_generator.py:170-255), --post_transform_option no_use
+# PostTensorTransform (utils/dataloader.py:11-22,45-60) over kornia 0.6.6 (requirements.txt:12)
+#
+# kornia is a third-party dependency that is absent from /root/reference and from this image, so its published algorithm is
+# restated with the torch ops kornia itself dispatches to:
+#   A.RandomCrop(size, padding=p)   -> F.pad(x, [p,p,p,p], "constant", 0) then the window x[.., ys:ys+H, xs:xs+W] per sample,
+#                                      (xs, ys) = floor(U[0, 2p+1))                         (kornia random_crop_generator)
+#   A.RandomRotation(d)             -> angle ~ U(-d, d); M = get_rotation_matrix2d(((W-1)/2,(H-1)/2), angle, 1)
+#                                      = [[a, b, (1-a)cx - b cy], [-b, a, b cx + (1-a) cy]], a = cos, b = sin;
+#                                      warp_affine(x, M, (H,W), "bilinear", "zeros", align_corners=True), i.e.
+#                                      F.grid_sample(x, F.affine_grid(normalised(M)^-1))     (kornia warp_affine)
+#   A.RandomHorizontalFlip(p=0.5)   -> per-sample Bernoulli(p); flipped rows are x.flip(-1)
+#   ProbTransform(f, p)             -> one random.random() < p per call gates the whole batch (dataloader.py:17)
+# PARITY UNPINNED for the kornia RNG stream: the reference holds no test or vector for it and the package cannot be run here;
+# given the parameters, pixels and gradients follow the algorithm above.
+# --------------------------------------------------------------------------
+
+
+def draw_post_transform(rows: int, opt):
+    """The random decisions of ONE PostTensorTransform call, in the module order random_crop, random_rotation,
+    random_horizontal_flip (utils/dataloader.py:48-55,58-59).  Gates: python `random`; per-sample parameters: torch CPU
+    generator, one torch.rand(rows) per parameter (xs, ys, angle, flip).  Returns a dict of per-sample tensors."""
+    import random as _random
+    option = getattr(opt, "post_transform_option", "no_use")
+    pad = int(getattr(opt, "random_crop", 5))
+    out = {"xs": torch.full((rows,), pad, dtype=torch.long), "ys": torch.full((rows,), pad, dtype=torch.long), "crop": False,
+           "angle": torch.zeros(rows), "rot": False, "flip": torch.zeros(rows, dtype=torch.bool), "pad": pad}
+    if option == "no_use":
+        return out
+    if option != "use_modified":
+        if _random.random() < 0.8:
+            span = float(2 * pad + 1)
+            out["xs"] = torch.floor(torch.rand(rows) * span).long()
+            out["ys"] = torch.floor(torch.rand(rows) * span).long()
+            out["crop"] = True
+    if _random.random() < 0.5:
+        deg = float(getattr(opt, "random_rotation", 10))
+        out["angle"] = torch.rand(rows) * (2.0 * deg) - deg
+        out["rot"] = True
+    if getattr(opt, "dataset", "cifar10") == "cifar10":
+        out["flip"] = torch.rand(rows) < 0.5
+    return out
+
+
+def _normal_transform_pixel(H: int, W: int) -> torch.Tensor:
+    """kornia normal_transform_pixel: pixel coordinates -> [-1, 1] with the (size-1) convention (align_corners=True)."""
+    return torch.tensor([[2.0 / (W - 1), 0.0, -1.0], [0.0, 2.0 / (H - 1), -1.0], [0.0, 0.0, 1.0]])
+
+
+def apply_post_transform(x: torch.Tensor, prm: dict) -> torch.Tensor:
+    """x: [rows, C, H, W] float32 (differentiable) -> the transformed batch."""
+    rows, C, H, W = x.shape
+    pad = prm["pad"]
+    if prm["crop"]:
+        xp = F.pad(x, [pad, pad, pad, pad], mode="constant", value=0.0)
+        x = torch.stack([xp[i, :, int(prm["ys"][i]):int(prm["ys"][i]) + H, int(prm["xs"][i]):int(prm["xs"][i]) + W]
+                         for i in range(rows)], 0) if rows else x
+    if prm["rot"] and rows:
+        rad = prm["angle"].to(torch.float32) * (math.pi / 180.0)
+        a, b = torch.cos(rad), torch.sin(rad)
+        cx, cy = (W - 1) / 2.0, (H - 1) / 2.0
+        M = torch.zeros(rows, 3, 3)
+        M[:, 0, 0], M[:, 0, 1], M[:, 0, 2] = a, b, (1 - a) * cx - b * cy
+        M[:, 1, 0], M[:, 1, 1], M[:, 1, 2] = -b, a, b * cx + (1 - a) * cy
+        M[:, 2, 2] = 1.0
+        Nrm = _normal_transform_pixel(H, W)
+        dst_norm_trans_src_norm = Nrm @ M @ torch.inverse(Nrm)          # kornia normalize_homography
+        src_norm_trans_dst_norm = torch.inverse(dst_norm_trans_src_norm)
+        grid = F.affine_grid(src_norm_trans_dst_norm[:, :2, :], [rows, C, H, W], align_corners=True)
+        x = F.grid_sample(x, grid, mode="bilinear", padding_mode="zeros", align_corners=True)
+    if bool(prm["flip"].any()):
+        x = torch.where(prm["flip"].view(-1, 1, 1, 1), x.flip(-1), x)
+    return x
+
+
+def post_transform(x: torch.Tensor, opt, log=None) -> torch.Tensor:
+    """transforms(x) of the training loops (train_generator.py:196,214,227,228,250).  `log`: list collecting the drawn
+    parameters of every call (so that a test can hand the SAME decisions to the CUDA path)."""
+    if getattr(opt, "post_transform_option", "no_use") == "no_use":
+        return x
+    prm = draw_post_transform(x.shape[0], opt)
+    if log is not None:
+        log.append(prm)
+    return apply_post_transform(x, prm)
+
+
+# --------------------------------------------------------------------------
+# The alternated step (train_generator.py:170-255)
 # --------------------------------------------------------------------------
 
 
@@ -337,6 +423,7 @@ def default_opt(**kw):
         input_height=32, input_width=32, input_channel=3, num_classes=10, attack_mode="all2one",
         noise_rate=0.08, target_label=0, pc=0.5, ratio=0.65, kernel_size=3, sigma=(0.1, 1.0),
         L2_weight=0.02, clean_model_weight=0.8, lr_C=1e-2, lr_G=1e-2, classifier="preact_resnet18",
+        post_transform_option="no_use", random_crop=5, random_rotation=10, dataset="cifar10",
     )
     for k, v in kw.items():
         setattr(o, k, v)
@@ -354,7 +441,8 @@ def make_bd(netG_p, x, opt, sigma, y=None):
 
 def alternated_step(state: dict, x: torch.Tensor, y: torch.Tensor, opt, with_metrics: bool = True, grad_hook=None,
                     buf_hook=None) -> dict:
-    """One iteration of train() (train_generator.py:170-255) with identity PostTensorTransform.
+    """One iteration of train() (train_generator.py:170-255); PostTensorTransform per opt.post_transform_option (identity for
+    "no_use", the default here; the five calls :196,:214,:227,:228,:250 draw their own parameters, logged in out["tf"]).
 
     `state` holds: netC_p/netC_b, clean_p/clean_b, netG_p (dicts of tensors, updated IN PLACE),
     netF_p/netF_b (optional), momC/momG (momentum buffer dicts, {} before the first step).
@@ -385,6 +473,8 @@ def alternated_step(state: dict, x: torch.Tensor, y: torch.Tensor, opt, with_met
     out["sigma_c"] = sigma_c
     total_x = torch.cat([x_bd_c, x[trg_ind[num_bd:]], x[ntrg_ind]], dim=0)  # :195
     total_y = torch.cat([bd_targets[trg_ind[:num_bd]], y[trg_ind[num_bd:]], y[ntrg_ind]], dim=0)  # :197-204
+    out["tf"] = tf_log = []
+    total_x = post_transform(total_x, opt, tf_log)  # :196
     logits_c = fwdC(netC_p, netC_b, total_x, True)  # netC.train()
     loss_c = F.cross_entropy(logits_c, total_y)
     loss_c.backward()
@@ -401,7 +491,7 @@ def alternated_step(state: dict, x: torch.Tensor, y: torch.Tensor, opt, with_met
         if buf_hook is not None:
             buf_hook(netC_b)
         if with_metrics:
-            out["clean_preds"] = fwdC(clean_p, clean_b, x, False)  # :214
+            out["clean_preds"] = fwdC(clean_p, clean_b, post_transform(x, opt, tf_log), False)  # :214
 
     # ---------------- G-step (:217-255) ----------------
     for t in netG_p.values():
@@ -412,11 +502,15 @@ def alternated_step(state: dict, x: torch.Tensor, y: torch.Tensor, opt, with_met
     x_bd, noise, noise_raw = make_bd(netG_p, x, opt, sigma_g)
     with torch.no_grad():
         if with_metrics:
-            out["pred_clean"] = fwdC(netC_p, netC_b, x, False)  # :227
-    pred_bd = fwdC(netC_p, netC_b, x_bd, False)  # :228 netC.eval(), weights AFTER the C update
+            out["pred_clean"] = fwdC(netC_p, netC_b, post_transform(x, opt, tf_log), False)  # :227
+    pred_bd = fwdC(netC_p, netC_b, post_transform(x_bd, opt, tf_log), False)  # :228 netC.eval(), weights AFTER the C update
     loss_ce = F.cross_entropy(pred_bd, bd_targets)  # :231
     loss_l2 = F.mse_loss(x_bd, x)  # :234
-    clean_model_preds = fwdC(clean_p, clean_b, x_bd, False)  # :250
+    with torch.no_grad():  # :235-243, logged only
+        xe, be = F.pad(x, (1, 1, 2, 1)), F.pad(x_bd.detach(), (1, 1, 2, 1))
+        out["loss_grad_l2"] = float(F.mse_loss(xe[:, :, 1:] - xe[:, :, :-1], be[:, :, 1:] - be[:, :, :-1])
+                                    + F.mse_loss(xe[:, :, :, 1:] - xe[:, :, :, :-1], be[:, :, :, 1:] - be[:, :, :, :-1]))
+    clean_model_preds = fwdC(clean_p, clean_b, post_transform(x_bd, opt, tf_log), False)  # :250
     clean_model_loss = F.cross_entropy(clean_model_preds, y)  # :251
     loss = loss_ce + opt.L2_weight * loss_l2 + opt.clean_model_weight * clean_model_loss  # :253
     loss.backward()
@@ -530,6 +624,8 @@ def alternated_step_multilabel(state: dict, x: torch.Tensor, y: torch.Tensor, op
             sigma_c, x_bd_c = None, x[:0]
     out["sigma_c"] = sigma_c
     total_x = torch.cat([x_bd_c, x[num_bd:]], dim=0)  # :178
+    out["tf"] = tf_log = []
+    total_x = post_transform(total_x, opt, tf_log)  # :179
     logits_c = fwdC(netC_p, netC_b, total_x, True)
     loss_c = F.cross_entropy(logits_c, y)  # :180-183, labels unchanged
     loss_c.backward()
@@ -540,14 +636,14 @@ def alternated_step_multilabel(state: dict, x: torch.Tensor, y: torch.Tensor, op
             t.requires_grad_(False)
         sgd_nesterov_step(netC_p, gradsC, state["momC"], opt.lr_C)
         if with_metrics:
-            out["clean_preds"] = fwdC(clean_p, clean_b, x, False)  # :191
+            out["clean_preds"] = fwdC(clean_p, clean_b, post_transform(x, opt, tf_log), False)  # :190
     # ---------------- G-step (:193-232)
     for t in netG_p.values():
         t.requires_grad_(True)
         t.grad = None
     with torch.no_grad():
         if with_metrics:
-            out["pred_clean"] = fwdC(netC_p, netC_b, x, False)  # :199
+            out["pred_clean"] = fwdC(netC_p, netC_b, post_transform(x, opt, tf_log), False)  # :199
     parts, bd_t, sigmas = [], [], []
     for ci, si, ei in multilabel_chunks(bs, opt.num_classes):
         tmp = y[si:ei] * 0 + ci
@@ -559,10 +655,10 @@ def alternated_step_multilabel(state: dict, x: torch.Tensor, y: torch.Tensor, op
     x_bd = torch.cat(parts, 0)
     bd_targets = torch.cat(bd_t, 0)
     out["sigmas_g"] = sigmas
-    pred_bd = fwdC(netC_p, netC_b, x_bd, False)  # :224
+    pred_bd = fwdC(netC_p, netC_b, post_transform(x_bd, opt, tf_log), False)  # :225
     loss_ce = F.cross_entropy(pred_bd, bd_targets)
     loss_l2 = F.mse_loss(x_bd, x)
-    clean_model_preds = fwdC(clean_p, clean_b, x_bd, False)  # :235
+    clean_model_preds = fwdC(clean_p, clean_b, post_transform(x_bd, opt, tf_log), False)  # :236
     clean_model_loss = F.cross_entropy(clean_model_preds, y)
     loss = loss_ce + opt.L2_weight * loss_l2 + opt.clean_model_weight * clean_model_loss  # :239
     loss.backward()

@@ -52,7 +52,7 @@ def test_cli_flags_match_reference():
         d = list(d) if isinstance(d, (list, tuple)) else d
         assert d == spec["default"], (dest, d, spec["default"])
     extra = set(mine) - set(g)
-    assert extra == {"dtype", "no_graph", "log_every"}, extra
+    assert extra == {"dtype", "no_graph", "log_every", "synthetic_data"}, extra
     opt = p.parse_args(["--pc", "0.3", "--noise_rate", "0.1", "--post_transform_option", "no_use"])
     assert opt.pc == 0.3 and opt.noise_rate == 0.1
 

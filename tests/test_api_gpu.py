@@ -117,3 +117,73 @@ def test_multilabel_train_api_runs_with_graph_replay():
     tm.train(netC, optC, schC, netG, optG, schG, netF, clean, data, None, None, w, 1, opt)
     torch.cuda.synchronize()
     assert len(w.scalars) == 1 and all(np.isfinite(v) for v in w.scalars[0][1].values())
+
+
+def test_resume_keeps_the_nesterov_momentum():
+    """--continue_training (train_generator.py:529-552): netC / netG / both optimisers are restored from a checkpoint dict and
+    training continues.  The fused SGD reads its momentum from the flat store, so the loaded `momentum_buffer`s have to be
+    adopted (they were silently reset).  save -> load into fresh objects -> one more epoch must equal the
+    uninterrupted run."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    import copy
+    from combat_b200 import train_generator as tg
+    opt = _opt(["--dtype", "fp32", "--no_graph", "--log_every", "100"])
+    g = torch.Generator().manual_seed(4)
+    data = [(torch.rand(24, 3, 32, 32, generator=g) * 2 - 1, torch.randint(0, 10, (24,), generator=g)) for _ in range(3)]
+
+    def seed(s):
+        torch.manual_seed(s); np.random.seed(s); random.seed(s)
+
+    seed(0)
+    m = tg.get_model(opt)
+    netC, optC, schC, netG, optG, schG, netF, clean = m
+    seed(1)
+    tg.train(netC, optC, schC, netG, optG, schG, netF, clean, data[:2], _Writer(), 1, opt)
+    ckpt = copy.deepcopy({"netC": netC.state_dict(), "optimizerC": optC.state_dict(), "schedulerC": schC.state_dict(),
+                          "netG": netG.state_dict(), "optimizerG": optG.state_dict(), "schedulerG": schG.state_dict(),
+                          "clean_model": clean.state_dict(), "netF": netF.state_dict()})
+    assert float(ckpt["optimizerC"]["state"][0]["momentum_buffer"].abs().sum()) > 0
+    seed(2)
+    tg.train(netC, optC, schC, netG, optG, schG, netF, clean, data[2:], _Writer(), 2, opt)
+    want_C, want_G = netC.net.store.flat.clone(), netG.net.store.flat.clone()
+    want_mC = netC.net.store.mom.clone()
+
+    seed(5)   # different init: everything must come from the checkpoint
+    netC2, optC2, schC2, netG2, optG2, schG2, netF2, clean2 = tg.get_model(opt)
+    netC2.load_state_dict(ckpt["netC"]); netG2.load_state_dict(ckpt["netG"]); clean2.load_state_dict(ckpt["clean_model"])
+    netF2.load_state_dict(ckpt["netF"])
+    optC2.load_state_dict(ckpt["optimizerC"]); optG2.load_state_dict(ckpt["optimizerG"])
+    schC2.load_state_dict(ckpt["schedulerC"]); schG2.load_state_dict(ckpt["schedulerG"])
+    seed(2)
+    tg.train(netC2, optC2, schC2, netG2, optG2, schG2, netF2, clean2, data[2:], _Writer(), 2, opt)
+    torch.cuda.synchronize()
+    rel = lambda a, b: float((a - b).norm() / b.norm())
+    assert rel(netC2.net.store.flat, want_C) < 1e-5 and rel(netG2.net.store.flat, want_G) < 1e-5
+    assert rel(netC2.net.store.mom, want_mC) < 1e-4
+    assert int(netC2.state_dict()["layer1.0.bn1.num_batches_tracked"]) == 3
+
+
+def test_main_runs_with_the_reference_default_flags(capsys):
+    """`python -m combat_b200.train_generator` with NO flags: the reference's default --post_transform_option use included
+    (it raised NotImplementedError in round 1)."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from combat_b200 import train_generator as tg
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        args = ["--synthetic_data", "--debug", "--bs", "32", "--n_iters", "2", "--log_every", "4", "--saving_prefix", "t",
+                "--checkpoints", tmp, "--F_checkpoints", tmp]
+        bests = tg.main(args)
+        out = capsys.readouterr().out
+        assert "Clean Acc" in out and "Train from scratch" in out and " Saving..." in out
+        import os
+        ckpt = os.path.join(tmp, "t_clean", "cifar10", "cifar10_t_clean.pth.tar")
+        sd = torch.load(ckpt, map_location="cpu")
+        assert {"netC", "optimizerC", "schedulerC", "netG", "optimizerG", "schedulerG", "clean_model", "best_clean_acc",
+                "epoch_current"} <= set(sd)
+        # --continue_training resumes from the saved epoch with the saved bests
+        tg.main(args + ["--continue_training", "--n_iters", "3"])
+        out = capsys.readouterr().out
+        assert "Continue training!!" in out and "Epoch {}:".format(sd["epoch_current"] + 1) in out
+        assert len(bests) == 6

@@ -1,0 +1,90 @@
+"""The graph-replay loop with the host running ahead of the GPU (how train() and bench.py drive it: no sync per iteration).
+
+Every iteration's labels / permutation / num_bd / blur taps travel through pinned staging memory with asynchronous copies;
+if a staging buffer is rewritten before an earlier iteration's copy has executed, that iteration silently trains on another
+batch's plan.  The parameter block is now a ring of event-guarded slots
+(engine.upload_plan).  Checked here: K graph-replayed iterations with DISTINCT labels and NO host synchronisation, the GPU
+parked behind a long spin kernel so that all K host iterations are issued before the first copy executes, against the same K
+iterations with a synchronisation after each.  Integer outputs (accuracy counters, num_bd-dependent pass-through rows of the
+last iteration) must be bit-equal, float32 losses within 2e-5."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(sync_each, K, B, tf="no_use", multilabel=False):
+    from test_step_gpu import make_engine, seeded_state
+    from combat_b200.engine import AlternatedStep, default_opt
+    import random
+    state = seeded_state(17)
+    eng = make_engine(state, torch.float32, opt=default_opt(post_transform_option=tf))
+    g = torch.Generator().manual_seed(5)
+    xs = [(torch.rand(B, 3, 32, 32, generator=g) * 2 - 1).cuda() for _ in range(K + 2)]
+    ys = []
+    for i in range(K + 2):          # distinct label vectors with very different target-class counts (num_bd varies a lot)
+        y = torch.randint(0, 10, (B,), generator=g).numpy()
+        y[: (3 * i) % B] = 0
+        ys.append(y)
+    np.random.seed(3)
+    torch.manual_seed(3)
+    random.seed(3)
+    for i in range(2):              # eager warm-up + capture
+        eng.step(xs[i], ys[i], use_graph=True)
+    torch.cuda.synchronize()
+    losses = torch.zeros((K, 8), dtype=torch.float32, device="cuda")
+    counts = torch.zeros((K, 16), dtype=torch.int32, device="cuda")
+    plans = []
+    if not sync_each:
+        torch.cuda._sleep(int(0.25 * 1.9e9))   # ~250 ms: every host iteration below is issued before the GPU starts
+    for i in range(K):
+        out = eng.step(xs[2 + i], ys[2 + i], use_graph=True)
+        losses[i].copy_(out["losses"])
+        counts[i].copy_(out["counts"])
+        plans.append(out["plan"])
+        if sync_each:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    b = eng._bufs
+    return dict(losses=losses.cpu().numpy(), counts=counts.cpu().numpy(), num_bd=[p.num_bd for p in plans],
+                perm=b["perm"].cpu().numpy(), total_y=b["total_y"].cpu().numpy(), nbd_dev=int(b["num_bd"].cpu()[0]),
+                last_plan=plans[-1], netC=eng.netC.store.flat.clone().cpu())
+
+
+@pytest.mark.parametrize("tf", ["no_use", "use"])
+def test_graph_replay_without_host_sync_keeps_every_iterations_plan(tf):
+    K, B = 12, 48
+    ref = _run(True, K, B, tf)
+    got = _run(False, K, B, tf)
+    assert ref["num_bd"] == got["num_bd"] and len(set(ref["num_bd"])) > 3          # the plans really differ per iteration
+    assert np.array_equal(ref["counts"], got["counts"]), "accuracy counters of some iteration used another iteration's labels"
+    # the device copy of the LAST plan is that iteration's own
+    assert got["nbd_dev"] == got["last_plan"].num_bd
+    assert np.array_equal(got["perm"], got["last_plan"].perm) and np.array_equal(got["total_y"], got["last_plan"].total_targets)
+    d = np.abs(ref["losses"][:, :4] - got["losses"][:, :4]).max()
+    assert d <= 2e-5 * max(1.0, np.abs(ref["losses"][:, :4]).max()), d
+    assert float((ref["netC"] - got["netC"]).norm() / ref["netC"].norm()) < 1e-5
+
+
+def test_buffers_and_graphs_are_cached_per_batch_size():
+    """The shorter last batch of an epoch must not throw the full-size graph away (re-capture twice per epoch)."""
+    from test_step_gpu import make_engine, seeded_state
+    state = seeded_state(2)
+    eng = make_engine(state, torch.float32)
+    g = torch.Generator().manual_seed(1)
+    mk = lambda n: ((torch.rand(n, 3, 32, 32, generator=g) * 2 - 1).cuda(), torch.randint(0, 10, (n,), generator=g).numpy())
+    np.random.seed(0)
+    torch.manual_seed(0)
+    for n in (32, 32, 20, 20, 32, 20):
+        x, y = mk(n)
+        eng.step(x, y, use_graph=True)
+    torch.cuda.synchronize()
+    assert set(eng._bufs_by_B) == {32, 20}
+    g32, g20 = eng._bufs_by_B[32]["graph"], eng._bufs_by_B[20]["graph"]
+    assert g32 is not None and g20 is not None
+    x, y = mk(32)
+    eng.step(x, y, use_graph=True)
+    assert eng._bufs_by_B[32]["graph"] is g32
+    # num_batches_tracked counts executed iterations (eager warm-up + replays), not capture passes
+    assert set(eng.netC.num_batches_tracked.values()) == {7}
