@@ -118,6 +118,174 @@ def cpu_reference_rate(batch, steps, warmup, seed=0):
     return batch * len(times) / sum(times), sum(times) / len(times)
 
 
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def _timed_kernel(fn, iters=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e-3
+
+
+def sub_hbm_kernels(dev, peak_bw):
+    """BASELINE configs[4] + the north_star's HBM targets, timed alone with CUDA events on tensors far larger than the 126 MB
+    L2: batched 2-D DCT / IDCT / low_freq over 65,536 CIFAR-shape and 16,384 CelebA-shape images (float32 and uint8 input),
+    the fused poison-blend forward / backward over 65,536 rows, PostTensorTransform, the flat Nesterov-SGD update.
+    bytes = ALGORITHMIC bytes: one read + one write of every plane, etc."""
+    from combat_b200 import ops
+    from combat_b200.utils.dataloader import draw_params
+    out = []
+
+    def rec(name, nbytes, sec, units=None):
+        gbs = nbytes / sec / 1e9
+        r = {"kernel": name, "bytes": nbytes, "us": round(sec * 1e6, 2), "GB/s": round(gbs, 1), "frac": round(gbs / peak_bw, 4)}
+        if units:
+            r["images_per_s"] = round(units / sec, 1)
+        out.append(r)
+
+    for N, NI, keep in ((32, 65536, 20), (64, 16384, 41)):
+        x = torch.rand(NI, 3, N, N, device=dev) * 2 - 1
+        o = torch.empty_like(x)
+        for kind in ("dct", "idct", "lowfreq"):
+            t = _timed_kernel(lambda: ops.plane_op(x, kind, keep=keep, out=o))
+            rec("dct%d %s fp32 %dx3x%dx%d" % (N, kind, NI, N, N), 2 * x.numel() * 4, t, NI)
+        xu = (torch.rand(NI, 3, N, N, device=dev) * 255).to(torch.uint8)
+        t = _timed_kernel(lambda: ops.plane_op(xu, "dct", in_mode=1, out=o))
+        rec("dct%d dct uint8-in %dx3x%dx%d" % (N, NI, N, N), x.numel() * 5, t, NI)
+        # full-size correctness through size-independent properties (round trip, Parseval)
+        X = ops.plane_op(x, "dct", out=o)
+        e = float((x.double() ** 2).sum())
+        pars = abs(float((X.double() ** 2).sum()) - e) / e
+        rt = float((ops.plane_op(X, "idct") - x).abs().max())
+        assert rt < 5e-6 and pars < 1e-6, (N, rt, pars)
+        out[-1]["properties"] = {"idct(dct(x)) max abs err": rt, "Parseval rel err": pars}
+        del x, o, xu, X
+    B = 65536
+    x = torch.rand(B, 3, 32, 32, device=dev) * 2 - 1
+    noise = torch.rand(B, 3, 32, 32, device=dev) * 2 - 1
+    o = torch.empty_like(x)
+    taps = ops.gaussian_taps(0.6)
+    sq = torch.empty(B * 3, device=dev)
+    t = _timed_kernel(lambda: ops.poison_blend_fwd(x, noise, None, B, 0.08, taps, out=o, sq_partial=sq))
+    rec("poison_blend_fwd (blend+clamp+blur+MSE partials) 65536 rows", 3 * x.numel() * 4, t, B)
+    g1 = torch.randn(B, 3, 32, 32, device=dev)
+    dn = torch.empty_like(x)
+    t = _timed_kernel(lambda: ops.poison_blend_bwd(x, noise, o, g1, None, 1e-6, 0.08, taps, out=dn))
+    rec("poison_blend_bwd 65536 rows", 5 * x.numel() * 4, t, B)
+    opt_tf = argparse.Namespace(post_transform_option="use", random_crop=5, random_rotation=10, dataset="cifar10")
+    import random as _r
+    _r.seed(1)   # seed 1: crop, rotation and flip gates all on
+    P = None
+    while P is None or not (P[0, 4] == 1 and abs(P[:, 0]).sum() > 0):
+        P = draw_params(B, opt_tf)
+    Pd = torch.from_numpy(P).to(dev)
+    t = _timed_kernel(lambda: ops.post_transform_fwd(x, Pd, out=o))
+    rec("post_transform_fwd (crop+rotate+flip) 65536 rows", 2 * x.numel() * 4, t, B)
+    del x, noise, o, g1, dn, sq
+    n = 20541389
+    p_, g_, m_ = (torch.randn(n, device=dev) for _ in range(3))
+    lr = torch.full((1,), 1e-2, device=dev)
+    t = _timed_kernel(lambda: ops.sgd_nesterov(p_, g_, m_, lr, 0.9, 5e-4, False))
+    rec("sgd_nesterov 20.5M params", 20 * n, t)
+    del p_, g_, m_
+    torch.cuda.empty_cache()
+    return out
+
+
+def sub_step_config(name, dataset, S, ncls, B, multilabel, flops, lr, dev, rank, world, sync, barrier, peak_tf, steps=5, warmup=3,
+                    post_transform="no_use"):
+    """One of the OTHER step shapes BASELINE.json names, same engine, device-resident inputs, CUDA-graph replay, weak DP."""
+    import torch.distributed as dist
+    from combat_b200 import config
+    from combat_b200 import train_generator as tg
+    from combat_b200 import train_generator_multilabel as tgm
+    from combat_b200.engine import AlternatedStep
+    mod = tgm if multilabel else tg
+    opt = config.get_arguments().parse_args(["--device", str(dev), "--post_transform_option", post_transform, "--dataset", dataset])
+    opt.input_height = opt.input_width = S
+    opt.input_channel, opt.num_classes = 3, ncls
+    opt.lr_C = opt.lr_G = lr
+    torch.manual_seed(0)
+    netC, _, _, netG, _, _, netF, clean_model = mod.get_model(opt)
+    eng = AlternatedStep(opt, device=dev, with_metrics=True, multilabel=multilabel,
+                         nets=(netC.net, clean_model.net, netG.net, netF.net if netF is not None else None),
+                         grad_hook=sync.grad_hook if world > 1 else None, buf_hook=sync.buf_hook if world > 1 else None)
+    g = torch.Generator().manual_seed(7 + rank)
+    xs = [(torch.rand(B, 3, S, S, generator=g) * 2 - 1).to(dev) for _ in range(2)]
+    ys = [torch.randint(0, ncls, (B,), generator=g).numpy() for _ in range(2)]
+    for i in range(warmup):
+        out = eng.step(xs[i % 2], ys[i % 2], use_graph=True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        out = eng.step(xs[i % 2], ys[i % 2], use_graph=True)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    ms /= steps
+    losses = [float(v) for v in out["losses"].cpu()]
+    rate = world * B / (ms * 1e-3)
+    r = {"case": name, "images_per_s": rate, "ms_per_step": ms, "batch_per_gpu": B, "n_gpus": world, "steps": steps, "warmup": warmup,
+         "dtype": "bf16", "lr": lr, "post_transform_option": post_transform, "update_flops_per_image": flops,
+         "step_frac_of_tensor_peak": rate / world * flops / 1e12 / peak_tf, "finite": bool(np.all(np.isfinite(losses))),
+         "max_memory_GB": torch.cuda.max_memory_allocated() / 1e9, "launches_per_step": eng.launches_per_step}
+    del eng, netC, netG, netF, clean_model, xs
+    torch.cuda.empty_cache()
+    return r
+
+
+def gpu_eager_baseline(dev, batch=512, steps=3, warmup=2):
+    """'PyTorch eager on the same B200' comparator: the reference's algorithm (oracle restatement:
+    aten / cuDNN / cuFFT kernels, autograd, fp32) with every tensor on the GPU.  A reported baseline next to cpu_baseline;
+    never the product path."""
+    from oracle import combat_oracle as O
+    res = {}
+    for tf32 in (False, True):
+        torch.backends.cudnn.benchmark = True
+        torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = tf32
+        gen = torch.Generator().manual_seed(0)
+        st = synthetic_state(0)
+        to = lambda d: {k: v.to(dev) for k, v in d.items()}
+        state = {k: (to(v) if isinstance(v, dict) and k not in ("momC", "momG") else v) for k, v in st.items()}
+        opt = O.default_opt()
+        xs = [(torch.rand(batch, 3, 32, 32, generator=gen) * 2 - 1).to(dev) for _ in range(2)]
+        ys = [torch.randint(0, 10, (batch,), generator=gen).to(dev) for _ in range(2)]
+        times = []
+        for i in range(warmup + steps):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            O.alternated_step(state, xs[i % 2], ys[i % 2], opt)
+            torch.cuda.synchronize()
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+        ms = 1e3 * sum(times) / len(times)
+        res["tf32" if tf32 else "fp32"] = {"value": batch / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms}
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    res.update(batch=batch, steps=steps, warmup=warmup,
+               impl="oracle/combat_oracle.py with all tensors on cuda:0 (torch %s eager: cuDNN convs, cuFFT DCT, autograd)" % torch.__version__)
+    torch.cuda.empty_cache()
+    return res
+
+
 WORKLOAD = ("CIFAR-10 shape alternated step (train_generator.py:170-255), PreActResNet18 + UnetGenerator, pc=0.5 noise_rate=0.08, "
             "bf16 tcgen05 convs, all metric forwards included (BASELINE configs[1])")
 
@@ -135,7 +303,7 @@ def run_reference(args):
         return
     # size the per-step sample so that the whole run ends within a few minutes
     r32, t32 = cpu_reference_rate(32, 1, 0)
-    budget = 150.0
+    budget = 300.0   # BASELINE configs[0] (batch 128) unless this box's cores would need more than ~5 minutes for K + W steps
     batch = 128
     while batch > 16 and (args.steps + args.warmup) * t32 * batch / 32 > budget:
         batch //= 2
@@ -148,7 +316,7 @@ def run_reference(args):
         # same workload as the CUDA arm; every timed step is a bounded SAMPLE of it (one alternated step over `batch` images of
         # the same synthetic distribution, fp32, all host threads) -- images/s is batch-size independent on the CPU
         "config": dict(workload_config(args.batch, max(1, args.gpus), not args.no_graph), reference_sample_batch=batch),
-        "cpu_baseline": {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": rate, "unit": "images/s", "cores": cores, "kind": "port", "cpu_model": cpu_model(),
                          "sample": "%d alternated steps of batch %d on the host cores (oracle/combat_oracle.py)" % (args.steps, batch)},
         "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -295,8 +463,39 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, tstep = cpu_reference_rate(128, 2, 1)
-        cpu = {"value": rate, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+        cpu = {"value": rate, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port", "cpu_model": cpu_model(),
                "sample": "2 alternated steps of batch 128 (BASELINE configs[0]) after 1 warm-up, oracle/combat_oracle.py on the host cores"}
+    # ---- sub-records: the other targets BASELINE.json / north_star name, measured by the same process (not the headline)
+    sub = {}
+    if not args.no_sub:
+        peak_tf, peak_bw, _ = peaks()
+        torch.cuda.empty_cache()
+        if rank == 0 and world == 1:
+            sub["hbm_kernels"] = sub_hbm_kernels(dev, peak_bw)
+        steps_cfg = []
+        cases = [("configs[4] CelebA 64x64 multilabel step (ResNet18(8) + CUnetGeneratorv1), batch 256 per GPU", "celeba", 64, 8, 256, True, 37.4e9, 1e-2)]
+        if world in (1, 8):
+            # 224x224 with the scaler-49 head diverges within a few iterations at the reference's lr 1e-2 on random data (the
+            # reference itself raises KeyError for this size); throughput does not depend on lr: timed at 1e-4, stated here
+            cases.append(("configs[3] ImageNet-10 shape 224x224 (ResNet18 scaler-49 + UnetGenerator), batch 256 per GPU", "imagenet10", 224, 10, 256, False, 458e9, 1e-4))
+        if world == 1:
+            cases.append(("configs[1] with the reference's DEFAULT --post_transform_option use, batch 512", "cifar10", 32, 10, 512, False, 9.35e9, 1e-2))
+        if world in (2, 4):
+            cases.append(("configs[2] CIFAR-10 STRONG scaling point: global batch 4096 (%d per GPU)" % (4096 // world), "cifar10", 32, 10, 4096 // world, False, 9.35e9, 1e-2))
+        for c in cases:
+            try:
+                torch.cuda.reset_peak_memory_stats()
+                ptf = "use" if "DEFAULT" in c[0] else "no_use"
+                steps_cfg.append(sub_step_config(*c, dev, rank, world, sync, barrier, peak_tf, post_transform=ptf))
+            except Exception as e:  # a failing extra shape must not cost the headline line
+                steps_cfg.append({"case": c[0], "error": "%s: %s" % (type(e).__name__, str(e)[:300])})
+        sub["step_configs"] = steps_cfg
+    eager = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            eager = gpu_eager_baseline(dev)
+        except Exception as e:
+            eager = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
     if rank == 0:
         line = {
             "metric": "alternated-step images/sec at CIFAR-10 shape", "value": value, "unit": "images/s", "n_gpus": world,
@@ -306,6 +505,7 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
+            "gpu_eager_baseline": eager, "sub": sub,
         }
         print(json.dumps(line))
     if world > 1:
@@ -321,6 +521,7 @@ def main():
     ap.add_argument("--batch", type=int, default=512, help="batch per GPU")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub", action="store_true", help="skip the sub-records (HBM kernels, other step shapes)")
     ap.add_argument("--dump-layers", default=None, help="write the per-layer tcgen05 conv timing table to this file")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -16,6 +16,7 @@ from the HOST copy of the labels, so the device never has to sync.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from types import SimpleNamespace
 
@@ -291,6 +292,10 @@ class AlternatedStep:
         return b
 
     def _next_slot(self, b):
+        if os.environ.get("COMBAT_UNSAFE_PLAN_STAGING"):
+            # round-1 behaviour (ONE unguarded pinned image), kept only so that tests/test_graph_nosync_gpu.py can be shown to
+            # FAIL without the guard (profiles/r02_staging_race.md); never set in production
+            return b["slots"][0]
         s = b["slots"][b["slot"]]
         b["slot"] = (b["slot"] + 1) % len(b["slots"])
         if s["ev"] is not None:

@@ -721,10 +721,10 @@ class Generator(NetBase):
               "upconv0_0": (nf, out_channel)}
         # CUnetGeneratorv1.conv0_1 reads nf + num_classes channels (72 for CelebA): not a multiple of the 64-channel K chunk of
         # the tcgen05 kernels, so it ran on the generic CUDA-core kernel (1.2 ms per launch, 8.5 ms of the 34.7 ms CelebA step,
-        # profiles/r01_launches_celeba_multilabel_partial.md).  COMBAT_PAD_COND=1 stores that weight with its input channels
-        # padded to the next multiple of 64 (zeros, see ParamStore) and gives the concatenated activation the same width.
-        # Opt-in until it has been through the GPU parity tests (written after round 1's GPU budget was spent).
-        self.cond_pad = bool(os.environ.get("COMBAT_PAD_COND")) and self.use_tc and num_classes > 0 and (nf + num_classes) % 64 != 0
+        # profiles/r01_launches_celeba_multilabel_partial.md).  That weight is therefore STORED with its input channels padded
+        # to the next multiple of 64 (zeros, see ParamStore) and the concatenated activation gets the same width.
+        # COMBAT_NO_PAD_COND=1 restores the unpadded layout (A/B measurements).
+        self.cond_pad = (not os.environ.get("COMBAT_NO_PAD_COND")) and self.use_tc and num_classes > 0 and (nf + num_classes) % 64 != 0
         specs, convs, store_ci = [], [], {}
         for name, stride in self.LAYERS:
             ci, co = ch[name]

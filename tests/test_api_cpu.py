@@ -141,7 +141,7 @@ def test_multilabel_plan_matches_oracle_chunks_and_draws():
 def test_param_store_padded_input_channels_round_trip():
     """ParamStore(store_ci=...): a conv weight stored with extra (zero) input channels keeps the reference's logical OIHW
     shape in p()/g()/state(), loads a reference tensor into the leading channels only, and lays the storage out
-    channels-last with the stored width -- what the opt-in padded CUnetGeneratorv1.conv0_1 (COMBAT_PAD_COND) relies on."""
+    channels-last with the stored width -- what the padded CUnetGeneratorv1.conv0_1 relies on."""
     import torch
 
     from combat_b200.nets import ParamStore
@@ -165,10 +165,10 @@ def test_param_store_padded_input_channels_round_trip():
 
 def test_padded_conditional_generator_keeps_the_reference_shapes(monkeypatch):
     from combat_b200 import nets
-    monkeypatch.setenv("COMBAT_PAD_COND", "1")
     g = nets.Generator(num_classes=8, device="meta")
-    monkeypatch.delenv("COMBAT_PAD_COND")
+    monkeypatch.setenv("COMBAT_NO_PAD_COND", "1")
     ref = nets.Generator(num_classes=8, device="meta")
+    monkeypatch.delenv("COMBAT_NO_PAD_COND")
     assert g.cond_pad and not ref.cond_pad
     assert g.convs["conv0_1"].Cin == 128 and ref.convs["conv0_1"].Cin == 72
     assert g.store.shapes == ref.store.shapes

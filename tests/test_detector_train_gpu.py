@@ -1,9 +1,7 @@
 """Frequency-detector TRAINING iteration on the CUDA path (combat_b200.defenses.frequency_based.train, float32 CUDA-core
 kernels) against oracle/detector_oracle.py and the fixture recorded from the unmodified reference train().
 
-GATED: this path was written after round 1's GPU budget was spent and has not run on a GPU yet.  Set
-COMBAT_DETECTOR_TRAIN=1 to run it; once it is green the gate goes away."""
-import os
+"""
 import random
 import types
 
@@ -11,8 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("COMBAT_DETECTOR_TRAIN"), reason="detector training path not yet GPU-validated")]
+pytestmark = pytest.mark.gpu
 
 from oracle import combat_oracle as O  # noqa: E402
 from oracle import detector_oracle as D  # noqa: E402
