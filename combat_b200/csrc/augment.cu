@@ -67,76 +67,124 @@ __device__ __forceinline__ Taps make_taps(const TfRow& r, int x, int y, int H, i
   return t;
 }
 
+// One CTA per (image, chunk of PIX_PER_CTA output pixels): the 8-float parameter row is read once per CTA, pixel indices are
+// 32-bit.  STAGED: the whole C x H x W source image is first copied into shared memory with coalesced 16-byte loads and the
+// gather (up to four taps per pixel, arbitrary under rotation) is served from there, so HBM sees exactly one read and one
+// write of every image; used when the image fits (CIFAR 12 KB, CelebA 48 KB).  Larger images gather from global memory
+// (neighbouring taps share sectors; L1 absorbs the re-reads).
+#define PIX_PER_CTA 1024
+
+template <bool STAGED>
 __global__ void __launch_bounds__(256) post_transform_fwd_k(const float* __restrict__ in, float* __restrict__ out,
-                                                            const float* __restrict__ params, int rows, int C, int H, int W) {
-  const long long total = (long long)rows * H * W;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(i % W);
-    const int y = (int)((i / W) % H);
-    const int n = (int)(i / ((long long)W * H));
-    const TfRow r = load_row(params, n);
+                                                            const float* __restrict__ params, int C, int H, int W) {
+  extern __shared__ float4 simg4[];
+  float* simg = (float*)simg4;
+  const int n = blockIdx.x;
+  const int HW = H * W;
+  const float* src = in + (long long)n * C * HW;
+  if (STAGED) {
+    const int n4 = (C * HW) >> 2;   // the launcher guarantees C*H*W % 4 == 0 for the staged variant
+    const float4* s4 = (const float4*)src;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) simg4[i] = __ldg(s4 + i);
+    __syncthreads();
+  }
+  const TfRow r = load_row(params, n);
+  const float* base = STAGED ? simg : src;
+  float* dst = out + (long long)n * C * HW;
+  const int p0 = STAGED ? 0 : blockIdx.y * PIX_PER_CTA;   // staged: one CTA owns the whole image
+  const int p1 = STAGED ? HW : min(p0 + PIX_PER_CTA, HW);
+  for (int p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
+    const int y = p / W, x = p - y * W;
     const Taps t = make_taps(r, x, y, H, W);
-    const float* src = in + (long long)n * C * H * W;
-    float* dst = out + (long long)n * C * H * W + y * W + x;
     for (int c = 0; c < C; ++c) {
-      const float* pl = src + (long long)c * H * W;
+      const float* pl = base + c * HW;
       float v = 0.f;
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        if (t.off[k] >= 0) v = fmaf(t.w[k], __ldg(pl + t.off[k]), v);
-      dst[(long long)c * H * W] = v;
+        if (t.off[k] >= 0) v = fmaf(t.w[k], STAGED ? pl[t.off[k]] : __ldg(pl + t.off[k]), v);
+      dst[c * HW + p] = v;
     }
   }
 }
 
 // adjoint: din(src) += w * dout(dst) for every tap of every output pixel (din zero-filled by the entry point unless
-// `accumulate`); float atomics -- at most a handful of contributions per input pixel
+// `accumulate`).  STAGED: the scatter goes to a zeroed shared-memory image with shared atomics and is written (or added)
+// to global memory once, coalesced; otherwise float atomics on global memory.
+template <bool STAGED>
 __global__ void __launch_bounds__(256) post_transform_bwd_k(const float* __restrict__ dout, float* __restrict__ din,
-                                                            const float* __restrict__ params, int rows, int C, int H, int W) {
-  const long long total = (long long)rows * H * W;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(i % W);
-    const int y = (int)((i / W) % H);
-    const int n = (int)(i / ((long long)W * H));
-    const TfRow r = load_row(params, n);
+                                                            const float* __restrict__ params, int C, int H, int W, int accumulate) {
+  extern __shared__ float4 simg4[];
+  float* simg = (float*)simg4;
+  const int n = blockIdx.x;
+  const int HW = H * W;
+  const TfRow r = load_row(params, n);
+  const float* g = dout + (long long)n * C * HW;
+  float* dst = din + (long long)n * C * HW;
+  if (STAGED) {
+    for (int i = threadIdx.x; i < C * HW; i += blockDim.x) simg[i] = 0.f;
+    __syncthreads();
+  }
+  const int p0 = STAGED ? 0 : blockIdx.y * PIX_PER_CTA;
+  const int p1 = STAGED ? HW : min(p0 + PIX_PER_CTA, HW);
+  for (int p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
+    const int y = p / W, x = p - y * W;
     const Taps t = make_taps(r, x, y, H, W);
-    const float* g = dout + (long long)n * C * H * W + y * W + x;
-    float* dst = din + (long long)n * C * H * W;
     for (int c = 0; c < C; ++c) {
-      const float gv = __ldg(g + (long long)c * H * W);
-      float* pl = dst + (long long)c * H * W;
+      const float gv = __ldg(g + c * HW + p);
+      float* pl = (STAGED ? simg : dst) + c * HW;
 #pragma unroll
       for (int k = 0; k < 4; ++k)
         if (t.off[k] >= 0 && t.w[k] != 0.f) atomicAdd(pl + t.off[k], t.w[k] * gv);
+    }
+  }
+  if (STAGED) {
+    __syncthreads();
+    const int n4 = (C * HW) >> 2;
+    float4* d4 = (float4*)dst;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      float4 v = simg4[i];
+      if (accumulate) { const float4 o = d4[i]; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+      d4[i] = v;
     }
   }
 }
 
 }  // namespace
 
+static bool tf_staged(int C, int H, int W, size_t* bytes) {
+  *bytes = (size_t)C * H * W * sizeof(float);
+  return (((long long)C * H * W) & 3) == 0 && *bytes <= 64 * 1024;  // CIFAR 12 KB, CelebA 48 KB per image
+}
+
 extern "C" int combat_post_transform_fwd(const float* in, float* out, const float* params, int rows, int C, int H, int W,
                                          void* stream) {
   COMBAT_ARG(in && out && params && in != out, 0);
-  COMBAT_ARG(rows >= 0 && C > 0 && H > 0 && W > 0, 1);
+  COMBAT_ARG(rows >= 0 && C > 0 && H > 0 && W > 0 && (long long)C * H * W < (1LL << 30), 1);
   if (rows == 0) return 0;
-  const long long total = (long long)rows * H * W;
-  int grid = cdiv(total, 256);
-  const int cap = resident_ctas(post_transform_fwd_k, 256) * 4;
-  if (cap > 0 && grid > cap) grid = cap;
-  post_transform_fwd_k<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, params, rows, C, H, W);
+  size_t bytes;
+  if (tf_staged(C, H, W, &bytes)) {
+    cudaFuncSetAttribute(post_transform_fwd_k<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    post_transform_fwd_k<true><<<dim3(rows, 1), 256, bytes, (cudaStream_t)stream>>>(in, out, params, C, H, W);
+    COMBAT_RETURN_LAUNCH("post_transform_fwd");
+  }
+  dim3 grid(rows, cdiv(H * W, PIX_PER_CTA));
+  post_transform_fwd_k<false><<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, params, C, H, W);
   COMBAT_RETURN_LAUNCH("post_transform_fwd");
 }
 
 extern "C" int combat_post_transform_bwd(const float* dout, float* din, const float* params, int rows, int C, int H, int W,
                                          int accumulate, void* stream) {
   COMBAT_ARG(dout && din && params && dout != din, 0);
-  COMBAT_ARG(rows >= 0 && C > 0 && H > 0 && W > 0, 1);
+  COMBAT_ARG(rows >= 0 && C > 0 && H > 0 && W > 0 && (long long)C * H * W < (1LL << 30), 1);
   if (rows == 0) return 0;
-  const long long total = (long long)rows * H * W;
-  if (!accumulate) cudaMemsetAsync(din, 0, (size_t)total * C * sizeof(float), (cudaStream_t)stream);
-  int grid = cdiv(total, 256);
-  const int cap = resident_ctas(post_transform_bwd_k, 256) * 4;
-  if (cap > 0 && grid > cap) grid = cap;
-  post_transform_bwd_k<<<grid, 256, 0, (cudaStream_t)stream>>>(dout, din, params, rows, C, H, W);
+  size_t bytes;
+  if (tf_staged(C, H, W, &bytes)) {
+    cudaFuncSetAttribute(post_transform_bwd_k<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    post_transform_bwd_k<true><<<dim3(rows, 1), 256, bytes, (cudaStream_t)stream>>>(dout, din, params, C, H, W, accumulate);
+    COMBAT_RETURN_LAUNCH("post_transform_bwd");
+  }
+  if (!accumulate) cudaMemsetAsync(din, 0, (size_t)rows * C * H * W * sizeof(float), (cudaStream_t)stream);
+  dim3 grid(rows, cdiv(H * W, PIX_PER_CTA));
+  post_transform_bwd_k<false><<<grid, 256, 0, (cudaStream_t)stream>>>(dout, din, params, C, H, W, accumulate);
   COMBAT_RETURN_LAUNCH("post_transform_bwd");
 }

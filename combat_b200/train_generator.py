@@ -296,7 +296,7 @@ def main(argv=None):
         opt.F_ckpt_path = os.path.join(opt.F_ckpt_folder, opt.F_model, "{}_{}_detector.pth.tar".format(opt.dataset, opt.F_model))
         if os.path.exists(opt.F_ckpt_path) or not opt.synthetic_data:
             print(f"Loading {opt.F_model} at {opt.F_ckpt_path}")
-            netF.load_state_dict(torch.load(opt.F_ckpt_path, map_location=opt.device)["netC"])
+            netF.load_state_dict(torch.load(opt.F_ckpt_path, map_location=opt.device, weights_only=False)["netC"])
             print("Done")
         netF.eval()
     # pretrained clean model (:513-527)
@@ -306,7 +306,7 @@ def main(argv=None):
         if not os.path.exists(load_path):
             print("Error: {} not found".format(load_path))
             sys.exit()
-        clean_model.load_state_dict(torch.load(load_path, map_location=opt.device)["netC"])
+        clean_model.load_state_dict(torch.load(load_path, map_location=opt.device, weights_only=False)["netC"])
     clean_model.eval()
 
     bests = [0.0] * 6
@@ -316,7 +316,7 @@ def main(argv=None):
             print("Pretrained model doesnt exist")
             sys.exit()
         print("Continue training!!")
-        sd = torch.load(opt.ckpt_path, map_location=opt.device)
+        sd = torch.load(opt.ckpt_path, map_location=opt.device, weights_only=False)  # our own checkpoint (holds numpy scalars, as the reference's)
         netC.load_state_dict(sd["netC"])
         optimizerC.load_state_dict(sd["optimizerC"])
         schedulerC.load_state_dict(sd["schedulerC"])

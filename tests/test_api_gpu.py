@@ -179,7 +179,7 @@ def test_main_runs_with_the_reference_default_flags(capsys):
         assert "Clean Acc" in out and "Train from scratch" in out and " Saving..." in out
         import os
         ckpt = os.path.join(tmp, "t_clean", "cifar10", "cifar10_t_clean.pth.tar")
-        sd = torch.load(ckpt, map_location="cpu")
+        sd = torch.load(ckpt, map_location="cpu", weights_only=False)
         assert {"netC", "optimizerC", "schedulerC", "netG", "optimizerG", "schedulerG", "clean_model", "best_clean_acc",
                 "epoch_current"} <= set(sd)
         # --continue_training resumes from the saved epoch with the saved bests

@@ -5,8 +5,10 @@ if a staging buffer is rewritten before an earlier iteration's copy has executed
 batch's plan.  The parameter block is now a ring of event-guarded slots
 (engine.upload_plan).  Checked here: K graph-replayed iterations with DISTINCT labels and NO host synchronisation, the GPU
 parked behind a long spin kernel so that all K host iterations are issued before the first copy executes, against the same K
-iterations with a synchronisation after each.  Integer outputs (accuracy counters, num_bd-dependent pass-through rows of the
-last iteration) must be bit-equal, float32 losses within 2e-5."""
+iterations with a synchronisation after each.  Integer outputs (accuracy counters of every iteration, the device copy of the
+last plan) must be bit-equal; float32 losses of the first iteration within 2e-5, later ones within the growth of atomic-order
+noise.  On round 1's single unguarded staging buffer (COMBAT_UNSAFE_PLAN_STAGING=1) this test FAILS on the counters:
+profiles/r02_staging_race.md."""
 import numpy as np
 import pytest
 import torch
@@ -62,9 +64,15 @@ def test_graph_replay_without_host_sync_keeps_every_iterations_plan(tf):
     # the device copy of the LAST plan is that iteration's own
     assert got["nbd_dev"] == got["last_plan"].num_bd
     assert np.array_equal(got["perm"], got["last_plan"].perm) and np.array_equal(got["total_y"], got["last_plan"].total_targets)
-    d = np.abs(ref["losses"][:, :4] - got["losses"][:, :4]).max()
-    assert d <= 2e-5 * max(1.0, np.abs(ref["losses"][:, :4]).max()), d
-    assert float((ref["netC"] - got["netC"]).norm() / ref["netC"].norm()) < 1e-5
+    # floats: both runs launch the same kernels on the same inputs; the float32 atomics of the weight-gradient kernels make the
+    # sums order dependent (~1e-7 relative per step), and twelve SGD steps at lr 1e-2 on a random-init network amplify that
+    # (measured on B200: 4.7e-3 absolute on a loss of 2.5 after 12 iterations; a swapped plan moves a loss by O(1)).  The
+    # first iteration -- before any amplification -- must agree to float32 accuracy.
+    d = np.abs(ref["losses"][:, :4] - got["losses"][:, :4])
+    scale = max(1.0, np.abs(ref["losses"][:, :4]).max())
+    assert d[0].max() <= 2e-5 * scale, d[0]
+    assert d.max() <= 2e-2 * scale, d.max(axis=1)
+    assert float((ref["netC"] - got["netC"]).norm() / ref["netC"].norm()) < 1e-3
 
 
 def test_buffers_and_graphs_are_cached_per_batch_size():
