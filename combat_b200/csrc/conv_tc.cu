@@ -106,6 +106,66 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- CTA pairs (cta_group::2): two CTAs of a cluster (the two SMs of a TPC) execute ONE 256-row MMA; each stages its own 128
+// rows of A and HALF of B, so per SM the shared-memory traffic of the B operand (TMA writes and MMA reads) is halved.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address -> shared::cluster address of the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads whose completion is signalled on an mbarrier of the PAIR'S LEADER CTA (bar_cluster_addr: shared::cluster address)
+__device__ __forceinline__ void tma_load_4d_2sm(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1, int c2,
+                                                int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// arrives on the mbarrier at the same offset in BOTH CTAs of the pair once all previously issued MMAs have completed
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B, version 1
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -149,6 +209,8 @@ struct TcParams {
   int lbw, lbh;           // log2(BW), log2(BH)
   int tiles_w, tiles_h, tiles_n, tiles_co, n_classes, total_tiles;
   int kchunks;            // Ci / 64
+  // CTA-pair kernels: work item v = 2 * pair + cta_rank; a pair = two pixel tiles of ONE class and ONE output-channel tile
+  int pair_mode, px_tiles_per_class, pairs_per_class, total_items;
   void* out;             // bf16 or float32 (out_f32)
   const void* residual;  // bf16 or float32 (res_f32)
   const float* bias;
@@ -184,6 +246,23 @@ struct TcCfg {
 };
 
 __device__ __forceinline__ void decode_tile(const TcParams& p, int tile, int& cls, int& nt, int& ht, int& wt, int& cot) {
+  if (p.pair_mode) {
+    const int rank = tile & 1, q = tile >> 1;
+    cot = q % p.tiles_co;
+    const int pp = q / p.tiles_co;
+    cls = pp / p.pairs_per_class;
+    const int px = 2 * (pp - cls * p.pairs_per_class) + rank;
+    if (px >= p.px_tiles_per_class) {  // odd tile count: the pair's second half is all padding (TMA zero fill, no stores)
+      nt = p.tiles_n;
+      ht = wt = 0;
+      return;
+    }
+    wt = px % p.tiles_w;
+    const int r2 = px / p.tiles_w;
+    ht = r2 % p.tiles_h;
+    nt = r2 / p.tiles_h;
+    return;
+  }
   cot = tile % p.tiles_co;
   int r = tile / p.tiles_co;
   wt = r % p.tiles_w;
@@ -198,9 +277,15 @@ __device__ __forceinline__ void decode_tile(const TcParams& p, int tile, int& cl
 // MODE 0: out = act(acc + bias)*post_scale+post_shift + residual; out2 = bf16 relu(out*scale2+shift2)
 // MODE 2: MODE 0 + per-(CTA, row quarter) partial sums / sums of squares of `out` (train-mode BatchNorm statistics)
 // MODE 1: out = bf16( mask > 0 ? (acc + residual) * mask_scale : 0 ) + post_add     (residual XOR post_add, both bf16)
-template <int BLOCK_N, int MODE>
+template <int BLOCK_N, int MODE, bool PAIR = false>
 __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* stg_base, uint32_t tmem_base, uint64_t* tfull_bar,
                                             uint64_t* tempty_bar, int warp, int lane) {
+  // PAIR: the accumulator-empty barriers live in the pair's leader CTA (its MMA thread waits for the epilogue warps of BOTH CTAs)
+  uint32_t tempty_leader[2] = {0, 0};
+  if (PAIR) {
+    tempty_leader[0] = mapa_u32(smem_u32(&tempty_bar[0]), 0);
+    tempty_leader[1] = mapa_u32(smem_u32(&tempty_bar[1]), 0);
+  }
   // ===================== epilogue: TMEM -> registers -> shared (transpose) -> coalesced global =====================
   // 8 warps: warp w owns TMEM lanes [32*(w%4), +32) (hardware rule) and the column half (w-2)/4 of the tile.
   // tcgen05.ld hands a thread one accumulator ROW (pixel); writing rows straight to NHWC memory makes every store
@@ -422,7 +507,10 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* stg_base
     if (has_acc) {
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(tempty_leader[acc]);
+        else mbar_arrive(&tempty_bar[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (dbg_w) {
@@ -437,7 +525,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* stg_base
   }
   if (STATS) {
     // partial block = (CTA, quarter): [2][Co]; lanes with sub == 0 hold the sums of the warp's 32 rows after the reduction
-    const int cot = (int)blockIdx.x % p.tiles_co;
+    const int cot = (PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x) % p.tiles_co;
     float* dst = p.stats + ((long long)blockIdx.x * 4 + quarter) * 2 * p.Co + cot * BLOCK_N + half * (BLOCK_N / 2) + cseg * 4;
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) {
@@ -561,6 +649,133 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- fwd / dgrad kernel, CTA pairs
+// Same pipeline as conv_tc_kernel, executed by a cluster of two CTAs (the two SMs of a TPC) as ONE 256 x BLOCK_N MMA per K step
+// (tcgen05.mma.cta_group::2): CTA r of the pair owns pixel tile 2*pair + r (its 128 accumulator rows live in its own TMEM) and
+// stages rows [r * BLOCK_N/2, +BLOCK_N/2) of the weight tile; the tensor cores of both SMs read both halves.  Per SM and K step
+// of 64: 16 KB of A + BLOCK_N/2 * 128 B of B through the shared-memory port (TMA write + MMA read) instead of 16 KB + BLOCK_N *
+// 128 B -- the port (128 B/clk, shared with the epilogue transposes) is what bounds the single-CTA kernel.
+// Barriers: the leader's (rank 0) full barriers collect the TMA bytes of BOTH CTAs; its MMA thread frees smem slots and
+// publishes accumulators with multicast commits (one arrive in each CTA); the epilogue warps of both CTAs release an
+// accumulator buffer by arriving on the LEADER's barrier.
+template <int BLOCK_N>
+struct TcPairCfg {
+  static constexpr int A_BYTES = TILE_M * KCHUNK * 2;            // 16 KB
+  static constexpr int B_BYTES = (BLOCK_N / 2) * KCHUNK * 2;     // this CTA's half: 8 / 16 KB
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = BLOCK_N == 256 ? 5 : 7;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + TC_EPI_WARPS * 32 * EPI_ROWB;
+};
+
+template <int BLOCK_N, int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+    conv_tc_pair_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
+  using Cfg = TcPairCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::STAGES;
+  uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;
+  uint64_t* tempty_bar = bars + 2 * Cfg::STAGES + 2;
+  uint32_t* tmem_ptr_smem = (uint32_t*)(bars + 2 * Cfg::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.w);
+    tma_prefetch_desc(&maps.in[0]);
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);    // leader: its own arrive.expect_tx; the bytes of both CTAs complete the phase
+      mbar_init(&empty_bar[s], 1);   // one multicast commit arrive per use
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 2 * TC_EPI_WARPS);  // leader: the epilogue warps of both CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_ptr_smem, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / multicast commit / remote complete_tx
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int cls, nt, ht, wt, cot;
+        decode_tile(p, tile, cls, nt, ht, wt, cot);
+        const int ntaps = p.taps.ntaps[cls];
+        for (int t = 0; t < ntaps; ++t) {
+          const CUtensorMap* amap = &maps.in[p.taps.view[cls][t]];
+          const int cw = wt * p.BW + p.taps.dw[cls][t];
+          const int ch = ht * p.BH + p.taps.dh[cls][t];
+          const int cn = nt * p.BNI;
+          const int wtap = p.taps.wtap[cls][t];
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+            uint8_t* sb = sa + Cfg::A_BYTES;
+            const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+            tma_load_4d_2sm(sa, amap, lead_full, kc * KCHUNK, cw, ch, cn);
+            tma_load_3d_2sm(sb, &maps.w, lead_full, kc * KCHUNK, wtap, cot * BLOCK_N + (int)rank * (BLOCK_N / 2));
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc(2 * TILE_M, BLOCK_N, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int cls, nt, ht, wt, cot;
+        decode_tile(p, tile, cls, nt, ht, wt, cot);
+        const int kiters = p.taps.ntaps[cls] * p.kchunks;
+        if (kiters == 0) continue;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int it = 0; it < kiters; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint64_t adesc = make_smem_desc(sa, 16, 1024);
+          const uint64_t bdesc = make_smem_desc(sb, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < KCHUNK / 16; ++k) umma_bf16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+          umma_commit_2sm(&empty_bar[stage]);  // frees the slot in both CTAs
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(&tfull_bar[acc]);  // accumulator complete, both CTAs
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    tc_epilogue<BLOCK_N, MODE, true>(p, smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256, tmem_base, tfull_bar, tempty_bar, warp, lane);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer may still be reading this CTA's shared memory / writing its tensor memory until here
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -775,6 +990,32 @@ static int num_sms() {
   return n;
 }
 
+// clusters of two CTAs that can be resident at once (one CTA per SM: the two SMs of a TPC); queried once
+static int max_pair_clusters() {
+  static int n = 0;
+  if (!n) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * num_sms());
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = TcPairCfg<256>::SMEM_BYTES;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2;
+    attr.val.clusterDim.y = attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    cudaFuncSetAttribute(conv_tc_pair_kernel<256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcPairCfg<256>::SMEM_BYTES);
+    int q = 0;
+    if (cudaOccupancyMaxActiveClusters(&q, conv_tc_pair_kernel<256, 0>, &cfg) != cudaSuccess || q <= 0) {
+      cudaGetLastError();
+      q = num_sms() / 2;
+    }
+    n = q < num_sms() / 2 ? q : num_sms() / 2;
+  }
+  return n;
+}
+
 static int g_last_grid = 0;
 extern "C" int combat_conv_tc_last_grid(void) { return g_last_grid; }
 
@@ -887,8 +1128,6 @@ extern "C" int combat_conv_tc(const combat_conv_tc_desc* d, void* stream) {
     rc = make_act_map(&maps.in[0], d->in, d->Ci, d->Wi, d->Hi, d->N, C, W * C, H * W * C, p.BW, p.BH, p.BNI);
     if (rc) return rc;
   }
-  rc = make_w_map(&maps.w, d->w, d->Ci, KH * KW, d->Co, BLOCK_N);
-  if (rc) return rc;
   // 64 -> 64, 3x3, stride 1, tiles of whole image rows (8 | W so that a row is a whole number of swizzle atoms)
   const int stage_bytes64 = (p.BH + 2) * p.BW * 128;
   int n_stages64 = (232448 - Tc64Cfg::SMEM_BYTES_FIXED) / stage_bytes64;
@@ -900,6 +1139,10 @@ extern "C" int combat_conv_tc(const combat_conv_tc_desc* d, void* stream) {
     rc = make_act_map(&maps.in[0], d->in, d->Ci, d->Wi, d->Hi, d->N, C, W * C, H * W * C, p.BW, p.BH + 2, 1);
     if (rc) return rc;
   }
+  // CTA pairs (cta_group::2) for every layer with >= 128 output channels: each CTA of a pair stages half of the weight tile
+  const bool pair = !use64 && BLOCK_N >= 128 && !getenv("COMBAT_NO_PAIR");
+  rc = make_w_map(&maps.w, d->w, d->Ci, KH * KW, d->Co, pair ? BLOCK_N / 2 : BLOCK_N);
+  if (rc) return rc;
   p.lbw = 0;
   while ((1 << p.lbw) < p.BW) ++p.lbw;
   p.lbh = 0;
@@ -909,9 +1152,24 @@ extern "C" int combat_conv_tc(const combat_conv_tc_desc* d, void* stream) {
   p.tiles_n = cdiv(p.N, p.BNI);
   p.total_tiles = p.n_classes * p.tiles_n * p.tiles_h * p.tiles_w * p.tiles_co;
   int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  if (pair) {
+    p.pair_mode = 1;
+    p.px_tiles_per_class = p.tiles_n * p.tiles_h * p.tiles_w;
+    p.pairs_per_class = (p.px_tiles_per_class + 1) / 2;
+    const int total_pairs = p.n_classes * p.pairs_per_class * p.tiles_co;
+    p.total_items = p.total_tiles = 2 * total_pairs;   // the kernels' tile loops run over work items v = 2 * pair + cta_rank
+    int nclusters = total_pairs < max_pair_clusters() ? total_pairs : max_pair_clusters();
+    if (d->stats && nclusters >= p.tiles_co) nclusters -= nclusters % p.tiles_co;  // a CTA's channel tile must never change
+    grid = 2 * nclusters;
+  }
   g_last_grid = grid;
   COMBAT_ARG(!d->stats || (d->Co <= 512 && !d->mask), 0);
   cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH_P(BN, MD)                                                                                                        \
+  {                                                                                                                             \
+    cudaFuncSetAttribute(conv_tc_pair_kernel<BN, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcPairCfg<BN>::SMEM_BYTES);  \
+    conv_tc_pair_kernel<BN, MD><<<grid, TC_THREADS, TcPairCfg<BN>::SMEM_BYTES, st>>>(maps, p);                                  \
+  }
 #define LAUNCH_C(BN, MD)                                                                                                  \
   {                                                                                                                       \
     cudaFuncSetAttribute(conv_tc_kernel<BN, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES);     \
@@ -937,10 +1195,16 @@ extern "C" int combat_conv_tc(const combat_conv_tc_desc* d, void* stream) {
     }
     COMBAT_RETURN_LAUNCH("conv_tc64");
   }
+  if (pair) {
+    if (BLOCK_N == 256) { if (mode == 1) LAUNCH_P(256, 1) else if (mode == 2) LAUNCH_P(256, 2) else LAUNCH_P(256, 0) }
+    else { if (mode == 1) LAUNCH_P(128, 1) else if (mode == 2) LAUNCH_P(128, 2) else LAUNCH_P(128, 0) }
+    COMBAT_RETURN_LAUNCH("conv_tc_pair");
+  }
   if (BLOCK_N == 256) { if (mode == 1) LAUNCH_C(256, 1) else if (mode == 2) LAUNCH_C(256, 2) else LAUNCH_C(256, 0) }
   else if (BLOCK_N == 128) { if (mode == 1) LAUNCH_C(128, 1) else if (mode == 2) LAUNCH_C(128, 2) else LAUNCH_C(128, 0) }
   else { if (mode == 1) LAUNCH_C(64, 1) else if (mode == 2) LAUNCH_C(64, 2) else LAUNCH_C(64, 0) }
 #undef LAUNCH_C
+#undef LAUNCH_P
   COMBAT_RETURN_LAUNCH("conv_tc");
 }
 

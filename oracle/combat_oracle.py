@@ -46,16 +46,40 @@ import torch.nn.functional as F
 #   qg(t): a float32 forward tensor whose GRADIENT is stored in bf16 (pre-normalisation tensors, the residual stream)
 #   qw(w): a conv weight rounded for the tensor cores; its gradient accumulates in float32 (straight through)
 # --------------------------------------------------------------------------
-_QUANT = {"on": False}
+#   cj(t): a float32 conv output; identity, or -- `quantised(jitter=e)` -- multiplied by (1 + e * N(0,1)) element-wise from a
+#          PRIVATE generator: a model of float32 accumulation-order noise (the CUDA kernels sit 5e-7 .. 4e-6 from torch's conv
+#          on identical inputs, scripts/diag_bf16_layers.py).  Two runs of the SAME quantised algorithm that differ only by this
+#          jitter bound what any faithful bf16 implementation can agree to: a value within that noise of a rounding boundary
+#          rounds the other way, and a random-init network amplifies every flip layer by layer.
+_QUANT = {"on": False, "jitter": 0.0, "gen": None}
 
 
 class quantised:
+    def __init__(self, jitter: float = 0.0, seed: int = 1234):
+        self.jitter, self.seed = float(jitter), seed
+
     def __enter__(self):
-        self.prev = _QUANT["on"]
+        self.prev = dict(_QUANT)
         _QUANT["on"] = True
+        _QUANT["jitter"] = self.jitter
+        _QUANT["gen"] = torch.Generator().manual_seed(self.seed) if self.jitter else None
 
     def __exit__(self, *a):
-        _QUANT["on"] = self.prev
+        _QUANT.update(self.prev)
+
+
+class _CJ(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, t):
+        return t * (1.0 + _QUANT["jitter"] * torch.randn(t.shape, generator=_QUANT["gen"]))
+
+    @staticmethod
+    def backward(ctx, g):
+        return g * (1.0 + _QUANT["jitter"] * torch.randn(g.shape, generator=_QUANT["gen"]))
+
+
+def cj(t):
+    return _CJ.apply(t) if (_QUANT["on"] and _QUANT["jitter"]) else t
 
 
 def _r(t):
@@ -257,7 +281,7 @@ def gaussian_blur(img: torch.Tensor, sigma: float, ksize: int = 3) -> torch.Tens
 # --------------------------------------------------------------------------
 
 
-def unet_forward(p: dict, x: torch.Tensor, y: torch.Tensor | None = None, num_classes: int | None = None):
+def unet_forward(p: dict, x: torch.Tensor, y: torch.Tensor | None = None, num_classes: int | None = None, taps: dict | None = None):
     """UnetGenerator.forward (networks/models.py:318-341) and, when `y` is given,
     CUnetGeneratorv1.forward (networks/models.py:523-555).
 
@@ -273,7 +297,10 @@ def unet_forward(p: dict, x: torch.Tensor, y: torch.Tensor | None = None, num_cl
         return F.leaky_relu(t, 0.2)
 
     def conv(name, t, stride=1):
-        return F.conv2d(t, qw(p[name + ".weight"]), p[name + ".bias"], stride=stride, padding=1)
+        o = cj(F.conv2d(t, qw(p[name + ".weight"]), p[name + ".bias"], stride=stride, padding=1))
+        if taps is not None:  # layer-by-layer diagnostics (scripts/diag_bf16_layers.py): conv input and output of every layer
+            taps[name] = (t.detach(), o.detach())
+        return o
 
     def inorm(t):
         return F.instance_norm(qg(t), eps=1e-5)
@@ -316,18 +343,18 @@ def preact_resnet18_forward(p: dict, b: dict, x: torch.Tensor, training: bool):
     `p` = parameters, `b` = buffers (running stats; updated in place when training)."""
     # quantised(): bf16 conv weights and relu(bn(.)) tensors, float32 residual stream / pre-normalisation tensors whose
     # gradients are stored in bf16 (combat_b200/nets.py Classifier.forward / backward); the image stays float32
-    out = qg(F.conv2d(x, qw(p["conv1.weight"]), None, 1, 1))  # :77,93
+    out = qg(cj(F.conv2d(x, qw(p["conv1.weight"]), None, 1, 1)))  # :77,93
     in_planes = 64
     for li, (planes, stride0) in enumerate([(64, 1), (128, 2), (256, 2), (512, 2)], start=1):
         for bi, stride in enumerate([stride0, 1]):
             pre = "layer%d.%d." % (li, bi)
             o = qa(F.relu(_bn(p, b, pre + "bn1", out, training)))  # :32
             if stride != 1 or in_planes != planes:  # :26-29,33
-                sc = F.conv2d(o, qw(p[pre + "shortcut.0.weight"]), None, stride, 0)
+                sc = cj(F.conv2d(o, qw(p[pre + "shortcut.0.weight"]), None, stride, 0))
             else:
                 sc = out
-            o = qg(F.conv2d(o, qw(p[pre + "conv1.weight"]), None, stride, 1))  # :34
-            o = F.conv2d(qa(F.relu(_bn(p, b, pre + "bn2", o, training))), qw(p[pre + "conv2.weight"]), None, 1, 1)  # :35
+            o = qg(cj(F.conv2d(o, qw(p[pre + "conv1.weight"]), None, stride, 1)))  # :34
+            o = cj(F.conv2d(qa(F.relu(_bn(p, b, pre + "bn2", o, training))), qw(p[pre + "conv2.weight"]), None, 1, 1))  # :35
             out = qg(o + sc)  # :39
             in_planes = planes
     out = F.avg_pool2d(out, 4)  # :99

@@ -233,6 +233,13 @@ TC_CASES = [
     (5, 64, 64, 16, 3, 1, 1),     # resident-filter / row-reuse kernel, tile = 8 rows of 16
     (300, 64, 64, 32, 3, 1, 1),   # same kernel, more tiles than SMs (persistent loop, pipeline wrap-around)
     (2, 64, 64, 24, 3, 1, 1),     # 8 | W but H not a multiple of the tile height
+    # CTA-pair kernels (cta_group::2, Co >= 128) and the shapes bench.py actually runs
+    (5, 256, 256, 8, 3, 1, 1),    # 3 pixel tiles: the last pair's second half is padding
+    (9, 128, 384, 8, 3, 1, 1),    # three 128-wide channel tiles per pixel-tile pair
+    (512, 64, 64, 32, 3, 1, 1),   # layer1 at the benchmark batch
+    (1024, 256, 256, 8, 3, 1, 1),  # the batched [x ; x_bd] forward: 256-wide tiles, 512 tiles on 74 clusters
+    (512, 128, 256, 16, 3, 2, 1),  # stride 2 at the benchmark batch (parity views; dgrad = 4 parity classes, paired per class)
+    (512, 256, 512, 8, 1, 2, 0),   # 1x1 stride-2 shortcut: dgrad classes without taps
 ]
 
 
