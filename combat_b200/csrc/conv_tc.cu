@@ -595,7 +595,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           const int cn = nt * p.BNI;
           const int wtap = p.taps.wtap[cls][t];
           for (int kc = 0; kc < p.kchunks; ++kc) {
+            const long long t0 = p.dbg ? clock64() : 0;
             mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (p.dbg) p.dbg[blockIdx.x * 8 + 0] += clock64() - t0;   // producer waiting for a free slot
             uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
             uint8_t* sb = sa + Cfg::A_BYTES;
             mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
@@ -614,16 +616,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      const long long tstart = p.dbg ? clock64() : 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        if (p.dbg) p.dbg[blockIdx.x * 8 + 3] = clock64() - tstart;  // (time up to the start of the last tile)
         int cls, nt, ht, wt, cot;
         decode_tile(p, tile, cls, nt, ht, wt, cot);
         const int kiters = p.taps.ntaps[cls] * p.kchunks;
         if (kiters == 0) continue;
+        long long t0 = p.dbg ? clock64() : 0;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        if (p.dbg) p.dbg[blockIdx.x * 8 + 1] += clock64() - t0;     // MMA thread waiting for the epilogue (accumulator buffer)
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
         for (int it = 0; it < kiters; ++it) {
+          t0 = p.dbg ? clock64() : 0;
           mbar_wait(&full_bar[stage], phase);
+          if (p.dbg) p.dbg[blockIdx.x * 8 + 2] += clock64() - t0;   // MMA thread waiting for operands (TMA)
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t sb = sa + Cfg::A_BYTES;
@@ -723,7 +731,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           const int cn = nt * p.BNI;
           const int wtap = p.taps.wtap[cls][t];
           for (int kc = 0; kc < p.kchunks; ++kc) {
+            const long long t0 = p.dbg ? clock64() : 0;
             mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (p.dbg) p.dbg[blockIdx.x * 8 + 0] += clock64() - t0;   // producer waiting for a free slot
             uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
             uint8_t* sb = sa + Cfg::A_BYTES;
             const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
@@ -743,16 +753,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      const long long tstart = p.dbg ? clock64() : 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        if (p.dbg) p.dbg[blockIdx.x * 8 + 3] = clock64() - tstart;  // (time up to the start of the last tile)
         int cls, nt, ht, wt, cot;
         decode_tile(p, tile, cls, nt, ht, wt, cot);
         const int kiters = p.taps.ntaps[cls] * p.kchunks;
         if (kiters == 0) continue;
+        long long t0 = p.dbg ? clock64() : 0;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        if (p.dbg) p.dbg[blockIdx.x * 8 + 1] += clock64() - t0;     // MMA thread waiting for the epilogue (accumulator buffer)
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
         for (int it = 0; it < kiters; ++it) {
+          t0 = p.dbg ? clock64() : 0;
           mbar_wait(&full_bar[stage], phase);
+          if (p.dbg) p.dbg[blockIdx.x * 8 + 2] += clock64() - t0;   // MMA thread waiting for operands (TMA)
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t sb = sa + Cfg::A_BYTES;
@@ -1139,8 +1155,11 @@ extern "C" int combat_conv_tc(const combat_conv_tc_desc* d, void* stream) {
     rc = make_act_map(&maps.in[0], d->in, d->Ci, d->Wi, d->Hi, d->N, C, W * C, H * W * C, p.BW, p.BH + 2, 1);
     if (rc) return rc;
   }
-  // CTA pairs (cta_group::2) for every layer with >= 128 output channels: each CTA of a pair stages half of the weight tile
-  const bool pair = !use64 && BLOCK_N >= 128 && !getenv("COMBAT_NO_PAIR");
+  // CTA pairs (cta_group::2): each CTA of a pair stages half of the weight tile.  Measured inside the step (B200, batch 512):
+  // 256-wide tiles gain 13-15 % (256->256 @8x8 fwd 1042 -> 1204 TFLOP/s, 512->512 @4x4 1107 -> 1272, their input gradients 900 ->
+  // 1005); 128-wide tiles LOSE 6-9 % (half-size MMAs, twice the cluster-scope barrier round trips per byte) and keep the
+  // single-CTA kernel unless COMBAT_PAIR128 is set.
+  const bool pair = !use64 && (BLOCK_N == 256 || (BLOCK_N == 128 && getenv("COMBAT_PAIR128"))) && !getenv("COMBAT_NO_PAIR");
   rc = make_w_map(&maps.w, d->w, d->Ci, KH * KW, d->Co, pair ? BLOCK_N / 2 : BLOCK_N);
   if (rc) return rc;
   p.lbw = 0;

@@ -157,6 +157,32 @@ def make_plan_multilabel(targets_host, opt, with_metrics=True) -> StepPlan:
                     sigmas[0], taps_c, (float(taps_rows[0, 0]), float(taps_rows[0, 1])), taps_rows, sigmas, tf=tf)
 
 
+def make_plan_victim(targets_host, poisoned_host, opt) -> StepPlan:
+    """train_victim.py:113-130: the poisoned rows come from the DATASET's flags (utils/dataloader_cleanbd.py:124-145), not from
+    an RNG draw; the C-step blur sigma is drawn only when the batch holds a poisoned row (:128-129), then T1 (:131).
+    `ntrg_ind = (poisoned is False).nonzero()` at :121 raises AttributeError as shipped (`poisoned is False` is a Python bool);
+    the evident intent -- the rows whose flag is False -- is what is built here.  poisoned_host=None: train_clean_classifier.py
+    (:88-104), no poisoned rows, no sigma draw."""
+    y = np.asarray(targets_host, dtype=np.int64)
+    B = y.shape[0]
+    pz = np.zeros(B, dtype=bool) if poisoned_host is None else np.asarray(poisoned_host).astype(bool)
+    bd = create_targets_bd_np(y, opt).astype(np.int64)
+    trg, ntrg = np.nonzero(pz)[0], np.nonzero(~pz)[0]
+    num_bd = int(trg.shape[0])
+    sigma_c, taps_c = None, (1.0, 0.0)
+    if num_bd > 0:
+        sigma_c = torch.empty(1).uniform_(opt.sigma[0], opt.sigma[1]).item()
+        taps_c = ops.gaussian_taps(sigma_c)
+    tf = None
+    if _tf_on(opt):
+        tf = np.zeros((5, B, TF_W), dtype=np.float32)
+        tf[:, :, 2] = 1.0
+        tf[TF_SLOT["T1"]] = draw_tf_params(B, opt)
+    perm = np.concatenate([trg, ntrg]).astype(np.int32)
+    total_y = np.concatenate([bd[trg], y[ntrg]]).astype(np.int64)
+    return StepPlan(perm, num_bd, trg, ntrg, bd, total_y, sigma_c, 1.0, taps_c, (1.0, 0.0), tf=tf)
+
+
 class AlternatedStep:
     """Owns netC / clean_model / netG / netF and runs alternated iterations on one GPU.
 
@@ -332,7 +358,7 @@ class AlternatedStep:
     #   C: netG SGD, frequency-detector metric leg
     # Single GPU: one CUDA graph over A+B+C.  Data parallel: one graph per phase, the NCCL all-reduces are issued between
     # the replays on the same stream (no collective inside a captured graph).
-    def _phase_a(self, b, st):
+    def _phase_a(self, b, st, save_g=True, with_g=True):
         o = self.opt
         x = b["x"]
         losses, counts = b["losses"], b["counts"]
@@ -344,8 +370,11 @@ class AlternatedStep:
             total_x = ops.poison_blend_fwd(x, noise_c, None, 0, o.noise_rate, None, taps_dev=b["taps_c"],
                                            num_bd_dev=b["num_bd"])                            # first num_bd rows, :178
             noise_raw = ctxG = noise = None
+        elif not with_g:  # train_clean_classifier.py: no generator, the batch as it is
+            noise_raw = ctxG = noise = None
+            total_x = x
         else:
-            noise_raw, ctxG = self.netG.forward(x, None, save=True)                          # :189 and :223, once
+            noise_raw, ctxG = self.netG.forward(x, None, save=save_g)                        # :189 and :223, once
             noise = ops.plane_op(noise_raw, "lowfreq", keep=self.keep)                      # :190-191 / :224
             total_x = ops.poison_blend_fwd(x, noise, b["perm"], 0, o.noise_rate, None, taps_dev=b["taps_c"],
                                            num_bd_dev=b["num_bd"])                            # :192-195
@@ -550,6 +579,59 @@ class AlternatedStep:
             dbg = self._launch(b, keep_debug)
         out = {"losses": b["losses"], "counts": b["counts"], "plan": plan}
         if dbg is not None:
+            out["debug"] = dbg
+        return out
+
+    # ------------------------------------------------------------ victim / clean-classifier training
+    def victim_step(self, x_dev, y_host, poisoned_host=None, plan: StepPlan | None = None, use_graph=False, keep_debug=False):
+        """One iteration of train_victim.py:110-140 (poisoned_host given: the dataset's per-sample flags, the frozen generator
+        builds the triggers) or of train_clean_classifier.py:88-104 (poisoned_host None and no generator): the C-step half of
+        the alternated step -- batch assembly, PostTensorTransform, netC train-mode forward / backward, SGD.
+        Returns {'losses': dev[8] (loss_ce at [0]), 'counts': dev[16] (correct predictions on total_targets at [0])}."""
+        if plan is None:
+            plan = make_plan_victim(y_host, poisoned_host, self.opt)
+        B = len(plan.perm)
+        b = self._ensure_bufs(B)
+        self._take_input(x_dev, b["x"])
+        self.upload_plan(y_host, plan)
+        with_g = self.netG is not None
+
+        def launch(st):
+            self._phase_a(b, st, save_g=False, with_g=with_g)
+            self._exchange_c()
+            self.netC.sgd_step(self.lr_C)
+
+        dbg = None
+        if use_graph and not keep_debug:
+            if b.get("vgraph") is None:
+                launch({})
+                torch.cuda.current_stream().synchronize()
+                b["vstate"] = {}
+                if self._parallel:   # no collective inside a captured graph: forward/backward graph, exchange, optimiser graph
+                    g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                    pool = torch.cuda.graph_pool_handle()
+                    with torch.cuda.graph(g1, pool=pool):
+                        self._phase_a(b, b["vstate"], save_g=False, with_g=with_g)
+                    with torch.cuda.graph(g2, pool=pool):
+                        self.netC.sgd_step(self.lr_C)
+                    b["vgraph"] = [g1, g2]
+                else:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        launch(b["vstate"])
+                    b["vgraph"] = [g]
+            else:
+                gs = b["vgraph"]
+                gs[0].replay()
+                if len(gs) > 1:
+                    self._exchange_c()
+                    gs[1].replay()
+                self.netC.bump_batches_tracked()
+        else:
+            dbg = {}
+            launch(dbg)
+        out = {"losses": b["losses"], "counts": b["counts"], "plan": plan}
+        if keep_debug:
             out["debug"] = dbg
         return out
 

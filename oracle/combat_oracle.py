@@ -680,6 +680,66 @@ def eval_batch(state: dict, x: torch.Tensor, y: torch.Tensor, opt) -> dict:
     return out
 
 
+def victim_train_step(netC_p, netC_b, netG_p, momC: dict, x: torch.Tensor, y: torch.Tensor, poisoned, opt) -> dict:
+    """One iteration of train_victim.py:110-140 (poisoned given: per-sample bool flags from the dataset) or of
+    train_clean_classifier.py:88-104 (poisoned None, netG_p None).  `(poisoned is False).nonzero()` at train_victim.py:121 raises
+    as shipped; the rows whose flag is False are taken.  RNG: one torch uniform for the blur when a poisoned row exists (:129),
+    then the transform draws (:131)."""
+    fwdC = CLASSIFIERS[opt.classifier]
+    out = {}
+    for t in netC_p.values():
+        t.requires_grad_(True)
+        t.grad = None
+    if poisoned is None:
+        total_x, total_y = x, y
+        out["num_bd"] = 0
+    else:
+        pz = torch.as_tensor(poisoned).bool()
+        bd_targets = create_targets_bd(y, opt.attack_mode, opt.target_label, opt.num_classes)
+        trg_ind, ntrg_ind = pz.nonzero()[:, 0], (~pz).nonzero()[:, 0]
+        out["num_bd"] = int(trg_ind.shape[0])
+        with torch.no_grad():
+            x_sel = x[trg_ind]
+            if out["num_bd"] > 0:
+                out["sigma"] = draw_sigma(*opt.sigma)
+                x_bd, _, _ = make_bd(netG_p, x_sel, opt, out["sigma"])
+            else:
+                x_bd = x_sel
+        total_x = torch.cat([x_bd, x[ntrg_ind]], dim=0)  # :130
+        total_y = torch.cat([bd_targets[trg_ind], y[ntrg_ind]], dim=0)  # :132
+    out["tf"] = tf_log = []
+    total_in = post_transform(total_x, opt, tf_log)  # :131
+    logits = fwdC(netC_p, netC_b, total_in, True)
+    loss = F.cross_entropy(logits, total_y)
+    loss.backward()
+    grads = {k: v.grad for k, v in netC_p.items()}
+    with torch.no_grad():
+        for t in netC_p.values():
+            t.requires_grad_(False)
+        sgd_nesterov_step(netC_p, grads, momC, opt.lr_C)
+    out.update(total_x=total_x.detach(), total_y=total_y, logits=logits.detach(), loss=float(loss.detach()),
+               n_correct=int((torch.argmax(logits, 1) == total_y).sum()), grads={k: g.clone() for k, g in grads.items()})
+    return out
+
+
+def victim_eval_batch(netC_p, netC_b, netG_p, x: torch.Tensor, y: torch.Tensor, opt) -> dict:
+    """One iteration of eval.py:115-141 (the stand-alone evaluator): clean accuracy, and on the gathered non-target rows the
+    benign accuracy and attack success of the triggered images.  RNG: one torch uniform per batch (GaussianBlur, :131)."""
+    fwdC = CLASSIFIERS[opt.classifier]
+    am = lambda t: torch.argmax(t, dim=1)
+    with torch.no_grad():
+        preds_clean = fwdC(netC_p, netC_b, x, False)  # :119
+        ntrg = (y != opt.target_label).nonzero()[:, 0]  # :125
+        x_sel, y_sel = x[ntrg], y[ntrg]
+        sigma = draw_sigma(*opt.sigma)
+        x_bd, _, _ = make_bd(netG_p, x_sel, opt, sigma)  # :128-131
+        bd_t = create_targets_bd(y_sel, opt.attack_mode, opt.target_label, opt.num_classes)
+        preds_bd = fwdC(netC_p, netC_b, x_bd, False)  # :133
+    return dict(sigma=sigma, ntrg=ntrg, x_bd=x_bd, preds_clean=preds_clean, preds_bd=preds_bd, n_clean=len(x), n_bd=len(ntrg),
+                clean_correct=int((am(preds_clean) == y).sum()), bd_ba=int((am(preds_bd) == y_sel).sum()),
+                bd_asr=int((am(preds_bd) == bd_t).sum()))
+
+
 # --------------------------------------------------------------------------
 # multilabel variant (train_generator_multilabel.py:160-242): conditional generator, class-chunked G-step
 # --------------------------------------------------------------------------

@@ -74,10 +74,14 @@ for name, Ci, Co, H in SHAPES:
         print("%-8s %-16s %8.1f us  %7.1f TFLOP/s" % (name, vn, us, flops / us / 1e6))
         if dbg is not None:
             torch.cuda.synchronize()
-            m = dbg.view(148, 8).double().mean(0) / (args.iters + NBUF)
-            tiles = N * H * H / 128 / 148
-            print("   per tile (cycles): producer wait-empty %.0f | mma wait-tempty %.0f wait-full %.0f total %.0f | epi wait-acc %.0f body %.0f"
-                  % tuple(float(v) / tiles for v in m[:6]))
+            dv = dbg.view(148, 8).double()
+            used = dv[:, 4] + dv[:, 5] > 0
+            m = dv[used].mean(0) / (args.iters + NBUF)
+            tiles = N * H * H / 128 * max(1, Co // 256 if Co % 256 == 0 else Co // 128 if Co % 128 == 0 else Co // 64) / max(1, int(used.sum()))
+            print("   %d CTAs, %.2f tiles per CTA; per tile (cycles): producer wait-empty %.0f | mma wait-tempty %.0f wait-full %.0f "
+                  "[mma loop total/launch %.0f] | epi wait-acc %.0f body %.0f"
+                  % ((int(used.sum()), tiles) + tuple(float(v) / tiles for v in m[:3]) + (float(dv[used][:, 3].mean()),)
+                     + tuple(float(v) / tiles for v in m[4:6])))
     if args.variant:
         continue
     # wgrad

@@ -92,3 +92,53 @@ def test_eval_api_reproduces_the_reference_fixture(golden, tmp_path):
     os.remove(opt.ckpt_path)
     best2 = tg.eval(netC, optC, schC, netG, optG, schG, netF, clean, batches, *best, w, 2, opt)
     assert best2 == best and not os.path.exists(opt.ckpt_path)
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_standalone_evaluator_vs_oracle(dtype, capsys):
+    """combat_b200.eval (reference eval.py:83-152): get_model / eval on three batches against the oracle's gathered-sub-batch
+    restatement; all2one and all2all targets."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from combat_b200 import config
+    from combat_b200 import eval as ev
+    for attack in ("all2one", "all2all"):
+        opt = config.get_arguments().parse_args(["--device", "cuda", "--dtype", dtype, "--attack_mode", attack])
+        opt.input_height = opt.input_width = 32
+        opt.input_channel = 3
+        torch.manual_seed(8)
+        netC, netG = ev.get_model(opt)
+        sdC = {k: v.detach().cpu().clone() for k, v in netC.state_dict().items()}
+        sdG = {k: v.detach().cpu().clone() for k, v in netG.state_dict().items()}
+        pC, bC = O.split_state(sdC)
+        oopt = O.default_opt(attack_mode=attack)
+        g = torch.Generator().manual_seed(2)
+        batches = [(torch.rand(40, 3, 32, 32, generator=g) * 2 - 1, torch.randint(0, 10, (40,), generator=g)) for _ in range(3)]
+        torch.manual_seed(50)
+        refs = [O.victim_eval_batch(pC, bC, sdG, x, y, oopt) for x, y in batches]
+        torch.manual_seed(50)
+
+        class W:
+            def add_scalars(self, tag, d, step):
+                self.last = (tag, d)
+
+        w = W()
+        acc = ev.eval(netC, netG, batches, w, opt)
+        n, nb = sum(r["n_clean"] for r in refs), sum(r["n_bd"] for r in refs)
+        want = (sum(r["clean_correct"] for r in refs) * 100.0 / n, sum(r["bd_ba"] for r in refs) * 100.0 / nb,
+                sum(r["bd_asr"] for r in refs) * 100.0 / nb)
+        slack = (0 if dtype == "fp32" else 3)   # bf16 logits of a random-init net flip a few near-tied argmaxes
+        for got, ref, q in zip(acc, want, (100.0 / n, 100.0 / nb, 100.0 / nb)):
+            assert abs(got - ref) <= slack * q + 1e-9, (attack, acc, want)
+        assert w.last[0] == "Test Accuracy" and set(w.last[1]) == {"Clean", "Bd BA", "Bd ASR"}
+        # tensors of one batch, same sigma
+        torch.manual_seed(51)
+        r = O.victim_eval_batch(pC, bC, sdG, *batches[0], oopt)
+        torch.manual_seed(51)
+        _, nbd, d = ev.eval_batch(netC, netG, *batches[0], opt)
+        assert nbd == r["n_bd"] and d["sigma"] == r["sigma"]
+        nt = r["ntrg"].cuda()
+        tol = 2e-4 if dtype == "fp32" else 6e-2
+        assert rel(d["preds_clean"], r["preds_clean"]) < tol and rel(d["preds_bd"][nt], r["preds_bd"]) < tol
+        assert rel(d["x_bd"][nt], r["x_bd"]) < (1e-5 if dtype == "fp32" else 3e-2)
+    assert "Clean Acc" in capsys.readouterr().out
