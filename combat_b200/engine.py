@@ -220,6 +220,8 @@ class AlternatedStep:
         self.launches_per_step = 0  # kernels of this library launched by one iteration (counted on the last eager/capture pass)
         self._bufs = None           # buffers of the batch size used last
         self._bufs_by_B = {}        # batch size -> buffers + captured graphs (train and eval) + ring of plan slots
+        self._comm = None           # communication stream of the data-parallel exchanges
+        self._comm_done = None
         self._copy_stream = None   # side stream + staging buffers of prefetch()
         self._stage = {}
         self._stage_free = None
@@ -352,12 +354,15 @@ class AlternatedStep:
         s["ev"].record(torch.cuda.current_stream(self.device))
 
     # ------------------------------------------------------------ the step
-    # The iteration is three launch phases separated by the data-parallel exchange points (combat_b200.parallel):
-    #   A: generator forward, C-step forward + backward            -> mean of netC gradients and BatchNorm buffers
-    #   B: netC SGD, metric forwards, G-step forward + backward     -> mean of netG gradients
-    #   C: netG SGD, frequency-detector metric leg
-    # Single GPU: one CUDA graph over A+B+C.  Data parallel: one graph per phase, the NCCL all-reduces are issued between
-    # the replays on the same stream (no collective inside a captured graph).
+    # The iteration is five launch phases; the data-parallel exchanges (combat_b200.parallel) run on a communication stream
+    # BETWEEN them, overlapped with the phase that does not need their result:
+    #   A : generator forward, C-step forward + backward            -> all-reduce(netC gradients, BatchNorm buffers) starts
+    #   B1: trigger batch, clean_model forward + backward             (independent of the netC update: hides that all-reduce)
+    #   B2: netC SGD, netC metric/backdoor forward + backward, generator backward   -> all-reduce(netG gradients) starts
+    #   C1: frequency-detector metric leg                             (hides part of it)
+    #   C2: netG SGD
+    # Single GPU: one CUDA graph over A+B1+B2+C1+C2 (same launches, same order).  Data parallel: one graph per phase; no
+    # collective inside a captured graph (it hung under torch 2.11 / NCCL 2.28.9).
     def _phase_a(self, b, st, save_g=True, with_g=True):
         o = self.opt
         x = b["x"]
@@ -385,18 +390,22 @@ class AlternatedStep:
         self.netC.backward(ctxC, dlog, need_wgrad=True, need_dx=False)                       # :211
         st.update(noise_raw=noise_raw, ctxG=ctxG, noise=noise, total_x=total_x, total_in=total_in, logits_c=logits_c)
 
-    def _phase_b(self, b, st):
+    # Phase B is split at the point where the AVERAGED netC gradient is first needed: B1 (trigger batch x_bd, MSE terms, the
+    # clean_model forward / backward) does not depend on the C-step update and runs while the netC all-reduce is in flight on the
+    # communication stream; B2 starts with the netC optimiser step.  Likewise C1 (frequency-detector metric leg) overlaps the
+    # netG all-reduce and C2 is the netG optimiser step.  Single GPU: the same launches in the same order, one graph.
+    def _phase_b1(self, b, st):
         o = self.opt
         x, y, B = b["x"], b["y"], b["B"]
         losses, counts = b["losses"], b["counts"]
         noise = st["noise"]
         numel = x.numel()
-        self.netC.sgd_step(self.lr_C)                                                        # :212
         if self.multilabel:                                                                  # multilabel :203-221
             noise_raw, ctxG = self.netG.forward(x, b["bd_targets"], save=True)
             noise = ops.plane_op(noise_raw, "lowfreq", keep=self.keep)
             st.update(noise_raw=noise_raw, noise=noise, ctxG=ctxG)
         batched = self.with_metrics and self.netC.fuse_eval and self.clean.fuse_eval
+        st["batched"] = batched
         if batched:
             # the metric forward on x (:214 / :227) and the forward on x_bd (:228 / :250) of each frozen-in-this-phase
             # classifier run as ONE eval-mode forward over [x ; x_bd]: per-sample independent, so every output is
@@ -409,15 +418,7 @@ class AlternatedStep:
             ops.sum_scale(b["sq_partial"], 1.0 / numel, out=losses[2:3])                     # :234
             # PostTensorTransform: netC sees [T3(x) ; T4(x_bd)] (:227-228), clean_model [T2(x) ; T5(x_bd)] (:214,:250) -- one
             # gather launch per network over the 2B rows with per-row parameters
-            tfC = b["tf"][TF_SLOT["T3"]:TF_SLOT["T4"] + 1].view(2 * B, TF_W) if self.tf_on else None
             tfK = b["tf"][TF_SLOT["T2"]:TF_SLOT["T5"] + 1].view(2 * B, TF_W) if self.tf_on else None
-            x2c = ops.post_transform_fwd(x2, tfC) if self.tf_on else x2
-            lg, ctx2 = self.netC.forward(x2c, train=False, save=True)
-            pred_clean, pred_bd = lg[:B], lg[B:]
-            ops.cross_entropy(pred_clean, y, 1.0, False, loss_out=losses[5:6], counts_out=counts[4:6])
-            _, dl1, _ = ops.cross_entropy(pred_bd, b["bd_targets"], 1.0, True, loss_out=losses[1:2], counts_out=counts[6:8])
-            g1 = self.netC.backward(self.netC.slice_ctx(ctx2, B, 2 * B), dl1, need_wgrad=False, need_dx=True)
-            del ctx2
             x2k = ops.post_transform_fwd(x2, tfK) if self.tf_on else x2
             lgc, ctx2 = self.clean.forward(x2k, train=False, save=True)
             clean_preds, cm_preds = lgc[:B], lgc[B:]
@@ -426,7 +427,7 @@ class AlternatedStep:
                                           loss_out=losses[3:4], counts_out=counts[8:10])      # :251,266-267
             g2 = self.clean.backward(self.clean.slice_ctx(ctx2, B, 2 * B), dl2, need_wgrad=False, need_dx=True)
             del ctx2
-            st.update(clean_preds=clean_preds, pred_clean=pred_clean)
+            st.update(clean_preds=clean_preds)
         else:
             tfp = (lambda name, t: ops.post_transform_fwd(t, b["tf"][TF_SLOT[name]])) if self.tf_on else (lambda name, t: t)
             if self.with_metrics:
@@ -436,6 +437,35 @@ class AlternatedStep:
             x_bd = ops.poison_blend_fwd(x, noise, None, B, o.noise_rate, None, sq_partial=b["sq_partial"],
                                         taps_dev=b["taps_g"], taps_rows=b["taps_rows"])      # :225-226
             ops.sum_scale(b["sq_partial"], 1.0 / numel, out=losses[2:3])                     # :234
+            cm_preds, ctxK = self.clean.forward(tfp("T5", x_bd), train=False, save=True)     # :250
+            _, dl2, _ = ops.cross_entropy(cm_preds, y, o.clean_model_weight, True, targets2=b["bd_targets"],
+                                          loss_out=losses[3:4], counts_out=counts[8:10])      # :251,266-267
+            g2 = self.clean.backward(ctxK, dl2, need_wgrad=False, need_dx=True)
+            del ctxK
+        if self.with_metrics and not self.multilabel:
+            ops.grad_l2(x, x_bd, losses[7:8], b["gl2_partial"])                              # :235-243 (logged only)
+        st.update(x_bd=x_bd, clean_model_preds=cm_preds, g2=g2)
+
+    def _phase_b2(self, b, st):
+        o = self.opt
+        x, y, B = b["x"], b["y"], b["B"]
+        losses, counts = b["losses"], b["counts"]
+        noise, x_bd, g2 = st["noise"], st["x_bd"], st["g2"]
+        numel = x.numel()
+        self.netC.sgd_step(self.lr_C)                                                        # :212
+        if st["batched"]:
+            x2 = b["x2"]
+            tfC = b["tf"][TF_SLOT["T3"]:TF_SLOT["T4"] + 1].view(2 * B, TF_W) if self.tf_on else None
+            x2c = ops.post_transform_fwd(x2, tfC) if self.tf_on else x2
+            lg, ctx2 = self.netC.forward(x2c, train=False, save=True)
+            pred_clean, pred_bd = lg[:B], lg[B:]
+            ops.cross_entropy(pred_clean, y, 1.0, False, loss_out=losses[5:6], counts_out=counts[4:6])
+            _, dl1, _ = ops.cross_entropy(pred_bd, b["bd_targets"], 1.0, True, loss_out=losses[1:2], counts_out=counts[6:8])
+            g1 = self.netC.backward(self.netC.slice_ctx(ctx2, B, 2 * B), dl1, need_wgrad=False, need_dx=True)
+            del ctx2
+            st.update(pred_clean=pred_clean)
+        else:
+            tfp = (lambda name, t: ops.post_transform_fwd(t, b["tf"][TF_SLOT[name]])) if self.tf_on else (lambda name, t: t)
             if self.with_metrics:
                 pred_clean, _ = self.netC.forward(tfp("T3", x), train=False, save=False)     # :227
                 ops.cross_entropy(pred_clean, y, 1.0, False, loss_out=losses[5:6], counts_out=counts[4:6])
@@ -444,13 +474,6 @@ class AlternatedStep:
             _, dl1, _ = ops.cross_entropy(pred_bd, b["bd_targets"], 1.0, True, loss_out=losses[1:2], counts_out=counts[6:8])
             g1 = self.netC.backward(ctxB, dl1, need_wgrad=False, need_dx=True)
             del ctxB
-            cm_preds, ctxK = self.clean.forward(tfp("T5", x_bd), train=False, save=True)     # :250
-            _, dl2, _ = ops.cross_entropy(cm_preds, y, o.clean_model_weight, True, targets2=b["bd_targets"],
-                                          loss_out=losses[3:4], counts_out=counts[8:10])      # :251,266-267
-            g2 = self.clean.backward(ctxK, dl2, need_wgrad=False, need_dx=True)
-            del ctxK
-        if self.with_metrics and not self.multilabel:
-            ops.grad_l2(x, x_bd, losses[7:8], b["gl2_partial"])                              # :235-243 (logged only)
         if self.tf_on:  # back through T4 / T5 to x_bd: both adjoints accumulate into one buffer
             gsum = ops.post_transform_bwd(g1, b["tf"][TF_SLOT["T4"]])
             ops.post_transform_bwd(g2, b["tf"][TF_SLOT["T5"]], out=gsum, accumulate=True)
@@ -460,26 +483,48 @@ class AlternatedStep:
         dnoise_raw = ops.plane_op(dnoise, "lowfreq", keep=self.keep)                          # P is symmetric
         self.netG.zero_grad()                                                                # :220
         self.netG.backward(st.pop("ctxG"), dnoise_raw)                                       # :254
-        st.update(x_bd=x_bd, pred_bd=pred_bd, clean_model_preds=cm_preds, g1=g1, g2=g2, dnoise=dnoise)
+        st.update(pred_bd=pred_bd, g1=g1, g2=g2, dnoise=dnoise)
 
-    def _phase_c(self, b, st):
+    def _phase_c1(self, b, st):
         losses, counts = b["losses"], b["counts"]
-        self.netG.sgd_step(self.lr_G)                                                        # :255
         if self.with_metrics and self.netF is not None:
             inputs_F = ops.plane_op(st["x_bd"], "dct", in_mode=2)                             # :245
             pred_F = self.netF.forward(inputs_F)                                              # :247
             ops.cross_entropy(pred_F, b["ones"], 1.0, False, loss_out=losses[6:7], counts_out=counts[10:12])
             st.update(inputs_F=inputs_F, pred_F=pred_F)
 
-    def _exchange_c(self):
-        if self.grad_hook is not None:
-            self.grad_hook("netC", self.netC.store.grad)
-        if self.buf_hook is not None:
-            self.buf_hook(self.netC.bufs)
+    def _phase_c2(self, b, st):
+        self.netG.sgd_step(self.lr_G)                                                        # :255
 
-    def _exchange_g(self):
-        if self.grad_hook is not None:
-            self.grad_hook("netG", self.netG.store.grad)
+    # ---- data-parallel exchange: started on a communication stream right after the backward that produced the gradients,
+    # joined just before the optimiser step that consumes them; the flat gradient goes out in COMM_BUCKETS contiguous buckets
+    COMM_BUCKETS = 4
+
+    def _exchange_start(self, which):
+        if not self._parallel:
+            return
+        main = torch.cuda.current_stream(self.device)
+        if self._comm is None:
+            self._comm = torch.cuda.Stream(device=self.device)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self._comm.wait_event(ev)
+        with torch.cuda.stream(self._comm):
+            if self.grad_hook is not None:
+                flat = self.netC.store.grad if which == "netC" else self.netG.store.grad
+                n = flat.numel()
+                step = (n + self.COMM_BUCKETS - 1) // self.COMM_BUCKETS
+                for lo in range(0, n, step):
+                    self.grad_hook(which, flat[lo:lo + step])
+            if which == "netC" and self.buf_hook is not None:
+                self.buf_hook(self.netC.bufs)
+            self._comm_done = torch.cuda.Event()
+            self._comm_done.record(self._comm)
+
+    def _exchange_join(self):
+        if self._parallel and self._comm_done is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._comm_done)
+            self._comm_done = None
 
     @property
     def _parallel(self):
@@ -491,10 +536,14 @@ class AlternatedStep:
         st = {}
         try:
             self._phase_a(b, st)
-            self._exchange_c()
-            self._phase_b(b, st)
-            self._exchange_g()
-            self._phase_c(b, st)
+            self._exchange_start("netC")
+            self._phase_b1(b, st)
+            self._exchange_join()
+            self._phase_b2(b, st)
+            self._exchange_start("netG")
+            self._phase_c1(b, st)
+            self._exchange_join()
+            self._phase_c2(b, st)
         finally:
             self.launches_per_step = launch_count() - n0
         return st if keep_debug else None
@@ -549,7 +598,7 @@ class AlternatedStep:
                 torch.cuda.current_stream().synchronize()
                 pool = torch.cuda.graph_pool_handle()
                 b["gstate"] = {}  # tensors handed from one captured phase to the next stay referenced here
-                phases = [self._phase_a, self._phase_b, self._phase_c]
+                phases = [self._phase_a, self._phase_b1, self._phase_b2, self._phase_c1, self._phase_c2]
                 if self._parallel:
                     graphs = []
                     for ph in phases:
@@ -568,12 +617,16 @@ class AlternatedStep:
                 graphs = b["graph"]
                 if len(graphs) == 1:
                     graphs[0].replay()
-                else:
+                else:   # A | all-reduce(netC) overlapped with B1 | B2 | all-reduce(netG) overlapped with C1 | C2
                     graphs[0].replay()
-                    self._exchange_c()
+                    self._exchange_start("netC")
                     graphs[1].replay()
-                    self._exchange_g()
+                    self._exchange_join()
                     graphs[2].replay()
+                    self._exchange_start("netG")
+                    graphs[3].replay()
+                    self._exchange_join()
+                    graphs[4].replay()
                 self.netC.bump_batches_tracked()   # the replayed C-step forward is one train-mode pass of every BatchNorm
         else:
             dbg = self._launch(b, keep_debug)
@@ -598,7 +651,8 @@ class AlternatedStep:
 
         def launch(st):
             self._phase_a(b, st, save_g=False, with_g=with_g)
-            self._exchange_c()
+            self._exchange_start("netC")
+            self._exchange_join()
             self.netC.sgd_step(self.lr_C)
 
         dbg = None
@@ -624,7 +678,8 @@ class AlternatedStep:
                 gs = b["vgraph"]
                 gs[0].replay()
                 if len(gs) > 1:
-                    self._exchange_c()
+                    self._exchange_start("netC")
+                    self._exchange_join()
                     gs[1].replay()
                 self.netC.bump_batches_tracked()
         else:
