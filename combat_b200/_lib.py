@@ -36,7 +36,8 @@ class ConvTcDesc(C.Structure):
                 ("N", i32), ("Hi", i32), ("Wi", i32), ("Ci", i32), ("Ho", i32), ("Wo", i32), ("Co", i32),
                 ("KH", i32), ("KW", i32), ("stride", i32), ("pad", i32), ("up", i32), ("out_f32", i32), ("res_f32", i32),
                 ("act", i32), ("post_scale", vp), ("post_shift", vp),
-                ("out2", vp), ("scale2", vp), ("shift2", vp), ("mask", vp), ("mask_scale", vp), ("post_add", vp)]
+                ("out2", vp), ("scale2", vp), ("shift2", vp), ("mask", vp), ("mask_scale", vp), ("post_add", vp),
+                ("in2", vp), ("w2", vp)]
 
 
 P = C.POINTER

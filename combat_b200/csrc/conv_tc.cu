@@ -184,7 +184,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
 
 // ---------------------------------------------------------------------------------------------- parameters
 #define TC_MAX_CLASSES 4
-#define TC_MAX_TAPS 9
+#define TC_MAX_TAPS 10  // 9 filter taps + the fused shortcut tap
 #define TILE_M 128
 #define KCHUNK 64  // bf16 elements per 128-byte swizzle row
 #define TC_EPI_WARPS 8
@@ -198,6 +198,7 @@ struct TcTaps {
   signed char dh[TC_MAX_CLASSES][TC_MAX_TAPS];
   signed char dw[TC_MAX_CLASSES][TC_MAX_TAPS];
   signed char wtap[TC_MAX_CLASSES][TC_MAX_TAPS];
+  signed char wsel[TC_MAX_CLASSES][TC_MAX_TAPS];  // 1: the tap's filter comes from the second weight map (fused shortcut)
   int cls_p[TC_MAX_CLASSES], cls_q[TC_MAX_CLASSES];
 };
 
@@ -231,8 +232,9 @@ struct TcParams {
 };
 
 struct TcMaps {
-  CUtensorMap in[4];  // parity views of the input (only [0] when unstrided)
+  CUtensorMap in[4];  // parity views of the input (only [0] when unstrided; [1] = the shortcut's gradient tensor when fused)
   CUtensorMap w;      // [Co][taps][Ci] as (Ci, taps, Co)
+  CUtensorMap w2;     // fused shortcut: [Co][1][Ci]
 };
 
 template <int BLOCK_N>
@@ -594,6 +596,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           const int ch = ht * p.BH + p.taps.dh[cls][t];
           const int cn = nt * p.BNI;
           const int wtap = p.taps.wtap[cls][t];
+          const CUtensorMap* wmap = p.taps.wsel[cls][t] ? &maps.w2 : &maps.w;
           for (int kc = 0; kc < p.kchunks; ++kc) {
             const long long t0 = p.dbg ? clock64() : 0;
             mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -602,7 +605,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             uint8_t* sb = sa + Cfg::A_BYTES;
             mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
             tma_load_4d(sa, amap, &full_bar[stage], kc * KCHUNK, cw, ch, cn);
-            tma_load_3d(sb, &maps.w, &full_bar[stage], kc * KCHUNK, wtap, cot * BLOCK_N);
+            tma_load_3d(sb, wmap, &full_bar[stage], kc * KCHUNK, wtap, cot * BLOCK_N);
             if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -730,6 +733,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           const int ch = ht * p.BH + p.taps.dh[cls][t];
           const int cn = nt * p.BNI;
           const int wtap = p.taps.wtap[cls][t];
+          const CUtensorMap* wmap = p.taps.wsel[cls][t] ? &maps.w2 : &maps.w;
           for (int kc = 0; kc < p.kchunks; ++kc) {
             const long long t0 = p.dbg ? clock64() : 0;
             mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -739,7 +743,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
             const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
             if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
             tma_load_4d_2sm(sa, amap, lead_full, kc * KCHUNK, cw, ch, cn);
-            tma_load_3d_2sm(sb, &maps.w, lead_full, kc * KCHUNK, wtap, cot * BLOCK_N + (int)rank * (BLOCK_N / 2));
+            tma_load_3d_2sm(sb, wmap, lead_full, kc * KCHUNK, wtap, cot * BLOCK_N + (int)rank * (BLOCK_N / 2));
             if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -1045,6 +1049,8 @@ extern "C" int combat_conv_tc(const combat_conv_tc_desc* d, void* stream) {
   COMBAT_ARG(!d->mask || (d->out && !d->out_f32 && !d->res_f32 && !(d->residual && d->post_add) && !d->out2 && !d->bias &&
                           !d->act && !d->post_scale), 0);
   COMBAT_ARG(d->mask || !d->post_add, 0);
+  COMBAT_ARG(!d->in2 == !d->w2, 0);
+  COMBAT_ARG(!d->in2 || (d->up == 2 && d->KH == 3 && d->pad == 1), 0);  // pad = k - 1 - pad of the forward conv (3x3, pad 1)
   TcParams p;
   memset(&p, 0, sizeof(p));
   TcMaps maps;
@@ -1138,11 +1144,23 @@ extern "C" int combat_conv_tc(const combat_conv_tc_desc* d, void* stream) {
             p.taps.wtap[cls][nt] = (signed char)(kh * KW + kw);
             ++nt;
           }
+        if (cls == 0 && d->in2) {  // fused 1x1 stride-2 shortcut gradient: dx[2a, 2b] += w2^T in2[a, b]
+          p.taps.view[cls][nt] = 1;
+          p.taps.dh[cls][nt] = 0;
+          p.taps.dw[cls][nt] = 0;
+          p.taps.wtap[cls][nt] = 0;
+          p.taps.wsel[cls][nt] = 1;
+          ++nt;
+        }
         p.taps.ntaps[cls] = nt;
       }
     const long long C = d->Ci, W = d->Wi, H = d->Hi;
     rc = make_act_map(&maps.in[0], d->in, d->Ci, d->Wi, d->Hi, d->N, C, W * C, H * W * C, p.BW, p.BH, p.BNI);
     if (rc) return rc;
+    if (d->in2) {
+      rc = make_act_map(&maps.in[1], d->in2, d->Ci, d->Wi, d->Hi, d->N, C, W * C, H * W * C, p.BW, p.BH, p.BNI);
+      if (rc) return rc;
+    }
   }
   // 64 -> 64, 3x3, stride 1, tiles of whole image rows (8 | W so that a row is a whole number of swizzle atoms)
   const int stage_bytes64 = (p.BH + 2) * p.BW * 128;
@@ -1162,6 +1180,10 @@ extern "C" int combat_conv_tc(const combat_conv_tc_desc* d, void* stream) {
   const bool pair = !use64 && (BLOCK_N == 256 || (BLOCK_N == 128 && getenv("COMBAT_PAIR128"))) && !getenv("COMBAT_NO_PAIR");
   rc = make_w_map(&maps.w, d->w, d->Ci, KH * KW, d->Co, pair ? BLOCK_N / 2 : BLOCK_N);
   if (rc) return rc;
+  if (d->in2) {
+    rc = make_w_map(&maps.w2, d->w2, d->Ci, 1, d->Co, pair ? BLOCK_N / 2 : BLOCK_N);
+    if (rc) return rc;
+  }
   p.lbw = 0;
   while ((1 << p.lbw) < p.BW) ++p.lbw;
   p.lbh = 0;

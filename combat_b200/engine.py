@@ -504,6 +504,12 @@ class AlternatedStep:
         if not self._parallel:
             return
         main = torch.cuda.current_stream(self.device)
+        if os.environ.get("COMBAT_DP_OVERLAP") == "0":   # A/B switch: exchange on the compute stream, nothing overlapped
+            if self.grad_hook is not None:
+                self.grad_hook(which, self.netC.store.grad if which == "netC" else self.netG.store.grad)
+            if which == "netC" and self.buf_hook is not None:
+                self.buf_hook(self.netC.bufs)
+            return
         if self._comm is None:
             self._comm = torch.cuda.Stream(device=self.device)
         ev = torch.cuda.Event()

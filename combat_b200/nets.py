@@ -154,6 +154,8 @@ class NetBase:
         # way (pure-write streams run at ~3.3 TB/s here) and the im2col pass costs more than the FMA work it removes.  Opt-in.
         self.tc_first = bool(os.environ.get("COMBAT_TC_FIRST"))
         self.tc_first_wgrad = not os.environ.get("COMBAT_NO_TC_FIRST_WGRAD")  # the weight gradient of those convs through im2col3
+        # the 1x1 stride-2 shortcut's input gradient as an extra tap of the block's 3x3 stride-2 input-gradient launch
+        self.fuse_shortcut_dgrad = not os.environ.get("COMBAT_NO_FUSE_SC")
         self._w64 = {}
         self.last_stats_nblk = 0
         self.convs: dict[str, ConvSpec] = {}
@@ -271,10 +273,13 @@ class NetBase:
                       pad=cs.pad, bias=self._bias(cs), residual=residual)
         return out
 
-    def conv_dgrad(self, dy, cs: ConvSpec, in_hw, residual=None, n_out_ch=None, mask=None, mask_scale=None, post_add=None):
+    def conv_dgrad(self, dy, cs: ConvSpec, in_hw, residual=None, n_out_ch=None, mask=None, mask_scale=None, post_add=None,
+                   shortcut=None):
         """dy: NHWC [N,Ho,Wo,Cout] -> dx NHWC [N,H,W,n_out_ch or Cin] (+ residual).
         mask/mask_scale/post_add: fused backward of the eval-mode relu(bn(.)) in front of this conv (tcgen05 path only):
-        dx = (mask > 0 ? (dgrad + residual) * mask_scale[c] : 0) + post_add."""
+        dx = (mask > 0 ? (dgrad + residual) * mask_scale[c] : 0) + post_add.
+        shortcut=(dy_sc, cs_sc): the block's 1x1 stride-2 shortcut conv reads the same input; its input gradient is one more
+        tap of this launch (same accumulator) instead of a launch of its own plus a residual read."""
         N, Ho, Wo, _ = dy.shape
         H, W = in_hw
         Cx = cs.Cin if n_out_ch is None else n_out_ch
@@ -282,12 +287,21 @@ class NetBase:
         padp = cs.k - 1 - cs.pad
         # the dgrad filter is stored [Cin][taps][Cout]: its first Cx rows ARE the filter of the first Cx input channels, so a
         # leading multiple-of-64 subset runs on the tensor cores as a conv with Cx output channels (stride-1 convs only)
+        fuse_sc = (shortcut is not None and self.fuse_shortcut_dgrad and self._tc_ok(cs) and self._tc_ok(shortcut[1]) and Cx == cs.Cin
+                   and cs.stride == 2 and cs.k == 3 and cs.pad == 1 and shortcut[1].k == 1 and shortcut[1].stride == 2
+                   and shortcut[1].Cin == cs.Cin and shortcut[1].Cout == cs.Cout and residual is None)
+        if shortcut is not None and not fuse_sc:   # unfused: the shortcut's input gradient first, added as the residual
+            residual_sc = self.conv_dgrad(shortcut[0], shortcut[1], in_hw, residual=residual)
+            return self.conv_dgrad(dy, cs, in_hw, residual=residual_sc, n_out_ch=n_out_ch, mask=mask, mask_scale=mask_scale,
+                                   post_add=post_add)
         if self._tc_ok(cs) and (Cx == cs.Cin or (Cx % 64 == 0 and Cx < cs.Cin and cs.stride == 1)):
+            extra = dict(in2=shortcut[0], w2=self._wptr(shortcut[1], True)) if fuse_sc else {}
             d = ops.conv_tc_desc(dy, self._wptr(cs, True), dx, N, Ho, Wo, cs.Cout, H, W, Cx, cs.k, cs.k, 1, padp,
-                                 cs.stride, residual=residual, mask=mask, mask_scale=mask_scale, post_add=post_add)
+                                 cs.stride, residual=residual, mask=mask, mask_scale=mask_scale, post_add=post_add, **extra)
             if lib.combat_conv_tc_supported(C.byref(d)):
-                _tc_launch(lambda: lib.combat_conv_tc(C.byref(d), ops._s()), "conv_tc(dgrad)", 2.0 * N * Ho * Wo * cs.Cout * Cx * cs.k * cs.k,
-                           _tag(N, H, W, cs))
+                fl = 2.0 * N * Ho * Wo * cs.Cout * Cx * (cs.k * cs.k + (1 if fuse_sc else 0))
+                _tc_launch(lambda: lib.combat_conv_tc(C.byref(d), ops._s()), "conv_tc(dgrad)", fl,
+                           _tag(N, H, W, cs) + (" +sc" if fuse_sc else ""))
                 return dx
         if mask is not None or post_add is not None:
             raise RuntimeError("fused BatchNorm backward epilogue needs the tcgen05 path")
@@ -630,8 +644,7 @@ class Classifier(NetBase):
             hw_in, hw_mid = o1.shape[1:3], o2.shape[1:3]
             d_c1 = self.conv_dgrad(dh, blk["conv2"], hw_mid, mask=o2, mask_scale=scale2)
             if "sc" in blk:
-                t = self.conv_dgrad(dh, blk["sc"], hw_in)
-                dh = self.conv_dgrad(d_c1, blk["conv1"], hw_in, residual=t, mask=o1, mask_scale=scale1)
+                dh = self.conv_dgrad(d_c1, blk["conv1"], hw_in, mask=o1, mask_scale=scale1, shortcut=(dh, blk["sc"]))
             else:
                 dh = self.conv_dgrad(d_c1, blk["conv1"], hw_in, mask=o1, mask_scale=scale1, post_add=dh)
         if need_dx:
@@ -661,13 +674,13 @@ class Classifier(NetBase):
                 d_c1, _ = self._bn_bwd(blk["bn2"], d_o2, c1, o2, st2, train, True, need_wgrad)
                 if need_wgrad:
                     self.conv_wgrad(o1, d_c1, blk["conv1"])
-                d_o1 = self.conv_dgrad(d_c1, blk["conv1"], hw_in)
                 if "sc" in blk:
                     if need_wgrad:
                         self.conv_wgrad(o1, dh, blk["sc"])
-                    d_o1 = self.conv_dgrad(dh, blk["sc"], hw_in, residual=d_o1)
+                    d_o1 = self.conv_dgrad(d_c1, blk["conv1"], hw_in, shortcut=(dh, blk["sc"]))
                     dadd = None
                 else:
+                    d_o1 = self.conv_dgrad(d_c1, blk["conv1"], hw_in)
                     dadd = dh
                 dh, _ = self._bn_bwd(blk["bn1"], d_o1, h_in, o1, st1, train, True, need_wgrad, dadd=dadd)
             else:
@@ -684,8 +697,7 @@ class Classifier(NetBase):
                     d_cs, _ = self._bn_bwd(blk["scbn"], dres, cs_, None, sts, train, False, need_wgrad)
                     if need_wgrad:
                         self.conv_wgrad(h_in, d_cs, blk["sc"])
-                    d_h = self.conv_dgrad(d_cs, blk["sc"], hw_in)
-                    dh = self.conv_dgrad(d_c1, blk["conv1"], hw_in, residual=d_h)
+                    dh = self.conv_dgrad(d_c1, blk["conv1"], hw_in, shortcut=(d_cs, blk["sc"]))
                 else:
                     dh = self.conv_dgrad(d_c1, blk["conv1"], hw_in, residual=dres)
         if not pre:

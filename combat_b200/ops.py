@@ -295,8 +295,9 @@ def wgrad_cout3(a_nhwc, dz_nchw, dw, db):
 
 def conv_tc_desc(x, w_ptr, out, N, Hi, Wi, Ci, Ho, Wo, Co, KH, KW, stride, pad, up, bias=None, residual=None, stats=None,
                  act=0, post_scale=None, post_shift=None, out2=None, scale2=None, shift2=None, mask=None, mask_scale=None,
-                 post_add=None):
+                 post_add=None, in2=None, w2=None):
     d = ConvTcDesc()
+    d.in2, d.w2 = _p(in2), w2
     d.act, d.post_scale, d.post_shift = act, _p(post_scale), _p(post_shift)
     d.out2, d.scale2, d.shift2 = _p(out2), _p(scale2), _p(shift2)
     d.mask, d.mask_scale, d.post_add = _p(mask), _p(mask_scale), _p(post_add)

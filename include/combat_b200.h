@@ -180,6 +180,12 @@ typedef struct {
   const void* mask;
   const float* mask_scale;
   const void* post_add;
+  /* optional second operand pair of an INPUT-GRADIENT launch of a stride-2 3x3 conv (up == 2): the gradient arriving through
+   * the block's 1x1 stride-2 shortcut conv (preact_resnet.py:26-29,33; resnet.py:25-29) -- in2: bf16 NHWC like `in` (same
+   * N, Hi, Wi, Ci), w2: that conv's input-gradient filter [Co][1][Ci] bf16.  Its single tap lands on the even/even output
+   * pixels, i.e. it is one more (tensor, filter) tap of parity class (0,0) accumulated in the same TMEM accumulator. */
+  const void* in2;
+  const void* w2;
 } combat_conv_tc_desc;
 int combat_conv_tc(const combat_conv_tc_desc* d_host, void* stream);
 int combat_conv_tc_wgrad(const combat_conv_tc_desc* d_host, const void* dy, float* dw_ohwi, void* stream);

@@ -601,3 +601,42 @@ def test_im2col3_tensor_core_conv(ops, stride, N, H):
     check(lib.combat_conv_tc(C.byref(d), ops._s()), "conv_tc")
     torch.cuda.synchronize()
     assert rel(out.permute(0, 3, 1, 2), y) < 2e-5
+
+
+@pytest.mark.parametrize("case", [(6, 64, 128, 32), (16, 128, 256, 16), (33, 256, 512, 8)])
+@pytest.mark.parametrize("masked", [False, True])
+def test_conv_tc_dgrad_with_fused_shortcut(ops, case, masked):
+    """Input gradient of a PreAct / ResNet block with a projection shortcut (preact_resnet.py:26-35): conv1 (3x3, stride 2) and
+    shortcut (1x1, stride 2) read the same tensor, so dx = conv1^T(d_c1) + shortcut^T(dh) -- ONE launch, the shortcut's
+    gradient being one more tap of output-parity class (0,0) from a second (tensor, filter) pair.  256- and 512-channel cases
+    run the CTA-pair kernel; `masked` adds the fused eval-mode relu(bn(.)) backward epilogue."""
+    import ctypes as C
+
+    from combat_b200._lib import check, lib
+    N, Ci, Co, H = case
+    g = torch.Generator().manual_seed(sum(case) + int(masked))
+    x = torch.randn(N, Ci, H, H, generator=g).bfloat16().float().requires_grad_(True)
+    w1 = (torch.randn(Co, Ci, 3, 3, generator=g) * 0.05).bfloat16().float()
+    wsc = (torch.randn(Co, Ci, 1, 1, generator=g) * 0.1).bfloat16().float()
+    y = F.conv2d(x, w1, None, 2, 1)
+    ysc = F.conv2d(x, wsc, None, 2, 0)
+    dy1 = torch.randn(y.shape, generator=g).bfloat16().float()
+    dy2 = torch.randn(y.shape, generator=g).bfloat16().float()
+    (y * dy1 + ysc * dy2).sum().backward()
+    want = x.grad
+    Ho = y.shape[2]
+    w1_d = dev(w1.flip(2, 3).permute(1, 2, 3, 0).bfloat16())      # [ci][kh'][kw'][co]
+    wsc_d = dev(wsc.permute(1, 2, 3, 0).bfloat16())               # [ci][1][1][co]
+    d1, d2 = dev(_nhwc(dy1).bfloat16()), dev(_nhwc(dy2).bfloat16())
+    dx = torch.empty(N, H, H, Ci, device="cuda", dtype=torch.bfloat16)
+    kw = {}
+    if masked:
+        mask = torch.randn(N, H, H, Ci, generator=g).bfloat16()
+        ms = torch.rand(Ci, generator=g) + 0.5
+        kw = dict(mask=dev(mask), mask_scale=dev(ms))
+        want = torch.where(mask.float().permute(0, 3, 1, 2) > 0, want * ms.view(1, -1, 1, 1), torch.zeros(()))
+    d = ops.conv_tc_desc(d1, w1_d.data_ptr(), dx, N, Ho, Ho, Co, H, H, Ci, 3, 3, 1, 1, 2, in2=d2, w2=wsc_d.data_ptr(), **kw)
+    assert lib.combat_conv_tc_supported(C.byref(d))
+    check(lib.combat_conv_tc(C.byref(d), ops._s()), "conv_tc dgrad + shortcut")
+    torch.cuda.synchronize()
+    assert rel(dx.float().permute(0, 3, 1, 2), want) < 6e-3
