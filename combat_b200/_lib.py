@@ -73,6 +73,7 @@ _SIGS = {
     "combat_bn_bwd_reduce": ([vp, vp, i32, vp, i32, i64, i32, vp, vp, vp, i32, P(i32), i32, vp], i32),
     "combat_bn_bwd_finalize": ([vp, i32, i32, vp, vp, vp], i32),
     "combat_bn_bwd_apply": ([vp, vp, i32, vp, vp, vp, vp, i32, i64, i32, vp, vp, vp, vp, vp, vp, i32, vp], i32),
+    "combat_bn_bwd_fused": ([vp, vp, i32, vp, vp, vp, vp, i32, i64, i32, vp, vp, vp, vp, i32, vp, vp, i32, vp], i32),
     "combat_instnorm_fwd": ([vp, i32, vp, vp, i32, i32, i32, i32, f32, f32, i32, vp, vp, vp], i32),
     "combat_instnorm_bwd": ([vp, vp, vp, i32, vp, i32, i32, i32, i32, f32, i32, vp, vp, vp], i32),
     "combat_upsample2x_act": ([vp, vp, i32, i32, i32, i32, i32, f32, vp], i32),

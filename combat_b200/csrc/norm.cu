@@ -5,6 +5,8 @@
 //   nn.Upsample(bilinear, x2)        networks/models.py:274
 //   AvgPool2d(4) + Linear            classifier_models/preact_resnet.py:99-101 ; resnet.py:95-97
 //   MaxPool2d(2), ELU+BN(eval)       defenses/frequency_based/model.py:13-44
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 // ---- two adjacent channels per thread
@@ -395,6 +397,127 @@ extern "C" int combat_bn_finalize(const float* partial, int nblk, long long R, i
   COMBAT_RETURN_LAUNCH("bn_finalize");
 }
 
+// ---- train-mode BatchNorm backward in ONE cooperative launch: column reduction -> grid sync -> per-channel finalize -> grid
+// sync -> elementwise apply.  Replaces three launches (bn_bwd_reduce / _finalize / _apply) per BatchNorm of the C-step
+// backward; the second pass over dy / x / y is served from the 126 MB L2 for every layer but the first stage's.
+// Geometry: 256 threads viewed as (32, 8) in the reduction and flat in the apply phase; the grid is exactly the number of
+// co-resident CTAs (cooperative launch), every phase strides over its own virtual blocks.
+template <typename TX, typename T>
+__global__ void __launch_bounds__(256) bn_bwd_fused_k(const T* __restrict__ dy, const TX* __restrict__ x, const T* __restrict__ y,
+                                                      const T* __restrict__ dadd, T* __restrict__ dx, T* __restrict__ dres,
+                                                      long long R, int C, long long rows_per_block, int nblk,
+                                                      const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                      const float* __restrict__ invstd, float* __restrict__ partial,
+                                                      float* __restrict__ dgamma, float* __restrict__ dbeta, int relu) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  __shared__ float2 sa[CR_TY][CR_TX], sb[CR_TY][CR_TX];
+  // ---- phase 1: partial sums of dyh and dyh * xhat per (row block, channel)
+  const int ngroups = (C + CR_CPB - 1) / CR_CPB;
+  for (int vb = blockIdx.x; vb < nblk * ngroups; vb += gridDim.x) {
+    const int bx = vb % nblk, by = vb / nblk;
+    const int c = 2 * (by * CR_TX + tx);
+    const long long r0 = (long long)bx * rows_per_block;
+    long long r1 = r0 + rows_per_block;
+    if (r1 > R) r1 = R;
+    float2 s1 = {0.f, 0.f}, s2 = {0.f, 0.f};
+    if (c < C) {
+      const float m0 = mean[c], m1 = mean[c + 1], i0 = invstd[c], i1 = invstd[c + 1];
+      for (long long r = r0 + ty; r < r1; r += CR_TY) {
+        float2 g = ld2<T>(dy + r * C + c);
+        if (relu) {
+          const float2 yy = ld2<T>(y + r * C + c);
+          if (!(yy.x > 0.f)) g.x = 0.f;
+          if (!(yy.y > 0.f)) g.y = 0.f;
+        }
+        const float2 v = ld2<TX>(x + r * C + c);
+        s1.x += g.x; s1.y += g.y;
+        s2.x = fmaf(g.x, (v.x - m0) * i0, s2.x);
+        s2.y = fmaf(g.y, (v.y - m1) * i1, s2.y);
+      }
+    }
+    sa[ty][tx] = s1;
+    sb[ty][tx] = s2;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+      for (int yy = 1; yy < CR_TY; ++yy) {
+        const float2 u = sa[yy][tx], v = sb[yy][tx];
+        s1.x += u.x; s1.y += u.y; s2.x += v.x; s2.y += v.y;
+      }
+      float* p0 = partial + ((long long)bx * 2) * C + c;
+      p0[0] = s1.x; p0[1] = s1.y;
+      p0[C] = s2.x; p0[C + 1] = s2.y;
+    }
+    __syncthreads();
+  }
+  grid.sync();
+  // ---- phase 2: one CTA per channel sums the partial blocks in double precision
+  __shared__ double da[8], db_[8];
+  for (int c = blockIdx.x; c < C; c += gridDim.x) {
+    double a = 0.0, b = 0.0;
+    for (int k = threadIdx.x; k < nblk; k += 256) {
+      a += (double)partial[((long long)k * 2) * C + c];
+      b += (double)partial[((long long)k * 2 + 1) * C + c];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (tx == 0) { da[ty] = a; db_[ty] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < 8; ++w) { a += da[w]; b += db_[w]; }
+      dbeta[c] = (float)a;
+      dgamma[c] = (float)b;
+    }
+    __syncthreads();
+  }
+  grid.sync();
+  // ---- phase 3: dx = gamma * invstd * (dyh - dbeta / R - xhat * dgamma / R) (+ dadd), 8 channels per thread
+  const float invR = 1.f / (float)R;
+  const long long n8 = R * C / 8;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n8; i += (long long)gridDim.x * 256) {
+    const long long e = i * 8;
+    const int c = (int)(e % C);
+    float g[8], o[8], v[8], mu[8], is[8], dg[8], dbv[8], gm[8];
+    ld8<T>(dy + e, g);
+    if (relu) {
+      float yy[8];
+      ld8<T>(y + e, yy);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (!(yy[j] > 0.f)) g[j] = 0.f;
+    }
+    if (dres) st8<T>(dres + e, g);
+    ld8<TX>(x + e, v);
+    ld8<float>(mean + c, mu);
+    ld8<float>(invstd + c, is);
+    ld8<float>(dgamma + c, dg);
+    ld8<float>(dbeta + c, dbv);
+    if (gamma) {
+      ld8<float>(gamma + c, gm);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gm[j] = 1.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (v[j] - mu[j]) * is[j];
+      o[j] = gm[j] * is[j] * (g[j] - dbv[j] * invR - xh * dg[j] * invR);
+    }
+    if (dadd) {
+      float a[8];
+      ld8<T>(dadd + e, a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += a[j];
+    }
+    st8<T>(dx + e, o);
+  }
+}
+
+
 // eval-mode scale/shift of EVERY BatchNorm of a network in one launch: table4[i] = (gamma, beta, mean, var) indices of
 // flattened channel i into the flat parameter / running-stat buffers
 __global__ void bn_eval_affine_k(const float* __restrict__ params, const float* __restrict__ bufs, const int4* __restrict__ table,
@@ -473,6 +596,34 @@ extern "C" int combat_bn_bwd_apply(const void* dy, const void* x, int x_dtype, c
                                  (const T*)dy, (const TX*)x, (const T*)y, (const T*)dadd, (T*)dx, (T*)dres, n2, R, C, gamma,
                                  mean, invstd, dgamma, dbeta, eval_scale, relu);)
   COMBAT_RETURN_LAUNCH("bn_bwd_apply");
+}
+
+extern "C" int combat_bn_bwd_fused(const void* dy, const void* x, int x_dtype, const void* y, const void* dadd, void* dx,
+                                   void* dres, int dtype, long long R, int C, const float* gamma, const float* mean,
+                                   const float* invstd, float* partial, int max_blocks, float* dgamma, float* dbeta, int relu,
+                                   void* stream) {
+  COMBAT_ARG(dy && x && dx && partial && mean && invstd && dgamma && dbeta, 0);
+  COMBAT_ARG(!relu || y, 2);
+  COMBAT_ARG((C % 8) == 0 && R > 0, 9);
+  long long rpb;
+  int nblk = cr_plan(R, max_blocks, &rpb);
+  int relu_ = relu;
+  void* args[] = {(void*)&dy, (void*)&x, (void*)&y, (void*)&dadd, (void*)&dx, (void*)&dres, (void*)&R, (void*)&C, (void*)&rpb,
+                  (void*)&nblk, (void*)&gamma, (void*)&mean, (void*)&invstd, (void*)&partial, (void*)&dgamma, (void*)&dbeta,
+                  (void*)&relu_};
+  cudaError_t e = cudaErrorInvalidValue;
+  DISPATCH_2(x_dtype, dtype, {
+    static int resident = 0;   // co-resident CTAs of this instantiation (cooperative launches must fit in one wave)
+    if (!resident) resident = resident_ctas(bn_bwd_fused_k<TX, T>, 256);
+    if (resident <= 0) resident = 148;
+    e = cudaLaunchCooperativeKernel((const void*)bn_bwd_fused_k<TX, T>, dim3(resident), dim3(256), args, 0, (cudaStream_t)stream);
+  })
+  COMBAT_COUNT_LAUNCH();
+  if (e != cudaSuccess) {
+    combat_set_err("bn_bwd_fused", e);
+    return -(int)e;
+  }
+  return 0;
 }
 
 // ------------------------------------------------------------------ InstanceNorm + LeakyReLU (+ skip)

@@ -310,6 +310,12 @@ def conv_tc_desc(x, w_ptr, out, N, Hi, Wi, Ci, Ho, Wo, Co, KH, KW, stride, pad, 
 
 
 # ------------------------------------------------------------------ norm / activation
+import os as _os
+
+# train-mode BatchNorm backward as ONE cooperative launch (reduce -> grid sync -> finalize -> grid sync -> apply) instead of three
+# launches.  Measured on B200 inside the step (batch 512, 16 BatchNorm layers): 12.36 ms with it, 11.67 ms without -- two
+# grid-wide barriers over ~1200 resident CTAs cost more than the two launches and the DRAM re-read they remove.  Opt-in only.
+FUSED_BN_BWD = bool(_os.environ.get("COMBAT_FUSED_BN_BWD"))
 _PARTIAL_BLOCKS = 256
 _PARTIAL_FLOATS = _PARTIAL_BLOCKS * 2 * 2048
 
@@ -385,6 +391,13 @@ def bn_bwd_train(dy, x, y, gamma, mean, invstd, relu, dgamma_out, dbeta_out, dad
     Cc = x.shape[-1]
     R = x.numel() // Cc
     partial = Scratch.get(x.device)
+    if FUSED_BN_BWD and Cc % 8 == 0:   # one cooperative launch instead of reduce / finalize / apply
+        dx = torch.empty_like(dy)
+        dres = torch.empty_like(dy) if want_dres else None
+        check(lib.combat_bn_bwd_fused(_p(dy), _p(x), dt_code(x), _p(y), _p(dadd), _p(dx), _p(dres), dt_code(dy), R, Cc, _p(gamma),
+                                      _p(mean), _p(invstd), _p(partial), _max_partial_blocks(Cc), _p(dgamma_out), _p(dbeta_out),
+                                      int(relu), _s()), "bn_bwd_fused")
+        return dx, dres
     nblk = C.c_int(0)
     check(lib.combat_bn_bwd_reduce(_p(dy), _p(x), dt_code(x), _p(y), dt_code(dy), R, Cc, _p(mean), _p(invstd), _p(partial),
                                    _max_partial_blocks(Cc), C.byref(nblk), int(relu), _s()), "bn_bwd_reduce")

@@ -225,6 +225,12 @@ int combat_bn_bwd_apply(const void* dy, const void* x, int x_dtype, const void* 
                         int dtype, long long R, int C, const float* gamma, const float* mean, const float* invstd,
                         const float* dgamma, const float* dbeta, const float* eval_scale, int relu, void* stream);
 
+/* the three train-mode calls above as ONE cooperative launch (reduce -> grid sync -> finalize -> grid sync -> apply); C % 8 == 0.
+ * partial: scratch as for combat_bn_bwd_reduce; dgamma / dbeta are written and then read back by the apply phase. */
+int combat_bn_bwd_fused(const void* dy, const void* x, int x_dtype, const void* y, const void* dadd, void* dx, void* dres,
+                        int dtype, long long R, int C, const float* gamma, const float* mean, const float* invstd,
+                        float* partial, int max_blocks, float* dgamma, float* dbeta, int relu, void* stream);
+
 /* InstanceNorm2d(affine=False, eps) + LeakyReLU(slope) (+ skip), networks/models.py:273-340.
  *   y = IN(x); if (act) y = leaky_relu(y); if (skip) y += skip     ; saves mean/invstd [N,C] */
 int combat_instnorm_fwd(const void* x, int x_dtype, const void* skip, void* y, int dtype, int N, int HW, int C, float eps, float slope,
