@@ -77,6 +77,7 @@ __device__ __forceinline__ Taps make_taps(const TfRow& r, int x, int y, int H, i
 template <bool STAGED>
 __global__ void __launch_bounds__(256) post_transform_fwd_k(const float* __restrict__ in, float* __restrict__ out,
                                                             const float* __restrict__ params, int C, int H, int W) {
+  pdl_entry();
   extern __shared__ float4 simg4[];
   float* simg = (float*)simg4;
   const int n = blockIdx.x;
@@ -113,6 +114,7 @@ __global__ void __launch_bounds__(256) post_transform_fwd_k(const float* __restr
 template <bool STAGED>
 __global__ void __launch_bounds__(256) post_transform_bwd_k(const float* __restrict__ dout, float* __restrict__ din,
                                                             const float* __restrict__ params, int C, int H, int W, int accumulate) {
+  pdl_entry();
   extern __shared__ float4 simg4[];
   float* simg = (float*)simg4;
   const int n = blockIdx.x;
@@ -164,11 +166,11 @@ extern "C" int combat_post_transform_fwd(const float* in, float* out, const floa
   size_t bytes;
   if (tf_staged(C, H, W, &bytes)) {
     cudaFuncSetAttribute(post_transform_fwd_k<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    post_transform_fwd_k<true><<<dim3(rows, 1), 256, bytes, (cudaStream_t)stream>>>(in, out, params, C, H, W);
+    pdl_launch(post_transform_fwd_k<true>, dim3(rows, 1), 256, bytes, (cudaStream_t)stream, in, out, params, C, H, W);
     COMBAT_RETURN_LAUNCH("post_transform_fwd");
   }
   dim3 grid(rows, cdiv(H * W, PIX_PER_CTA));
-  post_transform_fwd_k<false><<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, params, C, H, W);
+  pdl_launch(post_transform_fwd_k<false>, grid, 256, 0, (cudaStream_t)stream, in, out, params, C, H, W);
   COMBAT_RETURN_LAUNCH("post_transform_fwd");
 }
 
@@ -180,11 +182,11 @@ extern "C" int combat_post_transform_bwd(const float* dout, float* din, const fl
   size_t bytes;
   if (tf_staged(C, H, W, &bytes)) {
     cudaFuncSetAttribute(post_transform_bwd_k<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    post_transform_bwd_k<true><<<dim3(rows, 1), 256, bytes, (cudaStream_t)stream>>>(dout, din, params, C, H, W, accumulate);
+    pdl_launch(post_transform_bwd_k<true>, dim3(rows, 1), 256, bytes, (cudaStream_t)stream, dout, din, params, C, H, W, accumulate);
     COMBAT_RETURN_LAUNCH("post_transform_bwd");
   }
   if (!accumulate) cudaMemsetAsync(din, 0, (size_t)rows * C * H * W * sizeof(float), (cudaStream_t)stream);
   dim3 grid(rows, cdiv(H * W, PIX_PER_CTA));
-  post_transform_bwd_k<false><<<grid, 256, 0, (cudaStream_t)stream>>>(dout, din, params, C, H, W, accumulate);
+  pdl_launch(post_transform_bwd_k<false>, grid, 256, 0, (cudaStream_t)stream, dout, din, params, C, H, W, accumulate);
   COMBAT_RETURN_LAUNCH("post_transform_bwd");
 }

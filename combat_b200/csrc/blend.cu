@@ -14,6 +14,7 @@ __global__ void __launch_bounds__(256) poison_blend_fwd_k(const float* __restric
                                                           int H, int W, int use_smem, const float* __restrict__ taps_dev,
                                                           const int* __restrict__ num_bd_dev,
                                                           const float* __restrict__ taps_rows) {
+  pdl_entry();
   extern __shared__ float tile[];  // H*W clamped values (use_smem)
   if (taps_dev) { k0 = taps_dev[0]; k1 = taps_dev[1]; }
   if (num_bd_dev) num_bd = num_bd_dev[0];
@@ -103,6 +104,7 @@ __global__ void __launch_bounds__(256) poison_blend_fwd_v4_k(const float* __rest
                                                              int H, int W, const float* __restrict__ taps_dev,
                                                              const int* __restrict__ num_bd_dev,
                                                              const float* __restrict__ taps_rows) {
+  pdl_entry();
   if (taps_dev) { k0 = taps_dev[0]; k1 = taps_dev[1]; }
   if (num_bd_dev) num_bd = num_bd_dev[0];
   const int plane = blockIdx.x;
@@ -180,6 +182,7 @@ __global__ void __launch_bounds__(256) poison_blend_fwd_b16_k(const float* __res
                                                               int H, int W, int planes, const float* __restrict__ taps_dev,
                                                               const int* __restrict__ num_bd_dev,
                                                               const float* __restrict__ taps_rows) {
+  pdl_entry();
   if (taps_dev) { k0 = taps_dev[0]; k1 = taps_dev[1]; }
   if (num_bd_dev) num_bd = num_bd_dev[0];
   const int W4 = W >> 2, H4 = H >> 2, TPP = W4 * H4;  // threads per plane
@@ -270,6 +273,7 @@ __global__ void __launch_bounds__(256) poison_blend_bwd_k(const float* __restric
                                                           float k0, float k1, float* __restrict__ dnoise, int HW, int H,
                                                           int W, const float* __restrict__ taps_dev, int C,
                                                           const float* __restrict__ taps_rows) {
+  pdl_entry();
   extern __shared__ float gt[];  // total upstream gradient of the plane
   if (taps_dev) { k0 = taps_dev[0]; k1 = taps_dev[1]; }
   if (taps_rows) { k0 = taps_rows[2 * (blockIdx.x / C)]; k1 = taps_rows[2 * (blockIdx.x / C) + 1]; }
@@ -308,6 +312,7 @@ __global__ void __launch_bounds__(256) poison_blend_bwd_v4_k(const float* __rest
                                                              float k0, float k1, float* __restrict__ dnoise, int H, int W,
                                                              const float* __restrict__ taps_dev, int C,
                                                              const float* __restrict__ taps_rows) {
+  pdl_entry();
   extern __shared__ float gt[];  // total upstream gradient of the plane
   if (taps_dev) { k0 = taps_dev[0]; k1 = taps_dev[1]; }
   if (taps_rows) { k0 = taps_rows[2 * (blockIdx.x / C)]; k1 = taps_rows[2 * (blockIdx.x / C) + 1]; }
@@ -377,18 +382,18 @@ extern "C" int combat_poison_blend_fwd(const float* x, const float* noise, const
     const int tpp = (W / 4) * (H / 4);
     if ((W & 3) == 0 && (H & 3) == 0 && tpp % 32 == 0 && tpp <= 256 && 256 % tpp == 0 && 32 % (W / 4) == 0) {
       const int planes = rows * C, ppc = 256 / tpp;
-      poison_blend_fwd_b16_k<<<(planes + ppc - 1) / ppc, 256, 0, (cudaStream_t)stream>>>(
+      pdl_launch(poison_blend_fwd_b16_k, (planes + ppc - 1) / ppc, 256, 0, (cudaStream_t)stream, 
           x, noise, perm, nperm, num_bd, noise_rate, k0, k1, out, sq_partial, C, H, W, planes, taps_dev, num_bd_dev, taps_rows);
       COMBAT_RETURN_LAUNCH("poison_blend_fwd");
     }
   }
   if ((W & 3) == 0 && W <= 128 && 32 % (W / 4) == 0) {  // a row = W/4 consecutive lanes of one warp
-    poison_blend_fwd_v4_k<<<rows * C, 256, 0, (cudaStream_t)stream>>>(x, noise, perm, nperm, num_bd, noise_rate, k0, k1, out,
+    pdl_launch(poison_blend_fwd_v4_k, rows * C, 256, 0, (cudaStream_t)stream, x, noise, perm, nperm, num_bd, noise_rate, k0, k1, out,
                                                                          sq_partial, C, H, W, taps_dev, num_bd_dev, taps_rows);
     COMBAT_RETURN_LAUNCH("poison_blend_fwd");
   }
   if (use_smem) cudaFuncSetAttribute(poison_blend_fwd_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  poison_blend_fwd_k<<<rows * C, 256, use_smem ? smem : 0, (cudaStream_t)stream>>>(x, noise, perm, nperm, num_bd, noise_rate,
+  pdl_launch(poison_blend_fwd_k, rows * C, 256, use_smem ? smem : 0, (cudaStream_t)stream, x, noise, perm, nperm, num_bd, noise_rate,
                                                                                   k0, k1, out, sq_partial, C, H, W, use_smem,
                                                                                   taps_dev, num_bd_dev, taps_rows);
   COMBAT_RETURN_LAUNCH("poison_blend_fwd");
@@ -405,12 +410,12 @@ extern "C" int combat_poison_blend_bwd(const float* x, const float* noise, const
   COMBAT_ARG(smem <= 200 * 1024, 13);
   if ((W & 3) == 0) {
     cudaFuncSetAttribute(poison_blend_bwd_v4_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    poison_blend_bwd_v4_k<<<rows * C, 256, smem, (cudaStream_t)stream>>>(x, noise, x_bd, g1, g2, mse_scale, noise_rate, k0, k1,
+    pdl_launch(poison_blend_bwd_v4_k, rows * C, 256, smem, (cudaStream_t)stream, x, noise, x_bd, g1, g2, mse_scale, noise_rate, k0, k1,
                                                                          dnoise, H, W, taps_dev, C, taps_rows);
     COMBAT_RETURN_LAUNCH("poison_blend_bwd");
   }
   cudaFuncSetAttribute(poison_blend_bwd_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  poison_blend_bwd_k<<<rows * C, 256, smem, (cudaStream_t)stream>>>(x, noise, x_bd, g1, g2, mse_scale, noise_rate, k0, k1,
+  pdl_launch(poison_blend_bwd_k, rows * C, 256, smem, (cudaStream_t)stream, x, noise, x_bd, g1, g2, mse_scale, noise_rate, k0, k1,
                                                                     dnoise, H * W, H, W, taps_dev, C, taps_rows);
   COMBAT_RETURN_LAUNCH("poison_blend_bwd");
 }
@@ -424,6 +429,7 @@ extern "C" int combat_poison_blend_bwd(const float* x, const float* noise, const
 // border terms e[0,c]^2, e[H-1,c]^2, e[r,0]^2, e[r,W-1]^2.
 __global__ void __launch_bounds__(256) grad_l2_partial_k(const float* __restrict__ x, const float* __restrict__ x_bd,
                                                          float* __restrict__ partial, int H, int W) {
+  pdl_entry();
   const long long base = (long long)blockIdx.x * H * W;
   float sv = 0.f, sh = 0.f;
   for (int i = threadIdx.x; i < H * W; i += blockDim.x) {
@@ -451,6 +457,7 @@ __global__ void __launch_bounds__(256) grad_l2_partial_k(const float* __restrict
 
 __global__ void __launch_bounds__(256) grad_l2_final_k(const float* __restrict__ partial, int planes, double inv_v, double inv_h,
                                                        float* __restrict__ out) {
+  pdl_entry();
   double av = 0.0, ah = 0.0;
   for (int i = threadIdx.x; i < planes; i += blockDim.x) { av += (double)partial[2 * i]; ah += (double)partial[2 * i + 1]; }
   __shared__ double red[2][256];
@@ -469,9 +476,9 @@ extern "C" int combat_grad_l2(const float* x, const float* x_bd, float* partial,
   COMBAT_ARG(x && x_bd && partial && out, 0);
   COMBAT_ARG(rows > 0 && C > 0 && H >= 2 && W >= 2, 4);
   const int planes = rows * C;
-  grad_l2_partial_k<<<planes, 256, 0, (cudaStream_t)stream>>>(x, x_bd, partial, H, W);
+  pdl_launch(grad_l2_partial_k, planes, 256, 0, (cudaStream_t)stream, x, x_bd, partial, H, W);
   COMBAT_CHECK_LAUNCH("grad_l2_partial");
   const double inv_v = 1.0 / ((double)planes * (H + 2) * (W + 2)), inv_h = 1.0 / ((double)planes * (H + 3) * (W + 1));
-  grad_l2_final_k<<<1, 256, 0, (cudaStream_t)stream>>>(partial, planes, inv_v, inv_h, out);
+  pdl_launch(grad_l2_final_k, 1, 256, 0, (cudaStream_t)stream, partial, planes, inv_v, inv_h, out);
   COMBAT_RETURN_LAUNCH("grad_l2");
 }

@@ -3,6 +3,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/combat_b200.h"
 
@@ -43,6 +44,36 @@ void combat_set_err(const char* what, cudaError_t e);
       return -1000 - (k);                        \
     }                                            \
   } while (0)
+
+// ---- programmatic dependent launch (PDL), opt-in with COMBAT_PDL=1 (measured slower inside the step, see lib.cu).  With it every
+// kernel of the library is launched with cudaLaunchAttributeProgrammaticStreamSerialization and begins with pdl_entry(): `griddepcontrol.launch_dependents` lets the
+// NEXT kernel of the stream / captured graph be scheduled while this one is still running (its CTAs become resident as SM
+// resources free up), `griddepcontrol.wait` blocks until every prerequisite grid has completed and its memory is visible -- so
+// nothing a kernel reads or writes can race with its predecessor, and what overlaps is the launch latency, CTA rasterisation
+// and (tcgen05 kernels) the barrier / tensor-memory prologue.  Without the attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_entry() {
+  pdl_launch_dependents();
+  pdl_wait();
+}
+bool combat_pdl_enabled();
+
+template <typename... P, typename... A>
+static inline cudaError_t pdl_launch(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = combat_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+}
 
 template <typename T>
 __device__ __forceinline__ float to_f(T v);

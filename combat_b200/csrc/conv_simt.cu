@@ -35,6 +35,7 @@ __device__ __forceinline__ float gather_a(const combat_conv_desc& d, int n, int 
 }
 
 __global__ void __launch_bounds__(256) conv_simt_k(const ConvK p) {
+  pdl_entry();
   const combat_conv_desc& d = p.d;
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
@@ -112,6 +113,7 @@ __global__ void __launch_bounds__(256) conv_simt_k(const ConvK p) {
 // wgrad: dW[co][k] += sum_p dy[p][co] * A[p][k], p split over blockIdx.z
 __global__ void __launch_bounds__(256) conv_wgrad_simt_k(const ConvK p, const void* __restrict__ dy, int dy_dtype,
                                                          float* __restrict__ dw, int p_per_z) {
+  pdl_entry();
   const combat_conv_desc& d = p.d;
   __shared__ float Ds[BK][BM + 4];  // [pp][co]
   __shared__ float As[BK][BN + 4];  // [pp][k]
@@ -195,7 +197,7 @@ extern "C" int combat_conv_simt(const combat_conv_desc* d, void* stream) {
   p.M = d->N * d->Ho * d->Wo;
   p.K = d->KH * d->KW * d->Ci;
   dim3 grid(cdiv(p.M, BM), cdiv(d->Co, BN));
-  conv_simt_k<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  pdl_launch(conv_simt_k, grid, 256, 0, (cudaStream_t)stream, p);
   COMBAT_RETURN_LAUNCH("conv_simt");
 }
 
@@ -218,6 +220,6 @@ extern "C" int combat_conv_wgrad_simt(const combat_conv_desc* d, const void* dy,
   p_per_z = cdiv(p_per_z, BK) * BK;
   z = cdiv(p.M, p_per_z);
   dim3 grid(cdiv(d->Co, BM), cdiv(p.K, BN), z);
-  conv_wgrad_simt_k<<<grid, 256, 0, (cudaStream_t)stream>>>(p, dy, dy_dtype, dw_ohwi, p_per_z);
+  pdl_launch(conv_wgrad_simt_k, grid, 256, 0, (cudaStream_t)stream, p, dy, dy_dtype, dw_ohwi, p_per_z);
   COMBAT_RETURN_LAUNCH("conv_wgrad_simt");
 }

@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(256) conv_cin3_generic_k(const float* __restri
                                                    const float* __restrict__ bias, TO* __restrict__ out, int N, int H, int W,
                                                    int Ho, int Wo, int Co, int stride, int act,
                                                    const float* __restrict__ post_scale, const float* __restrict__ post_shift) {
+  pdl_entry();
   extern __shared__ float ws[];  // [27][Co]
   for (int e = threadIdx.x; e < 27 * Co; e += blockDim.x) {
     const int co = e / 27, k = e % 27;
@@ -91,6 +92,7 @@ template <typename TI, typename TW>
 __global__ void __launch_bounds__(256) conv_cout3_generic_k(const TI* __restrict__ in, const TW* __restrict__ w,
                                                     const float* __restrict__ bias, float* __restrict__ out, int N, int H, int W,
                                                     int act) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -151,6 +153,7 @@ __global__ void __launch_bounds__(256) conv_cin3_k(const float* __restrict__ x, 
                                                    int Ho, int Wo, int Co, int act, const float* __restrict__ post_scale,
                                                    const float* __restrict__ post_shift, bf16* __restrict__ out2,
                                                    const float* __restrict__ scale2, const float* __restrict__ shift2) {
+  pdl_entry();
   extern __shared__ float ws[];  // [27][Co]
   for (int e = threadIdx.x; e < 27 * Co; e += blockDim.x) {
     const int co = e / 27, k = e % 27;
@@ -255,6 +258,7 @@ template <typename TI, typename TW, int PX>
 __global__ void __launch_bounds__(128) conv_cout3_k(const TI* __restrict__ in, const TW* __restrict__ w,
                                                     const float* __restrict__ bias, float* __restrict__ out, int N, int H, int W,
                                                     int act) {
+  pdl_entry();
   __shared__ float4 wsm[9 * 64];
   for (int e = threadIdx.x; e < 9 * 64; e += blockDim.x)
     wsm[e] = make_float4(to_f<TW>(w[e]), to_f<TW>(w[576 + e]), to_f<TW>(w[1152 + e]), 0.f);
@@ -337,6 +341,7 @@ template <typename T, int MODE>
 __global__ void __launch_bounds__(256) wgrad3_k(const float* __restrict__ narrow, const T* __restrict__ wide,
                                                 float* __restrict__ dw, float* __restrict__ db, int N, int Hn, int Wn, int Hw,
                                                 int Ww, int S) {
+  pdl_entry();
   __shared__ __align__(16) float patch[WG_TP * 32];
   __shared__ __align__(16) float red[4 * 32 * 64];  // tree reduction over the 8 warps: 4 x (32 lanes x 64 values)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -459,6 +464,7 @@ static int grid_for(long long work_items, int per_block) {
 // anyway, so the second half carries the rounding residual and the image enters with ~16 mantissa bits at no extra cost.
 __global__ void __launch_bounds__(256) im2col3_k(const float* __restrict__ x, bf16* __restrict__ A, int N, int H, int W, int Ho,
                                                  int Wo, int S) {
+  pdl_entry();
   const long long total = (long long)N * Ho * Wo * 8;  // one 16-byte chunk (8 columns) per thread
   const long long HW = (long long)H * W;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -495,6 +501,7 @@ __global__ void __launch_bounds__(256) im2col3_k(const float* __restrict__ x, bf
 //                               db[j] += colsum[12+j] + colsum[44+j]  (centre tap of the operand == the 3-channel tensor)
 __global__ void fold_w64_k(const float* __restrict__ dw64, float* __restrict__ dw, int rows, int mode,
                            const float* __restrict__ colsum, float* __restrict__ db) {
+  pdl_entry();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < rows * 27) {
     const int row = i / 27, k = i - row * 27;
@@ -511,7 +518,7 @@ __global__ void fold_w64_k(const float* __restrict__ dw64, float* __restrict__ d
 
 extern "C" int combat_fold_w64(const float* dw64, float* dw, int rows, int mode, const float* colsum, float* db, void* stream) {
   COMBAT_ARG(dw64 && dw && rows > 0 && (mode == 0 || mode == 1), 0);
-  fold_w64_k<<<cdiv(rows * 27, 256), 256, 0, (cudaStream_t)stream>>>(dw64, dw, rows, mode, colsum, db);
+  pdl_launch(fold_w64_k, cdiv(rows * 27, 256), 256, 0, (cudaStream_t)stream, dw64, dw, rows, mode, colsum, db);
   COMBAT_RETURN_LAUNCH("fold_w64");
 }
 
@@ -521,7 +528,7 @@ extern "C" int combat_im2col3(const float* x, void* A, int N, int H, int W, int 
   const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
   const long long total = (long long)N * Ho * Wo * 8;
   if (total <= 0) return 0;
-  im2col3_k<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (bf16*)A, N, H, W, Ho, Wo, stride);
+  pdl_launch(im2col3_k, grid_for(total, 256), 256, 0, (cudaStream_t)stream, x, (bf16*)A, N, H, W, Ho, Wo, stride);
   COMBAT_RETURN_LAUNCH("im2col3");
 }
 
@@ -544,7 +551,7 @@ extern "C" int combat_conv_cin3(const float* x, const void* w, int w_dtype, cons
     const int px = (Wo % 8 == 0 && getenv("COMBAT_CIN3_PX8")) ? 8 : 4;
     const int grid = grid_for(M / px, qpb);
 #define LCI2(TW, TO, SS, PP)                                                                                      \
-  conv_cin3_k<TW, TO, SS, PP><<<grid, 256, smem, st>>>(x, (const TW*)w, bias, (TO*)out, N, H, W, Ho, Wo, Co, act, \
+  pdl_launch(conv_cin3_k<TW, TO, SS, PP>, grid, 256, smem, st, x, (const TW*)w, bias, (TO*)out, N, H, W, Ho, Wo, Co, act, \
                                                        post_scale, post_shift, (bf16*)out2, scale2, shift2)
 #define LCI(TW, TO)                                          \
   {                                                          \
@@ -560,7 +567,7 @@ extern "C" int combat_conv_cin3(const float* x, const void* w, int w_dtype, cons
   COMBAT_ARG(!out2, 15);  // the fused second output needs Wo % 4 == 0
   const int ppb = 256 / (Co / 8);
   const int grid = grid_for(M, ppb * 4);
-#define LCI(TW, TO) conv_cin3_generic_k<TW, TO><<<grid, 256, smem, st>>>(x, (const TW*)w, bias, (TO*)out, N, H, W, Ho, Wo, Co, stride, act, post_scale, post_shift)
+#define LCI(TW, TO) pdl_launch(conv_cin3_generic_k<TW, TO>, grid, 256, smem, st, x, (const TW*)w, bias, (TO*)out, N, H, W, Ho, Wo, Co, stride, act, post_scale, post_shift)
   if (w_dtype == COMBAT_F32) { if (out_dtype == COMBAT_F32) LCI(float, float); else LCI(float, bf16); }
   else { if (out_dtype == COMBAT_F32) LCI(bf16, float); else LCI(bf16, bf16); }
 #undef LCI
@@ -579,8 +586,8 @@ extern "C" int combat_conv_cout3(const void* in, int in_dtype, const void* w, in
     const int grid = grid_for(M / px, 128);
 #define LCO(TI, TW)                                                                                                     \
   {                                                                                                                     \
-    if (px == 8) conv_cout3_k<TI, TW, 8><<<grid, 128, 0, st>>>((const TI*)in, (const TW*)w, bias, out, N, H, W, act);   \
-    else conv_cout3_k<TI, TW, 2><<<grid, 128, 0, st>>>((const TI*)in, (const TW*)w, bias, out, N, H, W, act);           \
+    if (px == 8) pdl_launch(conv_cout3_k<TI, TW, 8>, grid, 128, 0, st, (const TI*)in, (const TW*)w, bias, out, N, H, W, act);   \
+    else pdl_launch(conv_cout3_k<TI, TW, 2>, grid, 128, 0, st, (const TI*)in, (const TW*)w, bias, out, N, H, W, act);           \
   }
     if (in_dtype == COMBAT_F32) { if (w_dtype == COMBAT_F32) LCO(float, float) else LCO(float, bf16) }
     else { if (w_dtype == COMBAT_F32) LCO(bf16, float) else LCO(bf16, bf16) }
@@ -588,7 +595,7 @@ extern "C" int combat_conv_cout3(const void* in, int in_dtype, const void* w, in
     COMBAT_RETURN_LAUNCH("conv_cout3");
   }
   const int grid = grid_for(M, 8 * 16);
-#define LCO(TI, TW) conv_cout3_generic_k<TI, TW><<<grid, 256, 0, st>>>((const TI*)in, (const TW*)w, bias, out, N, H, W, act)
+#define LCO(TI, TW) pdl_launch(conv_cout3_generic_k<TI, TW>, grid, 256, 0, st, (const TI*)in, (const TW*)w, bias, out, N, H, W, act)
   if (in_dtype == COMBAT_F32) { if (w_dtype == COMBAT_F32) LCO(float, float); else LCO(float, bf16); }
   else { if (w_dtype == COMBAT_F32) LCO(bf16, float); else LCO(bf16, bf16); }
 #undef LCO
@@ -622,9 +629,9 @@ extern "C" int combat_wgrad_cin3(const float* x, const void* dy, int dy_dtype, f
   const int grid = wgrad_grid(M);
   cudaStream_t st = (cudaStream_t)stream;
   if (dy_dtype == COMBAT_F32)
-    wgrad3_k<float, 0><<<grid, 256, 0, st>>>(x, (const float*)dy, dw, db, N, H, W, Ho, Wo, stride);
+    pdl_launch(wgrad3_k<float, 0>, grid, 256, 0, st, x, (const float*)dy, dw, db, N, H, W, Ho, Wo, stride);
   else
-    wgrad3_k<bf16, 0><<<grid, 256, 0, st>>>(x, (const bf16*)dy, dw, db, N, H, W, Ho, Wo, stride);
+    pdl_launch(wgrad3_k<bf16, 0>, grid, 256, 0, st, x, (const bf16*)dy, dw, db, N, H, W, Ho, Wo, stride);
   COMBAT_RETURN_LAUNCH("wgrad_cin3");
 }
 
@@ -637,8 +644,8 @@ extern "C" int combat_wgrad_cout3(const void* a, int a_dtype, const float* dz, f
   const int grid = wgrad_grid(M);
   cudaStream_t st = (cudaStream_t)stream;
   if (a_dtype == COMBAT_F32)
-    wgrad3_k<float, 1><<<grid, 256, 0, st>>>(dz, (const float*)a, dw, db, N, H, W, H, W, 1);
+    pdl_launch(wgrad3_k<float, 1>, grid, 256, 0, st, dz, (const float*)a, dw, db, N, H, W, H, W, 1);
   else
-    wgrad3_k<bf16, 1><<<grid, 256, 0, st>>>(dz, (const bf16*)a, dw, db, N, H, W, H, W, 1);
+    pdl_launch(wgrad3_k<bf16, 1>, grid, 256, 0, st, dz, (const bf16*)a, dw, db, N, H, W, H, W, 1);
   COMBAT_RETURN_LAUNCH("wgrad_cout3");
 }

@@ -550,6 +550,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* stg_base
 // ---------------------------------------------------------------------------------------------- fwd / dgrad kernel
 template <int BLOCK_N, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
+  pdl_launch_dependents();  // the next kernel may be scheduled; this one waits for its predecessor after its prologue
   using Cfg = TcCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B atoms need 1024 B alignment
@@ -580,6 +581,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();  // barriers initialised, tensor memory allocated: nothing above touched global memory
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -685,6 +687,7 @@ struct TcPairCfg {
 template <int BLOCK_N, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     conv_tc_pair_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
+  pdl_launch_dependents();  // the next kernel may be scheduled; this one waits for its predecessor after its prologue
   using Cfg = TcPairCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -717,6 +720,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
   cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / multicast commit / remote complete_tx
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();  // barriers initialised, tensor memory allocated: nothing above touched global memory
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -816,6 +820,7 @@ struct Tc64Cfg {
 template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc64_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
                                                                   const int stage_bytes, const int n_stages) {
+  pdl_launch_dependents();  // the next kernel may be scheduled; this one waits for its predecessor after its prologue
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* wsm = smem;                               // [9 taps][64 co][64 ci] bf16, SWIZZLE_128B
@@ -849,6 +854,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc64_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();  // barriers initialised, tensor memory allocated: nothing above touched global memory
 
   if (warp == 0) {
     if (lane == 0) {
@@ -1209,12 +1215,12 @@ extern "C" int combat_conv_tc(const combat_conv_tc_desc* d, void* stream) {
 #define LAUNCH_P(BN, MD)                                                                                                        \
   {                                                                                                                             \
     cudaFuncSetAttribute(conv_tc_pair_kernel<BN, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcPairCfg<BN>::SMEM_BYTES);  \
-    conv_tc_pair_kernel<BN, MD><<<grid, TC_THREADS, TcPairCfg<BN>::SMEM_BYTES, st>>>(maps, p);                                  \
+    pdl_launch(conv_tc_pair_kernel<BN, MD>, grid, TC_THREADS, TcPairCfg<BN>::SMEM_BYTES, st, maps, p);                                  \
   }
 #define LAUNCH_C(BN, MD)                                                                                                  \
   {                                                                                                                       \
     cudaFuncSetAttribute(conv_tc_kernel<BN, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES);     \
-    conv_tc_kernel<BN, MD><<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st>>>(maps, p);                                     \
+    pdl_launch(conv_tc_kernel<BN, MD>, grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st, maps, p);                                     \
   }
   const int mode = d->mask ? 1 : (p.stats ? 2 : 0);
   if (p.stats) {  // partial blocks of (CTA, quarter): zero-filled, every warp writes only its own column range
@@ -1226,13 +1232,13 @@ extern "C" int combat_conv_tc(const combat_conv_tc_desc* d, void* stream) {
     const int smem_bytes = Tc64Cfg::SMEM_BYTES_FIXED + n_stages64 * stage_bytes64;
     if (mode == 1) {
       cudaFuncSetAttribute(conv_tc64_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-      conv_tc64_kernel<1><<<grid, TC_THREADS, smem_bytes, st>>>(maps, p, stage_bytes64, n_stages64);
+      pdl_launch(conv_tc64_kernel<1>, grid, TC_THREADS, smem_bytes, st, maps, p, stage_bytes64, n_stages64);
     } else if (mode == 2) {
       cudaFuncSetAttribute(conv_tc64_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-      conv_tc64_kernel<2><<<grid, TC_THREADS, smem_bytes, st>>>(maps, p, stage_bytes64, n_stages64);
+      pdl_launch(conv_tc64_kernel<2>, grid, TC_THREADS, smem_bytes, st, maps, p, stage_bytes64, n_stages64);
     } else {
       cudaFuncSetAttribute(conv_tc64_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-      conv_tc64_kernel<0><<<grid, TC_THREADS, smem_bytes, st>>>(maps, p, stage_bytes64, n_stages64);
+      pdl_launch(conv_tc64_kernel<0>, grid, TC_THREADS, smem_bytes, st, maps, p, stage_bytes64, n_stages64);
     }
     COMBAT_RETURN_LAUNCH("conv_tc64");
   }
@@ -1278,6 +1284,7 @@ struct TcWCfg {
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_kernel(const __grid_constant__ TcWgradMaps maps, const TcWgradParams p) {
+  pdl_launch_dependents();  // the next kernel may be scheduled; this one waits for its predecessor after its prologue
   using Cfg = TcWCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -1309,6 +1316,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();  // barriers initialised, tensor memory allocated: nothing above touched global memory
 
   // the two 64-row blocks of this M tile
   int rc[2], tap[2], cic[2];
@@ -1418,6 +1426,7 @@ struct TcW64Maps {
 };
 
 __global__ void __launch_bounds__(192, 1) conv_tc_wgrad64_kernel(const __grid_constant__ TcW64Maps maps, const TcW64Params p) {
+  pdl_launch_dependents();  // the next kernel may be scheduled; this one waits for its predecessor after its prologue
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int stage_bytes = 3 * p.copy_bytes + 128 * 128;  // three X copies + the 128-pixel dY box
@@ -1442,6 +1451,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad64_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();  // barriers initialised, tensor memory allocated: nothing above touched global memory
 
   if (warp == 0) {
     if (lane == 0) {
@@ -1551,7 +1561,7 @@ extern "C" int combat_conv_tc_wgrad(const combat_conv_tc_desc* d, const void* dy
       q.dw = dw_ohwi;
       const int grid = q.total_tiles < num_sms() ? q.total_tiles : num_sms();
       cudaFuncSetAttribute(conv_tc_wgrad64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-      conv_tc_wgrad64_kernel<<<grid, 192, smem_bytes, (cudaStream_t)stream>>>(wm, q);
+      pdl_launch(conv_tc_wgrad64_kernel, grid, 192, smem_bytes, (cudaStream_t)stream, wm, q);
       COMBAT_RETURN_LAUNCH("conv_tc_wgrad64");
     }
   }
@@ -1610,7 +1620,7 @@ extern "C" int combat_conv_tc_wgrad(const combat_conv_tc_desc* d, const void* dy
 #define LAUNCH_W(BN)                                                                                              \
   {                                                                                                               \
     cudaFuncSetAttribute(conv_tc_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcWCfg<BN>::SMEM_BYTES); \
-    conv_tc_wgrad_kernel<BN><<<grid, 192, TcWCfg<BN>::SMEM_BYTES, st>>>(maps, p);                                 \
+    pdl_launch(conv_tc_wgrad_kernel<BN>, grid, 192, TcWCfg<BN>::SMEM_BYTES, st, maps, p);                                 \
   }
   if (BLOCK_N == 256) LAUNCH_W(256) else if (BLOCK_N == 128) LAUNCH_W(128) else LAUNCH_W(64)
 #undef LAUNCH_W

@@ -21,6 +21,7 @@ template <int MODE>
 __global__ void __launch_bounds__(256) plane_transform_smem(const void* __restrict__ in, float* __restrict__ out,
                                                             const float* __restrict__ L, const float* __restrict__ R,
                                                             long long planes, int N) {
+  pdl_entry();
   extern __shared__ float sm[];
   const int XS = N + 4;  // keeps rows 16B aligned for float4 broadcast loads (N % 4 == 0 enforced by host)
   float* Ls = sm;
@@ -76,6 +77,7 @@ __global__ void __launch_bounds__(256) plane_transform_smem(const void* __restri
 template <int MODE, int SIDE>
 __global__ void __launch_bounds__(256) plane_mm(const void* __restrict__ in, float* __restrict__ out,
                                                 const float* __restrict__ M, int N) {
+  pdl_entry();
   __shared__ float As[32][33], Bs[32][33];
   const long long p = blockIdx.z;
   const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
@@ -123,7 +125,7 @@ extern "C" int combat_plane_transform(const void* in, float* out, const float* L
 #define LAUNCH(MODE)                                                                                          \
   {                                                                                                           \
     cudaFuncSetAttribute(plane_transform_smem<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    plane_transform_smem<MODE><<<grid, 256, smem, st>>>(in, out, L, R, planes, N);                            \
+    pdl_launch(plane_transform_smem<MODE>, grid, 256, smem, st, in, out, L, R, planes, N);                            \
   }
     if (in_mode == 0) LAUNCH(0) else if (in_mode == 1) LAUNCH(1) else LAUNCH(2)
 #undef LAUNCH
@@ -133,12 +135,12 @@ extern "C" int combat_plane_transform(const void* in, float* out, const float* L
   COMBAT_ARG(planes <= 65535, 4);
   dim3 grid(cdiv(N, 32), cdiv(N, 32), (unsigned)planes);
   if (in_mode == 0)
-    plane_mm<0, 0><<<grid, 256, 0, st>>>(in, workspace, R, N);
+    pdl_launch(plane_mm<0, 0>, grid, 256, 0, st, in, workspace, R, N);
   else if (in_mode == 1)
-    plane_mm<1, 0><<<grid, 256, 0, st>>>(in, workspace, R, N);
+    pdl_launch(plane_mm<1, 0>, grid, 256, 0, st, in, workspace, R, N);
   else
-    plane_mm<2, 0><<<grid, 256, 0, st>>>(in, workspace, R, N);
+    pdl_launch(plane_mm<2, 0>, grid, 256, 0, st, in, workspace, R, N);
   COMBAT_CHECK_LAUNCH("plane_mm<0>");
-  plane_mm<0, 1><<<grid, 256, 0, st>>>(workspace, out, L, N);
+  pdl_launch(plane_mm<0, 1>, grid, 256, 0, st, workspace, out, L, N);
   COMBAT_RETURN_LAUNCH("plane_mm<1>");
 }

@@ -141,6 +141,7 @@ __device__ __forceinline__ void planes_loop(const void* in, float* out, long lon
 template <int KIND, int IN_MODE, int KEEP>
 __global__ void __launch_bounds__(256, 3) dct32_k(const void* __restrict__ in, float* __restrict__ out, long long planes,
                                                   int keep) {
+  pdl_entry();
   __shared__ __align__(16) float smem[8 * Tile<32>::FLOATS];
   planes_loop<32, 8, KIND, IN_MODE, KEEP>(in, out, planes, keep, smem, WarpSync());
 }
@@ -148,6 +149,7 @@ __global__ void __launch_bounds__(256, 3) dct32_k(const void* __restrict__ in, f
 template <int KIND, int IN_MODE, int KEEP>
 __global__ void __launch_bounds__(64, 10) dct64_k(const void* __restrict__ in, float* __restrict__ out, long long planes,
                                                   int keep) {
+  pdl_entry();
   __shared__ __align__(16) float smem[Tile<64>::FLOATS];
   planes_loop<64, 1, KIND, IN_MODE, KEEP>(in, out, planes, keep, smem, BlockSync());
 }
@@ -166,7 +168,7 @@ static void launch_planes(long long ctas_needed, const void* in, float* out, lon
     if (cap <= 0) cap = 148 * 16;
   }
   const int grid = (int)(ctas_needed < cap ? ctas_needed : cap);
-  KERNEL<<<grid, THREADS, 0, st>>>(in, out, planes, keep);
+  pdl_launch(KERNEL, grid, THREADS, 0, st, in, out, planes, keep);
 }
 
 extern "C" int combat_dct32_fast(const void* in, float* out, long long planes, int kind, int keep, int in_mode,

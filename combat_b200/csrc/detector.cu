@@ -16,6 +16,7 @@ static inline int det_grid(long long n) {
 // a = elu(z) is what the forward kept: d elu / dz = 1 for z > 0, exp(z) = a + 1 otherwise (torch: elu_backward on the result)
 template <typename T>
 __global__ void __launch_bounds__(256) elu_bwd_k(const T* __restrict__ da, const T* __restrict__ a, T* __restrict__ dz, long long n) {
+  pdl_entry();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float v = to_f<T>(a[i]);
     dz[i] = from_f<T>(to_f<T>(da[i]) * (v > 0.f ? 1.f : v + 1.f));
@@ -25,7 +26,7 @@ __global__ void __launch_bounds__(256) elu_bwd_k(const T* __restrict__ da, const
 extern "C" int combat_elu_bwd(const void* da, const void* a, void* dz, int dtype, long long n, void* stream) {
   COMBAT_ARG(da && a && dz, 0);
   if (n <= 0) return 0;
-  DISPATCH_DTYPE(dtype, elu_bwd_k<T><<<det_grid(n), 256, 0, (cudaStream_t)stream>>>((const T*)da, (const T*)a, (T*)dz, n);)
+  DISPATCH_DTYPE(dtype, pdl_launch(elu_bwd_k<T>, det_grid(n), 256, 0, (cudaStream_t)stream, (const T*)da, (const T*)a, (T*)dz, n);)
   COMBAT_RETURN_LAUNCH("elu_bwd");
 }
 
@@ -36,6 +37,7 @@ extern "C" int combat_elu_bwd(const void* da, const void* a, void* dz, int dtype
 template <typename T>
 __global__ void __launch_bounds__(256) maxpool2_bwd_k(const T* __restrict__ dy, const T* __restrict__ x, T* __restrict__ dx,
                                                       long long total, int H, int W, int C) {
+  pdl_entry();
   const int Ho = H / 2, Wo = W / 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
@@ -64,7 +66,7 @@ extern "C" int combat_maxpool2_bwd(const void* dy, const void* x, void* dx, int 
   COMBAT_ARG(N >= 0 && H > 0 && W > 0 && C > 0 && (H % 2) == 0 && (W % 2) == 0, 4);
   const long long total = (long long)N * (H / 2) * (W / 2) * C;
   if (total <= 0) return 0;
-  DISPATCH_DTYPE(dtype, maxpool2_bwd_k<T><<<det_grid(total), 256, 0, (cudaStream_t)stream>>>((const T*)dy, (const T*)x, (T*)dx, total, H, W, C);)
+  DISPATCH_DTYPE(dtype, pdl_launch(maxpool2_bwd_k<T>, det_grid(total), 256, 0, (cudaStream_t)stream, (const T*)dy, (const T*)x, (T*)dx, total, H, W, C);)
   COMBAT_RETURN_LAUNCH("maxpool2_bwd");
 }
 
@@ -74,6 +76,7 @@ extern "C" int combat_maxpool2_bwd(const void* dy, const void* x, void* dx, int 
 template <typename T>
 __global__ void __launch_bounds__(256) mask_scale_k(const T* __restrict__ x, const unsigned char* __restrict__ keep, T* __restrict__ y,
                                                     long long n, float scale) {
+  pdl_entry();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] = from_f<T>(keep[i] ? to_f<T>(x[i]) * scale : 0.f);
 }
@@ -81,7 +84,7 @@ __global__ void __launch_bounds__(256) mask_scale_k(const T* __restrict__ x, con
 extern "C" int combat_mask_scale(const void* x, const unsigned char* keep, void* y, int dtype, long long n, float scale, void* stream) {
   COMBAT_ARG(x && keep && y, 0);
   if (n <= 0) return 0;
-  DISPATCH_DTYPE(dtype, mask_scale_k<T><<<det_grid(n), 256, 0, (cudaStream_t)stream>>>((const T*)x, keep, (T*)y, n, scale);)
+  DISPATCH_DTYPE(dtype, pdl_launch(mask_scale_k<T>, det_grid(n), 256, 0, (cudaStream_t)stream, (const T*)x, keep, (T*)y, n, scale);)
   COMBAT_RETURN_LAUNCH("mask_scale");
 }
 
@@ -92,6 +95,7 @@ extern "C" int combat_mask_scale(const void* x, const unsigned char* keep, void*
 __global__ void __launch_bounds__(256) adadelta_k(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ v,
                                                   float* __restrict__ u, long long n, const float* __restrict__ lr_dev, float rho,
                                                   float eps, float wd) {
+  pdl_entry();
   const float lr = lr_dev[0];
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float pi = p[i];
@@ -108,6 +112,6 @@ extern "C" int combat_adadelta(float* p, const float* g, float* square_avg, floa
                                float rho, float eps, float wd, void* stream) {
   COMBAT_ARG(p && g && square_avg && acc_delta && lr_dev, 0);
   if (n <= 0) return 0;
-  adadelta_k<<<det_grid(n), 256, 0, (cudaStream_t)stream>>>(p, g, square_avg, acc_delta, n, lr_dev, rho, eps, wd);
+  pdl_launch(adadelta_k, det_grid(n), 256, 0, (cudaStream_t)stream, p, g, square_avg, acc_delta, n, lr_dev, rho, eps, wd);
   COMBAT_RETURN_LAUNCH("adadelta");
 }

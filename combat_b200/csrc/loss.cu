@@ -9,6 +9,7 @@ __global__ void __launch_bounds__(1024) cross_entropy_k(const float* __restrict_
                                                         const long long* __restrict__ tgt2, int B, int C, float gscale,
                                                         float* __restrict__ loss_out, float* __restrict__ dlogits,
                                                         int* __restrict__ counts) {
+  pdl_entry();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   float loss_acc = 0.f;
   int c1 = 0, c2 = 0;
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(1024) cross_entropy_k(const float* __restrict_
 
 __global__ void __launch_bounds__(256) sum_scale_k(const float* __restrict__ partial, int n, float scale,
                                                    float* __restrict__ out) {
+  pdl_entry();
   double acc = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) acc += (double)partial[i];
   __shared__ double red[256];
@@ -116,13 +118,13 @@ extern "C" int combat_cross_entropy(const float* logits, const long long* target
                                     float grad_scale, float* loss_out, float* dlogits, int* counts_out, void* stream) {
   COMBAT_ARG(logits && targets, 0);
   COMBAT_ARG(B > 0 && C > 0, 3);
-  cross_entropy_k<<<1, 1024, 0, (cudaStream_t)stream>>>(logits, targets, targets2, B, C, grad_scale, loss_out, dlogits,
+  pdl_launch(cross_entropy_k, 1, 1024, 0, (cudaStream_t)stream, logits, targets, targets2, B, C, grad_scale, loss_out, dlogits,
                                                         counts_out);
   COMBAT_RETURN_LAUNCH("cross_entropy");
 }
 
 extern "C" int combat_sum_scale(const float* partial, int n, float scale, float* out, void* stream) {
   COMBAT_ARG(partial && out && n > 0, 0);
-  sum_scale_k<<<1, 256, 0, (cudaStream_t)stream>>>(partial, n, scale, out);
+  pdl_launch(sum_scale_k, 1, 256, 0, (cudaStream_t)stream, partial, n, scale, out);
   COMBAT_RETURN_LAUNCH("sum_scale");
 }

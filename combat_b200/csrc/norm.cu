@@ -82,6 +82,7 @@ __device__ __forceinline__ void block_reduce_y(float2& a, float2& b) {
 template <typename T>
 __global__ void __launch_bounds__(256) bn_stats_k(const T* __restrict__ x, long long R, int C, long long rows_per_block,
                                                   float* __restrict__ partial) {
+  pdl_entry();
   const int c = 2 * (blockIdx.y * CR_TX + threadIdx.x);
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   long long r1 = r0 + rows_per_block;
@@ -129,6 +130,7 @@ __global__ void bn_finalize_k(const float* __restrict__ partial, int nblk, long 
                               const float* __restrict__ gamma, const float* __restrict__ beta, float* running_mean,
                               float* running_var, float momentum, float eps, float* __restrict__ scale,
                               float* __restrict__ shift, float* save_mean, float* save_invstd) {
+  pdl_entry();
   const int c = blockIdx.x;
   const int lane = threadIdx.x;  // thread 0 finishes the channel
   float mean = 0.f, invstd = 0.f;
@@ -166,6 +168,7 @@ template <typename TX, typename T>
 __global__ void __launch_bounds__(256) affine_act_k(const TX* __restrict__ x, const T* __restrict__ res, T* __restrict__ y,
                                                     long long n2, int C, const float* __restrict__ scale,
                                                     const float* __restrict__ shift, int relu) {
+  pdl_entry();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
     const long long e = i * 2;
     const int c = (int)(e % C);
@@ -185,6 +188,7 @@ template <typename TX, typename T>
 __global__ void __launch_bounds__(256) affine_act_v8_k(const TX* __restrict__ x, const T* __restrict__ res, T* __restrict__ y,
                                                        long long n8, int C, const float* __restrict__ scale,
                                                        const float* __restrict__ shift, int relu) {
+  pdl_entry();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     const long long e = i * 8;
     const int c = (int)(e % C);
@@ -214,6 +218,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_k(const T* __restrict__ dy,
                                                        long long rows_per_block, const float* __restrict__ mean,
                                                        const float* __restrict__ invstd, float* __restrict__ partial,
                                                        int relu) {
+  pdl_entry();
   const int c = 2 * (blockIdx.y * CR_TX + threadIdx.x);
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   long long r1 = r0 + rows_per_block;
@@ -244,6 +249,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_k(const T* __restrict__ dy,
 
 __global__ void bn_bwd_finalize_k(const float* __restrict__ partial, int nblk, int C, float* __restrict__ dgamma,
                                   float* __restrict__ dbeta) {
+  pdl_entry();
   const int c = blockIdx.x;  // one block of 4 warps per channel
   double s = 0.0, sx = 0.0;
   for (int b = threadIdx.x; b < nblk; b += FIN_THREADS) {
@@ -265,6 +271,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_k(const T* __restrict__ dy, 
                                                       const float* __restrict__ mean, const float* __restrict__ invstd,
                                                       const float* __restrict__ dgamma, const float* __restrict__ dbeta,
                                                       const float* __restrict__ eval_scale, int relu) {
+  pdl_entry();
   const float invR = 1.f / (float)R;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
     const long long e = i * 2;
@@ -303,6 +310,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_v8_k(const T* __restrict__ d
                                                          const float* __restrict__ mean, const float* __restrict__ invstd,
                                                          const float* __restrict__ dgamma, const float* __restrict__ dbeta,
                                                          const float* __restrict__ eval_scale, int relu) {
+  pdl_entry();
   const float invR = 1.f / (float)R;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     const long long e = i * 8;
@@ -383,7 +391,7 @@ extern "C" int combat_bn_stats(const void* x, int dtype, long long R, int C, flo
   int nblk = cr_plan(R, max_blocks, &rpb);
   *nblk_out_host = nblk;
   dim3 grid(nblk, cdiv(C, CR_CPB)), block(CR_TX, CR_TY);
-  DISPATCH_DTYPE(dtype, bn_stats_k<T><<<grid, block, 0, (cudaStream_t)stream>>>((const T*)x, R, C, rpb, partial);)
+  DISPATCH_DTYPE(dtype, pdl_launch(bn_stats_k<T>, grid, block, 0, (cudaStream_t)stream, (const T*)x, R, C, rpb, partial);)
   COMBAT_RETURN_LAUNCH("bn_stats");
 }
 
@@ -392,7 +400,7 @@ extern "C" int combat_bn_finalize(const float* partial, int nblk, long long R, i
                                   float* shift, float* save_mean, float* save_invstd, void* stream) {
   COMBAT_ARG(scale && shift, 10);
   COMBAT_ARG(nblk > 0 ? partial != nullptr : (running_mean && running_var), 0);
-  bn_finalize_k<<<C, FIN_THREADS, 0, (cudaStream_t)stream>>>(partial, nblk, R, C, gamma, beta, running_mean, running_var,
+  pdl_launch(bn_finalize_k, C, FIN_THREADS, 0, (cudaStream_t)stream, partial, nblk, R, C, gamma, beta, running_mean, running_var,
                                                                 momentum, eps, scale, shift, save_mean, save_invstd);
   COMBAT_RETURN_LAUNCH("bn_finalize");
 }
@@ -409,6 +417,7 @@ __global__ void __launch_bounds__(256) bn_bwd_fused_k(const T* __restrict__ dy, 
                                                       const float* __restrict__ gamma, const float* __restrict__ mean,
                                                       const float* __restrict__ invstd, float* __restrict__ partial,
                                                       float* __restrict__ dgamma, float* __restrict__ dbeta, int relu) {
+  pdl_entry();
   namespace cg = cooperative_groups;
   cg::grid_group grid = cg::this_grid();
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -522,6 +531,7 @@ __global__ void __launch_bounds__(256) bn_bwd_fused_k(const T* __restrict__ dy, 
 // flattened channel i into the flat parameter / running-stat buffers
 __global__ void bn_eval_affine_k(const float* __restrict__ params, const float* __restrict__ bufs, const int4* __restrict__ table,
                                  int n, float eps, float* __restrict__ scale, float* __restrict__ shift) {
+  pdl_entry();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int4 t = table[i];
@@ -535,7 +545,7 @@ extern "C" int combat_bn_eval_affine(const float* params, const float* bufs, con
                                      float* shift, void* stream) {
   COMBAT_ARG(params && bufs && table4 && scale && shift, 0);
   if (n <= 0) return 0;
-  bn_eval_affine_k<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(params, bufs, (const int4*)table4, n, eps, scale, shift);
+  pdl_launch(bn_eval_affine_k, cdiv(n, 256), 256, 0, (cudaStream_t)stream, params, bufs, (const int4*)table4, n, eps, scale, shift);
   COMBAT_RETURN_LAUNCH("bn_eval_affine");
 }
 
@@ -547,11 +557,11 @@ extern "C" int combat_affine_act(const void* x, int x_dtype, const void* residua
   if (n2 <= 0) return 0;
   if ((C % 8) == 0) {
     const long long n8 = R * C / 8;
-    DISPATCH_2(x_dtype, dtype, affine_act_v8_k<TX, T><<<ew_grid(n8), 256, 0, (cudaStream_t)stream>>>(
+    DISPATCH_2(x_dtype, dtype, pdl_launch(affine_act_v8_k<TX, T>, ew_grid(n8), 256, 0, (cudaStream_t)stream, 
                                    (const TX*)x, (const T*)residual, (T*)y, n8, C, scale, shift, relu);)
     COMBAT_RETURN_LAUNCH("affine_act");
   }
-  DISPATCH_2(x_dtype, dtype, affine_act_k<TX, T><<<ew_grid(n2), 256, 0, (cudaStream_t)stream>>>(
+  DISPATCH_2(x_dtype, dtype, pdl_launch(affine_act_k<TX, T>, ew_grid(n2), 256, 0, (cudaStream_t)stream, 
                                  (const TX*)x, (const T*)residual, (T*)y, n2, C, scale, shift, relu);)
   COMBAT_RETURN_LAUNCH("affine_act");
 }
@@ -565,14 +575,14 @@ extern "C" int combat_bn_bwd_reduce(const void* dy, const void* x, int x_dtype, 
   int nblk = cr_plan(R, max_blocks, &rpb);
   *nblk_out_host = nblk;
   dim3 grid(nblk, cdiv(C, CR_CPB)), block(CR_TX, CR_TY);
-  DISPATCH_2(x_dtype, dtype, bn_bwd_reduce_k<TX, T><<<grid, block, 0, (cudaStream_t)stream>>>(
+  DISPATCH_2(x_dtype, dtype, pdl_launch(bn_bwd_reduce_k<TX, T>, grid, block, 0, (cudaStream_t)stream, 
                                  (const T*)dy, (const TX*)x, (const T*)y, R, C, rpb, mean, invstd, partial, relu);)
   COMBAT_RETURN_LAUNCH("bn_bwd_reduce");
 }
 
 extern "C" int combat_bn_bwd_finalize(const float* partial, int nblk, int C, float* dgamma, float* dbeta, void* stream) {
   COMBAT_ARG(partial && dgamma && dbeta && nblk > 0, 0);
-  bn_bwd_finalize_k<<<C, FIN_THREADS, 0, (cudaStream_t)stream>>>(partial, nblk, C, dgamma, dbeta);
+  pdl_launch(bn_bwd_finalize_k, C, FIN_THREADS, 0, (cudaStream_t)stream, partial, nblk, C, dgamma, dbeta);
   COMBAT_RETURN_LAUNCH("bn_bwd_finalize");
 }
 
@@ -587,12 +597,12 @@ extern "C" int combat_bn_bwd_apply(const void* dy, const void* x, int x_dtype, c
   if (n2 <= 0) return 0;
   if ((C % 8) == 0) {
     const long long n8 = R * C / 8;
-    DISPATCH_2(x_dtype, dtype, bn_bwd_apply_v8_k<TX, T><<<ew_grid(n8), 256, 0, (cudaStream_t)stream>>>(
+    DISPATCH_2(x_dtype, dtype, pdl_launch(bn_bwd_apply_v8_k<TX, T>, ew_grid(n8), 256, 0, (cudaStream_t)stream, 
                                    (const T*)dy, (const TX*)x, (const T*)y, (const T*)dadd, (T*)dx, (T*)dres, n8, R, C, gamma,
                                    mean, invstd, dgamma, dbeta, eval_scale, relu);)
     COMBAT_RETURN_LAUNCH("bn_bwd_apply");
   }
-  DISPATCH_2(x_dtype, dtype, bn_bwd_apply_k<TX, T><<<ew_grid(n2), 256, 0, (cudaStream_t)stream>>>(
+  DISPATCH_2(x_dtype, dtype, pdl_launch(bn_bwd_apply_k<TX, T>, ew_grid(n2), 256, 0, (cudaStream_t)stream, 
                                  (const T*)dy, (const TX*)x, (const T*)y, (const T*)dadd, (T*)dx, (T*)dres, n2, R, C, gamma,
                                  mean, invstd, dgamma, dbeta, eval_scale, relu);)
   COMBAT_RETURN_LAUNCH("bn_bwd_apply");
@@ -632,6 +642,7 @@ template <typename TX, typename T>
 __global__ void __launch_bounds__(256) instnorm_fwd_k(const TX* __restrict__ x, const T* __restrict__ skip, T* __restrict__ y,
                                                       int HW, int C, float eps, float slope, int act,
                                                       float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+  pdl_entry();
   const int n = blockIdx.x;
   const int c = 2 * (blockIdx.y * CR_TX + threadIdx.x);
   const bool ok = c < C;
@@ -688,6 +699,7 @@ __global__ void __launch_bounds__(256) instnorm_bwd_k(const T* __restrict__ dy1,
                                                       const TX* __restrict__ x, T* __restrict__ dx, int HW, int C,
                                                       float slope, int act, const float* __restrict__ mean_,
                                                       const float* __restrict__ invstd_) {
+  pdl_entry();
   const int n = blockIdx.x;
   const int c = 2 * (blockIdx.y * CR_TX + threadIdx.x);
   const bool ok = c < C;
@@ -743,7 +755,7 @@ extern "C" int combat_instnorm_fwd(const void* x, int x_dtype, const void* skip,
   COMBAT_ARG(x && y && save_mean && save_invstd, 0);
   COMBAT_ARG(N > 0 && HW > 0 && C > 0 && (C % 2) == 0, 4);
   dim3 grid(N, cdiv(C, CR_CPB)), block(CR_TX, CR_TY);
-  DISPATCH_2(x_dtype, dtype, instnorm_fwd_k<TX, T><<<grid, block, 0, (cudaStream_t)stream>>>(
+  DISPATCH_2(x_dtype, dtype, pdl_launch(instnorm_fwd_k<TX, T>, grid, block, 0, (cudaStream_t)stream, 
                                  (const TX*)x, (const T*)skip, (T*)y, HW, C, eps, slope, act, save_mean, save_invstd);)
   COMBAT_RETURN_LAUNCH("instnorm_fwd");
 }
@@ -753,7 +765,7 @@ extern "C" int combat_instnorm_bwd(const void* dy1, const void* dy2, const void*
   COMBAT_ARG(dy1 && x && dx && mean && invstd, 0);
   COMBAT_ARG(N > 0 && HW > 0 && C > 0 && (C % 2) == 0, 5);
   dim3 grid(N, cdiv(C, CR_CPB)), block(CR_TX, CR_TY);
-  DISPATCH_2(x_dtype, dtype, instnorm_bwd_k<TX, T><<<grid, block, 0, (cudaStream_t)stream>>>(
+  DISPATCH_2(x_dtype, dtype, pdl_launch(instnorm_bwd_k<TX, T>, grid, block, 0, (cudaStream_t)stream, 
                                  (const T*)dy1, (const T*)dy2, (const TX*)x, (T*)dx, HW, C, slope, act, mean, invstd);)
   COMBAT_RETURN_LAUNCH("instnorm_bwd");
 }
@@ -772,6 +784,7 @@ __device__ __forceinline__ void up_src(int o, int n_in, int& i0, int& i1, float&
 template <typename T>
 __global__ void __launch_bounds__(256) upsample2x_act_k(const T* __restrict__ x, T* __restrict__ y, long long total2, int H,
                                                         int W, int C, float slope) {
+  pdl_entry();
   const int C2 = C / 2, Ho = 2 * H, Wo = 2 * W;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total2; i += (long long)gridDim.x * blockDim.x) {
     const int c = 2 * (int)(i % C2);
@@ -799,6 +812,7 @@ __global__ void __launch_bounds__(256) upsample2x_act_k(const T* __restrict__ x,
 template <typename T>
 __global__ void __launch_bounds__(256) upsample2x_act_v8_k(const T* __restrict__ x, T* __restrict__ y, long long total8, int H,
                                                            int W, int C, float slope) {
+  pdl_entry();
   const int C8 = C / 8, Ho = 2 * H, Wo = 2 * W;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
     const int c = 8 * (int)(i % C8);
@@ -841,6 +855,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) upsample2x_act_bwd_k(const T* __restrict__ dy, const T* __restrict__ y,
                                                             T* __restrict__ dx, long long total2, int H, int W, int C,
                                                             float slope) {
+  pdl_entry();
   const int C2 = C / 2, Ho = 2 * H, Wo = 2 * W;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total2; i += (long long)gridDim.x * blockDim.x) {
     const int c = 2 * (int)(i % C2);
@@ -877,6 +892,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) upsample2x_act_bwd_v8_k(const T* __restrict__ dy, const T* __restrict__ y,
                                                                T* __restrict__ dx, long long total8, int H, int W, int C,
                                                                float slope) {
+  pdl_entry();
   const int C8 = C / 8, Ho = 2 * H, Wo = 2 * W;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
     const int c = 8 * (int)(i % C8);
@@ -919,11 +935,11 @@ extern "C" int combat_upsample2x_act(const void* x, void* y, int dtype, int N, i
   if (total2 <= 0) return 0;
   if ((C % 8) == 0) {
     const long long total8 = total2 / 4;
-    DISPATCH_DTYPE(dtype, upsample2x_act_v8_k<T><<<ew_grid(total8), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, total8, H,
+    DISPATCH_DTYPE(dtype, pdl_launch(upsample2x_act_v8_k<T>, ew_grid(total8), 256, 0, (cudaStream_t)stream, (const T*)x, (T*)y, total8, H,
                                                                                                    W, C, slope);)
     COMBAT_RETURN_LAUNCH("upsample2x_act");
   }
-  DISPATCH_DTYPE(dtype, upsample2x_act_k<T><<<ew_grid(total2), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, total2, H, W,
+  DISPATCH_DTYPE(dtype, pdl_launch(upsample2x_act_k<T>, ew_grid(total2), 256, 0, (cudaStream_t)stream, (const T*)x, (T*)y, total2, H, W,
                                                                                               C, slope);)
   COMBAT_RETURN_LAUNCH("upsample2x_act");
 }
@@ -936,11 +952,11 @@ extern "C" int combat_upsample2x_act_bwd(const void* dy, const void* y, void* dx
   if (total2 <= 0) return 0;
   if ((C % 8) == 0) {
     const long long total8 = total2 / 4;
-    DISPATCH_DTYPE(dtype, upsample2x_act_bwd_v8_k<T><<<ew_grid(total8), 256, 0, (cudaStream_t)stream>>>(
+    DISPATCH_DTYPE(dtype, pdl_launch(upsample2x_act_bwd_v8_k<T>, ew_grid(total8), 256, 0, (cudaStream_t)stream, 
                               (const T*)dy, (const T*)y, (T*)dx, total8, H, W, C, slope);)
     COMBAT_RETURN_LAUNCH("upsample2x_act_bwd");
   }
-  DISPATCH_DTYPE(dtype, upsample2x_act_bwd_k<T><<<ew_grid(total2), 256, 0, (cudaStream_t)stream>>>(
+  DISPATCH_DTYPE(dtype, pdl_launch(upsample2x_act_bwd_k<T>, ew_grid(total2), 256, 0, (cudaStream_t)stream, 
                             (const T*)dy, (const T*)y, (T*)dx, total2, H, W, C, slope);)
   COMBAT_RETURN_LAUNCH("upsample2x_act_bwd");
 }
@@ -948,6 +964,7 @@ extern "C" int combat_upsample2x_act_bwd(const void* dy, const void* y, void* dx
 // ------------------------------------------------------------------ elementwise
 template <typename T>
 __global__ void __launch_bounds__(256) leaky_relu_k(const T* __restrict__ x, T* __restrict__ y, long long n, float slope) {
+  pdl_entry();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float v = to_f<T>(x[i]);
     y[i] = from_f<T>(v > 0.f ? v : v * slope);
@@ -956,6 +973,7 @@ __global__ void __launch_bounds__(256) leaky_relu_k(const T* __restrict__ x, T* 
 template <typename T>
 __global__ void __launch_bounds__(256) leaky_relu_bwd_k(const T* __restrict__ dy, const T* __restrict__ x, T* __restrict__ dx,
                                                         long long n, float slope) {
+  pdl_entry();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float g = to_f<T>(dy[i]);
     dx[i] = from_f<T>(to_f<T>(x[i]) > 0.f ? g : g * slope);
@@ -963,6 +981,7 @@ __global__ void __launch_bounds__(256) leaky_relu_bwd_k(const T* __restrict__ dy
 }
 __global__ void __launch_bounds__(256) tanh_bwd_k(const float* __restrict__ dy, const float* __restrict__ y,
                                                   float* __restrict__ dz, long long n) {
+  pdl_entry();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float t = y[i];
     dz[i] = dy[i] * (1.f - t * t);
@@ -972,7 +991,7 @@ __global__ void __launch_bounds__(256) tanh_bwd_k(const float* __restrict__ dy, 
 extern "C" int combat_leaky_relu(const void* x, void* y, int dtype, long long n, float slope, void* stream) {
   COMBAT_ARG(x && y, 0);
   if (n <= 0) return 0;
-  DISPATCH_DTYPE(dtype, leaky_relu_k<T><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, n, slope);)
+  DISPATCH_DTYPE(dtype, pdl_launch(leaky_relu_k<T>, ew_grid(n), 256, 0, (cudaStream_t)stream, (const T*)x, (T*)y, n, slope);)
   COMBAT_RETURN_LAUNCH("leaky_relu");
 }
 extern "C" int combat_leaky_relu_bwd(const void* dy, const void* x, void* dx, int dtype, long long n, float slope,
@@ -980,13 +999,13 @@ extern "C" int combat_leaky_relu_bwd(const void* dy, const void* x, void* dx, in
   COMBAT_ARG(dy && x && dx, 0);
   if (n <= 0) return 0;
   DISPATCH_DTYPE(dtype,
-                 leaky_relu_bwd_k<T><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>((const T*)dy, (const T*)x, (T*)dx, n, slope);)
+                 pdl_launch(leaky_relu_bwd_k<T>, ew_grid(n), 256, 0, (cudaStream_t)stream, (const T*)dy, (const T*)x, (T*)dx, n, slope);)
   COMBAT_RETURN_LAUNCH("leaky_relu_bwd");
 }
 extern "C" int combat_tanh_bwd(const float* dy, const float* y, float* dz, long long n, void* stream) {
   COMBAT_ARG(dy && y && dz, 0);
   if (n <= 0) return 0;
-  tanh_bwd_k<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(dy, y, dz, n);
+  pdl_launch(tanh_bwd_k, ew_grid(n), 256, 0, (cudaStream_t)stream, dy, y, dz, n);
   COMBAT_RETURN_LAUNCH("tanh_bwd");
 }
 
@@ -994,6 +1013,7 @@ extern "C" int combat_tanh_bwd(const float* dy, const float* y, float* dz, long 
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_k(const T* __restrict__ x, long long R, int C, long long rows_per_block,
                                                 float* __restrict__ out) {
+  pdl_entry();
   const int c = 2 * (blockIdx.y * CR_TX + threadIdx.x);
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   long long r1 = r0 + rows_per_block;
@@ -1015,7 +1035,7 @@ extern "C" int combat_colsum(const void* x, int dtype, long long R, int C, float
   long long rpb;
   int nblk = cr_plan(R, 128, &rpb);
   dim3 grid(nblk, cdiv(C, CR_CPB)), block(CR_TX, CR_TY);
-  DISPATCH_DTYPE(dtype, colsum_k<T><<<grid, block, 0, (cudaStream_t)stream>>>((const T*)x, R, C, rpb, out);)
+  DISPATCH_DTYPE(dtype, pdl_launch(colsum_k<T>, grid, block, 0, (cudaStream_t)stream, (const T*)x, R, C, rpb, out);)
   COMBAT_RETURN_LAUNCH("colsum");
 }
 
@@ -1025,6 +1045,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) pool_linear_fwd_k(const T* __restrict__ x, int Hf, int Wf, int C, int P,
                                                          const float* __restrict__ Wt, const float* __restrict__ bias,
                                                          int ncls, float* __restrict__ pooled, float* __restrict__ logits) {
+  pdl_entry();
   extern __shared__ float feat[];  // F
   const int b = blockIdx.x;
   const int ph = Hf / P, pw = Wf / P, F = C * ph * pw;
@@ -1055,6 +1076,7 @@ __global__ void __launch_bounds__(256) pool_linear_fwd_k(const T* __restrict__ x
 template <typename T>
 __global__ void __launch_bounds__(256) pool_linear_bwd_dx_k(const float* __restrict__ dlogits, const float* __restrict__ Wt,
                                                             int Hf, int Wf, int C, int P, int ncls, T* __restrict__ dx) {
+  pdl_entry();
   extern __shared__ float dfeat[];  // F
   __shared__ float dl[64];
   const int b = blockIdx.x;
@@ -1096,6 +1118,7 @@ __global__ void __launch_bounds__(256) pool_linear_bwd_dx_k(const float* __restr
 // grid (F / 32, ncls), block (32 features, 8 batch slices): fixed-order shared-memory reduction over the slices
 __global__ void __launch_bounds__(256) linear_wgrad_k(const float* __restrict__ dlogits, const float* __restrict__ pooled,
                                                       int B, int F, int ncls, float* __restrict__ dW, float* __restrict__ db) {
+  pdl_entry();
   __shared__ float red[8][33];
   const int f = blockIdx.x * 32 + threadIdx.x;
   const int k = blockIdx.y;
@@ -1131,7 +1154,7 @@ extern "C" int combat_pool_linear_fwd(const void* x, int dtype, int B, int Hf, i
   COMBAT_ARG(smem <= 200 * 1024, 5);
   DISPATCH_DTYPE(dtype, {
     cudaFuncSetAttribute(pool_linear_fwd_k<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    pool_linear_fwd_k<T><<<B, 256, smem, (cudaStream_t)stream>>>((const T*)x, Hf, Wf, C, P, W, b, ncls, pooled, logits);
+    pdl_launch(pool_linear_fwd_k<T>, B, 256, smem, (cudaStream_t)stream, (const T*)x, Hf, Wf, C, P, W, b, ncls, pooled, logits);
   })
   COMBAT_RETURN_LAUNCH("pool_linear_fwd");
 }
@@ -1145,14 +1168,14 @@ extern "C" int combat_pool_linear_bwd(const float* dlogits, const float* pooled,
   if (dx) {
     DISPATCH_DTYPE(dtype, {
       cudaFuncSetAttribute(pool_linear_bwd_dx_k<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      pool_linear_bwd_dx_k<T><<<B, 256, smem, (cudaStream_t)stream>>>(dlogits, W, Hf, Wf, C, P, ncls, (T*)dx);
+      pdl_launch(pool_linear_bwd_dx_k<T>, B, 256, smem, (cudaStream_t)stream, dlogits, W, Hf, Wf, C, P, ncls, (T*)dx);
     })
     COMBAT_CHECK_LAUNCH("pool_linear_bwd_dx");
   }
   if (dW) {
     COMBAT_ARG(pooled && db, 1);
     dim3 grid(cdiv(F, 32), ncls), block(32, 8);
-    linear_wgrad_k<<<grid, block, 0, (cudaStream_t)stream>>>(dlogits, pooled, B, F, ncls, dW, db);
+    pdl_launch(linear_wgrad_k, grid, block, 0, (cudaStream_t)stream, dlogits, pooled, B, F, ncls, dW, db);
     COMBAT_CHECK_LAUNCH("linear_wgrad");
   }
   return 0;
@@ -1162,6 +1185,7 @@ extern "C" int combat_pool_linear_bwd(const float* dlogits, const float* pooled,
 template <typename T>
 __global__ void __launch_bounds__(256) maxpool2_k(const T* __restrict__ x, T* __restrict__ y, long long total, int H, int W,
                                                   int C) {
+  pdl_entry();
   const int Ho = H / 2, Wo = W / 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
@@ -1178,6 +1202,7 @@ __global__ void __launch_bounds__(256) maxpool2_k(const T* __restrict__ x, T* __
 template <typename T>
 __global__ void __launch_bounds__(256) maxpool2_v8_k(const T* __restrict__ x, T* __restrict__ y, long long total8, int H, int W,
                                                      int C) {
+  pdl_entry();
   const int Ho = H / 2, Wo = W / 2, C8 = C / 8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
     const int c = 8 * (int)(i % C8);
@@ -1202,16 +1227,17 @@ extern "C" int combat_maxpool2(const void* x, void* y, int dtype, int N, int H, 
   long long total = (long long)N * (H / 2) * (W / 2) * C;
   if (total <= 0) return 0;
   if ((C % 8) == 0) {
-    DISPATCH_DTYPE(dtype, maxpool2_v8_k<T><<<ew_grid(total / 8), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, total / 8, H, W, C);)
+    DISPATCH_DTYPE(dtype, pdl_launch(maxpool2_v8_k<T>, ew_grid(total / 8), 256, 0, (cudaStream_t)stream, (const T*)x, (T*)y, total / 8, H, W, C);)
     COMBAT_RETURN_LAUNCH("maxpool2");
   }
-  DISPATCH_DTYPE(dtype, maxpool2_k<T><<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, total, H, W, C);)
+  DISPATCH_DTYPE(dtype, pdl_launch(maxpool2_k<T>, ew_grid(total), 256, 0, (cudaStream_t)stream, (const T*)x, (T*)y, total, H, W, C);)
   COMBAT_RETURN_LAUNCH("maxpool2");
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256) nchw_to_nhwc_k(const float* __restrict__ x, T* __restrict__ y, long long total, int C,
                                                       int HW) {
+  pdl_entry();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
     long long p = i / C;
@@ -1223,6 +1249,7 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_k(const float* __restrict__ 
 template <typename T>
 __global__ void __launch_bounds__(256) nhwc_to_nchw_k(const T* __restrict__ x, float* __restrict__ y, long long total, int C,
                                                       int HW) {
+  pdl_entry();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int hw = (int)(i % HW);
     long long p = i / HW;
@@ -1235,14 +1262,14 @@ extern "C" int combat_nchw_to_nhwc(const float* x, void* y, int dtype, int N, in
   COMBAT_ARG(x && y, 0);
   long long total = (long long)N * C * H * W;
   if (total <= 0) return 0;
-  DISPATCH_DTYPE(dtype, nchw_to_nhwc_k<T><<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(x, (T*)y, total, C, H * W);)
+  DISPATCH_DTYPE(dtype, pdl_launch(nchw_to_nhwc_k<T>, ew_grid(total), 256, 0, (cudaStream_t)stream, x, (T*)y, total, C, H * W);)
   COMBAT_RETURN_LAUNCH("nchw_to_nhwc");
 }
 extern "C" int combat_nhwc_to_nchw(const void* x, int dtype, float* y, int N, int C, int H, int W, void* stream) {
   COMBAT_ARG(x && y, 0);
   long long total = (long long)N * C * H * W;
   if (total <= 0) return 0;
-  DISPATCH_DTYPE(dtype, nhwc_to_nchw_k<T><<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>((const T*)x, y, total, C, H * W);)
+  DISPATCH_DTYPE(dtype, pdl_launch(nhwc_to_nchw_k<T>, ew_grid(total), 256, 0, (cudaStream_t)stream, (const T*)x, y, total, C, H * W);)
   COMBAT_RETURN_LAUNCH("nhwc_to_nchw");
 }
 
@@ -1250,6 +1277,7 @@ extern "C" int combat_nhwc_to_nchw(const void* x, int dtype, float* y, int N, in
 template <typename T>
 __global__ void __launch_bounds__(256) onehot_planes_k(T* __restrict__ y, const long long* __restrict__ labels, long long total,
                                                        int HW, int Ctot, int c_off, int ncls) {
+  pdl_entry();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int k = (int)(i % ncls);
     const long long pix = i / ncls;
@@ -1262,7 +1290,7 @@ extern "C" int combat_onehot_planes(void* y, int dtype, const long long* labels,
   COMBAT_ARG(y && labels, 0);
   long long total = (long long)N * HW * ncls;
   if (total <= 0) return 0;
-  DISPATCH_DTYPE(dtype, onehot_planes_k<T><<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>((T*)y, labels, total, HW, Ctot,
+  DISPATCH_DTYPE(dtype, pdl_launch(onehot_planes_k<T>, ew_grid(total), 256, 0, (cudaStream_t)stream, (T*)y, labels, total, HW, Ctot,
                                                                                             c_off, ncls);)
   COMBAT_RETURN_LAUNCH("onehot_planes");
 }
@@ -1272,6 +1300,7 @@ extern "C" int combat_onehot_planes(void* y, int dtype, const long long* labels,
 template <typename T>
 __global__ void __launch_bounds__(256) lrelu_into_slice_k(const T* __restrict__ src, T* __restrict__ dst, long long total,
                                                           int Csrc, int Cdst, int c_off, float slope) {
+  pdl_entry();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % Csrc);
     const long long pix = i / Csrc;
@@ -1284,7 +1313,7 @@ extern "C" int combat_lrelu_into_slice(const void* src, void* dst, int dtype, lo
   COMBAT_ARG(src && dst && c_off + Csrc <= Cdst, 0);
   long long total = npix * Csrc;
   if (total <= 0) return 0;
-  DISPATCH_DTYPE(dtype, lrelu_into_slice_k<T><<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>((const T*)src, (T*)dst, total,
+  DISPATCH_DTYPE(dtype, pdl_launch(lrelu_into_slice_k<T>, ew_grid(total), 256, 0, (cudaStream_t)stream, (const T*)src, (T*)dst, total,
                                                                                                Csrc, Cdst, c_off, slope);)
   COMBAT_RETURN_LAUNCH("lrelu_into_slice");
 }

@@ -6,6 +6,7 @@
 __global__ void __launch_bounds__(256) sgd_nesterov_k(float* __restrict__ p, const float* __restrict__ g,
                                                       float* __restrict__ buf, long long n4, long long n,
                                                       const float* __restrict__ lr_dev, float mu, float wd, int first) {
+  pdl_entry();
   const float lr = lr_dev[0];
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -42,7 +43,7 @@ extern "C" int combat_sgd_nesterov(float* p, const float* g, float* buf, long lo
   int grid = (int)((n4 + 255) / 256);
   if (grid > 148 * 16) grid = 148 * 16;
   if (grid < 1) grid = 1;
-  sgd_nesterov_k<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, buf, n4, n, lr_dev, momentum, wd, first_step);
+  pdl_launch(sgd_nesterov_k, grid, 256, 0, (cudaStream_t)stream, p, g, buf, n4, n, lr_dev, momentum, wd, first_step);
   COMBAT_RETURN_LAUNCH("sgd_nesterov");
 }
 
@@ -52,6 +53,7 @@ extern "C" int combat_sgd_nesterov(float* p, const float* g, float* buf, long lo
 template <typename T>
 __global__ void __launch_bounds__(256) prep_weights_k(const float* __restrict__ params, T* __restrict__ wbuf,
                                                       const combat_wprep_desc* __restrict__ table) {
+  pdl_entry();
   __shared__ float tile[32][33];
   const combat_wprep_desc d = table[blockIdx.y];
   const int KK = d.KH * d.KW;
@@ -96,6 +98,6 @@ extern "C" int combat_prep_weights(const float* params, void* wbuf, int dtype, c
   if (gx > 592) gx = 592;  // the big layers need ~2300 tiles: latency-bound below ~4 blocks per SM per descriptor
   if (gx < 1) gx = 1;
   dim3 grid(gx, n_desc);
-  DISPATCH_DTYPE(dtype, prep_weights_k<T><<<grid, 256, 0, (cudaStream_t)stream>>>(params, (T*)wbuf, table_dev);)
+  DISPATCH_DTYPE(dtype, pdl_launch(prep_weights_k<T>, grid, 256, 0, (cudaStream_t)stream, params, (T*)wbuf, table_dev);)
   COMBAT_RETURN_LAUNCH("prep_weights");
 }
