@@ -499,7 +499,6 @@ class AlternatedStep:
     # ---- data-parallel exchange: started on a communication stream right after the backward that produced the gradients,
     # joined just before the optimiser step that consumes them; the flat gradient goes out in COMM_BUCKETS contiguous buckets
     COMM_BUCKETS = 4
-
     def _exchange_start(self, which):
         if not self._parallel:
             return
@@ -511,7 +510,7 @@ class AlternatedStep:
                 self.buf_hook(self.netC.bufs)
             return
         if self._comm is None:
-            self._comm = torch.cuda.Stream(device=self.device)
+            self._comm = torch.cuda.Stream(device=self.device, priority=-1)   # its CTAs are scheduled ahead of the compute stream's
         ev = torch.cuda.Event()
         ev.record(main)
         self._comm.wait_event(ev)
