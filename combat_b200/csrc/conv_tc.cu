@@ -106,6 +106,25 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- issue discipline of the TMA and MMA warps.  These warps run their loops CONVERGED (all 32 lanes) and hand the asynchronous
+// instructions to one lane with elect.sync.  Inside a divergent `if (lane == 0)` region nvcc cannot prove that descriptors, tensor
+// memory addresses and barrier addresses are warp-uniform, so every UTCHMMA / UTMALDG / UTCBAR (they take UNIFORM registers) is
+// wrapped in R2UR moves and an ELECT / BRA.U.ANY loop: ~93 cycles per tcgen05.mma on B200, i.e. the issuing thread -- not the
+// tensor pipe or the shared-memory port -- paced every tile narrower than 256 columns (scripts/mma_rate.cu,
+// profiles/r02_mma_issue.md: N = 64: 93 -> 48 cycles per MMA, N = 128: 93 -> 64 = the pipe's floor).  In converged code the same
+// values live in uniform registers and the four MMAs of a K chunk are four consecutive UTCHMMA instructions.
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n.reg .b32 %%rx;\n.reg .pred %%px;\nelect.sync %%rx|%%px, %1;\n@%%px mov.s32 %0, 1;\n}\n"
+      : "+r"(pred)
+      : "r"(0xffffffffu));
+  return pred;
+}
+// warp index / any value the compiler must treat as warp-uniform
+__device__ __forceinline__ int uniform_i(int v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ uint32_t uniform_u(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 // ---- CTA pairs (cta_group::2): two CTAs of a cluster (the two SMs of a TPC) execute ONE 256-row MMA; each stages its own 128
 // rows of A and HALF of B, so per SM the shared-memory traffic of the B operand (TMA writes and MMA reads) is halved.
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -561,7 +580,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   uint64_t* tempty_bar = bars + 2 * Cfg::STAGES + 2;
   uint32_t* tmem_ptr_smem = (uint32_t*)(bars + 2 * Cfg::STAGES + 4);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_i(threadIdx.x >> 5), lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.w);
@@ -580,79 +599,88 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tmem_base = uniform_u(*tmem_ptr_smem);
   pdl_wait();  // barriers initialised, tensor memory allocated: nothing above touched global memory
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        int cls, nt, ht, wt, cot;
-        decode_tile(p, tile, cls, nt, ht, wt, cot);
-        const int ntaps = p.taps.ntaps[cls];
-        for (int t = 0; t < ntaps; ++t) {
-          const CUtensorMap* amap = &maps.in[p.taps.view[cls][t]];
-          const int cw = wt * p.BW + p.taps.dw[cls][t];
-          const int ch = ht * p.BH + p.taps.dh[cls][t];
-          const int cn = nt * p.BNI;
-          const int wtap = p.taps.wtap[cls][t];
-          const CUtensorMap* wmap = p.taps.wsel[cls][t] ? &maps.w2 : &maps.w;
-          for (int kc = 0; kc < p.kchunks; ++kc) {
-            const long long t0 = p.dbg ? clock64() : 0;
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            if (p.dbg) p.dbg[blockIdx.x * 8 + 0] += clock64() - t0;   // producer waiting for a free slot
-            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-            uint8_t* sb = sa + Cfg::A_BYTES;
+    // ===================== TMA producer (converged warp, one elected lane issues) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    long long w_empty = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int cls, nt, ht, wt, cot;
+      decode_tile(p, tile, cls, nt, ht, wt, cot);
+      const int ntaps = p.taps.ntaps[cls];
+      for (int t = 0; t < ntaps; ++t) {
+        const CUtensorMap* amap = &maps.in[p.taps.view[cls][t]];
+        const int cw = wt * p.BW + p.taps.dw[cls][t];
+        const int ch = ht * p.BH + p.taps.dh[cls][t];
+        const int cn = nt * p.BNI;
+        const int wtap = p.taps.wtap[cls][t];
+        const CUtensorMap* wmap = p.taps.wsel[cls][t] ? &maps.w2 : &maps.w;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          const long long t0 = p.dbg ? clock64() : 0;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (p.dbg) w_empty += clock64() - t0;   // producer waiting for a free slot
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          if (elect_one_sync()) {
             mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
             tma_load_4d(sa, amap, &full_bar[stage], kc * KCHUNK, cw, ch, cn);
             tma_load_3d(sb, wmap, &full_bar[stage], kc * KCHUNK, wtap, cot * BLOCK_N);
-            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
           }
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
+    if (p.dbg && lane == 0) p.dbg[blockIdx.x * 8 + 0] += w_empty;
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(TILE_M, BLOCK_N, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      const long long tstart = p.dbg ? clock64() : 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        if (p.dbg) p.dbg[blockIdx.x * 8 + 3] = clock64() - tstart;  // (time up to the start of the last tile)
-        int cls, nt, ht, wt, cot;
-        decode_tile(p, tile, cls, nt, ht, wt, cot);
-        const int kiters = p.taps.ntaps[cls] * p.kchunks;
-        if (kiters == 0) continue;
-        long long t0 = p.dbg ? clock64() : 0;
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-        if (p.dbg) p.dbg[blockIdx.x * 8 + 1] += clock64() - t0;     // MMA thread waiting for the epilogue (accumulator buffer)
+    // ===================== MMA issuer (converged warp, one elected lane issues) =====================
+    constexpr uint32_t idesc = make_idesc(TILE_M, BLOCK_N, 0, 0);
+    const uint32_t smem_base = smem_u32(smem);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    long long w_tempty = 0, w_full = 0, t_last = 0;
+    const long long tstart = p.dbg ? clock64() : 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      if (p.dbg) t_last = clock64() - tstart;  // (time up to the start of the last tile)
+      int cls, nt, ht, wt, cot;
+      decode_tile(p, tile, cls, nt, ht, wt, cot);
+      const int kiters = p.taps.ntaps[cls] * p.kchunks;
+      if (kiters == 0) continue;
+      long long t0 = p.dbg ? clock64() : 0;
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      if (p.dbg) w_tempty += clock64() - t0;     // MMA warp waiting for the epilogue (accumulator buffer)
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      for (int it = 0; it < kiters; ++it) {
+        t0 = p.dbg ? clock64() : 0;
+        mbar_wait(&full_bar[stage], phase);
+        if (p.dbg) w_full += clock64() - t0;     // MMA warp waiting for operands (TMA)
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int it = 0; it < kiters; ++it) {
-          t0 = p.dbg ? clock64() : 0;
-          mbar_wait(&full_bar[stage], phase);
-          if (p.dbg) p.dbg[blockIdx.x * 8 + 2] += clock64() - t0;   // MMA thread waiting for operands (TMA)
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint32_t sb = sa + Cfg::A_BYTES;
-          const uint64_t adesc = make_smem_desc(sa, 16, 1024);
-          const uint64_t bdesc = make_smem_desc(sb, 16, 1024);
+        const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+        const uint32_t sb = sa + Cfg::A_BYTES;
+        const uint64_t adesc = make_smem_desc(sa, 16, 1024);
+        const uint64_t bdesc = make_smem_desc(sb, 16, 1024);
+        if (elect_one_sync()) {
 #pragma unroll
           for (int k = 0; k < KCHUNK / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
             umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
+      if (elect_one_sync()) umma_commit(&tfull_bar[acc]);  // accumulator complete
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (p.dbg && lane == 0) {
+      p.dbg[blockIdx.x * 8 + 1] += w_tempty;
+      p.dbg[blockIdx.x * 8 + 2] += w_full;
+      p.dbg[blockIdx.x * 8 + 3] = t_last;
     }
   } else {
     tc_epilogue<BLOCK_N, MODE>(p, smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256, tmem_base, tfull_bar, tempty_bar, warp, lane);
@@ -698,8 +726,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
   uint64_t* tempty_bar = bars + 2 * Cfg::STAGES + 2;
   uint32_t* tmem_ptr_smem = (uint32_t*)(bars + 2 * Cfg::STAGES + 4);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  const int warp = uniform_i(threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const uint32_t rank = uniform_u(cluster_ctarank());
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.w);
@@ -719,76 +747,87 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
   __syncthreads();
   cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / multicast commit / remote complete_tx
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tmem_base = uniform_u(*tmem_ptr_smem);
   pdl_wait();  // barriers initialised, tensor memory allocated: nothing above touched global memory
 
   if (warp == 0) {
-    // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        int cls, nt, ht, wt, cot;
-        decode_tile(p, tile, cls, nt, ht, wt, cot);
-        const int ntaps = p.taps.ntaps[cls];
-        for (int t = 0; t < ntaps; ++t) {
-          const CUtensorMap* amap = &maps.in[p.taps.view[cls][t]];
-          const int cw = wt * p.BW + p.taps.dw[cls][t];
-          const int ch = ht * p.BH + p.taps.dh[cls][t];
-          const int cn = nt * p.BNI;
-          const int wtap = p.taps.wtap[cls][t];
-          const CUtensorMap* wmap = p.taps.wsel[cls][t] ? &maps.w2 : &maps.w;
-          for (int kc = 0; kc < p.kchunks; ++kc) {
-            const long long t0 = p.dbg ? clock64() : 0;
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            if (p.dbg) p.dbg[blockIdx.x * 8 + 0] += clock64() - t0;   // producer waiting for a free slot
-            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-            uint8_t* sb = sa + Cfg::A_BYTES;
-            const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
+    // ===================== TMA producer (both CTAs; converged warp, one elected lane issues) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    long long w_empty = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int cls, nt, ht, wt, cot;
+      decode_tile(p, tile, cls, nt, ht, wt, cot);
+      const int ntaps = p.taps.ntaps[cls];
+      for (int t = 0; t < ntaps; ++t) {
+        const CUtensorMap* amap = &maps.in[p.taps.view[cls][t]];
+        const int cw = wt * p.BW + p.taps.dw[cls][t];
+        const int ch = ht * p.BH + p.taps.dh[cls][t];
+        const int cn = nt * p.BNI;
+        const int wtap = p.taps.wtap[cls][t];
+        const CUtensorMap* wmap = p.taps.wsel[cls][t] ? &maps.w2 : &maps.w;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          const long long t0 = p.dbg ? clock64() : 0;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (p.dbg) w_empty += clock64() - t0;   // producer waiting for a free slot
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          if (elect_one_sync()) {
             if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
             tma_load_4d_2sm(sa, amap, lead_full, kc * KCHUNK, cw, ch, cn);
             tma_load_3d_2sm(sb, wmap, lead_full, kc * KCHUNK, wtap, cot * BLOCK_N + (int)rank * (BLOCK_N / 2));
-            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
           }
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
+    if (p.dbg && lane == 0) p.dbg[blockIdx.x * 8 + 0] += w_empty;
   } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA only) =====================
-    if (lane == 0 && rank == 0) {
+    // ===================== MMA issuer (leader CTA only; converged warp, one elected lane issues) =====================
+    if (rank == 0) {
       constexpr uint32_t idesc = make_idesc(2 * TILE_M, BLOCK_N, 0, 0);
+      const uint32_t smem_base = smem_u32(smem);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      long long w_tempty = 0, w_full = 0, t_last = 0;
       const long long tstart = p.dbg ? clock64() : 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        if (p.dbg) p.dbg[blockIdx.x * 8 + 3] = clock64() - tstart;  // (time up to the start of the last tile)
+        if (p.dbg) t_last = clock64() - tstart;  // (time up to the start of the last tile)
         int cls, nt, ht, wt, cot;
         decode_tile(p, tile, cls, nt, ht, wt, cot);
         const int kiters = p.taps.ntaps[cls] * p.kchunks;
         if (kiters == 0) continue;
         long long t0 = p.dbg ? clock64() : 0;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-        if (p.dbg) p.dbg[blockIdx.x * 8 + 1] += clock64() - t0;     // MMA thread waiting for the epilogue (accumulator buffer)
+        if (p.dbg) w_tempty += clock64() - t0;     // MMA warp waiting for the epilogue (accumulator buffer)
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
         for (int it = 0; it < kiters; ++it) {
           t0 = p.dbg ? clock64() : 0;
           mbar_wait(&full_bar[stage], phase);
-          if (p.dbg) p.dbg[blockIdx.x * 8 + 2] += clock64() - t0;   // MMA thread waiting for operands (TMA)
+          if (p.dbg) w_full += clock64() - t0;     // MMA warp waiting for operands (TMA)
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t sb = sa + Cfg::A_BYTES;
           const uint64_t adesc = make_smem_desc(sa, 16, 1024);
           const uint64_t bdesc = make_smem_desc(sb, 16, 1024);
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < KCHUNK / 16; ++k) umma_bf16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
-          umma_commit_2sm(&empty_bar[stage]);  // frees the slot in both CTAs
+            for (int k = 0; k < KCHUNK / 16; ++k) umma_bf16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+            umma_commit_2sm(&empty_bar[stage]);  // frees the slot in both CTAs
+          }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit_2sm(&tfull_bar[acc]);  // accumulator complete, both CTAs
+        if (elect_one_sync()) umma_commit_2sm(&tfull_bar[acc]);  // accumulator complete, both CTAs
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      if (p.dbg && lane == 0) {
+        p.dbg[blockIdx.x * 8 + 1] += w_tempty;
+        p.dbg[blockIdx.x * 8 + 2] += w_full;
+        p.dbg[blockIdx.x * 8 + 3] = t_last;
       }
     }
   } else {
@@ -833,7 +872,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc64_kernel(const __grid_c
   uint64_t* tempty_bar = bars + 2 * Tc64Cfg::STAGES + 2;
   uint64_t* w_bar = bars + 2 * Tc64Cfg::STAGES + 4;
   uint32_t* tmem_ptr_smem = (uint32_t*)(bars + 2 * Tc64Cfg::STAGES + 5);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_i(threadIdx.x >> 5), lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.w);
@@ -853,55 +892,60 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc64_kernel(const __grid_c
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tmem_base = uniform_u(*tmem_ptr_smem);
   pdl_wait();  // barriers initialised, tensor memory allocated: nothing above touched global memory
 
   if (warp == 0) {
-    if (lane == 0) {
+    // TMA producer: converged warp, one elected lane issues
+    if (elect_one_sync()) {
       mbar_expect_tx(w_bar, Tc64Cfg::W_BYTES);
       for (int t = 0; t < 9; ++t) tma_load_3d(wsm + t * 8192, &maps.w, w_bar, 0, t, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      long long w_empty = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        int cls, nt, ht, wt, cot;
-        decode_tile(p, tile, cls, nt, ht, wt, cot);
-        for (int dw = -1; dw <= 1; ++dw) {
-          const long long t0 = p.dbg ? clock64() : 0;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (p.dbg) w_empty += clock64() - t0;
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    long long w_empty = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int cls, nt, ht, wt, cot;
+      decode_tile(p, tile, cls, nt, ht, wt, cot);
+      for (int dw = -1; dw <= 1; ++dw) {
+        const long long t0 = p.dbg ? clock64() : 0;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (p.dbg) w_empty += clock64() - t0;
+        if (elect_one_sync()) {
           mbar_expect_tx(&full_bar[stage], stage_bytes);
           tma_load_4d(stages + stage * stage_bytes, &maps.in[0], &full_bar[stage], 0, dw, ht * p.BH - 1, nt);
-          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
+        if (++stage == n_stages) { stage = 0; phase ^= 1; }
       }
-      if (p.dbg) p.dbg[blockIdx.x * 8 + 0] += w_empty;
     }
+    if (p.dbg && lane == 0) p.dbg[blockIdx.x * 8 + 0] += w_empty;
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(TILE_M, 64, 0, 0);
-      long long w_tempty = 0, w_full = 0;
-      mbar_wait(w_bar, 0);
+    // MMA issuer: converged warp, one elected lane issues
+    constexpr uint32_t idesc = make_idesc(TILE_M, 64, 0, 0);
+    long long w_tempty = 0, w_full = 0;
+    mbar_wait(w_bar, 0);
+    tc_fence_after();
+    const uint32_t wbase = smem_u32(wsm);
+    const uint32_t sbase = smem_u32(stages);
+    const uint32_t row_step = (uint32_t)p.BW * 128;  // one image row of the staged box
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const long long tstart = p.dbg ? clock64() : 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      long long t0 = p.dbg ? clock64() : 0;
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      if (p.dbg) w_tempty += clock64() - t0;
       tc_fence_after();
-      const uint32_t wbase = smem_u32(wsm);
-      const uint32_t row_step = (uint32_t)p.BW * 128;  // one image row of the staged box
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      const long long tstart = p.dbg ? clock64() : 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        long long t0 = p.dbg ? clock64() : 0;
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-        if (p.dbg) w_tempty += clock64() - t0;
+      const uint32_t d_tmem = tmem_base + acc * 64;
+      for (int dwi = 0; dwi < 3; ++dwi) {
+        t0 = p.dbg ? clock64() : 0;
+        mbar_wait(&full_bar[stage], phase);
+        if (p.dbg) w_full += clock64() - t0;
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * 64;
-        for (int dwi = 0; dwi < 3; ++dwi) {
-          t0 = p.dbg ? clock64() : 0;
-          mbar_wait(&full_bar[stage], phase);
-          if (p.dbg) w_full += clock64() - t0;
-          tc_fence_after();
-          const uint32_t sa = smem_u32(stages + stage * stage_bytes);
+        const uint32_t sa = sbase + stage * stage_bytes;
+        if (elect_one_sync()) {
 #pragma unroll
           for (int dhi = 0; dhi < 3; ++dhi) {
             const uint64_t adesc = make_smem_desc(sa + dhi * row_step, 16, 1024);
@@ -910,16 +954,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc64_kernel(const __grid_c
             for (int k = 0; k < KCHUNK / 16; ++k) umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (dwi | dhi | k) != 0);
           }
           umma_commit(&empty_bar[stage]);
-          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++stage == n_stages) { stage = 0; phase ^= 1; }
       }
-      if (p.dbg) {
-        p.dbg[blockIdx.x * 8 + 1] += w_tempty;
-        p.dbg[blockIdx.x * 8 + 2] += w_full;
-        p.dbg[blockIdx.x * 8 + 3] += clock64() - tstart;
-      }
+      if (elect_one_sync()) umma_commit(&tfull_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (p.dbg && lane == 0) {
+      p.dbg[blockIdx.x * 8 + 1] += w_tempty;
+      p.dbg[blockIdx.x * 8 + 2] += w_full;
+      p.dbg[blockIdx.x * 8 + 3] += clock64() - tstart;
     }
   } else {
     tc_epilogue<64, MODE>(p, tail + 256, tmem_base, tfull_bar, tempty_bar, warp, lane);
@@ -1293,7 +1337,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_kernel(const __grid_cons
   uint64_t* empty_bar = bars + Cfg::STAGES;
   uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;
   uint32_t* tmem_ptr_smem = (uint32_t*)(bars + 2 * Cfg::STAGES + 1);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_i(threadIdx.x >> 5), lane = threadIdx.x & 31;
 
   const int m_tile = blockIdx.x % p.m_tiles, n_tile = blockIdx.x / p.m_tiles;
   const int box0 = blockIdx.y * p.boxes_per_split;
@@ -1315,7 +1359,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_kernel(const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tmem_base = uniform_u(*tmem_ptr_smem);
   pdl_wait();  // barriers initialised, tensor memory allocated: nothing above touched global memory
 
   // the two 64-row blocks of this M tile
@@ -1329,16 +1373,17 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_kernel(const __grid_cons
   }
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int b = box0; b < box1; ++b) {
-        const int wt = b % p.tiles_w;
-        const int r2 = b / p.tiles_w;
-        const int ht = r2 % p.tiles_h, nt = r2 / p.tiles_h;
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-        uint8_t* sb = sa + Cfg::A_BYTES;
+    // TMA producer: converged warp, one elected lane issues
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int b = box0; b < box1; ++b) {
+      const int wt = b % p.tiles_w;
+      const int r2 = b / p.tiles_w;
+      const int ht = r2 % p.tiles_h, nt = r2 / p.tiles_h;
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+      uint8_t* sb = sa + Cfg::A_BYTES;
+      if (elect_one_sync()) {
         mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -1349,30 +1394,32 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_kernel(const __grid_cons
 #pragma unroll
         for (int j = 0; j < BLOCK_N / 64; ++j)
           tma_load_4d(sb + j * 8192, &maps.dy, &full_bar[stage], n_tile * BLOCK_N + j * 64, wt * p.BW, ht * p.BH, nt * p.BNI);
-        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
+      if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(TILE_M, BLOCK_N, 1, 1);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int b = 0; b < nbox; ++b) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-        const uint32_t sb = sa + Cfg::A_BYTES;
-        // MN-major SWIZZLE_128B: LBO = distance between 64-element MN chunks (8 KB), SBO = 8 K-rows (1 KB)
-        const uint64_t adesc = make_smem_desc(sa, 8192, 1024);
-        const uint64_t bdesc = make_smem_desc(sb, 8192, 1024);
+    // MMA issuer: converged warp, one elected lane issues
+    constexpr uint32_t idesc = make_idesc(TILE_M, BLOCK_N, 1, 1);
+    const uint32_t smem_base = smem_u32(smem);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int b = 0; b < nbox; ++b) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+      const uint32_t sb = sa + Cfg::A_BYTES;
+      // MN-major SWIZZLE_128B: LBO = distance between 64-element MN chunks (8 KB), SBO = 8 K-rows (1 KB)
+      const uint64_t adesc = make_smem_desc(sa, 8192, 1024);
+      const uint64_t bdesc = make_smem_desc(sb, 8192, 1024);
+      if (elect_one_sync()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)  // 16 pixels (K rows of 128 B) per MMA: +2048 B = +128 in the (addr >> 4) field
           umma_bf16(tmem_base, adesc + 128 * k, bdesc + 128 * k, idesc, (b | k) != 0);
         umma_commit(&empty_bar[stage]);
-        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
-      umma_commit(tfull_bar);
+      if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
     }
+    if (elect_one_sync()) umma_commit(tfull_bar);
   } else {
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
@@ -1435,7 +1482,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad64_kernel(const __grid_co
   uint64_t* empty_bar = bars + 2;
   uint64_t* tfull_bar = bars + 4;
   uint32_t* tmem_ptr_smem = (uint32_t*)(bars + 5);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_i(threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.x);
     tma_prefetch_desc(&maps.dy);
@@ -1450,37 +1497,40 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad64_kernel(const __grid_co
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tmem_base = uniform_u(*tmem_ptr_smem);
   pdl_wait();  // barriers initialised, tensor memory allocated: nothing above touched global memory
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int ht = tile % p.tiles_h, n = tile / p.tiles_h;
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * stage_bytes;
+    // TMA producer: converged warp, one elected lane issues
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int ht = tile % p.tiles_h, n = tile / p.tiles_h;
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      uint8_t* sa = smem + stage * stage_bytes;
+      if (elect_one_sync()) {
         mbar_expect_tx(&full_bar[stage], stage_bytes);
         for (int dwi = 0; dwi < 3; ++dwi) tma_load_4d(sa + dwi * p.copy_bytes, &maps.x, &full_bar[stage], 0, dwi - 1, ht * p.BH - 1, n);
         tma_load_4d(sa + 3 * p.copy_bytes, &maps.dy, &full_bar[stage], 0, 0, ht * p.BH, n);
-        if (++stage == 2) { stage = 0; phase ^= 1; }
       }
+      if (++stage == 2) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(TILE_M, 64, 1, 1);
-      const uint32_t row_step = (uint32_t)p.BW * 128;
-      int stage = 0;
-      uint32_t phase = 0;
-      bool first = true;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-        const uint32_t sb = sa + 3 * p.copy_bytes;
-        // taps in address order: index i = dwi*3 + dhi at sa + dwi*copy + dhi*row_step; accumulator a pairs (2a, 2a+1),
-        // the last one pairs (7, 8) again and only its upper 64 rows (tap index 8) are used
+    // MMA issuer: converged warp, one elected lane issues
+    constexpr uint32_t idesc = make_idesc(TILE_M, 64, 1, 1);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t row_step = (uint32_t)p.BW * 128;
+    int stage = 0;
+    uint32_t phase = 0;
+    bool first = true;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint32_t sa = smem_base + stage * stage_bytes;
+      const uint32_t sb = sa + 3 * p.copy_bytes;
+      // taps in address order: index i = dwi*3 + dhi at sa + dwi*copy + dhi*row_step; accumulator a pairs (2a, 2a+1),
+      // the last one pairs (7, 8) again and only its upper 64 rows (tap index 8) are used
+      if (elect_one_sync()) {
 #pragma unroll
         for (int a = 0; a < 5; ++a) {
           const int i0 = a < 4 ? 2 * a : 7, i1 = i0 + 1;
@@ -1492,12 +1542,12 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad64_kernel(const __grid_co
           for (int k = 0; k < 8; ++k)  // 16 pixels (K rows of 128 B) per MMA: +2048 B = +128 in the (addr >> 4) field
             umma_bf16(tmem_base + a * 64, adesc + 128 * k, bdesc + 128 * k, idesc, !(first && k == 0));
         }
-        first = false;
         umma_commit(&empty_bar[stage]);
-        if (++stage == 2) { stage = 0; phase ^= 1; }
       }
-      umma_commit(tfull_bar);
+      first = false;
+      if (++stage == 2) { stage = 0; phase ^= 1; }
     }
+    if (elect_one_sync()) umma_commit(tfull_bar);
   } else {
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
