@@ -121,6 +121,11 @@ __device__ __forceinline__ uint32_t elect_one_sync() {
       : "r"(0xffffffffu));
   return pred;
 }
+__device__ __forceinline__ long long globaltimer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 // warp index / any value the compiler must treat as warp-uniform
 __device__ __forceinline__ int uniform_i(int v) { return __shfl_sync(0xffffffffu, v, 0); }
 __device__ __forceinline__ uint32_t uniform_u(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
@@ -231,6 +236,9 @@ struct TcParams {
   int kchunks;            // Ci / 64
   // CTA-pair kernels: work item v = 2 * pair + cta_rank; a pair = two pixel tiles of ONE class and ONE output-channel tile
   int pair_mode, px_tiles_per_class, pairs_per_class, total_items;
+  // row-reuse kernel (conv_tc_rr_kernel): work item = super-tile of two vertically adjacent pixel tiles (2s, 2s+1) that share
+  // every weight tile; rr_rounds full rounds of gridDim.x items, then rr_rem items -- split into single tiles when they fit
+  int rr_rounds, rr_rem, rr_split;
   void* out;             // bf16 or float32 (out_f32)
   const void* residual;  // bf16 or float32 (res_f32)
   const float* bias;
@@ -294,11 +302,64 @@ __device__ __forceinline__ void decode_tile(const TcParams& p, int tile, int& cl
   cls = r / p.tiles_n;
 }
 
+// k-th pixel tile of this CTA, its accumulator buffer and the parity of that buffer's barriers.  GROUP == 1: tiles blockIdx.x +
+// k * gridDim.x, two buffers.  GROUP == 2 (row-reuse kernel): items of two tiles, four buffers (2 * (item & 1) + half).
+template <int GROUP>
+__device__ __forceinline__ bool tile_seq(const TcParams& p, int k, int& tile, int& acc, uint32_t& phase) {
+  if (GROUP == 1) {
+    tile = blockIdx.x + k * gridDim.x;
+    acc = k & 1;
+    phase = (k >> 1) & 1;
+    return tile < p.total_tiles;
+  }
+  int i, j, st;
+  if (k < 2 * p.rr_rounds) {
+    i = k >> 1;
+    j = k & 1;
+    st = blockIdx.x + i * gridDim.x;
+  } else {
+    const int kk = k - 2 * p.rr_rounds;
+    i = p.rr_rounds;
+    if (p.rr_split) {
+      if (kk > 0 || (int)blockIdx.x >= 2 * p.rr_rem) return false;
+      st = p.rr_rounds * gridDim.x + (blockIdx.x >> 1);
+      j = blockIdx.x & 1;
+    } else {
+      if (kk > 1 || (int)blockIdx.x >= p.rr_rem) return false;
+      st = p.rr_rounds * gridDim.x + blockIdx.x;
+      j = kk;
+    }
+  }
+  tile = 2 * st + j;
+  acc = 2 * (i & 1) + j;
+  phase = (i >> 1) & 1;
+  return true;
+}
+// i-th work item of the row-reuse kernel: super-tile index and which of its two tiles are computed (bit 0 / bit 1)
+__device__ __forceinline__ bool rr_item(const TcParams& p, int i, int& st, int& jmask) {
+  if (i < p.rr_rounds) {
+    st = blockIdx.x + i * gridDim.x;
+    jmask = 3;
+    return true;
+  }
+  if (i > p.rr_rounds) return false;
+  if (p.rr_split) {
+    if ((int)blockIdx.x >= 2 * p.rr_rem) return false;
+    st = p.rr_rounds * gridDim.x + (blockIdx.x >> 1);
+    jmask = 1 << (blockIdx.x & 1);
+    return true;
+  }
+  if ((int)blockIdx.x >= p.rr_rem) return false;
+  st = p.rr_rounds * gridDim.x + blockIdx.x;
+  jmask = 3;
+  return true;
+}
+
 // ---------------------------------------------------------------------------------------------- epilogue (shared by all mainloops)
 // MODE 0: out = act(acc + bias)*post_scale+post_shift + residual; out2 = bf16 relu(out*scale2+shift2)
 // MODE 2: MODE 0 + per-(CTA, row quarter) partial sums / sums of squares of `out` (train-mode BatchNorm statistics)
 // MODE 1: out = bf16( mask > 0 ? (acc + residual) * mask_scale : 0 ) + post_add     (residual XOR post_add, both bf16)
-template <int BLOCK_N, int MODE, bool PAIR = false>
+template <int BLOCK_N, int MODE, bool PAIR = false, int GROUP = 1>
 __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* stg_base, uint32_t tmem_base, uint64_t* tfull_bar,
                                             uint64_t* tempty_bar, int warp, int lane) {
   // PAIR: the accumulator-empty barriers live in the pair's leader CTA (its MMA thread waits for the epilogue warps of BOTH CTAs)
@@ -307,6 +368,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* stg_base
     tempty_leader[0] = mapa_u32(smem_u32(&tempty_bar[0]), 0);
     tempty_leader[1] = mapa_u32(smem_u32(&tempty_bar[1]), 0);
   }
+  static_assert(!(PAIR && GROUP != 1), "CTA pairs use two accumulator buffers");
   // ===================== epilogue: TMEM -> registers -> shared (transpose) -> coalesced global =====================
   // 8 warps: warp w owns TMEM lanes [32*(w%4), +32) (hardware rule) and the column half (w-2)/4 of the tile.
   // tcgen05.ld hands a thread one accumulator ROW (pixel); writing rows straight to NHWC memory makes every store
@@ -331,8 +393,6 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* stg_base
   for (int ch = 0; ch < NCH; ++ch) ssum[ch] = ssq[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
   const int sub = lane >> 3;     // row within a group of 4
   const int cseg = lane & 7;     // 16-byte column segment: columns cseg*4 .. cseg*4+3 of the chunk
-  int acc = 0;
-  uint32_t acc_phase = 0;
   // per-tile addressing + prefetch of the epilogue inputs, software-pipelined ONE TILE AHEAD: the loads of tile t+1 are
   // in flight while tile t is transposed, combined and stored
   struct TileCtx {
@@ -390,11 +450,18 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* stg_base
   constexpr bool AHEAD = NCH == 1;
   long long e_wait = 0, e_body = 0;
   TileCtx cur, nxt;
-  if (AHEAD && (int)blockIdx.x < p.total_tiles) prepare(blockIdx.x, cur);
-  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-    const bool more = AHEAD && tile + (int)gridDim.x < p.total_tiles;
+  int tile, acc, tile_n, acc_n;
+  uint32_t acc_phase, phase_n;
+  // GROUP == 1: tiles of a class without taps (strided input gradients) use no accumulator, so the buffer index / parity
+  // advance only on tiles that have one (as in the MMA warp)
+  int acc_run = 0;
+  uint32_t phase_run = 0;
+  if (AHEAD && tile_seq<GROUP>(p, 0, tile, acc, acc_phase)) prepare(tile, cur);
+  for (int k = 0; tile_seq<GROUP>(p, k, tile, acc, acc_phase); ++k) {
+    if (GROUP == 1) { acc = acc_run; acc_phase = phase_run; }
+    const bool more = AHEAD && tile_seq<GROUP>(p, k + 1, tile_n, acc_n, phase_n);
     if (AHEAD) {
-      if (more) prepare(tile + gridDim.x, nxt);
+      if (more) prepare(tile_n, nxt);
     } else {
       prepare(tile, cur);
     }
@@ -529,10 +596,10 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* stg_base
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (PAIR) mbar_arrive_cluster(tempty_leader[acc]);
+        if (PAIR) mbar_arrive_cluster(tempty_leader[acc & 1]);
         else mbar_arrive(&tempty_bar[acc]);
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc_run == 2) { acc_run = 0; phase_run ^= 1; }
     }
     if (dbg_w) {
       e_wait += te1 - te0;          // epilogue warp waiting for the accumulator
@@ -570,6 +637,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* stg_base
 template <int BLOCK_N, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   pdl_launch_dependents();  // the next kernel may be scheduled; this one waits for its predecessor after its prologue
+  const long long dbg_c0 = p.dbg ? clock64() : 0, dbg_g0 = p.dbg ? globaltimer_ns() : 0;  // whole-kernel cycles / ns of this CTA
   using Cfg = TcCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B atoms need 1024 B alignment
@@ -687,6 +755,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   }
   tc_fence_before();
   __syncthreads();
+  if (p.dbg && threadIdx.x == 0) {
+    p.dbg[blockIdx.x * 8 + 6] += clock64() - dbg_c0;
+    p.dbg[blockIdx.x * 8 + 7] += globaltimer_ns() - dbg_g0;
+  }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -716,6 +788,7 @@ template <int BLOCK_N, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     conv_tc_pair_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   pdl_launch_dependents();  // the next kernel may be scheduled; this one waits for its predecessor after its prologue
+  const long long dbg_c0 = p.dbg ? clock64() : 0, dbg_g0 = p.dbg ? globaltimer_ns() : 0;  // whole-kernel cycles / ns of this CTA
   using Cfg = TcPairCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -836,6 +909,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();  // the peer may still be reading this CTA's shared memory / writing its tensor memory until here
+  if (p.dbg && threadIdx.x == 0) {
+    p.dbg[blockIdx.x * 8 + 6] += clock64() - dbg_c0;
+    p.dbg[blockIdx.x * 8 + 7] += globaltimer_ns() - dbg_g0;
+  }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
@@ -860,6 +937,7 @@ template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc64_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
                                                                   const int stage_bytes, const int n_stages) {
   pdl_launch_dependents();  // the next kernel may be scheduled; this one waits for its predecessor after its prologue
+  const long long dbg_c0 = p.dbg ? clock64() : 0, dbg_g0 = p.dbg ? globaltimer_ns() : 0;  // whole-kernel cycles / ns of this CTA
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* wsm = smem;                               // [9 taps][64 co][64 ci] bf16, SWIZZLE_128B
@@ -970,9 +1048,183 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc64_kernel(const __grid_c
   }
   tc_fence_before();
   __syncthreads();
+  if (p.dbg && threadIdx.x == 0) {
+    p.dbg[blockIdx.x * 8 + 6] += clock64() - dbg_c0;
+    p.dbg[blockIdx.x * 8 + 7] += globaltimer_ns() - dbg_g0;
+  }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 128);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- 128 output channels, 3x3, stride 1
+// With the MMA issue fixed, the generic 128-wide kernel is bound by its operand stream (576 KB of TMA loads per 128-pixel tile:
+// ~75 B/clk per SM is what L2 -> shared memory sustains with 160 KB in flight).  This kernel loads less:
+//   * row re-use (as conv_tc64_kernel): per horizontal tap offset and K chunk ONE box of the tile's rows plus a halo row above and
+//     below; the three vertical taps read it at row offsets 0, W, 2W;
+//   * a work item is a SUPER-TILE of two vertically adjacent 128-pixel tiles (one (2 BH + 2)-row box serves both) that SHARE every
+//     weight tile: each 16 KB weight tile is loaded once per 256 pixels and feeds two accumulators.
+// Per 128 pixels (128 -> 128 @16x16): 108 KB of activations + 144 KB of weights instead of 288 + 288.  Four accumulator buffers
+// (2 items x 2 tiles, 512 TMEM columns); separate rings for activation boxes and weight tiles.
+struct TcRRCfg {
+  static constexpr int B_BYTES = 128 * KCHUNK * 2;  // 16 KB weight tile (128 output channels x 64 input channels)
+  static constexpr int SA = 3;                      // activation boxes in flight (upper bound)
+  static constexpr int SB = 6;                      // weight tiles in flight (upper bound)
+  static constexpr int SMEM_FIXED = 1024 /*align*/ + 256 /*barriers*/ + TC_EPI_WARPS * 32 * EPI_ROWB;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_rr_kernel(const __grid_constant__ TcMaps maps, const TcParams p, const int a_bytes,
+                                                                   const int n_a, const int n_b) {
+  pdl_launch_dependents();
+  const long long dbg_c0 = p.dbg ? clock64() : 0, dbg_g0 = p.dbg ? globaltimer_ns() : 0;  // whole-kernel cycles / ns of this CTA
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_ring = smem;                              // n_a x a_bytes: (2 BH + 2) rows x BW pixels x 128 B, SWIZZLE_128B
+  uint8_t* b_ring = smem + n_a * a_bytes;              // n_b x 16 KB
+  uint8_t* tail = b_ring + n_b * TcRRCfg::B_BYTES;
+  uint64_t* bars = (uint64_t*)tail;
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = bars + TcRRCfg::SA;
+  uint64_t* b_full = bars + 2 * TcRRCfg::SA;
+  uint64_t* b_empty = bars + 2 * TcRRCfg::SA + TcRRCfg::SB;
+  uint64_t* tfull_bar = bars + 2 * TcRRCfg::SA + 2 * TcRRCfg::SB;       // 4
+  uint64_t* tempty_bar = tfull_bar + 4;                                 // 4
+  uint32_t* tmem_ptr_smem = (uint32_t*)(tempty_bar + 4);
+  const int warp = uniform_i(threadIdx.x >> 5), lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.w);
+    tma_prefetch_desc(&maps.in[0]);
+    for (int s = 0; s < TcRRCfg::SA; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < TcRRCfg::SB; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    for (int a = 0; a < 4; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], TC_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_smem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = uniform_u(*tmem_ptr_smem);
+  pdl_wait();
+
+  const int supers_h = p.tiles_h >> 1;  // super-tiles per image
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    long long w_empty = 0;
+    int st, jmask;
+    for (int i = 0; rr_item(p, i, st, jmask); ++i) {
+      const int n = st / supers_h, hs = st - n * supers_h;
+      for (int dw = -1; dw <= 1; ++dw)
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          long long t0 = p.dbg ? clock64() : 0;
+          mbar_wait(&a_empty[sa], pa ^ 1);
+          if (p.dbg) w_empty += clock64() - t0;
+          if (elect_one_sync()) {
+            mbar_expect_tx(&a_full[sa], a_bytes);
+            tma_load_4d(a_ring + sa * a_bytes, &maps.in[0], &a_full[sa], kc * KCHUNK, dw, hs * 2 * p.BH - 1, n);
+          }
+          if (++sa == n_a) { sa = 0; pa ^= 1; }
+          for (int dh = 0; dh < 3; ++dh) {
+            t0 = p.dbg ? clock64() : 0;
+            mbar_wait(&b_empty[sb], pb ^ 1);
+            if (p.dbg) w_empty += clock64() - t0;
+            if (elect_one_sync()) {
+              mbar_expect_tx(&b_full[sb], TcRRCfg::B_BYTES);
+              tma_load_3d(b_ring + sb * TcRRCfg::B_BYTES, &maps.w, &b_full[sb], kc * KCHUNK, dh * 3 + dw + 1, 0);
+            }
+            if (++sb == n_b) { sb = 0; pb ^= 1; }
+          }
+        }
+    }
+    if (p.dbg && lane == 0) p.dbg[blockIdx.x * 8 + 0] += w_empty;
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc(TILE_M, 128, 0, 0);
+    const uint32_t a_base = smem_u32(a_ring), b_base = smem_u32(b_ring);
+    const uint32_t row_step = (uint32_t)p.BW * 128;   // one image row of the staged box
+    const uint32_t half_step = (uint32_t)p.BH * row_step;
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    long long w_tempty = 0, w_full = 0, t_last = 0;
+    const long long tstart = p.dbg ? clock64() : 0;
+    int st, jmask;
+    for (int i = 0; rr_item(p, i, st, jmask); ++i) {
+      if (p.dbg) t_last = clock64() - tstart;
+      const int buf = i & 1;
+      const uint32_t ph = (i >> 1) & 1;
+      long long t0 = p.dbg ? clock64() : 0;
+      if (jmask & 1) mbar_wait(&tempty_bar[2 * buf], ph ^ 1);
+      if (jmask & 2) mbar_wait(&tempty_bar[2 * buf + 1], ph ^ 1);
+      if (p.dbg) w_tempty += clock64() - t0;
+      tc_fence_after();
+      const uint32_t d0 = tmem_base + (2 * buf) * 128, d1 = d0 + 128;
+      bool first = true;
+      for (int dwi = 0; dwi < 3; ++dwi)
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          t0 = p.dbg ? clock64() : 0;
+          mbar_wait(&a_full[sa], pa);
+          if (p.dbg) w_full += clock64() - t0;
+          const uint32_t abox = a_base + sa * a_bytes;
+          for (int dhi = 0; dhi < 3; ++dhi) {
+            t0 = p.dbg ? clock64() : 0;
+            mbar_wait(&b_full[sb], pb);
+            if (p.dbg) w_full += clock64() - t0;
+            tc_fence_after();
+            const uint64_t bdesc = make_smem_desc(b_base + sb * TcRRCfg::B_BYTES, 16, 1024);
+            const uint64_t adesc0 = make_smem_desc(abox + dhi * row_step, 16, 1024);
+            const uint64_t adesc1 = make_smem_desc(abox + dhi * row_step + half_step, 16, 1024);
+            if (elect_one_sync()) {
+              if (jmask & 1) {
+#pragma unroll
+                for (int k = 0; k < KCHUNK / 16; ++k) umma_bf16(d0, adesc0 + 2 * k, bdesc + 2 * k, idesc, !(first && k == 0));
+              }
+              if (jmask & 2) {
+#pragma unroll
+                for (int k = 0; k < KCHUNK / 16; ++k) umma_bf16(d1, adesc1 + 2 * k, bdesc + 2 * k, idesc, !(first && k == 0));
+              }
+              umma_commit(&b_empty[sb]);
+            }
+            first = false;
+            if (++sb == n_b) { sb = 0; pb ^= 1; }
+          }
+          if (elect_one_sync()) umma_commit(&a_empty[sa]);
+          if (++sa == n_a) { sa = 0; pa ^= 1; }
+        }
+      if (elect_one_sync()) {
+        if (jmask & 1) umma_commit(&tfull_bar[2 * buf]);
+        if (jmask & 2) umma_commit(&tfull_bar[2 * buf + 1]);
+      }
+    }
+    if (p.dbg && lane == 0) {
+      p.dbg[blockIdx.x * 8 + 1] += w_tempty;
+      p.dbg[blockIdx.x * 8 + 2] += w_full;
+      p.dbg[blockIdx.x * 8 + 3] = t_last;
+    }
+  } else {
+    tc_epilogue<128, MODE, false, 2>(p, tail + 256, tmem_base, tfull_bar, tempty_bar, warp, lane);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (p.dbg && threadIdx.x == 0) {
+    p.dbg[blockIdx.x * 8 + 6] += clock64() - dbg_c0;
+    p.dbg[blockIdx.x * 8 + 7] += globaltimer_ns() - dbg_g0;
+  }
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -1223,11 +1475,32 @@ extern "C" int combat_conv_tc(const combat_conv_tc_desc* d, void* stream) {
     rc = make_act_map(&maps.in[0], d->in, d->Ci, d->Wi, d->Hi, d->N, C, W * C, H * W * C, p.BW, p.BH + 2, 1);
     if (rc) return rc;
   }
+  // 128 output channels, 3x3, stride 1, tiles of whole image rows: row re-use + two tiles per weight tile (conv_tc_rr_kernel)
+  int rr_a_bytes = 0, rr_na = 0, rr_nb = 0;
+  bool use_rr = !use64 && d->Co == 128 && KH == 3 && pad == 1 && d->stride == 1 && d->up == 1 && !d->in2 && p.BW == d->Wo &&
+                p.BNI == 1 && (p.BW % 8) == 0 && (p.Hc % (2 * p.BH)) == 0 && !getenv("COMBAT_NO_RR");
+  if (use_rr) {
+    rr_a_bytes = (2 * p.BH + 2) * p.BW * 128;
+    const int budget = 232448 - TcRRCfg::SMEM_FIXED;
+    rr_na = TcRRCfg::SA;
+    rr_nb = (budget - rr_na * rr_a_bytes) / TcRRCfg::B_BYTES;
+    if (rr_nb < 3) {
+      rr_na = 2;
+      rr_nb = (budget - rr_na * rr_a_bytes) / TcRRCfg::B_BYTES;
+    }
+    if (rr_nb > TcRRCfg::SB) rr_nb = TcRRCfg::SB;
+    if (rr_nb < 3) use_rr = false;
+  }
+  if (use_rr) {
+    const long long C = d->Ci, W = d->Wi, H = d->Hi;
+    rc = make_act_map(&maps.in[0], d->in, d->Ci, d->Wi, d->Hi, d->N, C, W * C, H * W * C, p.BW, 2 * p.BH + 2, 1);
+    if (rc) return rc;
+  }
   // CTA pairs (cta_group::2): each CTA of a pair stages half of the weight tile.  Measured inside the step (B200, batch 512):
   // 256-wide tiles gain 13-15 % (256->256 @8x8 fwd 1042 -> 1204 TFLOP/s, 512->512 @4x4 1107 -> 1272, their input gradients 900 ->
   // 1005); 128-wide tiles LOSE 6-9 % (half-size MMAs, twice the cluster-scope barrier round trips per byte) and keep the
   // single-CTA kernel unless COMBAT_PAIR128 is set.
-  const bool pair = !use64 && (BLOCK_N == 256 || (BLOCK_N == 128 && getenv("COMBAT_PAIR128"))) && !getenv("COMBAT_NO_PAIR");
+  const bool pair = !use64 && !use_rr && (BLOCK_N == 256 || (BLOCK_N == 128 && getenv("COMBAT_PAIR128"))) && !getenv("COMBAT_NO_PAIR");
   rc = make_w_map(&maps.w, d->w, d->Ci, KH * KW, d->Co, pair ? BLOCK_N / 2 : BLOCK_N);
   if (rc) return rc;
   if (d->in2) {
@@ -1252,6 +1525,13 @@ extern "C" int combat_conv_tc(const combat_conv_tc_desc* d, void* stream) {
     int nclusters = total_pairs < max_pair_clusters() ? total_pairs : max_pair_clusters();
     if (d->stats && nclusters >= p.tiles_co) nclusters -= nclusters % p.tiles_co;  // a CTA's channel tile must never change
     grid = 2 * nclusters;
+  }
+  if (use_rr) {
+    const int n_super = p.total_tiles / 2;   // tiles_co == 1, tiles_w == 1, tiles_h even: tiles 2s and 2s+1 are one image's neighbours
+    grid = n_super < num_sms() ? n_super : num_sms();
+    p.rr_rounds = n_super / grid;
+    p.rr_rem = n_super - p.rr_rounds * grid;
+    p.rr_split = p.rr_rem > 0 && 2 * p.rr_rem <= grid;
   }
   g_last_grid = grid;
   COMBAT_ARG(!d->stats || (d->Co <= 512 && !d->mask), 0);
@@ -1285,6 +1565,20 @@ extern "C" int combat_conv_tc(const combat_conv_tc_desc* d, void* stream) {
       pdl_launch(conv_tc64_kernel<0>, grid, TC_THREADS, smem_bytes, st, maps, p, stage_bytes64, n_stages64);
     }
     COMBAT_RETURN_LAUNCH("conv_tc64");
+  }
+  if (use_rr) {
+    const int smem_bytes = TcRRCfg::SMEM_FIXED + rr_na * rr_a_bytes + rr_nb * TcRRCfg::B_BYTES;
+    if (mode == 1) {
+      cudaFuncSetAttribute(conv_tc_rr_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+      pdl_launch(conv_tc_rr_kernel<1>, grid, TC_THREADS, smem_bytes, st, maps, p, rr_a_bytes, rr_na, rr_nb);
+    } else if (mode == 2) {
+      cudaFuncSetAttribute(conv_tc_rr_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+      pdl_launch(conv_tc_rr_kernel<2>, grid, TC_THREADS, smem_bytes, st, maps, p, rr_a_bytes, rr_na, rr_nb);
+    } else {
+      cudaFuncSetAttribute(conv_tc_rr_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+      pdl_launch(conv_tc_rr_kernel<0>, grid, TC_THREADS, smem_bytes, st, maps, p, rr_a_bytes, rr_na, rr_nb);
+    }
+    COMBAT_RETURN_LAUNCH("conv_tc_rr");
   }
   if (pair) {
     if (BLOCK_N == 256) { if (mode == 1) LAUNCH_P(256, 1) else if (mode == 2) LAUNCH_P(256, 2) else LAUNCH_P(256, 0) }

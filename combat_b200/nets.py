@@ -408,8 +408,14 @@ class Classifier(NetBase):
         super().__init__(device, dtype, use_tc)
         assert arch in ("preact_resnet18", "resnet18")
         self.arch, self.num_classes, self.n_input, self.input_size = arch, num_classes, n_input, input_size
-        # (measured: storing the pre-normalisation tensors / residual stream in bf16 instead of float32 passes the same parity
-        # bars but does not change the step time -- 12.85 vs 12.86 ms -- so the float32 tensors stay)
+        # bf16 path: the pre-normalisation tensors and the residual stream are STORED in bf16 (statistics are still taken from
+        # the float32 accumulators in the conv epilogue).  With the MMA issue fixed the 64- and 128-channel conv launches that
+        # read a float32 residual and write a float32 stream were HBM-bound (64->64 @32x32, batch 512: 402 MB in 80 us); bf16
+        # storage: 11.13 -> 10.68 ms per step.  (In round 1, when the issuing thread paced those kernels, it made no difference:
+        # 12.85 vs 12.86 ms.)  The generator keeps float32 (InstanceNorm of a bf16-rounded tensor costs 3.4e-2 vs 3e-2 allowed).
+        # COMBAT_PRE_F32=1 restores float32 storage.
+        if dtype == torch.bfloat16 and not os.environ.get("COMBAT_PRE_F32"):
+            self.pre_dtype = torch.bfloat16
         if scaler is None:
             scaler = {32: 1, 64: 4, 224: 49}[input_size]  # reference: {32:1, 64:4}; 224 -> 49 is the natural extension
         self.scaler = scaler

@@ -43,7 +43,10 @@ import torch.nn.functional as F
 # else -- so that (a) CUDA-bf16 vs this mode isolates implementation error and can be held to 1e-3 per tensor, and (b) this
 # mode vs the float32 reference is the measured cost of the storage format (tests/test_bf16_parity_*.py state both).
 #   qa(t): an activation stored in bf16 -- value rounded in the forward, its gradient rounded in the backward
-#   qg(t): a float32 forward tensor whose GRADIENT is stored in bf16 (pre-normalisation tensors, the residual stream)
+#   qg(t): a float32 forward tensor whose GRADIENT is stored in bf16 (the generator's pre-normalisation tensors)
+#   qp(t): a CLASSIFIER pre-normalisation tensor / the residual stream: stored in bf16 like qa (`quantised(pre_bf16=True)`, the
+#          default since combat_b200 stores them in bf16), or float32 with a bf16 gradient like qg (`pre_bf16=False`, which is
+#          COMBAT_PRE_F32=1 in combat_b200/nets.py)
 #   qw(w): a conv weight rounded for the tensor cores; its gradient accumulates in float32 (straight through)
 # --------------------------------------------------------------------------
 #   cj(t): a float32 conv output; identity, or -- `quantised(jitter=e)` -- multiplied by (1 + e * N(0,1)) element-wise from a
@@ -51,17 +54,18 @@ import torch.nn.functional as F
 #          on identical inputs, scripts/diag_bf16_layers.py).  Two runs of the SAME quantised algorithm that differ only by this
 #          jitter bound what any faithful bf16 implementation can agree to: a value within that noise of a rounding boundary
 #          rounds the other way, and a random-init network amplifies every flip layer by layer.
-_QUANT = {"on": False, "jitter": 0.0, "gen": None}
+_QUANT = {"on": False, "jitter": 0.0, "gen": None, "pre_bf16": True}
 
 
 class quantised:
-    def __init__(self, jitter: float = 0.0, seed: int = 1234):
-        self.jitter, self.seed = float(jitter), seed
+    def __init__(self, jitter: float = 0.0, seed: int = 1234, pre_bf16: bool = True):
+        self.jitter, self.seed, self.pre_bf16 = float(jitter), seed, bool(pre_bf16)
 
     def __enter__(self):
         self.prev = dict(_QUANT)
         _QUANT["on"] = True
         _QUANT["jitter"] = self.jitter
+        _QUANT["pre_bf16"] = self.pre_bf16
         _QUANT["gen"] = torch.Generator().manual_seed(self.seed) if self.jitter else None
 
     def __exit__(self, *a):
@@ -122,6 +126,15 @@ def qa(t):
 
 def qg(t):
     return _QG.apply(t) if _QUANT["on"] else t
+
+
+def qp(t):
+    return qa(t) if _QUANT["pre_bf16"] else qg(t)
+
+
+def qf(t):
+    """stored in bf16, gradient passed through unchanged (it is rounded where the float32 value was produced)"""
+    return _QW.apply(t) if _QUANT["on"] else t
 
 
 def qw(w):
@@ -341,38 +354,47 @@ def _bn(p, b, name, x, training, momentum=0.1, eps=1e-5):
 def preact_resnet18_forward(p: dict, b: dict, x: torch.Tensor, training: bool):
     """PreActResNet18 (classifier_models/preact_resnet.py:13-40,72-110).
     `p` = parameters, `b` = buffers (running stats; updated in place when training)."""
-    # quantised(): bf16 conv weights and relu(bn(.)) tensors, float32 residual stream / pre-normalisation tensors whose
-    # gradients are stored in bf16 (combat_b200/nets.py Classifier.forward / backward); the image stays float32
-    out = qg(cj(F.conv2d(x, qw(p["conv1.weight"]), None, 1, 1)))  # :77,93
+    # quantised(): bf16 conv weights and relu(bn(.)) tensors; the residual stream / pre-normalisation tensors are STORED in bf16
+    # (`pre_bf16`) with bf16 gradients, as in combat_b200/nets.py Classifier.forward / backward; the image stays float32.
+    # Which value a BatchNorm reads follows the CUDA schedule: in eval mode relu(bn(.)) is computed in the producing conv's
+    # epilogue from the float32 accumulator (the unrounded value), in train mode by a separate pass over the stored tensor.
+    def pre_t(t):  # -> (float32 value whose gradient is stored in bf16, the stored tensor)
+        t = qg(t)
+        return t, (qf(t) if _QUANT["pre_bf16"] else t)
+
+    def bn_in(pair):
+        return pair[1] if training else pair[0]
+
+    out = pre_t(cj(F.conv2d(x, qw(p["conv1.weight"]), None, 1, 1)))  # :77,93
     in_planes = 64
     for li, (planes, stride0) in enumerate([(64, 1), (128, 2), (256, 2), (512, 2)], start=1):
         for bi, stride in enumerate([stride0, 1]):
             pre = "layer%d.%d." % (li, bi)
-            o = qa(F.relu(_bn(p, b, pre + "bn1", out, training)))  # :32
+            o = qa(F.relu(_bn(p, b, pre + "bn1", bn_in(out), training)))  # :32
             if stride != 1 or in_planes != planes:  # :26-29,33
-                sc = cj(F.conv2d(o, qw(p[pre + "shortcut.0.weight"]), None, stride, 0))
+                sc = pre_t(cj(F.conv2d(o, qw(p[pre + "shortcut.0.weight"]), None, stride, 0)))[1]
             else:
-                sc = out
-            o = qg(cj(F.conv2d(o, qw(p[pre + "conv1.weight"]), None, stride, 1)))  # :34
-            o = cj(F.conv2d(qa(F.relu(_bn(p, b, pre + "bn2", o, training))), qw(p[pre + "conv2.weight"]), None, 1, 1))  # :35
-            out = qg(o + sc)  # :39
+                sc = out[1]
+            c1 = pre_t(cj(F.conv2d(o, qw(p[pre + "conv1.weight"]), None, stride, 1)))  # :34
+            o = cj(F.conv2d(qa(F.relu(_bn(p, b, pre + "bn2", bn_in(c1), training))), qw(p[pre + "conv2.weight"]), None, 1, 1))  # :35
+            out = pre_t(o + sc)  # :39
             in_planes = planes
-    out = F.avg_pool2d(out, 4)  # :99
+    out = F.avg_pool2d(out[1], 4)  # :99
     out = out.view(out.size(0), -1)
     return F.linear(out, p["linear.weight"], p["linear.bias"])  # :101
 
 
 def resnet18_forward(p: dict, b: dict, x: torch.Tensor, training: bool):
     """ResNet18 (classifier_models/resnet.py:15-37,68-106), post-activation BasicBlocks."""
-    out = qa(F.relu(_bn(p, b, "bn1", qg(F.conv2d(x, qw(p["conv1.weight"]), None, 1, 1)), training)))  # :90
+    out = qa(F.relu(_bn(p, b, "bn1", qp(F.conv2d(x, qw(p["conv1.weight"]), None, 1, 1)), training)))  # :90
     in_planes = 64
     for li, (planes, stride0) in enumerate([(64, 1), (128, 2), (256, 2), (512, 2)], start=1):
         for bi, stride in enumerate([stride0, 1]):
             pre = "layer%d.%d." % (li, bi)
-            o = qa(F.relu(_bn(p, b, pre + "bn1", qg(F.conv2d(out, qw(p[pre + "conv1.weight"]), None, stride, 1)), training)))
-            o = _bn(p, b, pre + "bn2", qg(F.conv2d(o, qw(p[pre + "conv2.weight"]), None, 1, 1)), training)
+            o = qa(F.relu(_bn(p, b, pre + "bn1", qp(F.conv2d(out, qw(p[pre + "conv1.weight"]), None, stride, 1)), training)))
+            o = _bn(p, b, pre + "bn2", qp(F.conv2d(o, qw(p[pre + "conv2.weight"]), None, 1, 1)), training)
             if stride != 1 or in_planes != planes:  # :25-29
-                sc = qa(_bn(p, b, pre + "shortcut.1", qg(F.conv2d(out, qw(p[pre + "shortcut.0.weight"]), None, stride, 0)), training))
+                sc = qa(_bn(p, b, pre + "shortcut.1", qp(F.conv2d(out, qw(p[pre + "shortcut.0.weight"]), None, stride, 0)), training))
             else:
                 sc = out
             out = qa(F.relu(o + sc))  # :34-35

@@ -82,6 +82,9 @@ for name, Ci, Co, H in SHAPES:
                   "[mma loop total/launch %.0f] | epi wait-acc %.0f body %.0f"
                   % ((int(used.sum()), tiles) + tuple(float(v) / tiles for v in m[:3]) + (float(dv[used][:, 3].mean()),)
                      + tuple(float(v) / tiles for v in m[4:6])))
+            if float(m[7]) > 0:
+                print("   whole kernel per CTA: %.0f cycles in %.2f us (SM clock %.0f MHz); event time per launch %.2f us"
+                      % (float(m[6]), float(m[7]) / 1e3, float(m[6]) / float(m[7]) * 1e3, us))
     if args.variant:
         continue
     # wgrad

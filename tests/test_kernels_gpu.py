@@ -240,6 +240,11 @@ TC_CASES = [
     (1024, 256, 256, 8, 3, 1, 1),  # the batched [x ; x_bd] forward: 256-wide tiles, 512 tiles on 74 clusters
     (512, 128, 256, 16, 3, 2, 1),  # stride 2 at the benchmark batch (parity views; dgrad = 4 parity classes, paired per class)
     (512, 256, 512, 8, 1, 2, 0),   # 1x1 stride-2 shortcut: dgrad classes without taps
+    # row-reuse kernel for 128 output channels (conv_tc_rr_kernel: super-tiles of two pixel tiles sharing each weight tile)
+    (150, 128, 128, 16, 3, 1, 1),  # 150 super-tiles on 148 CTAs: the 2 left over are split into 4 single tiles
+    (223, 128, 128, 16, 3, 1, 1),  # 75 left over: too many to split, 75 CTAs run a second full item
+    (512, 128, 128, 16, 3, 1, 1),  # layer2 at the benchmark batch: 3 full rounds + 68 split super-tiles
+    (4, 192, 128, 32, 3, 1, 1),    # three K chunks, 32-wide rows (tile = 4 rows, box = 10 rows), 4 super-tiles per image
 ]
 
 
@@ -505,8 +510,9 @@ def test_conv_tc_elu_affine_epilogue(ops):
     assert rel(out32.permute(0, 3, 1, 2), F.conv2d(x, w, None, 1, 1) + res) < 2e-5
 
 
+@pytest.mark.parametrize("shape", [(3, 64, 128, 8), (5, 128, 128, 16)])   # the second runs conv_tc_rr_kernel (stride_up (1, 1))
 @pytest.mark.parametrize("stride_up", [(1, 1), (1, 2)])
-def test_conv_tc_fused_batchnorm_epilogues(ops, stride_up):
+def test_conv_tc_fused_batchnorm_epilogues(ops, stride_up, shape):
     """out2 = relu(v*scale2+shift2) next to out (eval BatchNorm+ReLU of the consumer); mask/mask_scale/post_add (its
     backward) -- the epilogues behind nets.Classifier._forward_eval_fused / _backward_eval_fused."""
     import ctypes as C
@@ -514,7 +520,7 @@ def test_conv_tc_fused_batchnorm_epilogues(ops, stride_up):
     from combat_b200._lib import check, lib
     _, up = stride_up
     g = torch.Generator().manual_seed(77 + up)
-    N, Ci, Co, H = 3, 64, 128, 8
+    N, Ci, Co, H = shape
     x = torch.randn(N, Ci, H, H, generator=g).bfloat16().float()
     w = (torch.randn(Co, Ci, 3, 3, generator=g) * 0.05).bfloat16().float()
     sc, sh = torch.rand(Co, generator=g) + 0.5, torch.randn(Co, generator=g) * 0.3

@@ -229,12 +229,19 @@ def test_frequency_detector_bf16_tensor_core_path(golden):
     assert torch.equal(logits.argmax(1).cpu(), ref.argmax(1))
 
 
-def test_fused_eval_path_equals_unfused():
+@pytest.mark.parametrize("pre", ["f32", "bf16"])
+def test_fused_eval_path_equals_unfused(pre, monkeypatch):
     """The eval-mode PreAct path with BatchNorm+ReLU folded into the tcgen05 epilogues computes the same function as
-    the unfused kernels: forward bit-identical (same fp32 accumulators, same rounding points), input gradient equal up
-    to one bf16 rounding that the fused path no longer performs."""
+    the unfused kernels.  With float32 pre-normalisation storage (COMBAT_PRE_F32=1) the forward is bit-identical (same fp32
+    accumulators, same rounding points); with the default bf16 storage the unfused path normalises the STORED (rounded)
+    tensor while the fused epilogue normalises the accumulator, one bf16 rounding apart.  Input gradient equal up to one
+    bf16 rounding that the fused path no longer performs."""
     if not torch.cuda.is_available():
         pytest.skip("needs a GPU")
+    if pre == "f32":
+        monkeypatch.setenv("COMBAT_PRE_F32", "1")
+    else:
+        monkeypatch.delenv("COMBAT_PRE_F32", raising=False)
     from combat_b200 import ops
     from combat_b200.nets import Classifier
     from oracle import combat_oracle as O
@@ -256,9 +263,17 @@ def test_fused_eval_path_equals_unfused():
         _, dl, _ = ops.cross_entropy(logits, t, 1.0, True)
         dx = net.backward(ctx, dl, need_wgrad=False, need_dx=True)
         outs.append((logits.clone(), dx.clone()))
-    assert torch.equal(outs[0][0], outs[1][0])
+    assert (net.pre_dtype == torch.float32) == (pre == "f32")
+    if pre == "f32":
+        assert torch.equal(outs[0][0], outs[1][0])
+    else:
+        e = float((outs[0][0] - outs[1][0]).norm() / outs[1][0].norm())
+        assert e < 1e-2, e
     e = float((outs[0][1] - outs[1][1]).norm() / outs[1][1].norm())
-    assert e < 2e-2, e
+    # bf16 storage: the two paths round the pre-normalisation tensors at different points, so relu masks of near-zero values
+    # differ; at batch 8 / random init the input gradient carries that at the same level as its distance from the float64
+    # oracle below (measured 7.8e-2)
+    assert e < (2e-2 if pre == "f32" else 1.2e-1), e
     # and against the float64 oracle
     pr = {k: v.double() for k, v in p.items()}
     br = {k: (v.double() if v.is_floating_point() else v) for k, v in b.items()}
