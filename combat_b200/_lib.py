@@ -37,7 +37,8 @@ class ConvTcDesc(C.Structure):
                 ("KH", i32), ("KW", i32), ("stride", i32), ("pad", i32), ("up", i32), ("out_f32", i32), ("res_f32", i32),
                 ("act", i32), ("post_scale", vp), ("post_shift", vp),
                 ("out2", vp), ("scale2", vp), ("shift2", vp), ("mask", vp), ("mask_scale", vp), ("post_add", vp),
-                ("in2", vp), ("w2", vp)]
+                ("in2", vp), ("w2", vp),
+                ("bnb_x", vp), ("bnb_scale", vp), ("bnb_shift", vp), ("bnb_mean", vp), ("bnb_invstd", vp)]
 
 
 P = C.POINTER

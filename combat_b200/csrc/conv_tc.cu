@@ -253,6 +253,10 @@ struct TcParams {
   const bf16* mask;         // bf16 NHWC like out: v = mask > 0 ? v * mask_scale[c] : 0 -- backward of relu(bn_eval(.))
   const float* mask_scale;
   const bf16* post_add;     // bf16 NHWC like out, added after the mask (gradient arriving over an identity shortcut)
+  // MODE 3 (train-mode relu(bn(x)) backward, reduction half): `mask` = x, mask_scale = scale; out = (x*scale+shift > 0) ? acc : 0
+  const float* bnb_shift;
+  const float* bnb_mean;
+  const float* bnb_invstd;
   float* stats;             // optional [gridDim.x][2][Co] per-CTA partial sums / sums of squares of `out` (train-mode BatchNorm)
   long long* dbg;           // optional [gridDim.x][8] cycle counters (pipeline diagnostics, scripts/bench_conv.py --dbg)
   TcTaps taps;
@@ -359,6 +363,8 @@ __device__ __forceinline__ bool rr_item(const TcParams& p, int i, int& st, int& 
 // MODE 0: out = act(acc + bias)*post_scale+post_shift + residual; out2 = bf16 relu(out*scale2+shift2)
 // MODE 2: MODE 0 + per-(CTA, row quarter) partial sums / sums of squares of `out` (train-mode BatchNorm statistics)
 // MODE 1: out = bf16( mask > 0 ? (acc + residual) * mask_scale : 0 ) + post_add     (residual XOR post_add, both bf16)
+// MODE 3: out = bf16 g, g = (x * scale + shift > 0) ? acc : 0, + per-(CTA, row quarter) partial sums of g and g * (x - mean) * invstd
+//         (the reduction of a train-mode BatchNorm+ReLU backward; x = the saved bf16 pre-normalisation tensor)
 template <int BLOCK_N, int MODE, bool PAIR = false, int GROUP = 1>
 __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* stg_base, uint32_t tmem_base, uint64_t* tfull_bar,
                                             uint64_t* tempty_bar, int warp, int lane) {
@@ -384,8 +390,9 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* stg_base
   constexpr bool PREFETCH = NCH <= 2;
   constexpr int NPF = PREFETCH ? NCH : 1;
   const uint32_t stg = smem_u32(stg_base) + (warp - 2) * (32 * EPI_ROWB);  // explicit shared-space address
-  constexpr bool FWD = MODE != 1;    // MODE 2 = MODE 0 + train-mode BatchNorm statistics of `out`
-  constexpr bool STATS = MODE == 2;
+  constexpr bool FWD = MODE == 0 || MODE == 2;    // MODE 2 = MODE 0 + train-mode BatchNorm statistics of `out`
+  constexpr bool BNB = MODE == 3;
+  constexpr bool STATS = MODE == 2 || MODE == 3;
   // running per-column sum / sum of squares of this warp's rows over ALL its tiles (the launcher guarantees that the
   // output-channel tile of a CTA never changes: gridDim.x % tiles_co == 0); written once at the end
   float4 ssum[NCH], ssq[NCH];
@@ -407,7 +414,9 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* stg_base
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const uint32_t o = (t.okmask >> i & 1) ? t.ob[i] + ch * EPI_CH : 0u;
-      if (MODE != 1) {
+      if (BNB) {
+        *(uint2*)&dst[i].x = __ldg((const uint2*)(p.mask + o));
+      } else if (MODE != 1) {
         if (p.residual) {
           if (p.res_f32) dst[i] = __ldg((const float4*)((const float*)p.residual + o));
           else *(uint2*)&dst[i].x = __ldg((const uint2*)((const bf16*)p.residual + o));
@@ -542,6 +551,22 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* stg_base
             }
           }
         }
+      } else if (BNB) {
+        const float4 sc = *(const float4*)(p.mask_scale + colg), sh = *(const float4*)(p.bnb_shift + colg);
+        const float4 mu = *(const float4*)(p.bnb_mean + colg), is = *(const float4*)(p.bnb_invstd + colg);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t x0u = __float_as_uint(prc[i].x), x1u = __float_as_uint(prc[i].y);
+          const float2 x0 = __bfloat1622float2(*(const __nv_bfloat162*)&x0u), x1 = __bfloat1622float2(*(const __nv_bfloat162*)&x1u);
+          // the forward's affine_act computed fmaf(x, scale, shift) from the same stored x: the same predicate
+          f[i].x = fmaf(x0.x, sc.x, sh.x) > 0.f ? f[i].x : 0.f; f[i].y = fmaf(x0.y, sc.y, sh.y) > 0.f ? f[i].y : 0.f;
+          f[i].z = fmaf(x1.x, sc.z, sh.z) > 0.f ? f[i].z : 0.f; f[i].w = fmaf(x1.y, sc.w, sh.w) > 0.f ? f[i].w : 0.f;
+          if (okmask >> i & 1) {
+            ssum[ch].x += f[i].x; ssum[ch].y += f[i].y; ssum[ch].z += f[i].z; ssum[ch].w += f[i].w;
+            ssq[ch].x = fmaf(f[i].x, (x0.x - mu.x) * is.x, ssq[ch].x); ssq[ch].y = fmaf(f[i].y, (x0.y - mu.y) * is.y, ssq[ch].y);
+            ssq[ch].z = fmaf(f[i].z, (x1.x - mu.z) * is.z, ssq[ch].z); ssq[ch].w = fmaf(f[i].w, (x1.y - mu.w) * is.w, ssq[ch].w);
+          }
+        }
       } else {
         const float4 ms = *(const float4*)(p.mask_scale + colg);
         const bool pre_add = p.residual != nullptr;
@@ -558,7 +583,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* stg_base
           if (!pre_add) { f[i].x += a0.x; f[i].y += a0.y; f[i].z += a1.x; f[i].w += a1.y; }
         }
       }
-      if (STATS) {
+      if (STATS && !BNB) {
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           if (okmask >> i & 1) {
@@ -1377,7 +1402,18 @@ extern "C" int combat_conv_tc(const combat_conv_tc_desc* d, void* stream) {
   p.mask = (const bf16*)d->mask;
   p.mask_scale = d->mask_scale;
   p.post_add = (const bf16*)d->post_add;
-  p.dbg = getenv("COMBAT_TC_DBG") ? (long long*)d->stats : nullptr;
+  const bool bnb = d->bnb_x != nullptr;
+  if (bnb) {
+    // fused train-mode BatchNorm backward reduction: bf16 out, no other epilogue feature, partial sums wanted
+    COMBAT_ARG(d->bnb_scale && d->bnb_shift && d->bnb_mean && d->bnb_invstd && d->stats && d->out && !d->out_f32, 0);
+    COMBAT_ARG(!d->mask && !d->post_add && !d->residual && !d->out2 && !d->bias && !d->act && !d->post_scale, 0);
+    p.mask = (const bf16*)d->bnb_x;
+    p.mask_scale = d->bnb_scale;
+    p.bnb_shift = d->bnb_shift;
+    p.bnb_mean = d->bnb_mean;
+    p.bnb_invstd = d->bnb_invstd;
+  }
+  p.dbg = (getenv("COMBAT_TC_DBG") && !d->bnb_x) ? (long long*)d->stats : nullptr;
   p.stats = p.dbg ? nullptr : d->stats;
   // 256-wide tiles for the deep layers: per MMA the 128-row A operand is read once for 256 instead of 128 output channels
   // (the shared-memory operand path is what bounds the 128-wide kernel); they need K large enough to hide the epilogue
@@ -1546,7 +1582,7 @@ extern "C" int combat_conv_tc(const combat_conv_tc_desc* d, void* stream) {
     cudaFuncSetAttribute(conv_tc_kernel<BN, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES);     \
     pdl_launch(conv_tc_kernel<BN, MD>, grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st, maps, p);                                     \
   }
-  const int mode = d->mask ? 1 : (p.stats ? 2 : 0);
+  const int mode = bnb ? 3 : (d->mask ? 1 : (p.stats ? 2 : 0));
   if (p.stats) {  // partial blocks of (CTA, quarter): zero-filled, every warp writes only its own column range
     COMBAT_ARG(grid % p.tiles_co == 0, 0);
     cudaMemsetAsync(p.stats, 0, (size_t)grid * 4 * 2 * d->Co * sizeof(float), st);
@@ -1554,7 +1590,10 @@ extern "C" int combat_conv_tc(const combat_conv_tc_desc* d, void* stream) {
   }
   if (use64) {
     const int smem_bytes = Tc64Cfg::SMEM_BYTES_FIXED + n_stages64 * stage_bytes64;
-    if (mode == 1) {
+    if (mode == 3) {
+      cudaFuncSetAttribute(conv_tc64_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+      pdl_launch(conv_tc64_kernel<3>, grid, TC_THREADS, smem_bytes, st, maps, p, stage_bytes64, n_stages64);
+    } else if (mode == 1) {
       cudaFuncSetAttribute(conv_tc64_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
       pdl_launch(conv_tc64_kernel<1>, grid, TC_THREADS, smem_bytes, st, maps, p, stage_bytes64, n_stages64);
     } else if (mode == 2) {
@@ -1568,7 +1607,10 @@ extern "C" int combat_conv_tc(const combat_conv_tc_desc* d, void* stream) {
   }
   if (use_rr) {
     const int smem_bytes = TcRRCfg::SMEM_FIXED + rr_na * rr_a_bytes + rr_nb * TcRRCfg::B_BYTES;
-    if (mode == 1) {
+    if (mode == 3) {
+      cudaFuncSetAttribute(conv_tc_rr_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+      pdl_launch(conv_tc_rr_kernel<3>, grid, TC_THREADS, smem_bytes, st, maps, p, rr_a_bytes, rr_na, rr_nb);
+    } else if (mode == 1) {
       cudaFuncSetAttribute(conv_tc_rr_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
       pdl_launch(conv_tc_rr_kernel<1>, grid, TC_THREADS, smem_bytes, st, maps, p, rr_a_bytes, rr_na, rr_nb);
     } else if (mode == 2) {
@@ -1581,13 +1623,13 @@ extern "C" int combat_conv_tc(const combat_conv_tc_desc* d, void* stream) {
     COMBAT_RETURN_LAUNCH("conv_tc_rr");
   }
   if (pair) {
-    if (BLOCK_N == 256) { if (mode == 1) LAUNCH_P(256, 1) else if (mode == 2) LAUNCH_P(256, 2) else LAUNCH_P(256, 0) }
-    else { if (mode == 1) LAUNCH_P(128, 1) else if (mode == 2) LAUNCH_P(128, 2) else LAUNCH_P(128, 0) }
+    if (BLOCK_N == 256) { if (mode == 3) LAUNCH_P(256, 3) else if (mode == 1) LAUNCH_P(256, 1) else if (mode == 2) LAUNCH_P(256, 2) else LAUNCH_P(256, 0) }
+    else { if (mode == 3) LAUNCH_P(128, 3) else if (mode == 1) LAUNCH_P(128, 1) else if (mode == 2) LAUNCH_P(128, 2) else LAUNCH_P(128, 0) }
     COMBAT_RETURN_LAUNCH("conv_tc_pair");
   }
-  if (BLOCK_N == 256) { if (mode == 1) LAUNCH_C(256, 1) else if (mode == 2) LAUNCH_C(256, 2) else LAUNCH_C(256, 0) }
-  else if (BLOCK_N == 128) { if (mode == 1) LAUNCH_C(128, 1) else if (mode == 2) LAUNCH_C(128, 2) else LAUNCH_C(128, 0) }
-  else { if (mode == 1) LAUNCH_C(64, 1) else if (mode == 2) LAUNCH_C(64, 2) else LAUNCH_C(64, 0) }
+  if (BLOCK_N == 256) { if (mode == 3) LAUNCH_C(256, 3) else if (mode == 1) LAUNCH_C(256, 1) else if (mode == 2) LAUNCH_C(256, 2) else LAUNCH_C(256, 0) }
+  else if (BLOCK_N == 128) { if (mode == 3) LAUNCH_C(128, 3) else if (mode == 1) LAUNCH_C(128, 1) else if (mode == 2) LAUNCH_C(128, 2) else LAUNCH_C(128, 0) }
+  else { if (mode == 3) LAUNCH_C(64, 3) else if (mode == 1) LAUNCH_C(64, 1) else if (mode == 2) LAUNCH_C(64, 2) else LAUNCH_C(64, 0) }
 #undef LAUNCH_C
 #undef LAUNCH_P
   COMBAT_RETURN_LAUNCH("conv_tc");

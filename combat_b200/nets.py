@@ -156,6 +156,9 @@ class NetBase:
         self.tc_first_wgrad = not os.environ.get("COMBAT_NO_TC_FIRST_WGRAD")  # the weight gradient of those convs through im2col3
         # the 1x1 stride-2 shortcut's input gradient as an extra tap of the block's 3x3 stride-2 input-gradient launch
         self.fuse_shortcut_dgrad = not os.environ.get("COMBAT_NO_FUSE_SC")
+        # train-mode BatchNorm backward: the reduction (sum g, sum g * xhat) in the epilogue of the input-gradient conv that
+        # produces g, instead of a pass of its own over (dy, x, y)
+        self.fuse_bn_bwd_reduce = not os.environ.get("COMBAT_NO_FUSE_BNB")
         self._w64 = {}
         self.last_stats_nblk = 0
         self.convs: dict[str, ConvSpec] = {}
@@ -274,12 +277,15 @@ class NetBase:
         return out
 
     def conv_dgrad(self, dy, cs: ConvSpec, in_hw, residual=None, n_out_ch=None, mask=None, mask_scale=None, post_add=None,
-                   shortcut=None):
+                   shortcut=None, bnb=None):
         """dy: NHWC [N,Ho,Wo,Cout] -> dx NHWC [N,H,W,n_out_ch or Cin] (+ residual).
         mask/mask_scale/post_add: fused backward of the eval-mode relu(bn(.)) in front of this conv (tcgen05 path only):
         dx = (mask > 0 ? (dgrad + residual) * mask_scale[c] : 0) + post_add.
         shortcut=(dy_sc, cs_sc): the block's 1x1 stride-2 shortcut conv reads the same input; its input gradient is one more
-        tap of this launch (same accumulator) instead of a launch of its own plus a residual read."""
+        tap of this launch (same accumulator) instead of a launch of its own plus a residual read.
+        bnb=(x, scale, shift, mean, invstd): the conv's input went through a TRAIN-mode relu(bn(x)); the epilogue masks the
+        gradient with the forward's predicate and leaves the per-CTA partial sums of the BatchNorm backward reduction in
+        ops.Scratch (self.last_stats_nblk blocks) -- the caller finishes with ops.bn_bwd_train_from_partials."""
         N, Ho, Wo, _ = dy.shape
         H, W = in_hw
         Cx = cs.Cin if n_out_ch is None else n_out_ch
@@ -290,25 +296,39 @@ class NetBase:
         fuse_sc = (shortcut is not None and self.fuse_shortcut_dgrad and self._tc_ok(cs) and self._tc_ok(shortcut[1]) and Cx == cs.Cin
                    and cs.stride == 2 and cs.k == 3 and cs.pad == 1 and shortcut[1].k == 1 and shortcut[1].stride == 2
                    and shortcut[1].Cin == cs.Cin and shortcut[1].Cout == cs.Cout and residual is None)
+        if bnb is not None and (not self.bnb_ok(cs, bnb[0]) or (shortcut is not None and not fuse_sc) or residual is not None
+                                or mask is not None or Cx != cs.Cin):
+            raise RuntimeError("fused BatchNorm backward reduction: unsupported launch (check bnb_ok first)")
         if shortcut is not None and not fuse_sc:   # unfused: the shortcut's input gradient first, added as the residual
             residual_sc = self.conv_dgrad(shortcut[0], shortcut[1], in_hw, residual=residual)
             return self.conv_dgrad(dy, cs, in_hw, residual=residual_sc, n_out_ch=n_out_ch, mask=mask, mask_scale=mask_scale,
                                    post_add=post_add)
         if self._tc_ok(cs) and (Cx == cs.Cin or (Cx % 64 == 0 and Cx < cs.Cin and cs.stride == 1)):
             extra = dict(in2=shortcut[0], w2=self._wptr(shortcut[1], True)) if fuse_sc else {}
+            if bnb is not None:
+                extra.update(bnb=bnb, stats=ops.Scratch.get(self.device))
             d = ops.conv_tc_desc(dy, self._wptr(cs, True), dx, N, Ho, Wo, cs.Cout, H, W, Cx, cs.k, cs.k, 1, padp,
                                  cs.stride, residual=residual, mask=mask, mask_scale=mask_scale, post_add=post_add, **extra)
             if lib.combat_conv_tc_supported(C.byref(d)):
                 fl = 2.0 * N * Ho * Wo * cs.Cout * Cx * (cs.k * cs.k + (1 if fuse_sc else 0))
                 _tc_launch(lambda: lib.combat_conv_tc(C.byref(d), ops._s()), "conv_tc(dgrad)", fl,
-                           _tag(N, H, W, cs) + (" +sc" if fuse_sc else ""))
+                           _tag(N, H, W, cs) + (" +sc" if fuse_sc else "") + (" +bnb" if bnb is not None else ""))
+                if bnb is not None:
+                    self.last_stats_nblk = lib.combat_conv_tc_last_grid()
                 return dx
+        if bnb is not None:
+            raise RuntimeError("fused BatchNorm backward reduction needs the tcgen05 path")
         if mask is not None or post_add is not None:
             raise RuntimeError("fused BatchNorm backward epilogue needs the tcgen05 path")
         ops.conv_simt(dy, (N, Ho, Wo), ops.nhwc_strides(Ho, Wo, cs.Cout), self._wptr(cs, True), self.dt, dx, (H, W),
                       ops.nhwc_strides(H, W, Cx), Ci=cs.Cout, Co=Cx, KH=cs.k, KW=cs.k, stride=1, pad=padp, up=cs.stride,
                       residual=residual)
         return dx
+
+    def bnb_ok(self, cs: ConvSpec, x):
+        """can the input-gradient launch of `cs` carry the reduction of the train-mode BatchNorm backward in front of it?"""
+        return (self.fuse_bn_bwd_reduce and self._tc_ok(cs) and cs.k == 3 and x.dtype == torch.bfloat16 and cs.Cin <= 512
+                and (cs.stride == 1 or self.fuse_shortcut_dgrad))
 
     def conv_wgrad(self, x, dy, cs: ConvSpec, dead_bias=False):
         """accumulates dW (OIHW float32) and the bias gradient into the flat gradient buffer.
@@ -536,15 +556,15 @@ class Classifier(NetBase):
                                                                   self.eps)
             if not torch.cuda.is_current_stream_capturing():  # a capture pass executes nothing; replays are counted by
                 self.num_batches_tracked[bn.name] += 1        # bump_batches_tracked() (one call per replayed train forward)
-            st = (scale, mean, invstd)
+            st = (scale, mean, invstd, shift)
         else:
             scale, shift = ops.bn_eval_prepare(Cc, g, b, self.rm(bn), self.rv(bn), self.eps)
-            st = (scale, None, None)
+            st = (scale, None, None, shift)
         y = ops.affine_act(x, scale, shift, relu, residual=residual, out_dtype=self.dtype)
         return y, st
 
     def _bn_bwd(self, bn, dy, x, y, st, train, relu, need_wgrad, dadd=None, want_dres=False):
-        scale, mean, invstd = st
+        scale, mean, invstd = st[:3]
         if train:
             if need_wgrad:
                 dg, db = self.store.g(bn.name + ".weight"), self.store.g(bn.name + ".bias")
@@ -553,6 +573,16 @@ class Classifier(NetBase):
                 dg, db = tmp[0], tmp[1]
             return ops.bn_bwd_train(dy, x, y, self.store.p(bn.name + ".weight"), mean, invstd, relu, dg, db, dadd, want_dres)
         return ops.bn_bwd_eval(dy, y, scale, relu, dadd, want_dres)
+
+    def _bn_bwd_tail(self, bn, g, x, st, need_wgrad, dadd=None):
+        """finalize + apply of a train-mode BatchNorm backward whose reduction ran in the producing conv's epilogue"""
+        if need_wgrad:
+            dg, db = self.store.g(bn.name + ".weight"), self.store.g(bn.name + ".bias")
+        else:
+            tmp = torch.empty((2, bn.C), dtype=torch.float32, device=self.device)
+            dg, db = tmp[0], tmp[1]
+        return ops.bn_bwd_train_from_partials(g, x, self.store.p(bn.name + ".weight"), st[1], st[2], self.last_stats_nblk, dg, db,
+                                              dadd=dadd)
 
     # ---- forward
     def forward(self, x_nchw, train: bool, save: bool = True, fuse: bool = True):
@@ -676,19 +706,28 @@ class Classifier(NetBase):
                 hw_in, hw_mid = h_in.shape[1:3], c1.shape[1:3]
                 if need_wgrad:
                     self.conv_wgrad(o2, dh, blk["conv2"])
-                d_o2 = self.conv_dgrad(dh, blk["conv2"], hw_mid)
-                d_c1, _ = self._bn_bwd(blk["bn2"], d_o2, c1, o2, st2, train, True, need_wgrad)
+                if train and self.bnb_ok(blk["conv2"], c1):
+                    g2 = self.conv_dgrad(dh, blk["conv2"], hw_mid, bnb=(c1, st2[0], st2[3], st2[1], st2[2]))
+                    d_c1 = self._bn_bwd_tail(blk["bn2"], g2, c1, st2, need_wgrad)
+                else:
+                    d_o2 = self.conv_dgrad(dh, blk["conv2"], hw_mid)
+                    d_c1, _ = self._bn_bwd(blk["bn2"], d_o2, c1, o2, st2, train, True, need_wgrad)
                 if need_wgrad:
                     self.conv_wgrad(o1, d_c1, blk["conv1"])
+                fuse1 = train and self.bnb_ok(blk["conv1"], h_in)
+                bnb1 = (h_in, st1[0], st1[3], st1[1], st1[2]) if fuse1 else None
                 if "sc" in blk:
                     if need_wgrad:
                         self.conv_wgrad(o1, dh, blk["sc"])
-                    d_o1 = self.conv_dgrad(d_c1, blk["conv1"], hw_in, shortcut=(dh, blk["sc"]))
+                    d_o1 = self.conv_dgrad(d_c1, blk["conv1"], hw_in, shortcut=(dh, blk["sc"]), bnb=bnb1)
                     dadd = None
                 else:
-                    d_o1 = self.conv_dgrad(d_c1, blk["conv1"], hw_in)
+                    d_o1 = self.conv_dgrad(d_c1, blk["conv1"], hw_in, bnb=bnb1)
                     dadd = dh
-                dh, _ = self._bn_bwd(blk["bn1"], d_o1, h_in, o1, st1, train, True, need_wgrad, dadd=dadd)
+                if fuse1:
+                    dh = self._bn_bwd_tail(blk["bn1"], d_o1, h_in, st1, need_wgrad, dadd=dadd)
+                else:
+                    dh, _ = self._bn_bwd(blk["bn1"], d_o1, h_in, o1, st1, train, True, need_wgrad, dadd=dadd)
             else:
                 h_in, c1, o1, c2, out, cs_, st1, st2, sts = saved
                 hw_in, hw_mid = h_in.shape[1:3], c1.shape[1:3]

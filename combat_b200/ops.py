@@ -295,9 +295,12 @@ def wgrad_cout3(a_nhwc, dz_nchw, dw, db):
 
 def conv_tc_desc(x, w_ptr, out, N, Hi, Wi, Ci, Ho, Wo, Co, KH, KW, stride, pad, up, bias=None, residual=None, stats=None,
                  act=0, post_scale=None, post_shift=None, out2=None, scale2=None, shift2=None, mask=None, mask_scale=None,
-                 post_add=None, in2=None, w2=None):
+                 post_add=None, in2=None, w2=None, bnb=None):
+    """bnb = (x, scale, shift, mean, invstd): fused reduction of a train-mode relu(bn(x)) backward (needs `stats`)."""
     d = ConvTcDesc()
     d.in2, d.w2 = _p(in2), w2
+    if bnb is not None:
+        d.bnb_x, d.bnb_scale, d.bnb_shift, d.bnb_mean, d.bnb_invstd = (_p(t) for t in bnb)
     d.act, d.post_scale, d.post_shift = act, _p(post_scale), _p(post_shift)
     d.out2, d.scale2, d.shift2 = _p(out2), _p(scale2), _p(shift2)
     d.mask, d.mask_scale, d.post_add = _p(mask), _p(mask_scale), _p(post_add)
@@ -407,6 +410,19 @@ def bn_bwd_train(dy, x, y, gamma, mean, invstd, relu, dgamma_out, dbeta_out, dad
     check(lib.combat_bn_bwd_apply(_p(dy), _p(x), dt_code(x), _p(y), _p(dadd), _p(dx), _p(dres), dt_code(dy), R, Cc, _p(gamma),
                                   _p(mean), _p(invstd), _p(dgamma_out), _p(dbeta_out), None, int(relu), _s()), "bn_bwd_apply")
     return dx, dres
+
+
+def bn_bwd_train_from_partials(g, x, gamma, mean, invstd, nblk, dgamma_out, dbeta_out, dadd=None):
+    """Second half of bn_bwd_train when the producing input-gradient conv already masked the gradient (g) and left the
+    per-CTA partial sums of (g, g * xhat) in Scratch (conv_tc_desc(bnb=...)): finalize + apply, no reduction pass."""
+    Cc = x.shape[-1]
+    R = x.numel() // Cc
+    partial = Scratch.get(x.device)
+    check(lib.combat_bn_bwd_finalize(_p(partial), nblk, Cc, _p(dgamma_out), _p(dbeta_out), _s()), "bn_bwd_finalize")
+    dx = torch.empty_like(g)
+    check(lib.combat_bn_bwd_apply(_p(g), _p(x), dt_code(x), None, _p(dadd), _p(dx), None, dt_code(g), R, Cc, _p(gamma),
+                                  _p(mean), _p(invstd), _p(dgamma_out), _p(dbeta_out), None, 0, _s()), "bn_bwd_apply")
+    return dx
 
 
 def bn_bwd_eval(dy, y, eval_scale, relu, dadd=None, want_dres=False):

@@ -186,6 +186,17 @@ typedef struct {
    * pixels, i.e. it is one more (tensor, filter) tap of parity class (0,0) accumulated in the same TMEM accumulator. */
   const void* in2;
   const void* w2;
+  /* optional: backward of a TRAIN-mode relu(bn(x)) in front of this (input-gradient) launch, reduction half fused into the
+   * epilogue (preact_resnet.py:20-23 / torch batch_norm backward): bnb_x = the saved pre-normalisation tensor (bf16 NHWC like
+   * out), bnb_scale/bnb_shift = the forward's per-channel affine (y = relu(x * scale + shift)), bnb_mean/bnb_invstd = the batch
+   * statistics.  out <- g = (x * scale + shift > 0) ? acc : 0 (bf16) and `stats` receives per-CTA partial sums [grid][2][Co]
+   * of (g, g * (x - mean) * invstd): exactly what combat_bn_bwd_reduce leaves for combat_bn_bwd_finalize, so the separate
+   * reduction pass over (dy, x, y) disappears and combat_bn_bwd_apply runs on g with relu = 0. */
+  const void* bnb_x;
+  const float* bnb_scale;
+  const float* bnb_shift;
+  const float* bnb_mean;
+  const float* bnb_invstd;
 } combat_conv_tc_desc;
 int combat_conv_tc(const combat_conv_tc_desc* d_host, void* stream);
 int combat_conv_tc_wgrad(const combat_conv_tc_desc* d_host, const void* dy, float* dw_ohwi, void* stream);

@@ -577,6 +577,48 @@ def test_conv_tc_fused_batchnorm_epilogues(ops, stride_up, shape):
         assert rel(dx.float().permute(0, 3, 1, 2), exp) < 6e-3
 
 
+@pytest.mark.parametrize("shape", [(6, 64, 64, 32, 1), (5, 128, 128, 16, 1), (9, 256, 256, 8, 1), (6, 64, 128, 32, 2), (40, 512, 512, 4, 1)])
+def test_conv_tc_fused_batchnorm_backward_reduction(ops, shape):
+    """MODE 3 epilogue of an input-gradient launch: g = (x * scale + shift > 0) ? dgrad : 0 in bf16 plus the per-CTA partial sums
+    of g and g * (x - mean) * invstd -- the reduction half of the train-mode relu(bn(x)) backward (preact_resnet.py:20-23) that
+    combat_bn_bwd_reduce otherwise computes in a pass of its own.  Shapes hit conv_tc64 / conv_tc_rr / the CTA-pair kernel / the
+    four parity classes of a stride-2 input gradient / tiles spanning several images."""
+    import ctypes as C
+
+    from combat_b200._lib import check, lib
+    N, Ci, Co, H, s = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    Ho = H // s
+    w = (torch.randn(Co, Ci, 3, 3, generator=g) * 0.05).bfloat16().float()
+    dy = torch.randn(N, Co, Ho, Ho, generator=g).bfloat16().float()
+    xin = torch.zeros(N, Ci, H, H, requires_grad=True)
+    F.conv2d(xin, w, None, s, 1).backward(dy)
+    dgrad = xin.grad                                                  # [N, Ci, H, H]
+    x = (torch.randn(N, Ci, H, H, generator=g) * 1.5 + 0.3).bfloat16().float()    # the saved pre-normalisation tensor
+    mean, var = x.mean((0, 2, 3)), x.var((0, 2, 3), unbiased=False)
+    invstd = (var + 1e-5).rsqrt()
+    gamma, beta = torch.rand(Ci, generator=g) + 0.5, torch.randn(Ci, generator=g) * 0.3
+    scale = gamma * invstd
+    shift = beta - mean * scale
+    pred = torch.addcmul(shift[None, :, None, None], x, scale[None, :, None, None]) > 0   # not fused, but only ties differ
+    want_g = dgrad * pred
+    xhat = (x - mean[None, :, None, None]) * invstd[None, :, None, None]
+    w_d = dev(w.flip(2, 3).permute(1, 2, 3, 0).bfloat16())
+    dx = torch.empty(N, H, H, Ci, device="cuda", dtype=torch.bfloat16)
+    part = torch.full((148 * 4 * 2 * Ci,), 7.0, device="cuda")
+    d = ops.conv_tc_desc(dev(_nhwc(dy).bfloat16()), w_d.data_ptr(), dx, N, Ho, Ho, Co, H, H, Ci, 3, 3, 1, 1, s, stats=part,
+                         bnb=(dev(_nhwc(x).bfloat16()), dev(scale), dev(shift), dev(mean), dev(invstd)))
+    check(lib.combat_conv_tc(C.byref(d), ops._s()), "conv_tc dgrad + bn backward reduction")
+    nblk = lib.combat_conv_tc_last_grid()
+    torch.cuda.synchronize()
+    got = dx.float().permute(0, 3, 1, 2).cpu()
+    assert rel(got, want_g) < 6e-3
+    ps = part[: nblk * 2 * Ci].view(nblk, 2, Ci).double().sum(0).cpu()
+    # the sums are taken over the UNROUNDED float32 g (like bn_bwd_reduce over a float32 dy would): compare with float64 torch
+    assert rel(ps[0], want_g.double().sum((0, 2, 3))) < 1e-4
+    assert rel(ps[1], (want_g.double() * xhat.double()).sum((0, 2, 3))) < 1e-4
+
+
 @pytest.mark.parametrize("stride,N,H", [(1, 5, 16), (2, 6, 32), (1, 3, 24)])
 def test_im2col3_tensor_core_conv(ops, stride, N, H):
     """3 -> 64 conv as im2col3 ([hi | lo] bf16 halves of the float32 image) + 1x1 tcgen05 conv with the filter stored twice:
