@@ -67,6 +67,8 @@ _SIGS = {
     "combat_conv_tc_wgrad": ([P(ConvTcDesc), vp, vp, vp], i32),
     "combat_conv_tc_supported": ([P(ConvTcDesc)], i32),
     "combat_conv_tc_last_grid": ([], i32),
+    "combat_conv_tc_cout3": ([vp, vp, vp, vp, i32, i32, i32, i32, vp], i32),
+    "combat_conv_tc_cout3_supported": ([i32, i32, i32], i32),
     "combat_bn_stats": ([vp, i32, i64, i32, vp, i32, P(i32), vp], i32),
     "combat_bn_finalize": ([vp, i32, i64, i32, vp, vp, vp, vp, f32, f32, vp, vp, vp, vp, vp], i32),
     "combat_bn_eval_affine": ([vp, vp, vp, i32, f32, vp, vp, vp], i32),

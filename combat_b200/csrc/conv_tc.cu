@@ -1635,6 +1635,190 @@ extern "C" int combat_conv_tc(const combat_conv_tc_desc* d, void* stream) {
   COMBAT_RETURN_LAUNCH("conv_tc");
 }
 
+// ---------------------------------------------------------------------------------------------- 64 -> 3 channels, 3x3, stride 1
+// The image-side convs with 3 OUTPUT channels (the generator's last conv and the input gradient of the classifiers' first conv:
+// networks/models.py:316, preact_resnet.py:77 backward) ran on CUDA cores at ~106 us per 512 x 32 x 32 batch (FP32-FMA bound,
+// 2.8 % of the step).  On the tensor pipe they are pure data movement: conv_tc64_kernel's mainloop (resident filter, one
+// (BH+2)-row box per horizontal tap, vertical taps as row offsets) with N = 16 accumulator columns (3 used; filter rows 3..15 are
+// TMA zero fill), and an epilogue that needs NO transposition: a thread owns a pixel, consecutive lanes are consecutive pixels of
+// an image row, so the three NCHW float32 planes are written with coalesced 128-byte stores straight from tcgen05.ld.
+struct TcO3Params {
+  int N, H, W;
+  int BW, BH, tiles_h, total_tiles;
+  int act;             // 0 none, 1 tanh
+  const float* bias;   // [3] or NULL
+  float* out;          // NCHW float32 [N,3,H,W]
+};
+struct TcO3Maps {
+  CUtensorMap in;  // box (64, BW, BH+2, 1)
+  CUtensorMap w;   // [3 rows][9 taps][64]: box (64, 1, 16)
+};
+#define O3_STAGES 6
+
+__global__ void __launch_bounds__(192, 1) conv_tc_cout3_kernel(const __grid_constant__ TcO3Maps maps, const TcO3Params p, const int stage_bytes,
+                                                               const int n_stages) {
+  pdl_launch_dependents();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* wsm = smem;                      // [9 taps][16 rows][64 ci] bf16, SWIZZLE_128B (2 KB per tap)
+  uint8_t* stages = smem + 9 * 2048;        // 18 KB is a multiple of 1024
+  uint64_t* bars = (uint64_t*)(stages + n_stages * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + O3_STAGES;
+  uint64_t* tfull_bar = bars + 2 * O3_STAGES;
+  uint64_t* tempty_bar = bars + 2 * O3_STAGES + 2;
+  uint64_t* w_bar = bars + 2 * O3_STAGES + 4;
+  uint32_t* tmem_ptr_smem = (uint32_t*)(bars + 2 * O3_STAGES + 5);
+  const int warp = uniform_i(threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.w);
+    tma_prefetch_desc(&maps.in);
+    for (int s = 0; s < O3_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);
+    }
+    mbar_init(w_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_smem, 32);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = uniform_u(*tmem_ptr_smem);
+  pdl_wait();
+
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      mbar_expect_tx(w_bar, 9 * 2048);
+      for (int t = 0; t < 9; ++t) tma_load_3d(wsm + t * 2048, &maps.w, w_bar, 0, t, 0);
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int ht = tile % p.tiles_h, n = tile / p.tiles_h;
+      for (int dw = -1; dw <= 1; ++dw) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one_sync()) {
+          mbar_expect_tx(&full_bar[stage], stage_bytes);
+          tma_load_4d(stages + stage * stage_bytes, &maps.in, &full_bar[stage], 0, dw, ht * p.BH - 1, n);
+        }
+        if (++stage == n_stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc(TILE_M, 16, 0, 0);
+    mbar_wait(w_bar, 0);
+    tc_fence_after();
+    const uint32_t wbase = smem_u32(wsm), sbase = smem_u32(stages);
+    const uint32_t row_step = (uint32_t)p.BW * 128;
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * 16;
+      for (int dwi = 0; dwi < 3; ++dwi) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = sbase + stage * stage_bytes;
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int dhi = 0; dhi < 3; ++dhi) {
+            const uint64_t adesc = make_smem_desc(sa + dhi * row_step, 16, 1024);
+            const uint64_t bdesc = make_smem_desc(wbase + (dhi * 3 + dwi) * 2048, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < KCHUNK / 16; ++k) umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (dwi | dhi | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+        }
+        if (++stage == n_stages) { stage = 0; phase ^= 1; }
+      }
+      if (elect_one_sync()) umma_commit(&tfull_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // epilogue: warp w owns TMEM lanes [32 * (w % 4), +32) = 32 consecutive pixels of the tile
+    const int quarter = warp & 3;
+    const float b0 = p.bias ? p.bias[0] : 0.f, b1 = p.bias ? p.bias[1] : 0.f, b2 = p.bias ? p.bias[2] : 0.f;
+    const long long HW = (long long)p.H * p.W;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int ht = tile % p.tiles_h, n = tile / p.tiles_h;
+      const int row = quarter * 32 + lane;
+      const int hi = row / p.BW, wi = row - hi * p.BW;
+      const int h = ht * p.BH + hi;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      uint32_t v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 16, v);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (h < p.H) {
+        float y0 = __uint_as_float(v[0]) + b0, y1 = __uint_as_float(v[1]) + b1, y2 = __uint_as_float(v[2]) + b2;
+        if (p.act == 1) { y0 = tanhf(y0); y1 = tanhf(y1); y2 = tanhf(y2); }
+        float* o = p.out + (long long)n * 3 * HW + (long long)h * p.W + wi;
+        o[0] = y0;
+        o[HW] = y1;
+        o[2 * HW] = y2;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 32);
+  }
+}
+
+extern "C" int combat_conv_tc_cout3_supported(int N, int H, int W) {
+  int bw, bh, bni;
+  if (N <= 0 || H <= 0 || W <= 0) return 0;
+  pick_box(H, W, TILE_M, &bw, &bh, &bni);
+  const int stage_bytes = (bh + 2) * bw * 128;
+  return bw == W && bni == 1 && (bw % 8) == 0 && 2 * stage_bytes + 9 * 2048 + 1024 + 256 <= 232448;
+}
+
+extern "C" int combat_conv_tc_cout3(const void* in, const void* w, const float* bias, float* out, int N, int H, int W, int act,
+                                    void* stream) {
+  COMBAT_ARG(in && w && out && (act == 0 || act == 1), 0);
+  COMBAT_ARG(combat_conv_tc_cout3_supported(N, H, W), 0);
+  TcO3Params p;
+  memset(&p, 0, sizeof(p));
+  TcO3Maps maps;
+  memset(&maps, 0, sizeof(maps));
+  int bni;
+  pick_box(H, W, TILE_M, &p.BW, &p.BH, &bni);
+  p.N = N; p.H = H; p.W = W;
+  p.tiles_h = cdiv(H, p.BH);
+  p.total_tiles = p.tiles_h * N;
+  p.act = act;
+  p.bias = bias;
+  p.out = out;
+  const int stage_bytes = (p.BH + 2) * p.BW * 128;
+  int n_stages = (232448 - 9 * 2048 - 1024 - 256) / stage_bytes;
+  if (n_stages > O3_STAGES) n_stages = O3_STAGES;
+  int rc = make_act_map(&maps.in, in, 64, W, H, N, 64, (long long)W * 64, (long long)H * W * 64, p.BW, p.BH + 2, 1);
+  if (rc) return rc;
+  rc = make_w_map(&maps.w, w, 64, 9, 3, 16);
+  if (rc) return rc;
+  const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  const int smem_bytes = 9 * 2048 + n_stages * stage_bytes + 1024 + 256;
+  cudaFuncSetAttribute(conv_tc_cout3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  pdl_launch(conv_tc_cout3_kernel, grid, 192, smem_bytes, (cudaStream_t)stream, maps, p, stage_bytes, n_stages);
+  COMBAT_RETURN_LAUNCH("conv_tc_cout3");
+}
+
 // ---------------------------------------------------------------------------------------------- wgrad kernel
 // D[(tap,ci), co] = sum_pixels X[pixel @ tap, ci] * dY[pixel, co]; both operands MN-major (pixels are the K dim).
 // One CTA = (pair of 64-row (tap, ci-chunk) blocks) x (BLOCK_N output channels) x (one split of the pixel range);

@@ -159,6 +159,8 @@ class NetBase:
         # train-mode BatchNorm backward: the reduction (sum g, sum g * xhat) in the epilogue of the input-gradient conv that
         # produces g, instead of a pass of its own over (dy, x, y)
         self.fuse_bn_bwd_reduce = not os.environ.get("COMBAT_NO_FUSE_BNB")
+        # 64 -> 3 convs (generator output, input gradient of the classifiers' first conv) on the tensor pipe
+        self.tc_cout3 = not os.environ.get("COMBAT_NO_TC_COUT3")
         self._w64 = {}
         self.last_stats_nblk = 0
         self.convs: dict[str, ConvSpec] = {}
@@ -406,6 +408,8 @@ class NetBase:
         H, W = in_hw
         dx = torch.empty((N, cs.Cin, H, W), dtype=torch.float32, device=self.device)
         if self.fast_small and cs.Cin == 3 and cs.Cout == 64 and cs.k == 3 and cs.pad == 1 and cs.stride == 1:
+            if self.tc_cout3 and self.use_tc and ops.conv_tc_cout3_ok(dy):   # tensor pipe, N = 16 accumulator columns
+                return ops.conv_tc_cout3(dy, self._wptr(cs, True), dx)
             return ops.conv_cout3(dy, self._wptr(cs, True), self.dt, dx)
         ops.conv_simt(dy, (N, Ho, Wo), ops.nhwc_strides(Ho, Wo, cs.Cout), self._wptr(cs, True), self.dt, dx, (H, W),
                       ops.nchw_strides(cs.Cin, H, W), Ci=cs.Cout, Co=cs.Cin, KH=cs.k, KW=cs.k, stride=1,
@@ -848,7 +852,9 @@ class Generator(NetBase):
         cs = cv["upconv0_0"]
         out = torch.empty((N, self.out_channel, H, W), dtype=torch.float32, device=self.device)
         small = self.fast_small and nf == 64 and self.out_channel == 3
-        if small:
+        if small and self.tc_cout3 and self.use_tc and ops.conv_tc_cout3_ok(a01):
+            ops.conv_tc_cout3(a01, self._wptr(cs), out, bias=self._bias(cs), act=1)
+        elif small:
             ops.conv_cout3(a01, self._wptr(cs), self.dt, out, bias=self._bias(cs), act=1)
         else:
             ops.conv_simt(a01, (N, H, W), ops.nhwc_strides(H, W, nf), self._wptr(cs), self.dt, out, (H, W),

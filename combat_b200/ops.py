@@ -283,6 +283,18 @@ def conv_cout3(x_nhwc, w_ptr, w_dt, out_nchw, bias=None, act=0):
     return out_nchw
 
 
+def conv_tc_cout3_ok(x_nhwc):
+    N, H, W, Ci = x_nhwc.shape
+    return Ci == 64 and x_nhwc.dtype == torch.bfloat16 and bool(lib.combat_conv_tc_cout3_supported(N, H, W))
+
+
+def conv_tc_cout3(x_nhwc, w_ptr, out_nchw, bias=None, act=0):
+    """64 -> 3 conv on the tensor pipe (bf16 NHWC in, bf16 [3][9][64] filter, float32 NCHW out)."""
+    N, H, W, _ = x_nhwc.shape
+    check(lib.combat_conv_tc_cout3(_p(x_nhwc), w_ptr, _p(bias), _p(out_nchw), N, H, W, act, _s()), "conv_tc_cout3")
+    return out_nchw
+
+
 def wgrad_cin3(x_nchw, dy, dw, db, Co, stride):
     N, _, H, W = x_nchw.shape
     check(lib.combat_wgrad_cin3(_p(x_nchw), _p(dy), dt_code(dy), _p(dw), _p(db), N, H, W, Co, stride, _s()), "wgrad_cin3")

@@ -201,6 +201,12 @@ typedef struct {
 int combat_conv_tc(const combat_conv_tc_desc* d_host, void* stream);
 int combat_conv_tc_wgrad(const combat_conv_tc_desc* d_host, const void* dy, float* dw_ohwi, void* stream);
 int combat_conv_tc_supported(const combat_conv_tc_desc* d_host);
+/* 64 -> 3 channels, 3x3, stride 1, pad 1 on the tensor pipe (N = 16 accumulator columns, 3 used): the generator's last conv
+ * (networks/models.py:316,341; act 1 = tanh) and the input gradient of the classifiers' first conv (preact_resnet.py:77 /
+ * resnet.py:73 backward).  in: bf16 NHWC [N,H,W,64]; w: bf16 [3][9][64] (for the input gradient: the flipped / transposed
+ * filter); out: float32 NCHW [N,3,H,W].  Needs whole-row tiles: combat_conv_tc_cout3_supported(N, H, W). */
+int combat_conv_tc_cout3(const void* in, const void* w, const float* bias, float* out, int N, int H, int W, int act, void* stream);
+int combat_conv_tc_cout3_supported(int N, int H, int W);
 /* number of CTAs (= partial-sum blocks written to desc.stats) of the most recent combat_conv_tc launch of this thread */
 int combat_conv_tc_last_grid(void);
 

@@ -619,6 +619,28 @@ def test_conv_tc_fused_batchnorm_backward_reduction(ops, shape):
     assert rel(ps[1], (want_g.double() * xhat.double()).sum((0, 2, 3))) < 1e-4
 
 
+@pytest.mark.parametrize("N,H,act", [(5, 32, 1), (300, 32, 0), (7, 16, 1), (3, 64, 0)])
+def test_conv_tc_cout3(ops, N, H, act):
+    """64 -> 3 conv on the tensor pipe (conv_tc_cout3_kernel): the generator's last conv (bias + tanh, networks/models.py:316,341)
+    and the input gradient of the classifiers' first conv, float32 NCHW out, against torch on the same bf16 operands."""
+    from combat_b200._lib import lib
+    g = torch.Generator().manual_seed(1000 + N + H)
+    x = torch.randn(N, 64, H, H, generator=g).bfloat16().float()
+    w = (torch.randn(3, 64, 3, 3, generator=g) * 0.1).bfloat16().float()
+    bias = torch.randn(3, generator=g) if act else None
+    want = F.conv2d(x, w, bias, 1, 1)
+    if act:
+        want = torch.tanh(want)
+    xd = dev(_nhwc(x).bfloat16())
+    assert ops.conv_tc_cout3_ok(xd) == bool(lib.combat_conv_tc_cout3_supported(N, H, H))
+    assert ops.conv_tc_cout3_ok(xd)
+    wd = dev(w.permute(0, 2, 3, 1).bfloat16())   # [3][9][64]
+    out = torch.full((N, 3, H, H), 7.0, device="cuda")
+    ops.conv_tc_cout3(xd, wd.data_ptr(), out, bias=dev(bias) if act else None, act=act)
+    torch.cuda.synchronize()
+    assert rel(out, want) < 2e-5
+
+
 @pytest.mark.parametrize("stride,N,H", [(1, 5, 16), (2, 6, 32), (1, 3, 24)])
 def test_im2col3_tensor_core_conv(ops, stride, N, H):
     """3 -> 64 conv as im2col3 ([hi | lo] bf16 halves of the float32 image) + 1x1 tcgen05 conv with the filter stored twice:
