@@ -2180,7 +2180,11 @@ extern "C" int combat_conv_tc_wgrad(const combat_conv_tc_desc* d, const void* dy
   p.tiles_n = cdiv(d->N, p.BNI);
   p.total_boxes = p.tiles_w * p.tiles_h * p.tiles_n;
   const int ctas_mn = p.m_tiles * p.n_tiles;
-  int splits = cdiv(2 * num_sms(), ctas_mn);
+  // ONE wave of CTAs (the shared-memory ring leaves one CTA per SM): the pixel range is split so that m_tiles * n_tiles * splits
+  // is the largest multiple of the (M, N) tile count that fits the SMs.  (Round 1 aimed at two CTAs per SM with
+  // ceil(2 * SMs / tiles) splits: 297 / 306 / 360 CTAs for the 128 / 256 / 512-channel layers = a third, almost empty wave.)
+  int splits = num_sms() / ctas_mn;
+  if (getenv("COMBAT_WGRAD_SPLITS2")) splits = cdiv(2 * num_sms(), ctas_mn);
   if (splits > p.total_boxes) splits = p.total_boxes;
   if (splits < 1) splits = 1;
   p.boxes_per_split = cdiv(p.total_boxes, splits);
