@@ -69,6 +69,11 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// L2 prefetch of a tensor tile (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -239,6 +244,7 @@ struct TcParams {
   // row-reuse kernel (conv_tc_rr_kernel): work item = super-tile of two vertically adjacent pixel tiles (2s, 2s+1) that share
   // every weight tile; rr_rounds full rounds of gridDim.x items, then rr_rem items -- split into single tiles when they fit
   int rr_rounds, rr_rem, rr_split;
+  int n_epf;              // number of epilogue-input tensors to prefetch (maps.e[0 .. n_epf)), 0: off
   void* out;             // bf16 or float32 (out_f32)
   const void* residual;  // bf16 or float32 (res_f32)
   const float* bias;
@@ -266,6 +272,10 @@ struct TcMaps {
   CUtensorMap in[4];  // parity views of the input (only [0] when unstrided; [1] = the shortcut's gradient tensor when fused)
   CUtensorMap w;      // [Co][taps][Ci] as (Ci, taps, Co)
   CUtensorMap w2;     // fused shortcut: [Co][1][Ci]
+  // epilogue inputs (mask / residual / shortcut gradient: bf16 NHWC like the output), box = one pixel tile x 64 channels.  The TMA
+  // warp prefetches them into L2 two tiles ahead: the epilogue's coalesced loads of a 64-channel layer are otherwise exposed
+  // HBM latency (measured: 1700 of 4180 cycles per tile of the masked 64 -> 64 input gradient).
+  CUtensorMap e[2];
 };
 
 template <int BLOCK_N>
@@ -1020,6 +1030,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc64_kernel(const __grid_c
         }
         if (++stage == n_stages) { stage = 0; phase ^= 1; }
       }
+      const int tile2 = tile + 2 * gridDim.x;   // epilogue inputs of the tile after next -> L2
+      if (p.n_epf > 0 && tile2 < p.total_tiles) {
+        decode_tile(p, tile2, cls, nt, ht, wt, cot);
+        if (elect_one_sync()) {
+          tma_prefetch_4d(&maps.e[0], 0, 0, ht * p.BH, nt);
+          if (p.n_epf > 1) tma_prefetch_4d(&maps.e[1], 0, 0, ht * p.BH, nt);
+        }
+      }
     }
     if (p.dbg && lane == 0) p.dbg[blockIdx.x * 8 + 0] += w_empty;
   } else if (warp == 1) {
@@ -1173,6 +1191,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_rr_kernel(const __grid_
             if (++sb == n_b) { sb = 0; pb ^= 1; }
           }
         }
+      int st2, jm2;
+      if (p.n_epf > 0 && rr_item(p, i + 1, st2, jm2)) {   // epilogue inputs of the next item (two tiles, two 64-channel halves) -> L2
+        const int n2 = st2 / supers_h, hs2 = st2 - n2 * supers_h;
+        if (elect_one_sync()) {
+          for (int e = 0; e < p.n_epf; ++e)
+            for (int j = 0; j < 2; ++j)
+              if (jm2 >> j & 1) {
+                tma_prefetch_4d(&maps.e[e], 0, 0, (2 * hs2 + j) * p.BH, n2);
+                tma_prefetch_4d(&maps.e[e], 64, 0, (2 * hs2 + j) * p.BH, n2);
+              }
+        }
+      }
     }
     if (p.dbg && lane == 0) p.dbg[blockIdx.x * 8 + 0] += w_empty;
   } else if (warp == 1) {
@@ -1543,6 +1573,24 @@ extern "C" int combat_conv_tc(const combat_conv_tc_desc* d, void* stream) {
     rc = make_w_map(&maps.w2, d->w2, d->Ci, 1, d->Co, pair ? BLOCK_N / 2 : BLOCK_N);
     if (rc) return rc;
   }
+  // measured (B200, batch 512): masked 64 -> 64 input gradient 75.3 -> 69.1 us; the 128-channel row-reuse kernel loses 1 us with
+  // it (its epilogue is not the bound), so only the 64-channel kernel prefetches unless COMBAT_EPF_RR is set
+  if ((use64 || (use_rr && getenv("COMBAT_EPF_RR"))) && !getenv("COMBAT_NO_EPF")) {
+    // epilogue-input prefetch (bf16 tensors shaped like the output, whole-row tiles of one image)
+    const void* ein[2] = {nullptr, nullptr};
+    int ne = 0;
+    if (d->bnb_x) ein[ne++] = d->bnb_x;
+    if (d->mask) ein[ne++] = d->mask;
+    if (d->residual && !d->res_f32) ein[ne++] = d->residual;
+    if (d->post_add && ne < 2) ein[ne++] = d->post_add;
+    for (int e = 0; e < ne; ++e) {
+      const long long Cc = d->Co;
+      rc = make_act_map(&maps.e[e], ein[e], d->Co, d->Wo, d->Ho, d->N, Cc, (long long)d->Wo * Cc, (long long)d->Ho * d->Wo * Cc, p.BW,
+                        p.BH, 1);
+      if (rc) return rc;
+    }
+    p.n_epf = ne;
+  }
   p.lbw = 0;
   while ((1 << p.lbw) < p.BW) ++p.lbw;
   p.lbh = 0;
@@ -1570,7 +1618,7 @@ extern "C" int combat_conv_tc(const combat_conv_tc_desc* d, void* stream) {
     p.rr_split = p.rr_rem > 0 && 2 * p.rr_rem <= grid;
   }
   g_last_grid = grid;
-  COMBAT_ARG(!d->stats || (d->Co <= 512 && !d->mask), 0);
+  COMBAT_ARG(!p.stats || (d->Co <= 512 && !d->mask), 0);
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH_P(BN, MD)                                                                                                        \
   {                                                                                                                             \
