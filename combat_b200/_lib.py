@@ -11,7 +11,7 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcombat_b200.so")
+LIB_PATH = os.environ.get("COMBAT_LIB") or os.path.join(_HERE, "libcombat_b200.so")   # COMBAT_LIB: A/B builds of the same C-ABI
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "combat_b200.h")
 
 vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_longlong, C.c_float
