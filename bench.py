@@ -408,7 +408,8 @@ def run_ours(args):
     assert all(np.isfinite(v) for v in sink)
     e2e = world * B * args.steps / (ms_e2e / 1e3)
     h2d = xs_host[0].numel() * 4 + B * 8 * 3 + B * 4 + 20
-    d2h = 8 * 4 + 16 * 4
+    from combat_b200.engine import N_LOSSES
+    d2h = N_LOSSES * 4 + 16 * 4
 
     # ---- roofline leg: per-launch CUDA-event timing of the tcgen05 convolutions in one eager iteration
     roof = None

@@ -93,6 +93,7 @@ _SIGS = {
     "combat_mask_scale": ([vp, vp, vp, i32, i64, f32, vp], i32),
     "combat_adadelta": ([vp, vp, vp, vp, i64, vp, f32, f32, f32, vp], i32),
     "combat_grad_l2": ([vp, vp, vp, vp, i32, i32, i32, i32, vp], i32),
+    "combat_tv_loss": ([vp, vp, f32, vp, vp, i32, i32, i32, i32, vp], i32),
     "combat_post_transform_fwd": ([vp, vp, vp, i32, i32, i32, i32, vp], i32),
     "combat_post_transform_bwd": ([vp, vp, vp, i32, i32, i32, i32, i32, vp], i32),
     "combat_nchw_to_nhwc": ([vp, vp, i32, i32, i32, i32, i32, vp], i32),

@@ -482,3 +482,62 @@ extern "C" int combat_grad_l2(const float* x, const float* x_bd, float* partial,
   pdl_launch(grad_l2_final_k, 1, 256, 0, (cudaStream_t)stream, partial, planes, inv_v, inv_h, out);
   COMBAT_RETURN_LAUNCH("grad_l2");
 }
+
+// ---------------------------------------------------------------------------------------------- total-variation loss (imperceptible variant)
+// train_generator_imperceptible.py:228: loss_tv = kornia.losses.total_variation(inputs_bd).mean(), kornia 0.6.6 (requirements.txt:12):
+//   total_variation(img) = sum_{c,h,w} |img[c, h+1, w] - img[c, h, w]| + sum_{c,h,w} |img[c, h, w+1] - img[c, h, w]|   per image.
+// One CTA per (image, channel) plane: partial sum of the absolute differences, and -- when `grad` is given -- the gradient
+//   d loss / d x = weight * ( sign(x - up) - sign(down - x) + sign(x - left) - sign(right - x) )      (sign(0) = 0, torch's abs backward)
+// ADDED to grad (the gradient already arriving at inputs_bd from the classifier legs), weight = tv_weight / batch.
+__device__ __forceinline__ float sgnf(float v) { return (float)((v > 0.f) - (v < 0.f)); }
+
+__global__ void __launch_bounds__(256) tv_loss_k(const float* __restrict__ x, float* __restrict__ grad, float weight,
+                                                 float* __restrict__ partial, int H, int W) {
+  pdl_entry();
+  const long long base = (long long)blockIdx.x * H * W;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < H * W; i += blockDim.x) {
+    const int r = i / W, c = i - r * W;
+    const float v = x[base + i];
+    float g = 0.f;
+    if (r + 1 < H) { const float d = x[base + i + W] - v; s += fabsf(d); g -= sgnf(d); }
+    if (c + 1 < W) { const float d = x[base + i + 1] - v; s += fabsf(d); g -= sgnf(d); }
+    if (r > 0) g += sgnf(v - x[base + i - W]);
+    if (c > 0) g += sgnf(v - x[base + i - 1]);
+    if (grad) grad[base + i] = fmaf(weight, g, grad[base + i]);
+  }
+  __shared__ float red[8];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f;
+    for (int w = 0; w < 8; ++w) a += red[w];
+    partial[blockIdx.x] = a;
+  }
+}
+
+__global__ void __launch_bounds__(256) tv_final_k(const float* __restrict__ partial, int planes, double scale, float* __restrict__ out) {
+  pdl_entry();
+  double a = 0.0;
+  for (int i = threadIdx.x; i < planes; i += blockDim.x) a += (double)partial[i];
+  __shared__ double red[256];
+  red[threadIdx.x] = a;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = (float)(red[0] * scale);
+}
+
+extern "C" int combat_tv_loss(const float* x, float* grad, float grad_weight, float* partial, float* out, int rows, int C, int H, int W,
+                              void* stream) {
+  COMBAT_ARG(x && partial && out, 0);
+  COMBAT_ARG(rows > 0 && C > 0 && H >= 1 && W >= 1, 5);
+  const int planes = rows * C;
+  pdl_launch(tv_loss_k, planes, 256, 0, (cudaStream_t)stream, x, grad, grad_weight, partial, H, W);
+  COMBAT_CHECK_LAUNCH("tv_loss");
+  pdl_launch(tv_final_k, 1, 256, 0, (cudaStream_t)stream, partial, planes, 1.0 / (double)rows, out);
+  COMBAT_RETURN_LAUNCH("tv_loss");
+}

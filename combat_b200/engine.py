@@ -63,6 +63,7 @@ class StepPlan:
 
 
 TF_SLOT = {"T1": 0, "T3": 1, "T4": 2, "T2": 3, "T5": 4}
+N_LOSSES = 12   # float32 scalars a step leaves on the device (see _ensure_bufs)
 
 
 def _tf_on(opt) -> bool:
@@ -212,6 +213,9 @@ class AlternatedStep:
         if self.multilabel and not self.netG.cond:
             raise ValueError("the multilabel step needs the conditional generator (cond_classes = num_classes)")
         self.keep = int(H * o.ratio)
+        # variant of the step (getattr: the base trainer's opt carries no such attribute): "imperceptible" adds the total-variation
+        # term of train_generator_imperceptible.py to the G-step loss
+        self.tv_weight = float(getattr(o, "tv_weight", 0.0)) if getattr(o, "variant", "") == "imperceptible" else 0.0
         self.tf_on = _tf_on(o)      # PostTensorTransform active (five fused gather launches + two adjoints per iteration)
         self.lr_C = torch.full((1,), float(o.lr_C), dtype=torch.float32, device=self.device)
         self.lr_G = torch.full((1,), float(o.lr_G), dtype=torch.float32, device=self.device)
@@ -306,8 +310,9 @@ class AlternatedStep:
         b["ones"] = torch.ones(B, dtype=torch.int64, device=dev)
         b["sq_partial"] = torch.empty(B * o.input_channel, dtype=torch.float32, device=dev)
         b["gl2_partial"] = torch.empty(2 * B * o.input_channel, dtype=torch.float32, device=dev)
-        b["losses"] = torch.zeros(8, dtype=torch.float32, device=dev)   # loss_c, loss_ce, loss_l2, clean_model_loss, CE of the
-        #                                                                 metric forwards [4:7], loss_grad_l2 [7]
+        b["tv_partial"] = torch.empty(B * o.input_channel, dtype=torch.float32, device=dev)
+        b["losses"] = torch.zeros(N_LOSSES, dtype=torch.float32, device=dev)   # loss_c, loss_ce, loss_l2, clean_model_loss, CE
+        #                                                    of the metric forwards [4:7], loss_grad_l2 [7], loss_tv [8] (imperceptible)
         b["counts"] = torch.zeros(16, dtype=torch.int32, device=dev)
         # ring of pinned host images of the parameter block, each guarded by the event of the copy that last read it
         b["slots"] = []
@@ -478,6 +483,8 @@ class AlternatedStep:
             gsum = ops.post_transform_bwd(g1, b["tf"][TF_SLOT["T4"]])
             ops.post_transform_bwd(g2, b["tf"][TF_SLOT["T5"]], out=gsum, accumulate=True)
             g1, g2 = gsum, None
+        if self.tv_weight:   # train_generator_imperceptible.py:228,235: + tv_weight * total_variation(inputs_bd).mean()
+            ops.tv_loss(x_bd, losses[8:9], grad=g1, grad_weight=self.tv_weight / B, partial=b["tv_partial"])
         dnoise = ops.poison_blend_bwd(x, noise, x_bd, g1, g2, 2.0 * o.L2_weight / numel, o.noise_rate, None,
                                       taps_dev=b["taps_g"], taps_rows=b["taps_rows"])
         dnoise_raw = ops.plane_op(dnoise, "lowfreq", keep=self.keep)                          # P is symmetric
@@ -786,7 +793,7 @@ class AlternatedStep:
         slot = self._rd_slot
         self._rd_slot = slot ^ 1
         if self._rd_bufs is None:
-            self._rd_bufs = [(torch.empty(8, dtype=torch.float32).pin_memory(), torch.empty(16, dtype=torch.int32).pin_memory())
+            self._rd_bufs = [(torch.empty(N_LOSSES, dtype=torch.float32).pin_memory(), torch.empty(16, dtype=torch.int32).pin_memory())
                              for _ in range(2)]
         l, c = self._rd_bufs[slot]
         l.copy_(out["losses"], non_blocking=True)
@@ -798,7 +805,7 @@ class AlternatedStep:
     @staticmethod
     def _to_dict(l, c) -> dict:
         return dict(loss_c=float(l[0]), loss_ce=float(l[1]), loss_l2=float(l[2]), clean_model_loss=float(l[3]),
-                    loss_grad_l2=float(l[7]),
+                    loss_grad_l2=float(l[7]), loss_tv=float(l[8]),
                     n_total_correct=int(c[0]), n_clean_model_correct=int(c[2]), n_clean_correct=int(c[4]),
                     n_bd_correct=int(c[6]), n_clean_model_bd_ba=int(c[8]), n_clean_model_bd_asr=int(c[9]),
                     n_F_correct=int(c[10]))

@@ -214,6 +214,15 @@ def grad_l2(x, x_bd, out, partial=None):
     return out
 
 
+def tv_loss(x, out, grad=None, grad_weight=0.0, partial=None):
+    """total-variation loss of train_generator_imperceptible.py:228 -> out[0]; grad += grad_weight * d(sum TV)/dx when given"""
+    B, Cc, H, W = x.shape
+    if partial is None:
+        partial = torch.empty(B * Cc, dtype=torch.float32, device=x.device)
+    check(lib.combat_tv_loss(_p(x), _p(grad), float(grad_weight), _p(partial), _p(out), B, Cc, H, W, _s()), "tv_loss")
+    return out
+
+
 def sgd_nesterov(p, g, buf, lr_dev, momentum, wd, first):
     check(lib.combat_sgd_nesterov(_p(p), _p(g), _p(buf), p.numel(), _p(lr_dev), momentum, wd, int(first), _s()), "sgd_nesterov")
 

@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import config, ops
-from .engine import AlternatedStep, make_plan
+from .engine import N_LOSSES, AlternatedStep, make_plan
 from .modules import CUnetGeneratorv1, FrequencyModel, PreActResNet18, ResNet18, UnetGenerator  # noqa: F401
 from .networks.models import Denormalizer
 from .utils.dataloader import PostTensorTransform
@@ -82,7 +82,7 @@ def get_model(opt):
 
 
 _HOT_SCALARS = ("noise_rate", "ratio", "L2_weight", "clean_model_weight", "target_label", "attack_mode", "num_classes",
-                "post_transform_option", "random_crop", "random_rotation", "dataset")
+                "post_transform_option", "random_crop", "random_rotation", "dataset", "variant", "tv_weight")
 
 
 def _engine_for(netC, clean_model, netG, netF, opt, multilabel=False):
@@ -145,7 +145,7 @@ def train(netC, optimizerC, schedulerC, netG, optimizerG, schedulerG, netF, clea
     log_every = max(1, int(getattr(opt, "log_every", 50)))
     dev = netC.net.device
     tot = torch.zeros(16, dtype=torch.int64, device=dev)
-    lsum = torch.zeros(8, dtype=torch.float64, device=dev)
+    lsum = torch.zeros(N_LOSSES, dtype=torch.float64, device=dev)
     total_sample = 0
     n_batches = len(train_dl)
     acc = {}
@@ -176,17 +176,20 @@ def train(netC, optimizerC, schedulerC, netG, optimizerG, schedulerG, netF, clea
                        avg_acc_F=c[10] * 100.0 / total_sample, avg_clean_model_acc=c[2] * 100.0 / total_sample,
                        avg_clean_model_bd_ba=c[8] * 100.0 / total_sample, avg_clean_model_bd_asr=c[9] * 100.0 / total_sample,
                        avg_loss_l2=l[2] / total_sample, avg_clean_model_loss=l[3] / total_sample,
-                       avg_loss_grad_l2=l[7] / total_sample)
+                       avg_loss_grad_l2=l[7] / total_sample, avg_loss_tv=l[8] / total_sample)
             print("[%d/%d] Clean Acc: %.4f | Bd Acc: %.4f | F Acc: %.4f | Clean Model Acc: %.4f | Clean Model Bd BA: %.4f | "
                   "Clean Model Bd ASR: %.4f" % (batch_idx + 1, n_batches, acc["avg_acc_clean"], acc["avg_acc_bd"], acc["avg_acc_F"],
                                                acc["avg_clean_model_acc"], acc["avg_clean_model_bd_ba"],
                                                acc["avg_clean_model_bd_asr"]))
     if acc and not epoch % 1:
-        tf_writer.add_scalars("Clean Accuracy", {
+        scalars = {
             "Clean": acc["avg_acc_clean"], "Bd": acc["avg_acc_bd"], "F": acc["avg_acc_F"],
             "CleanModel Acc": acc["avg_clean_model_acc"], "CleanModel Bd BA": acc["avg_clean_model_bd_ba"],
             "CleanModel Bd ASR": acc["avg_clean_model_bd_asr"], "L2 Loss": acc["avg_loss_l2"],
-            "Grad L2 Loss": acc["avg_loss_grad_l2"], "CleanModel Loss": acc["avg_clean_model_loss"]}, epoch)
+            "Grad L2 Loss": acc["avg_loss_grad_l2"], "CleanModel Loss": acc["avg_clean_model_loss"]}
+        if getattr(opt, "variant", "") == "imperceptible":   # train_generator_imperceptible.py:304
+            scalars["TV Loss"] = acc["avg_loss_tv"]
+        tf_writer.add_scalars("Clean Accuracy", scalars, epoch)
     _bind_momentum(optimizerC, netC)
     _bind_momentum(optimizerG, netG)
     for n, b in netC.named_buffers():
@@ -271,8 +274,9 @@ def _dataset_shape(opt):
         raise Exception("Invalid Dataset")
 
 
-def main(argv=None):
-    """train_generator.py:466-609: dataset shape, loaders, get_model, detector / clean-model checkpoints, --continue_training
+def main(argv=None, train_fn=None, eval_fn=None):
+    """(train_fn / eval_fn: the variants -- train_generator_imperceptible.py -- run this driver with their own train / eval)
+    train_generator.py:466-609: dataset shape, loaders, get_model, detector / clean-model checkpoints, --continue_training
     resume, then n_iters epochs of train() + eval().  Build-only flag --synthetic_data replaces the dataset (there is no
     network here for torchvision's download) and makes the two pretrained checkpoints optional; everything else -- paths,
     checkpoint dict keys, prints -- is the reference's."""
@@ -338,9 +342,10 @@ def main(argv=None):
         tf_writer = _NullWriter()
     for epoch in range(epoch_current, opt.n_iters):
         print("Epoch {}:".format(epoch + 1))
-        train(netC, optimizerC, schedulerC, netG, optimizerG, schedulerG, netF, clean_model, train_dl, tf_writer, epoch, opt)
-        bests = list(eval(netC, optimizerC, schedulerC, netG, optimizerG, schedulerG, netF, clean_model, test_dl, *bests,
-                          tf_writer, epoch, opt))
+        (train_fn or train)(netC, optimizerC, schedulerC, netG, optimizerG, schedulerG, netF, clean_model, train_dl, tf_writer,
+                            epoch, opt)
+        bests = list((eval_fn or eval)(netC, optimizerC, schedulerC, netG, optimizerG, schedulerG, netF, clean_model, test_dl, *bests,
+                                       tf_writer, epoch, opt))
     return bests
 
 

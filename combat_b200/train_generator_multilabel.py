@@ -11,7 +11,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from .engine import AlternatedStep, make_plan_multilabel
+from .engine import N_LOSSES, AlternatedStep, make_plan_multilabel
 from .modules import CUnetGeneratorv1, FrequencyModel, PreActResNet18, ResNet18
 from .train_generator import _adopt_momentum, _bind_momentum, _dtype, _engine_for, create_targets_bd, low_freq  # noqa: F401
 from .utils.dataloader import PostTensorTransform
@@ -55,7 +55,7 @@ def train(netC, optimizerC, schedulerC, netG, optimizerG, schedulerG, netF, clea
     log_every = max(1, int(getattr(opt, "log_every", 50)))
     dev = netC.net.device
     tot = torch.zeros(16, dtype=torch.int64, device=dev)
-    lsum = torch.zeros(8, dtype=torch.float64, device=dev)
+    lsum = torch.zeros(N_LOSSES, dtype=torch.float64, device=dev)
     total_sample, n_batches, acc = 0, len(train_dl), {}
     for batch_idx, (inputs, targets) in enumerate(train_dl):
         y_host = targets.cpu().numpy() if torch.is_tensor(targets) else np.asarray(targets)

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import config
-from .engine import AlternatedStep, make_plan_victim
+from .engine import N_LOSSES, AlternatedStep, make_plan_victim
 from .eval import eval_batch
 from .modules import PreActResNet18, ResNet18, UnetGenerator
 from .train_generator import _adopt_momentum, _bind_momentum, _dataset_shape, _dtype, _HOT_SCALARS, create_targets_bd, low_freq  # noqa: F401
@@ -66,7 +66,7 @@ def _train_epoch(netC, optimizerC, schedulerC, netG, train_dl, tf_writer, epoch,
     log_every = max(1, int(getattr(opt, "log_every", 50)))
     dev = netC.net.device
     tot = torch.zeros(16, dtype=torch.int64, device=dev)
-    lsum = torch.zeros(8, dtype=torch.float64, device=dev)
+    lsum = torch.zeros(N_LOSSES, dtype=torch.float64, device=dev)
     total_sample, n_batches = 0, len(train_dl)
     avg_acc_clean = avg_loss_ce = 0.0
     for batch_idx, batch in enumerate(train_dl):

@@ -292,6 +292,11 @@ int combat_adadelta(float* p, const float* g, float* square_avg, float* acc_delt
  * between the vertical / horizontal difference images of F.pad(inputs, (1,1,2,1)) and F.pad(inputs_bd, (1,1,2,1)).
  * partial: rows*C*2 floats of scratch; out: 1 float. */
 int combat_grad_l2(const float* x, const float* x_bd, float* partial, float* out, int rows, int C, int H, int W, void* stream);
+/* total-variation loss of the imperceptible variant (train_generator_imperceptible.py:228; kornia 0.6.6 total_variation, mean
+ * over the batch): out[0] = (1/rows) * sum over images of (sum |x[h+1]-x[h]| + sum |x[w+1]-x[w]|); when `grad` is given,
+ * grad_weight * d(sum)/dx is ADDED to it (float32 NCHW like x; pass tv_weight / rows).  partial: >= rows*C floats of scratch. */
+int combat_tv_loss(const float* x, float* grad, float grad_weight, float* partial, float* out, int rows, int C, int H, int W,
+                   void* stream);
 
 /* ---------------------------------------------------------------- PostTensorTransform (csrc/augment.cu)
  * utils/dataloader.py:45-60: kornia RandomCrop(padding) -> RandomRotation -> RandomHorizontalFlip, as one gather over NCHW

@@ -550,10 +550,19 @@ def default_opt(**kw):
         noise_rate=0.08, target_label=0, pc=0.5, ratio=0.65, kernel_size=3, sigma=(0.1, 1.0),
         L2_weight=0.02, clean_model_weight=0.8, lr_C=1e-2, lr_G=1e-2, classifier="preact_resnet18",
         post_transform_option="no_use", random_crop=5, random_rotation=10, dataset="cifar10",
+        variant="", tv_weight=0.01,   # variant "imperceptible": train_generator_imperceptible.py (+ tv_weight * TV(x_bd).mean())
     )
     for k, v in kw.items():
         setattr(o, k, v)
     return o
+
+
+def total_variation(img: torch.Tensor) -> torch.Tensor:
+    """kornia.losses.total_variation of kornia 0.6.6 (requirements.txt:12; the package is absent here, restated from its published
+    source): per image, the sum over (C, H, W) of |img[.., 1:, :] - img[.., :-1, :]| plus |img[.., :, 1:] - img[.., :, :-1]|."""
+    d1 = img[..., 1:, :] - img[..., :-1, :]
+    d2 = img[..., :, 1:] - img[..., :, :-1]
+    return d1.abs().sum(dim=(-3, -2, -1)) + d2.abs().sum(dim=(-3, -2, -1))
 
 
 def make_bd(netG_p, x, opt, sigma, y=None):
@@ -639,6 +648,10 @@ def alternated_step(state: dict, x: torch.Tensor, y: torch.Tensor, opt, with_met
     clean_model_preds = fwdC(clean_p, clean_b, post_transform(x_bd, opt, tf_log), False)  # :250
     clean_model_loss = F.cross_entropy(clean_model_preds, y)  # :251
     loss = loss_ce + opt.L2_weight * loss_l2 + opt.clean_model_weight * clean_model_loss  # :253
+    if getattr(opt, "variant", "") == "imperceptible":  # train_generator_imperceptible.py:228,235-237
+        loss_tv = total_variation(x_bd).mean()
+        loss = loss + opt.tv_weight * loss_tv
+        out["loss_tv"] = float(loss_tv)
     loss.backward()
     gradsG = {k: v.grad for k, v in netG_p.items()}
     out["gradsG"] = {k: g.clone() for k, g in gradsG.items()}

@@ -31,6 +31,18 @@ def load_reference(ref: str = REF):
         for n in ("RandomCrop", "RandomRotation", "RandomHorizontalFlip"):
             setattr(ka, n, _absent)
         k.augmentation = ka
+        # kornia.losses.total_variation (train_generator_imperceptible.py:13): kornia is absent, so the stand-in is the oracle's
+        # restatement of the kornia 0.6.6 formula -- fixtures of the imperceptible variant pin everything AROUND that formula,
+        # not the formula itself ("parity unpinned w.r.t. kornia")
+        kl = types.ModuleType("kornia.losses")
+
+        def total_variation(img):
+            from oracle.combat_oracle import total_variation as tv
+            return tv(img)
+
+        kl.total_variation = total_variation
+        k.losses = kl
+        sys.modules["kornia.losses"] = kl
         sys.modules["kornia"], sys.modules["kornia.augmentation"] = k, ka
     if "vit_pytorch" not in sys.modules:
         v = types.ModuleType("vit_pytorch")
@@ -58,6 +70,14 @@ def load_reference_multilabel(ref: str = REF):
     import train_generator_multilabel
 
     return train_generator_multilabel
+
+
+def load_reference_imperceptible(ref: str = REF):
+    """train_generator_imperceptible.py of the reference (same stand-ins + kornia.losses.total_variation, see above)."""
+    load_reference(ref)
+    import train_generator_imperceptible
+
+    return train_generator_imperceptible
 
 
 class NullWriter:

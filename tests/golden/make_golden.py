@@ -201,11 +201,16 @@ def param_summary(prefix, before, after, out, full_keys=()):
             out[prefix + "dfull_" + k] = after[k] - before[k]
 
 
-def gen_step(name, B, n_batches, seed):
-    """SURVEY 8c-4 recipe: seed all three RNGs, get_model (netC, clean_model, netG, netF), then data."""
+def gen_step(name, B, n_batches, seed, mod=None):
+    """SURVEY 8c-4 recipe: seed all three RNGs, get_model (netC, clean_model, netG, netF), then data.
+    mod: the reference module whose UNMODIFIED get_model / train run (default train_generator; the imperceptible variant passes
+    train_generator_imperceptible, whose kornia.losses.total_variation is the stand-in of oracle/ref_loader.py)."""
+    import tempfile
+    tg = mod or globals()["tg"]
     opt = get_opt()
     opt.input_height = opt.input_width = 32
     opt.input_channel = 3
+    os.chdir(tempfile.mkdtemp())   # the variant dumps a debugging image every 5 batches into the RELATIVE opt.temps (:280-285)
     seed_all(seed)
     netC, optC, schC, netG, optG, schG, netF, clean = tg.get_model(opt)
     netF.eval()
@@ -364,6 +369,9 @@ if __name__ == "__main__":
     if "step" in which:
         gen_step("step_b128.npz", 128, 1, 0)      # the SURVEY 8c-4 known-answer vector
         gen_step("step_b32x2.npz", 32, 2, 7)      # two iterations: momentum buffers + RNG interleaving
+    if "variants" in which:
+        from oracle.ref_loader import load_reference_imperceptible
+        gen_step("step_imperceptible_b32x2.npz", 32, 2, 11, mod=load_reference_imperceptible())   # + tv_weight * TV(x_bd).mean()
 
 
 def gen_api():

@@ -68,6 +68,47 @@ def test_train_reproduces_the_reference_known_answer_vector(golden):
     assert int(netC.state_dict()["layer1.0.bn1.num_batches_tracked"]) == 1
 
 
+def test_imperceptible_train_reproduces_the_reference_fixture(golden):
+    """train_generator_imperceptible.train() through the public API against two iterations of the UNMODIFIED reference variant
+    (tests/golden/step_imperceptible_b32x2.npz): same RNG stream, per-tensor first-order updates, and the "TV Loss" scalar."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from combat_b200 import train_generator_imperceptible as ti
+    from oracle import combat_oracle as O
+    g = golden("step_imperceptible_b32x2.npz")
+    seed, B, nb = int(g["seed"]), int(g["B"]), int(g["n_batches"])
+    opt = _opt(["--dtype", "fp32", "--no_graph", "--log_every", "1"])
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    random.seed(seed)
+    netC, optC, schC, netG, optG, schG, netF, clean = ti.get_model(opt)
+    batches = [(torch.rand(B, 3, 32, 32) * 2 - 1, torch.randint(0, 10, (B,))) for _ in range(nb)]
+    for i in range(nb):
+        assert np.array_equal(batches[i][1].numpy(), g["y_%d" % i])
+    sd0 = {n: {k: v.detach().clone().cpu() for k, v in m.state_dict().items()} for n, m in (("netC_", netC), ("netG_", netG))}
+    w = _Writer()
+    ti.train(netC, optC, schC, netG, optG, schG, netF, clean, batches, w, 1, opt)
+    torch.cuda.synchronize()
+    sc = w.scalars[0][1]
+    assert "TV Loss" in sc and sc["TV Loss"] > 0
+    vals = g["loss_values"]           # per iteration: ce(C), ce(G), mse, mse, mse, ce(clean)
+    per = len(vals) // nb
+    assert abs(sc["L2 Loss"] * B * nb - (vals[2] + vals[per + 2])) < 1e-4 * (vals[2] + vals[per + 2])
+    # the TV scalar against the oracle's restatement on the fixture's own poisoned images is checked in test_step_gpu; here:
+    # updates after two iterations (the second inherits the first one's noise: 1e-2, as in tests/test_oracle_golden.py)
+    for pre, mod in (("netC_", netC), ("netG_", netG)):
+        sd = mod.state_dict()
+        for n, v0 in sd0[pre].items():
+            if not torch.is_floating_point(v0) or (pre + "dnorm_" + n) not in g.files:
+                continue
+            if pre == "netG_" and n.endswith("bias") and n not in ("conv0_0.bias", "upconv0_0.bias"):
+                continue
+            d = float((sd[n].detach().cpu() - v0).double().norm())
+            ref = g[pre + "dnorm_" + n][0]
+            assert abs(d - ref) <= 3e-2 * ref + 1e-12, (pre, n, d, ref)
+    assert O.total_variation(torch.zeros(1, 3, 4, 4)).shape == (1,)
+
+
 def test_modules_autograd_and_state_dict_roundtrip():
     if not torch.cuda.is_available():
         pytest.skip("needs a GPU")

@@ -619,6 +619,30 @@ def test_conv_tc_fused_batchnorm_backward_reduction(ops, shape):
     assert rel(ps[1], (want_g.double() * xhat.double()).sum((0, 2, 3))) < 1e-4
 
 
+@pytest.mark.parametrize("shape", [(5, 3, 32, 32), (2, 3, 64, 64), (3, 1, 7, 9)])
+def test_tv_loss_fwd_bwd(ops, shape):
+    """total-variation term of train_generator_imperceptible.py:228 (kornia 0.6.6 total_variation(.).mean()): loss and the gradient
+    ADDED to an existing gradient buffer, against torch autograd on the oracle's restatement (ties: sign(0) = 0 on both sides)."""
+    from oracle import combat_oracle as O
+    g = torch.Generator().manual_seed(sum(shape))
+    x = (torch.rand(shape, generator=g) * 2 - 1)
+    x[0, 0, 1, :] = x[0, 0, 0, :]          # exact ties: zero differences
+    xr = x.clone().requires_grad_(True)
+    loss = O.total_variation(xr).mean()
+    w = 0.37
+    (w * loss).backward()
+    g0 = torch.randn(shape, generator=g)
+    gd = dev(g0.clone())
+    out = torch.zeros(1, device="cuda")
+    ops.tv_loss(dev(x), out, grad=gd, grad_weight=w / shape[0])
+    torch.cuda.synchronize()
+    assert abs(float(out) - float(loss)) < 2e-6 * abs(float(loss))
+    assert rel(gd, g0 + xr.grad) < 1e-6
+    out2 = torch.zeros(1, device="cuda")
+    ops.tv_loss(dev(x), out2)              # loss only
+    assert float(out2) == float(out)
+
+
 @pytest.mark.parametrize("N,H,act", [(5, 32, 1), (300, 32, 0), (7, 16, 1), (3, 64, 0)])
 def test_conv_tc_cout3(ops, N, H, act):
     """64 -> 3 conv on the tensor pipe (conv_tc_cout3_kernel): the generator's last conv (bias + tanh, networks/models.py:316,341)

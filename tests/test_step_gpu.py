@@ -68,17 +68,20 @@ def net_delta(before, after_ref, sd_dev, skip_dead=False):
     return (num / den) ** 0.5, dot / (den ** 0.5 * nd ** 0.5)
 
 
+@pytest.mark.parametrize("variant", ["", "imperceptible"])
 @pytest.mark.parametrize("name,dtype", [("fp32", torch.float32), ("bf16", torch.bfloat16)])
-def test_two_iterations_vs_oracle(name, dtype):
+def test_two_iterations_vs_oracle(name, dtype, variant):
+    """variant "imperceptible": the step of train_generator_imperceptible.py (+ tv_weight * total_variation(x_bd).mean())."""
     if not torch.cuda.is_available():
         pytest.skip("needs a GPU")
     from combat_b200.engine import AlternatedStep, make_plan
     B = 32
     state = seeded_state(21)
-    eng = make_engine(state, dtype)
+    opt = O.default_opt(variant=variant)
+    eng = make_engine(state, dtype, opt=opt)
+    assert (eng.tv_weight > 0) == (variant == "imperceptible")
     before = {k: {n: v.clone() for n, v in state[k].items()} for k in ("netC_p", "netG_p")}
     batches = [(torch.rand(B, 3, 32, 32) * 2 - 1, torch.randint(0, 10, (B,))) for _ in range(2)]
-    opt = O.default_opt()
     np.random.seed(5)
     torch.manual_seed(5)
     refs = [O.alternated_step(state, x, y, opt) for x, y in batches]
@@ -108,7 +111,7 @@ def test_two_iterations_vs_oracle(name, dtype):
                       "pred_clean"):
                 assert rel2(d[k], r[k]) < 5e-2, (it, k, rel2(d[k], r[k]))
             ltol = 1e-2
-        for k in ("loss_c", "loss_ce", "loss_l2", "clean_model_loss"):
+        for k in ("loss_c", "loss_ce", "loss_l2", "clean_model_loss") + (("loss_tv",) if variant else ()):
             assert abs(s[k] - r[k]) < ltol * max(1.0, abs(r[k])), (it, k, s[k], r[k])
         if fp32 and it == 0:
             for k in ("n_clean_correct", "n_bd_correct", "n_clean_model_correct", "n_clean_model_bd_ba",
