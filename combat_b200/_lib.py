@@ -38,7 +38,7 @@ class ConvTcDesc(C.Structure):
                 ("act", i32), ("post_scale", vp), ("post_shift", vp),
                 ("out2", vp), ("scale2", vp), ("shift2", vp), ("mask", vp), ("mask_scale", vp), ("post_add", vp),
                 ("in2", vp), ("w2", vp),
-                ("bnb_x", vp), ("bnb_scale", vp), ("bnb_shift", vp), ("bnb_mean", vp), ("bnb_invstd", vp)]
+                ("bnb_x", vp), ("bnb_scale", vp), ("bnb_shift", vp), ("bnb_mean", vp), ("bnb_invstd", vp), ("in_nchw3", i32)]
 
 
 P = C.POINTER

@@ -16,6 +16,8 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -245,6 +247,11 @@ struct TcParams {
   // every weight tile; rr_rounds full rounds of gridDim.x items, then rr_rem items -- split into single tiles when they fit
   int rr_rounds, rr_rem, rr_split;
   int n_epf;              // number of epilogue-input tensors to prefetch (maps.e[0 .. n_epf)), 0: off
+  const float* img;       // conv_tc_first_kernel: the float32 NCHW [N,3,H,W] input image
+  // tile decode without integer division (measured: decode + addressing of the epilogue = 950 cycles per tile per warp with the
+  // hardware-emulated `/` and `%` by run-time values): q = umulhi(x, m), m = floor(2^32 / d) + 1, exact while x * d < 2^32
+  // (checked on the host); m = 0 encodes d = 1
+  uint32_t m_co, m_w, m_h, m_n, m_ppc;
   void* out;             // bf16 or float32 (out_f32)
   const void* residual;  // bf16 or float32 (res_f32)
   const float* bias;
@@ -288,32 +295,37 @@ struct TcCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + TC_EPI_WARPS * 32 * EPI_ROWB /*epilogue*/;
 };
 
+__device__ __forceinline__ uint32_t fdiv(uint32_t x, uint32_t m) { return m ? __umulhi(x, m) : x; }
+
 __device__ __forceinline__ void decode_tile(const TcParams& p, int tile, int& cls, int& nt, int& ht, int& wt, int& cot) {
   if (p.pair_mode) {
-    const int rank = tile & 1, q = tile >> 1;
-    cot = q % p.tiles_co;
-    const int pp = q / p.tiles_co;
-    cls = pp / p.pairs_per_class;
-    const int px = 2 * (pp - cls * p.pairs_per_class) + rank;
-    if (px >= p.px_tiles_per_class) {  // odd tile count: the pair's second half is all padding (TMA zero fill, no stores)
+    const uint32_t rank = tile & 1, q = (uint32_t)tile >> 1;
+    const uint32_t pp = fdiv(q, p.m_co);
+    cot = q - pp * p.tiles_co;
+    const uint32_t c = fdiv(pp, p.m_ppc);
+    cls = c;
+    const uint32_t px = 2 * (pp - c * p.pairs_per_class) + rank;
+    if ((int)px >= p.px_tiles_per_class) {  // odd tile count: the pair's second half is all padding (TMA zero fill, no stores)
       nt = p.tiles_n;
       ht = wt = 0;
       return;
     }
-    wt = px % p.tiles_w;
-    const int r2 = px / p.tiles_w;
-    ht = r2 % p.tiles_h;
-    nt = r2 / p.tiles_h;
+    const uint32_t r2 = fdiv(px, p.m_w);
+    wt = px - r2 * p.tiles_w;
+    const uint32_t r3 = fdiv(r2, p.m_h);
+    ht = r2 - r3 * p.tiles_h;
+    nt = r3;
     return;
   }
-  cot = tile % p.tiles_co;
-  int r = tile / p.tiles_co;
-  wt = r % p.tiles_w;
-  r /= p.tiles_w;
-  ht = r % p.tiles_h;
-  r /= p.tiles_h;
-  nt = r % p.tiles_n;
-  cls = r / p.tiles_n;
+  uint32_t r = fdiv((uint32_t)tile, p.m_co);
+  cot = tile - r * p.tiles_co;
+  uint32_t r1 = fdiv(r, p.m_w);
+  wt = r - r1 * p.tiles_w;
+  uint32_t r2 = fdiv(r1, p.m_h);
+  ht = r1 - r2 * p.tiles_h;
+  uint32_t r3 = fdiv(r2, p.m_n);
+  nt = r2 - r3 * p.tiles_n;
+  cls = r3;
 }
 
 // k-th pixel tile of this CTA, its accumulator buffer and the parity of that buffer's barriers.  GROUP == 1: tiles blockIdx.x +
@@ -375,9 +387,14 @@ __device__ __forceinline__ bool rr_item(const TcParams& p, int i, int& st, int& 
 // MODE 1: out = bf16( mask > 0 ? (acc + residual) * mask_scale : 0 ) + post_add     (residual XOR post_add, both bf16)
 // MODE 3: out = bf16 g, g = (x * scale + shift > 0) ? acc : 0, + per-(CTA, row quarter) partial sums of g and g * (x - mean) * invstd
 //         (the reduction of a train-mode BatchNorm+ReLU backward; x = the saved bf16 pre-normalisation tensor)
-template <int BLOCK_N, int MODE, bool PAIR = false, int GROUP = 1>
+struct NoTileHook {
+  __device__ __forceinline__ void operator()(int) const {}
+};
+// hook(k): called by every epilogue warp at the top of iteration k, before the wait on accumulator k (conv_tc_first_kernel builds
+// the A operand of tile k + 1 there)
+template <int BLOCK_N, int MODE, bool PAIR = false, int GROUP = 1, typename Hook = NoTileHook>
 __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* stg_base, uint32_t tmem_base, uint64_t* tfull_bar,
-                                            uint64_t* tempty_bar, int warp, int lane) {
+                                            uint64_t* tempty_bar, int warp, int lane, Hook hook = Hook()) {
   // PAIR: the accumulator-empty barriers live in the pair's leader CTA (its MMA thread waits for the epilogue warps of BOTH CTAs)
   uint32_t tempty_leader[2] = {0, 0};
   if (PAIR) {
@@ -444,7 +461,27 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* stg_base
     t.has_acc = p.taps.ntaps[cls] > 0;
     t.col0 = cot * BLOCK_N + half * (BLOCK_N / 2) + cseg * 4;  // this lane's first channel of chunk 0
     t.okmask = 0;
+    const uint32_t cp = p.taps.cls_p[cls], cq = p.taps.cls_q[cls];
     // the 8 rows this lane owns in the coalesced phase: row = quarter*32 + 4*i + sub
+    if (p.BW >= 32) {
+      // 32 | BW: the warp's 32 pixels are one run inside ONE image row -- one address, then a constant stride (the general
+      // loop below costs ~530 cycles per tile per warp, which is exposed whenever the epilogue is the bound)
+      const int row0 = quarter * 32 + sub;
+      const int wi0 = row0 & (p.BW - 1);
+      const int r2 = row0 >> p.lbw;
+      const int hi = r2 & (p.BH - 1);
+      const int ni = r2 >> p.lbh;
+      const int n = nt * p.BNI + ni, a = ht * p.BH + hi, b0 = wt * p.BW + wi0;
+      const bool vrow = n < p.N && a < p.Hc;
+      const uint32_t oh = a * p.out_scale + cp, ow0 = b0 * p.out_scale + cq;
+      const uint32_t o0 = (((uint32_t)n * (uint32_t)p.out_H + oh) * (uint32_t)p.out_W + ow0) * (uint32_t)p.Co + (uint32_t)t.col0;
+      const uint32_t step = 4u * (uint32_t)p.out_scale * (uint32_t)p.Co;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        t.ob[i] = o0 + i * step;
+        t.okmask |= ((vrow && b0 + 4 * i < p.Wc) ? 1u : 0u) << i;
+      }
+    } else
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int row = quarter * 32 + 4 * i + sub;
@@ -454,8 +491,10 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* stg_base
       const int ni = r2 >> p.lbh;
       const int n = nt * p.BNI + ni, a = ht * p.BH + hi, b = wt * p.BW + wi;
       const bool valid = n < p.N && a < p.Hc && b < p.Wc;
-      const int oh = a * p.out_scale + p.taps.cls_p[cls], ow = b * p.out_scale + p.taps.cls_q[cls];
-      t.ob[i] = (uint32_t)((((long long)n * p.out_H + oh) * p.out_W + ow) * p.Co + t.col0);
+      const uint32_t oh = a * p.out_scale + cp, ow = b * p.out_scale + cq;
+      // element offset < 2^32 (checked on the host): modular 32-bit arithmetic gives it directly (rows outside the tensor are
+      // masked, their value is irrelevant)
+      t.ob[i] = (((uint32_t)n * (uint32_t)p.out_H + oh) * (uint32_t)p.out_W + ow) * (uint32_t)p.Co + (uint32_t)t.col0;
       t.okmask |= (valid ? 1u : 0u) << i;
     }
     // Unconditional loads (rows outside the tensor read element 0 and are discarded at the store): a predicated load
@@ -478,6 +517,8 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* stg_base
   if (AHEAD && tile_seq<GROUP>(p, 0, tile, acc, acc_phase)) prepare(tile, cur);
   for (int k = 0; tile_seq<GROUP>(p, k, tile, acc, acc_phase); ++k) {
     if (GROUP == 1) { acc = acc_run; acc_phase = phase_run; }
+    hook(k);
+    const long long tp0 = (p.dbg && warp == 2 && lane == 0) ? clock64() : 0;
     const bool more = AHEAD && tile_seq<GROUP>(p, k + 1, tile_n, acc_n, phase_n);
     if (AHEAD) {
       if (more) prepare(tile_n, nxt);
@@ -492,6 +533,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* stg_base
     float4 pr_pipe[2][8];
     const bool dbg_w = p.dbg && warp == 2 && lane == 0;
     const long long te0 = dbg_w ? clock64() : 0;
+    if (dbg_w && p.img) p.dbg[blockIdx.x * 8 + 3] += te0 - tp0;   // (first-conv kernel only: slot 3 is free there) addressing / prefetch
     if (has_acc) {
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -1346,6 +1388,23 @@ static void pick_box(int Hc, int Wc, int pixels, int* BW, int* BH, int* BNI) {
 
 static int floordiv2(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }
 
+// multiplier of the division-free tile decode (fdiv); 0 encodes d == 1
+static uint32_t fdiv_magic(int d) { return d <= 1 ? 0u : (uint32_t)((1ull << 32) / (unsigned long long)d + 1ull); }
+// fills the multipliers; false if the exactness condition x * d < 2^32 could fail for this problem
+static bool set_fdiv(TcParams& p) {
+  p.m_co = fdiv_magic(p.tiles_co);
+  p.m_w = fdiv_magic(p.tiles_w);
+  p.m_h = fdiv_magic(p.tiles_h);
+  p.m_n = fdiv_magic(p.tiles_n);
+  p.m_ppc = fdiv_magic(p.pairs_per_class);
+  long long dmax = p.tiles_co;
+  if (p.tiles_w > dmax) dmax = p.tiles_w;
+  if (p.tiles_h > dmax) dmax = p.tiles_h;
+  if (p.tiles_n > dmax) dmax = p.tiles_n;
+  if (p.pairs_per_class > dmax) dmax = p.pairs_per_class;
+  return (long long)(p.total_tiles > 0 ? p.total_tiles : 1) * dmax < (1LL << 32);
+}
+
 extern "C" int combat_conv_tc_supported(const combat_conv_tc_desc* d) {
   if (!d) return 0;
   if (d->Ci % 64 || d->Co % 64) return 0;
@@ -1396,6 +1455,9 @@ static int max_pair_clusters() {
 static int g_last_grid = 0;
 extern "C" int combat_conv_tc_last_grid(void) { return g_last_grid; }
 
+template <int MODE>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_first_kernel(const __grid_constant__ TcMaps maps, const TcParams p);  // below
+
 extern "C" int combat_conv_tc(const combat_conv_tc_desc* d, void* stream) {
   COMBAT_ARG(d && d->in && d->w && (d->out || d->out2), 0);
   COMBAT_ARG(combat_conv_tc_supported(d), 0);
@@ -1445,6 +1507,45 @@ extern "C" int combat_conv_tc(const combat_conv_tc_desc* d, void* stream) {
   }
   p.dbg = (getenv("COMBAT_TC_DBG") && !d->bnb_x) ? (long long*)d->stats : nullptr;
   p.stats = p.dbg ? nullptr : d->stats;
+  if (d->in_nchw3) {
+    // first conv: float32 NCHW image, operand built in shared memory by the epilogue warps (conv_tc_first_kernel)
+    COMBAT_ARG(d->Co == 64 && d->Ci == 64 && KH == 3 && pad == 1 && d->stride == 1 && d->up == 1 && d->Ho == d->Hi && d->Wo == d->Wi, 0);
+    COMBAT_ARG(!d->mask && !d->residual && !d->in2 && !bnb && !d->post_add, 0);
+    p.n_classes = 1;
+    p.out_scale = 1;
+    p.Hc = d->Ho;
+    p.Wc = d->Wo;
+    pick_box(p.Hc, p.Wc, TILE_M, &p.BW, &p.BH, &p.BNI);
+    COMBAT_ARG(p.BW == d->Wo && p.BNI == 1, 0);   // tiles of whole image rows (W a power of two <= 128)
+    p.taps.ntaps[0] = 1;
+    p.tiles_co = 1;
+    p.tiles_w = 1;
+    p.tiles_h = cdiv(p.Hc, p.BH);
+    p.tiles_n = d->N;
+    p.total_tiles = p.tiles_h * p.tiles_n;
+    while ((1 << p.lbw) < p.BW) ++p.lbw;
+    while ((1 << p.lbh) < p.BH) ++p.lbh;
+    p.img = (const float*)d->in;
+    COMBAT_ARG(set_fdiv(p), 0);
+    int rc1 = make_w_map(&maps.w, d->w, 64, 1, 64, 64);
+    if (rc1) return rc1;
+    const int grid1 = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+    g_last_grid = grid1;
+    cudaStream_t st1 = (cudaStream_t)stream;
+    if (p.stats) {
+      cudaMemsetAsync(p.stats, 0, (size_t)grid1 * 4 * 2 * d->Co * sizeof(float), st1);
+      g_last_grid = grid1 * 4;
+    }
+    const int smem1 = 8192 + 2 * 16384 + 256 + TC_EPI_WARPS * 32 * EPI_ROWB + 1024;
+    if (p.stats) {
+      cudaFuncSetAttribute(conv_tc_first_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
+      pdl_launch(conv_tc_first_kernel<2>, grid1, TC_THREADS, smem1, st1, maps, p);
+    } else {
+      cudaFuncSetAttribute(conv_tc_first_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
+      pdl_launch(conv_tc_first_kernel<0>, grid1, TC_THREADS, smem1, st1, maps, p);
+    }
+    COMBAT_RETURN_LAUNCH("conv_tc_first");
+  }
   // 256-wide tiles for the deep layers: per MMA the 128-row A operand is read once for 256 instead of 128 output channels
   // (the shared-memory operand path is what bounds the 128-wide kernel); they need K large enough to hide the epilogue
   const bool wide = d->Co % 256 == 0 && d->Ci * d->KH * d->KW >= 1152 && !getenv("COMBAT_NO_BN256");
@@ -1618,6 +1719,7 @@ extern "C" int combat_conv_tc(const combat_conv_tc_desc* d, void* stream) {
     p.rr_split = p.rr_rem > 0 && 2 * p.rr_rem <= grid;
   }
   g_last_grid = grid;
+  COMBAT_ARG(set_fdiv(p), 0);
   COMBAT_ARG(!p.stats || (d->Co <= 512 && !d->mask), 0);
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH_P(BN, MD)                                                                                                        \
@@ -1681,6 +1783,175 @@ extern "C" int combat_conv_tc(const combat_conv_tc_desc* d, void* stream) {
 #undef LAUNCH_C
 #undef LAUNCH_P
   COMBAT_RETURN_LAUNCH("conv_tc");
+}
+
+// ---------------------------------------------------------------------------------------------- 3 -> 64 channels, 3x3, stride 1
+// The first conv of the classifiers / the detector (preact_resnet.py:77, resnet.py:73, model.py:12) read a float32 NCHW image:
+// K = 27 cannot be fetched by TMA as a K-major operand, and on CUDA cores the layer was FP32-FMA bound (conv_cin3_k: 115 us for a
+// 1024 x 32 x 32 batch, 6 % of the step).  Here the eight epilogue warps BUILD the A operand in shared memory -- 128 pixels x 64
+// bf16 columns [hi(27) | 0 | lo(27) | 0] with hi = bf16(x), lo = bf16(x - hi) (the image enters with ~16 mantissa bits; the filter
+// is stored twice, NetBase._w64_for) in the SWIZZLE_128B K-major layout TMA would have produced (16-byte chunk index XOR row & 7),
+// publish it to the async proxy (fence.proxy.async + mbarrier) and the MMA warp issues four N = 64 MMAs per tile.  Each warp builds
+// the operand of tile k + 1 and then runs the ordinary epilogue (all modes: fused eval BatchNorm+ReLU second output, train-mode
+// statistics, ELU + affine of the detector) of tile k, so the kernel is bound by its output stream.
+template <int MODE>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_first_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
+  pdl_launch_dependents();
+  const long long dbg_c0 = p.dbg ? clock64() : 0, dbg_g0 = p.dbg ? globaltimer_ns() : 0;  // whole-kernel cycles / ns of this CTA
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* wsm = smem;                 // [64 co][64 k] bf16, SWIZZLE_128B: 8 KB
+  uint8_t* abuf = smem + 8192;         // 2 x [128 pixels][64 k] bf16: 2 x 16 KB
+  uint8_t* tail = abuf + 2 * 16384;
+  uint64_t* bars = (uint64_t*)tail;
+  uint64_t* a_full = bars;             // 2: one arrive per building warp
+  uint64_t* a_empty = bars + 2;        // 2: MMA commit
+  uint64_t* tfull_bar = bars + 4;
+  uint64_t* tempty_bar = bars + 6;
+  uint64_t* w_bar = bars + 8;
+  uint32_t* tmem_ptr_smem = (uint32_t*)(bars + 9);
+  const int warp = uniform_i(threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.w);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&a_full[s], TC_EPI_WARPS);
+      mbar_init(&a_empty[s], 1);
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], TC_EPI_WARPS);
+    }
+    mbar_init(w_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_smem, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = uniform_u(*tmem_ptr_smem);
+  pdl_wait();
+
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      mbar_expect_tx(w_bar, 8192);
+      tma_load_3d(wsm, &maps.w, w_bar, 0, 0, 0);
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc(TILE_M, 64, 0, 0);
+    mbar_wait(w_bar, 0);
+    const uint32_t wbase = smem_u32(wsm), abase = smem_u32(abuf);
+    int k = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++k) {
+      const int s = k & 1;
+      const uint32_t ph = (k >> 1) & 1;
+      mbar_wait(&tempty_bar[s], ph ^ 1);
+      mbar_wait(&a_full[s], ph);
+      tc_fence_after();
+      const uint64_t adesc = make_smem_desc(abase + s * 16384, 16, 1024);
+      const uint64_t bdesc = make_smem_desc(wbase, 16, 1024);
+      if (elect_one_sync()) {
+#pragma unroll
+        for (int kk = 0; kk < KCHUNK / 16; ++kk) umma_bf16(tmem_base + s * 64, adesc + 2 * kk, bdesc + 2 * kk, idesc, kk != 0);
+        umma_commit(&a_empty[s]);
+        umma_commit(&tfull_bar[s]);
+      }
+    }
+  } else {
+    // builder of tile index kb (0-based position in this CTA's tile sequence): thread -> (pixel row, K half).  Warps 2..5 build
+    // k = 0..15, warps 6..9 k = 16..31 (k = tap * 3 + ci < 27, zero above) of BOTH the hi and the lo columns: every image value
+    // is loaded once; taps and channels are compile-time constants inside each branch.
+    const int eidx = (warp - 2) * 32 + lane;
+    const int row = eidx & 127;
+    const int khalf = uniform_i(eidx >> 7);
+    const int hi_r = row >> p.lbw, wi = row & (p.BW - 1);
+    const long long HW = (long long)p.Hc * p.Wc;
+    auto build = [&](int kb) {
+      const int tile = blockIdx.x + kb * gridDim.x;
+      if (tile >= p.total_tiles) return;
+      const int s = kb & 1;
+      const bool dbg_b = p.dbg && warp == 2 && lane == 0;
+      const long long tb0 = dbg_b ? clock64() : 0;
+      mbar_wait(&a_empty[s], ((kb >> 1) & 1) ^ 1);
+      const long long tb1 = dbg_b ? clock64() : 0;
+      const int ht = tile % p.tiles_h, n = tile / p.tiles_h;
+      const int h = ht * p.BH + hi_r;
+      // UNCONDITIONAL loads from clamped coordinates, zeroed afterwards: a predicated load into a pre-zeroed register is compiled to
+      // "load, wait, select" per value and serialises the whole batch (first version: ~3000 cycles per tile in this lambda)
+      const float* xn = p.img + (long long)n * 3 * HW;
+      int roff[3], coff[3];
+      bool vh[3], vw[3];
+#pragma unroll
+      for (int dd = 0; dd < 3; ++dd) {
+        const int ih = h + dd - 1, iw = wi + dd - 1;
+        vh[dd] = ih >= 0 && ih < p.Hc;
+        vw[dd] = iw >= 0 && iw < p.Wc;
+        roff[dd] = min(max(ih, 0), p.Hc - 1) * p.Wc;
+        coff[dd] = min(max(iw, 0), p.Wc - 1);
+      }
+      uint32_t hi_pk[8], lo_pk[8];
+      auto gather = [&](auto KH) {
+        constexpr int K0 = decltype(KH)::value * 16;
+        float raw[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int kq = K0 + j;
+          if (kq < 27) {
+            const int tap = kq / 3, ci = kq - tap * 3, dh = tap / 3, dw = tap - dh * 3;
+            raw[j] = __ldg(xn + ci * HW + roff[dh] + coff[dw]);
+          } else {
+            raw[j] = 0.f;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float v2[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int kq = K0 + 2 * q + e;
+            float v = 0.f;
+            if (kq < 27) {
+              const int tap = kq / 3, dh = tap / 3, dw = tap - dh * 3;
+              v = (vh[dh] && vw[dw]) ? raw[2 * q + e] : 0.f;
+            }
+            v2[e] = v;
+          }
+          const __nv_bfloat162 hv = __floats2bfloat162_rn(v2[0], v2[1]);
+          const float2 hf = __bfloat1622float2(hv);
+          const __nv_bfloat162 lv = __floats2bfloat162_rn(v2[0] - hf.x, v2[1] - hf.y);
+          hi_pk[q] = *(const uint32_t*)&hv;
+          lo_pk[q] = *(const uint32_t*)&lv;
+        }
+      };
+      if (khalf == 0) gather(std::integral_constant<int, 0>());
+      else gather(std::integral_constant<int, 1>());
+      const long long tb2 = dbg_b ? clock64() : 0;
+      const uint32_t dst = smem_u32(abuf + s * 16384) + row * 128;
+      const int sw = row & 7;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        sts128(dst + (((2 * khalf + c) ^ sw) << 4), hi_pk[4 * c], hi_pk[4 * c + 1], hi_pk[4 * c + 2], hi_pk[4 * c + 3]);
+        sts128(dst + (((4 + 2 * khalf + c) ^ sw) << 4), lo_pk[4 * c], lo_pk[4 * c + 1], lo_pk[4 * c + 2], lo_pk[4 * c + 3]);
+      }
+      fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_full[s]);
+      if (dbg_b) {   // builder: wait for the free operand buffer | gather + split | store + publish
+        p.dbg[blockIdx.x * 8 + 0] += tb1 - tb0;
+        p.dbg[blockIdx.x * 8 + 1] += tb2 - tb1;
+        p.dbg[blockIdx.x * 8 + 2] += clock64() - tb2;
+      }
+    };
+    build(0);
+    tc_epilogue<64, MODE>(p, tail + 256, tmem_base, tfull_bar, tempty_bar, warp, lane, [&](int k) { build(k + 1); });
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (p.dbg && threadIdx.x == 0) {
+    p.dbg[blockIdx.x * 8 + 6] += clock64() - dbg_c0;
+    p.dbg[blockIdx.x * 8 + 7] += globaltimer_ns() - dbg_g0;
+  }
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 128);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- 64 -> 3 channels, 3x3, stride 1

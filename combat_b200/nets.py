@@ -161,6 +161,8 @@ class NetBase:
         self.fuse_bn_bwd_reduce = not os.environ.get("COMBAT_NO_FUSE_BNB")
         # 64 -> 3 convs (generator output, input gradient of the classifiers' first conv) on the tensor pipe
         self.tc_cout3 = not os.environ.get("COMBAT_NO_TC_COUT3")
+        # 3 -> 64 first convs (stride 1) on the tensor pipe, operand built in shared memory from the float32 NCHW image
+        self.tc_first2 = not os.environ.get("COMBAT_NO_TC_FIRST2")
         self._w64 = {}
         self.last_stats_nblk = 0
         self.convs: dict[str, ConvSpec] = {}
@@ -361,6 +363,19 @@ class NetBase:
         if out is None:
             out = torch.empty((N, Ho, Wo, Ct), dtype=self.pre_dtype if pre else self.dtype, device=self.device)
         self.last_stats_nblk = 0
+        if (self.tc_first2 and self.use_tc and Cc == 3 and cs.k == 3 and cs.pad == 1 and cs.stride == 1 and Ct == cs.Cout == 64
+                and W in (16, 32, 64, 128) and H * W >= 128):
+            # tensor pipe: the epilogue warps build the [hi | lo] im2col operand in shared memory (conv_tc_first_kernel)
+            out2 = torch.empty((N, Ho, Wo, Ct), dtype=self.dtype, device=self.device) if bn_relu is not None else None
+            want_stats = stats and pre
+            d = ops.conv_tc_desc(x_nchw, self._w64_for(cs).data_ptr(), out, N, H, W, 64, Ho, Wo, 64, 3, 3, 1, 1, 1, bias=self._bias(cs),
+                                 out2=out2, scale2=bn_relu[0] if bn_relu is not None else None,
+                                 shift2=bn_relu[1] if bn_relu is not None else None,
+                                 stats=ops.Scratch.get(self.device) if want_stats else None, in_nchw3=True)
+            _tc_launch(lambda: lib.combat_conv_tc(C.byref(d), ops._s()), "conv_tc", 2.0 * N * Ho * Wo * 64 * 27,
+                       "N%d %dx%d 3->64 k3 s1 first%s" % (N, H, W, " +bn" if bn_relu is not None else (" +stats" if want_stats else "")))
+            self.last_stats_nblk = lib.combat_conv_tc_last_grid() if want_stats else 0
+            return (out, out2) if bn_relu is not None else out
         if Ct == cs.Cout and self._use_im2col(cs, cs.Cout, Cc):
             out2 = torch.empty((N, Ho, Wo, Ct), dtype=self.dtype, device=self.device) if bn_relu is not None else None
             self.cin3_tc(x_nchw, self._w64_for(cs), cs.Cout, cs.stride, out, bias=self._bias(cs), out2=out2, bn_relu=bn_relu,

@@ -316,10 +316,11 @@ def wgrad_cout3(a_nhwc, dz_nchw, dw, db):
 
 def conv_tc_desc(x, w_ptr, out, N, Hi, Wi, Ci, Ho, Wo, Co, KH, KW, stride, pad, up, bias=None, residual=None, stats=None,
                  act=0, post_scale=None, post_shift=None, out2=None, scale2=None, shift2=None, mask=None, mask_scale=None,
-                 post_add=None, in2=None, w2=None, bnb=None):
+                 post_add=None, in2=None, w2=None, bnb=None, in_nchw3=False):
     """bnb = (x, scale, shift, mean, invstd): fused reduction of a train-mode relu(bn(x)) backward (needs `stats`)."""
     d = ConvTcDesc()
     d.in2, d.w2 = _p(in2), w2
+    d.in_nchw3 = int(in_nchw3)
     if bnb is not None:
         d.bnb_x, d.bnb_scale, d.bnb_shift, d.bnb_mean, d.bnb_invstd = (_p(t) for t in bnb)
     d.act, d.post_scale, d.post_shift = act, _p(post_scale), _p(post_shift)

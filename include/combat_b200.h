@@ -197,6 +197,11 @@ typedef struct {
   const float* bnb_shift;
   const float* bnb_mean;
   const float* bnb_invstd;
+  /* 1: FIRST conv of a classifier / the detector (preact_resnet.py:77, resnet.py:73, model.py:12; 3 -> 64 channels, 3x3, stride 1,
+   * pad 1): `in` is the float32 NCHW image [N,3,Hi,Wi] and `w` the filter as [64][64] bf16 = [27 taps x ci | 5 zeros | the same 27
+   * again | 5 zeros] (the kernel splits the image into bf16 hi + lo halves, so it enters with ~16 mantissa bits); Ci must be
+   * given as 64.  Forward epilogue features only (bias, act, post affine, out2, stats).  Needs Wi a power of two <= 128. */
+  int in_nchw3;
 } combat_conv_tc_desc;
 int combat_conv_tc(const combat_conv_tc_desc* d_host, void* stream);
 int combat_conv_tc_wgrad(const combat_conv_tc_desc* d_host, const void* dy, float* dw_ohwi, void* stream);

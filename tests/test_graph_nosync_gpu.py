@@ -35,7 +35,8 @@ def _run(sync_each, K, B, tf="no_use", multilabel=False):
     for i in range(2):              # eager warm-up + capture
         eng.step(xs[i], ys[i], use_graph=True)
     torch.cuda.synchronize()
-    losses = torch.zeros((K, 8), dtype=torch.float32, device="cuda")
+    from combat_b200.engine import N_LOSSES
+    losses = torch.zeros((K, N_LOSSES), dtype=torch.float32, device="cuda")
     counts = torch.zeros((K, 16), dtype=torch.int32, device="cuda")
     plan_log = []   # the device parameter block as each iteration's kernels saw it (stream-ordered device-to-device copy)
     plans = []

@@ -619,6 +619,45 @@ def test_conv_tc_fused_batchnorm_backward_reduction(ops, shape):
     assert rel(ps[1], (want_g.double() * xhat.double()).sum((0, 2, 3))) < 1e-4
 
 
+@pytest.mark.parametrize("N,H", [(5, 32), (300, 32), (3, 16), (2, 64)])
+def test_conv_tc_first(ops, N, H):
+    """3 -> 64 first conv on the tensor pipe (conv_tc_first_kernel): float32 NCHW image split into bf16 hi + lo halves by the
+    kernel, operand built in shared memory, filter [64][27 | 0 | 27 | 0]; forward epilogue features (second output with the fused
+    eval BatchNorm+ReLU, train-mode statistics).  Only the bf16 rounding of the FILTER separates it from float32 torch."""
+    import ctypes as C
+
+    from combat_b200._lib import check, lib
+    g = torch.Generator().manual_seed(70 + N + H)
+    x = torch.randn(N, 3, H, H, generator=g) * 1.5
+    w = (torch.randn(64, 3, 3, 3, generator=g) * 0.2).bfloat16().float()
+    y = F.conv2d(x, w, None, 1, 1)
+    sc, sh = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.3
+    y2 = F.relu(y * sc[None, :, None, None] + sh[None, :, None, None])
+    w64 = torch.zeros(64, 64, dtype=torch.bfloat16)
+    w64[:, :27] = w.permute(0, 2, 3, 1).reshape(64, 27).bfloat16()
+    w64[:, 32:59] = w64[:, :27]
+    w64 = dev(w64)
+    xd = dev(x)
+    out = torch.full((N, H, H, 64), 7.0, device="cuda")
+    out2 = torch.zeros(N, H, H, 64, device="cuda", dtype=torch.bfloat16)
+    d = ops.conv_tc_desc(xd, w64.data_ptr(), out, N, H, H, 64, H, H, 64, 3, 3, 1, 1, 1, out2=out2, scale2=dev(sc), shift2=dev(sh),
+                         in_nchw3=True)
+    check(lib.combat_conv_tc(C.byref(d), ops._s()), "conv_tc first")
+    torch.cuda.synchronize()
+    assert rel(out.permute(0, 3, 1, 2), y) < 2e-5
+    assert rel(out2.float().permute(0, 3, 1, 2), y2) < 6e-3
+    # bf16 out + train-mode statistics (taken from the float32 accumulators)
+    outb = torch.zeros(N, H, H, 64, device="cuda", dtype=torch.bfloat16)
+    part = torch.full((148 * 4 * 2 * 64,), 7.0, device="cuda")
+    d = ops.conv_tc_desc(xd, w64.data_ptr(), outb, N, H, H, 64, H, H, 64, 3, 3, 1, 1, 1, stats=part, in_nchw3=True)
+    check(lib.combat_conv_tc(C.byref(d), ops._s()), "conv_tc first + stats")
+    nblk = lib.combat_conv_tc_last_grid()
+    torch.cuda.synchronize()
+    assert rel(outb.float().permute(0, 3, 1, 2), y) < 6e-3
+    ps = part[: nblk * 2 * 64].view(nblk, 2, 64).double().sum(0).cpu()
+    assert rel(ps[0], y.double().sum((0, 2, 3))) < 1e-4 and rel(ps[1], (y.double() ** 2).sum((0, 2, 3))) < 1e-4
+
+
 @pytest.mark.parametrize("shape", [(5, 3, 32, 32), (2, 3, 64, 64), (3, 1, 7, 9)])
 def test_tv_loss_fwd_bwd(ops, shape):
     """total-variation term of train_generator_imperceptible.py:228 (kornia 0.6.6 total_variation(.).mean()): loss and the gradient
