@@ -372,7 +372,7 @@ class NetBase:
                                  out2=out2, scale2=bn_relu[0] if bn_relu is not None else None,
                                  shift2=bn_relu[1] if bn_relu is not None else None,
                                  stats=ops.Scratch.get(self.device) if want_stats else None, in_nchw3=True)
-            _tc_launch(lambda: lib.combat_conv_tc(C.byref(d), ops._s()), "conv_tc", 2.0 * N * Ho * Wo * 64 * 27,
+            _tc_launch(lambda: lib.combat_conv_tc(C.byref(d), ops._s()), "conv_tc_boundary", 2.0 * N * Ho * Wo * 64 * 27,
                        "N%d %dx%d 3->64 k3 s1 first%s" % (N, H, W, " +bn" if bn_relu is not None else (" +stats" if want_stats else "")))
             self.last_stats_nblk = lib.combat_conv_tc_last_grid() if want_stats else 0
             return (out, out2) if bn_relu is not None else out
@@ -404,8 +404,8 @@ class NetBase:
             A = ops.im2col3(x_nchw, cs.stride)
             dw64 = torch.zeros((cs.Cout, 64), dtype=torch.float32, device=self.device)
             d = ops.conv_tc_desc(A, None, None, N, Ho, Wo, 64, Ho, Wo, cs.Cout, 1, 1, 1, 0, 1)
-            _tc_launch(lambda: lib.combat_conv_tc_wgrad(C.byref(d), ops._p(dy), ops._p(dw64), ops._s()), "conv_tc_wgrad",
-                       2.0 * N * Ho * Wo * cs.Cout * 27, "N%d %dx%d 3->%d k3 s%d im2col" % (N, H, W, cs.Cout, cs.stride))
+            _tc_launch(lambda: lib.combat_conv_tc_wgrad(C.byref(d), ops._p(dy), ops._p(dw64), ops._s()), "conv_tc_boundary",
+                       2.0 * N * Ho * Wo * cs.Cout * 27, "N%d %dx%d 3->%d k3 s%d im2col wgrad" % (N, H, W, cs.Cout, cs.stride))
             ops.fold_w64(dw64, self.store.raw(self.store.grad, cs.name + ".weight"), cs.Cout, 0)
             if cs.bias:
                 ops.colsum(dy, cs.Cout, self.store.g(cs.name + ".bias"))
@@ -897,15 +897,21 @@ class Generator(NetBase):
                 A = ops.im2col3(dz, 1)
                 dw64 = torch.zeros((nf, 64), dtype=torch.float32, device=self.device)
                 d = ops.conv_tc_desc(A, None, None, N, H, W, 64, H, W, nf, 1, 1, 1, 0, 1)
-                _tc_launch(lambda: lib.combat_conv_tc_wgrad(C.byref(d), ops._p(a01), ops._p(dw64), ops._s()), "conv_tc_wgrad",
-                           2.0 * N * H * W * nf * 27, "N%d %dx%d %d->3 k3 s1 im2col" % (N, H, W, nf))
+                _tc_launch(lambda: lib.combat_conv_tc_wgrad(C.byref(d), ops._p(a01), ops._p(dw64), ops._s()), "conv_tc_boundary",
+                           2.0 * N * H * W * nf * 27, "N%d %dx%d %d->3 k3 s1 im2col wgrad" % (N, H, W, nf))
                 csum = torch.zeros(64, dtype=torch.float32, device=self.device)
                 ops.colsum(A.view(-1, 64), 64, csum)
                 ops.fold_w64(dw64, self.store.raw(self.store.grad, cs.name + ".weight"), nf, 1, colsum=csum,
                              db=self.store.g(cs.name + ".bias"))
             else:
                 ops.wgrad_cout3(a01, dz, self.store.raw(self.store.grad, cs.name + ".weight"), self.store.g(cs.name + ".bias"))
-            if self._use_im2col(cs, nf, 3):  # input gradient of the 64 -> 3 conv == 3 -> 64 conv with the flipped filter
+            if self.tc_first2 and self.use_tc and nf == 64 and W in (16, 32, 64, 128) and H * W >= 128:
+                # input gradient of the 64 -> 3 conv == 3 -> 64 conv of dz with the flipped filter: conv_tc_first_kernel
+                d = ops.conv_tc_desc(dz, self._w64_for(cs, dgrad=True).data_ptr(), d_a01, N, H, W, 64, H, W, 64, 3, 3, 1, 1, 1,
+                                     in_nchw3=True)
+                _tc_launch(lambda: lib.combat_conv_tc(C.byref(d), ops._s()), "conv_tc_boundary", 2.0 * N * H * W * 64 * 27,
+                           "N%d %dx%d 3->64 k3 s1 first (dgrad of 64->3)" % (N, H, W))
+            elif self._use_im2col(cs, nf, 3):  # input gradient of the 64 -> 3 conv == 3 -> 64 conv with the flipped filter
                 self.cin3_tc(dz, self._w64_for(cs, dgrad=True), nf, 1, d_a01, tag=" (dgrad)")
             else:
                 ops.conv_cin3(dz, self._wptr(cs, True), self.dt, d_a01, nf, 1)
