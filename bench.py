@@ -8,8 +8,9 @@ ours      : one alternated generator/surrogate iteration (train_generator.py:170
             scaling for N > 1 with NCCL gradient all-reduce).  `value` = device-resident inputs, CUDA-graph replay;
             `e2e` = the same metric through the public API with HOST inputs (pinned H2D of the batch and D2H of the
             step's losses/counters inside the timed region).
-reference : the reference's algorithm on the box's host cores (oracle/combat_oracle.py -- the CPU restatement pinned
-            to the unmodified reference; /root/reference does not exist on the GPU box), same metric.
+reference : the UNMODIFIED reference `train_generator.train()` on the box's host cores, from baseline/_ref/ (a git-ignored
+            verbatim install of the reference's .py files made by build(), oracle/install_reference.py; it ships with the
+            snapshot), BASELINE configs[0] (batch 128), same metric; the oracle port only if baseline/_ref is absent.
 One JSON line on stdout (rank 0).
 """
 import argparse
@@ -116,6 +117,64 @@ def cpu_reference_rate(batch, steps, warmup, seed=0):
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     return batch * len(times) / sum(times), sum(times) / len(times)
+
+
+def reference_installed():
+    """baseline/_ref/ holds the UNMODIFIED reference (oracle/install_reference.py, run by build() in the build container)."""
+    return os.path.isfile(os.path.join(ROOT, "baseline", "_ref", "train_generator.py"))
+
+
+def reference_train_rate(batch, steps, warmup, seed=0, anomaly=True):
+    """images/sec of the UNMODIFIED reference `train_generator.train()` (baseline/_ref, `--device cpu --post_transform_option
+    no_use`) on the host cores.  Nothing of the reference is patched: the per-step times are observed from
+    OUTSIDE, by a loader object that notes the time each time train() asks for the next batch.  anomaly=False measures the
+    same code with `torch.autograd.set_detect_anomaly` (which train() switches on at :147) made inert for the call."""
+    import contextlib
+    import random
+    import tempfile
+
+    from oracle.ref_loader import NullWriter, load_reference
+    tg, config = load_reference(os.path.join(ROOT, "baseline", "_ref"))
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    random.seed(seed)
+    opt = config.get_arguments().parse_args(["--device", "cpu", "--post_transform_option", "no_use", "--bs", str(batch)])
+    opt.input_height = opt.input_width = 32
+    opt.input_channel = 3
+    netC, optC, schC, netG, optG, schG, netF, clean = tg.get_model(opt)
+    netF.eval()
+    clean.eval()
+
+    class TimedBatches:
+        def __init__(self, n):
+            self.n, self.t = n, []
+
+        def __len__(self):
+            return self.n
+
+        def __iter__(self):
+            for _ in range(self.n):
+                xy = (torch.rand(batch, 3, 32, 32) * 2 - 1, torch.randint(0, 10, (batch,)))
+                self.t.append(time.perf_counter())
+                yield xy
+            self.t.append(time.perf_counter())
+
+    dl = TimedBatches(warmup + steps)
+    real_setter = torch.autograd.set_detect_anomaly
+    cwd = os.getcwd()
+    try:
+        os.chdir(tempfile.mkdtemp())
+        if not anomaly:
+            torch.autograd.set_detect_anomaly = lambda *a, **k: None
+        with open(os.devnull, "w") as null, contextlib.redirect_stdout(null):   # the reference's progress bar writes to stdout
+            tg.train(netC, optC, schC, netG, optG, schG, netF, clean, dl, NullWriter(), 1, opt)
+    finally:
+        torch.autograd.set_detect_anomaly = real_setter
+        real_setter(False)
+        os.chdir(cwd)
+    dt = np.diff(np.array(dl.t))[warmup:]
+    return batch * len(dt) / float(dt.sum()), float(np.median(dt)), float(dt.mean())
 
 
 def cpu_model():
@@ -297,27 +356,44 @@ def workload_config(B, world, use_graph):
             "flops_per_image": FLOPS_PER_IMG_FULL}
 
 
+def cpu_baseline_record(batch, steps, warmup, with_anomaly_off=True):
+    """The reference arm / cpu_baseline measurement.  kind "reference": the UNMODIFIED reference train() from baseline/_ref
+    (anomaly mode as shipped = ON is the value; the same code with anomaly mode off is reported beside it, BASELINE.md 4.1);
+    kind "port": the oracle restatement (only when baseline/_ref did not travel)."""
+    if reference_installed():
+        rate, tmed, tmean = reference_train_rate(batch, steps, warmup, anomaly=True)
+        rec = {"value": rate, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "reference", "cpu_model": cpu_model(),
+               "sample": "%d iterations of the unmodified reference train_generator.train() at batch %d (BASELINE configs[0]) after %d "
+                         "warm-up, --device cpu --post_transform_option no_use, anomaly mode as shipped (on), all host threads"
+                         % (steps, batch, warmup),
+               "median_s_per_step": tmed}
+        if with_anomaly_off:
+            r2, tm2, _ = reference_train_rate(batch, max(1, min(steps, 5)), min(warmup, 1), anomaly=False)
+            rec["value_anomaly_off"] = r2
+            rec["median_s_per_step_anomaly_off"] = tm2
+        return rec, tmean
+    rate, tstep = cpu_reference_rate(batch, steps, warmup)
+    return {"value": rate, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port", "cpu_model": cpu_model(),
+            "sample": "%d alternated steps of batch %d on the host cores (oracle/combat_oracle.py; baseline/_ref absent)"
+                      % (steps, batch)}, tstep
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # size the per-step sample so that the whole run ends within a few minutes
-    r32, t32 = cpu_reference_rate(32, 1, 0)
-    budget = 300.0   # BASELINE configs[0] (batch 128) unless this box's cores would need more than ~5 minutes for K + W steps
+    # BASELINE configs[0]: batch 128, every step a bounded sample of the CUDA arm's workload (same synthetic distribution, fp32,
+    # all host threads); ~1.5 s per step on 16 cores, so K + W steps end within a few minutes for any sensible K
     batch = 128
-    while batch > 16 and (args.steps + args.warmup) * t32 * batch / 32 > budget:
-        batch //= 2
-    rate, tstep = cpu_reference_rate(batch, args.steps, args.warmup)
-    cores = torch.get_num_threads()
+    steps = min(args.steps, 40)
+    cpu, tstep = cpu_baseline_record(batch, steps, min(args.warmup, 5))
+    rate = cpu["value"]
     line = {
         "impl": "reference", "metric": "alternated-step images/sec at CIFAR-10 shape", "value": rate, "unit": "images/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": tstep * 1e3, "higher_is_better": True,
+        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 5), "ms_per_step": tstep * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        # same workload as the CUDA arm; every timed step is a bounded SAMPLE of it (one alternated step over `batch` images of
-        # the same synthetic distribution, fp32, all host threads) -- images/s is batch-size independent on the CPU
         "config": dict(workload_config(args.batch, max(1, args.gpus), not args.no_graph), reference_sample_batch=batch),
-        "cpu_baseline": {"value": rate, "unit": "images/s", "cores": cores, "kind": "port", "cpu_model": cpu_model(),
-                         "sample": "%d alternated steps of batch %d on the host cores (oracle/combat_oracle.py)" % (args.steps, batch)},
+        "cpu_baseline": cpu,
         "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -467,9 +543,7 @@ def run_ours(args):
     # ---- CPU baseline (rank 0, N == 1 only): the reference algorithm on the host cores, bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, tstep = cpu_reference_rate(128, 2, 1)
-        cpu = {"value": rate, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port", "cpu_model": cpu_model(),
-               "sample": "2 alternated steps of batch 128 (BASELINE configs[0]) after 1 warm-up, oracle/combat_oracle.py on the host cores"}
+        cpu, _ = cpu_baseline_record(128, 3, 1, with_anomaly_off=False)
     # ---- sub-records: the other targets BASELINE.json / north_star name, measured by the same process (not the headline)
     sub = {}
     if not args.no_sub:

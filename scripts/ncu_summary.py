@@ -22,6 +22,8 @@ METRICS = [
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots busy"),
     ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "FMA pipe"),
     ("sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active", "tensor pipe"),
+    ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe cycles active (of active cycles)"),
+    ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "tensor pipe cycles active (of elapsed cycles)"),
     ("smsp__inst_executed.sum", "warp instructions"),
     ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "shared-memory wavefronts"),
     ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "shared-memory bank conflicts"),
