@@ -60,14 +60,22 @@ class StepPlan:
     # order T1 (:196) | T3 (:227) | T4 (:228) | T2 (:214) | T5 (:250): [1:3] is the parameter block of netC's batched
     # [x ; x_bd] forward, [3:5] that of clean_model's.  None: --post_transform_option no_use.
     tf: np.ndarray | None = None
+    # inputaware variant (train_generator_inputaware.py:238-239): blur of inputs_bd2 = x + trigger of the second loader's image
+    sigma_g2: float | None = None
+    taps_g2: tuple = (1.0, 0.0)
 
 
-TF_SLOT = {"T1": 0, "T3": 1, "T4": 2, "T2": 3, "T5": 4}
+# "T6": the transform of inputs_bd2 (train_generator_inputaware.py:241), present only in that variant's parameter block
+TF_SLOT = {"T1": 0, "T3": 1, "T4": 2, "T2": 3, "T5": 4, "T6": 5}
 N_LOSSES = 12   # float32 scalars a step leaves on the device (see _ensure_bufs)
 
 
 def _tf_on(opt) -> bool:
     return getattr(opt, "post_transform_option", "no_use") != "no_use"
+
+
+def _inputaware(opt) -> bool:
+    return getattr(opt, "variant", "") == "inputaware"
 
 
 def create_targets_bd_np(targets: np.ndarray, opt) -> np.ndarray:
@@ -85,6 +93,7 @@ def make_plan(targets_host, opt, with_metrics=True) -> StepPlan:
     transforms draw nothing under --post_transform_option no_use; T2 / T3 belong to the metric forwards)."""
     y = np.asarray(targets_host, dtype=np.int64)
     B = y.shape[0]
+    ia = _inputaware(opt)   # train_generator_inputaware.py: one more sigma (:239) and one more transform (:241) in the G-step
     bd = create_targets_bd_np(y, opt).astype(np.int64)
     trg = np.nonzero(y == bd)[0]
     ntrg = np.nonzero(y != bd)[0]
@@ -96,20 +105,24 @@ def make_plan(targets_host, opt, with_metrics=True) -> StepPlan:
         taps_c = ops.gaussian_taps(sigma_c)
     tf = None
     if _tf_on(opt):
-        tf = np.zeros((5, B, TF_W), dtype=np.float32)
+        tf = np.zeros((6 if ia else 5, B, TF_W), dtype=np.float32)
         tf[:, :, 2] = 1.0
         tf[TF_SLOT["T1"]] = draw_tf_params(B, opt)                                    # :196
         if with_metrics:
             tf[TF_SLOT["T2"]] = draw_tf_params(B, opt)                                # :214
     sigma_g = torch.empty(1).uniform_(opt.sigma[0], opt.sigma[1]).item()              # :226
+    sigma_g2 = torch.empty(1).uniform_(opt.sigma[0], opt.sigma[1]).item() if ia else None   # inputaware :239
     if tf is not None:
         if with_metrics:
             tf[TF_SLOT["T3"]] = draw_tf_params(B, opt)                                # :227
+        if ia:
+            tf[TF_SLOT["T6"]] = draw_tf_params(B, opt)                                # inputaware :241 (before inputs_bd's, :242)
         tf[TF_SLOT["T4"]] = draw_tf_params(B, opt)                                    # :228
         tf[TF_SLOT["T5"]] = draw_tf_params(B, opt)                                    # :250
     perm = np.concatenate([trg, ntrg]).astype(np.int32)
     total_y = np.concatenate([bd[trg[:num_bd]], y[trg[num_bd:]], y[ntrg]]).astype(np.int64)
-    return StepPlan(perm, num_bd, trg, ntrg, bd, total_y, sigma_c, sigma_g, taps_c, ops.gaussian_taps(sigma_g), tf=tf)
+    return StepPlan(perm, num_bd, trg, ntrg, bd, total_y, sigma_c, sigma_g, taps_c, ops.gaussian_taps(sigma_g), tf=tf,
+                    sigma_g2=sigma_g2, taps_g2=ops.gaussian_taps(sigma_g2) if ia else (1.0, 0.0))
 
 
 def multilabel_chunks(bs: int, num_classes: int):
@@ -216,6 +229,12 @@ class AlternatedStep:
         # variant of the step (getattr: the base trainer's opt carries no such attribute): "imperceptible" adds the total-variation
         # term of train_generator_imperceptible.py to the G-step loss
         self.tv_weight = float(getattr(o, "tv_weight", 0.0)) if getattr(o, "variant", "") == "imperceptible" else 0.0
+        # "inputaware" (train_generator_inputaware.py): a second batch x2 per iteration; the generator runs ONCE over [x ; x2], the
+        # trigger of x2's rows is pasted on x (inputs_bd2), netC sees it through one more eval-mode forward + input gradient
+        self.inputaware = _inputaware(o)
+        self.cross_weight = float(getattr(o, "cross_weight", 0.2)) if self.inputaware else 0.0
+        if self.inputaware and self.multilabel:
+            raise ValueError("the inputaware variant has no multilabel form in the reference")
         self.tf_on = _tf_on(o)      # PostTensorTransform active (five fused gather launches + two adjoints per iteration)
         self.lr_C = torch.full((1,), float(o.lr_C), dtype=torch.float32, device=self.device)
         self.lr_G = torch.full((1,), float(o.lr_G), dtype=torch.float32, device=self.device)
@@ -266,18 +285,18 @@ class AlternatedStep:
     PLAN_SLOTS = 4
 
     @staticmethod
-    def _plan_layout(B, multilabel, tf_on=False):
+    def _plan_layout(B, multilabel, tf_on=False, n_tf=5):
         a16 = lambda n: (n + 15) // 16 * 16
         off, lay = 0, {}
         for name, nbytes in (("y", 8 * B), ("bd_targets", 8 * B), ("total_y", 8 * B), ("perm", 4 * B), ("small", 32),
                              ("num_bd", 16), ("taps_rows", 8 * B if multilabel else 0),
-                             ("tf", 5 * B * TF_W * 4 if tf_on else 0)):
+                             ("tf", n_tf * B * TF_W * 4 if tf_on else 0)):
             lay[name] = (off, nbytes)
             off += a16(nbytes)
         return lay, max(off, 16)
 
     @staticmethod
-    def _plan_views(block, lay, B):
+    def _plan_views(block, lay, B, n_tf=5):
         def v(name, dtype, shape=None):
             o, n = lay[name]
             t = block[o:o + n].view(dtype)
@@ -285,7 +304,7 @@ class AlternatedStep:
         return {"y": v("y", torch.int64), "bd_targets": v("bd_targets", torch.int64), "total_y": v("total_y", torch.int64),
                 "perm": v("perm", torch.int32), "small": v("small", torch.float32), "num_bd": v("num_bd", torch.int32),
                 "taps_rows": v("taps_rows", torch.float32, (B, 2)) if lay["taps_rows"][1] else None,
-                "tf": v("tf", torch.float32, (5, B, TF_W)) if lay["tf"][1] else None}
+                "tf": v("tf", torch.float32, (n_tf, B, TF_W)) if lay["tf"][1] else None}
 
     def _ensure_bufs(self, B):
         """Buffers (and the captured graphs that reference them) are cached PER BATCH SIZE: the shorter last batch of an
@@ -297,13 +316,18 @@ class AlternatedStep:
         dev = self.device
         o = self.opt
         b = {"B": B, "graph": None, "gstate": {}}
-        b["x"] = torch.empty((B, o.input_channel, o.input_height, o.input_width), dtype=torch.float32, device=dev)
+        if self.inputaware:   # [x ; second loader's batch]: one generator forward / backward over both
+            b["xx"] = torch.empty((2 * B, o.input_channel, o.input_height, o.input_width), dtype=torch.float32, device=dev)
+            b["x"] = b["xx"][:B]
+        else:
+            b["x"] = torch.empty((B, o.input_channel, o.input_height, o.input_width), dtype=torch.float32, device=dev)
         b["x2"] = torch.empty((2 * B, o.input_channel, o.input_height, o.input_width), dtype=torch.float32, device=dev)  # [x ; x_bd]
-        lay, nbytes = self._plan_layout(B, self.multilabel, self.tf_on)
+        n_tf = 6 if self.inputaware else 5
+        lay, nbytes = self._plan_layout(B, self.multilabel, self.tf_on, n_tf)
         b["plan_dev"] = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
-        dv = self._plan_views(b["plan_dev"], lay, B)
+        dv = self._plan_views(b["plan_dev"], lay, B, n_tf)
         b["y"], b["bd_targets"], b["total_y"], b["perm"] = dv["y"], dv["bd_targets"], dv["total_y"], dv["perm"]
-        b["taps_c"], b["taps_g"] = dv["small"][0:2], dv["small"][2:4]
+        b["taps_c"], b["taps_g"], b["taps_g2"] = dv["small"][0:2], dv["small"][2:4], dv["small"][4:6]
         b["num_bd"] = dv["num_bd"][0:1]
         b["taps_rows"] = dv["taps_rows"]
         b["tf"] = dv["tf"]
@@ -318,7 +342,7 @@ class AlternatedStep:
         b["slots"] = []
         for _ in range(self.PLAN_SLOTS):
             h = torch.zeros(nbytes, dtype=torch.uint8).pin_memory()
-            b["slots"].append({"h": h, "v": self._plan_views(h, lay, B), "ev": None})
+            b["slots"].append({"h": h, "v": self._plan_views(h, lay, B, n_tf), "ev": None})
         b["slot"] = 0
         self._bufs_by_B[B] = b
         self._bufs = b
@@ -347,12 +371,16 @@ class AlternatedStep:
         v["perm"].copy_(torch.from_numpy(plan.perm))
         v["small"][0], v["small"][1] = plan.taps_c
         v["small"][2], v["small"][3] = plan.taps_g
+        v["small"][4], v["small"][5] = plan.taps_g2
         v["num_bd"][0] = plan.num_bd
         if self.multilabel:
             v["taps_rows"].copy_(torch.from_numpy(plan.taps_rows))
         if self.tf_on:
             if plan.tf is None:
                 raise ValueError("the engine was built with PostTensorTransform on: the plan must carry its parameters")
+            if tuple(plan.tf.shape) != tuple(v["tf"].shape):
+                raise ValueError("the plan's PostTensorTransform block %s does not match the engine's %s (variant mismatch)"
+                                 % (tuple(plan.tf.shape), tuple(v["tf"].shape)))
             v["tf"].copy_(torch.from_numpy(plan.tf))
         b["plan_dev"].copy_(s["h"], non_blocking=True)
         s["ev"] = torch.cuda.Event()
@@ -384,9 +412,10 @@ class AlternatedStep:
             noise_raw = ctxG = noise = None
             total_x = x
         else:
-            noise_raw, ctxG = self.netG.forward(x, None, save=save_g)                        # :189 and :223, once
+            gin = b["xx"] if (self.inputaware and save_g) else x                             # inputaware: + netG(inputs2), :238
+            noise_raw, ctxG = self.netG.forward(gin, None, save=save_g)                      # :189 and :223, once
             noise = ops.plane_op(noise_raw, "lowfreq", keep=self.keep)                      # :190-191 / :224
-            total_x = ops.poison_blend_fwd(x, noise, b["perm"], 0, o.noise_rate, None, taps_dev=b["taps_c"],
+            total_x = ops.poison_blend_fwd(x, noise[:x.shape[0]], b["perm"], 0, o.noise_rate, None, taps_dev=b["taps_c"],
                                            num_bd_dev=b["num_bd"])                            # :192-195
         total_in = ops.post_transform_fwd(total_x, b["tf"][TF_SLOT["T1"]]) if self.tf_on else total_x   # :196
         logits_c, ctxC = self.netC.forward(total_in, train=True, save=True)                  # :205
@@ -405,6 +434,10 @@ class AlternatedStep:
         losses, counts = b["losses"], b["counts"]
         noise = st["noise"]
         numel = x.numel()
+        if self.inputaware:                                                                  # inputaware :238-239
+            noise, noise2 = noise[:B], noise[B:]
+            st["x_bd2"] = ops.poison_blend_fwd(x, noise2, None, B, o.noise_rate, None, taps_dev=b["taps_g2"])
+            st.update(noise=noise, noise2=noise2)
         if self.multilabel:                                                                  # multilabel :203-221
             noise_raw, ctxG = self.netG.forward(x, b["bd_targets"], save=True)
             noise = ops.plane_op(noise_raw, "lowfreq", keep=self.keep)
@@ -447,7 +480,7 @@ class AlternatedStep:
                                           loss_out=losses[3:4], counts_out=counts[8:10])      # :251,266-267
             g2 = self.clean.backward(ctxK, dl2, need_wgrad=False, need_dx=True)
             del ctxK
-        if self.with_metrics and not self.multilabel:
+        if self.with_metrics and not self.multilabel and not self.inputaware:
             ops.grad_l2(x, x_bd, losses[7:8], b["gl2_partial"])                              # :235-243 (logged only)
         st.update(x_bd=x_bd, clean_model_preds=cm_preds, g2=g2)
 
@@ -479,14 +512,32 @@ class AlternatedStep:
             _, dl1, _ = ops.cross_entropy(pred_bd, b["bd_targets"], 1.0, True, loss_out=losses[1:2], counts_out=counts[6:8])
             g1 = self.netC.backward(ctxB, dl1, need_wgrad=False, need_dx=True)
             del ctxB
+        gx = None
+        if self.inputaware:   # train_generator_inputaware.py:241,246,261: + cross_weight * CE(netC(T(inputs_bd2)), targets)
+            x_bd2 = st["x_bd2"]
+            xin = ops.post_transform_fwd(x_bd2, b["tf"][TF_SLOT["T6"]]) if self.tf_on else x_bd2
+            pred_cross, ctxX = self.netC.forward(xin, train=False, save=True)
+            _, dlx, _ = ops.cross_entropy(pred_cross, y, self.cross_weight, True, loss_out=losses[9:10], counts_out=counts[12:14])
+            gx = self.netC.backward(ctxX, dlx, need_wgrad=False, need_dx=True)
+            del ctxX
+            if self.tf_on:
+                gx = ops.post_transform_bwd(gx, b["tf"][TF_SLOT["T6"]])
+            st.update(pred_cross=pred_cross)
         if self.tf_on:  # back through T4 / T5 to x_bd: both adjoints accumulate into one buffer
             gsum = ops.post_transform_bwd(g1, b["tf"][TF_SLOT["T4"]])
             ops.post_transform_bwd(g2, b["tf"][TF_SLOT["T5"]], out=gsum, accumulate=True)
             g1, g2 = gsum, None
         if self.tv_weight:   # train_generator_imperceptible.py:228,235: + tv_weight * total_variation(inputs_bd).mean()
             ops.tv_loss(x_bd, losses[8:9], grad=g1, grad_weight=self.tv_weight / B, partial=b["tv_partial"])
-        dnoise = ops.poison_blend_bwd(x, noise, x_bd, g1, g2, 2.0 * o.L2_weight / numel, o.noise_rate, None,
-                                      taps_dev=b["taps_g"], taps_rows=b["taps_rows"])
+        if self.inputaware:   # gradients of both trigger batches, [d noise(x) ; d noise(x2)], through ONE generator backward
+            dnoise = torch.empty_like(b["xx"])
+            ops.poison_blend_bwd(x, noise, x_bd, g1, g2, 2.0 * o.L2_weight / numel, o.noise_rate, None, out=dnoise[:B],
+                                 taps_dev=b["taps_g"])
+            ops.poison_blend_bwd(x, st["noise2"], st["x_bd2"], gx, None, 0.0, o.noise_rate, None, out=dnoise[B:],
+                                 taps_dev=b["taps_g2"])
+        else:
+            dnoise = ops.poison_blend_bwd(x, noise, x_bd, g1, g2, 2.0 * o.L2_weight / numel, o.noise_rate, None,
+                                          taps_dev=b["taps_g"], taps_rows=b["taps_rows"])
         dnoise_raw = ops.plane_op(dnoise, "lowfreq", keep=self.keep)                          # P is symmetric
         self.netG.zero_grad()                                                                # :220
         self.netG.backward(st.pop("ctxG"), dnoise_raw)                                       # :254
@@ -592,15 +643,20 @@ class AlternatedStep:
         else:
             dst.copy_(x, non_blocking=True)
 
-    def step(self, x_dev, y_host, plan: StepPlan | None = None, use_graph=False, keep_debug=False):
+    def step(self, x_dev, y_host, plan: StepPlan | None = None, use_graph=False, keep_debug=False, x2=None):
         """One alternated iteration.  x_dev: float32 NCHW tensor already on the device (or a pinned host tensor,
-        which is copied asynchronously); y_host: host labels.  Returns {'losses': dev[8], 'counts': dev[16]}."""
+        which is copied asynchronously); y_host: host labels; x2: the second loader's batch (inputaware variant only).
+        Returns {'losses': dev[N_LOSSES], 'counts': dev[16]}."""
         if plan is None:
             mk = make_plan_multilabel if self.multilabel else make_plan
             plan = mk(y_host, self.opt, self.with_metrics)
         B = len(plan.perm)
         b = self._ensure_bufs(B)
         self._take_input(x_dev, b["x"])
+        if self.inputaware:
+            if x2 is None or tuple(x2.shape) != tuple(b["x"].shape):
+                raise ValueError("the inputaware step needs the second loader's batch, same shape as the first")
+            b["xx"][B:].copy_(x2, non_blocking=True)
         self.upload_plan(y_host, plan)
         dbg = None
         if use_graph and not keep_debug:
@@ -703,16 +759,23 @@ class AlternatedStep:
         return out
 
     # ------------------------------------------------------------ evaluation (train_generator.py:355-391)
-    def eval_step(self, x_dev, y_host, sigma=None, use_graph=False):
+    def eval_step(self, x_dev, y_host, sigma=None, use_graph=False, x2=None, sigma2=None):
         """One batch of eval(): clean accuracy of netC, attack success on the NON-TARGET samples, detector and clean-model
         legs.  The trigger is built for every row of the fixed-shape batch (eval-mode networks and the blur are per-sample
         independent, so the non-target rows are bit-identical to the reference's gathered sub-batch) and the target rows are
         masked out of the counters with a negative label; one blur sigma per batch, drawn like torchvision's GaussianBlur.
-        Returns device int32 counts [clean, -, bd, -, F, -, clean_model, -, bd_ba, bd_asr] and the host-side n_bd."""
+        Returns device int32 counts [clean, -, bd, -, F, -, clean_model, -, bd_ba, bd_asr, -, -, cross] and the host-side n_bd.
+        inputaware variant (train_generator_inputaware.py:402-413): x2 = the second loader's batch; the trigger of x2's rows
+        on x, its own sigma draw (after the first), netC's accuracy on the non-target rows against their TRUE labels."""
         o = self.opt
         y = np.asarray(y_host, dtype=np.int64)
         if sigma is None:
             sigma = torch.empty(1).uniform_(o.sigma[0], o.sigma[1]).item()
+        if self.inputaware:
+            if x2 is None:
+                raise ValueError("the inputaware evaluation needs the second loader's batch")
+            if sigma2 is None:
+                sigma2 = torch.empty(1).uniform_(o.sigma[0], o.sigma[1]).item()
         bd = create_targets_bd_np(y, o)
         ntrg = y != o.target_label
         B = len(y)
@@ -724,6 +787,9 @@ class AlternatedStep:
             eb["dev"] = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
             eb["t"] = eb["dev"][:4 * B * 8].view(torch.int64).view(4, B)   # y | bd masked | ones masked | y masked
             eb["taps"] = eb["dev"][4 * B * 8:].view(torch.float32)[0:2]
+            eb["taps2"] = eb["dev"][4 * B * 8:].view(torch.float32)[2:4]
+            if self.inputaware:
+                eb["x2"] = torch.empty_like(b["x"])
             eb["counts"] = torch.zeros(16, dtype=torch.int32, device=dev)
             eb["graph"] = None
             eb["slots"] = []   # event-guarded ring of pinned host images, as for the training plan (see _ensure_bufs)
@@ -739,6 +805,9 @@ class AlternatedStep:
         h[2].copy_(torch.from_numpy(np.where(ntrg, 1, -1).astype(np.int64)))
         h[3].copy_(torch.from_numpy(np.where(ntrg, y, -1)))
         s["taps"][0], s["taps"][1] = ops.gaussian_taps(sigma)
+        if self.inputaware:
+            s["taps"][2], s["taps"][3] = ops.gaussian_taps(sigma2)
+            eb["x2"].copy_(x2, non_blocking=True)
         eb["dev"].copy_(s["h"], non_blocking=True)
         s["ev"] = torch.cuda.Event()
         s["ev"].record(torch.cuda.current_stream(self.device))
@@ -753,6 +822,13 @@ class AlternatedStep:
             x_bd = ops.poison_blend_fwd(x, noise, None, B, o.noise_rate, None, taps_dev=eb["taps"])  # :372-373
             preds_bd, _ = self.netC.forward(x_bd, train=False, save=False)                          # :375
             ops.cross_entropy(preds_bd, t[1], 1.0, False, counts_out=counts[2:4])
+            extra = {}
+            if self.inputaware:                                                                      # inputaware :402-413
+                noise2 = ops.plane_op(self.netG.forward(eb["x2"], None, save=False)[0], "lowfreq", keep=self.keep)
+                x_bd2 = ops.poison_blend_fwd(x, noise2, None, B, o.noise_rate, None, taps_dev=eb["taps2"])
+                preds_cross, _ = self.netC.forward(x_bd2, train=False, save=False)
+                ops.cross_entropy(preds_cross, t[3], 1.0, False, counts_out=counts[12:14])
+                extra = dict(preds_cross=preds_cross, x_bd2=x_bd2)
             if self.netF is not None:
                 preds_F = self.netF.forward(ops.plane_op(x_bd, "dct", in_mode=2))                    # :381-383
                 ops.cross_entropy(preds_F, t[2], 1.0, False, counts_out=counts[4:6])
@@ -760,7 +836,7 @@ class AlternatedStep:
             ops.cross_entropy(cm_clean, t[0], 1.0, False, counts_out=counts[6:8])
             cm_bd, _ = self.clean.forward(x_bd, train=False, save=False)                             # :389
             ops.cross_entropy(cm_bd, t[3], 1.0, False, targets2=t[1], counts_out=counts[8:10])
-            return dict(preds_clean=preds_clean, preds_bd=preds_bd, x_bd=x_bd, cm_clean=cm_clean, cm_bd=cm_bd)
+            return dict(preds_clean=preds_clean, preds_bd=preds_bd, x_bd=x_bd, cm_clean=cm_clean, cm_bd=cm_bd, **extra)
 
         dbg = None
         if use_graph:
@@ -775,7 +851,7 @@ class AlternatedStep:
                 eb["graph"].replay()
         else:
             dbg = launch()
-        return {"counts": eb["counts"], "n_bd": int(ntrg.sum()), "n": B, "sigma": sigma, "debug": dbg}
+        return {"counts": eb["counts"], "n_bd": int(ntrg.sum()), "n": B, "sigma": sigma, "sigma2": sigma2, "debug": dbg}
 
     class _Pending:
         """Handle of an asynchronous device->host read of a step's scalars (stream-ordered right after that step)."""
@@ -805,7 +881,7 @@ class AlternatedStep:
     @staticmethod
     def _to_dict(l, c) -> dict:
         return dict(loss_c=float(l[0]), loss_ce=float(l[1]), loss_l2=float(l[2]), clean_model_loss=float(l[3]),
-                    loss_grad_l2=float(l[7]), loss_tv=float(l[8]),
+                    loss_grad_l2=float(l[7]), loss_tv=float(l[8]), loss_cross=float(l[9]), n_cross_correct=int(c[12]),
                     n_total_correct=int(c[0]), n_clean_model_correct=int(c[2]), n_clean_correct=int(c[4]),
                     n_bd_correct=int(c[6]), n_clean_model_bd_ba=int(c[8]), n_clean_model_bd_asr=int(c[9]),
                     n_F_correct=int(c[10]))

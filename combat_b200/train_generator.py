@@ -82,7 +82,7 @@ def get_model(opt):
 
 
 _HOT_SCALARS = ("noise_rate", "ratio", "L2_weight", "clean_model_weight", "target_label", "attack_mode", "num_classes",
-                "post_transform_option", "random_crop", "random_rotation", "dataset", "variant", "tv_weight")
+                "post_transform_option", "random_crop", "random_rotation", "dataset", "variant", "tv_weight", "cross_weight")
 
 
 def _engine_for(netC, clean_model, netG, netF, opt, multilabel=False):

@@ -551,6 +551,7 @@ def default_opt(**kw):
         L2_weight=0.02, clean_model_weight=0.8, lr_C=1e-2, lr_G=1e-2, classifier="preact_resnet18",
         post_transform_option="no_use", random_crop=5, random_rotation=10, dataset="cifar10",
         variant="", tv_weight=0.01,   # variant "imperceptible": train_generator_imperceptible.py (+ tv_weight * TV(x_bd).mean())
+        cross_weight=0.2,             # variant "inputaware": train_generator_inputaware.py (+ cross_weight * CE(netC(x + G(x2)), y))
     )
     for k, v in kw.items():
         setattr(o, k, v)
@@ -575,7 +576,7 @@ def make_bd(netG_p, x, opt, sigma, y=None):
 
 
 def alternated_step(state: dict, x: torch.Tensor, y: torch.Tensor, opt, with_metrics: bool = True, grad_hook=None,
-                    buf_hook=None) -> dict:
+                    buf_hook=None, x2: torch.Tensor | None = None) -> dict:
     """One iteration of train() (train_generator.py:170-255); PostTensorTransform per opt.post_transform_option (identity for
     "no_use", the default here; the five calls :196,:214,:227,:228,:250 draw their own parameters, logged in out["tf"]).
 
@@ -584,8 +585,15 @@ def alternated_step(state: dict, x: torch.Tensor, y: torch.Tensor, opt, with_met
     RNG order: numpy rand(n_trg) -> torch uniform (if num_bd>0) -> torch uniform.
     grad_hook(name, grads_dict) / buf_hook(buffers_dict): data-parallel exchange points (local-BN policy) --
     called after each backward, before the optimiser step / after the C-step update; None for the single-process step.
+    x2: the batch of the SECOND loader of train_generator_inputaware.py (:180-185), variant "inputaware" only: the G-step also
+    builds inputs_bd2 = blur(clamp(x + low_freq(netG(x2)) * noise_rate)) -- the trigger of ANOTHER image on this image, its own
+    sigma draw right after the G-step's (:234-239) -- and adds cross_weight * CE(netC(T(inputs_bd2)), y) (:241,246,259-264); the
+    transform calls of the G-step run in the order x, inputs_bd2, inputs_bd (:240-242); no gradient-image loss in this variant.
     Returns a dict of everything observable (indices, losses, logits, metric counts)."""
     fwdC = CLASSIFIERS[opt.classifier]
+    inputaware = getattr(opt, "variant", "") == "inputaware"
+    if inputaware and x2 is None:
+        raise ValueError("the inputaware step needs the second loader's batch")
     netC_p, netC_b, netG_p = state["netC_p"], state["netC_b"], state["netG_p"]
     clean_p, clean_b = state["clean_p"], state["clean_b"]
     out = {}
@@ -635,9 +643,18 @@ def alternated_step(state: dict, x: torch.Tensor, y: torch.Tensor, opt, with_met
     sigma_g = draw_sigma(*opt.sigma)
     out["sigma_g"] = sigma_g
     x_bd, noise, noise_raw = make_bd(netG_p, x, opt, sigma_g)
+    if inputaware:  # train_generator_inputaware.py:238-239
+        sigma_g2 = draw_sigma(*opt.sigma)
+        noise2 = low_freq(unet_forward(netG_p, x2), opt.input_height, opt.ratio)
+        x_bd2 = gaussian_blur(torch.clamp(x + noise2 * opt.noise_rate, -1, 1), sigma_g2, opt.kernel_size)
+        out.update(sigma_g2=sigma_g2, x_bd2=x_bd2.detach())
     with torch.no_grad():
-        if with_metrics:
+        if with_metrics or inputaware:
             out["pred_clean"] = fwdC(netC_p, netC_b, post_transform(x, opt, tf_log), False)  # :227
+    if inputaware:
+        pred_cross = fwdC(netC_p, netC_b, post_transform(x_bd2, opt, tf_log), False)  # inputaware :241
+        loss_cross = F.cross_entropy(pred_cross, y)  # :246
+        out.update(pred_cross=pred_cross.detach(), loss_cross=float(loss_cross), n_cross_correct=int((torch.argmax(pred_cross, 1) == y).sum()))
     pred_bd = fwdC(netC_p, netC_b, post_transform(x_bd, opt, tf_log), False)  # :228 netC.eval(), weights AFTER the C update
     loss_ce = F.cross_entropy(pred_bd, bd_targets)  # :231
     loss_l2 = F.mse_loss(x_bd, x)  # :234
@@ -652,6 +669,8 @@ def alternated_step(state: dict, x: torch.Tensor, y: torch.Tensor, opt, with_met
         loss_tv = total_variation(x_bd).mean()
         loss = loss + opt.tv_weight * loss_tv
         out["loss_tv"] = float(loss_tv)
+    if inputaware:  # :259-264
+        loss = loss + opt.cross_weight * loss_cross
     loss.backward()
     gradsG = {k: v.grad for k, v in netG_p.items()}
     out["gradsG"] = {k: g.clone() for k, g in gradsG.items()}
@@ -687,9 +706,11 @@ def alternated_step(state: dict, x: torch.Tensor, y: torch.Tensor, opt, with_met
 # --------------------------------------------------------------------------
 
 
-def eval_batch(state: dict, x: torch.Tensor, y: torch.Tensor, opt) -> dict:
+def eval_batch(state: dict, x: torch.Tensor, y: torch.Tensor, opt, x2: torch.Tensor | None = None) -> dict:
     """One iteration of eval() (:355-391): clean accuracy of netC, attack success on ALL non-target samples, detector
-    and clean-model legs.  RNG: one torch uniform per batch (GaussianBlur.get_params, :372)."""
+    and clean-model legs.  RNG: one torch uniform per batch (GaussianBlur.get_params, :372).
+    x2 (variant "inputaware", train_generator_inputaware.py:402-413): the second loader's batch; the trigger of its rows on x
+    (a second sigma draw, right after the first), netC's accuracy on the non-target rows against their true labels."""
     fwdC = CLASSIFIERS[opt.classifier]
     netC_p, netC_b, netG_p = state["netC_p"], state["netC_b"], state["netG_p"]
     clean_p, clean_b = state["clean_p"], state["clean_b"]
@@ -703,6 +724,12 @@ def eval_batch(state: dict, x: torch.Tensor, y: torch.Tensor, opt) -> dict:
         x_bd, _, _ = make_bd(netG_p, x_sel, opt, sigma)  # :369-373
         bd_t = create_targets_bd(y_sel, opt.attack_mode, opt.target_label, opt.num_classes)
         preds_bd = fwdC(netC_p, netC_b, x_bd, False)
+        if x2 is not None:
+            sigma2 = draw_sigma(*opt.sigma)
+            noise2 = low_freq(unet_forward(netG_p, x2), opt.input_height, opt.ratio)
+            x_bd2 = gaussian_blur(torch.clamp(x + noise2 * opt.noise_rate, -1, 1), sigma2, opt.kernel_size)
+            preds_cross = fwdC(netC_p, netC_b, x_bd2, False)
+            out.update(sigma2=sigma2, x_bd2=x_bd2, preds_cross=preds_cross, cross_correct=int((am(preds_cross[ntrg]) == y_sel).sum()))
         inputs_F = dct_2d(((x_bd + 1) / 2 * 255).byte())  # :381
         preds_F = frequency_model_forward(state["netF_p"], state["netF_b"], inputs_F)
         cm_clean = fwdC(clean_p, clean_b, x, False)
@@ -757,9 +784,11 @@ def victim_train_step(netC_p, netC_b, netG_p, momC: dict, x: torch.Tensor, y: to
     return out
 
 
-def victim_eval_batch(netC_p, netC_b, netG_p, x: torch.Tensor, y: torch.Tensor, opt) -> dict:
+def victim_eval_batch(netC_p, netC_b, netG_p, x: torch.Tensor, y: torch.Tensor, opt, x2: torch.Tensor | None = None) -> dict:
     """One iteration of eval.py:115-141 (the stand-alone evaluator): clean accuracy, and on the gathered non-target rows the
-    benign accuracy and attack success of the triggered images.  RNG: one torch uniform per batch (GaussianBlur, :131)."""
+    benign accuracy and attack success of the triggered images.  RNG: one torch uniform per batch (GaussianBlur, :131).
+    x2: train_victim_inputaware.py:213-223 -- the cross-trigger accuracy (trigger of the second loader's rows on x, second sigma
+    draw, non-target rows against their true labels)."""
     fwdC = CLASSIFIERS[opt.classifier]
     am = lambda t: torch.argmax(t, dim=1)
     with torch.no_grad():
@@ -770,7 +799,14 @@ def victim_eval_batch(netC_p, netC_b, netG_p, x: torch.Tensor, y: torch.Tensor, 
         x_bd, _, _ = make_bd(netG_p, x_sel, opt, sigma)  # :128-131
         bd_t = create_targets_bd(y_sel, opt.attack_mode, opt.target_label, opt.num_classes)
         preds_bd = fwdC(netC_p, netC_b, x_bd, False)  # :133
-    return dict(sigma=sigma, ntrg=ntrg, x_bd=x_bd, preds_clean=preds_clean, preds_bd=preds_bd, n_clean=len(x), n_bd=len(ntrg),
+        extra = {}
+        if x2 is not None:
+            sigma2 = draw_sigma(*opt.sigma)
+            noise2 = low_freq(unet_forward(netG_p, x2), opt.input_height, opt.ratio)
+            x_bd2 = gaussian_blur(torch.clamp(x + noise2 * opt.noise_rate, -1, 1), sigma2, opt.kernel_size)
+            preds_cross = fwdC(netC_p, netC_b, x_bd2, False)
+            extra = dict(sigma2=sigma2, x_bd2=x_bd2, preds_cross=preds_cross, cross_correct=int((am(preds_cross[ntrg]) == y_sel).sum()))
+    return dict(**extra, sigma=sigma, ntrg=ntrg, x_bd=x_bd, preds_clean=preds_clean, preds_bd=preds_bd, n_clean=len(x), n_bd=len(ntrg),
                 clean_correct=int((am(preds_clean) == y).sum()), bd_ba=int((am(preds_bd) == y_sel).sum()),
                 bd_asr=int((am(preds_bd) == bd_t).sum()))
 

@@ -80,6 +80,14 @@ def load_reference_imperceptible(ref: str = REF):
     return train_generator_imperceptible
 
 
+def load_reference_inputaware(ref: str = REF):
+    """train_generator_inputaware.py of the reference (same stand-ins)."""
+    load_reference(ref)
+    import train_generator_inputaware
+
+    return train_generator_inputaware
+
+
 class NullWriter:
     """tf_writer stand-in for train()."""
 

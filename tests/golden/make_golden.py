@@ -262,6 +262,68 @@ def gen_step(name, B, n_batches, seed, mod=None):
     save(name, **out)
 
 
+def gen_step_inputaware(name, B, n_batches, seed):
+    """Iterations of the UNMODIFIED train_generator_inputaware.train() (:141-335): two loaders (the second one supplies the images
+    whose triggers are pasted on the first one's images), cross-trigger loss, lr_G = 0.1 * lr_C (get_model :120-127).
+    Per iteration the reference calls netG 3x (C-step subset, x, x2), netC 4x (train total_x; eval x, inputs_bd2, inputs_bd),
+    clean_model 2x, netF 1x; losses in call order: ce(C), ce(bd), ce(cross), mse, ce(clean model)."""
+    import tempfile
+    from oracle.ref_loader import load_reference_inputaware
+    ti = load_reference_inputaware()
+    opt = get_opt()
+    opt.input_height = opt.input_width = 32
+    opt.input_channel = 3
+    os.chdir(tempfile.mkdtemp())   # debugging image dumps every 5 batches go to the RELATIVE opt.temps (:305-312)
+    seed_all(seed)
+    netC, optC, schC, netG, optG, schG, netF, clean = ti.get_model(opt)
+    netF.eval()
+    clean.eval()
+    batches = [(torch.rand(B, 3, 32, 32) * 2 - 1, torch.randint(0, 10, (B,))) for _ in range(n_batches)]
+    batches2 = [(torch.rand(B, 3, 32, 32) * 2 - 1, torch.randint(0, 10, (B,))) for _ in range(n_batches)]
+    sd0 = {n: {k: v.clone() for k, v in m.state_dict().items()} for n, m in (("netC", netC), ("netG", netG), ("clean", clean))}
+    rec = Recorder(netC, netG, clean, netF)
+    with rec:
+        ti.train(netC, optC, schC, netG, optG, schG, netF, clean, batches, batches2, None, None, NullWriter(), 1, opt)
+    torch.autograd.set_detect_anomaly(False)
+    out = {"seed": seed, "B": B, "n_batches": n_batches, "sigmas": np.array(rec.sigmas), "lr_G": optG.param_groups[0]["lr"]}
+    out["loss_kinds"] = np.array([k for k, _ in rec.losses])
+    out["loss_values"] = np.array([v for _, v in rec.losses])
+    assert len(rec.calls["netG"]) == 3 * n_batches and len(rec.calls["netC"]) == 4 * n_batches
+    for i, (x, y) in enumerate(batches):
+        out["y_%d" % i] = y
+        g_sel_in, _, _ = rec.calls["netG"][3 * i]
+        _, g_all_out, _ = rec.calls["netG"][3 * i + 1]
+        g2_in, g2_out, _ = rec.calls["netG"][3 * i + 2]
+        assert torch.equal(g2_in, batches2[i][0])
+        idx = [int((x == r).flatten(1).all(1).nonzero()[0, 0]) for r in g_sel_in]
+        out["poison_idx_%d" % i] = np.array(idx, dtype=np.int64)
+        out["num_bd_%d" % i] = len(idx)
+        c_tot_in, c_tot_out, c_tr = rec.calls["netC"][4 * i]
+        _, c_cl_out, _ = rec.calls["netC"][4 * i + 1]
+        c_x_in, c_x_out, _ = rec.calls["netC"][4 * i + 2]
+        c_bd_in, c_bd_out, _ = rec.calls["netC"][4 * i + 3]
+        assert c_tr
+        perm = [int((x == r).flatten(1).all(1).nonzero()[0, 0]) if (x == r).flatten(1).all(1).any() else -1 for r in c_tot_in]
+        out["total_perm_%d" % i] = np.array(perm, dtype=np.int64)
+        out["logits_c_%d" % i] = c_tot_out
+        out["pred_clean_%d" % i] = c_cl_out
+        out["pred_cross_%d" % i] = c_x_out
+        out["pred_bd_%d" % i] = c_bd_out
+        out["clean_preds_%d" % i] = rec.calls["clean"][2 * i][1]
+        out["clean_model_preds_%d" % i] = rec.calls["clean"][2 * i + 1][1]
+        out["pred_F_%d" % i] = rec.calls["netF"][i][1]
+        out["x_bd_head_%d" % i] = c_bd_in[:4]
+        out["x_bd2_head_%d" % i] = c_x_in[:4]
+        out["x_bd2_digest_%d" % i] = tensor_digest(c_x_in)
+        out["noise_head_%d" % i] = g_all_out[:4]
+        out["noise2_head_%d" % i] = g2_out[:4]
+        out["x_bd_c_%d" % i] = c_tot_in[: len(idx)]
+    param_summary("netC_", sd0["netC"], netC.state_dict(), out, full_keys=("conv1.weight", "linear.weight", "linear.bias", "layer1.0.bn1.running_mean", "layer1.0.bn1.running_var", "layer3.1.bn2.weight"))
+    param_summary("netG_", sd0["netG"], netG.state_dict(), out, full_keys=("conv0_0.weight", "conv0_0.bias", "upconv0_0.weight", "upconv0_0.bias", "conv3_1.bias"))
+    param_summary("clean_", sd0["clean"], clean.state_dict(), out)
+    save(name, **out)
+
+
 def gen_mstep(name, dataset, B, n_batches, seed):
     """One or more iterations of the UNMODIFIED train_generator_multilabel.train() (reference :142-318).
     cifar10: models from the reference's own get_model; celeba: get_model passes an unknown keyword to CUnetGeneratorv1
@@ -372,6 +434,8 @@ if __name__ == "__main__":
     if "variants" in which:
         from oracle.ref_loader import load_reference_imperceptible
         gen_step("step_imperceptible_b32x2.npz", 32, 2, 11, mod=load_reference_imperceptible())   # + tv_weight * TV(x_bd).mean()
+    if "inputaware" in which:
+        gen_step_inputaware("step_inputaware_b32x2.npz", 32, 2, 13)   # second loader + cross-trigger loss
 
 
 def gen_api():

@@ -109,6 +109,61 @@ def test_imperceptible_train_reproduces_the_reference_fixture(golden):
     assert O.total_variation(torch.zeros(1, 3, 4, 4)).shape == (1,)
 
 
+def test_inputaware_train_and_eval_reproduce_the_reference_fixture(golden, tmp_path):
+    """train_generator_inputaware.{get_model, train, eval} through the public API against two iterations of the UNMODIFIED
+    reference variant (tests/golden/step_inputaware_b32x2.npz): lr_G = 0.1 * lr_C, the RNG stream incl. the extra sigma, the
+    summed losses, per-tensor two-iteration updates, the "Cross" scalar; then eval() writes the variant's checkpoint keys."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from combat_b200 import train_generator_inputaware as ti
+    g = golden("step_inputaware_b32x2.npz")
+    seed, B, nb = int(g["seed"]), int(g["B"]), int(g["n_batches"])
+    opt = _opt(["--dtype", "fp32", "--no_graph", "--log_every", "1"])
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    random.seed(seed)
+    netC, optC, schC, netG, optG, schG, netF, clean = ti.get_model(opt)
+    assert abs(optG.param_groups[0]["lr"] - float(g["lr_G"])) < 1e-12
+    batches = [(torch.rand(B, 3, 32, 32) * 2 - 1, torch.randint(0, 10, (B,))) for _ in range(nb)]
+    batches2 = [(torch.rand(B, 3, 32, 32) * 2 - 1, torch.randint(0, 10, (B,))) for _ in range(nb)]
+    for i in range(nb):
+        assert np.array_equal(batches[i][1].numpy(), g["y_%d" % i])
+    sd0 = {n: {k: v.detach().clone().cpu() for k, v in m.state_dict().items()} for n, m in (("netC_", netC), ("netG_", netG))}
+    w = _Writer()
+    ti.train(netC, optC, schC, netG, optG, schG, netF, clean, batches, batches2, None, None, w, 1, opt)
+    torch.cuda.synchronize()
+    sc = w.scalars[0][1]
+    assert "Cross" in sc and "Grad L2 Loss" not in sc
+    vals = g["loss_values"]           # per iteration: ce(C), ce(bd), ce(cross), mse, ce(clean)
+    per = len(vals) // nb
+    assert per == 5
+    l2 = vals[3] + vals[per + 3]
+    assert abs(sc["L2 Loss"] * B * nb - l2) < 1e-4 * l2
+    cm = vals[4] + vals[per + 4]
+    assert abs(sc["CleanModel Loss"] * B * nb - cm) < 1e-3 * cm
+    n_cross = sum(int((np.argmax(g["pred_cross_%d" % i], 1) == g["y_%d" % i]).sum()) for i in range(nb))
+    assert abs(sc["Cross"] - n_cross * 100.0 / (B * nb)) < 100.0 / (B * nb) + 1e-9   # at most one near-tied argmax in iteration 2
+    for pre, mod in (("netC_", netC), ("netG_", netG)):
+        sd = mod.state_dict()
+        for n, v0 in sd0[pre].items():
+            if not torch.is_floating_point(v0) or (pre + "dnorm_" + n) not in g.files:
+                continue
+            if pre == "netG_" and n.endswith("bias") and n not in ("conv0_0.bias", "upconv0_0.bias"):
+                continue
+            d = float((sd[n].detach().cpu() - v0).double().norm())
+            ref = g[pre + "dnorm_" + n][0]
+            assert abs(d - ref) <= 3e-2 * ref + 1e-12, (pre, n, d, ref)
+    # eval(): seven bests in the reference's order, checkpoint dict with best_cross_acc / mask / pattern
+    opt.ckpt_path = str(tmp_path / "ia.pth.tar")
+    mask, pattern = torch.zeros(32, 32, device="cuda"), torch.rand(3, 32, 32, device="cuda")
+    bests = ti.eval(netC, optC, schC, netG, optG, schG, netF, clean, batches, batches2, mask, pattern, -1.0, 0.0, 0.0, 0.0, 0.0, 0.0,
+                    0.0, w, 1, opt)
+    assert len(bests) == 7
+    ck = torch.load(opt.ckpt_path, map_location="cpu", weights_only=False)
+    assert {"best_cross_acc", "mask", "pattern", "netC", "netG", "clean_model", "optimizerG", "epoch_current"} <= set(ck)
+    assert abs(float(ck["best_cross_acc"]) - float(bests[2])) < 1e-9
+
+
 def test_modules_autograd_and_state_dict_roundtrip():
     if not torch.cuda.is_available():
         pytest.skip("needs a GPU")

@@ -53,6 +53,40 @@ def test_eval_step_vs_oracle(dtype, use_graph):
             assert rel(d["preds_bd"][nt], r["preds_bd"]) < tol and rel(d["cm_bd"][nt], r["cm_bd"]) < tol
 
 
+@pytest.mark.parametrize("use_graph", [False, True], ids=["eager", "graph"])
+def test_inputaware_eval_step_vs_oracle(use_graph):
+    """train_generator_inputaware.py:376-413: the base evaluation + the cross-trigger accuracy (trigger of the second loader's
+    rows on this batch, its own sigma draw, non-target rows against their TRUE labels)."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from combat_b200.engine import AlternatedStep
+    st = O.init_step_state(8)
+    opt = O.default_opt(variant="inputaware")
+    eng = AlternatedStep(opt=opt, device="cuda", dtype=torch.float32)
+    j = lambda p, b: {**p, **b}
+    eng.load_state(netC=j(st["netC_p"], st["netC_b"]), clean=j(st["clean_p"], st["clean_b"]), netG=st["netG_p"],
+                   netF=j(st["netF_p"], st["netF_b"]))
+    g = torch.Generator().manual_seed(4)
+    for it in range(3):
+        x = torch.rand(40, 3, 32, 32, generator=g) * 2 - 1
+        x2 = torch.rand(40, 3, 32, 32, generator=g) * 2 - 1
+        y = torch.randint(0, 10, (40,), generator=g)
+        torch.manual_seed(50 + it)
+        r = O.eval_batch(st, x, y, opt, x2=x2)
+        torch.manual_seed(50 + it)
+        out = eng.eval_step(x.cuda(), y.numpy(), use_graph=use_graph, x2=x2.cuda())
+        c = out["counts"].cpu().numpy()
+        assert out["sigma"] == r["sigma"] and out["sigma2"] == r["sigma2"] and out["n_bd"] == r["n_bd"]
+        got = dict(clean_correct=c[0], bd_correct=c[2], cross_correct=c[12], F_correct=c[4], cm_correct=c[6], cm_bd_ba=c[8], cm_bd_asr=c[9])
+        for k, v in got.items():
+            assert int(v) == r[k], (it, k, int(v), r[k])
+        if out["debug"] is not None:
+            d = out["debug"]
+            assert rel(d["x_bd2"], r["x_bd2"]) < 1e-5 and rel(d["preds_cross"], r["preds_cross"]) < 2e-4
+    with pytest.raises(ValueError):
+        eng.eval_step(x.cuda(), y.numpy())   # the second batch is not optional in this variant
+
+
 def test_eval_api_reproduces_the_reference_fixture(golden, tmp_path):
     if not torch.cuda.is_available():
         pytest.skip("needs a GPU")

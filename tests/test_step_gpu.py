@@ -130,6 +130,71 @@ def test_two_iterations_vs_oracle(name, dtype, variant):
             assert rel2(eng.netC.state_dict()[n], state["netC_b"][n]) < 3e-2
 
 
+@pytest.mark.parametrize("tf", ["no_use", "use"])
+@pytest.mark.parametrize("name,dtype,use_graph", [("fp32", torch.float32, False), ("fp32", torch.float32, True),
+                                                  ("bf16", torch.bfloat16, False)])
+def test_inputaware_iterations_vs_oracle(name, dtype, use_graph, tf):
+    """The step of train_generator_inputaware.py (second loader, cross-trigger loss): two eager / three graph-replayed iterations
+    against the oracle restatement (itself pinned to the unmodified reference variant, tests/golden/step_inputaware_b32x2.npz).
+    Integer decisions and RNG draws bit-exact (incl. the extra sigma and the extra transform), float32 forward tensors 1e-4,
+    losses 2e-5, per-net update 2e-2; bf16: the bars of test_two_iterations_vs_oracle."""
+    from combat_b200.engine import AlternatedStep, make_plan
+    B = 32
+    state = seeded_state(23)
+    opt = O.default_opt(variant="inputaware", post_transform_option=tf)
+    opt.lr_G = opt.lr_C * 0.1
+    eng = make_engine(state, dtype, opt=opt)
+    eng.set_lr(opt.lr_C, opt.lr_G)
+    assert eng.inputaware and eng.cross_weight == 0.2
+    before = {k: {n: v.clone() for n, v in state[k].items()} for k in ("netC_p", "netG_p")}
+    n_it = 3 if use_graph else 2
+    batches = [(torch.rand(B, 3, 32, 32) * 2 - 1, torch.randint(0, 10, (B,)), torch.rand(B, 3, 32, 32) * 2 - 1) for _ in range(n_it)]
+
+    def seed():
+        np.random.seed(6)
+        torch.manual_seed(6)
+        random.seed(6)
+
+    seed()
+    refs = [O.alternated_step(state, x, y, opt, x2=x2) for x, y, x2 in batches]
+    seed()
+    fp32 = name == "fp32"
+    for it, ((x, y, x2), r) in enumerate(zip(batches, refs)):
+        plan = make_plan(y.numpy(), eng.opt)
+        assert plan.num_bd == r["num_bd"] and plan.sigma_c == r["sigma_c"]
+        assert plan.sigma_g == r["sigma_g"] and plan.sigma_g2 == r["sigma_g2"]
+        if tf == "use":   # call order T1, T2, T3, T6 (inputs_bd2), T4, T5 -> storage slots 0, 3, 1, 5, 2, 4
+            assert len(r["tf"]) == 6 and plan.tf.shape[0] == 6
+            for slot, call in ((0, 0), (3, 1), (1, 2), (5, 3), (2, 4), (4, 5)):
+                prm = r["tf"][call]
+                assert np.array_equal(plan.tf[slot][:, 0], (prm["xs"] - prm["pad"]).numpy().astype(np.float32))
+                assert np.array_equal(plan.tf[slot][:, 5] != 0, prm["flip"].numpy())
+        out = eng.step(x.cuda(), y.numpy(), plan, use_graph=use_graph, keep_debug=not use_graph, x2=x2.cuda())
+        s = AlternatedStep.unpack(out)
+        ltol = (2e-5 if it == 0 else 2e-3) if fp32 else 1e-2
+        for k in ("loss_c", "loss_ce", "loss_cross", "loss_l2", "clean_model_loss"):
+            assert abs(s[k] - r[k]) < ltol * max(1.0, abs(r[k])), (it, k, s[k], r[k])
+        if not use_graph:
+            d = out["debug"]
+            keys = ("x_bd", "x_bd2", "logits_c", "pred_bd", "pred_cross", "clean_model_preds", "clean_preds", "pred_clean")
+            for k in keys:
+                if fp32:
+                    assert rel(d[k], r[k]) < (1e-4 if it == 0 else 3e-3), (it, k, rel(d[k], r[k]))
+                else:
+                    assert rel2(d[k], r[k]) < 5e-2, (it, k, rel2(d[k], r[k]))
+            if fp32 and it == 0:
+                for k in ("n_clean_correct", "n_bd_correct", "n_cross_correct", "n_clean_model_correct", "n_clean_model_bd_ba",
+                          "n_clean_model_bd_asr"):
+                    assert s[k] == r[k], k
+    eC, cC = net_delta(before["netC_p"], state["netC_p"], eng.netC.state_dict())
+    eG, cG = net_delta(before["netG_p"], state["netG_p"], eng.netG.state_dict(), skip_dead=True)
+    print("inputaware update: netC L2 err %.3e cos %.5f | netG L2 err %.3e cos %.5f" % (eC, cC, eG, cG))
+    if fp32:
+        assert eC < 2e-2 and eG < 2e-2, (eC, eG)
+    else:
+        assert cC > 0.9 and cG > 0.9, (cC, cG)
+
+
 def test_known_answer_vector_from_reference(golden):
     """seed 0, B=128 -- poison idx [5,17,30]; losses, logits and one-step updates recorded from the
     unmodified reference train()."""

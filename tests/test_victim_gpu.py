@@ -105,3 +105,40 @@ def test_victim_and_clean_trainers_public_api(tmp_path, capsys):
     p0 = next(iter(netC.parameters()))
     assert float(optC.state[p0]["momentum_buffer"].abs().sum()) > 0
     assert int(netC.state_dict()["layer1.0.bn1.num_batches_tracked"]) == 4
+
+
+def test_inputaware_victim_eval_vs_oracle_and_public_main(tmp_path, capsys):
+    """train_victim_inputaware.py: eval_batch (clean / attack / cross-trigger accuracy, two sigma draws) against the oracle
+    restatement of :187-223, then main() on synthetic data (three loaders, seven-key checkpoint dict)."""
+    from combat_b200 import config
+    from combat_b200 import train_victim_inputaware as tvi
+    opt = config.get_arguments().parse_args(["--device", "cuda", "--dtype", "fp32"])
+    opt.input_height = opt.input_width = 32
+    opt.input_channel = 3
+    _seed(4)
+    netC, optC, schC, netG = tvi.get_model(opt)
+    sdC = {k: v.detach().cpu().clone() for k, v in netC.state_dict().items()}
+    sdG = {k: v.detach().cpu().clone() for k, v in netG.state_dict().items()}
+    netC_p, netC_b = O.split_state(sdC)
+    o = O.default_opt()
+    g = torch.Generator().manual_seed(9)
+    for it in range(2):
+        x = torch.rand(24, 3, 32, 32, generator=g) * 2 - 1
+        x2 = torch.rand(24, 3, 32, 32, generator=g) * 2 - 1
+        y = torch.randint(0, 10, (24,), generator=g)
+        torch.manual_seed(70 + it)
+        r = O.victim_eval_batch(netC_p, netC_b, sdG, x, y, o, x2=x2)
+        torch.manual_seed(70 + it)
+        counts, nb, d = tvi.eval_batch(netC, netG, x, x2, y, tvi._variant(opt))
+        c = counts.cpu().numpy()
+        assert d["sigma"] == r["sigma"] and d["sigma2"] == r["sigma2"] and nb == r["n_bd"]
+        assert int(c[0]) == r["clean_correct"] and int(c[2]) == r["bd_asr"] and int(c[4]) == r["cross_correct"]
+        nt = r["ntrg"].cuda()
+        assert rel(d["x_bd"][nt], r["x_bd"]) < 1e-5 and rel(d["x_bd2"], r["x_bd2"]) < 1e-5
+        assert rel(d["preds_cross"], r["preds_cross"]) < 2e-4 and rel(d["preds_bd"][nt], r["preds_bd"]) < 2e-4
+    args = ["--synthetic_data", "--debug", "--bs", "32", "--n_iters", "1", "--log_every", "4", "--saving_prefix", "vi",
+            "--checkpoints", str(tmp_path), "--load_checkpoint", "none"]
+    _seed(0)
+    best = tvi.main(args)
+    out = capsys.readouterr().out
+    assert "Cross Acc" in out and len(best) == 3
