@@ -156,7 +156,10 @@ def test_inputaware_iterations_vs_oracle(name, dtype, use_graph, tf):
         random.seed(6)
 
     seed()
-    refs = [O.alternated_step(state, x, y, opt, x2=x2) for x, y, x2 in batches]
+    refs, snaps = [], []
+    for x, y, x2 in batches:
+        refs.append(O.alternated_step(state, x, y, opt, x2=x2))
+        snaps.append({k: {n: v.clone() for n, v in state[k].items()} for k in ("netC_p", "netG_p")})
     seed()
     fp32 = name == "fp32"
     for it, ((x, y, x2), r) in enumerate(zip(batches, refs)):
@@ -186,13 +189,17 @@ def test_inputaware_iterations_vs_oracle(name, dtype, use_graph, tf):
                 for k in ("n_clean_correct", "n_bd_correct", "n_cross_correct", "n_clean_model_correct", "n_clean_model_bd_ba",
                           "n_clean_model_bd_asr"):
                     assert s[k] == r[k], k
-    eC, cC = net_delta(before["netC_p"], state["netC_p"], eng.netC.state_dict())
-    eG, cG = net_delta(before["netG_p"], state["netG_p"], eng.netG.state_dict(), skip_dead=True)
-    print("inputaware update: netC L2 err %.3e cos %.5f | netG L2 err %.3e cos %.5f" % (eC, cC, eG, cG))
-    if fp32:
-        assert eC < 2e-2 and eG < 2e-2, (eC, eG)
-    else:
-        assert cC > 0.9 and cG > 0.9, (cC, cG)
+        # cumulative parameter update after this iteration, whole net, device vs oracle.  The FIRST iteration is the gradient check
+        # (both generator batches, the cross leg and its transform adjoint feed it): 1e-2; later iterations inherit the first
+        # one's rounding noise through random-init networks (the reference differs from itself by 6e-3 there, see the header)
+        eC, cC = net_delta(before["netC_p"], snaps[it]["netC_p"], eng.netC.state_dict())
+        eG, cG = net_delta(before["netG_p"], snaps[it]["netG_p"], eng.netG.state_dict(), skip_dead=True)
+        print("inputaware update after iteration %d: netC L2 err %.3e cos %.5f | netG L2 err %.3e cos %.5f" % (it + 1, eC, cC, eG, cG))
+        if fp32:
+            bar = 1e-2 if it == 0 else 8e-2
+            assert eC < bar and eG < bar, (it, eC, eG)
+        else:
+            assert cC > 0.9 and cG > 0.9, (it, cC, cG)
 
 
 def test_known_answer_vector_from_reference(golden):
