@@ -342,6 +342,128 @@ def unet_forward(p: dict, x: torch.Tensor, y: torch.Tensor | None = None, num_cl
     return torch.tanh(conv("upconv0_0", u0))
 
 
+def grid_generator_forward(p: dict, x: torch.Tensor, S: int) -> torch.Tensor:
+    """GridGenerator.forward (networks/models.py:372-385): the encoder half of UnetGenerator (same in-place LeakyReLU rule, same
+    InstanceNorm), global average pool, fc1 -> LeakyReLU -> fc2 -> reshape (-1, 2, S, S) -> tanh: the S x S control grid of a flow."""
+    def act(t):
+        return F.leaky_relu(t, 0.2)
+
+    def conv(name, t, stride=1):
+        return cj(F.conv2d(t, qw(p[name + ".weight"]), p[name + ".bias"], stride=stride, padding=1))
+
+    def inorm(t):
+        return F.instance_norm(qg(t), eps=1e-5)
+
+    f0 = qa(conv("conv0_0", x, 2))
+    f0 = qa(act(inorm(conv("conv0_1", qa(act(f0))))))
+    f1 = qa(act(inorm(conv("conv1_0", f0, 2))))
+    f1 = qa(act(inorm(conv("conv1_1", f1))))
+    f2 = qa(act(inorm(conv("conv2_0", f1, 2))))
+    f2 = qa(act(inorm(conv("conv2_1", f2))))
+    f3 = qa(act(inorm(conv("conv3_0", f2, 2))))
+    f3 = qa(inorm(conv("conv3_1", f3)))
+    f = F.adaptive_avg_pool2d(f3, 1).flatten(1)   # `.squeeze()` at :381 (also drops a batch of one; restored by the reshape at :383)
+    f = F.linear(f, p["fc1.weight"], p["fc1.bias"])
+    f = F.linear(act(f), p["fc2.weight"], p["fc2.bias"]).reshape((-1, 2, S, S))
+    return torch.tanh(f)
+
+
+def identity_grid(H: int) -> torch.Tensor:
+    """train_generator_wanet.py:560-562: linspace(-1, 1, H) mesh, [..., 0] = column (x) coordinate, [..., 1] = row (y)."""
+    a = torch.linspace(-1, 1, steps=H)
+    xx, yy = torch.meshgrid(a, a, indexing="ij")
+    return torch.stack((yy, xx), 2)[None, ...]
+
+
+def wanet_warp(x: torch.Tensor, flow: torch.Tensor, opt):
+    """train_generator_wanet.py:152-158 / :197-203: bicubic (align_corners) upsampling of the S x S control grid to the image size,
+    blend with the identity grid by grid_rescale, clamp, bilinear `grid_sample` (zeros padding, align_corners).
+    Returns (inputs_bd, noise_grid [N, H, W, 2])."""
+    H = opt.input_height
+    noise_grid = F.interpolate(flow, size=H, mode="bicubic", align_corners=True).permute((0, 2, 3, 1))
+    grid = torch.clamp(identity_grid(H) * (1 - opt.grid_rescale) + noise_grid * opt.grid_rescale, -1, 1)
+    return F.grid_sample(x, grid, align_corners=True), noise_grid
+
+
+def wanet_grad_l2(noise_grid: torch.Tensor) -> torch.Tensor:
+    """the logged-only "gradient loss" of train_generator_wanet.py:213-222 (finite differences of the zero-padded noise grid)."""
+    e, z = F.pad(noise_grid, (1, 1, 2, 1)), F.pad(noise_grid * 0, (1, 1, 2, 1))
+    return (F.mse_loss(e[:, :, 1:] - e[:, :, :-1], z[:, :, 1:] - z[:, :, :-1])
+            + F.mse_loss(e[:, :, :, 1:] - e[:, :, :, :-1], z[:, :, :, 1:] - z[:, :, :, :-1]))
+
+
+def alternated_step_wanet(state: dict, x: torch.Tensor, y: torch.Tensor, opt, with_metrics: bool = True) -> dict:
+    """One iteration of train_generator_wanet.train() (:133-234): the alternated step with a WARP trigger -- netG is a
+    GridGenerator, inputs_bd = grid_sample(inputs, clamp(identity * (1 - grid_rescale) + bicubic(netG(inputs)) * grid_rescale)) --
+    no DCT low-pass, no blur (hence no sigma draws), loss_l2 = MSE(noise_grid, 0).
+    RNG order: numpy rand(n_trg), then the PostTensorTransform calls T1, T2, T3, T4, T5.
+    The reference raises for num_bd == 0 (`reshape((-1, 2, S, S))` of an empty tensor, models.py:383); here no row is poisoned."""
+    fwdC = CLASSIFIERS[opt.classifier]
+    netC_p, netC_b, netG_p = state["netC_p"], state["netC_b"], state["netG_p"]
+    clean_p, clean_b = state["clean_p"], state["clean_b"]
+    out = {}
+    bd_targets = create_targets_bd(y, opt.attack_mode, opt.target_label, opt.num_classes)
+    trg_ind, ntrg_ind, num_bd = select_poison(y, bd_targets, opt.pc)
+    out["trg_ind"], out["ntrg_ind"], out["num_bd"] = trg_ind.clone(), ntrg_ind.clone(), num_bd
+    x_sel = x[trg_ind[:num_bd]]
+    for t in netC_p.values():
+        t.requires_grad_(True)
+        t.grad = None
+    with torch.no_grad():
+        x_bd_c = wanet_warp(x_sel, grid_generator_forward(netG_p, x_sel, opt.s), opt)[0] if num_bd > 0 else x_sel
+    total_x = torch.cat([x_bd_c, x[trg_ind[num_bd:]], x[ntrg_ind]], dim=0)
+    total_y = torch.cat([bd_targets[trg_ind[:num_bd]], y[trg_ind[num_bd:]], y[ntrg_ind]], dim=0)
+    out["tf"] = tf_log = []
+    total_x = post_transform(total_x, opt, tf_log)  # :161
+    logits_c = fwdC(netC_p, netC_b, total_x, True)
+    loss_c = F.cross_entropy(logits_c, total_y)
+    loss_c.backward()
+    out["total_x"], out["total_y"] = total_x.detach(), total_y
+    out["logits_c"], out["loss_c"] = logits_c.detach().clone(), float(loss_c.detach())
+    gradsC = {k: v.grad for k, v in netC_p.items()}
+    with torch.no_grad():
+        for t in netC_p.values():
+            t.requires_grad_(False)
+        sgd_nesterov_step(netC_p, gradsC, state["momC"], opt.lr_C)
+        out["clean_preds"] = fwdC(clean_p, clean_b, post_transform(x, opt, tf_log), False)  # :184
+    for t in netG_p.values():
+        t.requires_grad_(True)
+        t.grad = None
+    flow = grid_generator_forward(netG_p, x, opt.s)  # :196
+    x_bd, noise_grid = wanet_warp(x, flow, opt)
+    with torch.no_grad():
+        out["pred_clean"] = fwdC(netC_p, netC_b, post_transform(x, opt, tf_log), False)  # :205
+    pred_bd = fwdC(netC_p, netC_b, post_transform(x_bd, opt, tf_log), False)  # :206
+    loss_ce = F.cross_entropy(pred_bd, bd_targets)
+    loss_l2 = F.mse_loss(noise_grid, noise_grid * 0)  # :212
+    out["loss_grad_l2"] = float(wanet_grad_l2(noise_grid.detach()))
+    clean_model_preds = fwdC(clean_p, clean_b, post_transform(x_bd, opt, tf_log), False)  # :229
+    clean_model_loss = F.cross_entropy(clean_model_preds, y)
+    loss = loss_ce + opt.L2_weight * loss_l2 + opt.clean_model_weight * clean_model_loss  # :235
+    loss.backward()
+    gradsG = {k: v.grad for k, v in netG_p.items()}
+    out["gradsG"] = {k: g.clone() for k, g in gradsG.items()}
+    with torch.no_grad():
+        for t in netG_p.values():
+            t.requires_grad_(False)
+        sgd_nesterov_step(netG_p, gradsG, state["momG"], opt.lr_G)
+        if with_metrics and state.get("netF_p") is not None:
+            inputs_F = dct_2d(((x_bd.detach() + 1) / 2 * 255).byte())  # :224
+            out["inputs_F"] = inputs_F
+            out["pred_F"] = frequency_model_forward(state["netF_p"], state["netF_b"], inputs_F)
+    am = lambda t: torch.argmax(t, dim=1)
+    out.update(x_bd=x_bd.detach(), flow=flow.detach(), noise_grid=noise_grid.detach(), pred_bd=pred_bd.detach(),
+               clean_model_preds=clean_model_preds.detach(), loss_ce=float(loss_ce), loss_l2=float(loss_l2),
+               clean_model_loss=float(clean_model_loss), loss_g=float(loss), bd_targets=bd_targets,
+               n_clean_correct=int((am(out["pred_clean"]) == y).sum()), n_bd_correct=int((am(pred_bd) == bd_targets).sum()),
+               n_clean_model_correct=int((am(out["clean_preds"]) == y).sum()),
+               n_clean_model_bd_ba=int((am(clean_model_preds) == y).sum()),
+               n_clean_model_bd_asr=int((am(clean_model_preds) == bd_targets).sum()))
+    if "pred_F" in out:
+        out["n_F_correct"] = int((am(out["pred_F"]) == 1).sum())
+    return out
+
+
 def _bn(p, b, name, x, training, momentum=0.1, eps=1e-5):
     """nn.BatchNorm2d: batch stats + running update (train) or running stats (eval)."""
     rm, rv = b[name + ".running_mean"], b[name + ".running_var"]
@@ -551,6 +673,7 @@ def default_opt(**kw):
         L2_weight=0.02, clean_model_weight=0.8, lr_C=1e-2, lr_G=1e-2, classifier="preact_resnet18",
         post_transform_option="no_use", random_crop=5, random_rotation=10, dataset="cifar10",
         variant="", tv_weight=0.01,   # variant "imperceptible": train_generator_imperceptible.py (+ tv_weight * TV(x_bd).mean())
+        s=2, grid_rescale=0.15,       # variant "wanet": train_generator_wanet.py (GridGenerator control grid size, flow strength)
         cross_weight=0.2,             # variant "inputaware": train_generator_inputaware.py (+ cross_weight * CE(netC(x + G(x2)), y))
     )
     for k, v in kw.items():
@@ -963,6 +1086,18 @@ def init_unet_state(gen, in_ch=3, nf=64, num_classes=0):
     for name, ci, co in spec:
         w, bb = _conv_init(co, ci, 3, True, gen)
         p[name + ".weight"], p[name + ".bias"] = w, bb
+    return p
+
+
+def init_grid_generator_state(gen, in_ch=3, nf=64, S=2):
+    """Parameter shapes and construction order of GridGenerator (networks/models.py:344-370)."""
+    spec = [("conv0_0", in_ch, nf), ("conv0_1", nf, nf), ("conv1_0", nf, nf * 2), ("conv1_1", nf * 2, nf * 2),
+            ("conv2_0", nf * 2, nf * 4), ("conv2_1", nf * 4, nf * 4), ("conv3_0", nf * 4, nf * 8), ("conv3_1", nf * 8, nf * 8)]
+    p = {}
+    for name, ci, co in spec:
+        p[name + ".weight"], p[name + ".bias"] = _conv_init(co, ci, 3, True, gen)
+    p["fc1.weight"], p["fc1.bias"] = _linear_init(nf, nf * 8, gen)
+    p["fc2.weight"], p["fc2.bias"] = _linear_init(S * S * 2, nf, gen)
     return p
 
 
