@@ -88,6 +88,14 @@ def load_reference_inputaware(ref: str = REF):
     return train_generator_inputaware
 
 
+def load_reference_wanet(ref: str = REF):
+    """train_generator_wanet.py of the reference (same stand-ins)."""
+    load_reference(ref)
+    import train_generator_wanet
+
+    return train_generator_wanet
+
+
 class NullWriter:
     """tf_writer stand-in for train()."""
 

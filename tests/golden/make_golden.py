@@ -324,6 +324,64 @@ def gen_step_inputaware(name, B, n_batches, seed):
     save(name, **out)
 
 
+def gen_step_wanet(name, B, n_batches, seed):
+    """Iterations of the UNMODIFIED train_generator_wanet.train() (:92-300): GridGenerator, bicubic flow, grid_sample warp.
+    Per iteration: netG 2x (C-step subset, x), netC 3x, clean_model 2x, netF 1x; losses in call order ce(C), ce(bd), mse (noise
+    grid), mse, mse (logged gradient pair), ce(clean model).  No blur: no sigma draws.  The reference raises when an iteration
+    poisons no row (reshape of an empty tensor, models.py:383): the seed is chosen so that every iteration has num_bd > 0."""
+    import tempfile
+    from oracle.ref_loader import load_reference_wanet
+    tw = load_reference_wanet()
+    opt = get_opt()
+    opt.input_height = opt.input_width = 32
+    opt.input_channel = 3
+    os.chdir(tempfile.mkdtemp())
+    seed_all(seed)
+    netC, optC, schC, netG, optG, schG, netF, clean = tw.get_model(opt)
+    netF.eval()
+    clean.eval()
+    batches = [(torch.rand(B, 3, 32, 32) * 2 - 1, torch.randint(0, 10, (B,))) for _ in range(n_batches)]
+    sd0 = {n: {k: v.clone() for k, v in m.state_dict().items()} for n, m in (("netC", netC), ("netG", netG), ("clean", clean))}
+    a = torch.linspace(-1, 1, steps=opt.input_height)   # :560-562
+    gx, gy = torch.meshgrid(a, a)
+    ident = torch.stack((gy, gx), 2)[None, ...]
+    rec = Recorder(netC, netG, clean, netF)
+    with rec:
+        tw.train(netC, optC, schC, netG, optG, schG, netF, clean, batches, ident, NullWriter(), 1, opt)
+    torch.autograd.set_detect_anomaly(False)
+    out = {"seed": seed, "B": B, "n_batches": n_batches, "lr_G": optG.param_groups[0]["lr"], "s": opt.s,
+           "grid_rescale": opt.grid_rescale}
+    out["loss_kinds"] = np.array([k for k, _ in rec.losses])
+    out["loss_values"] = np.array([v for _, v in rec.losses])
+    assert len(rec.calls["netG"]) == 2 * n_batches and len(rec.calls["netC"]) == 3 * n_batches
+    for i, (x, y) in enumerate(batches):
+        out["y_%d" % i] = y
+        g_sel_in, _, _ = rec.calls["netG"][2 * i]
+        _, g_all_out, _ = rec.calls["netG"][2 * i + 1]
+        idx = [int((x == r).flatten(1).all(1).nonzero()[0, 0]) for r in g_sel_in]
+        out["poison_idx_%d" % i] = np.array(idx, dtype=np.int64)
+        out["num_bd_%d" % i] = len(idx)
+        c_tot_in, c_tot_out, c_tr = rec.calls["netC"][3 * i]
+        _, c_cl_out, _ = rec.calls["netC"][3 * i + 1]
+        c_bd_in, c_bd_out, _ = rec.calls["netC"][3 * i + 2]
+        assert c_tr
+        perm = [int((x == r).flatten(1).all(1).nonzero()[0, 0]) if (x == r).flatten(1).all(1).any() else -1 for r in c_tot_in]
+        out["total_perm_%d" % i] = np.array(perm, dtype=np.int64)
+        out["logits_c_%d" % i] = c_tot_out
+        out["pred_clean_%d" % i] = c_cl_out
+        out["pred_bd_%d" % i] = c_bd_out
+        out["clean_preds_%d" % i] = rec.calls["clean"][2 * i][1]
+        out["clean_model_preds_%d" % i] = rec.calls["clean"][2 * i + 1][1]
+        out["pred_F_%d" % i] = rec.calls["netF"][i][1]
+        out["x_bd_head_%d" % i] = c_bd_in[:8]
+        out["x_bd_digest_%d" % i] = tensor_digest(c_bd_in)
+        out["flow_%d" % i] = g_all_out
+        out["x_bd_c_%d" % i] = c_tot_in[: len(idx)]
+    param_summary("netC_", sd0["netC"], netC.state_dict(), out, full_keys=("conv1.weight", "linear.weight", "linear.bias", "layer1.0.bn1.running_mean", "layer1.0.bn1.running_var"))
+    param_summary("netG_", sd0["netG"], netG.state_dict(), out, full_keys=("conv0_0.weight", "conv0_0.bias", "conv3_1.bias", "fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias"))
+    save(name, **out)
+
+
 def gen_mstep(name, dataset, B, n_batches, seed):
     """One or more iterations of the UNMODIFIED train_generator_multilabel.train() (reference :142-318).
     cifar10: models from the reference's own get_model; celeba: get_model passes an unknown keyword to CUnetGeneratorv1
@@ -434,6 +492,8 @@ if __name__ == "__main__":
     if "variants" in which:
         from oracle.ref_loader import load_reference_imperceptible
         gen_step("step_imperceptible_b32x2.npz", 32, 2, 11, mod=load_reference_imperceptible())   # + tv_weight * TV(x_bd).mean()
+    if "wanet" in which:
+        gen_step_wanet("step_wanet_b32x2.npz", 32, 2, int(os.environ.get("WANET_SEED", "17")))
     if "inputaware" in which:
         gen_step_inputaware("step_inputaware_b32x2.npz", 32, 2, 13)   # second loader + cross-trigger loss
 
