@@ -96,6 +96,9 @@ _SIGS = {
     "combat_tv_loss": ([vp, vp, f32, vp, vp, i32, i32, i32, i32, vp], i32),
     "combat_post_transform_fwd": ([vp, vp, vp, i32, i32, i32, i32, vp], i32),
     "combat_post_transform_bwd": ([vp, vp, vp, i32, i32, i32, i32, i32, vp], i32),
+    "combat_tanh_fwd": ([vp, vp, i64, vp], i32),
+    "combat_wanet_warp_fwd": ([vp, vp, vp, vp, i32, i32, vp, f32, vp, vp, vp, vp, i32, i32, i32, i32, vp], i32),
+    "combat_wanet_warp_bwd": ([vp, vp, vp, vp, vp, f32, f32, vp, i32, i32, i32, i32, i32, vp], i32),
     "combat_nchw_to_nhwc": ([vp, vp, i32, i32, i32, i32, i32, vp], i32),
     "combat_nhwc_to_nchw": ([vp, i32, vp, i32, i32, i32, i32, vp], i32),
     "combat_onehot_planes": ([vp, i32, vp, i32, i32, i32, i32, i32, vp], i32),

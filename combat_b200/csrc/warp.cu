@@ -1,0 +1,271 @@
+// WaNet-style warp trigger of train_generator_wanet.py (:151-158 / :196-203 of the reference) as ONE kernel and its backward:
+//   flow       = netG(inputs)                 the GridGenerator's tanh output, [N, 2, S, S]                (networks/models.py:383-385)
+//   noise_grid = bicubic_upsample(flow, H x H, align_corners=True).permute(0, 2, 3, 1)                      (:152-154)
+//   grid       = clamp(identity_grid * (1 - grid_rescale) + noise_grid * grid_rescale, -1, 1)               (:155-156)
+//   inputs_bd  = grid_sample(inputs, grid, bilinear, zeros padding, align_corners=True)                     (:157)
+// plus the batch assembly of the C-step (:159: row i of the output is the warped image of sample perm[i] for i < num_bd and a
+// plain copy of sample perm[i] otherwise), the sum of squares of noise_grid (loss_l2 = MSE(noise_grid, 0), :212) and the
+// logged-only finite-difference term (:213-222).
+//
+// Bicubic upsampling is linear and separable: noise(c, h, w) = sum_{py, px} Wt[py][h] * Wt[px][w] * flow(c, py, px), with
+// Wt[p][o] = sum of the four cubic-convolution coefficients (A = -0.75) of output index o whose clamped source index is p.
+// S is tiny (--s 2: a 2 x 2 control grid), so the table lives in shared memory and a pixel costs S*S multiply-adds per
+// channel; the backward is the same table transposed (per-thread register accumulators, one block reduction, no atomics).
+// Images are NCHW float32 (the reference's tensors), square (identity_grid is built from input_height alone, :560-562).
+// HBM-bound: read + write of one image per row; the gather goes through L1 (a CIFAR image is 12 KB).
+#include "common.cuh"
+
+namespace {
+
+constexpr int WARP_MAX_S = 4;     // 2 * S * S <= 32 accumulators per thread; the reference default is S = 2
+constexpr int WARP_MAX_HW = 256;  // table rows in shared memory
+
+struct WarpShared {
+  float flow[2 * WARP_MAX_S * WARP_MAX_S];
+  float wt[WARP_MAX_S * WARP_MAX_HW];   // wt[p * H + o]
+  float red[32 * 8];
+};
+
+__device__ __forceinline__ void cubic_coeffs(float t, float c[4]) {
+  const float A = -0.75f;
+  const float x0 = t + 1.f, x3 = 2.f - t, u = 1.f - t;
+  c[0] = ((A * x0 - 5.f * A) * x0 + 8.f * A) * x0 - 4.f * A;
+  c[1] = ((A + 2.f) * t - (A + 3.f)) * t * t + 1.f;
+  c[2] = ((A + 2.f) * u - (A + 3.f)) * u * u + 1.f;
+  c[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
+}
+
+// the sample's flow and the separable bicubic table of an S -> H upsampling with align_corners=True
+__device__ __forceinline__ void warp_setup(WarpShared& sh, const float* __restrict__ z, int S, int H) {
+  const int nf = 2 * S * S;
+  if ((int)threadIdx.x < nf) sh.flow[threadIdx.x] = z[threadIdx.x];
+  const float scale = H > 1 ? (float)(S - 1) / (float)(H - 1) : 0.f;
+  for (int o = threadIdx.x; o < H; o += blockDim.x) {
+    const float real = scale * (float)o;
+    const float fl = floorf(real);
+    const int in = (int)fl;
+    float c[4];
+    cubic_coeffs(real - fl, c);
+    float acc[WARP_MAX_S];
+#pragma unroll
+    for (int p = 0; p < WARP_MAX_S; ++p) acc[p] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int p = min(max(in - 1 + i, 0), S - 1);
+#pragma unroll
+      for (int q = 0; q < WARP_MAX_S; ++q)
+        if (q == p) acc[q] += c[i];
+    }
+#pragma unroll
+    for (int p = 0; p < WARP_MAX_S; ++p)
+      if (p < S) sh.wt[p * H + o] = acc[p];
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void noise_at(const WarpShared& sh, int S, int H, int h, int w, float& nx, float& ny) {
+  nx = 0.f;
+  ny = 0.f;
+  const int SS = S * S;
+  for (int py = 0; py < S; ++py) {
+    const float wy = sh.wt[py * H + h];
+    for (int px = 0; px < S; ++px) {
+      const float k = wy * sh.wt[px * H + w];
+      nx = fmaf(k, sh.flow[py * S + px], nx);
+      ny = fmaf(k, sh.flow[SS + py * S + px], ny);
+    }
+  }
+}
+
+struct Bilin {
+  int x0, y0;
+  float wx, wy;   // weight of the x0+1 / y0+1 taps
+};
+
+__device__ __forceinline__ Bilin unnormalise(float gx, float gy, int H, int W) {
+  const float ix = (gx + 1.f) * 0.5f * (float)(W - 1);
+  const float iy = (gy + 1.f) * 0.5f * (float)(H - 1);
+  const float fx = floorf(ix), fy = floorf(iy);
+  Bilin b;
+  b.x0 = (int)fx;
+  b.y0 = (int)fy;
+  b.wx = ix - fx;
+  b.wy = iy - fy;
+  return b;
+}
+
+__device__ __forceinline__ float tap(const float* __restrict__ pl, int x, int y, int H, int W) {
+  return (x >= 0 && x < W && y >= 0 && y < H) ? __ldg(pl + y * W + x) : 0.f;
+}
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+  if (warp == 0) {
+    t = lane < (int)(blockDim.x >> 5) ? red[lane] : 0.f;
+    t = warp_sum(t);
+  }
+  return t;   // valid in warp 0
+}
+
+__global__ void __launch_bounds__(256) wanet_warp_fwd_k(const float* __restrict__ x, const float* __restrict__ z,
+                                                        const float* __restrict__ ident, const int* __restrict__ perm,
+                                                        int num_bd, const int* __restrict__ num_bd_dev, float rescale,
+                                                        float* __restrict__ out, float* __restrict__ noise_grid,
+                                                        float* __restrict__ sq_partial, float* __restrict__ gl_partial, int C,
+                                                        int H, int S) {
+  pdl_entry();
+  __shared__ WarpShared sh;
+  const int row = blockIdx.x;
+  const int W = H, HW = H * H;
+  const int src = perm ? perm[row] : row;
+  const int nbd = num_bd_dev ? *num_bd_dev : num_bd;
+  const float* xs = x + (long long)src * C * HW;
+  float* dst = out + (long long)row * C * HW;
+  if (row >= nbd) {  // pass-through row of the C-step batch (bit-exact copy)
+    for (int i = threadIdx.x; i < C * HW; i += blockDim.x) dst[i] = __ldg(xs + i);
+    return;
+  }
+  warp_setup(sh, z + (long long)src * 2 * S * S, S, H);
+  float sq = 0.f, gl1 = 0.f, gl2 = 0.f;
+  for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+    const int h = p / W, w = p - h * W;
+    float nx, ny;
+    noise_at(sh, S, H, h, w, nx, ny);
+    const float gx = fminf(fmaxf(__ldg(ident + w) * (1.f - rescale) + nx * rescale, -1.f), 1.f);
+    const float gy = fminf(fmaxf(__ldg(ident + h) * (1.f - rescale) + ny * rescale, -1.f), 1.f);
+    const Bilin b = unnormalise(gx, gy, H, W);
+    const float w00 = (1.f - b.wx) * (1.f - b.wy), w01 = b.wx * (1.f - b.wy), w10 = (1.f - b.wx) * b.wy, w11 = b.wx * b.wy;
+    for (int c = 0; c < C; ++c) {
+      const float* pl = xs + c * HW;
+      dst[c * HW + p] = tap(pl, b.x0, b.y0, H, W) * w00 + tap(pl, b.x0 + 1, b.y0, H, W) * w01 +
+                        tap(pl, b.x0, b.y0 + 1, H, W) * w10 + tap(pl, b.x0 + 1, b.y0 + 1, H, W) * w11;
+    }
+    if (noise_grid) *(float2*)(noise_grid + ((long long)row * HW + p) * 2) = make_float2(nx, ny);
+    sq += nx * nx + ny * ny;
+    if (gl_partial) {
+      // :213-222 on F.pad(noise_grid, (1, 1, 2, 1)): differences along the padded W axis ([0, 0, v_0 .. v_{W-1}, 0]) and along
+      // the padded channel axis ([0, nx, ny, 0]); the zero columns contribute nothing
+      float px_ = 0.f, py_ = 0.f;
+      if (w > 0) noise_at(sh, S, H, h, w - 1, px_, py_);
+      gl1 += (nx - px_) * (nx - px_) + (ny - py_) * (ny - py_);
+      if (w == W - 1) gl1 += nx * nx + ny * ny;
+      gl2 += nx * nx + (ny - nx) * (ny - nx) + ny * ny;
+    }
+  }
+  if (sq_partial) {
+    const float t = block_sum(sq, sh.red);
+    if (threadIdx.x == 0) sq_partial[row] = t;
+  }
+  if (gl_partial) {
+    const float t1 = block_sum(gl1, sh.red);
+    const float t2 = block_sum(gl2, sh.red);
+    if (threadIdx.x == 0) gl_partial[row] = t1 / (float)(H * (W + 2) * 4) + t2 / (float)(H * (W + 3) * 3);
+  }
+}
+
+// dz[n] = d loss / d flow[n] for  loss = <g1 + g2, inputs_bd> + (l2_scale / 2) * |noise_grid|^2
+__global__ void __launch_bounds__(256) wanet_warp_bwd_k(const float* __restrict__ x, const float* __restrict__ z,
+                                                        const float* __restrict__ ident, const float* __restrict__ g1,
+                                                        const float* __restrict__ g2, float rescale, float l2_scale,
+                                                        float* __restrict__ dz, int C, int H, int S) {
+  pdl_entry();
+  __shared__ WarpShared sh;
+  const int n = blockIdx.x;
+  const int W = H, HW = H * H, SS = S * S;
+  const float* xs = x + (long long)n * C * HW;
+  warp_setup(sh, z + (long long)n * 2 * SS, S, H);
+  float acc[2 * WARP_MAX_S * WARP_MAX_S];
+#pragma unroll
+  for (int k = 0; k < 2 * WARP_MAX_S * WARP_MAX_S; ++k) acc[k] = 0.f;
+  for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+    const int h = p / W, w = p - h * W;
+    float nx, ny;
+    noise_at(sh, S, H, h, w, nx, ny);
+    const float rx = __ldg(ident + w) * (1.f - rescale) + nx * rescale;
+    const float ry = __ldg(ident + h) * (1.f - rescale) + ny * rescale;
+    const Bilin b = unnormalise(fminf(fmaxf(rx, -1.f), 1.f), fminf(fmaxf(ry, -1.f), 1.f), H, W);
+    float dix = 0.f, diy = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const long long gi = ((long long)n * C + c) * HW + p;
+      float g = __ldg(g1 + gi);
+      if (g2) g += __ldg(g2 + gi);
+      const float* pl = xs + c * HW;
+      const float v00 = tap(pl, b.x0, b.y0, H, W), v01 = tap(pl, b.x0 + 1, b.y0, H, W);
+      const float v10 = tap(pl, b.x0, b.y0 + 1, H, W), v11 = tap(pl, b.x0 + 1, b.y0 + 1, H, W);
+      dix = fmaf(g, (v01 - v00) * (1.f - b.wy) + (v11 - v10) * b.wy, dix);
+      diy = fmaf(g, (v10 - v00) * (1.f - b.wx) + (v11 - v01) * b.wx, diy);
+    }
+    // clamp passes the gradient where -1 <= raw <= 1 (torch.clamp backward), then the blend with the identity grid
+    const float dnx = ((rx >= -1.f && rx <= 1.f) ? dix * 0.5f * (float)(W - 1) * rescale : 0.f) + l2_scale * nx;
+    const float dny = ((ry >= -1.f && ry <= 1.f) ? diy * 0.5f * (float)(H - 1) * rescale : 0.f) + l2_scale * ny;
+#pragma unroll
+    for (int py = 0; py < WARP_MAX_S; ++py) {
+      if (py < S) {
+        const float wy = sh.wt[py * H + h];
+#pragma unroll
+        for (int px = 0; px < WARP_MAX_S; ++px) {
+          if (px < S) {
+            const float k = wy * sh.wt[px * H + w];
+            acc[py * WARP_MAX_S + px] = fmaf(k, dnx, acc[py * WARP_MAX_S + px]);
+            acc[WARP_MAX_S * WARP_MAX_S + py * WARP_MAX_S + px] = fmaf(k, dny, acc[WARP_MAX_S * WARP_MAX_S + py * WARP_MAX_S + px]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+#pragma unroll
+    for (int py = 0; py < WARP_MAX_S; ++py)
+#pragma unroll
+      for (int px = 0; px < WARP_MAX_S; ++px) {
+        if (py < S && px < S) {   // uniform across the block
+          const float t = block_sum(acc[c * WARP_MAX_S * WARP_MAX_S + py * WARP_MAX_S + px], sh.red);
+          if (threadIdx.x == 0) dz[(long long)n * 2 * SS + c * SS + py * S + px] = t;
+        }
+      }
+}
+
+__global__ void __launch_bounds__(256) tanh_fwd_k(const float* __restrict__ x, float* __restrict__ y, long long n) {
+  pdl_entry();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = tanhf(x[i]);
+}
+
+}  // namespace
+
+extern "C" int combat_tanh_fwd(const float* x, float* y, long long n, void* stream) {
+  COMBAT_ARG(x && y && n >= 0, 0);
+  if (n == 0) return 0;
+  pdl_launch(tanh_fwd_k, (int)min((long long)cdiv(n, 256), 1184LL), 256, 0, (cudaStream_t)stream, x, y, n);
+  COMBAT_RETURN_LAUNCH("tanh_fwd");
+}
+
+extern "C" int combat_wanet_warp_fwd(const float* x, const float* z, const float* ident, const int* perm, int rows, int num_bd,
+                                     const int* num_bd_dev, float grid_rescale, float* out, float* noise_grid,
+                                     float* sq_partial, float* gl_partial, int C, int H, int W, int S, void* stream) {
+  COMBAT_ARG(x && z && ident && out && x != out, 0);
+  COMBAT_ARG(rows >= 0 && C > 0 && H > 1 && H == W && H <= WARP_MAX_HW, 4);
+  COMBAT_ARG(S >= 1 && S <= WARP_MAX_S, 15);
+  COMBAT_ARG(perm || !(noise_grid || sq_partial || gl_partial) || num_bd >= rows || num_bd_dev, 5);
+  if (rows == 0) return 0;
+  pdl_launch(wanet_warp_fwd_k, rows, 256, 0, (cudaStream_t)stream, x, z, ident, perm, num_bd, num_bd_dev, grid_rescale, out,
+             noise_grid, sq_partial, gl_partial, C, H, S);
+  COMBAT_RETURN_LAUNCH("wanet_warp_fwd");
+}
+
+extern "C" int combat_wanet_warp_bwd(const float* x, const float* z, const float* ident, const float* g1, const float* g2,
+                                     float grid_rescale, float l2_scale, float* dz, int rows, int C, int H, int W, int S,
+                                     void* stream) {
+  COMBAT_ARG(x && z && ident && g1 && dz, 0);
+  COMBAT_ARG(rows >= 0 && C > 0 && H > 1 && H == W && H <= WARP_MAX_HW, 8);
+  COMBAT_ARG(S >= 1 && S <= WARP_MAX_S, 12);
+  if (rows == 0) return 0;
+  pdl_launch(wanet_warp_bwd_k, rows, 256, 0, (cudaStream_t)stream, x, z, ident, g1, g2, grid_rescale, l2_scale, dz, C, H, S);
+  COMBAT_RETURN_LAUNCH("wanet_warp_bwd");
+}

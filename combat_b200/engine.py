@@ -24,7 +24,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .nets import Classifier, FrequencyDetector, Generator
+from .nets import Classifier, FrequencyDetector, Generator, GridGenerator
 from .utils.dataloader import PARAM_WIDTH as TF_W, draw_params as draw_tf_params
 
 
@@ -78,6 +78,10 @@ def _inputaware(opt) -> bool:
     return getattr(opt, "variant", "") == "inputaware"
 
 
+def _wanet(opt) -> bool:
+    return getattr(opt, "variant", "") == "wanet"
+
+
 def create_targets_bd_np(targets: np.ndarray, opt) -> np.ndarray:
     """train_generator.py:70-77."""
     if opt.attack_mode == "all2one":
@@ -94,13 +98,14 @@ def make_plan(targets_host, opt, with_metrics=True) -> StepPlan:
     y = np.asarray(targets_host, dtype=np.int64)
     B = y.shape[0]
     ia = _inputaware(opt)   # train_generator_inputaware.py: one more sigma (:239) and one more transform (:241) in the G-step
+    wn = _wanet(opt)        # train_generator_wanet.py: warp trigger, no GaussianBlur -> no sigma draws at all
     bd = create_targets_bd_np(y, opt).astype(np.int64)
     trg = np.nonzero(y == bd)[0]
     ntrg = np.nonzero(y != bd)[0]
     num_bd = int(np.sum(np.random.rand(trg.shape[0]) < opt.pc))
     sigma_c = None
     taps_c = (1.0, 0.0)
-    if num_bd > 0:
+    if num_bd > 0 and not wn:
         sigma_c = torch.empty(1).uniform_(opt.sigma[0], opt.sigma[1]).item()
         taps_c = ops.gaussian_taps(sigma_c)
     tf = None
@@ -110,7 +115,7 @@ def make_plan(targets_host, opt, with_metrics=True) -> StepPlan:
         tf[TF_SLOT["T1"]] = draw_tf_params(B, opt)                                    # :196
         if with_metrics:
             tf[TF_SLOT["T2"]] = draw_tf_params(B, opt)                                # :214
-    sigma_g = torch.empty(1).uniform_(opt.sigma[0], opt.sigma[1]).item()              # :226
+    sigma_g = torch.empty(1).uniform_(opt.sigma[0], opt.sigma[1]).item() if not wn else None   # :226
     sigma_g2 = torch.empty(1).uniform_(opt.sigma[0], opt.sigma[1]).item() if ia else None   # inputaware :239
     if tf is not None:
         if with_metrics:
@@ -121,8 +126,8 @@ def make_plan(targets_host, opt, with_metrics=True) -> StepPlan:
         tf[TF_SLOT["T5"]] = draw_tf_params(B, opt)                                    # :250
     perm = np.concatenate([trg, ntrg]).astype(np.int32)
     total_y = np.concatenate([bd[trg[:num_bd]], y[trg[num_bd:]], y[ntrg]]).astype(np.int64)
-    return StepPlan(perm, num_bd, trg, ntrg, bd, total_y, sigma_c, sigma_g, taps_c, ops.gaussian_taps(sigma_g), tf=tf,
-                    sigma_g2=sigma_g2, taps_g2=ops.gaussian_taps(sigma_g2) if ia else (1.0, 0.0))
+    return StepPlan(perm, num_bd, trg, ntrg, bd, total_y, sigma_c, sigma_g, taps_c,
+                    ops.gaussian_taps(sigma_g) if not wn else (1.0, 0.0), tf=tf, sigma_g2=sigma_g2, taps_g2=ops.gaussian_taps(sigma_g2) if ia else (1.0, 0.0))
 
 
 def multilabel_chunks(bs: int, num_classes: int):
@@ -184,7 +189,7 @@ def make_plan_victim(targets_host, poisoned_host, opt) -> StepPlan:
     trg, ntrg = np.nonzero(pz)[0], np.nonzero(~pz)[0]
     num_bd = int(trg.shape[0])
     sigma_c, taps_c = None, (1.0, 0.0)
-    if num_bd > 0:
+    if num_bd > 0 and not _wanet(opt):   # train_victim_wanet.py:86-97: warp trigger, no blur, nothing drawn
         sigma_c = torch.empty(1).uniform_(opt.sigma[0], opt.sigma[1]).item()
         taps_c = ops.gaussian_taps(sigma_c)
     tf = None
@@ -219,7 +224,7 @@ class AlternatedStep:
         else:
             self.netC = Classifier(classifier, o.num_classes, o.input_channel, H, **mk)
             self.clean = Classifier(classifier, o.num_classes, o.input_channel, H, **mk)
-            self.netG = Generator(o.input_channel, 64, cond_classes, **mk)
+            self.netG = GridGenerator(o.input_channel, 64, o.s, **mk) if _wanet(o) else Generator(o.input_channel, 64, cond_classes, **mk)
             self.netF = FrequencyDetector(2, o.input_channel, H, device=self.device, dtype=dtype) if (with_metrics and H in (32, 64)) else None
         # multilabel=True: the step of train_generator_multilabel.py (conditional generator, class-chunked G-step)
         self.multilabel = bool(multilabel)
@@ -235,6 +240,13 @@ class AlternatedStep:
         self.cross_weight = float(getattr(o, "cross_weight", 0.2)) if self.inputaware else 0.0
         if self.inputaware and self.multilabel:
             raise ValueError("the inputaware variant has no multilabel form in the reference")
+        # "wanet" (train_generator_wanet.py): netG is a GridGenerator (S x S flow control grid), the trigger is a WARP of the image
+        # (bicubic flow, grid_sample) -- one fused kernel instead of DCT low-pass + blend + blur; loss_l2 = MSE(noise_grid, 0)
+        self.wanet = _wanet(o)
+        if self.wanet:
+            if self.multilabel or not isinstance(self.netG, GridGenerator):
+                raise ValueError("the wanet variant needs a GridGenerator (and has no multilabel form in the reference)")
+            self.grid_rescale, self.S = float(o.grid_rescale), int(o.s)
         self.tf_on = _tf_on(o)      # PostTensorTransform active (five fused gather launches + two adjoints per iteration)
         self.lr_C = torch.full((1,), float(o.lr_C), dtype=torch.float32, device=self.device)
         self.lr_G = torch.full((1,), float(o.lr_G), dtype=torch.float32, device=self.device)
@@ -332,6 +344,10 @@ class AlternatedStep:
         b["taps_rows"] = dv["taps_rows"]
         b["tf"] = dv["tf"]
         b["ones"] = torch.ones(B, dtype=torch.int64, device=dev)
+        if self.wanet:   # identity-grid coordinates (train_generator_wanet.py:560: torch.linspace on the host, moved to the device)
+            b["ident"] = torch.linspace(-1, 1, steps=o.input_height).to(dev)
+            b["noise_grid"] = torch.empty((B, o.input_height, o.input_width, 2), dtype=torch.float32, device=dev)
+            b["gl_partial"] = torch.empty(B, dtype=torch.float32, device=dev)
         b["sq_partial"] = torch.empty(B * o.input_channel, dtype=torch.float32, device=dev)
         b["gl2_partial"] = torch.empty(2 * B * o.input_channel, dtype=torch.float32, device=dev)
         b["tv_partial"] = torch.empty(B * o.input_channel, dtype=torch.float32, device=dev)
@@ -411,6 +427,11 @@ class AlternatedStep:
         elif not with_g:  # train_clean_classifier.py: no generator, the batch as it is
             noise_raw = ctxG = noise = None
             total_x = x
+        elif self.wanet:                                                                     # wanet :150-159
+            noise_raw, ctxG = self.netG.forward(x, None, save=save_g)   # the flow control grid [B, 2, S, S], once for both steps
+            noise = None
+            total_x = ops.wanet_warp_fwd(x, noise_raw, b["ident"], b["perm"], 0, self.grid_rescale, self.S,
+                                         num_bd_dev=b["num_bd"])
         else:
             gin = b["xx"] if (self.inputaware and save_g) else x                             # inputaware: + netG(inputs2), :238
             noise_raw, ctxG = self.netG.forward(gin, None, save=save_g)                      # :189 and :223, once
@@ -428,6 +449,23 @@ class AlternatedStep:
     # clean_model forward / backward) does not depend on the C-step update and runs while the netC all-reduce is in flight on the
     # communication stream; B2 starts with the netC optimiser step.  Likewise C1 (frequency-detector metric leg) overlaps the
     # netG all-reduce and C2 is the netG optimiser step.  Single GPU: the same launches in the same order, one graph.
+    def _trigger_batch(self, b, st, noise, out):
+        """The G-step's poisoned batch inputs_bd and its distance term -> losses[2].  Additive trigger (train_generator.py:225-226,
+        234): blend + clamp + blur, MSE(inputs_bd, inputs).  wanet (:196-203, 212-222): warp of the image by the generated flow,
+        MSE(noise_grid, 0), and the logged finite-difference term -> losses[7]."""
+        o = self.opt
+        x, B, losses = b["x"], b["B"], b["losses"]
+        if self.wanet:
+            x_bd = ops.wanet_warp_fwd(x, st["noise_raw"], b["ident"], None, B, self.grid_rescale, self.S, out=out,
+                                      noise_grid=b["noise_grid"], sq_partial=b["sq_partial"], gl_partial=b["gl_partial"])
+            ops.sum_scale(b["sq_partial"][:B], 1.0 / b["noise_grid"].numel(), out=losses[2:3])
+            ops.sum_scale(b["gl_partial"], 1.0 / B, out=losses[7:8])
+            return x_bd
+        x_bd = ops.poison_blend_fwd(x, noise, None, B, o.noise_rate, None, out=out, sq_partial=b["sq_partial"],
+                                    taps_dev=b["taps_g"], taps_rows=b["taps_rows"])
+        ops.sum_scale(b["sq_partial"], 1.0 / x.numel(), out=losses[2:3])
+        return x_bd
+
     def _phase_b1(self, b, st):
         o = self.opt
         x, y, B = b["x"], b["y"], b["B"]
@@ -451,9 +489,7 @@ class AlternatedStep:
             # half of the saved state is back-propagated.
             x2 = b["x2"]
             x2[:B].copy_(x)
-            x_bd = ops.poison_blend_fwd(x, noise, None, B, o.noise_rate, None, out=x2[B:], sq_partial=b["sq_partial"],
-                                        taps_dev=b["taps_g"], taps_rows=b["taps_rows"])      # :225-226
-            ops.sum_scale(b["sq_partial"], 1.0 / numel, out=losses[2:3])                     # :234
+            x_bd = self._trigger_batch(b, st, noise, x2[B:])                                 # :225-226, :234
             # PostTensorTransform: netC sees [T3(x) ; T4(x_bd)] (:227-228), clean_model [T2(x) ; T5(x_bd)] (:214,:250) -- one
             # gather launch per network over the 2B rows with per-row parameters
             tfK = b["tf"][TF_SLOT["T2"]:TF_SLOT["T5"] + 1].view(2 * B, TF_W) if self.tf_on else None
@@ -472,15 +508,13 @@ class AlternatedStep:
                 clean_preds, _ = self.clean.forward(tfp("T2", x), train=False, save=False)   # :214
                 ops.cross_entropy(clean_preds, y, 1.0, False, loss_out=losses[4:5], counts_out=counts[2:4])
                 st["clean_preds"] = clean_preds
-            x_bd = ops.poison_blend_fwd(x, noise, None, B, o.noise_rate, None, sq_partial=b["sq_partial"],
-                                        taps_dev=b["taps_g"], taps_rows=b["taps_rows"])      # :225-226
-            ops.sum_scale(b["sq_partial"], 1.0 / numel, out=losses[2:3])                     # :234
+            x_bd = self._trigger_batch(b, st, noise, None)                                   # :225-226, :234
             cm_preds, ctxK = self.clean.forward(tfp("T5", x_bd), train=False, save=True)     # :250
             _, dl2, _ = ops.cross_entropy(cm_preds, y, o.clean_model_weight, True, targets2=b["bd_targets"],
                                           loss_out=losses[3:4], counts_out=counts[8:10])      # :251,266-267
             g2 = self.clean.backward(ctxK, dl2, need_wgrad=False, need_dx=True)
             del ctxK
-        if self.with_metrics and not self.multilabel and not self.inputaware:
+        if self.with_metrics and not self.multilabel and not self.inputaware and not self.wanet:
             ops.grad_l2(x, x_bd, losses[7:8], b["gl2_partial"])                              # :235-243 (logged only)
         st.update(x_bd=x_bd, clean_model_preds=cm_preds, g2=g2)
 
@@ -529,6 +563,13 @@ class AlternatedStep:
             g1, g2 = gsum, None
         if self.tv_weight:   # train_generator_imperceptible.py:228,235: + tv_weight * total_variation(inputs_bd).mean()
             ops.tv_loss(x_bd, losses[8:9], grad=g1, grad_weight=self.tv_weight / B, partial=b["tv_partial"])
+        if self.wanet:        # back through grid_sample / clamp / bicubic upsampling to the flow control grid (csrc/warp.cu)
+            dflow = ops.wanet_warp_bwd(x, st["noise_raw"], b["ident"], g1, g2, self.grid_rescale,
+                                       2.0 * o.L2_weight / b["noise_grid"].numel(), self.S)
+            self.netG.zero_grad()                                                            # :195
+            self.netG.backward(st.pop("ctxG"), dflow.view(B, 2, self.S, self.S))             # :236
+            st.update(pred_bd=pred_bd, g1=g1, g2=g2, dnoise=dflow)
+            return
         if self.inputaware:   # gradients of both trigger batches, [d noise(x) ; d noise(x2)], through ONE generator backward
             dnoise = torch.empty_like(b["xx"])
             ops.poison_blend_bwd(x, noise, x_bd, g1, g2, 2.0 * o.L2_weight / numel, o.noise_rate, None, out=dnoise[:B],
@@ -769,7 +810,7 @@ class AlternatedStep:
         on x, its own sigma draw (after the first), netC's accuracy on the non-target rows against their TRUE labels."""
         o = self.opt
         y = np.asarray(y_host, dtype=np.int64)
-        if sigma is None:
+        if sigma is None and not self.wanet:   # the warp trigger has no blur: nothing is drawn (train_generator_wanet.py:374-385)
             sigma = torch.empty(1).uniform_(o.sigma[0], o.sigma[1]).item()
         if self.inputaware:
             if x2 is None:
@@ -804,7 +845,7 @@ class AlternatedStep:
         h[1].copy_(torch.from_numpy(np.where(ntrg, bd, -1)))
         h[2].copy_(torch.from_numpy(np.where(ntrg, 1, -1).astype(np.int64)))
         h[3].copy_(torch.from_numpy(np.where(ntrg, y, -1)))
-        s["taps"][0], s["taps"][1] = ops.gaussian_taps(sigma)
+        s["taps"][0], s["taps"][1] = ops.gaussian_taps(sigma) if sigma is not None else (1.0, 0.0)
         if self.inputaware:
             s["taps"][2], s["taps"][3] = ops.gaussian_taps(sigma2)
             eb["x2"].copy_(x2, non_blocking=True)
@@ -818,8 +859,11 @@ class AlternatedStep:
             preds_clean, _ = self.netC.forward(x, train=False, save=False)                          # :360
             ops.cross_entropy(preds_clean, t[0], 1.0, False, counts_out=counts[0:2])
             noise_raw, _ = self.netG.forward(x, None, save=False)                                    # :369
-            noise = ops.plane_op(noise_raw, "lowfreq", keep=self.keep)                               # :370
-            x_bd = ops.poison_blend_fwd(x, noise, None, B, o.noise_rate, None, taps_dev=eb["taps"])  # :372-373
+            if self.wanet:
+                x_bd = ops.wanet_warp_fwd(x, noise_raw, b["ident"], None, B, self.grid_rescale, self.S)
+            else:
+                noise = ops.plane_op(noise_raw, "lowfreq", keep=self.keep)                               # :370
+                x_bd = ops.poison_blend_fwd(x, noise, None, B, o.noise_rate, None, taps_dev=eb["taps"])  # :372-373
             preds_bd, _ = self.netC.forward(x_bd, train=False, save=False)                          # :375
             ops.cross_entropy(preds_bd, t[1], 1.0, False, counts_out=counts[2:4])
             extra = {}

@@ -207,6 +207,41 @@ class CUnetGeneratorv1(_GeneratorModule):
         return _run(self, x, y.contiguous())
 
 
+class GridGenerator(_KernelModule):
+    """networks/models.py:344-385 (the WaNet variant's flow generator; `opt.s` = side of the control grid)."""
+
+    def __init__(self, opt, in_channels=3, nf=64, use_bias=True, device=None, dtype=None):
+        super().__init__()
+        if not use_bias:
+            raise NotImplementedError("use_bias=False is not used on the hot path")
+        dev = torch.device(device or getattr(opt, "device", None) or "cuda")
+        if dev.type != "cuda":
+            raise RuntimeError("combat_b200 modules are CUDA only")
+        self.S = opt.s
+        net = nets.GridGenerator(in_channels, nf, opt.s, device=dev, dtype=dtype or default_dtype())
+        self._bind(net)
+        import math
+        gain = math.sqrt(2.0 / (1 + math.sqrt(5) ** 2))
+        st = net.store
+        for name, _ in nets.GridGenerator.LAYERS:  # construction order of the reference (:350-368): convs, then fc1, fc2
+            shape = st.shapes[name + ".weight"]
+            fan_in = shape[1] * 9
+            b = math.sqrt(3.0) * gain / math.sqrt(fan_in)
+            st.p(name + ".weight").copy_(torch.empty(shape).uniform_(-b, b))
+            st.p(name + ".bias").copy_(torch.empty(shape[0]).uniform_(-1 / math.sqrt(fan_in), 1 / math.sqrt(fan_in)))
+        for name in ("fc1", "fc2"):
+            shape = st.shapes[name + ".weight"]
+            b = math.sqrt(3.0) * gain / math.sqrt(shape[1])
+            st.p(name + ".weight").copy_(torch.empty(shape).uniform_(-b, b))
+            st.p(name + ".bias").copy_(torch.empty(shape[0]).uniform_(-1 / math.sqrt(shape[1]), 1 / math.sqrt(shape[1])))
+        net.prep_weights()
+
+    def forward(self, x):
+        if x.shape[0] == 0:   # the reference raises here (reshape of an empty tensor, :383); an empty flow is returned instead
+            return x.new_empty((0, 2, self.S, self.S))
+        return _run(self, x, None)
+
+
 class FrequencyModel(_KernelModule):
     """defenses/frequency_based/model.py:8-52.  `forward` is the inference path; training goes through
     combat_b200.defenses.frequency_based.train (trainable=True builds the float32 training configuration)."""

@@ -953,6 +953,87 @@ class Generator(NetBase):
         self.conv_first_wgrad(x, d_c00, cv["conv0_0"])
 
 
+class GridGenerator(Generator):
+    """GridGenerator of the WaNet variant (networks/models.py:344-385): the ENCODER half of UnetGenerator (same kernels: first conv
+    on the 3-channel path, tcgen05 convs, InstanceNorm + LeakyReLU), global average pool + fc1 (one pool_linear launch),
+    LeakyReLU, fc2, tanh -> the S x S control grid of a flow, [N, 2, S, S] float32.  Subclass of Generator for the module
+    plumbing only (forward(x, labels, save) -> (y, ctx), backward(ctx, dy))."""
+
+    LAYERS = [("conv0_0", 2), ("conv0_1", 1), ("conv1_0", 2), ("conv1_1", 1), ("conv2_0", 2), ("conv2_1", 1), ("conv3_0", 2),
+              ("conv3_1", 1)]
+
+    def __init__(self, in_channels=3, nf=64, S=2, device="cuda", dtype=torch.bfloat16, use_tc=True):
+        NetBase.__init__(self, device, dtype, use_tc)
+        if not 1 <= S <= 4:
+            raise ValueError("GridGenerator: control grids up to 4 x 4 are supported (--s %d)" % S)
+        self.nf, self.cond, self.in_channels, self.out_channel, self.S = nf, 0, in_channels, 2, S
+        self.cond_pad = False
+        ch = {"conv0_0": (in_channels, nf), "conv0_1": (nf, nf), "conv1_0": (nf, nf * 2), "conv1_1": (nf * 2, nf * 2),
+              "conv2_0": (nf * 2, nf * 4), "conv2_1": (nf * 4, nf * 4), "conv3_0": (nf * 4, nf * 8), "conv3_1": (nf * 8, nf * 8)}
+        specs, convs = [], []
+        for name, stride in self.LAYERS:
+            ci, co = ch[name]
+            specs.append((name + ".weight", (co, ci, 3, 3)))
+            specs.append((name + ".bias", (co,)))
+            convs.append(ConvSpec(name, ci, co, 3, stride, 1, True, need_dgrad=(name != "conv0_0")))
+        specs += [("fc1.weight", (nf, nf * 8)), ("fc1.bias", (nf,)), ("fc2.weight", (S * S * 2, nf)), ("fc2.bias", (S * S * 2,))]
+        self._finish_params(specs, convs)
+
+    def forward(self, x_nchw, labels=None, save=True):
+        cv = self.convs
+        N, _, H, W = x_nchw.shape
+        ctx = {"x": x_nchw} if save else None
+        c00 = self.conv_first_fwd(x_nchw, cv["conv0_0"], pre=False)
+        a00 = ops.leaky_relu(c00)
+        acts = {"c00": c00, "a00": a00}
+
+        def down(name, xin, act=True):
+            c = self.conv_fwd(xin, cv[name])
+            y, st = ops.instnorm_fwd(c, act, out_dtype=self.dtype)
+            acts[name] = (xin, c, st)
+            return y
+
+        f0 = down("conv0_1", a00)
+        f1 = down("conv1_1", down("conv1_0", f0))
+        f2 = down("conv2_1", down("conv2_0", f1))
+        f3 = down("conv3_1", down("conv3_0", f2), act=False)
+        if f3.shape[1] != f3.shape[2]:
+            raise ValueError("GridGenerator: square images only")
+        st = self.store
+        h1, pooled = ops.pool_linear_fwd(f3, f3.shape[1], st.p("fc1.weight"), st.p("fc1.bias"))      # :381-382
+        a1 = ops.leaky_relu(h1)
+        z, _ = ops.pool_linear_fwd(a1.view(N, 1, 1, self.nf), 1, st.p("fc2.weight"), st.p("fc2.bias"))   # :383
+        out = ops.tanh_fwd(z).view(N, 2, self.S, self.S)                                            # :383-384
+        if save:
+            ctx.update(acts=acts, out=out, f3_shape=tuple(f3.shape), pooled=pooled, h1=h1, a1=a1)
+        return out, ctx
+
+    def backward(self, ctx, dout):
+        """dout: gradient w.r.t. the tanh output [N, 2, S, S] (float32).  Accumulates all parameter gradients."""
+        cv, acts = self.convs, ctx["acts"]
+        x = ctx["x"]
+        N = x.shape[0]
+        st = self.store
+        dz = ops.tanh_bwd(dout.contiguous().view(N, -1), ctx["out"].view(N, -1))
+        da1 = ops.pool_linear_bwd(dz, ctx["a1"], st.p("fc2.weight"), (N, 1, 1, self.nf), torch.float32, 1,
+                                  dW=st.g("fc2.weight"), db=st.g("fc2.bias"))
+        dh1 = ops.leaky_relu_bwd(da1.view(N, self.nf), ctx["h1"])
+        d_f3 = ops.pool_linear_bwd(dh1, ctx["pooled"], st.p("fc1.weight"), ctx["f3_shape"], self.dtype, ctx["f3_shape"][1],
+                                   dW=st.g("fc1.weight"), db=st.g("fc1.bias"))
+
+        def conv_in_bwd(name, dy1, act):
+            xin, c, stn = acts[name]
+            d_c = ops.instnorm_bwd(dy1, None, c, stn, act)
+            self.conv_wgrad(xin, d_c, cv[name], dead_bias=True)
+            return self.conv_dgrad(d_c, cv[name], xin.shape[1:3])
+
+        d = conv_in_bwd("conv3_1", d_f3, False)
+        for name in ("conv3_0", "conv2_1", "conv2_0", "conv1_1", "conv1_0", "conv0_1"):
+            d = conv_in_bwd(name, d, True)
+        d_c00 = ops.leaky_relu_bwd(d, acts["c00"])
+        self.conv_first_wgrad(x, d_c00, cv["conv0_0"])
+
+
 # ===================================================================== frequency detector (forward only)
 class FrequencyDetector(NetBase):
     """FrequencyModel in eval mode: conv -> ELU -> BN(eval) (x6), maxpool after 2/4/6, flatten (NCHW order), linear

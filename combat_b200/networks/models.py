@@ -1,8 +1,8 @@
-"""The names train_generator.py imports from networks/models.py of the reference: the two trigger generators (kernel-backed
+"""The names train_generator.py imports from networks/models.py of the reference: the trigger generators (additive U-Nets and the WaNet flow generator; kernel-backed
 modules) and the `Denormalizer` helper (reference networks/models.py:38-86) that maps normalised images back to [0, 1]."""
 import torch
 
-from ..modules import CUnetGeneratorv1, UnetGenerator  # noqa: F401
+from ..modules import CUnetGeneratorv1, GridGenerator, UnetGenerator  # noqa: F401
 
 # per-dataset (mean, std) of the reference's input normalisation; None = the dataset is not normalised
 _STATS = {"cifar10": (0.5, 0.5), "celeba": (0.5, 0.5), "imagenet10": (0.5, 0.5), "mnist": (0.5, 0.5), "gtsrb": None}

@@ -205,6 +205,35 @@ def sum_scale(partial, scale, out=None):
     return out
 
 
+def tanh_fwd(x):
+    y = torch.empty_like(x)
+    check(lib.combat_tanh_fwd(_p(x), _p(y), x.numel(), _s()), "tanh_fwd")
+    return y
+
+
+def wanet_warp_fwd(x, z, ident, perm, num_bd, grid_rescale, S, out=None, noise_grid=None, sq_partial=None, gl_partial=None,
+                   num_bd_dev=None):
+    """train_generator_wanet.py:151-159 / :196-203 (csrc/warp.cu): rows i < num_bd of the output are sample perm[i] warped by
+    its own flow z[perm[i]] (the GridGenerator's output), the others plain copies."""
+    x = _contig(x)
+    B, Cc, H, W = x.shape
+    rows = B if perm is None else perm.numel()
+    if out is None:
+        out = torch.empty((rows, Cc, H, W), dtype=torch.float32, device=x.device)
+    check(lib.combat_wanet_warp_fwd(_p(x), _p(z), _p(ident), _p(perm), rows, int(num_bd), _p(num_bd_dev), float(grid_rescale),
+                                    _p(out), _p(noise_grid), _p(sq_partial), _p(gl_partial), Cc, H, W, int(S), _s()),
+          "wanet_warp_fwd")
+    return out
+
+
+def wanet_warp_bwd(x, z, ident, g1, g2, grid_rescale, l2_scale, S):
+    B, Cc, H, W = x.shape
+    dz = torch.empty((B, 2 * S * S), dtype=torch.float32, device=x.device)
+    check(lib.combat_wanet_warp_bwd(_p(x), _p(z), _p(ident), _p(g1), _p(g2), float(grid_rescale), float(l2_scale), _p(dz), B, Cc,
+                                    H, W, int(S), _s()), "wanet_warp_bwd")
+    return dz
+
+
 def grad_l2(x, x_bd, out, partial=None):
     """the logged 'Grad L2 Loss' of train_generator.py:235-243 -> out[0]"""
     B, Cc, H, W = x.shape

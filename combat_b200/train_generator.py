@@ -82,7 +82,8 @@ def get_model(opt):
 
 
 _HOT_SCALARS = ("noise_rate", "ratio", "L2_weight", "clean_model_weight", "target_label", "attack_mode", "num_classes",
-                "post_transform_option", "random_crop", "random_rotation", "dataset", "variant", "tv_weight", "cross_weight")
+                "post_transform_option", "random_crop", "random_rotation", "dataset", "variant", "tv_weight", "cross_weight", "s",
+                "grid_rescale")
 
 
 def _engine_for(netC, clean_model, netG, netF, opt, multilabel=False):
@@ -274,8 +275,9 @@ def _dataset_shape(opt):
         raise Exception("Invalid Dataset")
 
 
-def main(argv=None, train_fn=None, eval_fn=None):
-    """(train_fn / eval_fn: the variants -- train_generator_imperceptible.py -- run this driver with their own train / eval)
+def main(argv=None, train_fn=None, eval_fn=None, get_model_fn=None):
+    """(train_fn / eval_fn / get_model_fn: the variants -- train_generator_imperceptible.py, train_generator_wanet.py -- run this
+    driver with their own train / eval / get_model)
     train_generator.py:466-609: dataset shape, loaders, get_model, detector / clean-model checkpoints, --continue_training
     resume, then n_iters epochs of train() + eval().  Build-only flag --synthetic_data replaces the dataset (there is no
     network here for torchvision's download) and makes the two pretrained checkpoints optional; everything else -- paths,
@@ -286,7 +288,7 @@ def main(argv=None, train_fn=None, eval_fn=None):
     from .utils.dataloader import get_dataloader
     train_dl = get_dataloader(opt, True)
     test_dl = get_dataloader(opt, False)
-    netC, optimizerC, schedulerC, netG, optimizerG, schedulerG, netF, clean_model = get_model(opt)
+    netC, optimizerC, schedulerC, netG, optimizerG, schedulerG, netF, clean_model = (get_model_fn or get_model)(opt)
 
     mode = opt.saving_prefix
     opt.ckpt_folder = os.path.join(opt.checkpoints, "{}_clean".format(mode), opt.dataset)

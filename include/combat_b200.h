@@ -316,6 +316,23 @@ int combat_tv_loss(const float* x, float* grad, float grad_weight, float* partia
 int combat_post_transform_fwd(const float* in, float* out, const float* params, int rows, int C, int H, int W, void* stream);
 int combat_post_transform_bwd(const float* dout, float* din, const float* params, int rows, int C, int H, int W,
                               int accumulate, void* stream);
+/* ---------------------------------------------------------------- WaNet warp trigger (csrc/warp.cu)
+ * train_generator_wanet.py:151-158 / :196-203: z = netG(inputs), the GridGenerator's tanh output [rows_of_x, 2, S, S]
+ * (networks/models.py:383-385); noise_grid = bicubic upsample (align_corners=True) of flow to H x H, permuted to [.., H, W, 2];
+ * grid = clamp(identity_grid * (1 - grid_rescale) + noise_grid * grid_rescale, -1, 1); out = grid_sample(x, grid) (bilinear, zeros
+ * padding, align_corners=True).  ident: the H values of torch.linspace(-1, 1, H) (:560).  Square NCHW float32 images, S <= 4.
+ * _fwd: row i of `out` is the warped image of sample perm[i] (i when perm is NULL) for i < num_bd (*num_bd_dev when given), a
+ * plain copy of it otherwise (the C-step batch assembly, :159).  Optional per-row outputs: noise_grid [rows, H, W, 2],
+ * sq_partial[i] = sum noise_grid^2 (loss_l2 = MSE(noise_grid, 0), :212), gl_partial[i] = this row's share of the logged
+ * finite-difference term (:213-222; mean it over the rows).
+ * _bwd: dz = d/dz of  <g1 + g2, out> + (l2_scale / 2) * |noise_grid|^2  (g2 may be NULL), [rows, 2, S, S].
+ * combat_tanh_fwd: the tanh at the end of GridGenerator.forward (models.py:384), float32. */
+int combat_tanh_fwd(const float* x, float* y, long long n, void* stream);
+int combat_wanet_warp_fwd(const float* x, const float* z, const float* ident, const int* perm, int rows, int num_bd,
+                          const int* num_bd_dev, float grid_rescale, float* out, float* noise_grid, float* sq_partial,
+                          float* gl_partial, int C, int H, int W, int S, void* stream);
+int combat_wanet_warp_bwd(const float* x, const float* z, const float* ident, const float* g1, const float* g2,
+                          float grid_rescale, float l2_scale, float* dz, int rows, int C, int H, int W, int S, void* stream);
 /* layout/dtype helpers */
 int combat_nchw_to_nhwc(const float* x, void* y, int dtype, int N, int C, int H, int W, void* stream);
 int combat_nhwc_to_nchw(const void* x, int dtype, float* y, int N, int C, int H, int W, void* stream);

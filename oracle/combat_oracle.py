@@ -843,8 +843,12 @@ def eval_batch(state: dict, x: torch.Tensor, y: torch.Tensor, opt, x2: torch.Ten
         preds_clean = fwdC(netC_p, netC_b, x, False)  # :360
         ntrg = (y != opt.target_label).nonzero()[:, 0]  # :366
         x_sel, y_sel = x[ntrg], y[ntrg]
-        sigma = draw_sigma(*opt.sigma)
-        x_bd, _, _ = make_bd(netG_p, x_sel, opt, sigma)  # :369-373
+        if getattr(opt, "variant", "") == "wanet":  # train_generator_wanet.py:352-364: warp trigger, nothing drawn
+            sigma = None
+            x_bd = wanet_warp(x_sel, grid_generator_forward(netG_p, x_sel, opt.s), opt)[0]
+        else:
+            sigma = draw_sigma(*opt.sigma)
+            x_bd, _, _ = make_bd(netG_p, x_sel, opt, sigma)  # :369-373
         bd_t = create_targets_bd(y_sel, opt.attack_mode, opt.target_label, opt.num_classes)
         preds_bd = fwdC(netC_p, netC_b, x_bd, False)
         if x2 is not None:
