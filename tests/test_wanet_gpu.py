@@ -47,7 +47,8 @@ def test_warp_kernels_vs_torch(S, H, r, N):
     ngd = torch.empty(N, H, H, 2, device="cuda")
     sq, gl = torch.empty(N, device="cuda"), torch.empty(N, device="cuda")
     out = ops.wanet_warp_fwd(xd, fd, ident, None, N, r, S, noise_grid=ngd, sq_partial=sq, gl_partial=gl)
-    assert rel(out, ref) < 2e-5 and rel(ngd, ng) < 2e-6
+    # float32 on both sides; with grid_rescale 2.5 most coordinates sit ON the clamp, where one ulp moves a tap boundary
+    assert rel(out, ref) < (2e-5 if r < 1 else 1e-4) and rel(ngd, ng) < 2e-6
     assert abs(float(sq.sum()) - float((ng.detach() ** 2).sum())) < 1e-5 * float((ng.detach() ** 2).sum())
     gref = float(O.wanet_grad_l2(ng.detach()))
     assert abs(float(gl.sum()) / N - gref) < 1e-5 * gref
@@ -82,10 +83,17 @@ def test_grid_generator_vs_oracle(N, H):
     assert tuple(out.shape) == (N, 2, 2, 2) and rel(out, ref) < 1e-4
     net.zero_grad()
     net.backward(ctx, dout.cuda())
+    # A property of the reference's architecture: the average pool sits right behind a non-affine InstanceNorm (models.py:380-381),
+    # whose output has zero mean per (sample, channel) -- so the pooled feature is 0 up to rounding, the flow does not depend on
+    # the image, and every encoder gradient (and fc1.weight's) is rounding noise in the reference too (~1e-8 here).  Only
+    # fc1.bias and fc2 carry a signal; all tensors are compared on the scale of the largest gradient.
+    assert float(ctx["pooled"].abs().max()) < 1e-5
+    scale = max(float(t.grad.norm()) for t in p.values())
     for k, t in p.items():
-        if k.endswith("bias") and k.startswith("conv") and k != "conv0_0.bias":
-            continue   # dead biases in front of a non-affine InstanceNorm: rounding noise in the reference too
-        assert rel2(net.store.g(k), t.grad) < 2e-3, (k, rel2(net.store.g(k), t.grad))
+        err = float((net.store.g(k).cpu().double() - t.grad.double()).norm())
+        assert err < 2e-3 * scale, (k, err, scale)
+    for k in ("fc1.bias", "fc2.weight", "fc2.bias"):
+        assert rel2(net.store.g(k), p[k].grad) < 1e-4, (k, rel2(net.store.g(k), p[k].grad))
 
 
 def _state(seed):
