@@ -14,6 +14,8 @@ opt.input_height = opt.input_width = 32; opt.input_channel = 3
 torch.manual_seed(seed); np.random.seed(seed); random.seed(seed)
 netC, optC, schC, netG, optG, schG, netF, clean = tw.get_model(opt)
 batches = [(torch.rand(B, 3, 32, 32) * 2 - 1, torch.randint(0, 10, (B,))) for _ in range(nb)]
+sd0 = {k: v.detach().clone().cpu() for k, v in netC.state_dict().items()}
+sdG0 = {k: v.detach().clone().cpu() for k, v in netG.state_dict().items()}
 opt = tw._variant(opt)
 eng = _engine_for(netC, clean, netG, netF, opt)
 eng.set_lr(optC.param_groups[0]["lr"], optG.param_groups[0]["lr"])
@@ -30,3 +32,11 @@ for i, (x, y) in enumerate(batches):
     for k, dk in (("logits_c", "logits_c"), ("pred_clean", "pred_clean"), ("pred_bd", "pred_bd"), ("clean_preds", "clean_preds"), ("clean_model_preds", "clean_model_preds"), ("flow", "noise_raw")):
         print("  ", k, rel(d[dk], g["%s_%d" % (k, i)]))
     print("   x_bd head", rel(d["x_bd"][:8], g["x_bd_head_%d" % i]), "x_bd_c", rel(d["total_x"][:plan.num_bd], g["x_bd_c_%d" % i]))
+sd = netC.state_dict()
+print("per-tensor two-iteration update norm, engine / fixture:")
+for pre, sd, s0 in (("netC_", netC.state_dict(), sd0), ("netG_", netG.state_dict(), sdG0)):
+    for n, v0 in s0.items():
+        if torch.is_floating_point(v0) and (pre + "dnorm_" + n) in g.files:
+            d = float((sd[n].detach().cpu() - v0).double().norm()); ref = float(g[pre + "dnorm_" + n][0])
+            flag = "" if abs(d - ref) <= 3e-2 * ref else "   <-----"
+            print("  %-40s %.6e %.6e ratio %.4f%s" % (pre + n, d, ref, d / max(ref, 1e-30), flag))
