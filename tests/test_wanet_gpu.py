@@ -228,6 +228,7 @@ def test_wanet_train_and_eval_reproduce_the_reference_fixture(golden, tmp_path):
     assert abs(sc["L2 Loss"] * B * nb - l2) < 2e-3 * l2
     gl = vals[3] + vals[4] + vals[9] + vals[10]
     assert abs(sc["Grad L2 Loss"] * B * nb - gl) < 2e-3 * gl
+    bad = []
     for pre, mod in (("netC_", netC), ("netG_", netG)):
         sd = mod.state_dict()
         for n, v0 in sd0[pre].items():
@@ -237,7 +238,9 @@ def test_wanet_train_and_eval_reproduce_the_reference_fixture(golden, tmp_path):
                 continue
             d = float((sd[n].detach().cpu() - v0).double().norm())
             ref = g[pre + "dnorm_" + n][0]
-            assert abs(d - ref) <= 3e-2 * ref + 1e-12, (pre, n, d, ref)
+            if abs(d - ref) > 3e-2 * ref + 1e-12:
+                bad.append((pre + n, d, float(ref)))
+    assert not bad, bad
     opt.ckpt_path = str(tmp_path / "wn.pth.tar")
     bests = tw.eval(netC, optC, schC, netG, optG, schG, netF, clean, batches, ident, -1.0, 0.0, 0.0, 0.0, 0.0, 0.0, w, 1, opt)
     assert len(bests) == 6
