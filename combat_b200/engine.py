@@ -661,7 +661,12 @@ class AlternatedStep:
             self._copy_stream = torch.cuda.Stream(device=self.device)
         buf = self._stage.get(tuple(x_host.shape))
         if buf is None:
-            buf = self._stage[tuple(x_host.shape)] = torch.empty(x_host.shape, dtype=torch.float32, device=self.device)
+            # allocated FROM THE COPY STREAM'S POOL: a block of the compute stream's pool may belong to a tensor that Python has
+            # already released while kernels reading it are still queued (the host runs ahead of the GPU) -- the side-stream copy
+            # below would overwrite it under them.  Seen as a wrong first-conv weight gradient (the one gradient that reads the
+            # step's input images at backward time) in tests/test_wanet_gpu.py when the allocator handed such a block out.
+            with torch.cuda.stream(self._copy_stream):
+                buf = self._stage[tuple(x_host.shape)] = torch.empty(x_host.shape, dtype=torch.float32, device=self.device)
         # only the previous consumer of the staging buffer (last step's device-to-device copy) must have finished -- NOT the
         # iteration that was just launched, which is what this copy overlaps with
         if self._stage_free is not None:
