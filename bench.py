@@ -254,7 +254,15 @@ def sub_hbm_kernels(dev, peak_bw):
     Pd = torch.from_numpy(P).to(dev)
     t = _timed_kernel(lambda: ops.post_transform_fwd(x, Pd, out=o))
     rec("post_transform_fwd (crop+rotate+flip) 65536 rows", 2 * x.numel() * 4, t, B)
-    del x, noise, o, g1, dn, sq
+    # WaNet warp trigger (train_generator_wanet.py:196-203): flow -> bicubic table -> clamp -> bilinear gather, and its backward
+    S_ = 2
+    flow = torch.tanh(torch.randn(B, 2, S_, S_, device=dev))
+    ident = torch.linspace(-1, 1, steps=32).to(dev)
+    t = _timed_kernel(lambda: ops.wanet_warp_fwd(x, flow, ident, None, B, 0.15, S_, out=o, sq_partial=sq))
+    rec("wanet_warp_fwd (bicubic flow + clamp + grid_sample) 65536 rows", 2 * x.numel() * 4, t, B)
+    t = _timed_kernel(lambda: ops.wanet_warp_bwd(x, flow, ident, g1, None, 0.15, 1e-6, S_))
+    rec("wanet_warp_bwd 65536 rows", 2 * x.numel() * 4, t, B)
+    del x, noise, o, g1, dn, sq, flow
     n = 20541389
     p_, g_, m_ = (torch.randn(n, device=dev) for _ in range(3))
     lr = torch.full((1,), 1e-2, device=dev)
