@@ -951,6 +951,37 @@ def make_bd_cond(netG_p, x, labels, opt, sigma):
     return gaussian_blur(x_bd, sigma), noise, noise_raw
 
 
+def eval_batch_multilabel(state: dict, x: torch.Tensor, y: torch.Tensor, opt) -> dict:
+    """One iteration of train_generator_multilabel.eval() (:343-378; train_victim_multilabel.py is the same file): clean accuracy
+    of netC and clean_model; then for EVERY class ci the whole batch is triggered towards ci (one sigma draw per class, the
+    module-level GaussianBlur :53), attack success / clean-model BA and ASR on the rows whose label is not ci, detector on all rows."""
+    fwdC = CLASSIFIERS[opt.classifier]
+    netC_p, netC_b, netG_p = state["netC_p"], state["netC_b"], state["netG_p"]
+    clean_p, clean_b = state["clean_p"], state["clean_b"]
+    am = lambda t: torch.argmax(t, dim=1)
+    out = dict(sigmas=[], n_clean=len(x), n_bd=0, bd_correct=0, cm_bd_ba=0, cm_bd_asr=0, F_correct=0, x_bd=[], preds_bd=[])
+    with torch.no_grad():
+        out["clean_correct"] = int((am(fwdC(netC_p, netC_b, x, False)) == y).sum())
+        out["cm_correct"] = int((am(fwdC(clean_p, clean_b, x, False)) == y).sum())
+        for ci in range(opt.num_classes):
+            tmp = y * 0 + ci
+            sigma = draw_sigma(0.1, 1.0)
+            x_bd, _, _ = make_bd_cond(netG_p, x, tmp, opt, sigma)
+            preds_bd = fwdC(netC_p, netC_b, x_bd, False)
+            cm_bd = fwdC(clean_p, clean_b, x_bd, False)
+            ntrg = (y != tmp).nonzero()[:, 0]
+            out["sigmas"].append(sigma)
+            out["n_bd"] += len(ntrg)
+            out["bd_correct"] += int((am(preds_bd[ntrg]) == ci).sum())
+            out["cm_bd_ba"] += int((am(cm_bd[ntrg]) == y[ntrg]).sum())
+            out["cm_bd_asr"] += int((am(cm_bd[ntrg]) == ci).sum())
+            preds_F = frequency_model_forward(state["netF_p"], state["netF_b"], dct_2d(((x_bd + 1) / 2 * 255).byte()))
+            out["F_correct"] += int((am(preds_F) == 1).sum())
+            out["x_bd"].append(x_bd)
+            out["preds_bd"].append(preds_bd)
+    return out
+
+
 def multilabel_chunks(bs: int, num_classes: int):
     """:203-211 -- contiguous chunks of ps rows, chunk ci is pushed towards class ci."""
     ps = int((bs - 1) / num_classes) + 1

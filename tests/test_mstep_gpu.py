@@ -121,3 +121,48 @@ def test_multilabel_graph_replay_runs():
         y = torch.randint(0, 10, (32,), generator=g)
         out = AlternatedStep.unpack(eng.step(x.cuda(), y.numpy(), use_graph=True))
     assert all(np.isfinite(out[k]) for k in ("loss_c", "loss_ce", "loss_l2", "clean_model_loss"))
+
+
+def test_multilabel_eval_and_main_public_api(tmp_path, capsys):
+    """train_generator_multilabel.eval (= train_victim_multilabel.eval, the reference files differ by two comments): every class
+    in turn is the attack target, one sigma per class; eval_batch against the oracle restatement of :343-378 (float32, counters
+    bit-exact), then main() on synthetic data (train + eval, checkpoint with mask / pattern, --continue_training)."""
+    from combat_b200 import config
+    from combat_b200 import train_generator_multilabel as tm
+    from combat_b200 import train_victim_multilabel as tvm
+    assert tvm.eval is tm.eval and tvm.main is tm.main
+    opt = config.get_arguments().parse_args(["--device", "cuda", "--dtype", "fp32"])
+    opt.input_height = opt.input_width = 32
+    opt.input_channel = 3
+    torch.manual_seed(7); np.random.seed(7); random.seed(7)
+    netC, optC, schC, netG, optG, schG, netF, clean = tm.get_model(opt)
+    sd = lambda m: {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    netC_p, netC_b = O.split_state(sd(netC))
+    clean_p, clean_b = O.split_state(sd(clean))
+    netF_p, netF_b = O.split_state(sd(netF))
+    state = dict(netC_p=netC_p, netC_b=netC_b, clean_p=clean_p, clean_b=clean_b, netG_p=sd(netG), netF_p=netF_p, netF_b=netF_b)
+    o = O.default_opt()
+    g = torch.Generator().manual_seed(2)
+    x = torch.rand(20, 3, 32, 32, generator=g) * 2 - 1
+    y = torch.randint(0, 10, (20,), generator=g)
+    torch.manual_seed(90)
+    r = O.eval_batch_multilabel(state, x, y, o)
+    torch.manual_seed(90)
+    counts, n_bd, d = tm.eval_batch(netC, clean, netG, netF, x, y, opt)
+    c = counts.cpu().numpy()
+    assert d["sigmas"] == r["sigmas"] and n_bd == r["n_bd"]
+    assert int(c[0, 0]) == r["clean_correct"] and int(c[0, 2]) == r["cm_correct"]
+    assert int(c[1:, 0].sum()) == r["bd_correct"] and int(c[1:, 2].sum()) == r["cm_bd_ba"] and int(c[1:, 3].sum()) == r["cm_bd_asr"]
+    assert int(c[1:, 4].sum()) == r["F_correct"]
+    for ci in (0, 9):
+        assert rel(d["x_bd"][ci], r["x_bd"][ci]) < 1e-5 and rel(d["preds_bd"][ci], r["preds_bd"][ci]) < 2e-4
+    args = ["--synthetic_data", "--debug", "--bs", "30", "--n_iters", "1", "--log_every", "4", "--saving_prefix", "ml",
+            "--checkpoints", str(tmp_path)]
+    torch.manual_seed(0); np.random.seed(0); random.seed(0)
+    best = tm.main(args)
+    out = capsys.readouterr().out
+    assert "Clean Model Bd ASR" in out and len(best) == 6
+    ck = torch.load(str(tmp_path / "ml_clean" / "cifar10" / "cifar10_ml_clean.pth.tar"), map_location="cpu", weights_only=False)
+    assert {"mask", "pattern", "netG", "optimizerG", "best_F_acc"} <= set(ck)
+    tm.main(args + ["--continue_training", "--n_iters", "2"])
+    assert "Continue training!!" in capsys.readouterr().out
