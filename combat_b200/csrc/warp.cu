@@ -231,6 +231,250 @@ __global__ void __launch_bounds__(256) wanet_warp_bwd_k(const float* __restrict_
       }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------
+// Fast path (W % 4 == 0, the shapes of the reference: 32 / 64 / 224): PERSISTENT CTAs (a few per SM) that build the bicubic table
+// once and loop over images; a thread owns four consecutive pixels of a row -- 16-byte loads of the gradients, 16-byte stores of
+// the warped image and the noise grid; S is a template parameter (compile-time S*S loops); one warp-shuffle + one shared-memory
+// pass reduces all per-image sums at once.  First version (one CTA per image, scalar pixels, a block reduction per sum):
+// 1057 us forward / 2180 us backward for 65,536 CIFAR images (23 % / 11 % of the HBM bound).
+template <int S>
+__device__ __forceinline__ void build_table(WarpShared& sh, int H) {
+  const float scale = H > 1 ? (float)(S - 1) / (float)(H - 1) : 0.f;
+  for (int o = threadIdx.x; o < H; o += blockDim.x) {
+    const float real = scale * (float)o;
+    const float fl = floorf(real);
+    const int in = (int)fl;
+    float c[4];
+    cubic_coeffs(real - fl, c);
+    float acc[S];
+#pragma unroll
+    for (int p = 0; p < S; ++p) acc[p] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int p = min(max(in - 1 + i, 0), S - 1);
+#pragma unroll
+      for (int q = 0; q < S; ++q)
+        if (q == p) acc[q] += c[i];
+    }
+#pragma unroll
+    for (int p = 0; p < S; ++p) sh.wt[p * H + o] = acc[p];
+  }
+}
+
+template <int S>
+__device__ __forceinline__ void noise4(const WarpShared& sh, int H, int h, int w0, float nx[4], float ny[4]) {
+  float wy[S];
+#pragma unroll
+  for (int py = 0; py < S; ++py) wy[py] = sh.wt[py * H + h];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) nx[j] = ny[j] = 0.f;
+#pragma unroll
+  for (int px = 0; px < S; ++px) {
+    const float4 wx = *(const float4*)(sh.wt + px * H + w0);
+    const float wxv[4] = {wx.x, wx.y, wx.z, wx.w};
+#pragma unroll
+    for (int py = 0; py < S; ++py) {
+      const float fx = sh.flow[py * S + px], fy = sh.flow[S * S + py * S + px];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float k = wy[py] * wxv[j];
+        nx[j] = fmaf(k, fx, nx[j]);
+        ny[j] = fmaf(k, fy, ny[j]);
+      }
+    }
+  }
+}
+
+template <int S>
+__global__ void __launch_bounds__(256, 3) wanet_warp_fwd4_k(const float* __restrict__ x, const float* __restrict__ z,
+                                                         const float* __restrict__ ident, const int* __restrict__ perm,
+                                                         int num_bd, const int* __restrict__ num_bd_dev, float rescale,
+                                                         float* __restrict__ out, float* __restrict__ noise_grid,
+                                                         float* __restrict__ sq_partial, float* __restrict__ gl_partial, int C,
+                                                         int H, int rows) {
+  pdl_entry();
+  __shared__ __align__(16) WarpShared sh;
+  const int W = H, HW = H * H, W4 = W >> 2, G = HW >> 2;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nbd = num_bd_dev ? *num_bd_dev : num_bd;
+  build_table<S>(sh, H);
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int src = perm ? perm[row] : row;
+    const float* xs = x + (long long)src * C * HW;
+    float* dst = out + (long long)row * C * HW;
+    if (row >= nbd) {  // pass-through row of the C-step batch (bit-exact copy)
+      const float4* s4 = (const float4*)xs;
+      float4* d4 = (float4*)dst;
+      for (int i = tid; i < (C * HW) >> 2; i += blockDim.x) d4[i] = __ldg(s4 + i);
+      continue;
+    }
+    __syncthreads();   // the table is complete / the previous image is done with sh.flow and sh.red
+    if (tid < 2 * S * S) sh.flow[tid] = z[(long long)src * 2 * S * S + tid];
+    __syncthreads();
+    float sq = 0.f, gl1 = 0.f, gl2 = 0.f;
+    for (int g = tid; g < G; g += blockDim.x) {
+      const int h = g / W4, w0 = (g - h * W4) << 2;
+      float nx[4], ny[4];
+      noise4<S>(sh, H, h, w0, nx, ny);
+      const float4 idw = __ldg((const float4*)(ident + w0));
+      const float idx_[4] = {idw.x, idw.y, idw.z, idw.w};
+      const float idh = __ldg(ident + h);
+      Bilin b[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float gx = fminf(fmaxf(idx_[j] * (1.f - rescale) + nx[j] * rescale, -1.f), 1.f);
+        const float gy = fminf(fmaxf(idh * (1.f - rescale) + ny[j] * rescale, -1.f), 1.f);
+        b[j] = unnormalise(gx, gy, H, W);
+      }
+      for (int c = 0; c < C; ++c) {
+        const float* pl = xs + c * HW;
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float wx = b[j].wx, wy = b[j].wy;
+          o[j] = tap(pl, b[j].x0, b[j].y0, H, W) * ((1.f - wx) * (1.f - wy)) + tap(pl, b[j].x0 + 1, b[j].y0, H, W) * (wx * (1.f - wy)) +
+                 tap(pl, b[j].x0, b[j].y0 + 1, H, W) * ((1.f - wx) * wy) + tap(pl, b[j].x0 + 1, b[j].y0 + 1, H, W) * (wx * wy);
+        }
+        *(float4*)(dst + c * HW + h * W + w0) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+      if (noise_grid) {
+        float4* ng = (float4*)(noise_grid + ((long long)row * HW + h * W + w0) * 2);
+        ng[0] = make_float4(nx[0], ny[0], nx[1], ny[1]);
+        ng[1] = make_float4(nx[2], ny[2], nx[3], ny[3]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sq += nx[j] * nx[j] + ny[j] * ny[j];
+      if (gl_partial) {   // :213-222, see the scalar kernel
+        float px_ = 0.f, py_ = 0.f;
+        if (w0 > 0) noise_at(sh, S, H, h, w0 - 1, px_, py_);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          gl1 += (nx[j] - px_) * (nx[j] - px_) + (ny[j] - py_) * (ny[j] - py_);
+          gl2 += nx[j] * nx[j] + (ny[j] - nx[j]) * (ny[j] - nx[j]) + ny[j] * ny[j];
+          px_ = nx[j];
+          py_ = ny[j];
+        }
+        if (w0 + 4 == W) gl1 += px_ * px_ + py_ * py_;
+      }
+    }
+    if (sq_partial || gl_partial) {
+      sq = warp_sum(sq);
+      gl1 = warp_sum(gl1);
+      gl2 = warp_sum(gl2);
+      if (lane == 0) {
+        sh.red[warp * 3 + 0] = sq;
+        sh.red[warp * 3 + 1] = gl1;
+        sh.red[warp * 3 + 2] = gl2;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        float a = 0.f, b1 = 0.f, b2 = 0.f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
+          a += sh.red[i * 3 + 0];
+          b1 += sh.red[i * 3 + 1];
+          b2 += sh.red[i * 3 + 2];
+        }
+        if (sq_partial) sq_partial[row] = a;
+        if (gl_partial) gl_partial[row] = b1 / (float)(H * (W + 2) * 4) + b2 / (float)(H * (W + 3) * 3);
+      }
+    }
+  }
+}
+
+template <int S>
+__global__ void __launch_bounds__(256, 3) wanet_warp_bwd4_k(const float* __restrict__ x, const float* __restrict__ z,
+                                                         const float* __restrict__ ident, const float* __restrict__ g1,
+                                                         const float* __restrict__ g2, float rescale, float l2_scale,
+                                                         float* __restrict__ dz, int C, int H, int rows) {
+  pdl_entry();
+  __shared__ __align__(16) WarpShared sh;
+  constexpr int NF = 2 * S * S;
+  const int W = H, HW = H * H, W4 = W >> 2, G = HW >> 2;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  build_table<S>(sh, H);
+  for (int n = blockIdx.x; n < rows; n += gridDim.x) {
+    const float* xs = x + (long long)n * C * HW;
+    __syncthreads();
+    if (tid < NF) sh.flow[tid] = z[(long long)n * NF + tid];
+    __syncthreads();
+    float acc[NF];
+#pragma unroll
+    for (int k = 0; k < NF; ++k) acc[k] = 0.f;
+    for (int g = tid; g < G; g += blockDim.x) {
+      const int h = g / W4, w0 = (g - h * W4) << 2;
+      float nx[4], ny[4], rx[4], ry[4], dix[4], diy[4];
+      noise4<S>(sh, H, h, w0, nx, ny);
+      const float4 idw = __ldg((const float4*)(ident + w0));
+      const float idx_[4] = {idw.x, idw.y, idw.z, idw.w};
+      const float idh = __ldg(ident + h);
+      Bilin b[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        rx[j] = idx_[j] * (1.f - rescale) + nx[j] * rescale;
+        ry[j] = idh * (1.f - rescale) + ny[j] * rescale;
+        b[j] = unnormalise(fminf(fmaxf(rx[j], -1.f), 1.f), fminf(fmaxf(ry[j], -1.f), 1.f), H, W);
+        dix[j] = diy[j] = 0.f;
+      }
+      for (int c = 0; c < C; ++c) {
+        const long long gi = ((long long)n * C + c) * HW + h * W + w0;
+        float4 gv = __ldg((const float4*)(g1 + gi));
+        if (g2) {
+          const float4 g2v = __ldg((const float4*)(g2 + gi));
+          gv.x += g2v.x; gv.y += g2v.y; gv.z += g2v.z; gv.w += g2v.w;
+        }
+        const float gg[4] = {gv.x, gv.y, gv.z, gv.w};
+        const float* pl = xs + c * HW;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float v00 = tap(pl, b[j].x0, b[j].y0, H, W), v01 = tap(pl, b[j].x0 + 1, b[j].y0, H, W);
+          const float v10 = tap(pl, b[j].x0, b[j].y0 + 1, H, W), v11 = tap(pl, b[j].x0 + 1, b[j].y0 + 1, H, W);
+          dix[j] = fmaf(gg[j], (v01 - v00) * (1.f - b[j].wy) + (v11 - v10) * b[j].wy, dix[j]);
+          diy[j] = fmaf(gg[j], (v10 - v00) * (1.f - b[j].wx) + (v11 - v01) * b[j].wx, diy[j]);
+        }
+      }
+      float wy[S];
+#pragma unroll
+      for (int py = 0; py < S; ++py) wy[py] = sh.wt[py * H + h];
+#pragma unroll
+      for (int px = 0; px < S; ++px) {
+        const float4 wx4 = *(const float4*)(sh.wt + px * H + w0);
+        const float wxv[4] = {wx4.x, wx4.y, wx4.z, wx4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          // clamp passes the gradient where -1 <= raw <= 1 (torch.clamp backward), then the blend with the identity grid
+          const float dnx = ((rx[j] >= -1.f && rx[j] <= 1.f) ? dix[j] * 0.5f * (float)(W - 1) * rescale : 0.f) + l2_scale * nx[j];
+          const float dny = ((ry[j] >= -1.f && ry[j] <= 1.f) ? diy[j] * 0.5f * (float)(H - 1) * rescale : 0.f) + l2_scale * ny[j];
+#pragma unroll
+          for (int py = 0; py < S; ++py) {
+            const float k = wy[py] * wxv[j];
+            acc[py * S + px] = fmaf(k, dnx, acc[py * S + px]);
+            acc[S * S + py * S + px] = fmaf(k, dny, acc[S * S + py * S + px]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NF; ++k) {
+      const float t = warp_sum(acc[k]);
+      if (lane == 0) sh.red[warp * NF + k] = t;
+    }
+    __syncthreads();
+    if (tid < NF) {
+      float t = 0.f;
+      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh.red[i * NF + tid];
+      dz[(long long)n * NF + tid] = t;
+    }
+  }
+}
+
+static int warp_grid(int rows) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int g = sms * 3;   // three resident CTAs per SM (launch bounds), every CTA builds the table once
+  return rows < g ? rows : g;
+}
+
 __global__ void __launch_bounds__(256) tanh_fwd_k(const float* __restrict__ x, float* __restrict__ y, long long n) {
   pdl_entry();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -254,6 +498,15 @@ extern "C" int combat_wanet_warp_fwd(const float* x, const float* z, const float
   COMBAT_ARG(S >= 1 && S <= WARP_MAX_S, 15);
   COMBAT_ARG(perm || !(noise_grid || sq_partial || gl_partial) || num_bd >= rows || num_bd_dev, 5);
   if (rows == 0) return 0;
+  if (W % 4 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)out % 16) == 0 && ((uintptr_t)ident % 16) == 0 &&
+      (!noise_grid || ((uintptr_t)noise_grid % 16) == 0)) {
+#define WARP_FWD(S_)                                                                                                             \
+  pdl_launch(wanet_warp_fwd4_k<S_>, warp_grid(rows), 256, 0, (cudaStream_t)stream, x, z, ident, perm, num_bd, num_bd_dev,          \
+             grid_rescale, out, noise_grid, sq_partial, gl_partial, C, H, rows)
+    if (S == 1) WARP_FWD(1); else if (S == 2) WARP_FWD(2); else if (S == 3) WARP_FWD(3); else WARP_FWD(4);
+#undef WARP_FWD
+    COMBAT_RETURN_LAUNCH("wanet_warp_fwd");
+  }
   pdl_launch(wanet_warp_fwd_k, rows, 256, 0, (cudaStream_t)stream, x, z, ident, perm, num_bd, num_bd_dev, grid_rescale, out,
              noise_grid, sq_partial, gl_partial, C, H, S);
   COMBAT_RETURN_LAUNCH("wanet_warp_fwd");
@@ -266,6 +519,14 @@ extern "C" int combat_wanet_warp_bwd(const float* x, const float* z, const float
   COMBAT_ARG(rows >= 0 && C > 0 && H > 1 && H == W && H <= WARP_MAX_HW, 8);
   COMBAT_ARG(S >= 1 && S <= WARP_MAX_S, 12);
   if (rows == 0) return 0;
+  if (W % 4 == 0 && ((uintptr_t)g1 % 16) == 0 && ((uintptr_t)ident % 16) == 0 && (!g2 || ((uintptr_t)g2 % 16) == 0)) {
+#define WARP_BWD(S_)                                                                                                             \
+  pdl_launch(wanet_warp_bwd4_k<S_>, warp_grid(rows), 256, 0, (cudaStream_t)stream, x, z, ident, g1, g2, grid_rescale, l2_scale, \
+             dz, C, H, rows)
+    if (S == 1) WARP_BWD(1); else if (S == 2) WARP_BWD(2); else if (S == 3) WARP_BWD(3); else WARP_BWD(4);
+#undef WARP_BWD
+    COMBAT_RETURN_LAUNCH("wanet_warp_bwd");
+  }
   pdl_launch(wanet_warp_bwd_k, rows, 256, 0, (cudaStream_t)stream, x, z, ident, g1, g2, grid_rescale, l2_scale, dz, C, H, S);
   COMBAT_RETURN_LAUNCH("wanet_warp_bwd");
 }
