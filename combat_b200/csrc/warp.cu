@@ -285,15 +285,26 @@ __device__ __forceinline__ void noise4(const WarpShared& sh, int H, int h, int w
   }
 }
 
-template <int S>
+template <bool STAGED>
+__device__ __forceinline__ float tap4(const float* __restrict__ pl, int x, int y, int H, int W) {
+  if (x < 0 || x >= W || y < 0 || y >= H) return 0.f;
+  return STAGED ? pl[y * W + x] : __ldg(pl + y * W + x);
+}
+
+// STAGED: the 3 x H x W source image is copied into shared memory with coalesced 16-byte loads, all in flight at once (one HBM
+// latency per image instead of one per channel and tap round), and the gather reads it from there.
+template <int S, bool STAGED>
 __global__ void __launch_bounds__(256, 3) wanet_warp_fwd4_k(const float* __restrict__ x, const float* __restrict__ z,
-                                                         const float* __restrict__ ident, const int* __restrict__ perm,
-                                                         int num_bd, const int* __restrict__ num_bd_dev, float rescale,
-                                                         float* __restrict__ out, float* __restrict__ noise_grid,
-                                                         float* __restrict__ sq_partial, float* __restrict__ gl_partial, int C,
-                                                         int H, int rows) {
+                                                            const float* __restrict__ ident, const int* __restrict__ perm,
+                                                            int num_bd, const int* __restrict__ num_bd_dev, float rescale,
+                                                            float* __restrict__ out, float* __restrict__ noise_grid,
+                                                            float* __restrict__ sq_partial, float* __restrict__ gl_partial,
+                                                            int H, int rows) {
   pdl_entry();
   __shared__ __align__(16) WarpShared sh;
+  extern __shared__ float4 simg4[];
+  float* simg = (float*)simg4;
+  constexpr int C = 3;
   const int W = H, HW = H * H, W4 = W >> 2, G = HW >> 2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nbd = num_bd_dev ? *num_bd_dev : num_bd;
@@ -308,9 +319,14 @@ __global__ void __launch_bounds__(256, 3) wanet_warp_fwd4_k(const float* __restr
       for (int i = tid; i < (C * HW) >> 2; i += blockDim.x) d4[i] = __ldg(s4 + i);
       continue;
     }
-    __syncthreads();   // the table is complete / the previous image is done with sh.flow and sh.red
+    __syncthreads();   // the table is complete / the previous image is done with sh.flow, sh.red and the staged image
+    if (STAGED) {
+      const float4* s4 = (const float4*)xs;
+      for (int i = tid; i < (C * HW) >> 2; i += blockDim.x) simg4[i] = __ldg(s4 + i);
+    }
     if (tid < 2 * S * S) sh.flow[tid] = z[(long long)src * 2 * S * S + tid];
     __syncthreads();
+    const float* img = STAGED ? simg : xs;
     float sq = 0.f, gl1 = 0.f, gl2 = 0.f;
     for (int g = tid; g < G; g += blockDim.x) {
       const int h = g / W4, w0 = (g - h * W4) << 2;
@@ -326,14 +342,17 @@ __global__ void __launch_bounds__(256, 3) wanet_warp_fwd4_k(const float* __restr
         const float gy = fminf(fmaxf(idh * (1.f - rescale) + ny[j] * rescale, -1.f), 1.f);
         b[j] = unnormalise(gx, gy, H, W);
       }
+#pragma unroll
       for (int c = 0; c < C; ++c) {
-        const float* pl = xs + c * HW;
+        const float* pl = img + c * HW;
         float o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float wx = b[j].wx, wy = b[j].wy;
-          o[j] = tap(pl, b[j].x0, b[j].y0, H, W) * ((1.f - wx) * (1.f - wy)) + tap(pl, b[j].x0 + 1, b[j].y0, H, W) * (wx * (1.f - wy)) +
-                 tap(pl, b[j].x0, b[j].y0 + 1, H, W) * ((1.f - wx) * wy) + tap(pl, b[j].x0 + 1, b[j].y0 + 1, H, W) * (wx * wy);
+          o[j] = tap4<STAGED>(pl, b[j].x0, b[j].y0, H, W) * ((1.f - wx) * (1.f - wy)) +
+                 tap4<STAGED>(pl, b[j].x0 + 1, b[j].y0, H, W) * (wx * (1.f - wy)) +
+                 tap4<STAGED>(pl, b[j].x0, b[j].y0 + 1, H, W) * ((1.f - wx) * wy) +
+                 tap4<STAGED>(pl, b[j].x0 + 1, b[j].y0 + 1, H, W) * (wx * wy);
         }
         *(float4*)(dst + c * HW + h * W + w0) = make_float4(o[0], o[1], o[2], o[3]);
       }
@@ -381,27 +400,45 @@ __global__ void __launch_bounds__(256, 3) wanet_warp_fwd4_k(const float* __restr
   }
 }
 
-template <int S>
+template <int S, bool STAGED>
 __global__ void __launch_bounds__(256, 3) wanet_warp_bwd4_k(const float* __restrict__ x, const float* __restrict__ z,
-                                                         const float* __restrict__ ident, const float* __restrict__ g1,
-                                                         const float* __restrict__ g2, float rescale, float l2_scale,
-                                                         float* __restrict__ dz, int C, int H, int rows) {
+                                                            const float* __restrict__ ident, const float* __restrict__ g1,
+                                                            const float* __restrict__ g2, float rescale, float l2_scale,
+                                                            float* __restrict__ dz, int H, int rows) {
   pdl_entry();
   __shared__ __align__(16) WarpShared sh;
-  constexpr int NF = 2 * S * S;
+  extern __shared__ float4 simg4[];
+  float* simg = (float*)simg4;
+  constexpr int NF = 2 * S * S, C = 3;
   const int W = H, HW = H * H, W4 = W >> 2, G = HW >> 2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   build_table<S>(sh, H);
   for (int n = blockIdx.x; n < rows; n += gridDim.x) {
     const float* xs = x + (long long)n * C * HW;
     __syncthreads();
+    if (STAGED) {
+      const float4* s4 = (const float4*)xs;
+      for (int i = tid; i < (C * HW) >> 2; i += blockDim.x) simg4[i] = __ldg(s4 + i);
+    }
     if (tid < NF) sh.flow[tid] = z[(long long)n * NF + tid];
     __syncthreads();
+    const float* img = STAGED ? simg : xs;
     float acc[NF];
 #pragma unroll
     for (int k = 0; k < NF; ++k) acc[k] = 0.f;
     for (int g = tid; g < G; g += blockDim.x) {
       const int h = g / W4, w0 = (g - h * W4) << 2;
+      // the incoming gradients of the four pixels, all channels: issued first, independent of everything below
+      float4 gq[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const long long gi = ((long long)n * C + c) * HW + h * W + w0;
+        gq[c] = __ldg((const float4*)(g1 + gi));
+        if (g2) {
+          const float4 g2v = __ldg((const float4*)(g2 + gi));
+          gq[c].x += g2v.x; gq[c].y += g2v.y; gq[c].z += g2v.z; gq[c].w += g2v.w;
+        }
+      }
       float nx[4], ny[4], rx[4], ry[4], dix[4], diy[4];
       noise4<S>(sh, H, h, w0, nx, ny);
       const float4 idw = __ldg((const float4*)(ident + w0));
@@ -415,19 +452,14 @@ __global__ void __launch_bounds__(256, 3) wanet_warp_bwd4_k(const float* __restr
         b[j] = unnormalise(fminf(fmaxf(rx[j], -1.f), 1.f), fminf(fmaxf(ry[j], -1.f), 1.f), H, W);
         dix[j] = diy[j] = 0.f;
       }
+#pragma unroll
       for (int c = 0; c < C; ++c) {
-        const long long gi = ((long long)n * C + c) * HW + h * W + w0;
-        float4 gv = __ldg((const float4*)(g1 + gi));
-        if (g2) {
-          const float4 g2v = __ldg((const float4*)(g2 + gi));
-          gv.x += g2v.x; gv.y += g2v.y; gv.z += g2v.z; gv.w += g2v.w;
-        }
-        const float gg[4] = {gv.x, gv.y, gv.z, gv.w};
-        const float* pl = xs + c * HW;
+        const float gg[4] = {gq[c].x, gq[c].y, gq[c].z, gq[c].w};
+        const float* pl = img + c * HW;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float v00 = tap(pl, b[j].x0, b[j].y0, H, W), v01 = tap(pl, b[j].x0 + 1, b[j].y0, H, W);
-          const float v10 = tap(pl, b[j].x0, b[j].y0 + 1, H, W), v11 = tap(pl, b[j].x0 + 1, b[j].y0 + 1, H, W);
+          const float v00 = tap4<STAGED>(pl, b[j].x0, b[j].y0, H, W), v01 = tap4<STAGED>(pl, b[j].x0 + 1, b[j].y0, H, W);
+          const float v10 = tap4<STAGED>(pl, b[j].x0, b[j].y0 + 1, H, W), v11 = tap4<STAGED>(pl, b[j].x0 + 1, b[j].y0 + 1, H, W);
           dix[j] = fmaf(gg[j], (v01 - v00) * (1.f - b[j].wy) + (v11 - v10) * b[j].wy, dix[j]);
           diy[j] = fmaf(gg[j], (v10 - v00) * (1.f - b[j].wx) + (v11 - v01) * b[j].wx, diy[j]);
         }
@@ -467,6 +499,11 @@ __global__ void __launch_bounds__(256, 3) wanet_warp_bwd4_k(const float* __restr
   }
 }
 
+static bool warp_staged(int H, size_t* bytes) {
+  *bytes = (size_t)3 * H * H * sizeof(float);
+  return *bytes <= 48 * 1024;   // CIFAR 12 KB, CelebA 48 KB per image; 224 x 224 gathers from global memory
+}
+
 static int warp_grid(int rows) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -498,11 +535,21 @@ extern "C" int combat_wanet_warp_fwd(const float* x, const float* z, const float
   COMBAT_ARG(S >= 1 && S <= WARP_MAX_S, 15);
   COMBAT_ARG(perm || !(noise_grid || sq_partial || gl_partial) || num_bd >= rows || num_bd_dev, 5);
   if (rows == 0) return 0;
-  if (W % 4 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)out % 16) == 0 && ((uintptr_t)ident % 16) == 0 &&
+  if (C == 3 && W % 4 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)out % 16) == 0 && ((uintptr_t)ident % 16) == 0 &&
       (!noise_grid || ((uintptr_t)noise_grid % 16) == 0)) {
+    size_t bytes;
+    const bool staged = warp_staged(H, &bytes);
 #define WARP_FWD(S_)                                                                                                             \
-  pdl_launch(wanet_warp_fwd4_k<S_>, warp_grid(rows), 256, 0, (cudaStream_t)stream, x, z, ident, perm, num_bd, num_bd_dev,          \
-             grid_rescale, out, noise_grid, sq_partial, gl_partial, C, H, rows)
+  do {                                                                                                                           \
+    if (staged) {                                                                                                                \
+      cudaFuncSetAttribute(wanet_warp_fwd4_k<S_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);                \
+      pdl_launch(wanet_warp_fwd4_k<S_, true>, warp_grid(rows), 256, bytes, (cudaStream_t)stream, x, z, ident, perm, num_bd,       \
+                 num_bd_dev, grid_rescale, out, noise_grid, sq_partial, gl_partial, H, rows);                                    \
+    } else {                                                                                                                     \
+      pdl_launch(wanet_warp_fwd4_k<S_, false>, warp_grid(rows), 256, 0, (cudaStream_t)stream, x, z, ident, perm, num_bd,          \
+                 num_bd_dev, grid_rescale, out, noise_grid, sq_partial, gl_partial, H, rows);                                    \
+    }                                                                                                                            \
+  } while (0)
     if (S == 1) WARP_FWD(1); else if (S == 2) WARP_FWD(2); else if (S == 3) WARP_FWD(3); else WARP_FWD(4);
 #undef WARP_FWD
     COMBAT_RETURN_LAUNCH("wanet_warp_fwd");
@@ -519,10 +566,21 @@ extern "C" int combat_wanet_warp_bwd(const float* x, const float* z, const float
   COMBAT_ARG(rows >= 0 && C > 0 && H > 1 && H == W && H <= WARP_MAX_HW, 8);
   COMBAT_ARG(S >= 1 && S <= WARP_MAX_S, 12);
   if (rows == 0) return 0;
-  if (W % 4 == 0 && ((uintptr_t)g1 % 16) == 0 && ((uintptr_t)ident % 16) == 0 && (!g2 || ((uintptr_t)g2 % 16) == 0)) {
+  if (C == 3 && W % 4 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)g1 % 16) == 0 && ((uintptr_t)ident % 16) == 0 &&
+      (!g2 || ((uintptr_t)g2 % 16) == 0)) {
+    size_t bytes;
+    const bool staged = warp_staged(H, &bytes);
 #define WARP_BWD(S_)                                                                                                             \
-  pdl_launch(wanet_warp_bwd4_k<S_>, warp_grid(rows), 256, 0, (cudaStream_t)stream, x, z, ident, g1, g2, grid_rescale, l2_scale, \
-             dz, C, H, rows)
+  do {                                                                                                                           \
+    if (staged) {                                                                                                                \
+      cudaFuncSetAttribute(wanet_warp_bwd4_k<S_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);                \
+      pdl_launch(wanet_warp_bwd4_k<S_, true>, warp_grid(rows), 256, bytes, (cudaStream_t)stream, x, z, ident, g1, g2,             \
+                 grid_rescale, l2_scale, dz, H, rows);                                                                           \
+    } else {                                                                                                                     \
+      pdl_launch(wanet_warp_bwd4_k<S_, false>, warp_grid(rows), 256, 0, (cudaStream_t)stream, x, z, ident, g1, g2,                \
+                 grid_rescale, l2_scale, dz, H, rows);                                                                           \
+    }                                                                                                                            \
+  } while (0)
     if (S == 1) WARP_BWD(1); else if (S == 2) WARP_BWD(2); else if (S == 3) WARP_BWD(3); else WARP_BWD(4);
 #undef WARP_BWD
     COMBAT_RETURN_LAUNCH("wanet_warp_bwd");
