@@ -21,6 +21,7 @@ constexpr int WARP_MAX_S = 4;     // 2 * S * S <= 32 accumulators per thread; th
 constexpr int WARP_MAX_HW = 256;  // table rows in shared memory
 
 struct WarpShared {
+  float flow2[2 * 32];                  // fast kernels: the flow of the current image (+ the next one when pipelined)
   float flow[2 * WARP_MAX_S * WARP_MAX_S];
   float wt[WARP_MAX_S * WARP_MAX_HW];   // wt[p * H + o]
   float red[32 * 8];
@@ -262,7 +263,22 @@ __device__ __forceinline__ void build_table(WarpShared& sh, int H) {
 }
 
 template <int S>
-__device__ __forceinline__ void noise4(const WarpShared& sh, int H, int h, int w0, float nx[4], float ny[4]) {
+__device__ __forceinline__ void noise_one(const WarpShared& sh, const float* flow, int H, int h, int w, float& nx, float& ny) {
+  nx = ny = 0.f;
+#pragma unroll
+  for (int py = 0; py < S; ++py) {
+    const float wy = sh.wt[py * H + h];
+#pragma unroll
+    for (int px = 0; px < S; ++px) {
+      const float k = wy * sh.wt[px * H + w];
+      nx = fmaf(k, flow[py * S + px], nx);
+      ny = fmaf(k, flow[S * S + py * S + px], ny);
+    }
+  }
+}
+
+template <int S>
+__device__ __forceinline__ void noise4(const WarpShared& sh, const float* flow, int H, int h, int w0, float nx[4], float ny[4]) {
   float wy[S];
 #pragma unroll
   for (int py = 0; py < S; ++py) wy[py] = sh.wt[py * H + h];
@@ -274,7 +290,7 @@ __device__ __forceinline__ void noise4(const WarpShared& sh, int H, int h, int w
     const float wxv[4] = {wx.x, wx.y, wx.z, wx.w};
 #pragma unroll
     for (int py = 0; py < S; ++py) {
-      const float fx = sh.flow[py * S + px], fy = sh.flow[S * S + py * S + px];
+      const float fx = flow[py * S + px], fy = flow[S * S + py * S + px];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float k = wy[py] * wxv[j];
@@ -285,6 +301,15 @@ __device__ __forceinline__ void noise4(const WarpShared& sh, int H, int h, int w
   }
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
 template <bool STAGED>
 __device__ __forceinline__ float tap4(const float* __restrict__ pl, int x, int y, int H, int W) {
   if (x < 0 || x >= W || y < 0 || y >= H) return 0.f;
@@ -293,7 +318,10 @@ __device__ __forceinline__ float tap4(const float* __restrict__ pl, int x, int y
 
 // STAGED: the 3 x H x W source image is copied into shared memory with coalesced 16-byte loads, all in flight at once (one HBM
 // latency per image instead of one per channel and tap round), and the gather reads it from there.
-template <int S, bool STAGED>
+// PIPE (every row is warped, no permutation: the G-step / evaluation batch): the staged image and the flow of image n + 1 are
+// fetched with cp.async into the other half of a double buffer while image n is computed -- three resident CTAs alone keep only
+// ~36 KB per SM in flight, less than the bandwidth-latency product needs, and each CTA sat in a load -> sync -> compute chain.
+template <int S, bool STAGED, bool PIPE>
 __global__ void __launch_bounds__(256, 3) wanet_warp_fwd4_k(const float* __restrict__ x, const float* __restrict__ z,
                                                             const float* __restrict__ ident, const int* __restrict__ perm,
                                                             int num_bd, const int* __restrict__ num_bd_dev, float rescale,
@@ -309,29 +337,52 @@ __global__ void __launch_bounds__(256, 3) wanet_warp_fwd4_k(const float* __restr
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nbd = num_bd_dev ? *num_bd_dev : num_bd;
   build_table<S>(sh, H);
-  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-    const int src = perm ? perm[row] : row;
+  const int Q = (C * HW) >> 2;   // float4s per image
+  auto fetch = [&](int r, int half) {   // PIPE: image r and its flow -> buffer half `half` (asynchronous)
+    const float4* s4 = (const float4*)(x + (long long)r * C * HW);
+    for (int i = tid; i < Q; i += blockDim.x) cp_async16(simg4 + half * Q + i, s4 + i);
+    if (tid < 2 * S * S) cp_async4(sh.flow2 + half * 32 + tid, z + (long long)r * 2 * S * S + tid);
+  };
+  if (PIPE) {
+    if ((int)blockIdx.x < rows) fetch(blockIdx.x, 0);
+    cp_async_commit();
+  }
+  int it = 0;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x, ++it) {
+    const int src = (!PIPE && perm) ? perm[row] : row;
     const float* xs = x + (long long)src * C * HW;
     float* dst = out + (long long)row * C * HW;
-    if (row >= nbd) {  // pass-through row of the C-step batch (bit-exact copy)
+    if (!PIPE && row >= nbd) {  // pass-through row of the C-step batch (bit-exact copy)
       const float4* s4 = (const float4*)xs;
       float4* d4 = (float4*)dst;
-      for (int i = tid; i < (C * HW) >> 2; i += blockDim.x) d4[i] = __ldg(s4 + i);
+      for (int i = tid; i < Q; i += blockDim.x) d4[i] = __ldg(s4 + i);
       continue;
     }
-    __syncthreads();   // the table is complete / the previous image is done with sh.flow, sh.red and the staged image
-    if (STAGED) {
-      const float4* s4 = (const float4*)xs;
-      for (int i = tid; i < (C * HW) >> 2; i += blockDim.x) simg4[i] = __ldg(s4 + i);
+    __syncthreads();   // the table is complete / the previous image is done with the flow, sh.red and the staged image
+    const float* img;
+    const float* flow;
+    if (PIPE) {
+      const int half = it & 1;
+      if (row + (int)gridDim.x < rows) fetch(row + gridDim.x, half ^ 1);
+      cp_async_commit();
+      cp_async_wait1();   // everything but the group just committed has landed: this image is in `half`
+      img = simg + half * (C * HW);
+      flow = sh.flow2 + half * 32;
+    } else {
+      if (STAGED) {
+        const float4* s4 = (const float4*)xs;
+        for (int i = tid; i < Q; i += blockDim.x) simg4[i] = __ldg(s4 + i);
+      }
+      if (tid < 2 * S * S) sh.flow2[tid] = z[(long long)src * 2 * S * S + tid];
+      img = STAGED ? simg : xs;
+      flow = sh.flow2;
     }
-    if (tid < 2 * S * S) sh.flow[tid] = z[(long long)src * 2 * S * S + tid];
     __syncthreads();
-    const float* img = STAGED ? simg : xs;
     float sq = 0.f, gl1 = 0.f, gl2 = 0.f;
     for (int g = tid; g < G; g += blockDim.x) {
       const int h = g / W4, w0 = (g - h * W4) << 2;
       float nx[4], ny[4];
-      noise4<S>(sh, H, h, w0, nx, ny);
+      noise4<S>(sh, flow, H, h, w0, nx, ny);
       const float4 idw = __ldg((const float4*)(ident + w0));
       const float idx_[4] = {idw.x, idw.y, idw.z, idw.w};
       const float idh = __ldg(ident + h);
@@ -365,7 +416,7 @@ __global__ void __launch_bounds__(256, 3) wanet_warp_fwd4_k(const float* __restr
       for (int j = 0; j < 4; ++j) sq += nx[j] * nx[j] + ny[j] * ny[j];
       if (gl_partial) {   // :213-222, see the scalar kernel
         float px_ = 0.f, py_ = 0.f;
-        if (w0 > 0) noise_at(sh, S, H, h, w0 - 1, px_, py_);
+        if (w0 > 0) noise_one<S>(sh, flow, H, h, w0 - 1, px_, py_);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           gl1 += (nx[j] - px_) * (nx[j] - px_) + (ny[j] - py_) * (ny[j] - py_);
@@ -400,7 +451,8 @@ __global__ void __launch_bounds__(256, 3) wanet_warp_fwd4_k(const float* __restr
   }
 }
 
-template <int S, bool STAGED>
+// PIPE here double-buffers BOTH the source image and the incoming gradient g1 (g2 must be NULL): [x | g1] of image n + 1 by cp.async.
+template <int S, bool STAGED, bool PIPE>
 __global__ void __launch_bounds__(256, 3) wanet_warp_bwd4_k(const float* __restrict__ x, const float* __restrict__ z,
                                                             const float* __restrict__ ident, const float* __restrict__ g1,
                                                             const float* __restrict__ g2, float rescale, float l2_scale,
@@ -413,16 +465,45 @@ __global__ void __launch_bounds__(256, 3) wanet_warp_bwd4_k(const float* __restr
   const int W = H, HW = H * H, W4 = W >> 2, G = HW >> 2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   build_table<S>(sh, H);
-  for (int n = blockIdx.x; n < rows; n += gridDim.x) {
+  const int Q = (C * HW) >> 2;
+  auto fetch = [&](int r, int half) {   // PIPE: [x | g1] of image r and its flow -> buffer half `half`
+    const float4* s4 = (const float4*)(x + (long long)r * C * HW);
+    const float4* q4 = (const float4*)(g1 + (long long)r * C * HW);
+    for (int i = tid; i < Q; i += blockDim.x) {
+      cp_async16(simg4 + half * 2 * Q + i, s4 + i);
+      cp_async16(simg4 + half * 2 * Q + Q + i, q4 + i);
+    }
+    if (tid < NF) cp_async4(sh.flow2 + half * 32 + tid, z + (long long)r * NF + tid);
+  };
+  if (PIPE) {
+    if ((int)blockIdx.x < rows) fetch(blockIdx.x, 0);
+    cp_async_commit();
+  }
+  int it = 0;
+  for (int n = blockIdx.x; n < rows; n += gridDim.x, ++it) {
     const float* xs = x + (long long)n * C * HW;
     __syncthreads();
-    if (STAGED) {
-      const float4* s4 = (const float4*)xs;
-      for (int i = tid; i < (C * HW) >> 2; i += blockDim.x) simg4[i] = __ldg(s4 + i);
+    const float* img;
+    const float* flow;
+    const float* gsm = nullptr;
+    if (PIPE) {
+      const int half = it & 1;
+      if (n + (int)gridDim.x < rows) fetch(n + gridDim.x, half ^ 1);
+      cp_async_commit();
+      cp_async_wait1();
+      img = simg + half * 2 * (C * HW);
+      gsm = img + C * HW;
+      flow = sh.flow2 + half * 32;
+    } else {
+      if (STAGED) {
+        const float4* s4 = (const float4*)xs;
+        for (int i = tid; i < Q; i += blockDim.x) simg4[i] = __ldg(s4 + i);
+      }
+      if (tid < NF) sh.flow2[tid] = z[(long long)n * NF + tid];
+      img = STAGED ? simg : xs;
+      flow = sh.flow2;
     }
-    if (tid < NF) sh.flow[tid] = z[(long long)n * NF + tid];
     __syncthreads();
-    const float* img = STAGED ? simg : xs;
     float acc[NF];
 #pragma unroll
     for (int k = 0; k < NF; ++k) acc[k] = 0.f;
@@ -433,14 +514,14 @@ __global__ void __launch_bounds__(256, 3) wanet_warp_bwd4_k(const float* __restr
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         const long long gi = ((long long)n * C + c) * HW + h * W + w0;
-        gq[c] = __ldg((const float4*)(g1 + gi));
-        if (g2) {
+        gq[c] = PIPE ? *(const float4*)(gsm + c * HW + h * W + w0) : __ldg((const float4*)(g1 + gi));
+        if (!PIPE && g2) {
           const float4 g2v = __ldg((const float4*)(g2 + gi));
           gq[c].x += g2v.x; gq[c].y += g2v.y; gq[c].z += g2v.z; gq[c].w += g2v.w;
         }
       }
       float nx[4], ny[4], rx[4], ry[4], dix[4], diy[4];
-      noise4<S>(sh, H, h, w0, nx, ny);
+      noise4<S>(sh, flow, H, h, w0, nx, ny);
       const float4 idw = __ldg((const float4*)(ident + w0));
       const float idx_[4] = {idw.x, idw.y, idw.z, idw.w};
       const float idh = __ldg(ident + h);
@@ -539,14 +620,20 @@ extern "C" int combat_wanet_warp_fwd(const float* x, const float* z, const float
       (!noise_grid || ((uintptr_t)noise_grid % 16) == 0)) {
     size_t bytes;
     const bool staged = warp_staged(H, &bytes);
+    // pipelined double buffer: every row warped, rows in place (the G-step / evaluation batch), two images fit next to the table
+    const bool pipe = staged && !perm && !num_bd_dev && num_bd >= rows && 2 * bytes <= 96 * 1024;
 #define WARP_FWD(S_)                                                                                                             \
   do {                                                                                                                           \
-    if (staged) {                                                                                                                \
-      cudaFuncSetAttribute(wanet_warp_fwd4_k<S_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);                \
-      pdl_launch(wanet_warp_fwd4_k<S_, true>, warp_grid(rows), 256, bytes, (cudaStream_t)stream, x, z, ident, perm, num_bd,       \
-                 num_bd_dev, grid_rescale, out, noise_grid, sq_partial, gl_partial, H, rows);                                    \
+    if (pipe) {                                                                                                                  \
+      cudaFuncSetAttribute(wanet_warp_fwd4_k<S_, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * bytes));    \
+      pdl_launch(wanet_warp_fwd4_k<S_, true, true>, warp_grid(rows), 256, 2 * bytes, (cudaStream_t)stream, x, z, ident, perm,     \
+                 num_bd, num_bd_dev, grid_rescale, out, noise_grid, sq_partial, gl_partial, H, rows);                            \
+    } else if (staged) {                                                                                                         \
+      cudaFuncSetAttribute(wanet_warp_fwd4_k<S_, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);         \
+      pdl_launch(wanet_warp_fwd4_k<S_, true, false>, warp_grid(rows), 256, bytes, (cudaStream_t)stream, x, z, ident, perm,        \
+                 num_bd, num_bd_dev, grid_rescale, out, noise_grid, sq_partial, gl_partial, H, rows);                            \
     } else {                                                                                                                     \
-      pdl_launch(wanet_warp_fwd4_k<S_, false>, warp_grid(rows), 256, 0, (cudaStream_t)stream, x, z, ident, perm, num_bd,          \
+      pdl_launch(wanet_warp_fwd4_k<S_, false, false>, warp_grid(rows), 256, 0, (cudaStream_t)stream, x, z, ident, perm, num_bd,   \
                  num_bd_dev, grid_rescale, out, noise_grid, sq_partial, gl_partial, H, rows);                                    \
     }                                                                                                                            \
   } while (0)
@@ -570,14 +657,19 @@ extern "C" int combat_wanet_warp_bwd(const float* x, const float* z, const float
       (!g2 || ((uintptr_t)g2 % 16) == 0)) {
     size_t bytes;
     const bool staged = warp_staged(H, &bytes);
+    const bool pipe = staged && !g2 && 4 * bytes <= 96 * 1024;   // [x | g1] x 2 buffers (CIFAR: 48 KB per CTA)
 #define WARP_BWD(S_)                                                                                                             \
   do {                                                                                                                           \
-    if (staged) {                                                                                                                \
-      cudaFuncSetAttribute(wanet_warp_bwd4_k<S_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);                \
-      pdl_launch(wanet_warp_bwd4_k<S_, true>, warp_grid(rows), 256, bytes, (cudaStream_t)stream, x, z, ident, g1, g2,             \
+    if (pipe) {                                                                                                                  \
+      cudaFuncSetAttribute(wanet_warp_bwd4_k<S_, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * bytes));    \
+      pdl_launch(wanet_warp_bwd4_k<S_, true, true>, warp_grid(rows), 256, 4 * bytes, (cudaStream_t)stream, x, z, ident, g1, g2,   \
+                 grid_rescale, l2_scale, dz, H, rows);                                                                           \
+    } else if (staged) {                                                                                                         \
+      cudaFuncSetAttribute(wanet_warp_bwd4_k<S_, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);         \
+      pdl_launch(wanet_warp_bwd4_k<S_, true, false>, warp_grid(rows), 256, bytes, (cudaStream_t)stream, x, z, ident, g1, g2,      \
                  grid_rescale, l2_scale, dz, H, rows);                                                                           \
     } else {                                                                                                                     \
-      pdl_launch(wanet_warp_bwd4_k<S_, false>, warp_grid(rows), 256, 0, (cudaStream_t)stream, x, z, ident, g1, g2,                \
+      pdl_launch(wanet_warp_bwd4_k<S_, false, false>, warp_grid(rows), 256, 0, (cudaStream_t)stream, x, z, ident, g1, g2,         \
                  grid_rescale, l2_scale, dz, H, rows);                                                                           \
     }                                                                                                                            \
   } while (0)
