@@ -310,6 +310,29 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
+// The clamped grid keeps ix in [0, W-1] and iy in [0, H-1]: the top-left tap is always inside the image and a right / bottom tap
+// is outside only when ix == W-1 / iy == H-1 exactly, where its bilinear weight is exactly 0.  So the four taps are read from
+// offsets folded back into the image (off, off + dx, off + dy, off + dx + dy with dx in {0, 1}, dy in {0, W}) without a predicate
+// per load; the backward, which needs the VALUES of the outside taps to be zero (zeros padding), selects on two flags per pixel.
+struct Tap {
+  int off, dx, dy;
+  float wx, wy;
+};
+__device__ __forceinline__ Tap make_tap(float gx, float gy, int H, int W) {
+  const Bilin b = unnormalise(gx, gy, H, W);
+  Tap t;
+  t.off = b.y0 * W + b.x0;
+  t.dx = b.x0 + 1 < W ? 1 : 0;
+  t.dy = b.y0 + 1 < H ? W : 0;
+  t.wx = b.wx;
+  t.wy = b.wy;
+  return t;
+}
+template <bool STAGED>
+__device__ __forceinline__ float ld(const float* __restrict__ p) {
+  return STAGED ? *p : __ldg(p);
+}
+
 template <bool STAGED>
 __device__ __forceinline__ float tap4(const float* __restrict__ pl, int x, int y, int H, int W) {
   if (x < 0 || x >= W || y < 0 || y >= H) return 0.f;
@@ -386,12 +409,17 @@ __global__ void __launch_bounds__(256, 3) wanet_warp_fwd4_k(const float* __restr
       const float4 idw = __ldg((const float4*)(ident + w0));
       const float idx_[4] = {idw.x, idw.y, idw.z, idw.w};
       const float idh = __ldg(ident + h);
-      Bilin b[4];
+      Tap b[4];
+      float w00[4], w01[4], w10[4], w11[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float gx = fminf(fmaxf(idx_[j] * (1.f - rescale) + nx[j] * rescale, -1.f), 1.f);
         const float gy = fminf(fmaxf(idh * (1.f - rescale) + ny[j] * rescale, -1.f), 1.f);
-        b[j] = unnormalise(gx, gy, H, W);
+        b[j] = make_tap(gx, gy, H, W);
+        w00[j] = (1.f - b[j].wx) * (1.f - b[j].wy);
+        w01[j] = b[j].wx * (1.f - b[j].wy);
+        w10[j] = (1.f - b[j].wx) * b[j].wy;
+        w11[j] = b[j].wx * b[j].wy;
       }
 #pragma unroll
       for (int c = 0; c < C; ++c) {
@@ -399,11 +427,9 @@ __global__ void __launch_bounds__(256, 3) wanet_warp_fwd4_k(const float* __restr
         float o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float wx = b[j].wx, wy = b[j].wy;
-          o[j] = tap4<STAGED>(pl, b[j].x0, b[j].y0, H, W) * ((1.f - wx) * (1.f - wy)) +
-                 tap4<STAGED>(pl, b[j].x0 + 1, b[j].y0, H, W) * (wx * (1.f - wy)) +
-                 tap4<STAGED>(pl, b[j].x0, b[j].y0 + 1, H, W) * ((1.f - wx) * wy) +
-                 tap4<STAGED>(pl, b[j].x0 + 1, b[j].y0 + 1, H, W) * (wx * wy);
+          const float* q = pl + b[j].off;
+          o[j] = ld<STAGED>(q) * w00[j] + ld<STAGED>(q + b[j].dx) * w01[j] + ld<STAGED>(q + b[j].dy) * w10[j] +
+                 ld<STAGED>(q + b[j].dx + b[j].dy) * w11[j];
         }
         *(float4*)(dst + c * HW + h * W + w0) = make_float4(o[0], o[1], o[2], o[3]);
       }
@@ -525,12 +551,12 @@ __global__ void __launch_bounds__(256, 3) wanet_warp_bwd4_k(const float* __restr
       const float4 idw = __ldg((const float4*)(ident + w0));
       const float idx_[4] = {idw.x, idw.y, idw.z, idw.w};
       const float idh = __ldg(ident + h);
-      Bilin b[4];
+      Tap b[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         rx[j] = idx_[j] * (1.f - rescale) + nx[j] * rescale;
         ry[j] = idh * (1.f - rescale) + ny[j] * rescale;
-        b[j] = unnormalise(fminf(fmaxf(rx[j], -1.f), 1.f), fminf(fmaxf(ry[j], -1.f), 1.f), H, W);
+        b[j] = make_tap(fminf(fmaxf(rx[j], -1.f), 1.f), fminf(fmaxf(ry[j], -1.f), 1.f), H, W);
         dix[j] = diy[j] = 0.f;
       }
 #pragma unroll
@@ -539,8 +565,12 @@ __global__ void __launch_bounds__(256, 3) wanet_warp_bwd4_k(const float* __restr
         const float* pl = img + c * HW;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float v00 = tap4<STAGED>(pl, b[j].x0, b[j].y0, H, W), v01 = tap4<STAGED>(pl, b[j].x0 + 1, b[j].y0, H, W);
-          const float v10 = tap4<STAGED>(pl, b[j].x0, b[j].y0 + 1, H, W), v11 = tap4<STAGED>(pl, b[j].x0 + 1, b[j].y0 + 1, H, W);
+          const float* q = pl + b[j].off;
+          const bool vx = b[j].dx != 0, vy = b[j].dy != 0;   // outside taps count as zeros (padding_mode="zeros")
+          const float v00 = ld<STAGED>(q);
+          const float v01 = vx ? ld<STAGED>(q + b[j].dx) : 0.f;
+          const float v10 = vy ? ld<STAGED>(q + b[j].dy) : 0.f;
+          const float v11 = (vx && vy) ? ld<STAGED>(q + b[j].dx + b[j].dy) : 0.f;
           dix[j] = fmaf(gg[j], (v01 - v00) * (1.f - b[j].wy) + (v11 - v10) * b[j].wy, dix[j]);
           diy[j] = fmaf(gg[j], (v10 - v00) * (1.f - b[j].wx) + (v11 - v01) * b[j].wx, diy[j]);
         }
