@@ -597,7 +597,7 @@ class AlternatedStep:
 
     # ---- data-parallel exchange: started on a communication stream right after the backward that produced the gradients,
     # joined just before the optimiser step that consumes them; the flat gradient goes out in COMM_BUCKETS contiguous buckets
-    COMM_BUCKETS = 4
+    COMM_BUCKETS = int(os.environ.get("COMBAT_COMM_BUCKETS", "4"))
     def _exchange_start(self, which):
         if not self._parallel:
             return
