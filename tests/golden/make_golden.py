@@ -27,7 +27,7 @@ tg, config = load_reference()
 from classifier_models.preact_resnet import PreActResNet18  # noqa: E402
 from classifier_models.resnet import ResNet18  # noqa: E402
 from defenses.frequency_based.model import FrequencyModel  # noqa: E402
-from networks.models import CUnetGeneratorv1, UnetGenerator  # noqa: E402
+from networks.models import CUnetGeneratorv1, GridGenerator, UnetGenerator  # noqa: E402
 from utils.dct import dct_2d, idct_2d  # noqa: E402
 
 torch.set_num_threads(8)
@@ -515,6 +515,7 @@ def gen_api():
     mods = {
         "PreActResNet18": PreActResNet18(), "ResNet18_c8_64": ResNet18(num_classes=8),
         "UnetGenerator": UnetGenerator(opt), "CUnetGeneratorv1_c8": CUnetGeneratorv1(opt8), "FrequencyModel": FrequencyModel(2, 3, 32),
+        "GridGenerator_s2": GridGenerator(opt),
     }
     sds = {k: {n: list(v.shape) for n, v in m.state_dict().items()} for k, m in mods.items()}
     nparams = {k: sum(p.numel() for p in m.parameters()) for k, m in mods.items()}

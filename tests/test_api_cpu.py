@@ -62,6 +62,7 @@ def test_cli_flags_match_reference():
     ("ResNet18_c8_64", lambda N: N.Classifier("resnet18", 8, 3, 64, device="meta", dtype=torch.float32)),
     ("UnetGenerator", lambda N: N.Generator(3, 64, 0, device="meta", dtype=torch.float32)),
     ("CUnetGeneratorv1_c8", lambda N: N.Generator(3, 64, 8, device="meta", dtype=torch.float32)),
+    ("GridGenerator_s2", lambda N: N.GridGenerator(3, 64, 2, device="meta", dtype=torch.float32)),
 ])
 def test_parameter_names_and_shapes_match_reference(key, ctor):
     from combat_b200 import nets
@@ -107,6 +108,46 @@ def test_plan_matches_oracle_selection():
     assert plan.num_bd == 0 and list(plan.bd_targets) == [2, 3, 4]
     with pytest.raises(Exception):
         make_plan(np.array([1]), default_opt(attack_mode="nope"))
+
+
+def test_variant_plans_consume_the_rng_streams_like_the_reference_variants():
+    """engine.make_plan for the input-aware step draws one more sigma right after the G-step's and a sixth transform between T3
+    and T4 (train_generator_inputaware.py:234-242); for the WaNet step nothing but the poison count and the transforms
+    (train_generator_wanet.py has no blur).  Checked against the oracle's own draws on the same seeds, transforms on."""
+    import random
+
+    import numpy as np
+
+    from combat_b200.engine import default_opt, make_plan
+    from oracle import combat_oracle as O
+    y = torch.randint(0, 10, (40,), generator=torch.Generator().manual_seed(3))
+    y[:5] = 0
+
+    def seed():
+        np.random.seed(9); torch.manual_seed(9); random.seed(9)
+
+    for variant in ("inputaware", "wanet", ""):
+        opt = default_opt(variant=variant, post_transform_option="use", dataset="cifar10")
+        seed()
+        bd = O.create_targets_bd(y, "all2one", 0, 10)
+        _, _, nbd = O.select_poison(y, bd, 0.5)
+        blur = variant != "wanet"
+        s_c = O.draw_sigma() if (nbd > 0 and blur) else None
+        t1, t2 = O.draw_post_transform(40, opt), O.draw_post_transform(40, opt)
+        s_g = O.draw_sigma() if blur else None
+        s_g2 = O.draw_sigma() if variant == "inputaware" else None
+        t3 = O.draw_post_transform(40, opt)
+        t6 = O.draw_post_transform(40, opt) if variant == "inputaware" else None
+        t4, t5 = O.draw_post_transform(40, opt), O.draw_post_transform(40, opt)
+        tail = float(torch.rand(1))
+        seed()
+        plan = make_plan(y.numpy(), opt)
+        assert float(torch.rand(1)) == tail, variant          # the torch stream is at the same position afterwards
+        assert plan.num_bd == nbd and plan.sigma_c == s_c and plan.sigma_g == s_g and plan.sigma_g2 == s_g2
+        assert plan.tf.shape[0] == (6 if variant == "inputaware" else 5)
+        for slot, prm in ((0, t1), (3, t2), (1, t3), (2, t4), (4, t5)) + (((5, t6),) if t6 is not None else ()):
+            assert np.array_equal(plan.tf[slot][:, 0], (prm["xs"] - prm["pad"]).numpy().astype(np.float32)), (variant, slot)
+            assert np.array_equal(plan.tf[slot][:, 5] != 0, prm["flip"].numpy()), (variant, slot)
 
 
 def test_multilabel_plan_matches_oracle_chunks_and_draws():
