@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(256, 3) wanet_warp_fwd4_k(const float* __restr
   extern __shared__ float4 simg4[];
   float* simg = (float*)simg4;
   constexpr int C = 3;
-  const int W = H, HW = H * H;
+  const int W = H, HW = H * H, W4 = W >> 2, G = HW >> 2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nbd = num_bd_dev ? *num_bd_dev : num_bd;
   build_table<S>(sh, H);
@@ -402,22 +402,19 @@ __global__ void __launch_bounds__(256, 3) wanet_warp_fwd4_k(const float* __restr
     }
     __syncthreads();
     float sq = 0.f, gl1 = 0.f, gl2 = 0.f;
-    // a warp owns 128 consecutive pixels per pass, a lane the pixels base + 32 j + lane (j = 0..3): consecutive lanes read consecutive
-    // shared-memory words in the table and (near the identity) in the staged image -- the first mapping, four CONSECUTIVE pixels
-    // per lane, was a 4-way bank conflict on every gather (ncu: 61 % of the shared wavefronts were conflicts, L1 pipe 83 %)
-    for (int base = warp * 128; base < HW; base += (int)(blockDim.x >> 5) * 128) {
-      int hh[4], ww[4];
+    for (int g = tid; g < G; g += blockDim.x) {
+      const int h = g / W4, w0 = (g - h * W4) << 2;
       float nx[4], ny[4];
+      noise4<S>(sh, flow, H, h, w0, nx, ny);
+      const float4 idw = __ldg((const float4*)(ident + w0));
+      const float idx_[4] = {idw.x, idw.y, idw.z, idw.w};
+      const float idh = __ldg(ident + h);
       Tap b[4];
       float w00[4], w01[4], w10[4], w11[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int pj = base + j * 32 + lane;
-        hh[j] = pj / W;
-        ww[j] = pj - hh[j] * W;
-        noise_one<S>(sh, flow, H, hh[j], ww[j], nx[j], ny[j]);
-        const float gx = fminf(fmaxf(__ldg(ident + ww[j]) * (1.f - rescale) + nx[j] * rescale, -1.f), 1.f);
-        const float gy = fminf(fmaxf(__ldg(ident + hh[j]) * (1.f - rescale) + ny[j] * rescale, -1.f), 1.f);
+        const float gx = fminf(fmaxf(idx_[j] * (1.f - rescale) + nx[j] * rescale, -1.f), 1.f);
+        const float gy = fminf(fmaxf(idh * (1.f - rescale) + ny[j] * rescale, -1.f), 1.f);
         b[j] = make_tap(gx, gy, H, W);
         w00[j] = (1.f - b[j].wx) * (1.f - b[j].wy);
         w01[j] = b[j].wx * (1.f - b[j].wy);
@@ -427,25 +424,33 @@ __global__ void __launch_bounds__(256, 3) wanet_warp_fwd4_k(const float* __restr
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         const float* pl = img + c * HW;
+        float o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float* q = pl + b[j].off;
-          dst[c * HW + base + j * 32 + lane] = ld<STAGED>(q) * w00[j] + ld<STAGED>(q + b[j].dx) * w01[j] +
-                                               ld<STAGED>(q + b[j].dy) * w10[j] + ld<STAGED>(q + b[j].dx + b[j].dy) * w11[j];
+          o[j] = ld<STAGED>(q) * w00[j] + ld<STAGED>(q + b[j].dx) * w01[j] + ld<STAGED>(q + b[j].dy) * w10[j] +
+                 ld<STAGED>(q + b[j].dx + b[j].dy) * w11[j];
         }
+        *(float4*)(dst + c * HW + h * W + w0) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+      if (noise_grid) {
+        float4* ng = (float4*)(noise_grid + ((long long)row * HW + h * W + w0) * 2);
+        ng[0] = make_float4(nx[0], ny[0], nx[1], ny[1]);
+        ng[1] = make_float4(nx[2], ny[2], nx[3], ny[3]);
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (noise_grid) *(float2*)(noise_grid + ((long long)row * HW + base + j * 32 + lane) * 2) = make_float2(nx[j], ny[j]);
-        sq += nx[j] * nx[j] + ny[j] * ny[j];
-        if (gl_partial) {   // :213-222, see the scalar kernel: the left neighbour is the previous lane's pixel (or recomputed)
-          float px_ = __shfl_up_sync(0xffffffffu, nx[j], 1), py_ = __shfl_up_sync(0xffffffffu, ny[j], 1);
-          if (ww[j] == 0) px_ = py_ = 0.f;
-          else if (lane == 0) noise_one<S>(sh, flow, H, hh[j], ww[j] - 1, px_, py_);
+      for (int j = 0; j < 4; ++j) sq += nx[j] * nx[j] + ny[j] * ny[j];
+      if (gl_partial) {   // :213-222, see the scalar kernel
+        float px_ = 0.f, py_ = 0.f;
+        if (w0 > 0) noise_one<S>(sh, flow, H, h, w0 - 1, px_, py_);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
           gl1 += (nx[j] - px_) * (nx[j] - px_) + (ny[j] - py_) * (ny[j] - py_);
-          if (ww[j] == W - 1) gl1 += nx[j] * nx[j] + ny[j] * ny[j];
           gl2 += nx[j] * nx[j] + (ny[j] - nx[j]) * (ny[j] - nx[j]) + ny[j] * ny[j];
+          px_ = nx[j];
+          py_ = ny[j];
         }
+        if (w0 + 4 == W) gl1 += px_ * px_ + py_ * py_;
       }
     }
     if (sq_partial || gl_partial) {
@@ -483,7 +488,7 @@ __global__ void __launch_bounds__(256, 3) wanet_warp_bwd4_k(const float* __restr
   extern __shared__ float4 simg4[];
   float* simg = (float*)simg4;
   constexpr int NF = 2 * S * S, C = 3;
-  const int W = H, HW = H * H;
+  const int W = H, HW = H * H, W4 = W >> 2, G = HW >> 2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   build_table<S>(sh, H);
   const int Q = (C * HW) >> 2;
@@ -528,38 +533,35 @@ __global__ void __launch_bounds__(256, 3) wanet_warp_bwd4_k(const float* __restr
     float acc[NF];
 #pragma unroll
     for (int k = 0; k < NF; ++k) acc[k] = 0.f;
-    for (int base = warp * 128; base < HW; base += (int)(blockDim.x >> 5) * 128) {   // pixel mapping: see the forward kernel
+    for (int g = tid; g < G; g += blockDim.x) {
+      const int h = g / W4, w0 = (g - h * W4) << 2;
       // the incoming gradients of the four pixels, all channels: issued first, independent of everything below
-      float gq[C][4];
+      float4 gq[C];
 #pragma unroll
-      for (int c = 0; c < C; ++c)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int pj = base + j * 32 + lane;
-          if (PIPE) {
-            gq[c][j] = gsm[c * HW + pj];
-          } else {
-            const long long gi = ((long long)n * C + c) * HW + pj;
-            gq[c][j] = __ldg(g1 + gi);
-            if (g2) gq[c][j] += __ldg(g2 + gi);
-          }
+      for (int c = 0; c < C; ++c) {
+        const long long gi = ((long long)n * C + c) * HW + h * W + w0;
+        gq[c] = PIPE ? *(const float4*)(gsm + c * HW + h * W + w0) : __ldg((const float4*)(g1 + gi));
+        if (!PIPE && g2) {
+          const float4 g2v = __ldg((const float4*)(g2 + gi));
+          gq[c].x += g2v.x; gq[c].y += g2v.y; gq[c].z += g2v.z; gq[c].w += g2v.w;
         }
-      int hh[4], ww[4];
+      }
       float nx[4], ny[4], rx[4], ry[4], dix[4], diy[4];
+      noise4<S>(sh, flow, H, h, w0, nx, ny);
+      const float4 idw = __ldg((const float4*)(ident + w0));
+      const float idx_[4] = {idw.x, idw.y, idw.z, idw.w};
+      const float idh = __ldg(ident + h);
       Tap b[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int pj = base + j * 32 + lane;
-        hh[j] = pj / W;
-        ww[j] = pj - hh[j] * W;
-        noise_one<S>(sh, flow, H, hh[j], ww[j], nx[j], ny[j]);
-        rx[j] = __ldg(ident + ww[j]) * (1.f - rescale) + nx[j] * rescale;
-        ry[j] = __ldg(ident + hh[j]) * (1.f - rescale) + ny[j] * rescale;
+        rx[j] = idx_[j] * (1.f - rescale) + nx[j] * rescale;
+        ry[j] = idh * (1.f - rescale) + ny[j] * rescale;
         b[j] = make_tap(fminf(fmaxf(rx[j], -1.f), 1.f), fminf(fmaxf(ry[j], -1.f), 1.f), H, W);
         dix[j] = diy[j] = 0.f;
       }
 #pragma unroll
       for (int c = 0; c < C; ++c) {
+        const float gg[4] = {gq[c].x, gq[c].y, gq[c].z, gq[c].w};
         const float* pl = img + c * HW;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -571,21 +573,25 @@ __global__ void __launch_bounds__(256, 3) wanet_warp_bwd4_k(const float* __restr
           const float v01 = ld<STAGED>(q + b[j].dx) * mx;
           const float v10 = ld<STAGED>(q + b[j].dy) * my;
           const float v11 = ld<STAGED>(q + b[j].dx + b[j].dy) * (mx * my);
-          dix[j] = fmaf(gq[c][j], (v01 - v00) * (1.f - b[j].wy) + (v11 - v10) * b[j].wy, dix[j]);
-          diy[j] = fmaf(gq[c][j], (v10 - v00) * (1.f - b[j].wx) + (v11 - v01) * b[j].wx, diy[j]);
+          dix[j] = fmaf(gg[j], (v01 - v00) * (1.f - b[j].wy) + (v11 - v10) * b[j].wy, dix[j]);
+          diy[j] = fmaf(gg[j], (v10 - v00) * (1.f - b[j].wx) + (v11 - v01) * b[j].wx, diy[j]);
         }
       }
+      float wy[S];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        // clamp passes the gradient where -1 <= raw <= 1 (torch.clamp backward), then the blend with the identity grid
-        const float dnx = ((rx[j] >= -1.f && rx[j] <= 1.f) ? dix[j] * 0.5f * (float)(W - 1) * rescale : 0.f) + l2_scale * nx[j];
-        const float dny = ((ry[j] >= -1.f && ry[j] <= 1.f) ? diy[j] * 0.5f * (float)(H - 1) * rescale : 0.f) + l2_scale * ny[j];
+      for (int py = 0; py < S; ++py) wy[py] = sh.wt[py * H + h];
 #pragma unroll
-        for (int py = 0; py < S; ++py) {
-          const float wy = sh.wt[py * H + hh[j]];
+      for (int px = 0; px < S; ++px) {
+        const float4 wx4 = *(const float4*)(sh.wt + px * H + w0);
+        const float wxv[4] = {wx4.x, wx4.y, wx4.z, wx4.w};
 #pragma unroll
-          for (int px = 0; px < S; ++px) {
-            const float k = wy * sh.wt[px * H + ww[j]];
+        for (int j = 0; j < 4; ++j) {
+          // clamp passes the gradient where -1 <= raw <= 1 (torch.clamp backward), then the blend with the identity grid
+          const float dnx = ((rx[j] >= -1.f && rx[j] <= 1.f) ? dix[j] * 0.5f * (float)(W - 1) * rescale : 0.f) + l2_scale * nx[j];
+          const float dny = ((ry[j] >= -1.f && ry[j] <= 1.f) ? diy[j] * 0.5f * (float)(H - 1) * rescale : 0.f) + l2_scale * ny[j];
+#pragma unroll
+          for (int py = 0; py < S; ++py) {
+            const float k = wy[py] * wxv[j];
             acc[py * S + px] = fmaf(k, dnx, acc[py * S + px]);
             acc[S * S + py * S + px] = fmaf(k, dny, acc[S * S + py * S + px]);
           }
@@ -642,7 +648,7 @@ extern "C" int combat_wanet_warp_fwd(const float* x, const float* z, const float
   COMBAT_ARG(S >= 1 && S <= WARP_MAX_S, 15);
   COMBAT_ARG(perm || !(noise_grid || sq_partial || gl_partial) || num_bd >= rows || num_bd_dev, 5);
   if (rows == 0) return 0;
-  if (C == 3 && (H * W) % 128 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)out % 16) == 0 && ((uintptr_t)ident % 16) == 0 &&
+  if (C == 3 && W % 4 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)out % 16) == 0 && ((uintptr_t)ident % 16) == 0 &&
       (!noise_grid || ((uintptr_t)noise_grid % 16) == 0)) {
     size_t bytes;
     const bool staged = warp_staged(H, &bytes);
@@ -679,7 +685,7 @@ extern "C" int combat_wanet_warp_bwd(const float* x, const float* z, const float
   COMBAT_ARG(rows >= 0 && C > 0 && H > 1 && H == W && H <= WARP_MAX_HW, 8);
   COMBAT_ARG(S >= 1 && S <= WARP_MAX_S, 12);
   if (rows == 0) return 0;
-  if (C == 3 && (H * W) % 128 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)g1 % 16) == 0 && ((uintptr_t)ident % 16) == 0 &&
+  if (C == 3 && W % 4 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)g1 % 16) == 0 && ((uintptr_t)ident % 16) == 0 &&
       (!g2 || ((uintptr_t)g2 % 16) == 0)) {
     size_t bytes;
     const bool staged = warp_staged(H, &bytes);
