@@ -245,10 +245,12 @@ class NetBase:
     def _tc_ok(self, cs: ConvSpec):
         return self.use_tc and cs.Cin % 64 == 0 and cs.Cout % 64 == 0
 
-    def conv_fwd(self, x, cs: ConvSpec, residual=None, pre=True, bn_relu=None, want_out=True, stats=False):
+    def conv_fwd(self, x, cs: ConvSpec, residual=None, pre=True, bn_relu=None, want_out=True, stats=False, post=None):
         """x: NHWC [N,H,W,Cin] in the activation dtype -> NHWC out (float32 when `pre`, i.e. feeding a norm).
         bn_relu=(scale, shift): the tcgen05 epilogue ALSO writes out2 = bf16 relu(out*scale+shift) (eval BatchNorm+ReLU of
-        the consumer); returns (out or None, out2) then."""
+        the consumer); returns (out or None, out2) then.
+        post=(scale, shift): out = (acc + bias) * scale + shift + residual (an eval-mode BatchNorm BEHIND this conv, the residual
+        added after it -- the non-PreAct ResNet ordering; tcgen05 path only)."""
         N, H, W, Ct = x.shape
         Ho = (H + 2 * cs.pad - cs.k) // cs.stride + 1
         Wo = (W + 2 * cs.pad - cs.k) // cs.stride + 1
@@ -256,7 +258,8 @@ class NetBase:
             out = torch.empty((N, Ho, Wo, cs.Cout), dtype=self.pre_dtype, device=self.device) if want_out else None
             out2 = torch.empty((N, Ho, Wo, cs.Cout), dtype=self.dtype, device=self.device)
             d = ops.conv_tc_desc(x, self._wptr(cs), out, N, H, W, cs.Cin, Ho, Wo, cs.Cout, cs.k, cs.k, cs.stride, cs.pad, 1,
-                                 bias=self._bias(cs), residual=residual, out2=out2, scale2=bn_relu[0], shift2=bn_relu[1])
+                                 bias=self._bias(cs), residual=residual, out2=out2, scale2=bn_relu[0], shift2=bn_relu[1],
+                                 post_scale=post[0] if post is not None else None, post_shift=post[1] if post is not None else None)
             d.res_f32 = int(residual is not None and residual.dtype == torch.float32)
             if not (self._tc_ok(cs) and Ct == cs.Cin and lib.combat_conv_tc_supported(C.byref(d))):
                 raise RuntimeError("fused BatchNorm epilogue needs the tcgen05 path")
@@ -268,13 +271,16 @@ class NetBase:
         if self._tc_ok(cs) and Ct == cs.Cin:
             want_stats = stats and pre and cs.Cout <= 512
             d = ops.conv_tc_desc(x, self._wptr(cs), out, N, H, W, cs.Cin, Ho, Wo, cs.Cout, cs.k, cs.k, cs.stride, cs.pad, 1,
-                                 bias=self._bias(cs), residual=residual, stats=ops.Scratch.get(self.device) if want_stats else None)
+                                 bias=self._bias(cs), residual=residual, stats=ops.Scratch.get(self.device) if want_stats else None,
+                                 post_scale=post[0] if post is not None else None, post_shift=post[1] if post is not None else None)
             if lib.combat_conv_tc_supported(C.byref(d)):
                 _tc_launch(lambda: lib.combat_conv_tc(C.byref(d), ops._s()), "conv_tc", 2.0 * N * Ho * Wo * cs.Cout * cs.Cin * cs.k * cs.k,
                            _tag(N, H, W, cs) + (" +stats" if want_stats else ""))
                 if want_stats:
                     self.last_stats_nblk = lib.combat_conv_tc_last_grid()
                 return out
+        if post is not None:
+            raise RuntimeError("fused BatchNorm epilogue needs the tcgen05 path")
         ops.conv_simt(x, (N, H, W), ops.nhwc_strides(H, W, Ct), self._wptr(cs), self.dt, out, (Ho, Wo),
                       ops.nhwc_strides(Ho, Wo, cs.Cout), Ci=cs.Cin, Co=cs.Cout, KH=cs.k, KW=cs.k, stride=cs.stride,
                       pad=cs.pad, bias=self._bias(cs), residual=residual)
@@ -522,8 +528,10 @@ class Classifier(NetBase):
             n += bn.C
         self.n_bn_ch = n
         self._aff_table = torch.tensor(tab, dtype=torch.int32).to(self.device) if self.device.type == "cuda" else None
-        # the fused eval path (BatchNorm+ReLU in the tcgen05 epilogues) exists for the PreAct ordering on the bf16 path
-        self.fuse_eval = pre and self.use_tc
+        # the fused eval path (BatchNorm+ReLU in the tcgen05 epilogues, bf16 path): PreAct ordering (round 1) and, [r2], the plain
+        # ResNet ordering conv-bn-relu-conv-bn-add-relu (post-affine residual epilogue); COMBAT_NO_FUSE_RESNET=1 for A/B
+        self.fuse_eval = self.use_tc and (pre or not os.environ.get("COMBAT_NO_FUSE_RESNET"))
+        self._unit = {}
 
     def eval_affine(self):
         out = torch.empty((2, self.n_bn_ch), dtype=torch.float32, device=self.device)
@@ -658,6 +666,8 @@ class Classifier(NetBase):
             o = self.aff_off[bn.name]
             return aff[0, o:o + bn.C], aff[1, o:o + bn.C]
 
+        if self.arch != "preact_resnet18":
+            return self._forward_eval_fused_resnet(x_nchw, save, sl)
         ctx = {"x": x_nchw, "train": False, "fused": True, "blocks": []} if save else None
         blocks = self.blocks
         sc1 = sl(blocks[0]["bn1"])
@@ -679,6 +689,64 @@ class Classifier(NetBase):
             ctx["feat_shape"], ctx["pooled"] = tuple(h.shape), pooled
         return logits, ctx
 
+    def _unit_affine(self, Cc):
+        u = self._unit.get(Cc)
+        if u is None:
+            u = self._unit[Cc] = (torch.ones(Cc, dtype=torch.float32, device=self.device),
+                                  torch.zeros(Cc, dtype=torch.float32, device=self.device))
+        return u
+
+    def _forward_eval_fused_resnet(self, x_nchw, save, sl):
+        """Eval-mode forward of the plain ResNet block ordering (classifier_models/resnet.py:22-32: relu(bn1(conv1(x))),
+        bn2(conv2(.)) + shortcut(x), relu) with every BatchNorm folded into a tcgen05 epilogue: conv1 writes relu(bn1(.)) directly,
+        the 1x1 shortcut conv writes its BatchNorm's output (post affine), conv2 computes (acc * scale2 + shift2) + shortcut and
+        writes relu(.) -- three launches per block (two without a shortcut conv), no elementwise pass."""
+        ctx = {"x": x_nchw, "train": False, "fused": True, "blocks": []} if save else None
+        s0 = sl(self.bn1)
+        _, h = self.conv_first_fwd(x_nchw, self.conv1, bn_relu=s0)                                  # resnet.py:86
+        if save:
+            ctx["stem"] = (h, s0[0])
+        for blk in self.blocks:
+            s1, s2 = sl(blk["bn1"]), sl(blk["bn2"])
+            if "sc" in blk:
+                ssc = sl(blk["scbn"])
+                s = self.conv_fwd(h, blk["sc"], pre=False, post=ssc)
+            else:
+                ssc, s = None, h
+            _, o1 = self.conv_fwd(h, blk["conv1"], bn_relu=s1, want_out=False)
+            _, out = self.conv_fwd(o1, blk["conv2"], residual=s, post=s2, bn_relu=self._unit_affine(blk["conv2"].Cout), want_out=False)
+            if save:
+                ctx["blocks"].append((o1, out, s1[0], s2[0], ssc[0] if ssc is not None else None))
+            h = out
+        logits, pooled = ops.pool_linear_fwd(h, 4, self.store.p("linear.weight"), self.store.p("linear.bias"))
+        if save:
+            ctx["feat_shape"], ctx["pooled"] = tuple(h.shape), pooled
+        return logits, ctx
+
+    def _backward_eval_fused_resnet(self, ctx, dlogits, need_dx):
+        """Input gradient of the forward above: per block ONE elementwise pass (relu mask of the block output, times bn2's scale;
+        the unscaled masked gradient goes to the shortcut) and two tcgen05 input-gradient launches -- conv2's carries the
+        relu(bn1(.)) backward in its epilogue, conv1's adds the identity-shortcut gradient or carries the 1x1 shortcut conv as
+        an extra tap."""
+        st = self.store
+        dh = ops.pool_linear_bwd(dlogits, ctx["pooled"], st.p("linear.weight"), ctx["feat_shape"], self.dtype, 4, dW=None, db=None)
+        prev_in = [ctx["stem"][0]] + [b[1] for b in ctx["blocks"][:-1]]   # input tensor of every block (for its spatial size)
+        for blk, (o1, out, scale1, scale2, scale_sc), h_in in zip(reversed(self.blocks), reversed(ctx["blocks"]), reversed(prev_in)):
+            hw_in, hw_mid = h_in.shape[1:3], o1.shape[1:3]
+            d_c2, d_pre = ops.bn_bwd_eval(dh, out, scale2, True, None, True)
+            d_c1 = self.conv_dgrad(d_c2, blk["conv2"], hw_mid, mask=o1, mask_scale=scale1)
+            if "sc" in blk:
+                zero = self._unit_affine(blk["sc"].Cout)[1]
+                d_cs = ops.affine_act(d_pre, scale_sc, zero, False)
+                dh = self.conv_dgrad(d_c1, blk["conv1"], hw_in, shortcut=(d_cs, blk["sc"]))
+            else:
+                dh = self.conv_dgrad(d_c1, blk["conv1"], hw_in, residual=d_pre)
+        h0, scale0 = ctx["stem"]
+        d_c0, _ = ops.bn_bwd_eval(dh, h0, scale0, True, None, False)
+        if need_dx:
+            return self.conv_first_dgrad(d_c0, self.conv1, ctx["x"].shape[2:4])
+        return None
+
     @staticmethod
     def slice_ctx(ctx, lo, hi):
         """The saved state of rows [lo, hi) of a fused eval-mode forward (batch-major tensors: slices are contiguous views) --
@@ -687,12 +755,17 @@ class Classifier(NetBase):
             raise RuntimeError("slice_ctx needs a fused eval-mode context")
         out = dict(ctx)
         out["x"] = ctx["x"][lo:hi]
-        out["blocks"] = [(o1[lo:hi], o2[lo:hi], s1, s2) for (o1, o2, s1, s2) in ctx["blocks"]]
+        cut = lambda t: t[lo:hi] if (torch.is_tensor(t) and t.dim() == 4) else t   # activations; per-channel scales pass through
+        out["blocks"] = [tuple(cut(t) for t in blk) for blk in ctx["blocks"]]
+        if "stem" in ctx:
+            out["stem"] = tuple(cut(t) for t in ctx["stem"])
         out["pooled"] = ctx["pooled"][lo:hi]
         out["feat_shape"] = (hi - lo,) + tuple(ctx["feat_shape"][1:])
         return out
 
     def _backward_eval_fused(self, ctx, dlogits, need_dx):
+        if self.arch != "preact_resnet18":
+            return self._backward_eval_fused_resnet(ctx, dlogits, need_dx)
         st = self.store
         dh = ops.pool_linear_bwd(dlogits, ctx["pooled"], st.p("linear.weight"), ctx["feat_shape"], self.dtype, 4, dW=None, db=None)
         for blk, (o1, o2, scale1, scale2) in zip(reversed(self.blocks), reversed(ctx["blocks"])):

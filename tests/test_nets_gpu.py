@@ -282,3 +282,59 @@ def test_fused_eval_path_equals_unfused(pre, monkeypatch):
     torch.nn.functional.cross_entropy(lo, t.cpu()).backward()
     assert float((outs[0][0].cpu().double() - lo).norm() / lo.norm()) < 3e-2
     assert float((outs[0][1].cpu().double() - xr.grad).norm() / xr.grad.norm()) < 1e-1
+
+
+@pytest.mark.parametrize("size,ncls,N", [(64, 8, 6), (32, 10, 8)])
+def test_fused_eval_path_of_the_plain_resnet_equals_unfused(size, ncls, N):
+    """[r2] The non-PreAct ResNet18 (classifier_models/resnet.py: relu(bn1(conv1)), bn2(conv2) + shortcut, relu) with every
+    eval-mode BatchNorm folded into a tcgen05 epilogue (post-affine residual) against the unfused kernels of the same network
+    (one bf16 rounding apart per layer: the fused epilogue normalises the accumulator, the unfused path the stored tensor) and
+    against the float64 oracle; the batched [x ; x] forward with a sliced context gives the same input gradient."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from combat_b200 import ops
+    from combat_b200.nets import Classifier
+    from oracle import combat_oracle as O
+    gen = torch.Generator().manual_seed(6)
+    scaler = {32: 1, 64: 4}[size]
+    p, b = O.init_resnet18_state(gen, num_classes=ncls, scaler=scaler)
+    for k in b:
+        if k.endswith("running_mean"):
+            b[k] = torch.randn(b[k].shape, generator=gen) * 0.1
+        elif k.endswith("running_var"):
+            b[k] = torch.rand(b[k].shape, generator=gen) + 0.5
+    for k in p:
+        if k.endswith("bn1.weight") or k.endswith("bn2.weight") or k.endswith("shortcut.1.weight"):
+            p[k] = torch.rand(p[k].shape, generator=gen) + 0.5      # non-trivial BatchNorm scales / shifts
+        elif k.endswith("bn1.bias") or k.endswith("bn2.bias") or k.endswith("shortcut.1.bias"):
+            p[k] = torch.randn(p[k].shape, generator=gen) * 0.1
+    net = Classifier("resnet18", ncls, 3, size, device="cuda", dtype=torch.bfloat16)
+    assert net.fuse_eval
+    net.load_state_dict({**p, **b})
+    x = (torch.rand(N, 3, size, size, generator=gen) * 2 - 1).cuda()
+    t = torch.randint(0, ncls, (N,), generator=gen).cuda()
+    outs = []
+    for fuse in (True, False):
+        logits, ctx = net.forward(x, train=False, save=True, fuse=fuse)
+        assert bool(ctx.get("fused")) == fuse
+        _, dl, _ = ops.cross_entropy(logits, t, 1.0, True)
+        dx = net.backward(ctx, dl, need_wgrad=False, need_dx=True)
+        outs.append((logits.clone(), dx.clone()))
+    e = float((outs[0][0] - outs[1][0]).norm() / outs[1][0].norm())
+    assert e < 1e-2, e
+    e = float((outs[0][1] - outs[1][1]).norm() / outs[1][1].norm())
+    assert e < 1.2e-1, e
+    pr = {k: v.double() for k, v in p.items()}
+    br = {k: (v.double() if v.is_floating_point() else v) for k, v in b.items()}
+    xr = x.cpu().double().requires_grad_(True)
+    lo = O.resnet18_forward(pr, br, xr, False)
+    torch.nn.functional.cross_entropy(lo, t.cpu()).backward()
+    assert float((outs[0][0].cpu().double() - lo).norm() / lo.norm()) < 3e-2
+    assert float((outs[0][1].cpu().double() - xr.grad).norm() / xr.grad.norm()) < 1e-1
+    # batched forward over [x ; x], back-propagating only the second half through a sliced context
+    x2 = torch.cat([x, x])
+    lg, ctx2 = net.forward(x2, train=False, save=True)
+    assert torch.equal(lg[:N], lg[N:])
+    _, dl, _ = ops.cross_entropy(lg[N:], t, 1.0, True)
+    dxb = net.backward(net.slice_ctx(ctx2, N, 2 * N), dl, need_wgrad=False, need_dx=True)
+    assert float((dxb - outs[0][1]).norm() / outs[0][1].norm()) < 1e-5
