@@ -79,6 +79,9 @@ _SIGS = {
     "combat_bn_bwd_fused": ([vp, vp, i32, vp, vp, vp, vp, i32, i64, i32, vp, vp, vp, vp, i32, vp, vp, i32, vp], i32),
     "combat_instnorm_fwd": ([vp, i32, vp, vp, i32, i32, i32, i32, f32, f32, i32, vp, vp, vp], i32),
     "combat_instnorm_bwd": ([vp, vp, vp, i32, vp, i32, i32, i32, i32, f32, i32, vp, vp, vp], i32),
+    "combat_instnorm_splits": ([i32, i32, i32], i32),
+    "combat_instnorm_fwd_split": ([vp, i32, vp, vp, i32, i32, i32, i32, f32, f32, i32, vp, vp, vp, i32, vp], i32),
+    "combat_instnorm_bwd_split": ([vp, vp, vp, i32, vp, i32, i32, i32, i32, f32, i32, vp, vp, vp, i32, vp], i32),
     "combat_upsample2x_act": ([vp, vp, i32, i32, i32, i32, i32, f32, vp], i32),
     "combat_upsample2x_act_bwd": ([vp, vp, vp, i32, i32, i32, i32, i32, f32, vp], i32),
     "combat_leaky_relu": ([vp, vp, i32, i64, f32, vp], i32),

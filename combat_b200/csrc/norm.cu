@@ -750,6 +750,191 @@ __global__ void __launch_bounds__(256) instnorm_bwd_k(const T* __restrict__ dy1,
     }
 }
 
+// ---- large planes (ImageNet-10 shape: 112 x 112 = 12,544 pixels per (sample, channel), batch 64 -> only N * C/64 = 64 CTAs above, each
+// streaming 3.2 MB three times: 732 us per launch, 12 % of that step).  The plane is split over K CTAs: the first kernel leaves
+// per-chunk (mean, centred sum of squares) partials, the second merges them (Chan's parallel-variance formula: the same centred
+// two-pass statistic up to rounding) and applies the normalisation to its chunk.  grid = (N, C/64, K).
+template <typename TX>
+__global__ void __launch_bounds__(256) instnorm_part_k(const TX* __restrict__ x, int HW, int C, int K, float* __restrict__ part) {
+  pdl_entry();
+  const int n = blockIdx.x, k = blockIdx.z;
+  const int c = 2 * (blockIdx.y * CR_TX + threadIdx.x);
+  const bool ok = c < C;
+  const int rows = (HW + K - 1) / K, r0 = k * rows, r1 = min(HW, r0 + rows);
+  const long long base = (long long)n * HW * C + c;
+  float2 s = {0.f, 0.f}, dummy = {0.f, 0.f};
+  if (ok)
+    for (int r = r0 + threadIdx.y; r < r1; r += CR_TY) {
+      float2 v = ld2<TX>(x + base + (long long)r * C);
+      s.x += v.x; s.y += v.y;
+    }
+  block_reduce_y(s, dummy);
+  __shared__ float2 bc[CR_TX];
+  const float cnt = (float)max(r1 - r0, 1);
+  if (threadIdx.y == 0) bc[threadIdx.x] = make_float2(s.x / cnt, s.y / cnt);
+  __syncthreads();
+  const float2 mean = bc[threadIdx.x];
+  float2 q = {0.f, 0.f};
+  if (ok)
+    for (int r = r0 + threadIdx.y; r < r1; r += CR_TY) {
+      float2 v = ld2<TX>(x + base + (long long)r * C);
+      float a = v.x - mean.x, b = v.y - mean.y;
+      q.x = fmaf(a, a, q.x); q.y = fmaf(b, b, q.y);
+    }
+  block_reduce_y(q, dummy);
+  if (threadIdx.y == 0 && ok) {
+    float* p0 = part + (((long long)n * K + k) * 2) * C + c;   // [N][K][2][C]: chunk mean | chunk centred sum of squares
+    p0[0] = mean.x; p0[1] = mean.y;
+    p0[C] = q.x; p0[C + 1] = q.y;
+  }
+}
+
+template <typename TX, typename T>
+__global__ void __launch_bounds__(256) instnorm_apply_k(const TX* __restrict__ x, const T* __restrict__ skip, T* __restrict__ y,
+                                                        int HW, int C, int K, float eps, float slope, int act,
+                                                        const float* __restrict__ part, float* __restrict__ save_mean,
+                                                        float* __restrict__ save_invstd) {
+  pdl_entry();
+  const int n = blockIdx.x, k = blockIdx.z;
+  const int c = 2 * (blockIdx.y * CR_TX + threadIdx.x);
+  const bool ok = c < C;
+  const int rows = (HW + K - 1) / K, r0 = k * rows, r1 = min(HW, r0 + rows);
+  const long long base = (long long)n * HW * C + c;
+  __shared__ float2 bc[CR_TX], bi[CR_TX];
+  if (threadIdx.y == 0) {
+    float2 mean = {0.f, 0.f}, m2 = {0.f, 0.f};
+    if (ok) {
+      const float* p0 = part + ((long long)n * K * 2) * C + c;
+      for (int j = 0; j < K; ++j) {   // overall mean: chunk means weighted by their row counts
+        const float cj = (float)max(min(HW, (j + 1) * rows) - j * rows, 0);
+        mean.x += cj * p0[(long long)j * 2 * C]; mean.y += cj * p0[(long long)j * 2 * C + 1];
+      }
+      mean.x /= (float)HW; mean.y /= (float)HW;
+      for (int j = 0; j < K; ++j) {   // M2 = sum_j (M2_j + n_j (mean_j - mean)^2)
+        const float cj = (float)max(min(HW, (j + 1) * rows) - j * rows, 0);
+        const float dx = p0[(long long)j * 2 * C] - mean.x, dy = p0[(long long)j * 2 * C + 1] - mean.y;
+        m2.x += p0[(long long)j * 2 * C + C] + cj * dx * dx; m2.y += p0[(long long)j * 2 * C + C + 1] + cj * dy * dy;
+      }
+    }
+    const float2 iv = make_float2(1.0f / sqrtf(m2.x / (float)HW + eps), 1.0f / sqrtf(m2.y / (float)HW + eps));
+    bc[threadIdx.x] = mean;
+    bi[threadIdx.x] = iv;
+    if (ok && k == 0) {
+      save_mean[(long long)n * C + c] = mean.x; save_mean[(long long)n * C + c + 1] = mean.y;
+      save_invstd[(long long)n * C + c] = iv.x; save_invstd[(long long)n * C + c + 1] = iv.y;
+    }
+  }
+  __syncthreads();
+  const float2 mean = bc[threadIdx.x], inv = bi[threadIdx.x];
+  if (ok)
+    for (int r = r0 + threadIdx.y; r < r1; r += CR_TY) {
+      const long long o = base + (long long)r * C;
+      float2 v = ld2<TX>(x + o);
+      v.x = (v.x - mean.x) * inv.x;
+      v.y = (v.y - mean.y) * inv.y;
+      if (act) {
+        v.x = v.x > 0.f ? v.x : v.x * slope;
+        v.y = v.y > 0.f ? v.y : v.y * slope;
+      }
+      if (skip) {
+        float2 kk = ld2<T>(skip + o);
+        v.x += kk.x; v.y += kk.y;
+      }
+      st2<T>(y + o, v);
+    }
+}
+
+// backward, split the same way: chunk sums of g and g * xhat, then merge + apply
+template <typename TX, typename T>
+__global__ void __launch_bounds__(256) instnorm_bwd_part_k(const T* __restrict__ dy1, const T* __restrict__ dy2,
+                                                           const TX* __restrict__ x, int HW, int C, int K, float slope, int act,
+                                                           const float* __restrict__ mean_, const float* __restrict__ invstd_,
+                                                           float* __restrict__ part) {
+  pdl_entry();
+  const int n = blockIdx.x, k = blockIdx.z;
+  const int c = 2 * (blockIdx.y * CR_TX + threadIdx.x);
+  const bool ok = c < C;
+  const int rows = (HW + K - 1) / K, r0 = k * rows, r1 = min(HW, r0 + rows);
+  const long long base = (long long)n * HW * C + c;
+  float2 mean = {0.f, 0.f}, inv = {0.f, 0.f};
+  if (ok) {
+    mean = make_float2(mean_[(long long)n * C + c], mean_[(long long)n * C + c + 1]);
+    inv = make_float2(invstd_[(long long)n * C + c], invstd_[(long long)n * C + c + 1]);
+  }
+  float2 s = {0.f, 0.f}, sx = {0.f, 0.f};
+  if (ok)
+    for (int r = r0 + threadIdx.y; r < r1; r += CR_TY) {
+      const long long o = base + (long long)r * C;
+      float2 g = ld2<T>(dy1 + o);
+      if (dy2) { float2 g2 = ld2<T>(dy2 + o); g.x += g2.x; g.y += g2.y; }
+      float2 v = ld2<TX>(x + o);
+      float xh0 = (v.x - mean.x) * inv.x, xh1 = (v.y - mean.y) * inv.y;
+      if (act) {
+        if (!(xh0 > 0.f)) g.x *= slope;
+        if (!(xh1 > 0.f)) g.y *= slope;
+      }
+      s.x += g.x; s.y += g.y;
+      sx.x = fmaf(g.x, xh0, sx.x); sx.y = fmaf(g.y, xh1, sx.y);
+    }
+  block_reduce_y(s, sx);
+  if (threadIdx.y == 0 && ok) {
+    float* p0 = part + (((long long)n * K + k) * 2) * C + c;
+    p0[0] = s.x; p0[1] = s.y;
+    p0[C] = sx.x; p0[C + 1] = sx.y;
+  }
+}
+
+template <typename TX, typename T>
+__global__ void __launch_bounds__(256) instnorm_bwd_apply_k(const T* __restrict__ dy1, const T* __restrict__ dy2,
+                                                            const TX* __restrict__ x, T* __restrict__ dx, int HW, int C, int K,
+                                                            float slope, int act, const float* __restrict__ mean_,
+                                                            const float* __restrict__ invstd_, const float* __restrict__ part) {
+  pdl_entry();
+  const int n = blockIdx.x, k = blockIdx.z;
+  const int c = 2 * (blockIdx.y * CR_TX + threadIdx.x);
+  const bool ok = c < C;
+  const int rows = (HW + K - 1) / K, r0 = k * rows, r1 = min(HW, r0 + rows);
+  const long long base = (long long)n * HW * C + c;
+  float2 mean = {0.f, 0.f}, inv = {0.f, 0.f}, mg = {0.f, 0.f}, mgx = {0.f, 0.f};
+  if (ok) {
+    mean = make_float2(mean_[(long long)n * C + c], mean_[(long long)n * C + c + 1]);
+    inv = make_float2(invstd_[(long long)n * C + c], invstd_[(long long)n * C + c + 1]);
+    const float* p0 = part + ((long long)n * K * 2) * C + c;
+    for (int j = 0; j < K; ++j) {
+      mg.x += p0[(long long)j * 2 * C]; mg.y += p0[(long long)j * 2 * C + 1];
+      mgx.x += p0[(long long)j * 2 * C + C]; mgx.y += p0[(long long)j * 2 * C + C + 1];
+    }
+    mg.x /= (float)HW; mg.y /= (float)HW; mgx.x /= (float)HW; mgx.y /= (float)HW;
+  }
+  if (ok)
+    for (int r = r0 + threadIdx.y; r < r1; r += CR_TY) {
+      const long long o = base + (long long)r * C;
+      float2 g = ld2<T>(dy1 + o);
+      if (dy2) { float2 g2 = ld2<T>(dy2 + o); g.x += g2.x; g.y += g2.y; }
+      float2 v = ld2<TX>(x + o);
+      float xh0 = (v.x - mean.x) * inv.x, xh1 = (v.y - mean.y) * inv.y;
+      if (act) {
+        if (!(xh0 > 0.f)) g.x *= slope;
+        if (!(xh1 > 0.f)) g.y *= slope;
+      }
+      float2 d;
+      d.x = inv.x * (g.x - mg.x - xh0 * mgx.x);
+      d.y = inv.y * (g.y - mg.y - xh1 * mgx.y);
+      st2<T>(dx + o, d);
+    }
+}
+
+// number of plane chunks: 1 (the single-kernel path) unless the plane is large and the grid would leave most SMs idle
+static int instnorm_splits(int N, int HW, int C) {
+  const long long ctas = (long long)N * cdiv(C, CR_CPB);
+  if (HW < 4096 || ctas >= 296) return 1;
+  int k = (int)((592 + ctas - 1) / ctas);   // ~4 CTAs per SM
+  if (k > 32) k = 32;
+  while (k > 1 && HW / k < 256) --k;
+  return k;
+}
+extern "C" int combat_instnorm_splits(int N, int HW, int C) { return instnorm_splits(N, HW, C); }
+
 extern "C" int combat_instnorm_fwd(const void* x, int x_dtype, const void* skip, void* y, int dtype, int N, int HW, int C, float eps,
                                    float slope, int act, float* save_mean, float* save_invstd, void* stream) {
   COMBAT_ARG(x && y && save_mean && save_invstd, 0);
@@ -760,6 +945,19 @@ extern "C" int combat_instnorm_fwd(const void* x, int x_dtype, const void* skip,
   COMBAT_RETURN_LAUNCH("instnorm_fwd");
 }
 
+extern "C" int combat_instnorm_fwd_split(const void* x, int x_dtype, const void* skip, void* y, int dtype, int N, int HW, int C,
+                                         float eps, float slope, int act, float* save_mean, float* save_invstd, float* part, int K,
+                                         void* stream) {
+  COMBAT_ARG(x && y && save_mean && save_invstd && part, 0);
+  COMBAT_ARG(N > 0 && HW > 0 && C > 0 && (C % 2) == 0 && K >= 1 && K <= 32, 4);
+  dim3 grid(N, cdiv(C, CR_CPB), K), block(CR_TX, CR_TY);
+  DISPATCH_2(x_dtype, dtype, pdl_launch(instnorm_part_k<TX>, grid, block, 0, (cudaStream_t)stream, (const TX*)x, HW, C, K, part);)
+  COMBAT_CHECK_LAUNCH("instnorm_part");
+  DISPATCH_2(x_dtype, dtype, pdl_launch(instnorm_apply_k<TX, T>, grid, block, 0, (cudaStream_t)stream, (const TX*)x, (const T*)skip,
+                                        (T*)y, HW, C, K, eps, slope, act, (const float*)part, save_mean, save_invstd);)
+  COMBAT_RETURN_LAUNCH("instnorm_apply");
+}
+
 extern "C" int combat_instnorm_bwd(const void* dy1, const void* dy2, const void* x, int x_dtype, void* dx, int dtype, int N, int HW,
                                    int C, float slope, int act, const float* mean, const float* invstd, void* stream) {
   COMBAT_ARG(dy1 && x && dx && mean && invstd, 0);
@@ -768,6 +966,20 @@ extern "C" int combat_instnorm_bwd(const void* dy1, const void* dy2, const void*
   DISPATCH_2(x_dtype, dtype, pdl_launch(instnorm_bwd_k<TX, T>, grid, block, 0, (cudaStream_t)stream, 
                                  (const T*)dy1, (const T*)dy2, (const TX*)x, (T*)dx, HW, C, slope, act, mean, invstd);)
   COMBAT_RETURN_LAUNCH("instnorm_bwd");
+}
+
+extern "C" int combat_instnorm_bwd_split(const void* dy1, const void* dy2, const void* x, int x_dtype, void* dx, int dtype, int N,
+                                         int HW, int C, float slope, int act, const float* mean, const float* invstd, float* part,
+                                         int K, void* stream) {
+  COMBAT_ARG(dy1 && x && dx && mean && invstd && part, 0);
+  COMBAT_ARG(N > 0 && HW > 0 && C > 0 && (C % 2) == 0 && K >= 1 && K <= 32, 5);
+  dim3 grid(N, cdiv(C, CR_CPB), K), block(CR_TX, CR_TY);
+  DISPATCH_2(x_dtype, dtype, pdl_launch(instnorm_bwd_part_k<TX, T>, grid, block, 0, (cudaStream_t)stream, (const T*)dy1, (const T*)dy2,
+                                        (const TX*)x, HW, C, K, slope, act, mean, invstd, part);)
+  COMBAT_CHECK_LAUNCH("instnorm_bwd_part");
+  DISPATCH_2(x_dtype, dtype, pdl_launch(instnorm_bwd_apply_k<TX, T>, grid, block, 0, (cudaStream_t)stream, (const T*)dy1,
+                                        (const T*)dy2, (const TX*)x, (T*)dx, HW, C, K, slope, act, mean, invstd, (const float*)part);)
+  COMBAT_RETURN_LAUNCH("instnorm_bwd_apply");
 }
 
 // ------------------------------------------------------------------ bilinear x2 upsample (+ LeakyReLU)

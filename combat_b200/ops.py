@@ -490,6 +490,12 @@ def instnorm_fwd(x, act, skip=None, eps=1e-5, slope=0.2, out_dtype=None):
     N, H, W, Cc = x.shape
     y = torch.empty(x.shape, dtype=out_dtype or x.dtype, device=x.device)
     st = torch.empty((2, N, Cc), dtype=torch.float32, device=x.device)
+    K = lib.combat_instnorm_splits(N, H * W, Cc)
+    if K > 1:   # large planes, few (sample, channel-group) pairs: every plane split over K CTAs (csrc/norm.cu)
+        part = torch.empty((N, K, 2, Cc), dtype=torch.float32, device=x.device)
+        check(lib.combat_instnorm_fwd_split(_p(x), dt_code(x), _p(skip), _p(y), dt_code(y), N, H * W, Cc, eps, slope, int(act),
+                                            _p(st[0]), _p(st[1]), _p(part), K, _s()), "instnorm_fwd_split")
+        return y, st
     check(lib.combat_instnorm_fwd(_p(x), dt_code(x), _p(skip), _p(y), dt_code(y), N, H * W, Cc, eps, slope, int(act),
                                   _p(st[0]), _p(st[1]), _s()), "instnorm_fwd")
     return y, st
@@ -498,6 +504,12 @@ def instnorm_fwd(x, act, skip=None, eps=1e-5, slope=0.2, out_dtype=None):
 def instnorm_bwd(dy1, dy2, x, st, act, slope=0.2):
     N, H, W, Cc = x.shape
     dx = torch.empty_like(dy1)
+    K = lib.combat_instnorm_splits(N, H * W, Cc)
+    if K > 1:
+        part = torch.empty((N, K, 2, Cc), dtype=torch.float32, device=x.device)
+        check(lib.combat_instnorm_bwd_split(_p(dy1), _p(dy2), _p(x), dt_code(x), _p(dx), dt_code(dy1), N, H * W, Cc, slope, int(act),
+                                            _p(st[0]), _p(st[1]), _p(part), K, _s()), "instnorm_bwd_split")
+        return dx
     check(lib.combat_instnorm_bwd(_p(dy1), _p(dy2), _p(x), dt_code(x), _p(dx), dt_code(dy1), N, H * W, Cc, slope, int(act),
                                   _p(st[0]), _p(st[1]), _s()), "instnorm_bwd")
     return dx

@@ -260,6 +260,14 @@ int combat_instnorm_fwd(const void* x, int x_dtype, const void* skip, void* y, i
 /* dy = dy1 (+ dy2); dyh = act ? dy*lrelu'(xhat) : dy; dx = invstd*(dyh - mean(dyh) - xhat*mean(dyh*xhat)) */
 int combat_instnorm_bwd(const void* dy1, const void* dy2, const void* x, int x_dtype, void* dx, int dtype, int N, int HW, int C,
                         float slope, int act, const float* mean, const float* invstd, void* stream);
+/* Large planes (H*W >= 4096 with too few (sample, channel-group) pairs to fill the GPU, e.g. the ImageNet-10 shape): the same
+ * InstanceNorm forward / backward with every plane split over K CTAs (combat_instnorm_splits gives K; 1 = use the calls above).
+ * part: N * K * 2 * C floats of scratch (chunk means / centred sums of squares, merged with Chan's formula; chunk gradient sums). */
+int combat_instnorm_splits(int N, int HW, int C);
+int combat_instnorm_fwd_split(const void* x, int x_dtype, const void* skip, void* y, int dtype, int N, int HW, int C, float eps,
+                              float slope, int act, float* save_mean, float* save_invstd, float* part, int K, void* stream);
+int combat_instnorm_bwd_split(const void* dy1, const void* dy2, const void* x, int x_dtype, void* dx, int dtype, int N, int HW, int C,
+                              float slope, int act, const float* mean, const float* invstd, float* part, int K, void* stream);
 /* t = leaky_relu(bilinear_up2x(x)) (align_corners=False), networks/models.py:274; slope==1 -> no activation */
 int combat_upsample2x_act(const void* x, void* y, int dtype, int N, int H, int W, int C, float slope, void* stream);
 int combat_upsample2x_act_bwd(const void* dy, const void* y, void* dx, int dtype, int N, int H, int W, int C, float slope,

@@ -363,6 +363,39 @@ def test_instancenorm_lrelu(ops, dtype, tol, H):
         assert float((dx.float().permute(0, 3, 1, 2).cpu() - xr.grad).abs().max() / xr.grad.abs().max()) < tol * (4 if H == 2 else 2 if H == 4 else 1)
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 1.5e-2)])
+@pytest.mark.parametrize("N,Cc,H", [(3, 64, 112), (2, 128, 72), (5, 66, 64)])
+def test_instancenorm_lrelu_large_planes_split_path(ops, dtype, tol, N, Cc, H):
+    """[r2] planes of >= 4096 pixels with few (sample, channel-group) pairs (the ImageNet-10 shape) take the split kernels: chunk
+    partials merged with Chan's formula.  Same bars as the single-kernel path; a large mean (+40) checks the centred merge; ragged
+    last chunk (72 * 72 = 5184 rows over K chunks) and a channel count that is not a multiple of 64."""
+    from combat_b200._lib import lib
+    K = lib.combat_instnorm_splits(N, H * H, Cc)
+    assert K > 1, K
+    g = torch.Generator().manual_seed(16 + H)
+    x = torch.randn(N, Cc, H, H, generator=g) * 3 + 40
+    skip = torch.randn(N, Cc, H, H, generator=g)
+    dy = torch.randn(N, Cc, H, H, generator=g)
+    if dtype == torch.bfloat16:
+        x = (x - 40).bfloat16().float()   # bf16 storage cannot carry a large offset; the float32 case does
+        skip, dy = skip.bfloat16().float(), dy.bfloat16().float()
+    for act, use_skip in [(True, False), (False, True)]:
+        xr = x.clone().requires_grad_(True)
+        y = F.instance_norm(xr, eps=1e-5)
+        if act:
+            y = F.leaky_relu(y, 0.2)
+        if use_skip:
+            y = y + skip
+        y.backward(dy)
+        xd = dev(_nhwc(x).to(dtype))
+        yd, st = ops.instnorm_fwd(xd, act, skip=dev(_nhwc(skip).to(dtype)) if use_skip else None)
+        assert rel(yd.float().permute(0, 3, 1, 2), y) < tol
+        assert rel(st[0].view(N, Cc), x.mean(dim=(2, 3))) < 1e-5
+        dx = ops.instnorm_bwd(dev(_nhwc(dy).to(dtype)), None, xd, st, act)
+        assert float((dx.float().permute(0, 3, 1, 2).cpu() - xr.grad).abs().max() / xr.grad.abs().max()) < tol
+    assert lib.combat_instnorm_splits(512, 1024, 64) == 1 and lib.combat_instnorm_splits(512, 16384, 64) == 1
+
+
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-6), (torch.bfloat16, 1e-2)])
 def test_upsample_lrelu(ops, dtype, tol):
     g = torch.Generator().manual_seed(8)
