@@ -379,7 +379,11 @@ def test_instancenorm_lrelu_large_planes_split_path(ops, dtype, tol, N, Cc, H):
     if dtype == torch.bfloat16:
         x = (x - 40).bfloat16().float()   # bf16 storage cannot carry a large offset; the float32 case does
         skip, dy = skip.bfloat16().float(), dy.bfloat16().float()
+    x_all = x
     for act, use_skip in [(True, False), (False, True)]:
+        # with the LeakyReLU the large offset stays out: a value within float32 rounding of the plane mean flips its mask, and
+        # one flipped element moves the max-norm of the gradient by 16 % in torch's own float32 path (measured against float64)
+        x = x_all - 39 if (act and dtype == torch.float32) else x_all
         xr = x.clone().requires_grad_(True)
         y = F.instance_norm(xr, eps=1e-5)
         if act:
