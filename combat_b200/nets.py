@@ -619,11 +619,11 @@ class Classifier(NetBase):
         if fuse and self.fuse_eval and not train and self.fast_small and x_nchw.shape[1] == 3 and x_nchw.shape[3] % 4 == 0:
             return self._forward_eval_fused(x_nchw, save)
         ctx = {"x": x_nchw, "train": train, "blocks": []} if save else None
-        h = self.conv_first_fwd(x_nchw, self.conv1, stats=train and pre)
+        h = self.conv_first_fwd(x_nchw, self.conv1, stats=train)
         h0_nblk = self.last_stats_nblk
         if not pre:
             c0 = h
-            h, st0 = self._bn_fwd(self.bn1, c0, train, True)
+            h, st0 = self._bn_fwd(self.bn1, c0, train, True, stats_nblk=h0_nblk if train else 0)
             if save:
                 ctx["stem"] = (c0, h, st0)
         h_nblk = h0_nblk if (train and pre) else 0  # partial-sum blocks of h left by its producer conv (train mode, tcgen05 path)
@@ -638,15 +638,18 @@ class Classifier(NetBase):
                 if save:
                     ctx["blocks"].append((h, o1, c1, o2, st1, st2))
             else:
-                c1 = self.conv_fwd(h, blk["conv1"])
-                o1, st1 = self._bn_fwd(blk["bn1"], c1, train, True)
-                c2 = self.conv_fwd(o1, blk["conv2"])
+                # [r2] train mode: every conv leaves the BatchNorm statistics of its output in its epilogue (one scratch buffer:
+                # each set of partial sums is finalised by its BatchNorm before the next conv overwrites it)
+                nb = lambda: self.last_stats_nblk if train else 0
+                c1 = self.conv_fwd(h, blk["conv1"], stats=train)
+                o1, st1 = self._bn_fwd(blk["bn1"], c1, train, True, stats_nblk=nb())
                 if "sc" in blk:
-                    cs_ = self.conv_fwd(h, blk["sc"])
-                    s, sts = self._bn_fwd(blk["scbn"], cs_, train, False)
+                    cs_ = self.conv_fwd(h, blk["sc"], stats=train)
+                    s, sts = self._bn_fwd(blk["scbn"], cs_, train, False, stats_nblk=nb())
                 else:
                     cs_, s, sts = None, h, None
-                out, st2 = self._bn_fwd(blk["bn2"], c2, train, True, residual=s)
+                c2 = self.conv_fwd(o1, blk["conv2"], stats=train)
+                out, st2 = self._bn_fwd(blk["bn2"], c2, train, True, residual=s, stats_nblk=nb())
                 if save:
                     ctx["blocks"].append((h, c1, o1, c2, out, cs_, st1, st2, sts))
             h = out
@@ -826,8 +829,12 @@ class Classifier(NetBase):
                 d_c2, dres = self._bn_bwd(blk["bn2"], dh, c2, out, st2, train, True, need_wgrad, want_dres=True)
                 if need_wgrad:
                     self.conv_wgrad(o1, d_c2, blk["conv2"])
-                d_o1 = self.conv_dgrad(d_c2, blk["conv2"], hw_mid)
-                d_c1, _ = self._bn_bwd(blk["bn1"], d_o1, c1, o1, st1, train, True, need_wgrad)
+                if train and self.bnb_ok(blk["conv2"], c1):   # [r2] reduction of bn1's backward in conv2's input-gradient epilogue
+                    g1 = self.conv_dgrad(d_c2, blk["conv2"], hw_mid, bnb=(c1, st1[0], st1[3], st1[1], st1[2]))
+                    d_c1 = self._bn_bwd_tail(blk["bn1"], g1, c1, st1, need_wgrad)
+                else:
+                    d_o1 = self.conv_dgrad(d_c2, blk["conv2"], hw_mid)
+                    d_c1, _ = self._bn_bwd(blk["bn1"], d_o1, c1, o1, st1, train, True, need_wgrad)
                 if need_wgrad:
                     self.conv_wgrad(h_in, d_c1, blk["conv1"])
                 if "sc" in blk:
