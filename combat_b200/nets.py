@@ -532,6 +532,10 @@ class Classifier(NetBase):
         # ResNet ordering conv-bn-relu-conv-bn-add-relu (post-affine residual epilogue); COMBAT_NO_FUSE_RESNET=1 for A/B
         self.fuse_eval = self.use_tc and (pre or not os.environ.get("COMBAT_NO_FUSE_RESNET"))
         self._unit = {}
+        # train-mode fusions of the plain ResNet ordering (statistics in the conv epilogues, bn1's backward sums in conv2's
+        # input-gradient epilogue): written at the very end of round 2 while the GPU pool was draining -- NOT yet run on a GPU,
+        # hence opt-in (COMBAT_FUSE_RESNET_TRAIN=1); the PreAct path has had both since early in the round
+        self.fuse_train_plain = pre or bool(os.environ.get("COMBAT_FUSE_RESNET_TRAIN"))
 
     def eval_affine(self):
         out = torch.empty((2, self.n_bn_ch), dtype=torch.float32, device=self.device)
@@ -619,7 +623,7 @@ class Classifier(NetBase):
         if fuse and self.fuse_eval and not train and self.fast_small and x_nchw.shape[1] == 3 and x_nchw.shape[3] % 4 == 0:
             return self._forward_eval_fused(x_nchw, save)
         ctx = {"x": x_nchw, "train": train, "blocks": []} if save else None
-        h = self.conv_first_fwd(x_nchw, self.conv1, stats=train)
+        h = self.conv_first_fwd(x_nchw, self.conv1, stats=train and self.fuse_train_plain)
         h0_nblk = self.last_stats_nblk
         if not pre:
             c0 = h
@@ -641,14 +645,15 @@ class Classifier(NetBase):
                 # [r2] train mode: every conv leaves the BatchNorm statistics of its output in its epilogue (one scratch buffer:
                 # each set of partial sums is finalised by its BatchNorm before the next conv overwrites it)
                 nb = lambda: self.last_stats_nblk if train else 0
-                c1 = self.conv_fwd(h, blk["conv1"], stats=train)
+                ft = train and self.fuse_train_plain
+                c1 = self.conv_fwd(h, blk["conv1"], stats=ft)
                 o1, st1 = self._bn_fwd(blk["bn1"], c1, train, True, stats_nblk=nb())
                 if "sc" in blk:
-                    cs_ = self.conv_fwd(h, blk["sc"], stats=train)
+                    cs_ = self.conv_fwd(h, blk["sc"], stats=ft)
                     s, sts = self._bn_fwd(blk["scbn"], cs_, train, False, stats_nblk=nb())
                 else:
                     cs_, s, sts = None, h, None
-                c2 = self.conv_fwd(o1, blk["conv2"], stats=train)
+                c2 = self.conv_fwd(o1, blk["conv2"], stats=ft)
                 out, st2 = self._bn_fwd(blk["bn2"], c2, train, True, residual=s, stats_nblk=nb())
                 if save:
                     ctx["blocks"].append((h, c1, o1, c2, out, cs_, st1, st2, sts))
@@ -829,7 +834,7 @@ class Classifier(NetBase):
                 d_c2, dres = self._bn_bwd(blk["bn2"], dh, c2, out, st2, train, True, need_wgrad, want_dres=True)
                 if need_wgrad:
                     self.conv_wgrad(o1, d_c2, blk["conv2"])
-                if train and self.bnb_ok(blk["conv2"], c1):   # [r2] reduction of bn1's backward in conv2's input-gradient epilogue
+                if train and self.fuse_train_plain and self.bnb_ok(blk["conv2"], c1):   # [r2] bn1's backward sums in conv2's dgrad epilogue
                     g1 = self.conv_dgrad(d_c2, blk["conv2"], hw_mid, bnb=(c1, st1[0], st1[3], st1[1], st1[2]))
                     d_c1 = self._bn_bwd_tail(blk["bn1"], g1, c1, st1, need_wgrad)
                 else:
