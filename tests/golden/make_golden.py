@@ -519,8 +519,16 @@ def gen_api():
     }
     sds = {k: {n: list(v.shape) for n, v in m.state_dict().items()} for k, m in mods.items()}
     nparams = {k: sum(p.numel() for p in m.parameters()) for k, m in mods.items()}
+    # positional signatures of the top-level functions of every reference script that has a mirror (parsed, not imported)
+    import ast
+    sigs = {}
+    for script in ("train_generator", "train_generator_multilabel", "train_generator_imperceptible", "train_generator_inputaware",
+                   "train_generator_wanet", "train_victim", "train_victim_multilabel", "train_victim_imperceptible",
+                   "train_victim_inputaware", "train_victim_wanet", "train_clean_classifier", "eval"):
+        tree = ast.parse(open(os.path.join("/root/reference", script + ".py")).read())
+        sigs[script] = {n.name: [a.arg for a in n.args.args] for n in tree.body if isinstance(n, ast.FunctionDef)}
     with open(os.path.join(HERE, "api.json"), "w") as f:
-        json.dump({"flags": flags, "state_dicts": sds, "n_params": nparams}, f, indent=0, sort_keys=True)
+        json.dump({"flags": flags, "state_dicts": sds, "n_params": nparams, "signatures": sigs}, f, indent=0, sort_keys=True)
     print("wrote api.json")
 
 

@@ -80,6 +80,30 @@ def test_parameter_names_and_shapes_match_reference(key, ctor):
         assert bufs == set(ref) - set(ref_params)
 
 
+@pytest.mark.parametrize("script", ["train_generator", "train_generator_multilabel", "train_generator_imperceptible",
+                                    "train_generator_inputaware", "train_generator_wanet", "train_victim", "train_victim_multilabel",
+                                    "train_victim_imperceptible", "train_victim_inputaware", "train_victim_wanet",
+                                    "train_clean_classifier", "eval"])
+def test_mirror_signatures_match_the_reference_scripts(script):
+    """Every reference script with a mirror: get_model / train / eval / main (and the helpers a caller may import) exist under
+    the same names and take the reference's positional parameters, in order (tests/golden/api.json holds the signatures parsed
+    from the unmodified reference); mirrors may only APPEND optional parameters (e.g. main(argv=None))."""
+    import importlib
+    import inspect
+    ref = json.load(open(os.path.join(GOLDEN, "api.json")))["signatures"][script]
+    mod = importlib.import_module("combat_b200." + script)
+    helpers = {"ViT", "vit_small", "create_inputs_bd", "create_inputs_bd_from_noise", "create_dir"}   # classifier zoo (out of
+    #            scope) / inlined into the engine / os.makedirs
+    for name, args in ref.items():
+        if name in helpers:
+            continue
+        assert hasattr(mod, name), (script, name)
+        prm = list(inspect.signature(getattr(mod, name)).parameters.values())
+        mine = [p.name for p in prm]
+        assert mine[:len(args)] == args, (script, name, mine, args)
+        assert all(p.default is not inspect.Parameter.empty for p in prm[len(args):]), (script, name, mine)
+
+
 def test_plan_matches_oracle_selection():
     """host-side poison selection / RNG order (engine.make_plan) == oracle.select_poison on the same seeds"""
     import numpy as np

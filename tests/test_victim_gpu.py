@@ -142,3 +142,23 @@ def test_inputaware_victim_eval_vs_oracle_and_public_main(tmp_path, capsys):
     best = tvi.main(args)
     out = capsys.readouterr().out
     assert "Cross Acc" in out and len(best) == 3
+
+
+def test_clean_classifier_main_writes_the_checkpoint_the_generator_trainer_loads(tmp_path, capsys):
+    """train_clean_classifier.main() (reference :163-236): train + eval on synthetic data, checkpoint at
+    <checkpoints>/<prefix>/<dataset>/<dataset>_<prefix>.pth.tar -- the path train_generator.main() resolves from
+    --load_checkpoint_clean (:513-527) -- then the generator trainer's main() starts from it."""
+    import os
+    from combat_b200 import train_clean_classifier as tc
+    from combat_b200 import train_generator as tg
+    _seed(0)
+    best = tc.main(["--synthetic_data", "--debug", "--bs", "32", "--n_iters", "1", "--log_every", "4", "--saving_prefix", "cc",
+                    "--checkpoints", str(tmp_path)])
+    out = capsys.readouterr().out
+    path = tmp_path / "cc" / "cifar10" / "cifar10_cc.pth.tar"
+    assert "Clean Acc" in out and " Saving..." in out and os.path.exists(path) and best >= 0.0
+    ck = torch.load(str(path), map_location="cpu", weights_only=False)
+    assert {"netC", "optimizerC", "schedulerC", "best_clean_acc", "epoch_current"} == set(ck)
+    bests = tg.main(["--synthetic_data", "--debug", "--bs", "32", "--n_iters", "1", "--log_every", "4", "--saving_prefix", "g",
+                     "--checkpoints", str(tmp_path), "--load_checkpoint_clean", "cc", "--post_transform_option", "no_use"])
+    assert len(bests) == 6 and "Clean Model Acc" in capsys.readouterr().out
