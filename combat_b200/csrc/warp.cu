@@ -333,12 +333,6 @@ __device__ __forceinline__ float ld(const float* __restrict__ p) {
   return STAGED ? *p : __ldg(p);
 }
 
-template <bool STAGED>
-__device__ __forceinline__ float tap4(const float* __restrict__ pl, int x, int y, int H, int W) {
-  if (x < 0 || x >= W || y < 0 || y >= H) return 0.f;
-  return STAGED ? pl[y * W + x] : __ldg(pl + y * W + x);
-}
-
 // STAGED: the 3 x H x W source image is copied into shared memory with coalesced 16-byte loads, all in flight at once (one HBM
 // latency per image instead of one per channel and tap round), and the gather reads it from there.
 // PIPE (every row is warped, no permutation: the G-step / evaluation batch): the staged image and the flow of image n + 1 are
