@@ -239,3 +239,27 @@ def test_padded_conditional_generator_keeps_the_reference_shapes(monkeypatch):
     assert g.store.shapes == ref.store.shapes
     assert tuple(g.store.p("conv0_1.weight").shape) == (64, 72, 3, 3)
     assert g.store.numel - ref.store.numel == 64 * 9 * (128 - 72)
+
+
+def test_instancenorm_split_policy_and_merge_formula():
+    """Host side of the large-plane InstanceNorm (csrc/norm.cu): the split policy exported by the library (no GPU needed), and a
+    numpy model of the merge the second kernel performs -- chunk (mean, centred sum of squares) partials combined with Chan's
+    formula give the two-pass centred variance of the whole plane, ragged last chunk included."""
+    import numpy as np
+
+    from combat_b200._lib import lib
+    f = lib.combat_instnorm_splits
+    assert f(512, 1024, 64) == 1 and f(512, 256, 128) == 1          # CIFAR shapes: enough (sample, channel-group) pairs
+    assert f(256, 4096, 64) == 3 and f(512, 16384, 64) == 1          # CelebA-size planes at batch 256: 256 CTAs -> 3 chunks
+    k = f(64, 112 * 112, 64)
+    assert 2 <= k <= 32 and (112 * 112) // k >= 256                  # ImageNet-10 shape, batch 64
+    assert f(2, 72 * 72, 128) == 20                                  # capped by the 256-row minimum per chunk
+    rng = np.random.default_rng(0)
+    for HW, K in ((12544, 32), (5184, 20), (4096, 3)):
+        x = rng.normal(40.0, 3.0, size=HW)
+        rows = (HW + K - 1) // K
+        parts = [(x[j * rows:(j + 1) * rows].mean(), ((x[j * rows:(j + 1) * rows] - x[j * rows:(j + 1) * rows].mean()) ** 2).sum(),
+                  len(x[j * rows:(j + 1) * rows])) for j in range(K) if j * rows < HW]
+        mean = sum(c * m for m, _, c in parts) / HW
+        m2 = sum(q + c * (m - mean) ** 2 for m, q, c in parts)
+        assert abs(mean - x.mean()) < 1e-12 and abs(m2 / HW - x.var()) < 1e-10 * x.var()
