@@ -7,9 +7,8 @@ the per-plane scipy DCT loops (:195-197, :242-246) become ONE launch of the uint
 backward, Adadelta) runs on the CUDA kernels of nets.FrequencyDetector.  Checker: oracle/detector_oracle.py, pinned to the
 unmodified reference (tests/golden/detector_b8x2.npz).
 
-STATUS: written at the close of round 1 after the GPU budget was spent -- the DCT launch is GPU-validated
-(tests/test_z_detector_dct_gpu.py), the training iteration has NOT yet run on a GPU (tests/test_detector_train_gpu.py is gated
-behind COMBAT_DETECTOR_TRAIN=1 until it has).
+STATUS: GPU-validated in round 2 -- the DCT launch (tests/test_z_detector_dct_gpu.py) and the training iteration / evaluation
+against the fixture of the unmodified reference (tests/test_detector_train_gpu.py, un-gated).
 """
 from __future__ import annotations
 

@@ -869,6 +869,23 @@ def eval_batch(state: dict, x: torch.Tensor, y: torch.Tensor, opt, x2: torch.Ten
     return out
 
 
+def detector_test_batch(netF_p, netF_b, netG_p, x: torch.Tensor, opt) -> dict:
+    """One iteration of defenses/frequency_based/test.py:76-103: trigger on every image (one blur sigma per batch), uint8 DCT of
+    [clean ; poisoned] (the per-plane scipy `dct2` the script defines at :19-20 -- its loop calls the torch dct_2d on a numpy plane
+    and raises as shipped), detector logits, accuracy against labels [0 ; 1] and detection rate on the poisoned half."""
+    am = lambda t: torch.argmax(t, dim=1)
+    with torch.no_grad():
+        bs = x.shape[0]
+        sigma = draw_sigma(*opt.sigma)
+        poi_x, _, _ = make_bd(netG_p, x, opt, sigma)
+        both = torch.cat([x, poi_x])
+        coef = dct_2d(((both + 1) / 2 * 255).byte())
+        preds = frequency_model_forward(netF_p, netF_b, coef)
+        labels = torch.cat([torch.zeros(bs, dtype=torch.long), torch.ones(bs, dtype=torch.long)])
+    return dict(sigma=sigma, poi_x=poi_x, coef=coef, preds=preds, correct=int((am(preds) == labels).sum()),
+                detected=int((am(preds[bs:]) == 1).sum()))
+
+
 def victim_train_step(netC_p, netC_b, netG_p, momC: dict, x: torch.Tensor, y: torch.Tensor, poisoned, opt) -> dict:
     """One iteration of train_victim.py:110-140 (poisoned given: per-sample bool flags from the dataset) or of
     train_clean_classifier.py:88-104 (poisoned None, netG_p None).  `(poisoned is False).nonzero()` at train_victim.py:121 raises
