@@ -123,10 +123,30 @@ def _bind_adadelta_state(optimizerC, netC):
         state["step"] = state.get("step", torch.zeros((), dtype=torch.float32)) + 0
 
 
+def _adopt_adadelta_state(optimizerC, netC):
+    """`optimizerC.load_state_dict(ckpt)` (train.py:318, --continue_training) leaves fresh copies of square_avg / acc_delta in
+    optimizer.state; the fused Adadelta reads the flat store.  Copy any accumulator that does not alias the store into it, so that a
+    resumed run continues with the saved accumulators instead of zeros."""
+    st = netC.net.store
+    for name, p in netC._plist:
+        state = optimizerC.state.get(p, {})
+        sq, ad = state.get("square_avg"), state.get("acc_delta")
+        if sq is None or ad is None:
+            continue
+        if not hasattr(st, "acc_delta"):
+            st.acc_delta = torch.zeros_like(st.flat)
+        v_sq, v_ad = st._view(st.mom, name), st._view(st.acc_delta, name)
+        if sq.data_ptr() != v_sq.data_ptr():
+            v_sq.copy_(sq.to(v_sq.device, torch.float32))
+        if ad.data_ptr() != v_ad.data_ptr():
+            v_ad.copy_(ad.to(v_ad.device, torch.float32))
+
+
 def train(netC, optimizerC, train_dl, tf_writer, epoch, opt, augment=None):
     """train.py:178-221"""
     print(" Train:")
     netC.train()
+    _adopt_adadelta_state(optimizerC, netC)
     dev = torch.device(opt.device)
     group = optimizerC.param_groups[0]
     lr_dev = torch.full((1,), float(group["lr"]), dtype=torch.float32, device=dev)
@@ -172,3 +192,99 @@ def eval(netC, optimizerC, test_dl, best_acc, tf_writer, epoch, opt, augment=Non
         torch.save({"netC": netC.state_dict(), "optimizerC": optimizerC.state_dict(), "best_acc": acc, "epoch_current": epoch},
                    opt.ckpt_path)
     return best_acc
+
+
+class _NullWriter:
+    def add_scalars(self, *a, **k):
+        pass
+
+    def add_scalar(self, *a, **k):
+        pass
+
+
+class SyntheticUnitBatches:
+    """--synthetic_data: batches of uniform [0, 1] images (the range defenses/frequency_based/dataloader.py yields: ToTensor
+    without normalisation) with random labels -- there is no network here for torchvision's download=True."""
+
+    def __init__(self, opt, train, n_batches=None, seed=0):
+        g = torch.Generator().manual_seed(seed + (0 if train else 1))
+        if n_batches is None:
+            n_batches = (4 if train else 2) if getattr(opt, "debug", False) else (16 if train else 4)
+        self.batches = [(torch.rand(opt.bs, opt.input_channel, opt.input_height, opt.input_width, generator=g),
+                         torch.randint(0, opt.num_classes, (opt.bs,), generator=g)) for _ in range(n_batches)]
+
+    def __len__(self):
+        return len(self.batches)
+
+    def __iter__(self):
+        return iter(self.batches)
+
+
+def get_dataloader(opt, train=True, shuffle=True):
+    """defenses/frequency_based/dataloader.py:103-122: CIFAR-10 / CelebA through torchvision, images in [0, 1] (ToTensor only,
+    :12-28; CelebA resized to the input size).  GTSRB / MNIST (1 or 3 channels at 32 x 32 from local files) are not built."""
+    if getattr(opt, "synthetic_data", False):
+        return SyntheticUnitBatches(opt, train)
+    import torchvision
+    import torchvision.transforms as T
+    tf = T.Compose([T.Resize((opt.input_height, opt.input_width)), T.ToTensor()])
+    if opt.dataset == "cifar10":
+        ds = torchvision.datasets.CIFAR10(opt.data_root, train, transform=tf, download=True)
+    elif opt.dataset == "celeba":
+        from ...utils.dataloader import CelebA_attr
+        ds = CelebA_attr(opt, "train" if train else "test", tf)
+    else:
+        raise NotImplementedError("dataset %s is outside the built path" % opt.dataset)
+    return torch.utils.data.DataLoader(ds, batch_size=opt.bs, num_workers=opt.num_workers, shuffle=shuffle)
+
+
+def main(argv=None, augment=None):
+    """train.py:275-344: dataset shape, loaders (images in [0, 1]), get_model, --continue_training, n_iters epochs of train() +
+    eval(); checkpoint `<checkpoints>/<dataset>/<model>/<dataset>_<model>_detector.pth.tar` -- the file train_generator.py's main()
+    loads as the frequency detector (F_ckpt_path)."""
+    import shutil
+
+    from . import config
+    opt = config.get_arguments().parse_args(argv)
+    sizes = {"cifar10": (32, 3, 10), "celeba": (64, 3, 8)}
+    if opt.dataset in ("gtsrb", "mnist"):
+        raise NotImplementedError("dataset %s is outside the built path (local GTSRB / MNIST files)" % opt.dataset)
+    if opt.dataset not in sizes:
+        raise Exception("Invalid Dataset")
+    opt.input_height = opt.input_width = sizes[opt.dataset][0]
+    opt.input_channel, opt.num_classes = sizes[opt.dataset][1], sizes[opt.dataset][2]
+    train_dl, test_dl = get_dataloader(opt, True), get_dataloader(opt, False)
+    netC, optimizerC = get_model(opt)
+    opt.ckpt_folder = os.path.join(opt.checkpoints, opt.dataset, opt.model)
+    opt.ckpt_path = os.path.join(opt.ckpt_folder, "{}_{}_detector.pth.tar".format(opt.dataset, opt.model))
+    opt.log_dir = os.path.join(opt.ckpt_folder, "log_dir")
+    os.makedirs(opt.log_dir, exist_ok=True)
+    best_acc, epoch_current = 0.0, 0
+    if opt.continue_training:
+        if not os.path.exists(opt.ckpt_path):
+            print("Pretrained model doesnt exist")
+            raise SystemExit
+        print("Continue training!!")
+        sd = torch.load(opt.ckpt_path, map_location=opt.device, weights_only=False)
+        netC.load_state_dict(sd["netC"])
+        optimizerC.load_state_dict(sd["optimizerC"])
+        best_acc, epoch_current = sd["best_acc"], sd["epoch_current"]
+    else:
+        print("Train from scratch!!!")
+        shutil.rmtree(opt.ckpt_folder, ignore_errors=True)
+        os.makedirs(opt.log_dir, exist_ok=True)
+    try:
+        from torch.utils.tensorboard import SummaryWriter
+        tf_writer = SummaryWriter(log_dir=opt.log_dir)
+    except Exception:
+        tf_writer = _NullWriter()
+    augment = augment or AlbumentationsAugment()
+    for epoch in range(epoch_current, opt.n_iters):
+        print("Epoch {}:".format(epoch + 1))
+        train(netC, optimizerC, train_dl, tf_writer, epoch, opt, augment)
+        best_acc = eval(netC, optimizerC, test_dl, best_acc, tf_writer, epoch, opt, augment)
+    return best_acc
+
+
+if __name__ == "__main__":
+    main()

@@ -95,3 +95,31 @@ def test_two_training_iterations_vs_oracle_and_reference_fixture(golden):
     coef, y = T.make_batch(xs[2], opt, False, StandInAugment())
     assert rel(coef, fx["eval_x_final"]) < 5e-6
     assert rel(netC(coef), fx["eval_preds"]) < 5e-4
+
+
+def test_detector_trainer_main_on_synthetic_data(tmp_path, capsys):
+    """train.py:275-344 through the mirror's main(): two epochs of train() + eval() on synthetic [0, 1] images, the detector
+    checkpoint at the path train_generator.py's main() loads (F_ckpt_path), then --continue_training from it."""
+    import os
+    from combat_b200.defenses.frequency_based import train as ftrain
+    args = ["--device", "cuda", "--synthetic_data", "--debug", "--bs", "16", "--n_iters", "2", "--checkpoints", str(tmp_path)]
+    random.seed(0); np.random.seed(0); torch.manual_seed(0)
+    best = ftrain.main(args, augment=StandInAugment())
+    out = capsys.readouterr().out
+    path = tmp_path / "cifar10" / "original" / "cifar10_original_detector.pth.tar"
+    assert "CE Loss" in out and "Acc:" in out and os.path.exists(path) and 0.0 <= best <= 100.0
+    ck = torch.load(str(path), map_location="cpu", weights_only=False)
+    assert {"netC", "optimizerC", "best_acc", "epoch_current"} == set(ck) and "linear6.weight" in ck["netC"]
+    ftrain.main(args + ["--continue_training", "--n_iters", "3"], augment=StandInAugment())
+    assert "Continue training!!" in capsys.readouterr().out
+    # the fused Adadelta adopts the accumulators a checkpoint restores into the torch optimiser's state
+    opt = types.SimpleNamespace(device="cuda", model="original", input_channel=3, input_height=32)
+    netC, optC = ftrain.get_model(opt)
+    optC.load_state_dict(ck["optimizerC"])
+    ftrain._adopt_adadelta_state(optC, netC)
+    st = netC.net.store
+    name, p0 = netC._plist[0]
+    saved = ck["optimizerC"]["state"][0]
+    assert float(saved["square_avg"].abs().sum()) > 0
+    assert torch.allclose(st._view(st.mom, name).cpu(), saved["square_avg"].cpu().float())
+    assert torch.allclose(st._view(st.acc_delta, name).cpu(), saved["acc_delta"].cpu().float())
