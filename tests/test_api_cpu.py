@@ -263,3 +263,19 @@ def test_instancenorm_split_policy_and_merge_formula():
         mean = sum(c * m for m, _, c in parts) / HW
         m2 = sum(q + c * (m - mean) ** 2 for m, q, c in parts)
         assert abs(mean - x.mean()) < 1e-12 and abs(m2 / HW - x.var()) < 1e-10 * x.var()
+
+
+def test_utils_helpers_keep_the_reference_signatures(capsys):
+    """utils/utils.py names the reference scripts import (`from utils.utils import progress_bar`)."""
+    import inspect
+
+    from combat_b200.utils import utils as U
+    assert list(inspect.signature(U.progress_bar).parameters) == ["current", "total", "msg"]
+    for i in range(3):
+        U.progress_bar(i, 3, "Clean Acc: 1.0")
+    out = capsys.readouterr().out
+    assert out.endswith("3/3 \n") and out.count("\r") == 2 and "Clean Acc" in out
+    assert U.format_time(0.0) == "0ms" and U.format_time(3.25) == "3s250ms" and U.format_time(3661) == "1h1m"
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3), torch.nn.BatchNorm2d(4), torch.nn.Flatten(), torch.nn.Linear(4, 2))
+    U.init_params(net)
+    assert float(net[1].weight.min()) == 1.0 and float(net[3].weight.abs().max()) < 1e-2
