@@ -279,3 +279,16 @@ def test_utils_helpers_keep_the_reference_signatures(capsys):
     net = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3), torch.nn.BatchNorm2d(4), torch.nn.Flatten(), torch.nn.Linear(4, 2))
     U.init_params(net)
     assert float(net[1].weight.min()) == 1.0 and float(net[3].weight.abs().max()) < 1e-2
+
+
+def test_inference_loader_yields_indices():
+    """utils/dataloader_infer.py: (input, target, index) items; the synthetic batches carry the running sample index."""
+    import types
+
+    from combat_b200.utils import dataloader_infer as DI
+    ds = DI.PoisonedDataset([(torch.zeros(3, 4, 4), 1), (torch.ones(3, 4, 4), 2)], 10, None)
+    assert len(ds) == 2 and ds[1][1] == 2 and ds[1][2] == 1
+    opt = types.SimpleNamespace(synthetic_data=True, debug=True, bs=8, input_channel=3, input_height=32, input_width=32, num_classes=10)
+    dl = DI.get_dataloader(opt, train=False)
+    x, y, idx = next(iter(dl))
+    assert tuple(x.shape) == (8, 3, 32, 32) and idx.tolist() == list(range(8)) and len(dl) == 2
