@@ -292,3 +292,34 @@ def test_inference_loader_yields_indices():
     dl = DI.get_dataloader(opt, train=False)
     x, y, idx = next(iter(dl))
     assert tuple(x.shape) == (8, 3, 32, 32) and idx.tolist() == list(range(8)) and len(dl) == 2
+
+
+def test_parameter_block_layout_and_victim_plans_for_the_variants():
+    """Host logic of the per-iteration parameter block (engine.AlternatedStep._plan_layout): every section 16-byte aligned, the
+    PostTensorTransform section sized for five slots (six for the input-aware step), views that tile the block without overlap;
+    make_plan_victim draws a blur sigma only for the additive trigger (the WaNet victim step draws nothing)."""
+    import numpy as np
+
+    from combat_b200.engine import TF_SLOT, AlternatedStep, default_opt, make_plan_victim
+    from combat_b200.utils.dataloader import PARAM_WIDTH
+    for B, ml, tf_on, n_tf in ((512, False, True, 5), (32, False, True, 6), (30, True, False, 5), (7, False, False, 5)):
+        lay, nbytes = AlternatedStep._plan_layout(B, ml, tf_on, n_tf)
+        spans = sorted((o, o + n) for o, n in lay.values() if n)
+        assert all(o % 16 == 0 for o, _ in spans) and all(a[1] <= b[0] for a, b in zip(spans, spans[1:])) and spans[-1][1] <= nbytes
+        assert lay["tf"][1] == (n_tf * B * PARAM_WIDTH * 4 if tf_on else 0) and lay["taps_rows"][1] == (8 * B if ml else 0)
+        v = AlternatedStep._plan_views(torch.zeros(nbytes, dtype=torch.uint8), lay, B, n_tf)
+        assert v["perm"].numel() == B and v["small"].numel() == 8 and (v["tf"] is None) == (not tf_on)
+        if tf_on:
+            assert tuple(v["tf"].shape) == (n_tf, B, PARAM_WIDTH)
+    assert TF_SLOT["T6"] == 5 and sorted(TF_SLOT.values()) == list(range(6))
+    y = np.array([0, 3, 0, 5, 0, 7])
+    flags = np.array([True, False, True, False, False, False])
+    for variant, draws in (("", True), ("wanet", False)):
+        opt = default_opt(variant=variant)
+        torch.manual_seed(4)
+        tail = float(torch.rand(1)) if not draws else None
+        torch.manual_seed(4)
+        plan = make_plan_victim(y, flags, opt)
+        assert plan.num_bd == 2 and list(plan.perm) == [0, 2, 1, 3, 4, 5] and (plan.sigma_c is not None) == draws
+        if not draws:
+            assert float(torch.rand(1)) == tail     # the torch stream was not touched
